@@ -1,0 +1,128 @@
+"""ctypes declarations for the C ABI in include/gvpm_b200.h and loaders for the in-tree libraries.
+
+The product library (libgvpm_b200.so, built from gvpm_b200/csrc by nvcc for sm_100a) has no CPU
+fallback: loading fails loudly when the file is missing, and gvpm_ctx_create fails when there is
+no CUDA device.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvpm_b200.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "synth", "libgvpm_synth.so")
+
+GVPM_OUT_FLOATS = 27
+PARENT_EMITTER, PARENT_SURFACE, PARENT_MEDIUM, PARENT_OTHER = 0, 1, 2, 3
+PHASE_ISOTROPIC, PHASE_HG = 0, 1
+SURF2MEDIA, MEDIA2MEDIA = 1 << 2, 1 << 4
+ALL2MEDIA = SURF2MEDIA | MEDIA2MEDIA
+
+f32p = C.POINTER(C.c_float)
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class Medium(C.Structure):
+    _fields_ = [("sigma_s", C.c_float * 3), ("sigma_a", C.c_float * 3), ("phase_type", C.c_int32),
+                ("hg_g", C.c_float), ("sampling_weight", C.c_float)]
+
+
+class Config(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("min_depth", C.c_int32), ("lighting_mode", C.c_int32),
+                ("use_mis", C.c_int32), ("use_shift_null", C.c_int32), ("path_set", C.c_int32),
+                ("power_heuristic", C.c_int32), ("kernel_3d", C.c_int32), ("film_w", C.c_int32),
+                ("film_h", C.c_int32), ("shadow_maxt_scale", C.c_float), ("epsilon", C.c_float),
+                ("reserved", C.c_int32 * 4)]
+
+
+class PhotonSoA(C.Structure):
+    _fields_ = [("pos", f32p), ("flux", f32p), ("parent_pos", f32p), ("pred_pos", f32p),
+                ("parent_n", f32p), ("prefix_flux", f32p), ("parent_albedo", f32p),
+                ("parent_pdf", f32p), ("edge_pdf", f32p), ("rr_weight", f32p),
+                ("parent_type", u8p), ("depth", u8p), ("path_id", u32p)]
+
+
+class RaySoA(C.Structure):
+    _fields_ = [("o", f32p), ("d", f32p), ("mint", f32p), ("maxt", f32p), ("edge_len", f32p),
+                ("eye_contrib", f32p), ("xi", f32p), ("px", i32p), ("py", i32p), ("edge_id", i32p),
+                ("off_valid", u8p), ("off_o", f32p), ("off_d", f32p), ("off_len", f32p),
+                ("off_eye", f32p), ("off_sensor", f32p)]
+
+
+# every symbol include/gvpm_b200.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = [
+    "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
+    "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
+    "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points",
+    "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre",
+    "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_dump_neighbours_bre",
+    "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_launch_count",
+]
+
+_lib = None
+_synth = None
+
+
+def load_lib():
+    """Load the product library.  Raises if it was not built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  gvpm_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gvpm_abi_version.restype = C.c_int
+    lib.gvpm_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.gvpm_ctx_destroy.argtypes = [vp]
+    lib.gvpm_last_error.argtypes = [vp]
+    lib.gvpm_last_error.restype = C.c_char_p
+    lib.gvpm_sync.argtypes = [vp]
+    lib.gvpm_stream.argtypes = [vp]
+    lib.gvpm_stream.restype = vp
+    lib.gvpm_set_medium.argtypes = [vp, C.POINTER(Medium)]
+    lib.gvpm_set_config.argtypes = [vp, C.POINTER(Config)]
+    lib.gvpm_set_occluders.argtypes = [vp, f32p, C.c_size_t]
+    lib.gvpm_upload_photons.argtypes = [vp, C.POINTER(PhotonSoA), C.c_size_t]
+    lib.gvpm_photon_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.gvpm_build_points.argtypes = [vp, C.c_float]
+    lib.gvpm_upload_rays.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t]
+    lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.gvpm_commit_rays.argtypes = [vp]
+    lib.gvpm_gather_bre.argtypes = [vp, f32p, u32p]
+    lib.gvpm_gather_bre_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.gvpm_gather_bre_into.argtypes = [vp, vp, vp]
+    lib.gvpm_dump_neighbours_bre.argtypes = [vp, u64p, u32p, C.c_size_t]
+    lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
+    lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]
+    lib.gvpm_launch_count.argtypes = [vp]
+    lib.gvpm_launch_count.restype = C.c_uint64
+    for name in ABI_SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("gvpm_abi_version",):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def load_synth():
+    global _synth
+    if _synth is not None:
+        return _synth
+    if not os.path.exists(SYNTH_LIB_PATH):
+        raise RuntimeError(f"{SYNTH_LIB_PATH} is missing: run __graft_entry__.build()")
+    s = C.CDLL(SYNTH_LIB_PATH)
+    s.gvpm_synth_photons.argtypes = [C.c_uint64, C.c_size_t, C.POINTER(Medium), C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_int, C.POINTER(PhotonSoA)]
+    s.gvpm_synth_photons.restype = C.c_longlong
+    s.gvpm_synth_occluders.argtypes = [f32p]
+    s.gvpm_synth_occluders.restype = C.c_size_t
+    s.gvpm_synth_rays.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_float, C.c_float, C.POINTER(RaySoA)]
+    s.gvpm_synth_rays.restype = C.c_size_t
+    _synth = s
+    return s

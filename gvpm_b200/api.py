@@ -1,0 +1,153 @@
+"""Thin Python handle on the C ABI (include/gvpm_b200.h).  Every method is one C call; errors raise.
+
+This is the call a host integrator makes per iteration:
+    ctx.set_medium / set_config / set_occluders           once per scene
+    ctx.upload_photons(photons); ctx.build_points(r)      replaces gvpm.cpp:453 + gvpm_accel.cpp:10-55
+    ctx.upload_rays(rays)                                 the gather points of the iteration
+    out, counts = ctx.gather_bre()                        replaces gvpm.cpp:999-1052
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class GvpmError(RuntimeError):
+    pass
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = N.load_lib()
+        h = C.c_void_p()
+        rc = self.lib.gvpm_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise GvpmError(f"gvpm_ctx_create({device}) failed ({rc}): "
+                            f"{self.lib.gvpm_last_error(None).decode()}")
+        self.h = h
+        self.n_rays = 0
+        self.n_photons = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gvpm_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise GvpmError(f"{what} failed ({rc}): {self.lib.gvpm_last_error(self.h).decode()}")
+
+    # ---- scene constants
+    def set_medium(self, medium):
+        self._ck(self.lib.gvpm_set_medium(self.h, C.byref(medium)), "gvpm_set_medium")
+
+    def set_config(self, config):
+        self._ck(self.lib.gvpm_set_config(self.h, C.byref(config)), "gvpm_set_config")
+
+    def set_occluders(self, tri):
+        tri = np.ascontiguousarray(tri, dtype=np.float32).reshape(-1)
+        self._ck(self.lib.gvpm_set_occluders(self.h, tri.ctypes.data_as(N.f32p), tri.size // 9),
+                 "gvpm_set_occluders")
+
+    # ---- photons
+    def upload_photons(self, photons):
+        cs = photons.as_c()
+        self._ck(self.lib.gvpm_upload_photons(self.h, C.byref(cs), photons.n), "gvpm_upload_photons")
+        self.n_photons = photons.n
+
+    def photon_staging(self, n):
+        dev, nbytes = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.gvpm_photon_staging(self.h, n, C.byref(dev), C.byref(nbytes)), "gvpm_photon_staging")
+        self.n_photons = n
+        return dev.value, nbytes.value
+
+    def build_points(self, radius):
+        self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
+
+    # ---- rays
+    def upload_rays(self, rays):
+        cs = rays.as_c()
+        self._ck(self.lib.gvpm_upload_rays(self.h, C.byref(cs), rays.n), "gvpm_upload_rays")
+        self.n_rays = rays.n
+
+    def ray_staging(self, n):
+        dev, nbytes = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.gvpm_ray_staging(self.h, n, C.byref(dev), C.byref(nbytes)), "gvpm_ray_staging")
+        self.n_rays = n
+        return dev.value, nbytes.value
+
+    def commit_rays(self):
+        self._ck(self.lib.gvpm_commit_rays(self.h), "gvpm_commit_rays")
+
+    # ---- gathers
+    def gather_bre(self, out=None, counts=True):
+        """-> (out [n_rays,27] float32, counts [n_rays,2] uint32 or None), on the host."""
+        n = self.n_rays
+        if out is None:
+            out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
+        self._ck(self.lib.gvpm_gather_bre(self.h, out.ctypes.data_as(N.f32p),
+                                          cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_bre")
+        return out.reshape(n, N.GVPM_OUT_FLOATS), (cnt.reshape(n, 2) if counts else None)
+
+    def gather_bre_device(self):
+        """Launch only; returns device pointers (out, counts) owned by the context."""
+        o, c = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.gvpm_gather_bre_device(self.h, C.byref(o), C.byref(c)), "gvpm_gather_bre_device")
+        return o.value, c.value
+
+    def gather_bre_into(self, out_dev_ptr, counts_dev_ptr=None):
+        self._ck(self.lib.gvpm_gather_bre_into(self.h, C.c_void_p(out_dev_ptr),
+                                               C.c_void_p(counts_dev_ptr) if counts_dev_ptr else None),
+                 "gvpm_gather_bre_into")
+
+    def dump_neighbours_bre(self):
+        """-> (offsets [n_rays+1] uint64, idx uint32 with bit 31 = contributes), per-ray sorted."""
+        n = self.n_rays
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        rc = self.lib.gvpm_dump_neighbours_bre(self.h, offsets.ctypes.data_as(N.u64p), None, 0)
+        total = int(offsets[n])
+        if rc != 0 and total == 0:
+            self._ck(rc, "gvpm_dump_neighbours_bre")
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            self._ck(self.lib.gvpm_dump_neighbours_bre(self.h, offsets.ctypes.data_as(N.u64p),
+                                                       idx.ctypes.data_as(N.u32p), total),
+                     "gvpm_dump_neighbours_bre")
+        idx = idx[:total]
+        # traversal order -> ascending photon index inside every ray's segment
+        if total:
+            seg = np.repeat(np.arange(n, dtype=np.uint64), np.diff(offsets).astype(np.int64))
+            order = np.lexsort((idx & np.uint32(0x7FFFFFFF), seg))
+            idx = idx[order]
+        return offsets, idx
+
+    def compute_gradient(self, acc, w, h, use_abs=False):
+        acc = np.ascontiguousarray(acc, dtype=np.float32).reshape(-1)
+        assert acc.size == w * h * N.GVPM_OUT_FLOATS
+        thr, gx, gy = (np.empty(w * h * 3, dtype=np.float32) for _ in range(3))
+        self._ck(self.lib.gvpm_compute_gradient(self.h, acc.ctypes.data_as(N.f32p), w, h, int(use_abs),
+                                                thr.ctypes.data_as(N.f32p), gx.ctypes.data_as(N.f32p),
+                                                gy.ctypes.data_as(N.f32p)), "gvpm_compute_gradient")
+        return thr.reshape(h, w, 3), gx.reshape(h, w, 3), gy.reshape(h, w, 3)
+
+    def sync(self):
+        self._ck(self.lib.gvpm_sync(self.h), "gvpm_sync")
+
+    def stream(self):
+        return self.lib.gvpm_stream(self.h)
+
+    def last_timings(self):
+        b, g = C.c_float(), C.c_float()
+        self._ck(self.lib.gvpm_last_timings(self.h, C.byref(b), C.byref(g)), "gvpm_last_timings")
+        return b.value, g.value
+
+    def launch_count(self):
+        return int(self.lib.gvpm_launch_count(self.h))

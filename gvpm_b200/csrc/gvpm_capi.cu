@@ -1,0 +1,571 @@
+// gvpm_capi.cu — the extern "C" boundary of include/gvpm_b200.h: context, grow-only device
+// buffers, uploads, build and gather launches.  No torch types, no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gvpm_device.cuh"
+
+namespace gvpm {
+size_t sort_temp_bytes(uint32_t n);
+cudaError_t run_sort(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
+                     uint32_t *vout, uint32_t n, cudaStream_t st);
+int bounds_blocks(uint32_t n);
+void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st);
+void launch_morton(const float *pos, uint32_t n, const float *bounds, uint64_t *keys, uint32_t *vals,
+                   cudaStream_t st);
+void launch_pack_sorted(const PhotonStaging &S, const uint32_t *sorted, uint32_t n, float4 *planes,
+                        uint32_t *orig, cudaStream_t st);
+void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
+                       cudaStream_t st);
+void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, uint32_t nParent, float4 *plo,
+                        float4 *phi, cudaStream_t st);
+void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st);
+cudaError_t launch_gather_bre(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
+void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
+                     cudaStream_t st);
+}  // namespace gvpm
+
+using namespace gvpm;
+
+namespace {
+
+struct DevBuf {  // grow-only device allocation
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return (T *)p; }
+};
+
+std::string g_create_error;
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct gvpm_ctx {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  uint64_t launches = 0;
+
+  gvpm_medium medium{};
+  bool have_medium = false;
+  gvpm_config cfg{};
+  bool have_cfg = false;
+
+  DevBuf tri, tri_plane;
+  uint32_t n_tri = 0;
+
+  DevBuf ph_staging;
+  uint32_t n_photons = 0;
+  bool photons_loaded = false;
+  DevBuf keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
+  Tree tree{};
+  float radius = 0.f;
+  bool built = false;
+
+  DevBuf ray_staging, rays;
+  uint32_t n_rays = 0;
+  bool rays_loaded = false;
+
+  DevBuf out, counts, nbr_offsets, nbr_idx, work_counter;
+  DevBuf grad_in, grad_out;
+  float build_ms = 0.f, gather_ms = 0.f;
+  bool timed_build = false, timed_gather = false;
+};
+
+namespace {
+
+int fail(gvpm_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, GVPM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+// offsets of the raw photon SoA arrays inside the staging buffer
+struct PhotonLayout {
+  size_t off[13];
+  size_t bytes;
+  explicit PhotonLayout(size_t n) {
+    const size_t sz[13] = {12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 4 * n, 4 * n, 4 * n, n, n, 4 * n};
+    size_t o = 0;
+    for (int i = 0; i < 13; ++i) { off[i] = o; o += align256(sz[i]); }
+    bytes = o;
+  }
+};
+PhotonStaging photon_staging_ptrs(const void *base, size_t n) {
+  PhotonLayout L(n);
+  const char *b = (const char *)base;
+  PhotonStaging S;
+  S.pos = (const float *)(b + L.off[0]);
+  S.flux = (const float *)(b + L.off[1]);
+  S.parent_pos = (const float *)(b + L.off[2]);
+  S.pred_pos = (const float *)(b + L.off[3]);
+  S.parent_n = (const float *)(b + L.off[4]);
+  S.prefix_flux = (const float *)(b + L.off[5]);
+  S.parent_albedo = (const float *)(b + L.off[6]);
+  S.parent_pdf = (const float *)(b + L.off[7]);
+  S.edge_pdf = (const float *)(b + L.off[8]);
+  S.rr_weight = (const float *)(b + L.off[9]);
+  S.parent_type = (const uint8_t *)(b + L.off[10]);
+  S.depth = (const uint8_t *)(b + L.off[11]);
+  S.path_id = (const uint32_t *)(b + L.off[12]);
+  return S;
+}
+struct RayLayout {
+  size_t off[16];
+  size_t bytes;
+  explicit RayLayout(size_t n) {
+    const size_t sz[16] = {12 * n, 12 * n, 4 * n, 4 * n, 4 * n, 12 * n, 4 * n, 4 * n, 4 * n, 4 * n,
+                           4 * n,  48 * n, 48 * n, 16 * n, 48 * n, 16 * n};
+    size_t o = 0;
+    for (int i = 0; i < 16; ++i) { off[i] = o; o += align256(sz[i]); }
+    bytes = o;
+  }
+};
+RayStaging ray_staging_ptrs(const void *base, size_t n) {
+  RayLayout L(n);
+  const char *b = (const char *)base;
+  RayStaging S;
+  S.o = (const float *)(b + L.off[0]);
+  S.d = (const float *)(b + L.off[1]);
+  S.mint = (const float *)(b + L.off[2]);
+  S.maxt = (const float *)(b + L.off[3]);
+  S.edge_len = (const float *)(b + L.off[4]);
+  S.eye_contrib = (const float *)(b + L.off[5]);
+  S.xi = (const float *)(b + L.off[6]);
+  S.px = (const int32_t *)(b + L.off[7]);
+  S.py = (const int32_t *)(b + L.off[8]);
+  S.edge_id = (const int32_t *)(b + L.off[9]);
+  S.off_valid = (const uint8_t *)(b + L.off[10]);
+  S.off_o = (const float *)(b + L.off[11]);
+  S.off_d = (const float *)(b + L.off[12]);
+  S.off_len = (const float *)(b + L.off[13]);
+  S.off_eye = (const float *)(b + L.off[14]);
+  S.off_sensor = (const float *)(b + L.off[15]);
+  return S;
+}
+
+int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts_dev) {
+  if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
+  if (!ctx->built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points has not been called");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
+  memset(&P, 0, sizeof(P));
+  P.tree = ctx->tree;
+  P.planes = ctx->planes.as<float4>();
+  P.orig = ctx->orig.as<uint32_t>();
+  P.rays = ctx->rays.as<float4>();
+  P.n_rays = ctx->n_rays;
+  const float r = ctx->radius;
+  P.radius = r;
+  P.radius_sq = r * r;
+  // Float kernelVol = (4.0/3.0)*M_PI*pow(r,3) evaluated in double (shift_volume_photon.cpp:707)
+  if (ctx->cfg.kernel_3d)
+    P.kernel_vol = (float)((4.0 / 3.0) * (double)GVPM_PI * std::pow((double)r, 3));
+  else
+    P.kernel_vol = (float)((double)GVPM_PI * std::pow((double)r, 2));
+  P.bounds = ctx->bounds.as<float>();
+  for (int i = 0; i < 3; ++i) {
+    P.sigma_s[i] = ctx->medium.sigma_s[i];
+    P.sigma_t[i] = ctx->medium.sigma_s[i] + ctx->medium.sigma_a[i];
+  }
+  P.phase_type = ctx->medium.phase_type;
+  P.hg_g = ctx->medium.hg_g;
+  P.sampling_weight = ctx->medium.sampling_weight;
+  P.cfg = ctx->cfg;
+  P.tri = ctx->tri.as<float>();
+  P.tri_plane = ctx->tri_plane.as<float4>();
+  P.n_tri = ctx->n_tri;
+  P.out = out_dev;
+  P.counts = counts_dev;
+  P.work_counter = ctx->work_counter.as<uint32_t>();
+  return GVPM_OK;
+}
+
+int gather_common(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
+  GatherParams P;
+  int rc = fill_params(ctx, P, out_dev, counts_dev);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(launch_gather_bre(P, false, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  return GVPM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvpm_abi_version(void) { return GVPM_ABI_VERSION; }
+
+int gvpm_ctx_create(int device, gvpm_ctx **out) {
+  if (!out) return GVPM_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                     " (gvpm_b200 has no CPU fallback)";
+    return GVPM_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return GVPM_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return GVPM_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library is built for sm_100a only";
+    return GVPM_ERR_NO_DEVICE;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GVPM_ERR_CUDA; }
+  gvpm_ctx *ctx = new gvpm_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return GVPM_ERR_CUDA;
+  }
+  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  ctx->work_counter.reserve(256);
+  ctx->bounds.reserve(256);
+  ctx->bounds_partial.reserve(1024 * 6 * sizeof(float));
+  *out = ctx;
+  return GVPM_OK;
+}
+
+int gvpm_ctx_destroy(gvpm_ctx *ctx) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
+                    &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
+                    &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
+                    &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GVPM_OK;
+}
+
+const char *gvpm_last_error(const gvpm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gvpm_sync(gvpm_ctx *ctx) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+void *gvpm_stream(gvpm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int gvpm_set_medium(gvpm_ctx *ctx, const gvpm_medium *m) {
+  if (!ctx || !m) return GVPM_ERR_INVALID;
+  const float st0 = m->sigma_s[0] + m->sigma_a[0];
+  for (int i = 1; i < 3; ++i)
+    if (m->sigma_s[i] + m->sigma_a[i] != st0)
+      // the reference aborts the same way: homogeneous.cpp:188-201
+      return fail(ctx, GVPM_ERR_UNSUPPORTED, "sigma_t must be equal across channels (balance strategy)");
+  if (m->phase_type != GVPM_PHASE_ISOTROPIC && m->phase_type != GVPM_PHASE_HG)
+    return fail(ctx, GVPM_ERR_UNSUPPORTED, "phase function must be isotropic or hg");
+  ctx->medium = *m;
+  ctx->have_medium = true;
+  return GVPM_OK;
+}
+
+int gvpm_set_config(gvpm_ctx *ctx, const gvpm_config *c) {
+  if (!ctx || !c) return GVPM_ERR_INVALID;
+  if (c->use_shift_null && !c->kernel_3d)
+    // gvpm_struct.h:305-308: "Not possible to shift null without using 3D kernel"
+    return fail(ctx, GVPM_ERR_UNSUPPORTED, "useShiftNull requires the 3D kernel");
+  ctx->cfg = *c;
+  ctx->have_cfg = true;
+  return GVPM_OK;
+}
+
+int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz, size_t n_tri) {
+  if (!ctx || (n_tri && !tri_xyz)) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ctx->n_tri = (uint32_t)n_tri;
+  if (n_tri == 0) return GVPM_OK;
+  std::vector<float> planes(4 * n_tri);
+  for (size_t t = 0; t < n_tri; ++t) {
+    const float *p = tri_xyz + 9 * t;
+    double e1[3], e2[3], n[3];
+    for (int a = 0; a < 3; ++a) { e1[a] = (double)p[3 + a] - p[a]; e2[a] = (double)p[6 + a] - p[a]; }
+    n[0] = e1[1] * e2[2] - e1[2] * e2[1];
+    n[1] = e1[2] * e2[0] - e1[0] * e2[2];
+    n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (len > 0) {
+      for (int a = 0; a < 3; ++a) n[a] /= len;
+      planes[4 * t] = (float)n[0]; planes[4 * t + 1] = (float)n[1]; planes[4 * t + 2] = (float)n[2];
+      planes[4 * t + 3] = (float)(-(n[0] * p[0] + n[1] * p[1] + n[2] * p[2]));
+    } else {
+      planes[4 * t] = planes[4 * t + 1] = planes[4 * t + 2] = planes[4 * t + 3] = 0.f;  // never culled
+    }
+  }
+  CK(ctx->tri.reserve(9 * n_tri * sizeof(float)));
+  CK(ctx->tri_plane.reserve(4 * n_tri * sizeof(float)));
+  CK(cudaMemcpyAsync(ctx->tri.p, tri_xyz, 9 * n_tri * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tri_plane.p, planes.data(), 4 * n_tri * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
+  if (!ctx || n > 0xfffffff0u) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  PhotonLayout L(n);
+  CK(ctx->ph_staging.reserve(L.bytes ? L.bytes : 256));
+  ctx->n_photons = (uint32_t)n;
+  ctx->photons_loaded = true;
+  ctx->built = false;
+  if (dev) *dev = ctx->ph_staging.p;
+  if (bytes) *bytes = L.bytes;
+  return GVPM_OK;
+}
+
+int gvpm_upload_photons(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n) {
+  if (!ctx || (n && !p)) return GVPM_ERR_INVALID;
+  int rc = gvpm_photon_staging(ctx, n, nullptr, nullptr);
+  if (rc) return rc;
+  if (n == 0) return GVPM_OK;
+  PhotonLayout L(n);
+  char *b = (char *)ctx->ph_staging.p;
+  const void *src[13] = {p->pos, p->flux, p->parent_pos, p->pred_pos, p->parent_n, p->prefix_flux, p->parent_albedo,
+                         p->parent_pdf, p->edge_pdf, p->rr_weight, p->parent_type, p->depth, p->path_id};
+  const size_t sz[13] = {12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 4 * n, 4 * n, 4 * n, n, n, 4 * n};
+  for (int i = 0; i < 13; ++i) {
+    if (!src[i]) return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_photon_soa");
+    CK(cudaMemcpyAsync(b + L.off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return GVPM_OK;
+}
+
+int gvpm_build_points(gvpm_ctx *ctx, float radius) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (!ctx->photons_loaded) return fail(ctx, GVPM_ERR_INVALID, "no photons uploaded");
+  if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->n_photons;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  Tree T{};
+  T.n = n;
+  // level sizes
+  uint32_t cnt = (n + 31) / 32, total = 0;
+  int levels = 0;
+  if (n > 0) {
+    for (;;) {
+      T.cnt[levels] = cnt;
+      T.off[levels] = total;
+      total += cnt;
+      ++levels;
+      if (cnt <= 32) break;
+      if (levels >= GVPM_MAX_LEVELS) return fail(ctx, GVPM_ERR_INVALID, "too many photons");
+      cnt = (cnt + 31) / 32;
+    }
+  }
+  T.levels = levels;
+  if (n > 0) {
+    CK(ctx->keys_in.reserve(8 * (size_t)n));
+    CK(ctx->keys_out.reserve(8 * (size_t)n));
+    CK(ctx->vals_in.reserve(4 * (size_t)n));
+    CK(ctx->vals_out.reserve(4 * (size_t)n));
+    const size_t tb = sort_temp_bytes(n);
+    CK(ctx->sort_temp.reserve(tb));
+    CK(ctx->planes.reserve(GVPM_PHOTON_PLANES * 16 * (size_t)n));
+    CK(ctx->orig.reserve(4 * (size_t)n));
+    CK(ctx->box_lo.reserve(16 * (size_t)total));
+    CK(ctx->box_hi.reserve(16 * (size_t)total));
+    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    launch_bounds(S.pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st);
+    launch_morton(S.pos, n, ctx->bounds.as<float>(), ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), st);
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+                ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
+    launch_pack_sorted(S, ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(), ctx->orig.as<uint32_t>(), st);
+    float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
+    launch_leaf_boxes(ctx->planes.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
+    for (int l = 1; l < levels; ++l)
+      launch_level_boxes(lo + T.off[l - 1], hi + T.off[l - 1], T.cnt[l - 1], T.cnt[l], lo + T.off[l], hi + T.off[l], st);
+    ctx->launches += 5 + (levels - 1) + 4;  // + the radix sort's own passes (library, ~4 launches)
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemsetAsync(ctx->bounds.p, 0, 7 * sizeof(float), st));
+  }
+  T.lo = ctx->box_lo.as<float4>();
+  T.hi = ctx->box_hi.as<float4>();
+  ctx->tree = T;
+  ctx->radius = radius;
+  ctx->built = true;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->timed_build = true;
+  return GVPM_OK;
+}
+
+int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
+  if (!ctx || n > 0xfffffff0u) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  RayLayout L(n);
+  CK(ctx->ray_staging.reserve(L.bytes ? L.bytes : 256));
+  ctx->n_rays = (uint32_t)n;
+  ctx->rays_loaded = false;
+  if (dev) *dev = ctx->ray_staging.p;
+  if (bytes) *bytes = L.bytes;
+  return GVPM_OK;
+}
+
+int gvpm_commit_rays(gvpm_ctx *ctx) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->n_rays;
+  CK(ctx->rays.reserve((size_t)n * GVPM_RAY_FLOAT4 * 16 + 256));
+  CK(ctx->out.reserve((size_t)n * GVPM_OUT_FLOATS * 4 + 256));
+  CK(ctx->counts.reserve((size_t)n * 8 + 256));
+  if (n > 0) {
+    launch_pack_rays(ray_staging_ptrs(ctx->ray_staging.p, n), n, ctx->rays.as<float4>(), ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+  }
+  ctx->rays_loaded = true;
+  return GVPM_OK;
+}
+
+int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n) {
+  if (!ctx || (n && !r)) return GVPM_ERR_INVALID;
+  int rc = gvpm_ray_staging(ctx, n, nullptr, nullptr);
+  if (rc) return rc;
+  if (n > 0) {
+    RayLayout L(n);
+    char *b = (char *)ctx->ray_staging.p;
+    const void *src[16] = {r->o, r->d, r->mint, r->maxt, r->edge_len, r->eye_contrib, r->xi, r->px, r->py,
+                           r->edge_id, r->off_valid, r->off_o, r->off_d, r->off_len, r->off_eye, r->off_sensor};
+    const size_t sz[16] = {12 * n, 12 * n, 4 * n, 4 * n, 4 * n, 12 * n, 4 * n, 4 * n, 4 * n, 4 * n,
+                           4 * n,  48 * n, 48 * n, 16 * n, 48 * n, 16 * n};
+    for (int i = 0; i < 16; ++i) {
+      if (!src[i]) return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_ray_soa");
+      CK(cudaMemcpyAsync(b + L.off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  return gvpm_commit_rays(ctx);
+}
+
+int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
+  if (!ctx || !out_dev) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return gather_common(ctx, out_dev, counts_dev);
+}
+
+int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  if (rc) return rc;
+  if (out_dev) *out_dev = ctx->out.as<float>();
+  if (counts_dev) *counts_dev = ctx->counts.as<uint32_t>();
+  return GVPM_OK;
+}
+
+int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  if (rc) return rc;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts)
+      CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap) {
+  if (!ctx || !offsets) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n_rays;
+  // pass 1: counts
+  {
+    int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+    if (rc) return rc;
+  }
+  std::vector<uint32_t> counts(2 * n + 2);
+  if (n) CK(cudaMemcpyAsync(counts.data(), ctx->counts.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { offsets[i] = total; total += counts[2 * i]; }
+  offsets[n] = total;
+  if (total > cap || (total && !idx)) return fail(ctx, GVPM_ERR_INVALID, "neighbour buffer too small");
+  if (total == 0) return GVPM_OK;
+  CK(ctx->nbr_offsets.reserve((n + 1) * 8));
+  CK(ctx->nbr_idx.reserve(total * 4));
+  CK(cudaMemcpyAsync(ctx->nbr_offsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GatherParams P;
+  int rc = fill_params(ctx, P, ctx->out.as<float>(), nullptr);
+  if (rc) return rc;
+  P.nbr_offsets = ctx->nbr_offsets.as<uint64_t>();
+  P.nbr_idx = ctx->nbr_idx.as<uint32_t>();
+  CK(launch_gather_bre(P, true, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, float *throughput,
+                          float *gx, float *gy) {
+  if (!ctx || !acc || w <= 0 || h <= 0 || !throughput || !gx || !gy) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t np = (size_t)w * h;
+  CK(ctx->grad_in.reserve(np * GVPM_OUT_FLOATS * 4));
+  CK(ctx->grad_out.reserve(np * 9 * 4));
+  CK(cudaMemcpyAsync(ctx->grad_in.p, acc, np * GVPM_OUT_FLOATS * 4, cudaMemcpyHostToDevice, ctx->stream));
+  float *o = ctx->grad_out.as<float>();
+  launch_gradient(ctx->grad_in.as<float>(), w, h, use_abs, o, o + 3 * np, o + 6 * np, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(throughput, o, np * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(gx, o + 3 * np, np * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(gy, o + 6 * np, np * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->timed_build) CK(cudaEventElapsedTime(&ctx->build_ms, ctx->ev[0], ctx->ev[1]));
+  if (ctx->timed_gather) CK(cudaEventElapsedTime(&ctx->gather_ms, ctx->ev[2], ctx->ev[3]));
+  if (build_ms) *build_ms = ctx->build_ms;
+  if (gather_ms) *gather_ms = ctx->gather_ms;
+  return GVPM_OK;
+}
+
+uint64_t gvpm_launch_count(const gvpm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

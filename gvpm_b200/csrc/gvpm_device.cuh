@@ -1,0 +1,135 @@
+// gvpm_device.cuh — device-side data layout and arithmetic helpers shared by the kernels.
+//
+// Arithmetic policy: everything that decides WHICH photons a ray gathers or WHICH
+// shift branch is taken (neighbour predicate, kernel-chord sampling, null-shift / mirror tests,
+// reconnection geometry, visibility, side tests) is computed with the explicitly rounded
+// intrinsics (__fadd_rn, __fmul_rn, ...) in the reference's operation order, so nvcc can neither
+// contract them into FMAs nor reassociate them and the index sets are bit-identical to a
+// -ffp-contract=off CPU evaluation.  The wrapper type `sf` makes that readable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gvpm_b200.h"
+
+namespace gvpm {
+
+// ---- strictly rounded float -------------------------------------------------------------
+struct sf {
+  float v;
+  __host__ __device__ sf() : v(0.f) {}
+  __host__ __device__ sf(float x) : v(x) {}
+};
+__device__ __forceinline__ sf operator+(sf a, sf b) { return sf(__fadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sf operator-(sf a, sf b) { return sf(__fsub_rn(a.v, b.v)); }
+__device__ __forceinline__ sf operator*(sf a, sf b) { return sf(__fmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sf operator/(sf a, sf b) { return sf(__fdiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sf operator-(sf a) { return sf(-a.v); }
+__device__ __forceinline__ bool operator<(sf a, sf b) { return a.v < b.v; }
+__device__ __forceinline__ bool operator>(sf a, sf b) { return a.v > b.v; }
+__device__ __forceinline__ bool operator<=(sf a, sf b) { return a.v <= b.v; }
+__device__ __forceinline__ bool operator>=(sf a, sf b) { return a.v >= b.v; }
+__device__ __forceinline__ bool operator==(sf a, sf b) { return a.v == b.v; }
+__device__ __forceinline__ sf ssqrt(sf a) { return sf(__fsqrt_rn(a.v)); }
+__device__ __forceinline__ sf smax(sf a, sf b) { return sf(fmaxf(a.v, b.v)); }
+__device__ __forceinline__ sf safe_sqrt(sf a) { return ssqrt(smax(sf(0.f), a)); }
+
+struct v3 {
+  sf x, y, z;
+  __device__ v3() {}
+  __device__ v3(sf a, sf b, sf c) : x(a), y(b), z(c) {}
+  __device__ v3(float a, float b, float c) : x(a), y(b), z(c) {}
+};
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 operator-(v3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ v3 operator*(v3 a, sf f) { return v3(a.x * f, a.y * f, a.z * f); }
+__device__ __forceinline__ v3 operator*(sf f, v3 a) { return v3(a.x * f, a.y * f, a.z * f); }
+__device__ __forceinline__ v3 operator*(v3 a, v3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+// vector / scalar multiplies by the reciprocal (include/mitsuba/core/vector.h:535-542)
+__device__ __forceinline__ v3 operator/(v3 a, sf f) { sf r = sf(1.f) / f; return v3(a.x * r, a.y * r, a.z * r); }
+__device__ __forceinline__ sf dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ v3 cross(v3 a, v3 b) {
+  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ sf length_sq(v3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ sf length(v3 a) { return ssqrt(length_sq(a)); }
+__device__ __forceinline__ v3 normalize(v3 a) { return a / length(a); }
+__device__ __forceinline__ sf max3(v3 a) { return smax(a.x, smax(a.y, a.z)); }
+
+#define GVPM_INV_PI 0.31830988618379067154f
+#define GVPM_INV_FOURPI 0.07957747154594766788f
+#define GVPM_PI 3.14159265358979323846f
+
+// ---- device record layout -----------------------------------------------------
+// Photons: 7 float4 planes of n entries each, in Morton order after the build.
+//   P0 = pos.xyz,           meta bits   (leaf test touches only this plane)
+//   P1 = flux.xyz,          parent_pdf
+//   P2 = parent_pos.xyz,    edge_pdf
+//   P3 = pred_pos.xyz,      rr_weight
+//   P4 = parent_n.xyz,      -
+//   P5 = prefix_flux.xyz,   -
+//   P6 = parent_albedo.xyz, -
+// meta: bits 0-1 parent type, bits 2-9 depth, bit 10 pathID & 1.
+#define GVPM_PHOTON_PLANES 7
+__host__ __device__ inline uint32_t pack_meta(uint32_t type, uint32_t depth, uint32_t path_id) {
+  return (type & 3u) | ((depth & 255u) << 2) | ((path_id & 1u) << 10);
+}
+
+// Rays: 5 records of 64 B per ray (4 float4 each): base + offsets L,R,T,B.
+//   base: q0 = o.xyz, mint | q1 = d.xyz, maxt | q2 = eye.xyz, edge_len | q3 = xi, px, py, edge_id (bits)
+//   off : q0 = o.xyz, len  | q1 = d.xyz, sensor | q2 = eye.xyz, valid (bits) | q3 = unused
+#define GVPM_RAY_FLOAT4 20
+
+// raw staging layout: element offsets of each SoA array inside one contiguous device buffer
+struct PhotonStaging {
+  const float *pos, *flux, *parent_pos, *pred_pos, *parent_n, *prefix_flux, *parent_albedo;
+  const float *parent_pdf, *edge_pdf, *rr_weight;
+  const uint8_t *parent_type, *depth;
+  const uint32_t *path_id;
+};
+struct RayStaging {
+  const float *o, *d, *mint, *maxt, *edge_len, *eye_contrib, *xi;
+  const int32_t *px, *py, *edge_id;
+  const uint8_t *off_valid;
+  const float *off_o, *off_d, *off_len, *off_eye, *off_sensor;
+};
+
+// implicit 32-ary hierarchy over Morton-sorted photons: level 0 = leaves of 32 photons,
+// level l+1 node j = union of level l nodes [32j, 32j+32).  Boxes already inflated by the radius
+// (+ conservative pad).  lo/hi: float4 arrays holding all levels, level l starts at off[l].
+#define GVPM_MAX_LEVELS 8
+struct Tree {
+  const float4 *lo, *hi;
+  uint32_t off[GVPM_MAX_LEVELS];
+  uint32_t cnt[GVPM_MAX_LEVELS];
+  int levels;       // number of levels; the top level has <= 32 nodes
+  uint32_t n;       // photons
+};
+
+struct GatherParams {
+  Tree tree;
+  const float4 *planes;  // [7][n] sorted
+  const uint32_t *orig;  // [n] original photon index of sorted slot
+  const float4 *rays;    // [n_rays][20]
+  uint32_t n_rays;
+  float radius, radius_sq, kernel_vol;
+  const float *bounds;  // device: photon AABB min[3], max[3], max |coordinate| (cull pad)
+  // medium
+  float sigma_s[3], sigma_t[3];
+  int phase_type;
+  float hg_g, sampling_weight;
+  gvpm_config cfg;
+  const float *tri;  // [n_tri*9]
+  const float4 *tri_plane;  // [n_tri] unit plane (n, d) for the conservative cull
+  uint32_t n_tri;
+  // outputs
+  float *out;        // [n_rays*27]
+  uint32_t *counts;  // [n_rays*2] or null
+  // neighbour dump (parity aid)
+  const uint64_t *nbr_offsets;
+  uint32_t *nbr_idx;
+  uint32_t *work_counter;
+};
+
+}  // namespace gvpm

@@ -1,0 +1,232 @@
+// tree_build.cu — GPU build of the photon-point hierarchy.  Replaces PointKDTree::build
+// (include/mitsuba/core/kdtree.h:326-378,921-1037; single-threaded sliding-midpoint recursion) and
+// GradientBeamRadianceEstimator's constructor + buildHierarchy (gvpm/gvpm_accel.cpp:10-55;
+// single-threaded bottom-up AABB recursion) with: bounds reduction -> 63-bit Morton keys ->
+// radix sort -> gather of the raw SoA into Morton-ordered 128-bit record planes -> bottom-up
+// 32-ary box levels (one warp per node, shuffle reductions).  Every step is a streaming pass.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "gvpm_device.cuh"
+
+namespace gvpm {
+
+// ---- bounds: per-block partial min/max of n points, then one block folds the partials -----
+__global__ void k_bounds_partial(const float *__restrict__ pos, uint32_t n, float *__restrict__ partial) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float v = pos[3 * (size_t)i + a];
+      lo[a] = fminf(lo[a], v);
+      hi[a] = fmaxf(hi[a], v);
+    }
+  }
+  __shared__ float s[6][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if (lane == 0) { s[a][w] = lo[a]; s[3 + a][w] = hi[a]; }
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float l = lane < nw ? s[a][lane] : INFINITY, h = lane < nw ? s[3 + a][lane] : -INFINITY;
+      for (int o = 16; o > 0; o >>= 1) {
+        l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+        h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+      }
+      if (lane == 0) { partial[6 * blockIdx.x + a] = l; partial[6 * blockIdx.x + 3 + a] = h; }
+    }
+  }
+}
+// bounds[0..2] = min, [3..5] = max, [6] = max |coordinate|
+__global__ void k_bounds_final(const float *__restrict__ partial, int nblocks, float *__restrict__ bounds) {
+  const int lane = threadIdx.x;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int b = lane; b < nblocks; b += 32)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], partial[6 * b + a]);
+      hi[a] = fmaxf(hi[a], partial[6 * b + 3 + a]);
+    }
+  float mag = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    mag = fmaxf(mag, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+  }
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) { bounds[a] = lo[a]; bounds[3 + a] = hi[a]; }
+    bounds[6] = mag;
+  }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits -> every third bit
+  uint64_t x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
+}
+
+__global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float *__restrict__ bounds,
+                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t q[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = bounds[a], ext = bounds[3 + a] - lo;
+    float u = ext > 0.f ? (pos[3 * (size_t)i + a] - lo) / ext : 0.f;
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    q[a] = min((uint32_t)(u * 2097152.f), 2097151u);
+  }
+  keys[i] = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+  vals[i] = i;
+}
+
+// gather raw SoA -> Morton-ordered float4 planes
+__global__ void k_pack_sorted(const PhotonStaging S, const uint32_t *__restrict__ sorted, uint32_t n,
+                              float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = sorted[i];
+  const size_t s3 = 3 * (size_t)s;
+  auto ld3 = [&](const float *p, float w) { return make_float4(p[s3], p[s3 + 1], p[s3 + 2], w); };
+  const uint32_t meta = pack_meta(S.parent_type[s], S.depth[s], S.path_id[s]);
+  planes[i] = ld3(S.pos, __uint_as_float(meta));
+  planes[(size_t)n + i] = ld3(S.flux, S.parent_pdf[s]);
+  planes[2 * (size_t)n + i] = ld3(S.parent_pos, S.edge_pdf[s]);
+  planes[3 * (size_t)n + i] = ld3(S.pred_pos, S.rr_weight[s]);
+  planes[4 * (size_t)n + i] = ld3(S.parent_n, 0.f);
+  planes[5 * (size_t)n + i] = ld3(S.prefix_flux, 0.f);
+  planes[6 * (size_t)n + i] = ld3(S.parent_albedo, 0.f);
+  orig[i] = s;
+}
+
+// level 0: one warp per leaf of 32 photons; box = AABB(centres) inflated by the radius.
+// (the reference's per-photon cube [p-r, p+r], gvpm_accel.cpp:38-42, unioned over the leaf)
+__global__ void k_leaf_boxes(const float4 *__restrict__ p0, uint32_t n, uint32_t nLeaves, float radius,
+                             float4 *__restrict__ lo, float4 *__restrict__ hi) {
+  const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (leaf >= nLeaves) return;
+  const uint32_t i = leaf * 32 + lane;
+  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (i < n) {
+    const float4 p = p0[i];
+    l[0] = h[0] = p.x; l[1] = h[1] = p.y; l[2] = h[2] = p.z;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      l[a] = fminf(l[a], __shfl_xor_sync(0xffffffffu, l[a], o));
+      h[a] = fmaxf(h[a], __shfl_xor_sync(0xffffffffu, h[a], o));
+    }
+  if (lane == 0) {
+    lo[leaf] = make_float4(l[0] - radius, l[1] - radius, l[2] - radius, 0.f);
+    hi[leaf] = make_float4(h[0] + radius, h[1] + radius, h[2] + radius, 0.f);
+  }
+}
+
+// level l+1 from level l: one warp per parent node
+__global__ void k_level_boxes(const float4 *__restrict__ clo, const float4 *__restrict__ chi, uint32_t nChild,
+                              uint32_t nParent, float4 *__restrict__ plo, float4 *__restrict__ phi) {
+  const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= nParent) return;
+  const uint32_t i = node * 32 + lane;
+  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (i < nChild) {
+    const float4 a = clo[i], b = chi[i];
+    l[0] = a.x; l[1] = a.y; l[2] = a.z; h[0] = b.x; h[1] = b.y; h[2] = b.z;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      l[a] = fminf(l[a], __shfl_xor_sync(0xffffffffu, l[a], o));
+      h[a] = fmaxf(h[a], __shfl_xor_sync(0xffffffffu, h[a], o));
+    }
+  if (lane == 0) {
+    plo[node] = make_float4(l[0], l[1], l[2], 0.f);
+    phi[node] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+}
+
+// raw ray SoA -> 5 x 64 B records per ray
+__global__ void k_pack_rays(const RayStaging S, uint32_t n, float4 *__restrict__ rays) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 *r = rays + (size_t)i * GVPM_RAY_FLOAT4;
+  const size_t i3 = 3 * (size_t)i;
+  r[0] = make_float4(S.o[i3], S.o[i3 + 1], S.o[i3 + 2], S.mint[i]);
+  r[1] = make_float4(S.d[i3], S.d[i3 + 1], S.d[i3 + 2], S.maxt[i]);
+  r[2] = make_float4(S.eye_contrib[i3], S.eye_contrib[i3 + 1], S.eye_contrib[i3 + 2], S.edge_len[i]);
+  r[3] = make_float4(S.xi[i], __uint_as_float((uint32_t)S.px[i]), __uint_as_float((uint32_t)S.py[i]),
+                     __uint_as_float((uint32_t)S.edge_id[i]));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const size_t j = 4 * (size_t)i + k, j3 = 3 * j;
+    r[4 * (k + 1)] = make_float4(S.off_o[j3], S.off_o[j3 + 1], S.off_o[j3 + 2], S.off_len[j]);
+    r[4 * (k + 1) + 1] = make_float4(S.off_d[j3], S.off_d[j3 + 1], S.off_d[j3 + 2], S.off_sensor[j]);
+    r[4 * (k + 1) + 2] = make_float4(S.off_eye[j3], S.off_eye[j3 + 1], S.off_eye[j3 + 2],
+                                     __uint_as_float(S.off_valid[j] ? 1u : 0u));
+    r[4 * (k + 1) + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ---- host-side drivers ---------------------------------------------------------------------
+size_t sort_temp_bytes(uint32_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 63);
+  return bytes;
+}
+
+cudaError_t run_sort(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
+                     uint32_t *vout, uint32_t n, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 63, st);
+}
+
+int bounds_blocks(uint32_t n) {
+  int b = (int)((n + 255) / 256);
+  return b < 1 ? 1 : (b > 1024 ? 1024 : b);
+}
+
+void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st) {
+  const int nb = bounds_blocks(n);
+  k_bounds_partial<<<nb, 256, 0, st>>>(pos, n, partial);
+  k_bounds_final<<<1, 32, 0, st>>>(partial, nb, bounds);
+}
+void launch_morton(const float *pos, uint32_t n, const float *bounds, uint64_t *keys, uint32_t *vals,
+                   cudaStream_t st) {
+  k_morton<<<(n + 255) / 256, 256, 0, st>>>(pos, n, bounds, keys, vals);
+}
+void launch_pack_sorted(const PhotonStaging &S, const uint32_t *sorted, uint32_t n, float4 *planes,
+                        uint32_t *orig, cudaStream_t st) {
+  k_pack_sorted<<<(n + 255) / 256, 256, 0, st>>>(S, sorted, n, planes, orig);
+}
+void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
+                       cudaStream_t st) {
+  k_leaf_boxes<<<(nLeaves + 7) / 8, 256, 0, st>>>(p0, n, nLeaves, radius, lo, hi);
+}
+void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, uint32_t nParent, float4 *plo,
+                        float4 *phi, cudaStream_t st) {
+  k_level_boxes<<<(nParent + 7) / 8, 256, 0, st>>>(clo, chi, nChild, nParent, plo, phi);
+}
+void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st) {
+  k_pack_rays<<<(n + 255) / 256, 256, 0, st>>>(S, n, rays);
+}
+
+}  // namespace gvpm

@@ -1,0 +1,210 @@
+/* gvpm_b200.h — C ABI of the B200-native density-estimation gather.
+ *
+ * This is the drop-in boundary for ONE path of gradientpm/gvpm: the per-iteration volumetric
+ * gather (primal + 4 offset-path gradient contributions per camera-ray medium segment) that
+ * the `gvpm` / `sppm` integrator plugins run on CPU threads.  The C++ integrator stays host
+ * code; the bodies of the reference's gather drivers become calls into this library.
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * reference root, src/integrators/photonmapper/...).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gvpm_status otherwise; the message is
+ *     available from gvpm_last_error().  No exception crosses this boundary (the reference
+ *     throws from SLog(EError), the host shim re-raises).
+ *   - host arrays are caller-owned and only read during the call; device buffers belong to
+ *     the context and are reused (grow-only) across iterations.
+ *   - Float is fp32 (north-star), Spectrum is 3 floats (SPECTRUM_SAMPLES=3).
+ *   - offsets are ordered {Left(-1,0), Right(+1,0), Top(0,+1), Bottom(0,-1)} as
+ *     generateOffsetPos, gvpm/shift/shift_utilities.h:255-261 / EPixel gvpm_struct.h:354-359.
+ *   - there is no CPU fallback: without a CUDA device gvpm_ctx_create fails.
+ */
+#ifndef GVPM_B200_H
+#define GVPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVPM_ABI_VERSION 1
+
+typedef struct gvpm_ctx gvpm_ctx; /* opaque, one per device, externally synchronised */
+
+enum gvpm_status {
+  GVPM_OK = 0,
+  GVPM_ERR_INVALID = -1,  /* bad argument / call order */
+  GVPM_ERR_CUDA = -2,     /* CUDA runtime error (text in gvpm_last_error) */
+  GVPM_ERR_NO_DEVICE = -3,/* no sm_100 device: the product path has no CPU fallback */
+  GVPM_ERR_UNSUPPORTED = -4
+};
+
+/* Parent-vertex type of a photon / beam (PathVertex::EVertexType of vertex c-1 on the light
+ * path; gvpm/shift/operation/shift_diffuse.cpp:18-88).  GVPM_PARENT_OTHER marks a glossy or
+ * specular surface parent: the reference routes those to the manifold shift
+ * (shift_utilities.h:112-136), which is out of scope; the gather treats it as the reference
+ * does with useManifold=false (shift fails, weight 1). */
+enum gvpm_parent_type {
+  GVPM_PARENT_EMITTER = 0,
+  GVPM_PARENT_SURFACE = 1,
+  GVPM_PARENT_MEDIUM = 2,
+  GVPM_PARENT_OTHER = 3
+};
+
+enum gvpm_phase_type { GVPM_PHASE_ISOTROPIC = 0, GVPM_PHASE_HG = 1 };
+
+/* ELightingEffects bits, src/integrators/volume_utils.h:95-103 */
+enum gvpm_lighting_mode {
+  GVPM_SURF2MEDIA = 1 << 2,
+  GVPM_MEDIA2MEDIA = 1 << 4,
+  GVPM_ALL2MEDIA = (1 << 2) | (1 << 4)
+};
+
+/* Homogeneous medium + phase function: src/medium/homogeneous.cpp:432-513 (balance strategy,
+ * equal sigma_t across channels is required by the reference, :188-201), phase/isotropic.cpp:76,
+ * phase/hg.cpp:107-110. */
+typedef struct gvpm_medium {
+  float sigma_s[3];
+  float sigma_a[3];
+  int32_t phase_type;      /* gvpm_phase_type */
+  float hg_g;
+  float sampling_weight;   /* mediumSamplingWeight; 1 for volume-only renders (gvpm.cpp:135-141) */
+} gvpm_medium;
+
+/* The subset of GPMConfig (gvpm/gvpm_struct.h:106-333) the gather reads. */
+typedef struct gvpm_config {
+  int32_t max_depth;        /* maxDepth (-1/0 = unbounded; test is maxDepth > 0) */
+  int32_t min_depth;        /* minDepth */
+  int32_t lighting_mode;    /* lightingInteractionMode bits (gvpm_lighting_mode) */
+  int32_t use_mis;          /* useMIS == "area" */
+  int32_t use_shift_null;   /* useShiftNull (mixed shift / spatial relaxation) */
+  int32_t path_set;         /* pathSet checkerboard (shift_volume_photon.cpp:689-697) */
+  int32_t power_heuristic;  /* powerHeuristic */
+  int32_t kernel_3d;        /* 1: bre3d (default "bre"), 0: bre2d */
+  int32_t film_w, film_h;   /* film size, for the right/top border rule (:843-846) */
+  float shadow_maxt_scale;  /* the reference passes maxt = lProj*ShadowEpsilon (=1e-3f) to the
+                               reconnection shadow ray, shift_volume_photon.cpp:396; kept as a
+                               parameter so the quirk is visible.  Default 1e-3f. */
+  float epsilon;            /* Epsilon (include/mitsuba/core/constants.h:24-30, 1e-4f in single
+                               precision): mint of the offset rays and of the shadow ray */
+  int32_t reserved[4];
+} gvpm_config;
+
+/* Volume photons, flattened from GPhotonNodeData + its light Path
+ * (gvpm/gvpm_accel.h:17-65,119-199).  c = vertexId of the photon on its light path. */
+typedef struct gvpm_photon_soa {
+  const float *pos;           /* [n*3] vertex(c).position */
+  const float *flux;          /* [n*3] running importance weight (gvpm_accel.h:134-148) */
+  const float *parent_pos;    /* [n*3] vertex(c-1).position; wi = normalize(parent - pos) */
+  const float *pred_pos;      /* [n*3] vertex(c-2).position, or (1,1,1) when c < 3
+                                        (shift_volume_photon.cpp:431) */
+  const float *parent_n;      /* [n*3] geometric normal of a surface / emitter parent */
+  const float *prefix_flux;   /* [n*3] prod_{i<c-1} weight*rr*edgeWeight (:415-422) */
+  const float *parent_albedo; /* [n*3] diffuse reflectance of a surface parent */
+  const float *parent_pdf;    /* [n] vertex(c-1).pdf[EImportance], area measure */
+  const float *edge_pdf;      /* [n] edge(c-1).pdf[EImportance] */
+  const float *rr_weight;     /* [n] vertex(c-1).rrWeight */
+  const uint8_t *parent_type; /* [n] gvpm_parent_type */
+  const uint8_t *depth;       /* [n] c-1 = number of preceding interactions */
+  const uint32_t *path_id;    /* [n] GPhotonNodeData::pathID */
+} gvpm_photon_soa;
+
+/* Camera-ray medium segments with their four offset segments: what
+ * computeVolumeGradientPhotonBRE builds per (gather point, medium edge), gvpm.cpp:1008-1042,
+ * plus the per-offset data ShiftGatherPoint caches (shift_cameraPath.h:29-140,
+ * gvpm_struct.h:585-631). */
+typedef struct gvpm_ray_soa {
+  const float *o;           /* [n*3] vertex(e).position */
+  const float *d;           /* [n*3] unit direction */
+  const float *mint;        /* [n]   Epsilon */
+  const float *maxt;        /* [n]   beamDist - Epsilon */
+  const float *edge_len;    /* [n]   edge(e).length */
+  const float *eye_contrib; /* [n*3] getWeightBeam(e-1)*getWeightVertex(e) */
+  const float *xi;          /* [n]   the sampler->next1D() of gvpm.cpp:1042 */
+  const int32_t *px;        /* [n]   int(samplePosition.x) */
+  const int32_t *py;        /* [n] */
+  const int32_t *edge_id;   /* [n]   e (currEdge) */
+  const uint8_t *off_valid; /* [n*4] validVolumeEdge(e, medium) */
+  const float *off_o;       /* [n*4*3] */
+  const float *off_d;       /* [n*4*3] -edge_k(e).d */
+  const float *off_len;     /* [n*4]   edge_k(e).length */
+  const float *off_eye;     /* [n*4*3] eyeShiftContrib */
+  const float *off_sensor;  /* [n*4]   sensorMIS(e, base, .,.) */
+} gvpm_ray_soa;
+
+/* Occluder triangles for the reconnection shadow ray (scene->rayIntersect,
+ * shift_volume_photon.cpp:396-402), tested as Triangle::rayIntersect
+ * (include/mitsuba/core/triangle.h:109-145). */
+
+/* Floats per ray in the gather output: mediumFlux[3], shiftedMediumFlux[4][3],
+ * weightedMediumFlux[4][3] (AbstractVolumeGradientRecord, shift_volume_photon.h:17-20). */
+#define GVPM_OUT_FLOATS 27
+
+/* ---- context ------------------------------------------------------------------------- */
+int gvpm_abi_version(void);
+int gvpm_ctx_create(int device, gvpm_ctx **out);
+int gvpm_ctx_destroy(gvpm_ctx *ctx);
+const char *gvpm_last_error(const gvpm_ctx *ctx); /* ctx may be NULL: last create error */
+int gvpm_sync(gvpm_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void *gvpm_stream(gvpm_ctx *ctx);
+
+/* ---- scene constants ----------------------------------------------------------------- */
+int gvpm_set_medium(gvpm_ctx *ctx, const gvpm_medium *m);
+int gvpm_set_config(gvpm_ctx *ctx, const gvpm_config *c);
+int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz /* [n_tri*9] */, size_t n_tri);
+
+/* ---- photon points: replaces GPhotonMap::tryAppend/build (gvpm_accel.h:119-203,
+ *      include/mitsuba/core/kdtree.h:326-378) and the GradientBeamRadianceEstimator
+ *      constructor + buildHierarchy (gvpm_accel.cpp:10-55) ---------------------------------- */
+int gvpm_upload_photons(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n);
+/* Device-resident variant for multi-GPU: returns the context's raw staging buffer sized for n
+ * photons (the 13 SoA arrays back to back, each 256-byte aligned, in the field order of
+ * gvpm_photon_soa).  Rank 0 fills it with gvpm_upload_photons, the host broadcasts `bytes`
+ * bytes at `dev` over NCCL, and every rank then calls gvpm_build_points. */
+int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes);
+/* Morton sort + implicit 32-ary AABB hierarchy for search radius `radius`
+ * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
+int gvpm_build_points(gvpm_ctx *ctx, float radius);
+
+/* ---- camera rays --------------------------------------------------------------------- */
+int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n);
+/* same idea for rays: staging buffer (16 SoA arrays, 256-byte aligned, field order of
+ * gvpm_ray_soa) to be filled on the device, then gvpm_commit_rays packs it. */
+int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes);
+int gvpm_commit_rays(gvpm_ctx *ctx);
+
+/* ---- gathers: replace bre->query(ray, medium, gRec, xi) over all gather points,
+ *      gvpm.cpp:999-1052 + gvpm_accel.h:268-312 + shift_volume_photon.cpp:658-856 ------------ */
+/* out: [n_rays*27] host floats (un-normalised: the caller divides by nbPathVolume and folds
+ * into the APA running mean, gvpm.cpp:1054-1069).  counts (may be NULL): [n_rays*2] =
+ * {geometric neighbours, contributing neighbours} per ray. */
+int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts);
+/* same, results left on the device (pointers owned by the context, valid until the next call) */
+int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev);
+/* same, written to caller-provided device memory (e.g. a peer-mapped / NCCL buffer) */
+int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
+
+/* Parity aid: neighbour index sets in CSR form.  offsets: [n_rays+1]; idx: capacity `cap`
+ * entries, original photon index with bit 31 set when the photon also passes the depth /
+ * interaction-mode / pathSet filters.  Returns GVPM_ERR_INVALID when cap is too small
+ * (offsets[n_rays] then holds the needed size). */
+int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
+
+/* ---- hand-off: computeGradient (gvpm.cpp:1205-1306) on the 27-float planes -------------
+ * acc: device or host? -> host [h*w*27] APA-averaged accumulators in pixel order;
+ * writes throughput, gx, gy [h*w*3] (interleaved RGB, row-major; poisson hand-off layout
+ * gvpm.cpp:560-578).  use_abs as the reference's useAbs flag. */
+int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs,
+                          float *throughput, float *gx, float *gy);
+
+/* ---- timing of the last build / gather on the context's stream (CUDA events, ms) ----- */
+int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms);
+/* number of kernel launches issued by this context since creation */
+uint64_t gvpm_launch_count(const gvpm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVPM_B200_H */

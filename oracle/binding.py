@@ -1,0 +1,108 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE — see oracle/gvpm_oracle.hpp).
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  The product package gvpm_b200 never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gvpm_b200 import _native as N
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvpm_oracle.so")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.gvpm_oracle_hw_threads.restype = C.c_int
+    lib.gvpm_oracle_tree_build.argtypes = [C.POINTER(N.PhotonSoA), C.c_size_t, C.c_float, C.c_int]
+    lib.gvpm_oracle_tree_build.restype = vp
+    lib.gvpm_oracle_tree_build_ms.argtypes = [vp]
+    lib.gvpm_oracle_tree_build_ms.restype = C.c_double
+    lib.gvpm_oracle_tree_depth.argtypes = [vp]
+    lib.gvpm_oracle_tree_depth.restype = C.c_size_t
+    lib.gvpm_oracle_tree_free.argtypes = [vp]
+    lib.gvpm_oracle_bre.argtypes = [vp, C.POINTER(N.PhotonSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                    C.c_size_t, C.POINTER(N.Medium), C.POINTER(N.Config), N.f32p, C.c_size_t,
+                                    C.c_float, C.c_int, C.c_int, N.f32p, N.u32p, N.u64p, N.u32p, C.c_size_t,
+                                    C.POINTER(C.c_double)]
+    lib.gvpm_oracle_bre.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def hw_threads():
+    return load().gvpm_oracle_hw_threads()
+
+
+class BreResult:
+    def __init__(self, out, counts, offsets, idx, gather_ms, build_ms):
+        self.out, self.counts, self.offsets, self.idx = out, counts, offsets, idx
+        self.gather_ms, self.build_ms = gather_ms, build_ms
+
+    def neighbours(self, i):
+        """(sorted original photon indices of the geometric set, contributes-mask)"""
+        a = self.idx[self.offsets[i]:self.offsets[i + 1]]
+        return a & np.uint32(0x7FFFFFFF), (a >> np.uint32(31)).astype(bool)
+
+
+def bre_gather(photons, rays, medium, config, tri, radius, mode="kdtree", double=False, threads=None,
+               begin=0, end=None, neighbours=False):
+    """Restated computeVolumeGradientPhotonBRE gather (gvpm.cpp:999-1052) over rays [begin,end).
+
+    mode "kdtree": reference-shaped sliding-midpoint kd layout + AABB hierarchy + stack DFS;
+    mode "brute":  all photons against the neighbour predicate (tree-independent set)."""
+    lib = load()
+    end = rays.n if end is None else end
+    threads = hw_threads() if threads is None else threads
+    cph, cr = photons.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    tree, build_ms = None, 0.0
+    if mode == "kdtree":
+        tree = lib.gvpm_oracle_tree_build(C.byref(cph), photons.n, radius, int(double))
+        build_ms = lib.gvpm_oracle_tree_build_ms(tree)
+    m = end - begin
+    out = np.zeros(m * N.GVPM_OUT_FLOATS, dtype=np.float32)
+    counts = np.zeros(m * 2, dtype=np.uint32)
+    ms = C.c_double(0)
+    offsets = idx = None
+    try:
+        if neighbours:
+            offsets = np.zeros(m + 1, dtype=np.uint64)
+            need = lib.gvpm_oracle_bre(tree, C.byref(cph), photons.n, C.byref(cr), begin, end, C.byref(medium),
+                                       C.byref(config), tri.ctypes.data_as(N.f32p), tri.size // 9, radius,
+                                       int(double), threads, out.ctypes.data_as(N.f32p),
+                                       counts.ctypes.data_as(N.u32p), offsets.ctypes.data_as(N.u64p), None, 0,
+                                       C.byref(ms))
+            if need < 0:
+                raise RuntimeError(f"gvpm_oracle_bre failed: {need}")
+            idx = np.zeros(max(int(need), 1), dtype=np.uint32)
+            cap = int(need)
+        else:
+            cap = 0
+        need = lib.gvpm_oracle_bre(tree, C.byref(cph), photons.n, C.byref(cr), begin, end, C.byref(medium),
+                                   C.byref(config), tri.ctypes.data_as(N.f32p), tri.size // 9, radius, int(double),
+                                   threads, out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p),
+                                   offsets.ctypes.data_as(N.u64p) if neighbours else None,
+                                   idx.ctypes.data_as(N.u32p) if neighbours else None, cap, C.byref(ms))
+        if need < 0:
+            raise RuntimeError(f"gvpm_oracle_bre failed: {need}")
+    finally:
+        if tree:
+            lib.gvpm_oracle_tree_free(tree)
+    return BreResult(out.reshape(m, N.GVPM_OUT_FLOATS), counts.reshape(m, 2), offsets,
+                     idx[:cap] if neighbours else None, ms.value, build_ms)

@@ -1,0 +1,597 @@
+// gvpm_oracle.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference's volumetric density-estimation gather (gradientpm/gvpm,
+// src/integrators/photonmapper/...), used ONLY by tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py as the checker and the timed CPU baseline.
+// The product path (gvpm_b200/csrc) never includes, links or calls anything in oracle/.
+//
+// PARITY UNPINNED: the reference ships no test, golden vector or fixture for this path
+//  and its Mitsuba build cannot be produced in this image (Boost, Eigen,
+// Xerces, OpenEXR ... are absent), so this restatement is pinned only by
+// self-consistency checks (tests/test_oracle_*.py), not by reference outputs.
+//
+// Template parameter Real = float restates the SINGLE_PRECISION build
+// (build/config-linux-gcc.py:7); Real = double is the error-budget variant.  Compile with
+// -ffp-contract=off so no FMA is formed: the neighbour predicate must be bit-reproducible.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../include/gvpm_b200.h"
+
+namespace gvpm_oracle {
+
+template <typename Real> struct V3 {
+  Real x, y, z;
+  V3() : x(0), y(0), z(0) {}
+  V3(Real a, Real b, Real c) : x(a), y(b), z(c) {}
+  explicit V3(const float *p) : x((Real)p[0]), y((Real)p[1]), z((Real)p[2]) {}
+  Real operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+  Real &at(int i) { return i == 0 ? x : (i == 1 ? y : z); }
+  V3 operator+(const V3 &o) const { return V3(x + o.x, y + o.y, z + o.z); }
+  V3 operator-(const V3 &o) const { return V3(x - o.x, y - o.y, z - o.z); }
+  V3 operator-() const { return V3(-x, -y, -z); }
+  V3 operator*(Real f) const { return V3(x * f, y * f, z * f); }
+  // include/mitsuba/core/vector.h:535-542: division multiplies by the reciprocal
+  V3 operator/(Real f) const { Real r = (Real)1 / f; return V3(x * r, y * r, z * r); }
+  V3 &operator+=(const V3 &o) { x += o.x; y += o.y; z += o.z; return *this; }
+  // component-wise (Spectrum) product, spectrum.h:385-397
+  V3 operator*(const V3 &o) const { return V3(x * o.x, y * o.y, z * o.z); }
+  Real lengthSquared() const { return x * x + y * y + z * z; }
+  Real length() const { return std::sqrt(lengthSquared()); }
+  Real maxc() const { return std::max(x, std::max(y, z)); }
+};
+template <typename Real> inline V3<Real> operator*(Real f, const V3<Real> &v) { return v * f; }
+template <typename Real> inline Real dot(const V3<Real> &a, const V3<Real> &b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z;  // vector.h:609-611
+}
+template <typename Real> inline V3<Real> cross(const V3<Real> &a, const V3<Real> &b) {
+  return V3<Real>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <typename Real> inline V3<Real> normalize(const V3<Real> &v) { return v / v.length(); }
+template <typename Real> inline Real safe_sqrt(Real v) { return std::sqrt(std::max((Real)0, v)); }
+
+// coordinateSystemCoherent, src/libcore/util.cpp:592-599 (Duff et al. 2017); sign, a, b are
+// `float` in the reference whatever Float is.
+template <typename Real> inline void coordinateSystemCoherent(const V3<Real> &n, V3<Real> &b1, V3<Real> &b2) {
+  float sign = copysignf(1.0f, (float)n.z);
+  const float a = (float)(-1.0f / (sign + n.z));
+  const float b = (float)(n.x * n.y * a);
+  b1 = V3<Real>((Real)(1.0f + sign * n.x * n.x * a), (Real)(sign * b), (Real)(-sign * n.x));
+  b2 = V3<Real>((Real)b, (Real)(sign + n.y * n.y * a), (Real)(-n.y));
+}
+
+template <typename Real> struct Consts;
+template <> struct Consts<float> {
+  static constexpr float pi = 3.14159265358979323846f, inv_pi = 0.31830988618379067154f,
+                         inv_fourpi = 0.07957747154594766788f;
+};
+template <> struct Consts<double> {
+  static constexpr double pi = 3.14159265358979323846, inv_pi = 0.31830988618379067154,
+                          inv_fourpi = 0.07957747154594766788;
+};
+
+// ---------------------------------------------------------------------------------------
+// Homogeneous medium (balance strategy), src/medium/homogeneous.cpp:432-513
+template <typename Real> struct Medium {
+  V3<Real> sigmaS, sigmaA, sigmaT;
+  int phaseType;
+  Real g, samplingWeight;
+  explicit Medium(const gvpm_medium &m)
+      : sigmaS(m.sigma_s), sigmaA(m.sigma_a), phaseType(m.phase_type), g((Real)m.hg_g),
+        samplingWeight((Real)m.sampling_weight) {
+    sigmaT = sigmaS + sigmaA;
+  }
+  struct Rec { V3<Real> transmittance; Real pdfSuccess, pdfFailure; };
+  // eval(ray, mRec) with EDistanceNormal: distance = maxt - mint
+  Rec eval(Real mint, Real maxt) const {
+    Rec r;
+    Real distance = maxt - mint;
+    r.pdfSuccess = 0;
+    r.pdfFailure = 0;
+    for (int i = 0; i < 3; ++i) {  // :478-483
+      Real tmp = std::exp(-sigmaT[i] * distance);
+      r.pdfFailure += tmp;
+      r.pdfSuccess += sigmaT[i] * tmp;
+    }
+    r.pdfSuccess /= 3;
+    r.pdfFailure /= 3;
+    r.transmittance = V3<Real>(std::exp(sigmaT.x * (-distance)), std::exp(sigmaT.y * (-distance)),
+                               std::exp(sigmaT.z * (-distance)));  // :504
+    r.pdfSuccess = r.pdfSuccess * samplingWeight;                    // :505
+    r.pdfFailure = r.pdfFailure * samplingWeight + (1 - samplingWeight);
+    if (r.transmittance.maxc() < (Real)1e-20) r.transmittance = V3<Real>();  // :511-512
+    return r;
+  }
+  // PhaseFunction::eval(pRec(wi, wo)): phase/isotropic.cpp:76, phase/hg.cpp:107-110
+  Real phase(const V3<Real> &wi, const V3<Real> &wo) const {
+    if (phaseType == GVPM_PHASE_ISOTROPIC) return Consts<Real>::inv_fourpi;
+    Real temp = (Real)1 + g * g + (Real)2 * g * dot(wi, wo);
+    return Consts<Real>::inv_fourpi * (1 - g * g) / (temp * std::sqrt(temp));
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Input views (float storage, converted on access)
+template <typename Real> struct Photon {
+  V3<Real> pos, flux, parentPos, predPos, parentN, prefix, albedo;
+  Real parentPdf, edgePdf, rrWeight;
+  int parentType, depth;
+  uint32_t pathId;
+};
+template <typename Real> inline Photon<Real> loadPhoton(const gvpm_photon_soa &s, size_t i) {
+  Photon<Real> p;
+  p.pos = V3<Real>(s.pos + 3 * i);
+  p.flux = V3<Real>(s.flux + 3 * i);
+  p.parentPos = V3<Real>(s.parent_pos + 3 * i);
+  p.predPos = V3<Real>(s.pred_pos + 3 * i);
+  p.parentN = V3<Real>(s.parent_n + 3 * i);
+  p.prefix = V3<Real>(s.prefix_flux + 3 * i);
+  p.albedo = V3<Real>(s.parent_albedo + 3 * i);
+  p.parentPdf = (Real)s.parent_pdf[i];
+  p.edgePdf = (Real)s.edge_pdf[i];
+  p.rrWeight = (Real)s.rr_weight[i];
+  p.parentType = s.parent_type[i];
+  p.depth = s.depth[i];
+  p.pathId = s.path_id[i];
+  return p;
+}
+
+template <typename Real> struct CamRay {
+  V3<Real> o, d, eye;
+  Real mint, maxt, edgeLen, xi;
+  int px, py, edgeId;
+  bool offValid[4];
+  V3<Real> offO[4], offD[4], offEye[4];
+  Real offLen[4], offSensor[4];
+};
+template <typename Real> inline CamRay<Real> loadRay(const gvpm_ray_soa &s, size_t i) {
+  CamRay<Real> r;
+  r.o = V3<Real>(s.o + 3 * i);
+  r.d = V3<Real>(s.d + 3 * i);
+  r.eye = V3<Real>(s.eye_contrib + 3 * i);
+  r.mint = (Real)s.mint[i];
+  r.maxt = (Real)s.maxt[i];
+  r.edgeLen = (Real)s.edge_len[i];
+  r.xi = (Real)s.xi[i];
+  r.px = s.px[i];
+  r.py = s.py[i];
+  r.edgeId = s.edge_id[i];
+  for (int k = 0; k < 4; ++k) {
+    r.offValid[k] = s.off_valid[4 * i + k] != 0;
+    r.offO[k] = V3<Real>(s.off_o + 3 * (4 * i + k));
+    r.offD[k] = V3<Real>(s.off_d + 3 * (4 * i + k));
+    r.offEye[k] = V3<Real>(s.off_eye + 3 * (4 * i + k));
+    r.offLen[k] = (Real)s.off_len[4 * i + k];
+    r.offSensor[k] = (Real)s.off_sensor[4 * i + k];
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Occluders: Triangle::rayIntersect, include/mitsuba/core/triangle.h:109-145, any-hit over a
+// flat list with the (mint, maxt) interval of Scene::rayIntersect(ray).
+template <typename Real> struct Occluders {
+  std::vector<V3<Real>> v;  // 3 per triangle
+  void set(const float *tri, size_t n) {
+    v.resize(3 * n);
+    for (size_t i = 0; i < 3 * n; ++i) v[i] = V3<Real>(tri + 3 * i);
+  }
+  bool anyHit(const V3<Real> &o, const V3<Real> &d, Real mint, Real maxt) const {
+    for (size_t t = 0; t + 2 < v.size(); t += 3) {
+      V3<Real> edge1 = v[t + 1] - v[t], edge2 = v[t + 2] - v[t];
+      V3<Real> pvec = cross(d, edge2);
+      Real det = dot(edge1, pvec);
+      if (det == 0) continue;
+      Real inv_det = (Real)1 / det;
+      V3<Real> tvec = o - v[t];
+      Real u = dot(tvec, pvec) * inv_det;
+      if (u < 0 || u > 1) continue;
+      V3<Real> qvec = cross(tvec, edge1);
+      Real vv = dot(d, qvec) * inv_det;
+      if (vv >= 0 && u + vv <= 1) {
+        Real tt = dot(edge2, qvec) * inv_det;
+        if (tt >= mint && tt <= maxt) return true;  // Ray interval, shape.h semantics
+      }
+    }
+    return false;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Per-ray accumulators: AbstractVolumeGradientRecord, shift/shift_volume_photon.h:17-20
+template <typename Real> struct Accum {
+  V3<Real> mediumFlux, shifted[4], weighted[4];
+  void store(float *out) const {
+    auto put = [&](int j, const V3<Real> &v) {
+      out[3 * j] = (float)v.x; out[3 * j + 1] = (float)v.y; out[3 * j + 2] = (float)v.z;
+    };
+    put(0, mediumFlux);
+    for (int k = 0; k < 4; ++k) put(1 + k, shifted[k]);
+    for (int k = 0; k < 4; ++k) put(5 + k, weighted[k]);
+  }
+};
+
+template <typename Real> struct GradientSamplingResult {  // shift_utilities.h:17-23
+  V3<Real> shiftedFlux;
+  Real weight = 1, jacobian = 1;
+};
+
+// 1/max(2*deltaT, 0.0001) evaluated in double like the reference (shift_volume_photon.cpp:723)
+template <typename Real> inline Real chordPdf(Real deltaT) {
+  return (Real)(1.f / std::max((double)deltaT * 2.0, 0.0001));
+}
+
+template <typename Real> struct Scene {
+  Medium<Real> medium;
+  gvpm_config cfg;
+  Occluders<Real> occ;
+  Real radius;
+  explicit Scene(const gvpm_medium &m, const gvpm_config &c, Real r) : medium(m), cfg(c), radius(r) {}
+
+  // computeVolumeContribution, shift_utilities.h:233-253 (bsdfInteractionMode = EAll)
+  bool lightingModeAccepts(int parentType) const {
+    int m = cfg.lighting_mode;
+    if ((m & GVPM_SURF2MEDIA) && (m & GVPM_MEDIA2MEDIA)) return true;
+    if (parentType == GVPM_PARENT_MEDIUM && !(m & GVPM_MEDIA2MEDIA)) return false;
+    if (parentType != GVPM_PARENT_MEDIUM && !(m & GVPM_SURF2MEDIA)) return false;
+    return true;
+  }
+
+  // getVolumePhotonContrib, shift_volume_photon.h:79-86
+  V3<Real> volumePhotonContrib(const V3<Real> &flux, const V3<Real> &wi, const V3<Real> &wo) const {
+    return (medium.sigmaS * flux) * medium.phase(wi, wo);
+  }
+
+  // diffuseReconnection, shift/operation/shift_diffuse.cpp:11-134, for the in-scope vertex
+  // types {area emitter (emitters/area.cpp:132-150), diffuse BSDF (bsdfs/diffuse.cpp:110-127),
+  // medium}.  Returns throughput and pdf (pdf = 0 when the reconnection is impossible).
+  void diffuseReconnection(const Photon<Real> &ph, const V3<Real> &newD, Real newDLength,
+                           V3<Real> &throughput, Real &pdf) const {
+    throughput = V3<Real>(1, 1, 1);
+    pdf = 0;
+    Real pdfValue;
+    const Real INV_PI = Consts<Real>::inv_pi;
+    if (ph.parentType == GVPM_PARENT_SURFACE) {
+      V3<Real> wiWorld = normalize(ph.predPos - ph.parentPos);
+      Real cosI = dot(ph.parentN, wiWorld), cosO = dot(ph.parentN, newD);
+      if (cosI <= 0 || cosO <= 0) {
+        throughput = V3<Real>();
+        pdfValue = 0;
+      } else {
+        throughput = throughput * (ph.albedo * (INV_PI * cosO));
+        pdfValue = INV_PI * cosO;
+      }
+      // geometric == shading normal for the flattened record: :43-47
+      if (cosI * cosI <= 0 || cosO * cosO <= 0) return;
+    } else if (ph.parentType == GVPM_PARENT_MEDIUM) {
+      V3<Real> pWi = normalize(ph.predPos - ph.parentPos);
+      Real phv = medium.phase(pWi, newD);
+      throughput = throughput * (medium.sigmaS * phv);
+      pdfValue = phv;
+    } else if (ph.parentType == GVPM_PARENT_EMITTER) {
+      Real dp = dot(newD, ph.parentN);
+      if (dp < 0) dp = 0;
+      throughput = throughput * V3<Real>(INV_PI * dp, INV_PI * dp, INV_PI * dp);
+      pdfValue = INV_PI * dp;
+    } else {
+      return;  // glossy parent: manifold shift, out of scope (treated as a failed shift)
+    }
+    Real GOp = 1 / (newDLength * newDLength);  // :89-92 (isVolumeBase)
+    pdf = pdfValue * GOp;
+    throughput = throughput * GOp;
+    if (ph.parentPdf == 0) { pdf = 0; return; }  // :100-104
+    throughput = throughput / ph.parentPdf;       // :111
+    throughput = throughput * ph.rrWeight;        // :112
+    // edge->medium != nullptr always holds for a volume photon's last edge: :114-131
+    typename Medium<Real>::Rec m = medium.eval(0, newDLength);
+    pdf *= m.pdfSuccess;
+    throughput = throughput * (m.transmittance / ph.edgePdf);
+  }
+
+  // AbstractVolumeGradientRecord::shiftNull, shift_volume_photon.cpp:119-158
+  void shiftNull(const Photon<Real> &ph, const V3<Real> &wi, const CamRay<Real> &ray, int k,
+                 const typename Medium<Real>::Rec &mShift, GradientSamplingResult<Real> &res,
+                 Real pdfBaseRay, Real pdfShiftRay) const {
+    V3<Real> contrib = volumePhotonContrib(ph.flux, wi, -ray.offD[k]);
+    res.shiftedFlux = ((mShift.transmittance * contrib) * ray.offEye[k]) * res.jacobian;
+    res.weight = (Real)0.5;
+    if (cfg.use_mis) {
+      if (pdfShiftRay == 0 || pdfBaseRay == 0) { res.weight = 1; return; }
+      res.weight = (Real)1 / ((Real)1 + ray.offSensor[k] * pdfShiftRay * res.jacobian / pdfBaseRay);
+    }
+  }
+
+  // shiftPhoton -> shiftPhotonDiffuse, shift_volume_photon.cpp:49-117,382-486
+  void shiftPhotonDiffuse(const Photon<Real> &ph, const V3<Real> &offsetPos, const CamRay<Real> &ray,
+                          int k, const typename Medium<Real>::Rec &mShift,
+                          GradientSamplingResult<Real> &res, Real pdfBaseRay, Real pdfShiftRay) const {
+    if (ph.parentType == GVPM_PARENT_OTHER) return;  // EManifoldShift with useManifold=false
+    V3<Real> dProj = offsetPos - ph.parentPos;
+    Real lProj = dProj.length();
+    dProj = dProj / lProj;
+    // Ray projRay(parent, dProj, Epsilon, lProj * ShadowEpsilon): :396
+    if (occ.anyHit(ph.parentPos, dProj, (Real)cfg.epsilon, lProj * (Real)cfg.shadow_maxt_scale)) return;
+    if (ph.parentType != GVPM_PARENT_MEDIUM) {  // :404-412
+      V3<Real> edgeD = normalize(ph.pos - ph.parentPos);
+      Real signDot = dot(ph.parentN, dProj) / dot(ph.parentN, edgeD);
+      if (signDot < 0) return;
+    }
+    V3<Real> thr;
+    Real sPdf;
+    diffuseReconnection(ph, dProj, lProj, thr, sPdf);
+    if (sPdf == 0) { res.weight = 1; return; }
+    V3<Real> photonWeight = ph.prefix * thr;
+    V3<Real> contrib = volumePhotonContrib(photonWeight, -dProj, -ray.offD[k]);
+    res.shiftedFlux = ((mShift.transmittance * contrib) * ray.offEye[k]) * res.jacobian;
+    res.weight = (Real)0.5;
+    if (cfg.use_mis) {
+      Real basePdf = pdfBaseRay;
+      basePdf *= ph.parentPdf;
+      basePdf *= ph.edgePdf;
+      Real offsetPdf = sPdf * pdfShiftRay;
+      if (offsetPdf == 0 || basePdf == 0) { res.weight = 1; return; }
+      Real q = ray.offSensor[k] * res.jacobian * (offsetPdf / basePdf);
+      res.weight = cfg.power_heuristic ? (Real)1 / ((Real)1 + q * q) : (Real)1 / ((Real)1 + q);
+    }
+  }
+
+  // AbstractVolumeGradientRecord::getShiftPos, shift_volume_photon.cpp:858-896 (3-D kernel)
+  V3<Real> getShiftPos(const CamRay<Real> &ray, int k, Real tBase, const V3<Real> &basePhotonPos) const {
+    V3<Real> zBase = ray.o + tBase * ray.d, zShift = ray.offO[k] + tBase * ray.offD[k];
+    V3<Real> offsetPos = zShift + (basePhotonPos - zBase);
+    if (!cfg.kernel_3d) {  // coherent frames for the 2-D kernel, :866-873
+      V3<Real> bs, bt, ns, nt;
+      coordinateSystemCoherent(ray.d, bs, bt);
+      coordinateSystemCoherent(ray.offD[k], ns, nt);
+      V3<Real> v = basePhotonPos - zBase;
+      V3<Real> localD(dot(v, bs), dot(v, bt), dot(v, ray.d));          // Frame::toLocal
+      offsetPos = zShift + ((ns * localD.x + nt * localD.y) + ray.offD[k] * localD.z);  // toWorld
+    }
+    if (cfg.use_shift_null) {
+      Real offDistSqr = (zBase - offsetPos).lengthSquared();
+      if (offDistSqr < radius * radius) {
+        V3<Real> dShift = zShift - zBase;
+        dShift = dShift / dShift.length();
+        Real cosD = dot(dShift, -(offsetPos - zShift));
+        offsetPos += (dShift * cosD) * (Real)2;
+      }
+    }
+    return offsetPos;
+  }
+
+  // The neighbour predicate of GradientBeamRadianceEstimator::query, gvpm_accel.h:293-301.
+  // Returns true and diskDistance when the photon reaches the functor.
+  bool diskTest(const CamRay<Real> &ray, const V3<Real> &p, Real &diskDistance) const {
+    V3<Real> originToCenter = p - ray.o;
+    diskDistance = dot(originToCenter, ray.d);
+    Real radSqr = radius * radius;
+    Real distSqr = ((ray.o + diskDistance * ray.d) - p).lengthSquared();
+    return diskDistance > ray.mint && distSqr < radSqr;
+  }
+
+  // VolumeGradientBREQuery::operator(), shift_volume_photon.cpp:658-856.
+  // Returns 0 = not in the geometric set, 1 = geometric only (filtered), 2 = contributes.
+  int breFunctor(const CamRay<Real> &ray, const Photon<Real> &ph, Real diskDistance, Accum<Real> &acc) const {
+    const Real r = radius;
+    bool filtered = false;
+    int pathLen = ph.depth + ray.edgeId;
+    if (cfg.max_depth > 0 && pathLen > cfg.max_depth) filtered = true;       // :670
+    if (cfg.min_depth != 0 && pathLen < cfg.min_depth) filtered = true;      // :672
+    if (!lightingModeAccepts(ph.parentType)) filtered = true;                // :675-677
+    Real rrGlobalWeight = 1;
+    if (cfg.path_set) {                                                      // :689-697
+      uint32_t currentGroup = (uint32_t)((ray.px + ray.py) % 2);
+      if (ph.pathId % 2 != currentGroup) filtered = true;
+      rrGlobalWeight = 2;
+    }
+    Real kernelVol, pdfCameraPos = 1, tBase = diskDistance;
+    if (cfg.kernel_3d) {                                                     // :707-724
+      kernelVol = (Real)((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3));
+      Real distSqr = ((ray.o + diskDistance * ray.d) - ph.pos).lengthSquared();
+      Real deltaT = safe_sqrt(r * r - distSqr);
+      Real tminKernel = diskDistance - deltaT;
+      Real diskDistanceRand = tminKernel + (deltaT * 2) * ray.xi;
+      if (diskDistanceRand < ray.mint || diskDistanceRand > ray.edgeLen) return 0;
+      tBase = diskDistanceRand;
+      pdfCameraPos = chordPdf(deltaT);
+    } else {
+      kernelVol = (Real)((double)Consts<Real>::pi * std::pow((double)r, 2));
+      // the reference leaves `baseProjDist > edgeLen` as an empty block (:726-731), which makes
+      // its 2-D result depend on the tree shape past the ray end; restated with the explicit
+      // bound sppm uses (bre.cpp:240-242).  Documented deviation, DESIGN.md §6.
+      if (diskDistance > ray.edgeLen) return 0;
+    }
+    if (filtered) return 1;
+
+    const V3<Real> wi = normalize(ph.parentPos - ph.pos);  // -edge(c-1).d
+    typename Medium<Real>::Rec mBase = medium.eval(ray.mint, tBase);
+    V3<Real> contrib = volumePhotonContrib(ph.flux, wi, -ray.d);
+    V3<Real> baseContrib = (mBase.transmittance * contrib) * ray.eye;
+    const Real norm = kernelVol * pdfCameraPos;
+    acc.mediumFlux += (baseContrib / norm) * rrGlobalWeight;                 // :751
+
+    for (int k = 0; k < 4; ++k) {
+      GradientSamplingResult<Real> res;
+      if (ray.offValid[k]) {
+        const Real shiftDistTotal = ray.offLen[k];
+        bool alreadyShift = false;
+        if (cfg.use_shift_null && cfg.kernel_3d) {                           // :776-802
+          V3<Real> zp = ray.offO[k] + tBase * ray.offD[k];
+          Real ZPtoY = (zp - ph.pos).lengthSquared();
+          if (ZPtoY < r * r && tBase < shiftDistTotal) {
+            Real dd = dot(ph.pos - ray.offO[k], ray.offD[k]);
+            Real ds = ((ray.offO[k] + dd * ray.offD[k]) - ph.pos).lengthSquared();
+            Real pdfShiftPos = chordPdf(safe_sqrt(r * r - ds));
+            typename Medium<Real>::Rec mShift = medium.eval((Real)cfg.epsilon, tBase);
+            shiftNull(ph, wi, ray, k, mShift, res, pdfCameraPos, pdfShiftPos);
+            alreadyShift = true;
+          }
+        }
+        if (!alreadyShift && shiftDistTotal >= tBase) {                      // :809-838
+          V3<Real> offsetPos = getShiftPos(ray, k, tBase, ph.pos);
+          Real pdfShiftPos = 1;
+          if (cfg.kernel_3d) {
+            Real dd = dot(offsetPos - ray.offO[k], ray.offD[k]);
+            Real ds = ((ray.offO[k] + dd * ray.offD[k]) - offsetPos).lengthSquared();
+            pdfShiftPos = chordPdf(safe_sqrt(r * r - ds));
+          }
+          typename Medium<Real>::Rec mShift = medium.eval((Real)cfg.epsilon, tBase);
+          shiftPhotonDiffuse(ph, offsetPos, ray, k, mShift, res, pdfCameraPos, pdfShiftPos);
+        }
+      }
+      if ((k == 1 && ray.px == cfg.film_w - 1) || (k == 2 && ray.py == cfg.film_h - 1))
+        res.weight = 1;                                                      // :843-846
+      acc.weighted[k] += ((rrGlobalWeight * res.weight) * baseContrib) / norm;
+      acc.shifted[k] += ((rrGlobalWeight * res.weight) * res.shiftedFlux) / norm;
+    }
+    return 2;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// PointKDTree<SimpleKDNode>::build with ESlidingMidpoint (include/mitsuba/core/kdtree.h:326-378,
+// 921-1037) + GradientBeamRadianceEstimator::buildHierarchy (gvpm/gvpm_accel.cpp:35-55) +
+// query (gvpm/gvpm_accel.h:268-312).
+template <typename Real> struct BreTree {
+  struct Node {
+    V3<Real> pos, bmin, bmax;
+    uint32_t right = 0, orig = 0;
+    bool leaf = false;
+  };
+  std::vector<Node> nodes;
+  size_t depth = 0;
+  Real radius = 0;
+
+  void build(const gvpm_photon_soa &ph, size_t n, Real r) {
+    radius = r;
+    nodes.resize(n);
+    if (n == 0) return;
+    std::vector<V3<Real>> pts(n);
+    V3<Real> amin(pts.empty() ? V3<Real>() : V3<Real>(ph.pos)), amax = amin;
+    for (size_t i = 0; i < n; ++i) {
+      pts[i] = V3<Real>(ph.pos + 3 * i);
+      for (int a = 0; a < 3; ++a) {
+        amin.at(a) = std::min(amin[a], pts[i][a]);
+        amax.at(a) = std::max(amax[a], pts[i][a]);
+      }
+    }
+    std::vector<uint32_t> ind(n);
+    for (size_t i = 0; i < n; ++i) ind[i] = (uint32_t)i;
+    std::vector<uint32_t> rightOf(n, 0);
+    std::vector<uint8_t> leafOf(n, 0);
+    depth = 0;
+    buildRec(1, pts, ind, rightOf, leafOf, 0, n, amin, amax);
+    for (size_t i = 0; i < n; ++i) {  // permute_inplace(indirection)
+      Node &nd = nodes[i];
+      nd.orig = ind[i];
+      nd.pos = pts[ind[i]];
+      nd.right = rightOf[ind[i]];
+      nd.leaf = leafOf[ind[i]] != 0;
+    }
+    hierarchy(0);
+  }
+
+  void buildRec(size_t d, const std::vector<V3<Real>> &pts, std::vector<uint32_t> &ind,
+                std::vector<uint32_t> &rightOf, std::vector<uint8_t> &leafOf, size_t b, size_t e,
+                V3<Real> &amin, V3<Real> &amax) {
+    depth = std::max(d, depth);
+    size_t count = e - b;
+    if (count == 1) { leafOf[ind[b]] = 1; return; }
+    V3<Real> ext = amax - amin;
+    int axis = 0;
+    for (int i = 1; i < 3; ++i) if (ext[i] > ext[axis]) axis = i;   // aabb.h:269-277
+    Real midpoint = (Real)0.5 * (amax[axis] + amin[axis]);
+    size_t nLT = 0;
+    for (size_t i = b; i < e; ++i) nLT += pts[ind[i]][axis] <= midpoint;
+    size_t split = b + nLT;
+    if (split == b) ++split; else if (split == e) --split;
+    std::nth_element(ind.begin() + b, ind.begin() + split, ind.begin() + e,
+                     [&](uint32_t i1, uint32_t i2) { return pts[i1][axis] < pts[i2][axis]; });
+    uint32_t sp = ind[split];
+    rightOf[sp] = (split + 1 != e) ? (uint32_t)(split + 1) : 0;
+    std::swap(ind[b], ind[split]);
+    Real splitPos = pts[sp][axis];
+    Real temp = amax[axis];
+    amax.at(axis) = splitPos;
+    buildRec(d + 1, pts, ind, rightOf, leafOf, b + 1, split + 1, amin, amax);
+    amax.at(axis) = temp;
+    if (split + 1 != e) {
+      temp = amin[axis];
+      amin.at(axis) = splitPos;
+      buildRec(d + 1, pts, ind, rightOf, leafOf, split + 1, e, amin, amax);
+      amin.at(axis) = temp;
+    }
+  }
+
+  void hierarchy(uint32_t root) {  // iterative post-order of gvpm_accel.cpp:35-55
+    // children always have larger indices than their parent (left = self+1, right > self)
+    for (size_t ii = nodes.size(); ii-- > 0;) {
+      Node &nd = nodes[ii];
+      V3<Real> rv(radius, radius, radius);
+      nd.bmin = nd.pos - rv;
+      nd.bmax = nd.pos + rv;
+      if (!nd.leaf) {
+        auto expand = [&](const Node &c) {
+          for (int a = 0; a < 3; ++a) {
+            nd.bmin.at(a) = std::min(nd.bmin[a], c.bmin[a]);
+            nd.bmax.at(a) = std::max(nd.bmax[a], c.bmax[a]);
+          }
+        };
+        expand(nodes[ii + 1]);
+        if (nd.right) expand(nodes[nd.right]);
+      }
+    }
+    (void)root;
+  }
+
+  // AABB::rayIntersect, include/mitsuba/core/aabb.h:310-340
+  static bool slab(const V3<Real> &bmin, const V3<Real> &bmax, const V3<Real> &o, const V3<Real> &d,
+                   const V3<Real> &dRcp, Real &nearT, Real &farT) {
+    nearT = -INFINITY;
+    farT = INFINITY;
+    for (int i = 0; i < 3; ++i) {
+      Real origin = o[i], minVal = bmin[i], maxVal = bmax[i];
+      if (d[i] == 0) {
+        if (origin < minVal || origin > maxVal) return false;
+      } else {
+        Real t1 = (minVal - origin) * dRcp[i], t2 = (maxVal - origin) * dRcp[i];
+        if (t1 > t2) std::swap(t1, t2);
+        nearT = std::max(t1, nearT);
+        farT = std::min(t2, farT);
+        if (!(nearT <= farT)) return false;
+      }
+    }
+    return true;
+  }
+
+  // visit(nodeIndexInTree, diskDistance) for every photon passing the predicate
+  template <typename F> void query(const Scene<Real> &sc, const CamRay<Real> &ray, F &&visit) const {
+    if (nodes.empty()) return;
+    std::vector<uint32_t> stack(depth + 2);
+    uint32_t index = 0, stackPos = 1;
+    V3<Real> dRcp((Real)1 / ray.d.x, (Real)1 / ray.d.y, (Real)1 / ray.d.z);
+    while (stackPos > 0) {
+      const Node &node = nodes[index];
+      Real mint, maxt;
+      if (!slab(node.bmin, node.bmax, ray.o, ray.d, dRcp, mint, maxt) || maxt < ray.mint || mint > ray.maxt) {
+        index = stack[--stackPos];
+        continue;
+      }
+      uint32_t self = index;
+      if (!node.leaf) {
+        if (node.right != 0) stack[stackPos++] = node.right;
+        index = self + 1;
+      } else {
+        index = stack[--stackPos];
+      }
+      Real diskDistance;
+      if (sc.diskTest(ray, node.pos, diskDistance)) visit(self, diskDistance);
+    }
+  }
+};
+
+}  // namespace gvpm_oracle
