@@ -5,7 +5,7 @@ four gradient contributions within 1e-4 relative (fp32)."""
 import numpy as np
 import pytest
 
-from tests import helpers as H
+import gvpm_testlib as H
 
 pytestmark = pytest.mark.gpu
 
