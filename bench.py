@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — one G-BRE 3D mixed-shift gather iteration per step (BASELINE.json configs[4]).
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+    python bench.py --impl reference ...                     CPU arm: the oracle restatement on host cores
+
+Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M photons per iteration,
+G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
+A step = accel build + gather of every camera-ray medium segment of the image (primal + 4 gradient
+contributions = 27 floats per ray).  N > 1: strong scaling — 32x32 image tiles dealt round-robin to
+the ranks, the iteration's photon set broadcast from rank 0 over NCCL, every rank builds the
+hierarchy and gathers its tiles, results gathered to rank 0 (north_star).  No data-path collective
+other than that broadcast/gather.
+
+value  = rays / s with the photon SoA and the rays already resident in HBM.
+e2e    = same through the C ABI with HOST (pinned) buffers: H2D of photons and rays, build, gather,
+         D2H of the 27 planes, every step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (w, h, photons, default scale)
+    "cfg5": (1920, 1080, 10_000_000, 0.1),
+    "cfg1": (256, 256, 100_000, 1.0),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=None, help="initialScaleVolume (paper preset 0.1)")
+    ap.add_argument("--photons", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU-baseline sample time")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+def pinned(n, dtype):
+    import torch
+    t = torch.empty(n, dtype=dtype, pin_memory=torch.cuda.is_available())
+    return t, t.numpy()
+
+
+def make_inputs(args, rank, world, pin=True):
+    """Synthetic inputs in pinned host memory (untimed set-up)."""
+    import torch
+    import gvpm_b200 as g
+    from gvpm_b200 import records as R
+    w, h, n_ph, scale = WORKLOADS[args.workload]
+    if args.photons:
+        n_ph = args.photons
+    if args.scale:
+        scale = args.scale
+    seed = 0xC0FFEE + 5
+    medium = g.make_medium()
+    keep = []
+
+    def alloc(fields, n):
+        arrs = {}
+        for name, dt, wd in fields:
+            tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.uint32: torch.int32,
+                   np.int32: torch.int32}[dt]
+            if pin:
+                t, a = pinned(n * wd, tdt)
+                keep.append(t)
+                arrs[name] = a.view(dt)
+            else:
+                arrs[name] = np.zeros(n * wd, dtype=dt)
+        return arrs
+
+    threads = max(1, min(32, (os.cpu_count() or 8) // max(1, world)))
+    photons = None
+    n_paths = 0
+    if rank == 0 or args.impl == "reference":
+        photons = R.PhotonSet(n_ph, **alloc(R._PHOTON_FIELDS, n_ph))
+        s = g._native.load_synth()
+        cs = photons.as_c()
+        n_paths = s.gvpm_synth_photons(seed, n_ph, C.byref(medium), 12, 1, 0, 100.0, threads, C.byref(cs))
+    full = g.synth_rays(w, h, seed=seed + 1, block=32)
+    # 32x32 tiles (block-major order from the generator) dealt round-robin to the ranks
+    tiles_x = (w + 31) // 32
+    tile_id = (full.py // 32) * tiles_x + (full.px // 32)
+    mine = np.nonzero(tile_id % world == rank)[0]
+    sub = full.take(mine)
+    rays = R.RaySet(sub.n, **alloc(R._RAY_FIELDS, sub.n))
+    for name, _, _ in R._RAY_FIELDS:
+        getattr(rays, name)[:] = getattr(sub, name)
+    cfg = g.make_config(w, h)
+    return dict(w=w, h=h, n_ph=n_ph, scale=scale, medium=medium, photons=photons, n_paths=int(n_paths),
+                rays=rays, rays_full_n=full.n, cfg=cfg, tri=g.synth_occluders(), radius=g.bre_radius(scale),
+                keep=keep, full_rays=full if (rank == 0) else None)
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DevView:
+    """__cuda_array_interface__ wrapper so torch can alias a raw device pointer (no copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_arm(args, inp, seconds):
+    """The reference's CPU gather as restated by the oracle (kd layout + AABB hierarchy + stack DFS,
+    worker threads pulling ray tiles), on all host cores, on a bounded sample of the same workload."""
+    from oracle import binding as ob
+    lib = ob.load()
+    from gvpm_b200 import _native as N
+    cores = ob.hw_threads()
+    ph, rays = inp["photons"], inp["full_rays"] if inp.get("full_rays") is not None else inp["rays"]
+    cph = ph.as_c()
+    tree = lib.gvpm_oracle_tree_build(C.byref(cph), ph.n, inp["radius"], 0)
+    build_ms = lib.gvpm_oracle_tree_build_ms(tree)
+    # sample = whole 1024-ray tiles spread evenly over the ray list (every k-th tile)
+    n_tiles = max(1, rays.n // 1024)
+
+    def run(tile_ids):
+        idx = (np.asarray(tile_ids)[:, None] * 1024 + np.arange(1024)[None, :]).reshape(-1)
+        idx = idx[idx < rays.n]
+        sub = rays.take(idx)
+        cr = sub.as_c()
+        out = np.zeros(sub.n * 27, dtype=np.float32)
+        ms = C.c_double(0)
+        tri = inp["tri"]
+        rc = lib.gvpm_oracle_bre(tree, C.byref(cph), ph.n, C.byref(cr), 0, sub.n, C.byref(inp["medium"]),
+                                 C.byref(inp["cfg"]), tri.ctypes.data_as(N.f32p), tri.size // 9, inp["radius"], 0,
+                                 cores, out.ctypes.data_as(N.f32p), None, None, None, 0, C.byref(ms))
+        assert rc >= 0
+        return sub.n, ms.value
+
+    pilot_tiles = np.linspace(0, n_tiles - 1, num=min(n_tiles, max(8, cores // 4)), dtype=np.int64)
+    n0, ms0 = run(np.unique(pilot_tiles))
+    rate = n0 / max(ms0, 1e-3) * 1e3
+    want = int(min(n_tiles, max(len(pilot_tiles), rate * seconds / 1024)))
+    tiles = np.unique(np.linspace(0, n_tiles - 1, num=want, dtype=np.int64))
+    n1, ms1 = run(tiles)
+    lib.gvpm_oracle_tree_free(tree)
+    return {"value": n1 / ms1 * 1e3, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n1} rays ({len(tiles)} of {n_tiles} 1024-ray tiles spread over the image) against all "
+                      f"{ph.n} photons; gather only ({ms1:.0f} ms); kd+AABB hierarchy build {build_ms:.0f} ms "
+                      f"single-threaded, not included"}, ms1, n1
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build_cpu_libs()
+    inp = make_inputs(args, 0, 1, pin=False)
+    inp["full_rays"] = inp["rays"]
+    per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, ms, n = cpu_arm(args, inp, per)
+        if i >= args.warmup:
+            vals.append((n, ms))
+    n_tot = sum(v[0] for v in vals)
+    ms_tot = sum(v[1] for v in vals)
+    value = n_tot / ms_tot * 1e3
+    cb["value"] = value
+    line = {"impl": "reference", "metric": "camera-ray gathers/sec (primal+4 gradients)", "value": value,
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_tot / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, inp, 1), "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, inp, world):
+    return {"workload": f"{args.workload}: {inp['w']}x{inp['h']} homogeneous-medium Cornell box, "
+                        f"{inp['n_ph']} photons/iteration, gvpm G-BRE 3D kernel, mixed shift, area MIS, pathSet",
+            "rays": inp["rays_full_n"], "photons": inp["n_ph"], "initialScaleVolume": inp["scale"],
+            "radius": inp["radius"], "parallelism": f"image tiles (32x32) round-robin over {world} GPU(s), "
+                                                    "photon set broadcast, results gathered to rank 0",
+            "l2": "inputs larger than L2 (photon records 1.1 GB, rays 0.66 GB): no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from gvpm_b200.api import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gvpm_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build_cpu_libs()
+    if world > 1:
+        dist.barrier()
+
+    inp = make_inputs(args, rank, world)
+    ctx = Context(local)
+    ctx.set_medium(inp["medium"])
+    ctx.set_config(inp["cfg"])
+    ctx.set_occluders(inp["tri"])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    n_ph, rays = inp["n_ph"], inp["rays"]
+    n_local = rays.n
+    # result buffers (device): own shard; rank 0 also the gathered image
+    counts_max = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(counts_max, op=dist.ReduceOp.MAX)
+    n_pad = int(counts_max.item())
+    with torch.cuda.stream(stream):
+        out_dev = torch.zeros(n_pad * 27, device="cuda", dtype=torch.float32)
+        cnt_dev = torch.zeros(n_pad * 2, device="cuda", dtype=torch.int32)
+        gathered = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    out_host_t, out_host = pinned((n_pad * 27) * (world if rank == 0 else 1), torch.float32)
+
+    ph_ptr, ph_bytes = ctx.photon_staging(n_ph)
+    ph_view = torch.as_tensor(DevView(ph_ptr, ph_bytes), device="cuda")
+
+    def exchange_photons():
+        if world > 1:
+            dist.broadcast(ph_view, src=0)
+
+    def collect():
+        if world > 1:
+            dist.gather(out_dev, gathered, dst=0)
+
+    def step_resident():
+        """inputs resident in HBM: (broadcast) + build + gather (+ result gather)"""
+        with torch.cuda.stream(stream):
+            exchange_photons()
+            ctx.photon_staging(n_ph)
+            ctx.build_points(inp["radius"])
+            ctx.gather_bre_into(out_dev.data_ptr(), cnt_dev.data_ptr())
+            collect()
+
+    def step_e2e():
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                ctx.upload_photons(inp["photons"])
+            exchange_photons()
+            ctx.photon_staging(n_ph)
+            ctx.build_points(inp["radius"])
+            ctx.upload_rays(rays)
+            ctx.gather_bre_into(out_dev.data_ptr(), cnt_dev.data_ptr())
+            collect()
+            if rank == 0 and world > 1:
+                for r in range(world):
+                    out_host_t[r * n_pad * 27:(r + 1) * n_pad * 27].copy_(gathered[r], non_blocking=True)
+            else:
+                out_host_t[:n_pad * 27].copy_(out_dev, non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        builds, gathers = [], []
+        l0 = ctx.launch_count()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for _ in range(steps):
+            fn()
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        b, g = ctx.last_timings()
+        return float(ms.item()), ctx.launch_count() - l0, b, g
+
+    # residency: upload once (untimed) for the `value` leg
+    with torch.cuda.stream(stream):
+        if rank == 0:
+            ctx.upload_photons(inp["photons"])
+        ctx.upload_rays(rays)
+    ctx.sync()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, build_ms, gather_ms = timed(step_resident, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    # gather-kernel duration averaged over a few launches on the launching stream (CUDA events)
+    kt = []
+    for _ in range(3):
+        step_resident()
+        kt.append(ctx.last_timings())
+    gather_ms = float(np.mean([k[1] for k in kt]))
+    build_ms = float(np.mean([k[0] for k in kt]))
+    h_geom = torch.tensor([int(cnt_dev.view(-1, 2)[:n_local, 0].to(torch.int64).sum().item())], device="cuda")
+    gk = torch.tensor([gather_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(h_geom)
+        dist.all_reduce(gk, op=dist.ReduceOp.MAX)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+
+    if rank == 0:
+        R = inp["rays_full_n"]
+        H = int(h_geom.item())
+        value = R * args.steps / (ms_total * 1e-3)
+        e2e = R * args.steps / (ms_e2e * 1e-3)
+        peak, src = peaks()
+        # algorithmic bytes of the dominant kernel (k_gather_bre) per launch, SURVEY.md §8(d):
+        # R*(320+108) + H*112 over this rank's rays (the N*112 term belongs to the build kernels)
+        alg = (R / world) * 428.0 + (H / world) * 112.0
+        achieved = alg / (float(gk.item()) * 1e-3) / 1e9
+        h2d = (inp["photons"].nbytes() if inp["photons"] is not None else 0) + rays.nbytes() * world
+        line = {"metric": "camera-ray gathers/sec (primal+4 gradients)", "value": value, "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, inp, world),
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(R * 27 * 4)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_gather_bre", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": float(gk.item()),
+                             "neighbours_H": H},
+                "phases_ms": {"build": build_ms, "gather": float(gk.item())},
+                "light_paths": inp["n_paths"]}
+        if world == 1 and not args.no_cpu_baseline:
+            inp["full_rays"] = inp["rays"]
+            cb, _, _ = cpu_arm(args, inp, args.cpu_seconds)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    # tensors allocated on the context's stream must go before the stream does
+    # (device tensors and pinned host buffers that were used on it record events on that stream when
+    # they are freed)
+    del out_dev, cnt_dev, gathered, ph_view, counts_max, h_geom, gk, out_host_t, out_host, rays
+    inp.clear()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    # the context (and its stream) is deliberately left to process exit: torch's caching allocators
+    # may still hold blocks tagged with that stream
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgvpm_b200.so")
+# GVPM_B200_LIB: load another build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("GVPM_B200_LIB") or os.path.join(_HERE, "libgvpm_b200.so")
 SYNTH_LIB_PATH = os.path.join(_HERE, "synth", "libgvpm_synth.so")
 
 GVPM_OUT_FLOATS = 27

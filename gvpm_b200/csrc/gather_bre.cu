@@ -18,12 +18,19 @@
 
 namespace gvpm {
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef GVPM_BRE_WARPS
+#define GVPM_BRE_WARPS 4
+#endif
+#ifndef GVPM_BRE_MIN_BLOCKS
+#define GVPM_BRE_MIN_BLOCKS 4
+#endif
+constexpr int kWarpsPerBlock = GVPM_BRE_WARPS;
 constexpr int kQueue = 64;
 
 struct WarpShared {
   float4 ray[GVPM_RAY_FLOAT4];  // 320 B
   uint32_t queue[kQueue];       // 256 B
+  float acc[GVPM_OUT_FLOATS * 32];  // 3456 B: [27][32], column = lane
   uint32_t mask[GVPM_MAX_LEVELS];
   uint32_t base[GVPM_MAX_LEVELS];
 };
@@ -158,15 +165,29 @@ __device__ __forceinline__ bool filters_pass(const GatherParams &P, const BaseRa
   return true;
 }
 
-struct Acc { float a[GVPM_OUT_FLOATS]; };
-
-__device__ __forceinline__ void acc_add(Acc &A, int j, v3 c) {
-  A.a[3 * j] += c.x.v; A.a[3 * j + 1] += c.y.v; A.a[3 * j + 2] += c.z.v;
+// per-warp accumulators live in shared memory, one conflict-free column per lane: [27][32]
+__device__ __forceinline__ void acc_add(float *A, int j, v3 c) {
+  A[(3 * j) * 32] += c.x.v; A[(3 * j + 1) * 32] += c.y.v; A[(3 * j + 2) * 32] += c.z.v;
 }
 
 // One contributing photon: VolumeGradientBREQuery::operator() after the filters.
-__device__ __forceinline__ void bre_photon(const GatherParams &P, const BaseRay &R, const float4 *sray,
-                                           uint32_t pi, Acc &A) {
+__device__ __forceinline__ BaseRay load_base_ray(const float4 *sray) {
+  BaseRay R;
+  const float4 b0 = sray[0], b1 = sray[1], b2 = sray[2], b3 = sray[3];
+  R.o = v3(b0.x, b0.y, b0.z); R.mint = sf(b0.w);
+  R.d = v3(b1.x, b1.y, b1.z); R.maxt = sf(b1.w);
+  R.eye = v3(b2.x, b2.y, b2.z); R.edgeLen = sf(b2.w);
+  R.xi = sf(b3.x);
+  R.px = (int)__float_as_uint(b3.y); R.py = (int)__float_as_uint(b3.z);
+  R.edgeId = (int)__float_as_uint(b3.w);
+  return R;
+}
+
+// Out of line on purpose: the shift code needs ~100 registers, the traversal loop ~40; keeping
+// them in separate register frames leaves the hot loop spill-free.
+__device__ __noinline__ void bre_photon(const GatherParams *Pp, const float4 *sray, uint32_t pi, float *A) {
+  const GatherParams &P = *Pp;
+  const BaseRay R = load_base_ray(sray);
   const uint32_t n = P.tree.n;
   const float4 q0 = ldg4(P.planes + pi);
   const float4 q1 = ldg4(P.planes + (size_t)n + pi);
@@ -196,7 +217,7 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const BaseRay 
   const MediumRec mShift = medium_eval(P, sf(P.cfg.epsilon), tBase);
   const v3 zBase = R.o + tBase * R.d;
 
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     const float4 s0 = sray[4 * (k + 1)], s1 = sray[4 * (k + 1) + 1], s2 = sray[4 * (k + 1) + 2];
     sf weight(1.f);
@@ -333,7 +354,7 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const BaseRay 
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const GatherParams P) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, GVPM_BRE_MIN_BLOCKS) k_gather_bre(const __grid_constant__ GatherParams P) {
   __shared__ WarpShared sh[kWarpsPerBlock];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   WarpShared &S = sh[w];
@@ -348,19 +369,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const Gat
     __syncwarp();
     if (lane < GVPM_RAY_FLOAT4) S.ray[lane] = ldg4(P.rays + (size_t)ray * GVPM_RAY_FLOAT4 + lane);
     __syncwarp();
-    BaseRay R;
-    {
-      float4 b0 = S.ray[0], b1 = S.ray[1], b2 = S.ray[2], b3 = S.ray[3];
-      R.o = v3(b0.x, b0.y, b0.z); R.mint = sf(b0.w);
-      R.d = v3(b1.x, b1.y, b1.z); R.maxt = sf(b1.w);
-      R.eye = v3(b2.x, b2.y, b2.z); R.edgeLen = sf(b2.w);
-      R.xi = sf(b3.x);
-      R.px = (int)__float_as_uint(b3.y); R.py = (int)__float_as_uint(b3.z);
-      R.edgeId = (int)__float_as_uint(b3.w);
-    }
-    Acc A;
+    const BaseRay R = load_base_ray(S.ray);
+    float *A = S.acc + lane;
 #pragma unroll
-    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) A.a[j] = 0.f;
+    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) A[j * 32] = 0.f;
     uint32_t nGeom = 0, nContrib = 0, qn = 0;
     uint64_t dumpBase = 0;
     if (DUMP) dumpBase = P.nbr_offsets[ray];
@@ -377,6 +389,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const Gat
       const float ix = 1.f / R.d.x.v, iy = 1.f / R.d.y.v, iz = 1.f / R.d.z.v;
       const float tlo = R.mint.v - 4.f * pad;
       const float thi = R.edgeLen.v + P.radius + 4.f * pad;
+      const float rpad2 = (P.radius + pad) * (P.radius + pad);
 
       uint32_t cur, base = 0;
       int l = top;
@@ -412,8 +425,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const Gat
           // ---- leaf: lane tests photon (node*32 + lane) with the reference predicate ----
           const uint32_t pi = (node << 5) + lane;
           bool geom = false, contrib = false;
+          float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          bool cand = false;
           if (pi < T.n) {
-            const float4 q0 = ldg4(P.planes + pi);
+            q0 = ldg4(P.planes + pi);
+            // relaxed (FMA) pre-test, conservative by `pad`: only candidates pay for the strictly
+            // rounded predicate below
+            const float cx = q0.x - R.o.x.v, cy = q0.y - R.o.y.v, cz = q0.z - R.o.z.v;
+            const float dd = cx * R.d.x.v + cy * R.d.y.v + cz * R.d.z.v;
+            const float qx = cx - dd * R.d.x.v, qy = cy - dd * R.d.y.v, qz = cz - dd * R.d.z.v;
+            cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tlo;
+          }
+          if (!__any_sync(0xffffffffu, cand)) continue;
+          if (cand) {
             sf tB, pc;
             geom = base_distance(P, R, v3(q0.x, q0.y, q0.z), tB, pc);
             contrib = geom && filters_pass(P, R, __float_as_uint(q0.w));
@@ -440,7 +464,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const Gat
           uint32_t mine = 0;
           if ((uint32_t)lane < take) mine = S.queue[qn + lane];
           __syncwarp();
-          if ((uint32_t)lane < take) bre_photon(P, R, S.ray, mine, A);
+#ifndef GVPM_EXP_SKIP_SHADE
+          if ((uint32_t)lane < take) bre_photon(&P, S.ray, mine, A);
+#endif
           __syncwarp();
         }
         if (flush) break;
@@ -448,21 +474,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) k_gather_bre(const Gat
     }
 
     if (!DUMP) {
+      // warp-level reduction of the per-lane accumulators: lane j < 27 sums row j (32 columns,
+      // rotated start so the 27 lanes hit distinct banks), one coalesced 108-byte store per ray
+      __syncwarp();
+      if (lane < GVPM_OUT_FLOATS) {
+        const float *row = S.acc + lane * 32;
+        float v = 0.f;
 #pragma unroll
-      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) {
-        float v = A.a[j];
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        A.a[j] = v;
+        for (int c = 0; c < 32; ++c) v += row[(c + lane) & 31];
+        P.out[(size_t)ray * GVPM_OUT_FLOATS + lane] = v;
       }
-      if (lane == 0) {
-        float *o = P.out + (size_t)ray * GVPM_OUT_FLOATS;
-#pragma unroll
-        for (int j = 0; j < GVPM_OUT_FLOATS; ++j) o[j] = A.a[j];
-      }
+      __syncwarp();
     }
     if (P.counts && lane == 0) {
       P.counts[2 * (size_t)ray] = nGeom;

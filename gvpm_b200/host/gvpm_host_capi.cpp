@@ -1,0 +1,59 @@
+// gvpm_host_capi.cpp — extern "C" handles on gvpm_host::VolumeGatherB200 so the host-side mirror can be
+// driven from tests (ctypes).  A Mitsuba build would include gvpm_host.hpp directly.
+#include <cstring>
+
+#include "gvpm_host.hpp"
+
+using namespace gvpm_host;
+
+static void set_err(char *err, size_t n, const std::string &m) {
+  if (err && n) { strncpy(err, m.c_str(), n - 1); err[n - 1] = 0; }
+}
+
+extern "C" {
+
+struct gvpm_host_params {
+  int maxDepth, minDepth;
+  double alpha, initialScaleVolume;
+  int volTechnique, lightingInteractionMode;
+  int useMIS, useShiftNull, pathSet, powerHeuristic, use3DKernelReduction;
+  char forceAPA[8];
+};
+
+static GPMConfig to_cfg(const gvpm_host_params *p) {
+  GPMConfig c;
+  c.maxDepth = p->maxDepth; c.minDepth = p->minDepth; c.alpha = p->alpha;
+  c.initialScaleVolume = p->initialScaleVolume; c.volTechnique = p->volTechnique;
+  c.lightingInteractionMode = p->lightingInteractionMode; c.useMIS = p->useMIS;
+  c.useShiftNull = p->useShiftNull; c.pathSet = p->pathSet; c.powerHeuristic = p->powerHeuristic;
+  c.use3DKernelReduction = p->use3DKernelReduction; c.forceAPA = p->forceAPA;
+  return c;
+}
+
+// the radius-reduction schedule alone (no device needed)
+int gvpm_host_scale_apa(double *scale, int it, const gvpm_host_params *p, char *err, size_t errlen) {
+  try { scaleVolumeAPA(*scale, it, to_cfg(p)); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+
+void *gvpm_host_create(int device, int w, int h, const gvpm_host_params *p, const gvpm_medium *m,
+                       float bsphereR, const float *tris, size_t nTris, char *err, size_t errlen) {
+  try { return new VolumeGatherB200(device, w, h, to_cfg(p), *m, bsphereR, tris, nTris); }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return nullptr; }
+}
+void gvpm_host_destroy(void *h) { delete (VolumeGatherB200 *)h; }
+
+int gvpm_host_bre_iteration(void *h, int it, const gvpm_photon_soa *ph, size_t n, const gvpm_ray_soa *rays,
+                            size_t nRays, size_t nbPathVolume, char *err, size_t errlen) {
+  try { ((VolumeGatherB200 *)h)->computeVolumeGradientPhotonBRE(it, ph, n, rays, nRays, nbPathVolume); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+int gvpm_host_gradient(void *h, float *thr, float *gx, float *gy, int useAbs, char *err, size_t errlen) {
+  try { ((VolumeGatherB200 *)h)->computeGradient(thr, gx, gy, useAbs != 0); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+double gvpm_host_scale(void *h) { return ((VolumeGatherB200 *)h)->globalScaleVolume; }
+float gvpm_host_radius(void *h) { return ((VolumeGatherB200 *)h)->currentRadius(); }
+const float *gvpm_host_accumulators(void *h) { return ((VolumeGatherB200 *)h)->accumulators().data(); }
+
+}  // extern "C"

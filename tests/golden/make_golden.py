@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Generates tests/golden/bre_small.npz: oracle (fp32, brute force) outputs for a small seeded case.
+
+The reference cannot be built or imported in this image and ships no fixture for the
+path, so this is a regression pin of OUR restatement, not reference output ("parity unpinned").
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import gvpm_testlib as H  # noqa: E402
+from oracle import binding as ob  # noqa: E402
+
+P = dict(n_photons=3000, w=24, h=16, scale=4.0, seed=1234)
+c = H.make_case(**P)
+res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute", neighbours=True,
+                    threads=2)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "bre_small.npz"), out=res.out, counts=res.counts,
+                    offsets=res.offsets, idx=res.idx, **P)
+print("neighbours", int(res.counts[:, 0].sum()), "contributing", int(res.counts[:, 1].sum()))

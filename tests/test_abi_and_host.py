@@ -1,0 +1,165 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/gvpm_b200.h declares, fails
+loudly without a device, host-side logic (radius reduction, tile sharding incl. a world-size-2 gloo
+run).  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from gvpm_b200 import _native
+    return _native.load_lib()
+
+
+def test_header_symbols_exported(lib):
+    from gvpm_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "gvpm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gvpm_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gvpm_b200.h but not exported"
+    assert declared == set(_native.ABI_SYMBOLS), declared ^ set(_native.ABI_SYMBOLS)
+    assert lib.gvpm_abi_version() == 1
+
+
+def test_struct_sizes_match_header(lib):
+    from gvpm_b200 import _native as N
+    assert C.sizeof(N.Medium) == 36
+    assert C.sizeof(N.Config) == 64
+    assert C.sizeof(N.PhotonSoA) == 13 * 8
+    assert C.sizeof(N.RaySoA) == 16 * 8
+
+
+def test_no_device_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from gvpm_b200.api import Context, GvpmError
+    with pytest.raises(GvpmError, match="no CUDA device|CPU fallback"):
+        Context(0)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (only tests, smoke and bench may)."""
+    pkg = os.path.join(ROOT, "gvpm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower(), f"{os.path.join(dp, f)} mentions the oracle"
+
+
+def _host():
+    import __graft_entry__ as ge
+    ge.build()
+    h = C.CDLL(os.path.join(ROOT, "gvpm_b200", "host", "libgvpm_host.so"))
+    return h
+
+
+class HostParams(C.Structure):
+    _fields_ = [("maxDepth", C.c_int), ("minDepth", C.c_int), ("alpha", C.c_double),
+                ("initialScaleVolume", C.c_double), ("volTechnique", C.c_int),
+                ("lightingInteractionMode", C.c_int), ("useMIS", C.c_int), ("useShiftNull", C.c_int),
+                ("pathSet", C.c_int), ("powerHeuristic", C.c_int), ("use3DKernelReduction", C.c_int),
+                ("forceAPA", C.c_char * 8)]
+
+
+def host_params(**kw):
+    p = HostParams(maxDepth=12, minDepth=0, alpha=0.7, initialScaleVolume=1.0, volTechnique=1,
+                   lightingInteractionMode=(1 << 2) | (1 << 4), useMIS=1, useShiftNull=1, pathSet=1,
+                   powerHeuristic=0, use3DKernelReduction=0, forceAPA=b"")
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.mark.parametrize("tech,force,expo", [(1, b"", 1 / 3), (0, b"", 1 / 2), (1, b"1D", 1.0), (0, b"3D", 1 / 3)])
+def test_scale_volume_apa_schedule(tech, force, expo):
+    """r_{i+1} = r_i * ((i-1+alpha)/i)^(1/d)  (gvpm.cpp:181-215), d by kernel dimension / forceAPA."""
+    h = _host()
+    h.gvpm_host_scale_apa.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(HostParams), C.c_char_p, C.c_size_t]
+    p = host_params(volTechnique=tech, forceAPA=force, alpha=0.7, initialScaleVolume=0.1)
+    s = C.c_double(0.1)
+    want = 0.1
+    err = C.create_string_buffer(256)
+    for it in range(1, 30):
+        assert h.gvpm_host_scale_apa(C.byref(s), it, C.byref(p), err, 256) == 0
+        want *= ((it - 1 + 0.7) / it) ** expo
+        assert abs(s.value - want) < 1e-15 * 10
+    bad = host_params(forceAPA=b"7D")
+    assert h.gvpm_host_scale_apa(C.byref(s), 1, C.byref(bad), err, 256) == -1
+    assert b"No Force APA" in err.value
+
+
+def test_tile_sharding_partitions_every_ray_once():
+    from gvpm_b200 import shard
+    w, h = 100, 70
+    py, px = np.mgrid[0:h, 0:w]
+    px, py = px.ravel(), py.ravel()
+    for world in (1, 2, 4, 8):
+        seen = np.zeros(px.size, dtype=int)
+        sizes = []
+        for r in range(world):
+            idx = shard.local_indices(px, py, w, world, r)
+            seen[idx] += 1
+            sizes.append(len(idx))
+        assert (seen == 1).all()
+        assert max(sizes) - min(sizes) <= 32 * 32 * 2
+    parts = [np.arange(27, dtype=np.float32)[None, :] + shard.local_indices(px, py, w, 2, r)[:, None] for r in (0, 1)]
+    full = shard.assemble(parts, [shard.local_indices(px, py, w, 2, r) for r in (0, 1)], px.size)
+    np.testing.assert_array_equal(full[:, 0], np.arange(px.size))
+    img = shard.to_image(full, px, py, w, h)
+    assert img.shape == (h, w, 27) and img[3, 5, 0] == 3 * w + 5
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from gvpm_b200 import shard
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w, h = 96, 80
+py, px = np.mgrid[0:h, 0:w]; px, py = px.ravel(), py.ravel()
+# replicated "photon set": broadcast from rank 0 like the iteration's photons
+photons = torch.arange(1000, dtype=torch.float32) if rank == 0 else torch.zeros(1000)
+dist.broadcast(photons, src=0)
+assert float(photons.sum()) == 999 * 1000 / 2
+idx = shard.local_indices(px, py, w, world, rank)
+n_pad = torch.tensor([len(idx)]); dist.all_reduce(n_pad, op=dist.ReduceOp.MAX); n_pad = int(n_pad)
+out = torch.zeros(n_pad, 27)
+out[:len(idx)] = torch.from_numpy((px[idx] * 1000 + py[idx]).astype(np.float32))[:, None] + torch.arange(27.0)
+gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+dist.gather(out, gathered, dst=0)
+if rank == 0:
+    lists = [shard.local_indices(px, py, w, world, r) for r in range(world)]
+    full = shard.assemble([g.numpy() for g in gathered], lists, px.size)
+    want = (px * 1000 + py).astype(np.float32)[:, None] + np.arange(27, dtype=np.float32)
+    assert np.array_equal(full, want)
+    print("GLOO_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_gather_world2_gloo(tmp_path):
+    """The N > 1 plumbing of bench.py (broadcast photons, gather per-rank results, reassemble) on
+    2 CPU ranks over gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "GLOO_OK" in res.stdout

@@ -1,0 +1,149 @@
+"""CPU tests of the oracle (oracle/ = test infrastructure).  The reference ships no golden vector for
+this path (parity unpinned), so the restatement is pinned by self-consistency:
+tree traversal vs brute force (mirrors src/tests/test_kd.cpp:133-214), fp64 vs fp32 error budget,
+closed-form identities of the shift mapping, and a committed regression fixture."""
+import os
+
+import numpy as np
+import pytest
+
+import gvpm_testlib as H
+from oracle import binding as ob
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "bre_small.npz")
+
+
+@pytest.fixture(scope="module")
+def case(built):
+    return H.make_case(n_photons=20000, w=40, h=24, scale=2.0)
+
+
+def test_kdtree_traversal_equals_bruteforce(case):
+    """Reference-shaped sliding-midpoint kd layout + AABB hierarchy + stack DFS (kdtree.h:921-1037,
+    gvpm_accel.cpp:35-55, gvpm_accel.h:268-312) against the tree-independent set."""
+    kd = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius,
+                       mode="kdtree", neighbours=True, threads=4)
+    bf = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius,
+                       mode="brute", neighbours=True, threads=4)
+    assert bf.counts[:, 0].sum() > 5000
+    n_diff = 0
+    for i in range(case.rays.n):
+        a, _ = kd.neighbours(i)
+        b, _ = bf.neighbours(i)
+        sa, sb = set(a.tolist()), set(b.tolist())
+        assert sa <= sb, "the tree visited a photon the predicate rejects"
+        n_diff += len(sb - sa)
+    # photons only the brute-force set has lie in the Epsilon-wide sliver at the ray end where the
+    # reference's node test uses ray.maxt = len - Epsilon (gvpm.cpp:1038): DESIGN.md §6
+    assert n_diff <= 1e-3 * bf.counts[:, 0].sum()
+    same = (kd.counts == bf.counts).all(axis=1)
+    H.assert_radiance_close(kd.out[same], bf.out[same], 1e-4, "kd vs brute")
+
+
+def test_fp64_error_budget(case):
+    f32 = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius,
+                        mode="brute", threads=4)
+    f64 = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius,
+                        mode="brute", double=True, threads=4)
+    same = (f32.counts == f64.counts).all(axis=1)
+    assert same.mean() > 0.98  # a photon within rounding of the kernel boundary may flip
+    err = H.rel_err(f32.out[same], f64.out[same])
+    # fp32 rounding itself: the chord pdf 1/(2*deltaT), deltaT = sqrt(r^2 - d^2), amplifies rounding for
+    # photons near the kernel boundary, so a fraction of a percent of the values moves by > 1e-4 between
+    # fp32 and fp64.  This is why GPU parity is defined against the fp32 oracle in the same operation
+    # order (bit-exact sets, ~1e-6 radiance), not against the fp64 variant.
+    assert np.percentile(err, 99) < 1e-4, float(np.percentile(err, 99))
+    assert err.max() < 1e-2, float(err.max())
+
+
+def test_null_shift_identity(built):
+    """Offset ray == base ray: every photon is null-shifted (shift_volume_photon.cpp:776-802), the
+    shifted contribution equals the base one and the MIS weight is 1/(1+1) = 0.5, so
+    shifted_k == weighted_k == primal/2, except where the border rule forces w = 1 (:843-846)."""
+    c = H.make_case(n_photons=20000, w=32, h=16, scale=2.5, perturb=False)
+    r = c.rays
+    r.off_o[:] = np.repeat(r.view("o"), 4, axis=0).reshape(-1)
+    r.off_d[:] = np.repeat(r.view("d"), 4, axis=0).reshape(-1)
+    r.off_len[:] = np.repeat(r.edge_len, 4)
+    r.off_valid[:] = 1
+    res = ob.bre_gather(c.photons, r, c.medium, c.config, c.tri, c.radius, mode="brute", threads=4)
+    out = res.out.reshape(-1, 9, 3)
+    primal = out[:, 0]
+    assert primal.sum() > 0
+    for k in range(4):
+        w = np.full(r.n, 0.5)
+        if k == 1:
+            w[r.px == c.w - 1] = 1.0
+        if k == 2:
+            w[r.py == c.h - 1] = 1.0
+        np.testing.assert_allclose(out[:, 1 + k], primal * w[:, None], rtol=2e-6, atol=0)
+        np.testing.assert_allclose(out[:, 5 + k], primal * w[:, None], rtol=2e-6, atol=0)
+
+
+def test_no_mis_gives_half_weights(built):
+    c = H.make_case(n_photons=15000, w=32, h=16, scale=2.5, use_mis=False)
+    res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute", threads=4)
+    out = res.out.reshape(-1, 9, 3)
+    inner = (c.rays.px < c.w - 1) & (c.rays.py < c.h - 1) & c.rays.view("off_valid").all(axis=1)
+    # weighted_k = w * primal with w in {0.5 (shift ok), 1 (shift failed)}
+    ratio = out[inner, 5:9] / np.maximum(out[inner, 0:1], 1e-30)
+    has = out[inner, 0].sum(axis=1) > 0
+    assert ((ratio[has] > 0.5 - 1e-5) & (ratio[has] < 1 + 1e-5)).all()
+
+
+def test_invalid_offsets_keep_full_weight(built):
+    """validVolumeEdge false => result keeps weight 1, shifted flux 0 (shift_volume_photon.cpp:757-763)."""
+    c = H.make_case(n_photons=15000, w=24, h=16, scale=2.5)
+    c.rays.off_valid[:] = 0
+    res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute", threads=4)
+    out = res.out.reshape(-1, 9, 3)
+    assert not out[:, 1:5].any()
+    for k in range(4):
+        np.testing.assert_allclose(out[:, 5 + k], out[:, 0], rtol=1e-6)
+
+
+def test_chord_pdf_fp32_form_matches_double_form():
+    """1.f / std::max(deltaT * 2.0, 0.0001) evaluated in double then rounded to float
+    (shift_volume_photon.cpp:723) == the fp32 expression the kernel uses."""
+    rng = np.random.default_rng(1)
+    dt = np.concatenate([rng.uniform(0, 1e-2, 200000), rng.uniform(0, 2e-4, 200000),
+                         np.array([0, 5e-5, 4.9999e-5, 5.0001e-5, 1e-4])]).astype(np.float32)
+    ref = (1.0 / np.maximum(dt.astype(np.float64) * 2.0, 0.0001)).astype(np.float32)
+    x2 = dt * np.float32(2)
+    with np.errstate(divide="ignore"):
+        got = np.where(x2 <= np.float32(0.0001), np.float32(10000.0), np.float32(1) / x2).astype(np.float32)
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_depth_and_pathset_filters(built):
+    c = H.make_case(n_photons=15000, w=24, h=16, scale=2.5, max_depth=5)
+    res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute",
+                        neighbours=True, threads=4)
+    for i in range(0, c.rays.n, 7):
+        idx, contributes = res.neighbours(i)
+        if len(idx) == 0:
+            continue
+        depth_ok = c.photons.depth[idx].astype(int) + 2 <= 5
+        parity_ok = (c.photons.path_id[idx] % 2) == ((c.rays.px[i] + c.rays.py[i]) % 2)
+        np.testing.assert_array_equal(contributes, depth_ok & parity_ok)
+
+
+def test_golden_fixture(built):
+    """Regression pin of the oracle itself (fixture made by tests/golden/make_golden.py)."""
+    z = np.load(GOLDEN)
+    c = H.make_case(**{k: z[k].item() for k in ("n_photons", "w", "h", "scale", "seed")})
+    res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute",
+                        neighbours=True, threads=4)
+    np.testing.assert_array_equal(res.counts, z["counts"])
+    np.testing.assert_array_equal(res.idx, z["idx"])
+    H.assert_radiance_close(res.out, z["out"], 1e-5, "golden")
+
+
+def test_synth_is_thread_count_independent(built):
+    import gvpm_b200 as g
+    med = g.make_medium()
+    a, pa = g.synth_photons(5000, med, seed=7, threads=1)
+    b, pb = g.synth_photons(5000, med, seed=7, threads=5)
+    assert pa == pb
+    for name, _, _ in a.FIELDS:
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
