@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_dump_neighbours_bre",
-    "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_launch_count",
+    "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
 ]
 
 _lib = None
@@ -100,6 +100,7 @@ def load_lib():
     lib.gvpm_dump_neighbours_bre.argtypes = [vp, u64p, u32p, C.c_size_t]
     lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]
+    lib.gvpm_last_gather_detail.argtypes = [vp, f32p, f32p, u64p]
     lib.gvpm_launch_count.argtypes = [vp]
     lib.gvpm_launch_count.restype = C.c_uint64
     for name in ABI_SYMBOLS:

@@ -149,5 +149,12 @@ class Context:
         self._ck(self.lib.gvpm_last_timings(self.h, C.byref(b), C.byref(g)), "gvpm_last_timings")
         return b.value, g.value
 
+    def last_gather_detail(self):
+        """-> (traverse_ms, shade_ms, contributing pairs) of the last gather."""
+        t, s, p = C.c_float(), C.c_float(), C.c_uint64()
+        self._ck(self.lib.gvpm_last_gather_detail(self.h, C.byref(t), C.byref(s), C.byref(p)),
+                 "gvpm_last_gather_detail")
+        return t.value, s.value, int(p.value)
+
     def launch_count(self):
         return int(self.lib.gvpm_launch_count(self.h))

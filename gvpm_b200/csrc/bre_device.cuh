@@ -1,0 +1,339 @@
+// bre_device.cuh — device functions of the G-BRE gather shared by the traversal and shading kernels.
+// Reference lines restated here:
+//   neighbour predicate                         gvpm/gvpm_accel.h:293-301
+//   VolumeGradientBREQuery::operator()          gvpm/shift/shift_volume_photon.cpp:658-856
+//   shiftNull / shiftPhotonDiffuse / getShiftPos    shift_volume_photon.cpp:119-158,382-486,858-896
+//   diffuseReconnection                         gvpm/shift/operation/shift_diffuse.cpp:11-134
+//   HomogeneousMedium::eval, phase eval         src/medium/homogeneous.cpp:432-513, src/phase/hg.cpp:107-110
+//   Triangle::rayIntersect                      include/mitsuba/core/triangle.h:109-145
+#pragma once
+#include "gvpm_device.cuh"
+
+namespace gvpm {
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// conservative slab test of a box (inflated by the radius at build time) against the ray interval
+// [tlo, thi]; the rounding/packet pad is folded into the origin: (lo - pad) - o == lo - (o + pad)
+__device__ __forceinline__ bool box_hit(const Tree &t, uint32_t i, float oxp, float oxm, float oyp, float oym,
+                                        float ozp, float ozm, float ix, float iy, float iz, float tlo,
+                                        float thi) {
+  const float4 lo = ldg4(t.lo + i), hi = ldg4(t.hi + i);
+  float t1 = (lo.x - oxp) * ix, t2 = (hi.x - oxm) * ix;
+  float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
+  t1 = (lo.y - oyp) * iy; t2 = (hi.y - oym) * iy;
+  tn = fmaxf(tn, fminf(t1, t2)); tf = fminf(tf, fmaxf(t1, t2));
+  t1 = (lo.z - ozp) * iz; t2 = (hi.z - ozm) * iz;
+  tn = fmaxf(tn, fminf(t1, t2)); tf = fminf(tf, fmaxf(t1, t2));
+  return tn <= tf && tf >= tlo && tn <= thi;
+}
+
+// 1/max(2*deltaT, 0.0001) as the reference evaluates it in double then rounds to Float
+// (shift_volume_photon.cpp:723): identical to this fp32 form (checked exhaustively-ish in tests/).
+__device__ __forceinline__ sf chord_pdf(sf deltaT) {
+  sf x2 = deltaT * sf(2.f);
+  return (x2.v <= 0.0001f) ? sf(10000.f) : sf(1.f) / x2;
+}
+
+struct MediumRec { sf T, pdfSuccess; };
+
+// HomogeneousMedium::eval with equal sigma_t over channels (enforced at gvpm_set_medium as the
+// reference does, homogeneous.cpp:188-201): transmittance is one scalar.
+__device__ __forceinline__ MediumRec medium_eval(const GatherParams &P, sf mint, sf maxt) {
+  MediumRec r;
+  sf distance = maxt - mint;
+  sf st(P.sigma_t[0]);
+  sf tmp(expf(((-st) * distance).v));
+  sf ps = st * tmp;
+  ps = ((ps + ps) + ps) / sf(3.f);
+  r.pdfSuccess = ps * sf(P.sampling_weight);
+  r.T = tmp;
+  if (r.T.v < 1e-20f) r.T = sf(0.f);
+  return r;
+}
+
+__device__ __forceinline__ sf phase_eval(const GatherParams &P, v3 wi, v3 wo) {
+  if (P.phase_type == GVPM_PHASE_ISOTROPIC) return sf(GVPM_INV_FOURPI);
+  sf g(P.hg_g);
+  sf temp = sf(1.f) + g * g + sf(2.f) * g * dot(wi, wo);
+  return sf(GVPM_INV_FOURPI) * (sf(1.f) - g * g) / (temp * ssqrt(temp));
+}
+
+// any-hit over the occluder list, preceded by a conservative plane-distance cull (|d| = 1, so
+// t >= distance from the origin to the triangle's plane)
+__device__ __forceinline__ bool occluded(const GatherParams &P, v3 o, v3 d, sf mint, sf maxt) {
+  if (maxt < mint) return false;
+  for (uint32_t t = 0; t < P.n_tri; ++t) {
+    float4 pl = ldg4(P.tri_plane + t);
+    float dist = fabsf(pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w);
+    if (dist > maxt.v * 1.001f + 1e-5f) continue;
+    const float *tv = P.tri + 9 * t;
+    v3 p0(__ldg(tv), __ldg(tv + 1), __ldg(tv + 2)), p1(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5)),
+        p2(__ldg(tv + 6), __ldg(tv + 7), __ldg(tv + 8));
+    v3 edge1 = p1 - p0, edge2 = p2 - p0;
+    v3 pvec = cross(d, edge2);
+    sf det = dot(edge1, pvec);
+    if (det.v == 0.f) continue;
+    sf inv_det = sf(1.f) / det;
+    v3 tvec = o - p0;
+    sf u = dot(tvec, pvec) * inv_det;
+    if (u.v < 0.f || u.v > 1.f) continue;
+    v3 qvec = cross(tvec, edge1);
+    sf v = dot(d, qvec) * inv_det;
+    if (v.v >= 0.f && (u + v).v <= 1.f) {
+      sf tt = dot(edge2, qvec) * inv_det;
+      if (tt >= mint && tt <= maxt) return true;
+    }
+  }
+  return false;
+}
+
+// coordinateSystemCoherent, src/libcore/util.cpp:592-599
+__device__ __forceinline__ void coherent_frame(v3 n, v3 &b1, v3 &b2) {
+  const sf sign(copysignf(1.0f, n.z.v));
+  const sf a = sf(-1.0f) / (sign + n.z);
+  const sf b = n.x * n.y * a;
+  b1 = v3(sf(1.0f) + sign * n.x * n.x * a, sign * b, -sign * n.x);
+  b2 = v3(b, sign + n.y * n.y * a, -n.y);
+}
+
+struct BaseRay {
+  v3 o, d, eye;
+  sf mint, maxt, edgeLen, xi;
+  int px, py, edgeId;
+};
+
+// works on shared or global (read-only) record pointers
+__device__ __forceinline__ BaseRay load_base_ray(const float4 *rec) {
+  BaseRay R;
+  const float4 b0 = rec[0], b1 = rec[1], b2 = rec[2], b3 = rec[3];
+  R.o = v3(b0.x, b0.y, b0.z); R.mint = sf(b0.w);
+  R.d = v3(b1.x, b1.y, b1.z); R.maxt = sf(b1.w);
+  R.eye = v3(b2.x, b2.y, b2.z); R.edgeLen = sf(b2.w);
+  R.xi = sf(b3.x);
+  R.px = (int)__float_as_uint(b3.y); R.py = (int)__float_as_uint(b3.z);
+  R.edgeId = (int)__float_as_uint(b3.w);
+  return R;
+}
+
+// Neighbour predicate + kernel-chord sampling of the 3-D kernel (gvpm_accel.h:297-301,
+// shift_volume_photon.cpp:707-724).  False when the photon is outside the geometric neighbour set.
+__device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseRay &R, v3 p, sf &tBase,
+                                              sf &pdfCam) {
+  v3 oc = p - R.o;
+  sf dd = dot(oc, R.d);
+  sf distSqr = length_sq((R.o + dd * R.d) - p);
+  if (!(dd > R.mint && distSqr < sf(P.radius_sq))) return false;
+  if (P.cfg.kernel_3d) {
+    sf r(P.radius);
+    sf deltaT = safe_sqrt(r * r - distSqr);
+    sf tminKernel = dd - deltaT;
+    sf tRand = tminKernel + (deltaT * sf(2.f)) * R.xi;
+    if (tRand < R.mint || tRand > R.edgeLen) return false;
+    tBase = tRand;
+    pdfCam = chord_pdf(deltaT);
+  } else {
+    if (dd > R.edgeLen) return false;  // explicit bound, DESIGN.md §6 (bre.cpp:240-242)
+    tBase = dd;
+    pdfCam = sf(1.f);
+  }
+  return true;
+}
+
+// depth / interaction-mode / pathSet filters, shift_volume_photon.cpp:670-697
+__device__ __forceinline__ bool filters_pass(const GatherParams &P, const BaseRay &R, uint32_t meta) {
+  int type = meta & 3, depth = (meta >> 2) & 255, parity = (meta >> 10) & 1;
+  int pathLen = depth + R.edgeId;
+  if (P.cfg.max_depth > 0 && pathLen > P.cfg.max_depth) return false;
+  if (P.cfg.min_depth != 0 && pathLen < P.cfg.min_depth) return false;
+  int m = P.cfg.lighting_mode;
+  if (!((m & GVPM_SURF2MEDIA) && (m & GVPM_MEDIA2MEDIA))) {
+    if (type == GVPM_PARENT_MEDIUM && !(m & GVPM_MEDIA2MEDIA)) return false;
+    if (type != GVPM_PARENT_MEDIUM && !(m & GVPM_SURF2MEDIA)) return false;
+  }
+  if (P.cfg.path_set && parity != ((R.px + R.py) % 2)) return false;
+  return true;
+}
+
+__device__ __forceinline__ void acc_add(float *a, int j, v3 c) {
+  a[3 * j] += c.x.v; a[3 * j + 1] += c.y.v; a[3 * j + 2] += c.z.v;
+}
+
+// One contributing (ray, photon) pair: VolumeGradientBREQuery::operator() after the filters.
+// rec: the ray's 20 float4 (base + 4 offsets); a: 27 accumulators (registers of the caller).
+__device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *__restrict__ rec, uint32_t pi,
+                                           float *a) {
+  const BaseRay R = load_base_ray(rec);
+  const uint32_t n = P.tree.n;
+  const float4 q0 = ldg4(P.planes + pi);
+  const float4 q1 = ldg4(P.planes + (size_t)n + pi);
+  const float4 q2 = ldg4(P.planes + 2 * (size_t)n + pi);
+  const float4 q3 = ldg4(P.planes + 3 * (size_t)n + pi);
+  const float4 q4 = ldg4(P.planes + 4 * (size_t)n + pi);
+  const float4 q5 = ldg4(P.planes + 5 * (size_t)n + pi);
+  const float4 q6 = ldg4(P.planes + 6 * (size_t)n + pi);
+  const v3 p(q0.x, q0.y, q0.z), flux(q1.x, q1.y, q1.z), parent(q2.x, q2.y, q2.z), pred(q3.x, q3.y, q3.z),
+      pn(q4.x, q4.y, q4.z), prefix(q5.x, q5.y, q5.z), albedo(q6.x, q6.y, q6.z);
+  const sf parentPdf(q1.w), edgePdf(q2.w), rrW(q3.w);
+  const int ptype = __float_as_uint(q0.w) & 3;
+  const sf r(P.radius), rr2 = r * r;
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+
+  sf tBase, pdfCam;
+  if (!base_distance(P, R, p, tBase, pdfCam)) return;  // cannot happen for an emitted pair
+  const sf rrG = P.cfg.path_set ? sf(2.f) : sf(1.f);
+  const v3 wi = normalize(parent - p);
+  const MediumRec mBase = medium_eval(P, R.mint, tBase);
+  const v3 contrib = (sigS * flux) * phase_eval(P, wi, -R.d);
+  const v3 baseContrib = (contrib * mBase.T) * R.eye;
+  const sf norm = sf(P.kernel_vol) * pdfCam;
+  const sf recip = sf(1.f) / norm;
+  acc_add(a, 0, (baseContrib * recip) * rrG);
+
+  const MediumRec mShift = medium_eval(P, sf(P.cfg.epsilon), tBase);
+  const v3 zBase = R.o + tBase * R.d;
+
+  // The offset loop is kept rolled (one copy of the shift code); its 4 x (S, weight) results go
+  // through a 16-float local array, and the accumulation below uses static indices.
+  float Sx[4], Sy[4], Sz[4], Wk[4];
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const float4 s0 = ldg4(rec + 4 * (k + 1)), s1 = ldg4(rec + 4 * (k + 1) + 1), s2 = ldg4(rec + 4 * (k + 1) + 2);
+    sf weight(1.f);
+    v3 S(0.f, 0.f, 0.f);
+    if (__float_as_uint(s2.w) != 0u) {  // validVolumeEdge, shift_cameraPath.h:135-140
+      const v3 ok(s0.x, s0.y, s0.z), dk(s1.x, s1.y, s1.z), eyeK(s2.x, s2.y, s2.z);
+      const sf lenK(s0.w), sensor(s1.w);
+      const v3 zShift = ok + tBase * dk;
+      bool done = false;
+      if (P.cfg.use_shift_null && P.cfg.kernel_3d) {  // :776-802
+        sf ZPtoY = length_sq(zShift - p);
+        if (ZPtoY < rr2 && tBase < lenK) {
+          sf dd = dot(p - ok, dk);
+          sf ds = length_sq((ok + dd * dk) - p);
+          sf pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
+          // shiftNull, :119-158
+          v3 c = (sigS * flux) * phase_eval(P, wi, -dk);
+          S = (c * mShift.T) * eyeK;
+          weight = sf(0.5f);
+          if (P.cfg.use_mis) {
+            if (pdfShift.v == 0.f || pdfCam.v == 0.f) weight = sf(1.f);
+            else weight = sf(1.f) / (sf(1.f) + sensor * pdfShift / pdfCam);
+          }
+          done = true;
+        }
+      }
+      if (!done && lenK >= tBase && ptype != GVPM_PARENT_OTHER) {  // :809-838
+        // getShiftPos, :858-896
+        v3 offsetPos = zShift + (p - zBase);
+        if (!P.cfg.kernel_3d) {  // coherent frames for the 2-D kernel, :866-873
+          v3 bs, bt, ns, nt;
+          coherent_frame(R.d, bs, bt);
+          coherent_frame(dk, ns, nt);
+          const v3 v = p - zBase;
+          const v3 local(dot(v, bs), dot(v, bt), dot(v, R.d));
+          offsetPos = zShift + ((ns * local.x + nt * local.y) + dk * local.z);
+        }
+        if (P.cfg.use_shift_null) {
+          sf offDistSqr = length_sq(zBase - offsetPos);
+          if (offDistSqr < rr2) {
+            v3 dShift = zShift - zBase;
+            dShift = dShift / length(dShift);
+            sf cosD = dot(dShift, -(offsetPos - zShift));
+            offsetPos = offsetPos + (dShift * cosD) * sf(2.f);
+          }
+        }
+        sf pdfShift(1.f);
+        if (P.cfg.kernel_3d) {
+          sf dd = dot(offsetPos - ok, dk);
+          sf ds = length_sq((ok + dd * dk) - offsetPos);
+          pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
+        }
+        // shiftPhotonDiffuse, :382-486
+        v3 dProj = offsetPos - parent;
+        sf lProj = length(dProj);
+        dProj = dProj / lProj;
+        bool ok2 = !occluded(P, parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale));
+        if (ok2 && ptype != GVPM_PARENT_MEDIUM) {
+          v3 edgeD = normalize(p - parent);
+          sf signDot = dot(pn, dProj) / dot(pn, edgeD);
+          if (signDot.v < 0.f) ok2 = false;
+        }
+        if (ok2) {
+          // diffuseReconnection, shift_diffuse.cpp:11-134
+          v3 thr(1.f, 1.f, 1.f);
+          sf pdfValue(0.f);
+          bool early = false;
+          if (ptype == GVPM_PARENT_SURFACE) {
+            v3 wiW = normalize(pred - parent);
+            sf cosI = dot(pn, wiW), cosO = dot(pn, dProj);
+            if (cosI.v <= 0.f || cosO.v <= 0.f) {
+              thr = v3(0.f, 0.f, 0.f);
+            } else {
+              thr = thr * (albedo * (sf(GVPM_INV_PI) * cosO));
+              pdfValue = sf(GVPM_INV_PI) * cosO;
+            }
+            if ((cosI * cosI).v <= 0.f || (cosO * cosO).v <= 0.f) early = true;
+          } else if (ptype == GVPM_PARENT_MEDIUM) {
+            v3 pWi = normalize(pred - parent);
+            sf phv = phase_eval(P, pWi, dProj);
+            thr = thr * (sigS * phv);
+            pdfValue = phv;
+          } else {  // emitter sample, emitters/area.cpp:132-150
+            sf dp = dot(dProj, pn);
+            if (dp.v < 0.f) dp = sf(0.f);
+            sf e = sf(GVPM_INV_PI) * dp;
+            thr = thr * v3(e, e, e);
+            pdfValue = e;
+          }
+          sf sPdf(0.f);
+          if (!early) {
+            sf GOp = sf(1.f) / (lProj * lProj);
+            sPdf = pdfValue * GOp;
+            thr = thr * GOp;
+            if (parentPdf.v == 0.f) {
+              sPdf = sf(0.f);
+            } else {
+              thr = thr / parentPdf;
+              thr = thr * rrW;
+              MediumRec mr = medium_eval(P, sf(0.f), lProj);
+              sPdf = sPdf * mr.pdfSuccess;
+              sf te = mr.T * (sf(1.f) / edgePdf);  // Spectrum / Float = * (1/f), spectrum.h:415-425
+              thr = thr * te;
+            }
+          }
+          if (sPdf.v == 0.f) {
+            weight = sf(1.f);
+          } else {
+            v3 photonWeight = prefix * thr;
+            v3 c = (sigS * photonWeight) * phase_eval(P, -dProj, -dk);
+            S = (c * mShift.T) * eyeK;
+            weight = sf(0.5f);
+            if (P.cfg.use_mis) {
+              sf basePdf = pdfCam;
+              basePdf = basePdf * parentPdf;
+              basePdf = basePdf * edgePdf;
+              sf offsetPdf = sPdf * pdfShift;
+              if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
+                weight = sf(1.f);
+              } else {
+                sf q = sensor * (offsetPdf / basePdf);
+                weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
+              }
+            }
+          }
+        }
+      }
+    }
+    if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);
+    Sx[k] = S.x.v; Sy[k] = S.y.v; Sz[k] = S.z.v; Wk[k] = weight.v;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const sf rw = rrG * sf(Wk[k]);
+    acc_add(a, 5 + k, (baseContrib * rw) * recip);
+    acc_add(a, 1 + k, (v3(Sx[k], Sy[k], Sz[k]) * rw) * recip);
+  }
+}
+
+}  // namespace gvpm

@@ -1,5 +1,6 @@
 // gvpm_capi.cu — the extern "C" boundary of include/gvpm_b200.h: context, grow-only device
 // buffers, uploads, build and gather launches.  No torch types, no CPU fallback.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -23,7 +24,8 @@ void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float rad
 void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, uint32_t nParent, float4 *plo,
                         float4 *phi, cudaStream_t st);
 void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st);
-cudaError_t launch_gather_bre(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
+cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
+cudaError_t launch_bre_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
                      cudaStream_t st);
 }  // namespace gvpm
@@ -58,7 +60,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct gvpm_ctx {
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
 
@@ -77,12 +79,16 @@ struct gvpm_ctx {
   Tree tree{};
   float radius = 0.f;
   bool built = false;
+  float extent_hint = 1.f;  // diagonal of the photon AABB (host copy, refreshed lazily)
 
   DevBuf ray_staging, rays;
   uint32_t n_rays = 0;
   bool rays_loaded = false;
 
-  DevBuf out, counts, nbr_offsets, nbr_idx, work_counter;
+  DevBuf out, counts, nbr_offsets, nbr_idx, work_counter, pairs;
+  unsigned long long pair_cap = 0;         // capacity of `pairs` in entries
+  unsigned long long *pair_count_host = nullptr;  // pinned read-back of the pair counter
+  unsigned long long last_pairs = 0;
   DevBuf grad_in, grad_out;
   float build_ms = 0.f, gather_ms = 0.f;
   bool timed_build = false, timed_gather = false;
@@ -198,7 +204,55 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   P.out = out_dev;
   P.counts = counts_dev;
   P.work_counter = ctx->work_counter.as<uint32_t>();
+  P.pair_counter = (unsigned long long *)(ctx->work_counter.as<char>() + 8);
+  P.ray_begin = 0;
+  P.ray_end = ctx->n_rays;
+  P.pairs = ctx->pairs.as<uint2>();
+  P.pair_cap = ctx->pair_cap;
+  // packets whose rays drift apart by more than this are traversed ray by ray (performance only)
+  P.packet_spread_max = 0.f;  // derived in the kernel from the photon bounds
   return GVPM_OK;
+}
+
+// Traverse rays [r0, r1) into the pair list and shade them.  If the pair list overflows, grow it
+// (up to a memory budget) and re-traverse; past the budget, split the ray range.
+int gather_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int depth) {
+  if (r1 <= r0) return GVPM_OK;
+  for (;;) {
+    P.ray_begin = r0;
+    P.ray_end = r1;
+    P.pairs = ctx->pairs.as<uint2>();
+    P.pair_cap = ctx->pair_cap;
+    CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(launch_bre_traverse(P, false, ctx->sm_count, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long total = *ctx->pair_count_host;
+    if (total <= ctx->pair_cap) {
+      ctx->last_pairs += total;
+      CK(launch_bre_shade(P, total, ctx->sm_count, ctx->stream));
+      if (total) ctx->launches += 1;
+      return GVPM_OK;
+    }
+    // overflow: grow within the budget, else halve the range
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+    const unsigned long long want = total + total / 8 + 1024;
+    const unsigned long long budget = (freeB / 2 + ctx->pairs.cap) / sizeof(uint2);
+    if (want <= budget) {
+      CK(ctx->pairs.reserve(want * sizeof(uint2)));
+      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+      continue;
+    }
+    if (r1 - r0 <= 1 || depth > 40) return fail(ctx, GVPM_ERR_CUDA, "pair list does not fit in device memory");
+    const uint32_t mid = r0 + (r1 - r0) / 2;
+    int rc = gather_range(ctx, P, r0, mid, depth + 1);
+    if (rc) return rc;
+    return gather_range(ctx, P, mid, r1, depth + 1);
+  }
 }
 
 int gather_common(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
@@ -206,8 +260,17 @@ int gather_common(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
   int rc = fill_params(ctx, P, out_dev, counts_dev);
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CK(launch_gather_bre(P, false, ctx->sm_count, ctx->stream));
-  ctx->launches += 1;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    if (ctx->pair_cap == 0) {
+      CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 16 * n) * sizeof(uint2)));
+      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    }
+    CK(cudaMemsetAsync(out_dev, 0, n * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
+    ctx->last_pairs = 0;
+    rc = gather_range(ctx, P, 0, (uint32_t)n, 0);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed_gather = true;
   return GVPM_OK;
@@ -251,6 +314,7 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
   ctx->work_counter.reserve(256);
+  cudaHostAlloc((void **)&ctx->pair_count_host, sizeof(unsigned long long), cudaHostAllocDefault);
   ctx->bounds.reserve(256);
   ctx->bounds_partial.reserve(1024 * 6 * sizeof(float));
   *out = ctx;
@@ -264,7 +328,8 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
                     &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
-                    &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out};
+                    &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs};
+  if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->stream);
@@ -530,7 +595,8 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   if (rc) return rc;
   P.nbr_offsets = ctx->nbr_offsets.as<uint64_t>();
   P.nbr_idx = ctx->nbr_idx.as<uint32_t>();
-  CK(launch_gather_bre(P, true, ctx->sm_count, ctx->stream));
+  CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+  CK(launch_bre_traverse(P, true, ctx->sm_count, ctx->stream));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -563,6 +629,20 @@ int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {
   if (ctx->timed_gather) CK(cudaEventElapsedTime(&ctx->gather_ms, ctx->ev[2], ctx->ev[3]));
   if (build_ms) *build_ms = ctx->build_ms;
   if (gather_ms) *gather_ms = ctx->gather_ms;
+  return GVPM_OK;
+}
+
+int gvpm_last_gather_detail(gvpm_ctx *ctx, float *traverse_ms, float *shade_ms, uint64_t *pairs) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  float t = 0.f, s = 0.f;
+  if (ctx->timed_gather && ctx->n_rays) {
+    CK(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
+    CK(cudaEventElapsedTime(&s, ctx->ev[5], ctx->ev[3]));
+  }
+  if (traverse_ms) *traverse_ms = t;
+  if (shade_ms) *shade_ms = s;
+  if (pairs) *pairs = ctx->last_pairs;
   return GVPM_OK;
 }
 

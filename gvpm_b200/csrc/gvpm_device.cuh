@@ -130,6 +130,16 @@ struct GatherParams {
   const uint64_t *nbr_offsets;
   uint32_t *nbr_idx;
   uint32_t *work_counter;
+  // traversal -> shading hand-off: (ray index, sorted photon slot) pairs
+  uint32_t ray_begin, ray_end;        // ray range of this launch
+  uint2 *pairs;
+  unsigned long long pair_cap;
+  unsigned long long *pair_counter;   // pairs emitted (may exceed pair_cap: overflow)
+  float packet_spread_max;            // packets wider than this are traversed ray by ray
 };
+
+#ifndef GVPM_PACKET
+#define GVPM_PACKET 4  // camera rays per traversal warp
+#endif
 
 }  // namespace gvpm

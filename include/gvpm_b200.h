@@ -201,6 +201,9 @@ int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use
 
 /* ---- timing of the last build / gather on the context's stream (CUDA events, ms) ----- */
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms);
+/* split of the last gather: traversal kernel, shading kernel (of the last ray range), and the number of
+ * contributing (ray, photon) pairs the traversal handed to the shading kernel */
+int gvpm_last_gather_detail(gvpm_ctx *ctx, float *traverse_ms, float *shade_ms, uint64_t *pairs);
 /* number of kernel launches issued by this context since creation */
 uint64_t gvpm_launch_count(const gvpm_ctx *ctx);
 

@@ -132,7 +132,9 @@ def test_properties_at_scale(built):
         o, _ = ctx.gather_bre()
         parts.append(o)
         lists.append(idx)
-    np.testing.assert_array_equal(shard.assemble(parts, lists, c.rays.n), out)
+    # (per-ray sums are folded by a segmented warp scan + float atomics whose grouping depends on where
+    #  a ray's pairs land in the pair list: equal up to fp32 summation order, not bitwise)
+    H.assert_radiance_close(shard.assemble(parts, lists, c.rays.n), out, 1e-5, "sharding invariance")
     # (2)
     ph2 = c.photons.copy()
     ph2.flux[:] *= np.float32(2)
@@ -142,7 +144,7 @@ def test_properties_at_scale(built):
     ctx.upload_rays(c.rays)
     out2, counts2 = ctx.gather_bre()
     np.testing.assert_array_equal(counts2, counts)
-    np.testing.assert_array_equal(out2, out * np.float32(2))
+    H.assert_radiance_close(out2, out * np.float32(2), 1e-5, "linearity in the flux")
     # (3)
     perm = np.random.default_rng(5).permutation(c.photons.n)
     ctx.upload_photons(c.photons.take(perm))

@@ -34,16 +34,20 @@ ctx.set_occluders(g.synth_occluders())
 ctx.upload_photons(ph)
 ctx.upload_rays(rays)
 r = g.bre_radius(a.scale)
-bs, gs = [], []
+bs, gs, ts, ss = [], [], [], []
 for i in range(a.reps + 1):
     ctx.build_points(r)
     ctx.gather_bre_device()
     b, gm = ctx.last_timings()
+    t, s, pairs = ctx.last_gather_detail()
     if i:
         bs.append(b)
         gs.append(gm)
+        ts.append(t)
+        ss.append(s)
 out, counts = ctx.gather_bre()
 print(f"lib={os.environ.get('GVPM_B200_LIB', 'default')} photons={a.photons} rays={rays.n} scale={a.scale} "
-      f"build_ms={np.mean(bs):.3f} gather_ms={np.mean(gs):.3f} rays/s={rays.n / np.mean(gs) * 1e3:.3e} "
+      f"build_ms={np.mean(bs):.3f} gather_ms={np.mean(gs):.3f} (traverse {np.mean(ts):.3f} shade {np.mean(ss):.3f} "
+      f"pairs {pairs}) rays/s={rays.n / np.mean(gs) * 1e3:.3e} "
       f"H={int(counts[:, 0].sum())} C={int(counts[:, 1].sum())} checksum={float(out.astype(np.float64).sum()):.6e}")
 ctx.close()
