@@ -385,10 +385,25 @@ size_t gvpm_synth_rays(uint64_t seed, int w, int h, int block, int y0, int y1, f
   };
   size_t n = 0;
   const int off[4][2] = {{-1, 0}, {1, 0}, {0, 1}, {0, -1}};
+  // block < 0: |block| x |block| blocks (power of two) walked in Z-order, so 4 consecutive rays are a
+  // 2x2 pixel quad, 16 a 4x4 tile, ... (ray order is the caller's choice; results are per ray)
+  const bool zorder = block < 0;
+  if (zorder) block = -block;
+  auto compact1by1 = [](uint32_t v) {
+    v &= 0x55555555u;
+    v = (v ^ (v >> 1)) & 0x33333333u;
+    v = (v ^ (v >> 2)) & 0x0f0f0f0fu;
+    v = (v ^ (v >> 4)) & 0x00ff00ffu;
+    v = (v ^ (v >> 8)) & 0x0000ffffu;
+    return (int)v;
+  };
   for (int by = y0; by < y1; by += block)
     for (int bx = 0; bx < w; bx += block)
-      for (int y = by; y < std::min(by + block, y1); ++y)
-        for (int x = bx; x < std::min(bx + block, w); ++x) {
+      for (int i = 0; i < block * block; ++i) {
+        const int x = bx + (zorder ? compact1by1((uint32_t)i) : i % block);
+        const int y = by + (zorder ? compact1by1((uint32_t)i >> 1) : i / block);
+        if (x >= w || y >= y1) continue;
+        {
           Rng rng(seed ^ 0x9E3779B97F4A7C15ULL, (uint64_t)y * (uint64_t)w + (uint64_t)x);
           float sx = x + rng.uniform(), sy = y + rng.uniform();
           Vec ro, rd;
@@ -417,6 +432,7 @@ size_t gvpm_synth_rays(uint64_t seed, int w, int h, int block, int y0, int y1, f
           }
           ++n;
         }
+      }
   return n;
 }
 
