@@ -5,8 +5,8 @@ mirror of the reference's gather drivers (host.py, host/), the flattened record 
 synthetic-input generator.  There is no CPU fallback: see _native.load_lib().
 """
 from . import _native
-from .records import (PhotonSet, RaySet, bre_radius, make_config, make_medium, synth_occluders,
-                      synth_photons, synth_rays)
+from .records import (PhotonSet, RaySet, VpmSampleSet, bre_radius, make_config, make_medium, synth_occluders,
+                      synth_photons, synth_rays, synth_vpm_samples)
 
 __all__ = ["_native", "PhotonSet", "RaySet", "bre_radius", "make_config", "make_medium",
-           "synth_occluders", "synth_photons", "synth_rays"]
+           "synth_occluders", "synth_photons", "synth_rays", "VpmSampleSet", "synth_vpm_samples"]

@@ -52,6 +52,11 @@ class RaySoA(C.Structure):
                 ("off_eye", f32p), ("off_sensor", f32p)]
 
 
+class VpmSampleSoA(C.Structure):
+    _fields_ = [("ray", u32p), ("t", f32p), ("transmittance", f32p), ("pdf_success", f32p),
+                ("pdf_sel", f32p), ("radius", f32p)]
+
+
 # every symbol include/gvpm_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
@@ -60,6 +65,7 @@ ABI_SYMBOLS = [
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
+    "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
 ]
 
 _lib = None
@@ -101,6 +107,9 @@ def load_lib():
     lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]
     lib.gvpm_last_gather_detail.argtypes = [vp, f32p, f32p, u64p]
+    lib.gvpm_upload_vpm_samples.argtypes = [vp, C.POINTER(VpmSampleSoA), C.c_size_t]
+    lib.gvpm_gather_vpm.argtypes = [vp, C.c_int, f32p, u32p, u32p]
+    lib.gvpm_dump_neighbours_vpm.argtypes = [vp, C.c_int, u64p, u32p, C.c_size_t]
     lib.gvpm_launch_count.argtypes = [vp]
     lib.gvpm_launch_count.restype = C.c_uint64
     for name in ABI_SYMBOLS:
@@ -126,5 +135,8 @@ def load_synth():
     s.gvpm_synth_rays.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                   C.c_float, C.c_float, C.POINTER(RaySoA)]
     s.gvpm_synth_rays.restype = C.c_size_t
+    s.gvpm_synth_vpm_samples.argtypes = [C.c_uint64, C.POINTER(RaySoA), C.c_size_t, C.c_int, C.c_int,
+                                         C.POINTER(Medium), C.c_float, f32p, C.POINTER(VpmSampleSoA)]
+    s.gvpm_synth_vpm_samples.restype = C.c_size_t
     _synth = s
     return s

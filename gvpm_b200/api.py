@@ -28,6 +28,7 @@ class Context:
         self.h = h
         self.n_rays = 0
         self.n_photons = 0
+        self.n_samples = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -127,6 +128,39 @@ class Context:
             seg = np.repeat(np.arange(n, dtype=np.uint64), np.diff(offsets).astype(np.int64))
             order = np.lexsort((idx & np.uint32(0x7FFFFFFF), seg))
             idx = idx[order]
+        return offsets, idx
+
+    # ---- G-VPM
+    def upload_vpm_samples(self, samples):
+        cs = samples.as_c()
+        self._ck(self.lib.gvpm_upload_vpm_samples(self.h, C.byref(cs), samples.n), "gvpm_upload_vpm_samples")
+        self.n_samples = samples.n
+
+    def gather_vpm(self, nb_camera_samples):
+        """-> (out [n_rays,27], mvol [n_rays] uint32, sample_counts [n_samples,2] uint32), on the host."""
+        n, ns = self.n_rays, self.n_samples
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        mvol = np.empty(n, dtype=np.uint32)
+        sc = np.empty(ns * 2, dtype=np.uint32)
+        self._ck(self.lib.gvpm_gather_vpm(self.h, nb_camera_samples, out.ctypes.data_as(N.f32p),
+                                          mvol.ctypes.data_as(N.u32p), sc.ctypes.data_as(N.u32p)), "gvpm_gather_vpm")
+        return out.reshape(n, N.GVPM_OUT_FLOATS), mvol, sc.reshape(ns, 2)
+
+    def dump_neighbours_vpm(self, nb_camera_samples):
+        ns = self.n_samples
+        offsets = np.zeros(ns + 1, dtype=np.uint64)
+        rc = self.lib.gvpm_dump_neighbours_vpm(self.h, nb_camera_samples, offsets.ctypes.data_as(N.u64p), None, 0)
+        total = int(offsets[ns])
+        if rc != 0 and total == 0:
+            self._ck(rc, "gvpm_dump_neighbours_vpm")
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            self._ck(self.lib.gvpm_dump_neighbours_vpm(self.h, nb_camera_samples, offsets.ctypes.data_as(N.u64p),
+                                                       idx.ctypes.data_as(N.u32p), total), "gvpm_dump_neighbours_vpm")
+        idx = idx[:total]
+        if total:
+            seg = np.repeat(np.arange(ns, dtype=np.uint64), np.diff(offsets).astype(np.int64))
+            idx = idx[np.lexsort((idx & np.uint32(0x7FFFFFFF), seg))]
         return offsets, idx
 
     def compute_gradient(self, acc, w, h, use_abs=False):

@@ -159,11 +159,13 @@ __device__ __forceinline__ void acc_add(float *a, int j, v3 c) {
   a[3 * j] += c.x.v; a[3 * j + 1] += c.y.v; a[3 * j + 2] += c.z.v;
 }
 
-// One contributing (ray, photon) pair: VolumeGradientBREQuery::operator() after the filters.
-// rec: the ray's 20 float4 (base + 4 offsets); a: 27 accumulators (registers of the caller).
-__device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *__restrict__ rec, uint32_t pi,
-                                           float *a) {
-  const BaseRay R = load_base_ray(rec);
+// A photon record as the shift code reads it (7 x 128-bit loads)
+struct PhotonRec {
+  v3 p, flux, parent, pred, pn, prefix, albedo;
+  sf parentPdf, edgePdf, rrW;
+  int ptype;
+};
+__device__ __forceinline__ PhotonRec load_photon(const GatherParams &P, uint32_t pi) {
   const uint32_t n = P.tree.n;
   const float4 q0 = ldg4(P.planes + pi);
   const float4 q1 = ldg4(P.planes + (size_t)n + pi);
@@ -172,19 +174,145 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
   const float4 q4 = ldg4(P.planes + 4 * (size_t)n + pi);
   const float4 q5 = ldg4(P.planes + 5 * (size_t)n + pi);
   const float4 q6 = ldg4(P.planes + 6 * (size_t)n + pi);
-  const v3 p(q0.x, q0.y, q0.z), flux(q1.x, q1.y, q1.z), parent(q2.x, q2.y, q2.z), pred(q3.x, q3.y, q3.z),
-      pn(q4.x, q4.y, q4.z), prefix(q5.x, q5.y, q5.z), albedo(q6.x, q6.y, q6.z);
-  const sf parentPdf(q1.w), edgePdf(q2.w), rrW(q3.w);
-  const int ptype = __float_as_uint(q0.w) & 3;
+  PhotonRec ph;
+  ph.p = v3(q0.x, q0.y, q0.z); ph.flux = v3(q1.x, q1.y, q1.z); ph.parent = v3(q2.x, q2.y, q2.z);
+  ph.pred = v3(q3.x, q3.y, q3.z); ph.pn = v3(q4.x, q4.y, q4.z); ph.prefix = v3(q5.x, q5.y, q5.z);
+  ph.albedo = v3(q6.x, q6.y, q6.z);
+  ph.parentPdf = sf(q1.w); ph.edgePdf = sf(q2.w); ph.rrW = sf(q3.w);
+  ph.ptype = __float_as_uint(q0.w) & 3;
+  return ph;
+}
+
+// AbstractVolumeGradientRecord::shiftNull, shift_volume_photon.cpp:119-158 (jacobian = 1)
+__device__ __forceinline__ void shift_null(const GatherParams &P, const PhotonRec &ph, v3 wi, v3 dk, v3 eyeK,
+                                           sf sensor, sf Tshift, sf pdfBase, sf pdfShift, v3 &S, sf &weight) {
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+  v3 c = (sigS * ph.flux) * phase_eval(P, wi, -dk);
+  S = (c * Tshift) * eyeK;
+  weight = sf(0.5f);
+  if (P.cfg.use_mis) {
+    if (pdfShift.v == 0.f || pdfBase.v == 0.f) weight = sf(1.f);
+    else weight = sf(1.f) / (sf(1.f) + sensor * pdfShift / pdfBase);
+  }
+}
+
+// AbstractVolumeGradientRecord::getShiftPos, shift_volume_photon.cpp:858-896
+__device__ __forceinline__ v3 get_shift_pos(const GatherParams &P, sf rr2, v3 p, v3 zBase, v3 zShift, v3 dBase,
+                                            v3 dk, bool coherent) {
+  v3 offsetPos = zShift + (p - zBase);
+  if (coherent) {  // coherent frames for the 2-D kernel, :866-873
+    v3 bs, bt, ns, nt;
+    coherent_frame(dBase, bs, bt);
+    coherent_frame(dk, ns, nt);
+    const v3 v = p - zBase;
+    const v3 local(dot(v, bs), dot(v, bt), dot(v, dBase));
+    offsetPos = zShift + ((ns * local.x + nt * local.y) + dk * local.z);
+  }
+  if (P.cfg.use_shift_null) {
+    sf offDistSqr = length_sq(zBase - offsetPos);
+    if (offDistSqr < rr2) {
+      v3 dShift = zShift - zBase;
+      dShift = dShift / length(dShift);
+      sf cosD = dot(dShift, -(offsetPos - zShift));
+      offsetPos = offsetPos + (dShift * cosD) * sf(2.f);
+    }
+  }
+  return offsetPos;
+}
+
+// shiftPhoton -> shiftPhotonDiffuse (shift_volume_photon.cpp:49-117,382-486) with diffuseReconnection
+// (shift_diffuse.cpp:11-134) inlined for {area emitter, diffuse surface, medium} parents.
+// S, weight keep their defaults (0, 1) when the shift fails.
+__device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, const PhotonRec &ph, v3 offsetPos,
+                                                     v3 dk, v3 eyeK, sf sensor, sf Tshift, sf pdfBase,
+                                                     sf pdfShift, v3 &S, sf &weight) {
+  if (ph.ptype == GVPM_PARENT_OTHER) return;  // manifold shift: out of scope, fails like useManifold=false
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+  v3 dProj = offsetPos - ph.parent;
+  sf lProj = length(dProj);
+  dProj = dProj / lProj;
+  if (occluded(P, ph.parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale))) return;
+  if (ph.ptype != GVPM_PARENT_MEDIUM) {  // :404-412
+    v3 edgeD = normalize(ph.p - ph.parent);
+    sf signDot = dot(ph.pn, dProj) / dot(ph.pn, edgeD);
+    if (signDot.v < 0.f) return;
+  }
+  // diffuseReconnection
+  v3 thr(1.f, 1.f, 1.f);
+  sf pdfValue(0.f);
+  bool early = false;
+  if (ph.ptype == GVPM_PARENT_SURFACE) {  // bsdfs/diffuse.cpp:110-127
+    v3 wiW = normalize(ph.pred - ph.parent);
+    sf cosI = dot(ph.pn, wiW), cosO = dot(ph.pn, dProj);
+    if (cosI.v <= 0.f || cosO.v <= 0.f) {
+      thr = v3(0.f, 0.f, 0.f);
+    } else {
+      thr = thr * (ph.albedo * (sf(GVPM_INV_PI) * cosO));
+      pdfValue = sf(GVPM_INV_PI) * cosO;
+    }
+    if ((cosI * cosI).v <= 0.f || (cosO * cosO).v <= 0.f) early = true;
+  } else if (ph.ptype == GVPM_PARENT_MEDIUM) {
+    v3 pWi = normalize(ph.pred - ph.parent);
+    sf phv = phase_eval(P, pWi, dProj);
+    thr = thr * (sigS * phv);
+    pdfValue = phv;
+  } else {  // emitter sample, emitters/area.cpp:132-150
+    sf dp = dot(dProj, ph.pn);
+    if (dp.v < 0.f) dp = sf(0.f);
+    sf e = sf(GVPM_INV_PI) * dp;
+    thr = thr * v3(e, e, e);
+    pdfValue = e;
+  }
+  sf sPdf(0.f);
+  if (!early) {
+    sf GOp = sf(1.f) / (lProj * lProj);
+    sPdf = pdfValue * GOp;
+    thr = thr * GOp;
+    if (ph.parentPdf.v == 0.f) {
+      sPdf = sf(0.f);
+    } else {
+      thr = thr / ph.parentPdf;
+      thr = thr * ph.rrW;
+      MediumRec mr = medium_eval(P, sf(0.f), lProj);
+      sPdf = sPdf * mr.pdfSuccess;
+      sf te = mr.T * (sf(1.f) / ph.edgePdf);  // Spectrum / Float = * (1/f), spectrum.h:415-425
+      thr = thr * te;
+    }
+  }
+  if (sPdf.v == 0.f) { weight = sf(1.f); return; }
+  v3 photonWeight = ph.prefix * thr;
+  v3 c = (sigS * photonWeight) * phase_eval(P, -dProj, -dk);
+  S = (c * Tshift) * eyeK;
+  weight = sf(0.5f);
+  if (P.cfg.use_mis) {
+    sf basePdf = pdfBase;
+    basePdf = basePdf * ph.parentPdf;
+    basePdf = basePdf * ph.edgePdf;
+    sf offsetPdf = sPdf * pdfShift;
+    if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
+      weight = sf(1.f);
+    } else {
+      sf q = sensor * (offsetPdf / basePdf);
+      weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
+    }
+  }
+}
+
+// One contributing (ray, photon) pair: VolumeGradientBREQuery::operator() after the filters.
+// rec: the ray's 20 float4 (base + 4 offsets); a: 27 accumulators (registers of the caller).
+__device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *__restrict__ rec, uint32_t pi,
+                                           float *a) {
+  const BaseRay R = load_base_ray(rec);
+  const PhotonRec ph = load_photon(P, pi);
   const sf r(P.radius), rr2 = r * r;
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
 
   sf tBase, pdfCam;
-  if (!base_distance(P, R, p, tBase, pdfCam)) return;  // cannot happen for an emitted pair
+  if (!base_distance(P, R, ph.p, tBase, pdfCam)) return;  // cannot happen for an emitted pair
   const sf rrG = P.cfg.path_set ? sf(2.f) : sf(1.f);
-  const v3 wi = normalize(parent - p);
+  const v3 wi = normalize(ph.parent - ph.p);
   const MediumRec mBase = medium_eval(P, R.mint, tBase);
-  const v3 contrib = (sigS * flux) * phase_eval(P, wi, -R.d);
+  const v3 contrib = (sigS * ph.flux) * phase_eval(P, wi, -R.d);
   const v3 baseContrib = (contrib * mBase.T) * R.eye;
   const sf norm = sf(P.kernel_vol) * pdfCam;
   const sf recip = sf(1.f) / norm;
@@ -207,122 +335,24 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
       const v3 zShift = ok + tBase * dk;
       bool done = false;
       if (P.cfg.use_shift_null && P.cfg.kernel_3d) {  // :776-802
-        sf ZPtoY = length_sq(zShift - p);
+        sf ZPtoY = length_sq(zShift - ph.p);
         if (ZPtoY < rr2 && tBase < lenK) {
-          sf dd = dot(p - ok, dk);
-          sf ds = length_sq((ok + dd * dk) - p);
+          sf dd = dot(ph.p - ok, dk);
+          sf ds = length_sq((ok + dd * dk) - ph.p);
           sf pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
-          // shiftNull, :119-158
-          v3 c = (sigS * flux) * phase_eval(P, wi, -dk);
-          S = (c * mShift.T) * eyeK;
-          weight = sf(0.5f);
-          if (P.cfg.use_mis) {
-            if (pdfShift.v == 0.f || pdfCam.v == 0.f) weight = sf(1.f);
-            else weight = sf(1.f) / (sf(1.f) + sensor * pdfShift / pdfCam);
-          }
+          shift_null(P, ph, wi, dk, eyeK, sensor, mShift.T, pdfCam, pdfShift, S, weight);
           done = true;
         }
       }
-      if (!done && lenK >= tBase && ptype != GVPM_PARENT_OTHER) {  // :809-838
-        // getShiftPos, :858-896
-        v3 offsetPos = zShift + (p - zBase);
-        if (!P.cfg.kernel_3d) {  // coherent frames for the 2-D kernel, :866-873
-          v3 bs, bt, ns, nt;
-          coherent_frame(R.d, bs, bt);
-          coherent_frame(dk, ns, nt);
-          const v3 v = p - zBase;
-          const v3 local(dot(v, bs), dot(v, bt), dot(v, R.d));
-          offsetPos = zShift + ((ns * local.x + nt * local.y) + dk * local.z);
-        }
-        if (P.cfg.use_shift_null) {
-          sf offDistSqr = length_sq(zBase - offsetPos);
-          if (offDistSqr < rr2) {
-            v3 dShift = zShift - zBase;
-            dShift = dShift / length(dShift);
-            sf cosD = dot(dShift, -(offsetPos - zShift));
-            offsetPos = offsetPos + (dShift * cosD) * sf(2.f);
-          }
-        }
+      if (!done && lenK >= tBase) {  // :809-838
+        const v3 offsetPos = get_shift_pos(P, rr2, ph.p, zBase, zShift, R.d, dk, !P.cfg.kernel_3d);
         sf pdfShift(1.f);
         if (P.cfg.kernel_3d) {
           sf dd = dot(offsetPos - ok, dk);
           sf ds = length_sq((ok + dd * dk) - offsetPos);
           pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
         }
-        // shiftPhotonDiffuse, :382-486
-        v3 dProj = offsetPos - parent;
-        sf lProj = length(dProj);
-        dProj = dProj / lProj;
-        bool ok2 = !occluded(P, parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale));
-        if (ok2 && ptype != GVPM_PARENT_MEDIUM) {
-          v3 edgeD = normalize(p - parent);
-          sf signDot = dot(pn, dProj) / dot(pn, edgeD);
-          if (signDot.v < 0.f) ok2 = false;
-        }
-        if (ok2) {
-          // diffuseReconnection, shift_diffuse.cpp:11-134
-          v3 thr(1.f, 1.f, 1.f);
-          sf pdfValue(0.f);
-          bool early = false;
-          if (ptype == GVPM_PARENT_SURFACE) {
-            v3 wiW = normalize(pred - parent);
-            sf cosI = dot(pn, wiW), cosO = dot(pn, dProj);
-            if (cosI.v <= 0.f || cosO.v <= 0.f) {
-              thr = v3(0.f, 0.f, 0.f);
-            } else {
-              thr = thr * (albedo * (sf(GVPM_INV_PI) * cosO));
-              pdfValue = sf(GVPM_INV_PI) * cosO;
-            }
-            if ((cosI * cosI).v <= 0.f || (cosO * cosO).v <= 0.f) early = true;
-          } else if (ptype == GVPM_PARENT_MEDIUM) {
-            v3 pWi = normalize(pred - parent);
-            sf phv = phase_eval(P, pWi, dProj);
-            thr = thr * (sigS * phv);
-            pdfValue = phv;
-          } else {  // emitter sample, emitters/area.cpp:132-150
-            sf dp = dot(dProj, pn);
-            if (dp.v < 0.f) dp = sf(0.f);
-            sf e = sf(GVPM_INV_PI) * dp;
-            thr = thr * v3(e, e, e);
-            pdfValue = e;
-          }
-          sf sPdf(0.f);
-          if (!early) {
-            sf GOp = sf(1.f) / (lProj * lProj);
-            sPdf = pdfValue * GOp;
-            thr = thr * GOp;
-            if (parentPdf.v == 0.f) {
-              sPdf = sf(0.f);
-            } else {
-              thr = thr / parentPdf;
-              thr = thr * rrW;
-              MediumRec mr = medium_eval(P, sf(0.f), lProj);
-              sPdf = sPdf * mr.pdfSuccess;
-              sf te = mr.T * (sf(1.f) / edgePdf);  // Spectrum / Float = * (1/f), spectrum.h:415-425
-              thr = thr * te;
-            }
-          }
-          if (sPdf.v == 0.f) {
-            weight = sf(1.f);
-          } else {
-            v3 photonWeight = prefix * thr;
-            v3 c = (sigS * photonWeight) * phase_eval(P, -dProj, -dk);
-            S = (c * mShift.T) * eyeK;
-            weight = sf(0.5f);
-            if (P.cfg.use_mis) {
-              sf basePdf = pdfCam;
-              basePdf = basePdf * parentPdf;
-              basePdf = basePdf * edgePdf;
-              sf offsetPdf = sPdf * pdfShift;
-              if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
-                weight = sf(1.f);
-              } else {
-                sf q = sensor * (offsetPdf / basePdf);
-                weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
-              }
-            }
-          }
-        }
+        shift_photon_diffuse(P, ph, offsetPos, dk, eyeK, sensor, mShift.T, pdfCam, pdfShift, S, weight);
       }
     }
     if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);

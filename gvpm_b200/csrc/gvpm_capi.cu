@@ -26,6 +26,8 @@ void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, u
 void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st);
 cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_bre_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
+cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
+cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
                      cudaStream_t st);
 }  // namespace gvpm
@@ -89,6 +91,10 @@ struct gvpm_ctx {
   unsigned long long pair_cap = 0;         // capacity of `pairs` in entries
   unsigned long long *pair_count_host = nullptr;  // pinned read-back of the pair counter
   unsigned long long last_pairs = 0;
+  DevBuf samples, sample_counts, mvol;  // G-VPM distance samples
+  uint32_t n_samples = 0;
+  bool samples_loaded = false;
+  float sample_radius_max = 0.f;
   DevBuf grad_in, grad_out;
   float build_ms = 0.f, gather_ms = 0.f;
   bool timed_build = false, timed_gather = false;
@@ -328,7 +334,8 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
                     &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
-                    &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs};
+                    &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs,
+                    &ctx->samples, &ctx->sample_counts, &ctx->mvol};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -597,6 +604,126 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   P.nbr_idx = ctx->nbr_idx.as<uint32_t>();
   CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
   CK(launch_bre_traverse(P, true, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+// ---- G-VPM -------------------------------------------------------------------------------------
+int gvpm_upload_vpm_samples(gvpm_ctx *ctx, const gvpm_vpm_sample_soa *s, size_t n) {
+  if (!ctx || (n && !s) || n > 0xfffffff0u) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ctx->n_samples = (uint32_t)n;
+  ctx->samples_loaded = true;
+  if (n == 0) return GVPM_OK;
+  if (!s->ray || !s->t || !s->transmittance || !s->pdf_success || !s->pdf_sel || !s->radius)
+    return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_vpm_sample_soa");
+  std::vector<float4> packed(2 * n);
+  float rmax = 0.f;
+  for (size_t i = 0; i < n; ++i) {
+    if (s->ray[i] >= ctx->n_rays) return fail(ctx, GVPM_ERR_INVALID, "sample refers to a ray that is not uploaded");
+    packed[2 * i] = make_float4(s->t[i], s->pdf_success[i], s->pdf_sel[i], s->radius[i]);
+    uint32_t rb = s->ray[i];
+    float rf;
+    memcpy(&rf, &rb, 4);
+    packed[2 * i + 1] = make_float4(s->transmittance[3 * i], s->transmittance[3 * i + 1], s->transmittance[3 * i + 2], rf);
+    rmax = std::max(rmax, s->radius[i]);
+  }
+  ctx->sample_radius_max = rmax;
+  CK(ctx->samples.reserve(2 * n * sizeof(float4)));
+  CK(ctx->sample_counts.reserve(2 * n * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(ctx->samples.p, packed.data(), 2 * n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+static int vpm_params(gvpm_ctx *ctx, GatherParams &P, int nb_camera_samples) {
+  int rc = fill_params(ctx, P, ctx->out.as<float>(), nullptr);
+  if (rc) return rc;
+  if (!ctx->samples_loaded) return fail(ctx, GVPM_ERR_INVALID, "no VPM samples uploaded");
+  if (nb_camera_samples <= 0) return fail(ctx, GVPM_ERR_INVALID, "nbCameraSamples must be positive");
+  if (ctx->sample_radius_max > ctx->radius)
+    return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points radius is smaller than a sample radius");
+  P.samples = ctx->samples.as<float4>();
+  P.n_samples = ctx->n_samples;
+  P.sample_counts = ctx->sample_counts.as<uint32_t>();
+  P.vpm_normalization = 1.0f / (float)nb_camera_samples;
+  return GVPM_OK;
+}
+
+int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *mvol, uint32_t *sample_counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  GatherParams P;
+  int rc = vpm_params(ctx, P, nb_camera_samples);
+  if (rc) return rc;
+  const size_t nr = ctx->n_rays, ns = ctx->n_samples;
+  CK(ctx->mvol.reserve(nr * 4 + 256));
+  P.mvol = ctx->mvol.as<uint32_t>();
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (ctx->pair_cap == 0) {
+    CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 8 * ns) * sizeof(uint2)));
+    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+  }
+  unsigned long long total = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    P.pairs = ctx->pairs.as<uint2>();
+    P.pair_cap = ctx->pair_cap;
+    CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+    if (nr) CK(cudaMemsetAsync(ctx->out.p, 0, nr * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
+    if (nr) CK(cudaMemsetAsync(ctx->mvol.p, 0, nr * 4, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(launch_vpm_traverse(P, false, ctx->sm_count, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->launches += ns ? 1 : 0;
+    CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    total = *ctx->pair_count_host;
+    if (total <= ctx->pair_cap) break;
+    CK(ctx->pairs.reserve((total + total / 8 + 1024) * sizeof(uint2)));
+    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    if (attempt == 2) return fail(ctx, GVPM_ERR_CUDA, "VPM pair list overflow");
+  }
+  ctx->last_pairs = total;
+  CK(launch_vpm_shade(P, total, ctx->sm_count, ctx->stream));
+  ctx->launches += total ? 1 : 0;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  if (nr) {
+    CK(cudaMemcpyAsync(out, ctx->out.p, nr * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (mvol) CK(cudaMemcpyAsync(mvol, ctx->mvol.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (ns && sample_counts)
+    CK(cudaMemcpyAsync(sample_counts, ctx->sample_counts.p, ns * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *offsets, uint32_t *idx, size_t cap) {
+  if (!ctx || !offsets) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t ns = ctx->n_samples;
+  std::vector<float> tmp((size_t)ctx->n_rays * GVPM_OUT_FLOATS + 1);
+  std::vector<uint32_t> counts(2 * ns + 2);
+  int rc = gvpm_gather_vpm(ctx, nb_camera_samples, tmp.data(), nullptr, counts.data());
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (size_t i = 0; i < ns; ++i) { offsets[i] = total; total += counts[2 * i]; }
+  offsets[ns] = total;
+  if (total > cap || (total && !idx)) return fail(ctx, GVPM_ERR_INVALID, "neighbour buffer too small");
+  if (total == 0) return GVPM_OK;
+  CK(ctx->nbr_offsets.reserve((ns + 1) * 8));
+  CK(ctx->nbr_idx.reserve(total * 4));
+  CK(cudaMemcpyAsync(ctx->nbr_offsets.p, offsets, (ns + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GatherParams P;
+  rc = vpm_params(ctx, P, nb_camera_samples);
+  if (rc) return rc;
+  P.sample_counts = nullptr;
+  P.nbr_offsets = ctx->nbr_offsets.as<uint64_t>();
+  P.nbr_idx = ctx->nbr_idx.as<uint32_t>();
+  CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+  CK(launch_vpm_traverse(P, true, ctx->sm_count, ctx->stream));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

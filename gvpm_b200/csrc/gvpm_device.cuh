@@ -136,6 +136,13 @@ struct GatherParams {
   unsigned long long pair_cap;
   unsigned long long *pair_counter;   // pairs emitted (may exceed pair_cap: overflow)
   float packet_spread_max;            // packets wider than this are traversed ray by ray
+  // G-VPM distance samples: 2 float4 per sample
+  //   s0 = t, pdf_success, pdf_sel, radius | s1 = transmittance.xyz, ray index (bits)
+  const float4 *samples;
+  uint32_t n_samples;
+  uint32_t *sample_counts;            // [n_samples*2] found / contributing, or null
+  uint32_t *mvol;                     // [n_rays] sum of `found` over the ray's samples, or null
+  float vpm_normalization;            // 1 / nbCameraSamples
 };
 
 #ifndef GVPM_PACKET

@@ -87,6 +87,31 @@ class RaySet(_SoA):
     CSTRUCT = N.RaySoA
 
 
+_VPM_FIELDS = [
+    ("ray", np.uint32, 1), ("t", np.float32, 1), ("transmittance", np.float32, 3),
+    ("pdf_success", np.float32, 1), ("pdf_sel", np.float32, 1), ("radius", np.float32, 1),
+]
+
+
+class VpmSampleSet(_SoA):
+    """Camera distance samples of the G-VPM gather (gvpm.cpp:1141-1175), one per (pixel, sample)."""
+    FIELDS = _VPM_FIELDS
+    CSTRUCT = N.VpmSampleSoA
+
+
+def synth_vpm_samples(rays, medium, radius_per_ray, nb_camera_samples=40, stratified=False, seed=0xC0FFEE,
+                      epsilon=1e-4):
+    """Host-side edge selection + HomogeneousMedium::sampleDistance(EDistanceAlwaysValid) for gather points
+    with one medium edge (homogeneous.cpp:293-430)."""
+    s = N.load_synth()
+    radius_per_ray = np.ascontiguousarray(np.broadcast_to(np.asarray(radius_per_ray, dtype=np.float32), (rays.n,)))
+    full = VpmSampleSet(rays.n * nb_camera_samples)
+    cs, cr = full.as_c(), rays.as_c()
+    n = s.gvpm_synth_vpm_samples(seed, C.byref(cr), rays.n, nb_camera_samples, int(stratified), C.byref(medium),
+                                 epsilon, radius_per_ray.ctypes.data_as(N.f32p), C.byref(cs))
+    return full.take(np.arange(n))
+
+
 def make_medium(sigma_t=2.0, albedo=0.8, phase="isotropic", g=0.0, sampling_weight=1.0):
     m = N.Medium()
     ss, sa = np.float32(sigma_t * albedo), np.float32(sigma_t * (1.0 - albedo))

@@ -436,4 +436,62 @@ size_t gvpm_synth_rays(uint64_t seed, int w, int h, int block, int y0, int y1, f
   return n;
 }
 
+// G-VPM camera distance samples, as computeVolumeGradientPhoton draws them (gvpm.cpp:1141-1175) for
+// gather points with ONE medium edge (selBeam = {1}, pdfSel = 1): per ray `nb` samples,
+// randSample = next1D() (stratified: (i + rand)/nb), then HomogeneousMedium::sampleDistance(ray(o, d,
+// Epsilon, beamDist), EDistanceAlwaysValid, randSample) with the balance strategy
+// (homogeneous.cpp:293-430).  Rays whose medium segment is empty get no samples.
+// Arrays are caller-allocated for n_rays*nb entries; returns the number of samples written.
+size_t gvpm_synth_vpm_samples(uint64_t seed, const gvpm_ray_soa *rays, size_t n_rays, int nb, int stratified,
+                              const gvpm_medium *med, float epsilon, const float *radius_per_ray,
+                              gvpm_vpm_sample_soa *out) {
+  uint32_t *ray = (uint32_t *)out->ray;
+  float *t = (float *)out->t, *T = (float *)out->transmittance, *ps = (float *)out->pdf_success,
+        *psel = (float *)out->pdf_sel, *rad = (float *)out->radius;
+  const float sigT[3] = {med->sigma_s[0] + med->sigma_a[0], med->sigma_s[1] + med->sigma_a[1],
+                         med->sigma_s[2] + med->sigma_a[2]};
+  const float samplingDensity = sigT[1];  // channel = min(int(0.5*3), 2) = 1
+  const float normalization = 1.f / nb;
+  size_t n = 0;
+  for (size_t r = 0; r < n_rays; ++r) {
+    const float beamDist = rays->edge_len[r];
+    if (!(beamDist > 4 * epsilon)) continue;
+    Rng rng(seed ^ 0xD1B54A32D192ED03ULL, r);
+    const float mint = epsilon, maxt = beamDist;
+    for (int i = 0; i < nb; ++i) {
+      float rand = rng.uniform();
+      if (stratified) rand = i * normalization + rand * normalization;
+      // sampleDistance, EDistanceAlwaysValid (currentMediumSampling = 1)
+      const float maxDist = std::max((maxt - mint) - epsilon, 0.0f);
+      const float norm = 1 - std::exp(-samplingDensity * maxDist);
+      const float sampledDistance = -std::log(1 - rand * norm) / samplingDensity;
+      const float distSurf = maxt - mint;
+      if (!(sampledDistance < distSurf)) continue;  // "Failed to sample the distance": sample skipped
+      const float tt = sampledDistance + mint;
+      const float px = rays->o[3 * r] + tt * rays->d[3 * r], py = rays->o[3 * r + 1] + tt * rays->d[3 * r + 1],
+                  pz = rays->o[3 * r + 2] + tt * rays->d[3 * r + 2];
+      if (px == rays->o[3 * r] && py == rays->o[3 * r + 1] && pz == rays->o[3 * r + 2]) continue;
+      float pdfSuccess = 0;
+      const float maxDist2 = maxt - mint;
+      for (int c = 0; c < 3; ++c) {
+        const float nrm = 1 - std::exp(-sigT[c] * maxDist2);
+        const float tmp = std::exp(-sigT[c] * sampledDistance);
+        pdfSuccess += (sigT[c] / nrm) * tmp;
+      }
+      pdfSuccess /= 3;
+      float tr[3];
+      for (int c = 0; c < 3; ++c) tr[c] = std::exp(sigT[c] * (-sampledDistance));
+      if (std::max(tr[0], std::max(tr[1], tr[2])) < 1e-20f) tr[0] = tr[1] = tr[2] = 0.f;
+      ray[n] = (uint32_t)r;
+      t[n] = tt;
+      T[3 * n] = tr[0]; T[3 * n + 1] = tr[1]; T[3 * n + 2] = tr[2];
+      ps[n] = pdfSuccess;
+      psel[n] = 1.0f;
+      rad[n] = radius_per_ray[r];
+      ++n;
+    }
+  }
+  return n;
+}
+
 }  // extern "C"

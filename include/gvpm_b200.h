@@ -133,6 +133,21 @@ typedef struct gvpm_ray_soa {
   const float *off_sensor;  /* [n*4]   sensorMIS(e, base, .,.) */
 } gvpm_ray_soa;
 
+/* G-VPM distance samples: what computeVolumeGradientPhoton draws on the host per gather point
+ * (gvpm.cpp:1141-1175: edge selection by the discrete CDF, then
+ * HomogeneousMedium::sampleDistance(ray, mRec, sampler, EDistanceAlwaysValid), homogeneous.cpp:293-430).
+ * One entry per (pixel, camera sample); `ray` indexes the gvpm_ray_soa record of the chosen medium edge.
+ * The distance is sampled on the host (it consumes the integrator's sampler and libm's logf), so the
+ * query points are bit-identical inputs for the gather. */
+typedef struct gvpm_vpm_sample_soa {
+  const uint32_t *ray;         /* [n]   index into the uploaded rays */
+  const float *t;              /* [n]   mRec.t (the query point is o + t*d) */
+  const float *transmittance;  /* [n*3] mRec.transmittance */
+  const float *pdf_success;    /* [n]   mRec.pdfSuccess (baseDistPDF) */
+  const float *pdf_sel;        /* [n]   selBeam[sampleIndex] (pdfSelSection) */
+  const float *radius;         /* [n]   BBPourcentageCONST * gp.scaleVol of the pixel (gvpm.cpp:1131) */
+} gvpm_vpm_sample_soa;
+
 /* Occluder triangles for the reconnection shadow ray (scene->rayIntersect,
  * shift_volume_photon.cpp:396-402), tested as Triangle::rayIntersect
  * (include/mitsuba/core/triangle.h:109-145). */
@@ -191,6 +206,19 @@ int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
  * interaction-mode / pathSet filters.  Returns GVPM_ERR_INVALID when cap is too small
  * (offsets[n_rays] then holds the needed size). */
 int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
+
+/* ---- G-VPM: replaces gradientPhotonMap->evaluate(gRec, p, querySize) over all camera distance
+ *      samples, gvpm.cpp:1141-1185 + kdtree.h:675-731 + shift_volume_photon.cpp:489-655 ----------------
+ * Call order: gvpm_upload_photons, gvpm_build_points(radius >= every sample radius), gvpm_upload_rays
+ * (one record per (gather point, medium edge)), gvpm_upload_vpm_samples, gvpm_gather_vpm.
+ * out: [n_rays*27] with the reference's 1/nbCameraSamples normalisation applied (gvpm.cpp:1177-1182);
+ * mvol (may be NULL): [n_rays] the MVol of gvpm.cpp:1175 = photons found by the range queries of the
+ * ray's samples (drives the per-pixel radius update :1191-1195, which stays on the host);
+ * sample_counts (may be NULL): [n_samples*2] = {found, contributing}. */
+int gvpm_upload_vpm_samples(gvpm_ctx *ctx, const gvpm_vpm_sample_soa *s, size_t n);
+int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *mvol, uint32_t *sample_counts);
+/* per-SAMPLE neighbour index sets, same CSR convention as gvpm_dump_neighbours_bre */
+int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *offsets, uint32_t *idx, size_t cap);
 
 /* ---- hand-off: computeGradient (gvpm.cpp:1205-1306) on the 27-float planes -------------
  * acc: device or host? -> host [h*w*27] APA-averaged accumulators in pixel order;

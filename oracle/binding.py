@@ -41,6 +41,11 @@ def load():
                                     C.c_float, C.c_int, C.c_int, N.f32p, N.u32p, N.u64p, N.u32p, C.c_size_t,
                                     C.POINTER(C.c_double)]
     lib.gvpm_oracle_bre.restype = C.c_longlong
+    lib.gvpm_oracle_vpm.argtypes = [vp, C.POINTER(N.PhotonSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                    C.POINTER(N.VpmSampleSoA), C.c_size_t, C.POINTER(N.Medium), C.POINTER(N.Config),
+                                    N.f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, N.f32p, N.f32p, N.u32p, N.u64p,
+                                    N.u32p, C.c_size_t, C.POINTER(C.c_double)]
+    lib.gvpm_oracle_vpm.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -106,3 +111,48 @@ def bre_gather(photons, rays, medium, config, tri, radius, mode="kdtree", double
             lib.gvpm_oracle_tree_free(tree)
     return BreResult(out.reshape(m, N.GVPM_OUT_FLOATS), counts.reshape(m, 2), offsets,
                      idx[:cap] if neighbours else None, ms.value, build_ms)
+
+
+class VpmResult:
+    def __init__(self, out, mvol, sample_counts, offsets, idx, gather_ms):
+        self.out, self.mvol, self.sample_counts, self.offsets, self.idx = out, mvol, sample_counts, offsets, idx
+        self.gather_ms = gather_ms
+
+
+def vpm_gather(photons, rays, samples, medium, config, tri, nb_camera_samples, mode="kdtree", double=False,
+               threads=None, neighbours=False):
+    """Restated computeVolumeGradientPhoton gather (gvpm.cpp:1141-1185) over all distance samples."""
+    lib = load()
+    threads = hw_threads() if threads is None else threads
+    cph, cr, cs = photons.as_c(), rays.as_c(), samples.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    tree = lib.gvpm_oracle_tree_build(C.byref(cph), photons.n, 1.0, int(double)) if mode == "kdtree" else None
+    out = np.zeros(rays.n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+    mvol = np.zeros(rays.n, dtype=np.float32)
+    sc = np.zeros(samples.n * 2, dtype=np.uint32)
+    ms = C.c_double(0)
+    offsets = idx = None
+    cap = 0
+
+    def call(offp, idxp, capv):
+        r = lib.gvpm_oracle_vpm(tree, C.byref(cph), photons.n, C.byref(cr), rays.n, C.byref(cs), samples.n,
+                                C.byref(medium), C.byref(config), tri.ctypes.data_as(N.f32p), tri.size // 9,
+                                nb_camera_samples, int(double), threads, out.ctypes.data_as(N.f32p),
+                                mvol.ctypes.data_as(N.f32p), sc.ctypes.data_as(N.u32p), offp, idxp, capv,
+                                C.byref(ms))
+        if r < 0:
+            raise RuntimeError(f"gvpm_oracle_vpm failed: {r}")
+        return r
+    try:
+        if neighbours:
+            offsets = np.zeros(samples.n + 1, dtype=np.uint64)
+            cap = int(call(offsets.ctypes.data_as(N.u64p), None, 0))
+            idx = np.zeros(max(cap, 1), dtype=np.uint32)
+            call(offsets.ctypes.data_as(N.u64p), idx.ctypes.data_as(N.u32p), cap)
+            idx = idx[:cap]
+        else:
+            call(None, None, 0)
+    finally:
+        if tree:
+            lib.gvpm_oracle_tree_free(tree)
+    return VpmResult(out.reshape(rays.n, N.GVPM_OUT_FLOATS), mvol, sc.reshape(samples.n, 2), offsets, idx, ms.value)

@@ -138,3 +138,109 @@ long long gvpm_oracle_bre(void *tree, const gvpm_photon_soa *ph, size_t n, const
 }
 
 }  // extern "C"
+
+// ---- G-VPM: computeVolumeGradientPhoton's per-sample range queries (gvpm.cpp:1141-1185) -------------
+namespace {
+template <typename Real>
+void vpmRange(const BreTree<Real> *tree, const gvpm_photon_soa &ph, size_t n, const gvpm_ray_soa &rays, size_t nRays,
+              const gvpm_vpm_sample_soa &smp, size_t nSamples, const Scene<Real> &sc, int nbCameraSamples,
+              int threads, float *out, float *mvol, uint32_t *sampleCounts,
+              std::vector<std::vector<uint32_t>> *nbr) {
+  // per-sample accumulators first (gRec), folded into the pixel with the reference's normalisation
+  std::vector<Accum<Real>> perSample(nSamples);
+  const size_t tile = 4096;
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      size_t b = next.fetch_add(tile);
+      if (b >= nSamples) break;
+      size_t e = std::min(nSamples, b + tile);
+      for (size_t i = b; i < e; ++i) {
+        CamRay<Real> ray = loadRay<Real>(rays, smp.ray[i]);
+        typename Scene<Real>::VpmSample s = sc.loadVpmSample(smp, i, ray);
+        Accum<Real> &acc = perSample[i];
+        uint32_t found = 0, contrib = 0;
+        std::vector<uint32_t> *mine = nbr ? &(*nbr)[i] : nullptr;
+        const V3<Real> q = ray.o + s.t * ray.d;
+        auto visit = [&](uint32_t orig) {
+          Photon<Real> p = loadPhoton<Real>(ph, orig);
+          int r = sc.vpmFunctor(ray, s, p, acc);
+          ++found;
+          if (r == 2) ++contrib;
+          if (mine) mine->push_back(orig | (r == 2 ? 0x80000000u : 0u));
+        };
+        if (tree) {
+          tree->rangeQuery(q, s.radius, [&](uint32_t nodeIdx) { visit(tree->nodes[nodeIdx].orig); });
+        } else {
+          for (size_t j = 0; j < n; ++j)
+            if (sc.sphereTest(q, s.radius, V3<Real>(ph.pos + 3 * j))) visit((uint32_t)j);
+        }
+        if (sampleCounts) { sampleCounts[2 * i] = found; sampleCounts[2 * i + 1] = contrib; }
+      }
+    }
+  };
+  if (threads <= 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+  // gp.mediumFlux += gRec.mediumFlux * normalization (gvpm.cpp:1177-1182), MVol += found (:1175)
+  const Real normalization = (Real)1 / (Real)nbCameraSamples;
+  std::vector<Accum<Real>> pix(nRays);
+  for (size_t r = 0; r < nRays; ++r) mvol[r] = 0.f;
+  for (size_t i = 0; i < nSamples; ++i) {
+    Accum<Real> &g = pix[smp.ray[i]];
+    g.mediumFlux += perSample[i].mediumFlux * normalization;
+    for (int k = 0; k < 4; ++k) {
+      g.shifted[k] += perSample[i].shifted[k] * normalization;
+      g.weighted[k] += perSample[i].weighted[k] * normalization;
+    }
+  }
+  for (size_t r = 0; r < nRays; ++r) pix[r].store(out + GVPM_OUT_FLOATS * r);
+  (void)nSamples;
+}
+}  // namespace
+
+extern "C" long long gvpm_oracle_vpm(void *tree, const gvpm_photon_soa *ph, size_t n, const gvpm_ray_soa *rays,
+                                     size_t nRays, const gvpm_vpm_sample_soa *smp, size_t nSamples,
+                                     const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri,
+                                     int nbCameraSamples, int use_double, int threads, float *out, float *mvol,
+                                     uint32_t *sampleCounts, uint64_t *nbr_offsets, uint32_t *nbr_idx, size_t cap,
+                                     double *gather_ms) {
+  TreeHandle *h = (TreeHandle *)tree;
+  if (h && (h->dbl != (use_double != 0) || h->n != n)) return -2;
+  std::vector<std::vector<uint32_t>> nbr;
+  if (nbr_offsets) nbr.resize(nSamples);
+  auto t0 = std::chrono::steady_clock::now();
+  if (use_double) {
+    Scene<double> sc(*med, *cfg, 0.0);
+    sc.occ.set(tri, n_tri);
+    vpmRange<double>(h ? &h->td : nullptr, *ph, n, *rays, nRays, *smp, nSamples, sc, nbCameraSamples, threads, out,
+                     mvol, sampleCounts, nbr_offsets ? &nbr : nullptr);
+  } else {
+    Scene<float> sc(*med, *cfg, 0.f);
+    sc.occ.set(tri, n_tri);
+    vpmRange<float>(h ? &h->tf : nullptr, *ph, n, *rays, nRays, *smp, nSamples, sc, nbCameraSamples, threads, out,
+                    mvol, sampleCounts, nbr_offsets ? &nbr : nullptr);
+  }
+  if (gather_ms)
+    *gather_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  // MVol per ray = sum of `found` over its samples
+  if (sampleCounts)
+    for (size_t i = 0; i < nSamples; ++i) mvol[smp->ray[i]] += (float)sampleCounts[2 * i];
+  long long total = 0;
+  if (nbr_offsets) {
+    for (size_t i = 0; i < nbr.size(); ++i) {
+      nbr_offsets[i] = (uint64_t)total;
+      std::sort(nbr[i].begin(), nbr[i].end(),
+                [](uint32_t a, uint32_t b) { return (a & 0x7fffffffu) < (b & 0x7fffffffu); });
+      for (uint32_t v : nbr[i]) {
+        if ((size_t)total < cap && nbr_idx) nbr_idx[total] = v;
+        ++total;
+      }
+    }
+    nbr_offsets[nbr.size()] = (uint64_t)total;
+  }
+  return total;
+}

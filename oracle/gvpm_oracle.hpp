@@ -341,9 +341,13 @@ template <typename Real> struct Scene {
 
   // AbstractVolumeGradientRecord::getShiftPos, shift_volume_photon.cpp:858-896 (3-D kernel)
   V3<Real> getShiftPos(const CamRay<Real> &ray, int k, Real tBase, const V3<Real> &basePhotonPos) const {
+    return getShiftPos(ray, k, tBase, basePhotonPos, radius, !cfg.kernel_3d);
+  }
+  V3<Real> getShiftPos(const CamRay<Real> &ray, int k, Real tBase, const V3<Real> &basePhotonPos, Real radius,
+                       bool coherent) const {
     V3<Real> zBase = ray.o + tBase * ray.d, zShift = ray.offO[k] + tBase * ray.offD[k];
     V3<Real> offsetPos = zShift + (basePhotonPos - zBase);
-    if (!cfg.kernel_3d) {  // coherent frames for the 2-D kernel, :866-873
+    if (coherent) {  // coherent frames for the 2-D kernel, :866-873
       V3<Real> bs, bt, ns, nt;
       coordinateSystemCoherent(ray.d, bs, bt);
       coordinateSystemCoherent(ray.offD[k], ns, nt);
@@ -450,6 +454,97 @@ template <typename Real> struct Scene {
     }
     return 2;
   }
+
+  // ---- G-VPM -----------------------------------------------------------------------------
+  // One camera distance sample (gvpm.cpp:1141-1175), with the four cached shiftMRec
+  // (VolumeGradientPositionQuery, shift_volume_photon.cpp:543-567): they depend on the sample only.
+  struct VpmSample {
+    uint32_t ray;
+    Real t, pdfSuccess, pdfSel, radius;
+    V3<Real> T;
+    bool validShiftDist[4];
+    typename Medium<Real>::Rec shiftMRec[4];
+  };
+  VpmSample loadVpmSample(const gvpm_vpm_sample_soa &s, size_t i, const CamRay<Real> &ray) const {
+    VpmSample v;
+    v.ray = s.ray[i];
+    v.t = (Real)s.t[i];
+    v.pdfSuccess = (Real)s.pdf_success[i];
+    v.pdfSel = (Real)s.pdf_sel[i];
+    v.radius = (Real)s.radius[i];
+    v.T = V3<Real>(s.transmittance + 3 * i);
+    for (int k = 0; k < 4; ++k) {
+      v.validShiftDist[k] = ray.offValid[k] && ray.offLen[k] >= v.t;  // :549-553
+      v.shiftMRec[k].pdfSuccess = 0;
+      v.shiftMRec[k].pdfFailure = 0;
+      if (v.validShiftDist[k]) {
+        // medium->eval(shiftRay(o_k, d_k, Epsilon, len_k), shiftMRec, EDistanceAlwaysValid) with mRec.t = t:
+        // homogeneous.cpp:468-476,504-513 (currentMediumSampling forced to 1)
+        const Real maxDist = ray.offLen[k] - (Real)cfg.epsilon, distance = v.t;
+        Real ps = 0;
+        for (int c = 0; c < 3; ++c) {
+          const Real normalization = 1 - std::exp(-medium.sigmaT[c] * maxDist);
+          const Real tmp = std::exp(-medium.sigmaT[c] * distance);
+          ps += (medium.sigmaT[c] / normalization) * tmp;
+        }
+        ps /= 3;
+        v.shiftMRec[k].pdfSuccess = ps;
+        v.shiftMRec[k].transmittance = V3<Real>(std::exp(medium.sigmaT.x * (-distance)),
+                                                std::exp(medium.sigmaT.y * (-distance)),
+                                                std::exp(medium.sigmaT.z * (-distance)));
+        if (v.shiftMRec[k].transmittance.maxc() < (Real)1e-20) v.shiftMRec[k].transmittance = V3<Real>();
+      }
+    }
+    return v;
+  }
+
+  // PointKDTree::executeQuery predicate, include/mitsuba/core/kdtree.h:721-723
+  bool sphereTest(const V3<Real> &queryPos, Real r, const V3<Real> &p) const {
+    return (p - queryPos).lengthSquared() < r * r;
+  }
+
+  // VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp:489-655.
+  // 1 = found by the range query but filtered, 2 = contributes.
+  int vpmFunctor(const CamRay<Real> &ray, const VpmSample &s, const Photon<Real> &ph, Accum<Real> &acc) const {
+    const Real r = s.radius;
+    const V3<Real> pos = ray.o + s.t * ray.d;
+    const Real lengthSqr = (pos - ph.pos).lengthSquared();
+    if ((r * r - lengthSqr) < 0) return 1;                                   // :497-500
+    if (cfg.max_depth > 0 && ray.edgeId + ph.depth > cfg.max_depth) return 1;  // :503-505
+    if (!lightingModeAccepts(ph.parentType)) return 1;                       // :508-510
+    const V3<Real> wi = normalize(ph.parentPos - ph.pos);
+    V3<Real> photonContrib = volumePhotonContrib(ph.flux, wi, -ray.d);
+    V3<Real> baseContrib = (ray.eye * s.T) * photonContrib;                  // :529
+    const Real kernelVol = (Real)((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3));
+    const Real pdfBase = s.pdfSuccess * s.pdfSel;                            // pdfBaseRay(), .h:189-192
+    const Real norm = kernelVol * pdfBase;
+    acc.mediumFlux += baseContrib / norm;
+    for (int k = 0; k < 4; ++k) {
+      GradientSamplingResult<Real> res;
+      if (s.validShiftDist[k]) {
+        const Real pdfShift = s.shiftMRec[k].pdfSuccess * s.pdfSel;          // pdfShiftRay(), .h:193-197
+        const V3<Real> zShift = ray.offO[k] + s.t * ray.offD[k];
+        bool alreadyShifted = false;
+        if (cfg.use_shift_null) {                                            // :584-602
+          Real distSqr = (ph.pos - zShift).lengthSquared();
+          if (distSqr < r * r) {
+            alreadyShifted = true;
+            shiftNull(ph, wi, ray, k, s.shiftMRec[k], res, pdfBase, pdfShift);
+          }
+        }
+        if (!alreadyShifted) {                                               // :604-639
+          V3<Real> offsetPos = getShiftPos(ray, k, s.t, ph.pos, r, false);
+          shiftPhotonDiffuse(ph, offsetPos, ray, k, s.shiftMRec[k], res, pdfBase, pdfShift);
+        }
+      } else {
+        res.weight = 1;
+      }
+      if ((k == 1 && ray.px == cfg.film_w - 1) || (k == 2 && ray.py == cfg.film_h - 1)) res.weight = 1;
+      acc.shifted[k] += (res.weight * res.shiftedFlux) / norm;
+      acc.weighted[k] += (res.weight * baseContrib) / norm;
+    }
+    return 2;
+  }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -461,6 +556,7 @@ template <typename Real> struct BreTree {
     V3<Real> pos, bmin, bmax;
     uint32_t right = 0, orig = 0;
     bool leaf = false;
+    uint8_t axis = 0;
   };
   std::vector<Node> nodes;
   size_t depth = 0;
@@ -490,9 +586,50 @@ template <typename Real> struct BreTree {
       nd.orig = ind[i];
       nd.pos = pts[ind[i]];
       nd.right = rightOf[ind[i]];
-      nd.leaf = leafOf[ind[i]] != 0;
+      nd.leaf = (leafOf[ind[i]] & 1) != 0;
+      nd.axis = leafOf[ind[i]] >> 1;
     }
     hierarchy(0);
+  }
+
+  // PointKDTree::executeQuery, include/mitsuba/core/kdtree.h:675-731: visit(nodeIndex) for every node with
+  // |node.pos - p|^2 < r^2; returns `found`.
+  template <typename F> size_t rangeQuery(const V3<Real> &p, Real searchRadius, F &&visit) const {
+    if (nodes.empty()) return 0;
+    std::vector<uint32_t> stack(depth + 2);
+    uint32_t index = 0, stackPos = 1, found = 0;
+    const Real distSquared = searchRadius * searchRadius;
+    stack[0] = 0;
+    while (stackPos > 0) {
+      const Node &node = nodes[index];
+      uint32_t nextIndex;
+      if (!node.leaf) {
+        const Real distToPlane = p[node.axis] - node.pos[node.axis];
+        const bool searchBoth = distToPlane * distToPlane <= distSquared;
+        if (distToPlane > 0) {
+          if (node.right != 0) {
+            if (searchBoth) stack[stackPos++] = index + 1;
+            nextIndex = node.right;
+          } else if (searchBoth) {
+            nextIndex = index + 1;
+          } else {
+            nextIndex = stack[--stackPos];
+          }
+        } else {
+          if (searchBoth && node.right != 0) stack[stackPos++] = node.right;
+          nextIndex = index + 1;
+        }
+      } else {
+        nextIndex = stack[--stackPos];
+      }
+      const Real pointDistSquared = (node.pos - p).lengthSquared();
+      if (pointDistSquared < distSquared) {
+        ++found;
+        visit(index);
+      }
+      index = nextIndex;
+    }
+    return found;
   }
 
   void buildRec(size_t d, const std::vector<V3<Real>> &pts, std::vector<uint32_t> &ind,
@@ -512,6 +649,7 @@ template <typename Real> struct BreTree {
     std::nth_element(ind.begin() + b, ind.begin() + split, ind.begin() + e,
                      [&](uint32_t i1, uint32_t i2) { return pts[i1][axis] < pts[i2][axis]; });
     uint32_t sp = ind[split];
+    leafOf[sp] = (uint8_t)(axis << 1);
     rightOf[sp] = (split + 1 != e) ? (uint32_t)(split + 1) : 0;
     std::swap(ind[b], ind[split]);
     Real splitPos = pts[sp][axis];

@@ -147,3 +147,19 @@ def test_synth_is_thread_count_independent(built):
     assert pa == pb
     for name, _, _ in a.FIELDS:
         np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
+
+
+def test_vpm_kdtree_range_query_equals_bruteforce(built):
+    """The restated PointKDTree::executeQuery (kdtree.h:675-731) visits exactly the brute-force set: the
+    reference's own test_kd.cpp:133-214 property, here for the G-VPM range queries."""
+    import gvpm_b200 as g
+    c = H.make_case(n_photons=30000, w=32, h=20, scale=3.0)
+    rad = np.full(c.rays.n, c.radius, dtype=np.float32) * np.random.default_rng(2).uniform(0.4, 1.0, c.rays.n).astype(np.float32)
+    smp = g.synth_vpm_samples(c.rays, c.medium, rad, nb_camera_samples=6, seed=99)
+    kd = ob.vpm_gather(c.photons, c.rays, smp, c.medium, c.config, c.tri, 6, mode="kdtree", neighbours=True, threads=4)
+    bf = ob.vpm_gather(c.photons, c.rays, smp, c.medium, c.config, c.tri, 6, mode="brute", neighbours=True, threads=4)
+    assert bf.sample_counts[:, 0].sum() > 1000
+    np.testing.assert_array_equal(kd.idx, bf.idx)
+    np.testing.assert_array_equal(kd.offsets, bf.offsets)
+    np.testing.assert_array_equal(kd.mvol, bf.mvol)
+    H.assert_radiance_close(kd.out, bf.out, 1e-5, "vpm kd vs brute")
