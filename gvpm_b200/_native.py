@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("use_mis", C.c_int32), ("use_shift_null", C.c_int32), ("path_set", C.c_int32),
                 ("power_heuristic", C.c_int32), ("kernel_3d", C.c_int32), ("film_w", C.c_int32),
                 ("film_h", C.c_int32), ("shadow_maxt_scale", C.c_float), ("epsilon", C.c_float),
-                ("reserved", C.c_int32 * 4)]
+                ("long_beams", C.c_int32), ("rng_seed", C.c_uint32), ("reserved", C.c_int32 * 2)]
 
 
 class PhotonSoA(C.Structure):
@@ -52,6 +52,13 @@ class RaySoA(C.Structure):
                 ("off_eye", f32p), ("off_sensor", f32p)]
 
 
+class BeamSoA(C.Structure):
+    _fields_ = [("origin", f32p), ("end", f32p), ("flux", f32p), ("prefix_flux", f32p), ("parent_n", f32p),
+                ("parent_albedo", f32p), ("pred_pos", f32p), ("end_n", f32p), ("parent_pdf", f32p),
+                ("rr_weight", f32p), ("parent_type", u8p), ("end_on_surface", u8p), ("depth", u8p),
+                ("path_id", u32p)]
+
+
 class VpmSampleSoA(C.Structure):
     _fields_ = [("ray", u32p), ("t", f32p), ("transmittance", f32p), ("pdf_success", f32p),
                 ("pdf_sel", f32p), ("radius", f32p)]
@@ -66,6 +73,7 @@ ABI_SYMBOLS = [
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
+    "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
 ]
 
 _lib = None
@@ -107,6 +115,10 @@ def load_lib():
     lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]
     lib.gvpm_last_gather_detail.argtypes = [vp, f32p, f32p, u64p]
+    lib.gvpm_upload_beams.argtypes = [vp, C.POINTER(BeamSoA), C.c_size_t]
+    lib.gvpm_build_beams.argtypes = [vp, C.c_float]
+    lib.gvpm_gather_beams.argtypes = [vp, f32p, u32p]
+    lib.gvpm_dump_neighbours_beams.argtypes = [vp, u64p, u32p, C.c_size_t]
     lib.gvpm_upload_vpm_samples.argtypes = [vp, C.POINTER(VpmSampleSoA), C.c_size_t]
     lib.gvpm_gather_vpm.argtypes = [vp, C.c_int, f32p, u32p, u32p]
     lib.gvpm_dump_neighbours_vpm.argtypes = [vp, C.c_int, u64p, u32p, C.c_size_t]
@@ -138,5 +150,8 @@ def load_synth():
     s.gvpm_synth_vpm_samples.argtypes = [C.c_uint64, C.POINTER(RaySoA), C.c_size_t, C.c_int, C.c_int,
                                          C.POINTER(Medium), C.c_float, f32p, C.POINTER(VpmSampleSoA)]
     s.gvpm_synth_vpm_samples.restype = C.c_size_t
+    s.gvpm_synth_beams.argtypes = [C.c_uint64, C.c_size_t, C.POINTER(Medium), C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_int, C.POINTER(BeamSoA)]
+    s.gvpm_synth_beams.restype = C.c_longlong
     _synth = s
     return s

@@ -130,6 +130,36 @@ class Context:
             idx = idx[order]
         return offsets, idx
 
+    # ---- G-Beams 3D
+    def upload_beams(self, beams):
+        cs = beams.as_c()
+        self._ck(self.lib.gvpm_upload_beams(self.h, C.byref(cs), beams.n), "gvpm_upload_beams")
+
+    def build_beams(self, radius):
+        self._ck(self.lib.gvpm_build_beams(self.h, C.c_float(radius)), "gvpm_build_beams")
+
+    def gather_beams(self, counts=True):
+        n = self.n_rays
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
+        self._ck(self.lib.gvpm_gather_beams(self.h, out.ctypes.data_as(N.f32p),
+                                            cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_beams")
+        return out.reshape(n, N.GVPM_OUT_FLOATS), (cnt.reshape(n, 2) if counts else None)
+
+    def dump_neighbours_beams(self):
+        n = self.n_rays
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        rc = self.lib.gvpm_dump_neighbours_beams(self.h, offsets.ctypes.data_as(N.u64p), None, 0)
+        total = int(offsets[n])
+        if rc != 0 and total == 0:
+            self._ck(rc, "gvpm_dump_neighbours_beams")
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            self._ck(self.lib.gvpm_dump_neighbours_beams(self.h, offsets.ctypes.data_as(N.u64p),
+                                                         idx.ctypes.data_as(N.u32p), total),
+                     "gvpm_dump_neighbours_beams")
+        return offsets, idx[:total]
+
     # ---- G-VPM
     def upload_vpm_samples(self, samples):
         cs = samples.as_c()

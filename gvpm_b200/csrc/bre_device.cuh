@@ -35,7 +35,7 @@ __device__ __forceinline__ sf chord_pdf(sf deltaT) {
   return (x2.v <= 0.0001f) ? sf(10000.f) : sf(1.f) / x2;
 }
 
-struct MediumRec { sf T, pdfSuccess; };
+struct MediumRec { sf T, pdfSuccess, pdfFailure; };
 
 // HomogeneousMedium::eval with equal sigma_t over channels (enforced at gvpm_set_medium as the
 // reference does, homogeneous.cpp:188-201): transmittance is one scalar.
@@ -47,6 +47,8 @@ __device__ __forceinline__ MediumRec medium_eval(const GatherParams &P, sf mint,
   sf ps = st * tmp;
   ps = ((ps + ps) + ps) / sf(3.f);
   r.pdfSuccess = ps * sf(P.sampling_weight);
+  const sf pf = ((tmp + tmp) + tmp) / sf(3.f);
+  r.pdfFailure = pf * sf(P.sampling_weight) + (sf(1.f) - sf(P.sampling_weight));
   r.T = tmp;
   if (r.T.v < 1e-20f) r.T = sf(0.f);
   return r;

@@ -1,0 +1,364 @@
+// gather_beams.cu — G-Beams 3D gather.  Replaces, per iteration,
+//   SubBeamBVH construction + buildHierarchy + query   photonmapper/beams_accel.h:90-243
+//   BeamGradRadianceQuery::operator() and its shifts   gvpm/shift/shift_volume_beams.cpp:139-539,748-786
+//   the gather loop of computeVolumeGradientBeams      gvpm/gvpm.cpp:880-986
+//
+// Hierarchy: beams are cut into sub-beams of avgLength/10 like the reference (beams_accel.h:98-124); the
+// sub-beam midpoints are Morton-sorted and an implicit 32-ary AABB hierarchy is built over them (box of a
+// sub-beam = its two r-cubes, beams_accel.h:222-231).
+// k_beam_traverse: one warp per packet of 4 camera rays, same stackless ballot-mask walk as k_bre_traverse;
+//   at a leaf lane c holds sub-beam c and keeps it as a candidate for ray j when the two supporting lines
+//   pass within r of each other (relaxed, conservative).  Candidates go to the (ray, sub-beam) pair list.
+// k_beam_shade: one thread per pair.  The kernel record of the WHOLE beam is evaluated in strictly rounded
+//   fp32 / fp64 (cylinder intersection); the pair survives only in the sub-beam that owns tNear (half-open
+//   [t1, t2), the reference's ownership rule :214-220 made exact at sub-beam boundaries), so each (ray, beam)
+//   is counted once whatever the tree.  Then the functor with its 4 offsets, a segmented warp scan by ray,
+//   and 27 float atomics per run.
+#include "beam_device.cuh"
+
+namespace gvpm {
+
+// raw sub-beam records -> Morton order
+__global__ void k_sub_gather(const float4 *__restrict__ raw, const uint32_t *__restrict__ sorted, uint32_t n,
+                             float4 *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = raw[sorted[i]];
+}
+
+// level 0: one warp per leaf of 32 sub-beams
+__global__ void k_subbeam_leaf_boxes(const float4 *__restrict__ subs, const float4 *__restrict__ beams, uint32_t n,
+                                     uint32_t nLeaves, float radius, float4 *__restrict__ lo,
+                                     float4 *__restrict__ hi) {
+  const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (leaf >= nLeaves) return;
+  const uint32_t i = leaf * 32 + lane;
+  float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (i < n) {
+    const float4 s = subs[i];
+    const uint32_t bi = __float_as_uint(s.z);
+    const float4 b0 = beams[(size_t)bi * GVPM_BEAM_FLOAT4], b1 = beams[(size_t)bi * GVPM_BEAM_FLOAT4 + 1];
+    const float o[3] = {b0.x, b0.y, b0.z}, d[3] = {b1.x, b1.y, b1.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float p1 = o[a] + d[a] * s.x, p2 = o[a] + d[a] * s.y;
+      l[a] = fminf(p1, p2);
+      h[a] = fmaxf(p1, p2);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      l[a] = fminf(l[a], __shfl_xor_sync(0xffffffffu, l[a], o));
+      h[a] = fmaxf(h[a], __shfl_xor_sync(0xffffffffu, h[a], o));
+    }
+  if (lane == 0) {
+    const float pad = radius * 1.0001f;
+    lo[leaf] = make_float4(l[0] - pad, l[1] - pad, l[2] - pad, 0.f);
+    hi[leaf] = make_float4(h[0] + pad, h[1] + pad, h[2] + pad, 0.f);
+  }
+}
+
+constexpr int kBeamWarps = 4;
+constexpr int BPK = GVPM_PACKET;
+
+struct BeamTravShared {
+  float4 ray[BPK][4];
+  uint32_t queue[BPK][64];
+  uint32_t mask[GVPM_MAX_LEVELS];
+  uint32_t base[GVPM_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void flush_beam_pairs(const GatherParams &P, const uint32_t *queue, uint32_t ray,
+                                                 uint32_t &qn, uint32_t take, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)take);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  qn -= take;
+  if ((uint32_t)lane < take) {
+    const unsigned long long idx = base + lane;
+    if (idx < P.pair_cap) P.pairs[idx] = make_uint2(ray, queue[qn + lane]);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __grid_constant__ GatherParams P) {
+  __shared__ BeamTravShared sh[kBeamWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  BeamTravShared &S = sh[w];
+  const Tree &T = P.tree;
+  const int top = T.levels - 1;
+  const uint32_t nPackets = (P.ray_end - P.ray_begin + BPK - 1) / BPK;
+  const float coordMag = T.n ? __ldg(P.bounds + 6) : 0.f;
+  float spreadMax = 16.f * P.radius;
+  if (T.n) {
+    const float ex = __ldg(P.bounds + 3) - __ldg(P.bounds), ey = __ldg(P.bounds + 4) - __ldg(P.bounds + 1),
+                ez = __ldg(P.bounds + 5) - __ldg(P.bounds + 2);
+    spreadMax = fmaxf(spreadMax, 0.01f * sqrtf(ex * ex + ey * ey + ez * ez));
+  }
+  for (;;) {
+    uint32_t pk = 0;
+    if (lane == 0) pk = atomicAdd(P.work_counter, 1u);
+    pk = __shfl_sync(0xffffffffu, pk, 0);
+    if (pk >= nPackets) break;
+    const uint32_t r0 = P.ray_begin + pk * BPK;
+    const int nr = min((uint32_t)BPK, P.ray_end - r0);
+    __syncwarp();
+    if (lane < 4 * nr) S.ray[lane >> 2][lane & 3] = ldg4(P.rays + (size_t)(r0 + (lane >> 2)) * GVPM_RAY_FLOAT4 + (lane & 3));
+    __syncwarp();
+    float ox[BPK], oy[BPK], oz[BPK], dx[BPK], dy[BPK], dz[BPK], mint[BPK], elen[BPK];
+    int par[BPK], eid[BPK];
+    uint32_t qn[BPK];
+    uint32_t actMask = 0;
+#pragma unroll
+    for (int j = 0; j < BPK; ++j) {
+      const int jj = j < nr ? j : 0;
+      const float4 b0 = S.ray[jj][0], b1 = S.ray[jj][1], b2 = S.ray[jj][2], b3 = S.ray[jj][3];
+      ox[j] = b0.x; oy[j] = b0.y; oz[j] = b0.z; mint[j] = b0.w;
+      dx[j] = b1.x; dy[j] = b1.y; dz[j] = b1.z; elen[j] = b2.w;
+      par[j] = ((int)__float_as_uint(b3.y) + (int)__float_as_uint(b3.z)) % 2;
+      eid[j] = (int)__float_as_uint(b3.w);
+      qn[j] = 0;
+      if (j < nr && T.n > 0 && elen[j] >= mint[j]) actMask |= 1u << j;
+    }
+    uint32_t groups[BPK];
+    int ng = 0;
+    float spread = 0.f;
+    if (actMask) {
+      const int c0 = __ffs(actMask) - 1;
+      float cox = 0, coy = 0, coz = 0, cdx = 0, cdy = 0, cdz = 0, tEnd = 0;
+#pragma unroll
+      for (int j = 0; j < BPK; ++j) {
+        if (j == c0) { cox = ox[j]; coy = oy[j]; coz = oz[j]; cdx = dx[j]; cdy = dy[j]; cdz = dz[j]; }
+        if (actMask >> j & 1) tEnd = fmaxf(tEnd, elen[j]);
+      }
+      tEnd += P.radius;
+#pragma unroll
+      for (int j = 0; j < BPK; ++j)
+        if (actMask >> j & 1) {
+          const float ax = ox[j] - cox, ay = oy[j] - coy, az = oz[j] - coz;
+          const float bx = ax + tEnd * (dx[j] - cdx), by = ay + tEnd * (dy[j] - cdy), bz = az + tEnd * (dz[j] - cdz);
+          spread = fmaxf(spread, fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz)));
+        }
+      spread *= 1.0001f;
+      if (spread <= spreadMax) {
+        groups[ng++] = actMask;
+      } else {
+        spread = 0.f;
+#pragma unroll
+        for (int j = 0; j < BPK; ++j)
+          if (actMask >> j & 1) groups[ng++] = 1u << j;
+      }
+    }
+    for (int g = 0; g < ng; ++g) {
+      const uint32_t gm = groups[g];
+      const int c0 = __ffs(gm) - 1;
+      float cox = 0, coy = 0, coz = 0, cdx = 1, cdy = 1, cdz = 1, tloG = 3.4e38f, thiG = -3.4e38f, omag = 0.f;
+#pragma unroll
+      for (int j = 0; j < BPK; ++j) {
+        if (j == c0) { cox = ox[j]; coy = oy[j]; coz = oz[j]; cdx = dx[j]; cdy = dy[j]; cdz = dz[j]; }
+        if (gm >> j & 1) {
+          tloG = fminf(tloG, mint[j]);
+          thiG = fmaxf(thiG, elen[j]);
+          omag = fmaxf(omag, fmaxf(fmaxf(fabsf(ox[j]), fabsf(oy[j])), fabsf(oz[j])));
+        }
+      }
+      const float fpad = (omag + coordMag + fabsf(thiG) + P.radius) * 3.8147e-6f;
+      const float pad = fpad + ((gm & (gm - 1)) ? spread : 0.f);
+      const float oxp = cox + pad, oxm = cox - pad, oyp = coy + pad, oym = coy - pad, ozp = coz + pad,
+                  ozm = coz - pad;
+      const float ix = 1.f / cdx, iy = 1.f / cdy, iz = 1.f / cdz;
+      const float tlo = -4.f * fpad - P.radius;
+      const float thi = thiG + P.radius + 4.f * fpad;
+      const float rpad2 = (P.radius + 4.f * fpad) * (P.radius + 4.f * fpad);
+      uint32_t cur, base = 0;
+      int l = top;
+      cur = __ballot_sync(0xffffffffu, (uint32_t)lane < T.cnt[top] &&
+                                           box_hit(T, T.off[top] + lane, oxp, oxm, oyp, oym, ozp, ozm, ix, iy,
+                                                   iz, tlo, thi));
+      for (;;) {
+        if (cur == 0) {
+          if (l == top) break;
+          ++l;
+          cur = S.mask[l];
+          base = S.base[l];
+          continue;
+        }
+        const int c = __ffs(cur) - 1;
+        cur &= cur - 1;
+        const uint32_t node = base + c;
+        if (l > 0) {
+          S.mask[l] = cur;
+          S.base[l] = base;
+          --l;
+          base = node << 5;
+          const uint32_t idx = base + lane;
+          cur = __ballot_sync(0xffffffffu, idx < T.cnt[l] && box_hit(T, T.off[l] + idx, oxp, oxm, oyp, oym, ozp,
+                                                                       ozm, ix, iy, iz, tlo, thi));
+          continue;
+        }
+        // ---- leaf: lane holds sub-beam (node*32 + lane) ----
+        const uint32_t si = (node << 5) + lane;
+        uint32_t cand = 0;
+        if (si < T.n) {
+          const float4 sb = ldg4(P.subs + si);
+          const uint32_t bi = __float_as_uint(sb.z);
+          const float4 b0 = ldg4(P.beams + (size_t)bi * GVPM_BEAM_FLOAT4), b1 = ldg4(P.beams + (size_t)bi * GVPM_BEAM_FLOAT4 + 1);
+          const uint32_t meta = __float_as_uint(b1.w);
+          const int type = meta & 3, depth = (meta >> 2) & 255, parity = (meta >> 10) & 1;
+          const int m = P.cfg.lighting_mode;
+          bool modeOk = true;
+          if (!((m & GVPM_SURF2MEDIA) && (m & GVPM_MEDIA2MEDIA))) {
+            if (type == GVPM_PARENT_MEDIUM && !(m & GVPM_MEDIA2MEDIA)) modeOk = false;
+            if (type != GVPM_PARENT_MEDIUM && !(m & GVPM_SURF2MEDIA)) modeOk = false;
+          }
+#pragma unroll
+          for (int j = 0; j < BPK; ++j) {
+            // supporting lines within r of each other (cylinderIntersection's early test, relaxed + padded)
+            const float cx = dy[j] * b1.z - dz[j] * b1.y, cy = dz[j] * b1.x - dx[j] * b1.z,
+                        cz = dx[j] * b1.y - dy[j] * b1.x;
+            const float sin2 = cx * cx + cy * cy + cz * cz;
+            const float ad = (b0.x - ox[j]) * cx + (b0.y - oy[j]) * cy + (b0.z - oz[j]) * cz;
+            bool ok = (gm >> j & 1) && (sin2 < 1e-6f || ad * ad < rpad2 * sin2 * 1.001f);
+            // the filters only drop pairs (they never make one valid): keep them out of the pair list unless
+            // the parity dump needs the geometric set
+            if (P.beam_prefilter) {
+              if (P.cfg.max_depth > 0 && eid[j] + depth > P.cfg.max_depth) ok = false;
+              if (!modeOk) ok = false;
+              if (P.cfg.path_set && parity != par[j]) ok = false;
+            }
+            if (ok) cand |= 1u << j;
+          }
+        }
+        const uint32_t anyc = __reduce_or_sync(0xffffffffu, cand);
+        if (anyc == 0) continue;
+#pragma unroll
+        for (int j = 0; j < BPK; ++j) {
+          if (!(anyc >> j & 1)) continue;
+          const bool c1 = cand >> j & 1;
+          const uint32_t cmask = __ballot_sync(0xffffffffu, c1);
+          if (c1) S.queue[j][qn[j] + __popc(cmask & ((1u << lane) - 1u))] = si;
+          qn[j] += __popc(cmask);
+          __syncwarp();
+          if (qn[j] >= 32) flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], 32, lane);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BPK; ++j)
+      if (qn[j] > 0) flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], qn[j], lane);
+  }
+}
+
+__global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ GatherParams P) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long total = *P.pair_counter;
+  if (total > P.pair_cap) total = P.pair_cap;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total;
+       i0 += stride) {
+    const unsigned long long i = i0 + lane;
+    const bool valid = i < total;
+    float a[GVPM_OUT_FLOATS];
+#pragma unroll
+    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) a[j] = 0.f;
+    uint32_t key = 0xffffffffu;
+    if (valid) {
+      const uint2 pr = P.pairs[i];
+      key = pr.x;
+      const float4 sb = ldg4(P.subs + pr.y);
+      const uint32_t bi = __float_as_uint(sb.z), flags = __float_as_uint(sb.w);
+      const float4 *rec = P.rays + (size_t)key * GVPM_RAY_FLOAT4;
+      const BaseRay R = load_base_ray(rec);
+      const BeamRec beam = load_beam(P, bi);
+      double tNear = 0.0;
+      const uint32_t origBeam = bi;  // beam records keep the caller's order; only sub-beams are sorted
+      const BeamKernelRec kRec = beam_kernel_eval(P, beam, R, origBeam, tNear);
+      // sub-beam ownership: half-open [t1, t2), first sub-beam also owns tNear < 0, last one the tail
+      const bool owner = ((flags & 1u) || tNear >= (double)sb.x) && ((flags & 2u) || tNear < (double)sb.y);
+      if (kRec.valid && owner) {
+        const uint32_t meta = __float_as_uint(__ldg(&P.beams[(size_t)bi * GVPM_BEAM_FLOAT4 + 1].w));
+        // depth / interaction-mode / pathSet filters of the beam functor (shift_volume_beams.cpp:143-187;
+        // no minDepth test here: the driver skips camera edges instead, gvpm.cpp:922)
+        bool contributes = true;
+        {
+          const int type = meta & 3, depth = (meta >> 2) & 255, parity = (meta >> 10) & 1;
+          if (P.cfg.max_depth > 0 && R.edgeId + depth > P.cfg.max_depth) contributes = false;
+          const int m = P.cfg.lighting_mode;
+          if (!((m & GVPM_SURF2MEDIA) && (m & GVPM_MEDIA2MEDIA))) {
+            if (type == GVPM_PARENT_MEDIUM && !(m & GVPM_MEDIA2MEDIA)) contributes = false;
+            if (type != GVPM_PARENT_MEDIUM && !(m & GVPM_SURF2MEDIA)) contributes = false;
+          }
+          if (P.cfg.path_set && parity != ((R.px + R.py) % 2)) contributes = false;
+        }
+        if (P.counts) {
+          atomicAdd(P.counts + 2 * (size_t)key, 1u);
+          if (contributes) atomicAdd(P.counts + 2 * (size_t)key + 1, 1u);
+        }
+        if (P.dump_pairs) {
+          const unsigned long long slot = atomicAdd(P.dump_counter, 1ull);
+          if (slot < P.dump_cap) P.dump_pairs[slot] = make_uint2(key, origBeam | (contributes ? 0x80000000u : 0u));
+        } else if (contributes) {
+          beam_functor(P, rec, R, beam, kRec, a);
+        }
+      }
+    }
+    if (P.dump_pairs) continue;
+    const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const bool same = lane - off >= start;
+#pragma unroll
+      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) {
+        const float vu = __shfl_up_sync(0xffffffffu, a[j], off);
+        if (same) a[j] += vu;
+      }
+    }
+    if (valid && (lane == 31 || (heads >> (lane + 1) & 1u))) {
+      float *o = P.out + (size_t)key * GVPM_OUT_FLOATS;
+#pragma unroll
+      for (int j = 0; j < GVPM_OUT_FLOATS; ++j)
+        if (a[j] != 0.f) atomicAdd(o + j, a[j]);
+    }
+  }
+}
+
+// ---- host-side launchers -----------------------------------------------------------------------
+void launch_sub_gather(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *out, cudaStream_t st) {
+  if (n) k_sub_gather<<<(n + 255) / 256, 256, 0, st>>>(raw, sorted, n, out);
+}
+void launch_subbeam_leaf_boxes(const float4 *subs, const float4 *beams, uint32_t n, uint32_t nLeaves, float radius,
+                               float4 *lo, float4 *hi, cudaStream_t st) {
+  if (nLeaves) k_subbeam_leaf_boxes<<<(nLeaves + 7) / 8, 256, 0, st>>>(subs, beams, n, nLeaves, radius, lo, hi);
+}
+
+static int g_bt_blocks = 0, g_bs_blocks = 0;
+cudaError_t launch_beam_traverse(const GatherParams &P, int sm_count, cudaStream_t stream) {
+  if (P.ray_end <= P.ray_begin) return cudaSuccess;
+  if (g_bt_blocks == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_bt_blocks, k_beam_traverse, kBeamWarps * 32, 0);
+    if (g_bt_blocks < 1) g_bt_blocks = 1;
+  }
+  unsigned grid = (unsigned)(sm_count * g_bt_blocks);
+  const unsigned packets = (P.ray_end - P.ray_begin + BPK - 1) / BPK;
+  const unsigned need = (packets + kBeamWarps - 1) / kBeamWarps;
+  if (grid > need) grid = need;
+  k_beam_traverse<<<grid, kBeamWarps * 32, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream) {
+  if (total == 0) return cudaSuccess;
+  if (g_bs_blocks == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_bs_blocks, k_beam_shade, 128, 0);
+    if (g_bs_blocks < 1) g_bs_blocks = 1;
+  }
+  unsigned long long need = (total + 127) / 128;
+  unsigned long long grid = (unsigned long long)sm_count * g_bs_blocks * 4;
+  if (grid > need) grid = need;
+  k_beam_shade<<<(unsigned)grid, 128, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace gvpm

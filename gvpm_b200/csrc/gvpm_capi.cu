@@ -26,6 +26,11 @@ void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, u
 void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st);
 cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_bre_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
+void launch_sub_gather(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *out, cudaStream_t st);
+void launch_subbeam_leaf_boxes(const float4 *subs, const float4 *beams, uint32_t n, uint32_t nLeaves, float radius,
+                               float4 *lo, float4 *hi, cudaStream_t st);
+cudaError_t launch_beam_traverse(const GatherParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
@@ -91,6 +96,13 @@ struct gvpm_ctx {
   unsigned long long pair_cap = 0;         // capacity of `pairs` in entries
   unsigned long long *pair_count_host = nullptr;  // pinned read-back of the pair counter
   unsigned long long last_pairs = 0;
+  // G-Beams
+  DevBuf beams, beam_bounds, sub_pos, sub_raw, subs, beam_box_lo, beam_box_hi;
+  std::vector<float4> beam_host;
+  uint32_t n_beams = 0;
+  bool beams_loaded = false, beams_built = false;
+  Tree beam_tree{};
+  float beam_radius = 0.f;
   DevBuf samples, sample_counts, mvol;  // G-VPM distance samples
   uint32_t n_samples = 0;
   bool samples_loaded = false;
@@ -335,7 +347,8 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
                     &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs,
-                    &ctx->samples, &ctx->sample_counts, &ctx->mvol};
+                    &ctx->samples, &ctx->sample_counts, &ctx->mvol, &ctx->beams, &ctx->beam_bounds, &ctx->sub_pos,
+                    &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -607,6 +620,261 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   ctx->launches += 1;
   CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+// ---- G-Beams 3D --------------------------------------------------------------------------------
+int gvpm_upload_beams(gvpm_ctx *ctx, const gvpm_beam_soa *b, size_t n) {
+  if (!ctx || (n && !b) || n > 0x0ffffff0u) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ctx->n_beams = (uint32_t)n;
+  ctx->beams_loaded = true;
+  ctx->beams_built = false;
+  ctx->beam_host.assign(8 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (n == 0) return GVPM_OK;
+  if (!b->origin || !b->end || !b->flux || !b->prefix_flux || !b->parent_n || !b->parent_albedo || !b->pred_pos ||
+      !b->end_n || !b->parent_pdf || !b->rr_weight || !b->parent_type || !b->end_on_surface || !b->depth || !b->path_id)
+    return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_beam_soa");
+  for (size_t i = 0; i < n; ++i) {
+    const float *o = b->origin + 3 * i, *e = b->end + 3 * i;
+    // PhotonBeam::setEndPoint (beams_struct.h:73-81): dir = p2 - p1; length = |dir|; dir /= length
+    float d[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
+    const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float rcp = 1.0f / len;
+    d[0] *= rcp; d[1] *= rcp; d[2] *= rcp;
+    uint32_t meta = pack_meta(b->parent_type[i], b->depth[i], b->path_id[i]) | ((b->end_on_surface[i] ? 1u : 0u) << 11);
+    float mf;
+    memcpy(&mf, &meta, 4);
+    float4 *r = &ctx->beam_host[8 * i];
+    r[0] = make_float4(o[0], o[1], o[2], len);
+    r[1] = make_float4(d[0], d[1], d[2], mf);
+    r[2] = make_float4(b->flux[3 * i], b->flux[3 * i + 1], b->flux[3 * i + 2], b->parent_pdf[i]);
+    r[3] = make_float4(b->prefix_flux[3 * i], b->prefix_flux[3 * i + 1], b->prefix_flux[3 * i + 2], b->rr_weight[i]);
+    r[4] = make_float4(b->parent_n[3 * i], b->parent_n[3 * i + 1], b->parent_n[3 * i + 2], e[0]);
+    r[5] = make_float4(b->parent_albedo[3 * i], b->parent_albedo[3 * i + 1], b->parent_albedo[3 * i + 2], e[1]);
+    r[6] = make_float4(b->pred_pos[3 * i], b->pred_pos[3 * i + 1], b->pred_pos[3 * i + 2], e[2]);
+    r[7] = make_float4(b->end_n[3 * i], b->end_n[3 * i + 1], b->end_n[3 * i + 2], 0.f);
+  }
+  CK(ctx->beams.reserve(8 * n * sizeof(float4)));
+  CK(cudaMemcpyAsync(ctx->beams.p, ctx->beam_host.data(), 8 * n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (!ctx->beams_loaded) return fail(ctx, GVPM_ERR_INVALID, "no beams uploaded");
+  if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nb = ctx->n_beams;
+  // sub-beam split, SubBeamBVH ctor (beams_accel.h:98-124): size = average length / 10
+  float avgSize = 0.f;
+  for (size_t i = 0; i < nb; ++i) avgSize += ctx->beam_host[8 * i].w;
+  if (nb) avgSize /= (float)nb;
+  const float subbeamSize = avgSize / 10;
+  std::vector<float> subPos;
+  std::vector<float4> subRaw;
+  for (size_t i = 0; i < nb; ++i) {
+    const float4 b0 = ctx->beam_host[8 * i], b1 = ctx->beam_host[8 * i + 1];
+    int nSub = subbeamSize > 0.f ? (int)std::ceil(b0.w / subbeamSize) : 1;
+    if (nSub < 1) nSub = 1;
+    const float lengthSub = b0.w / nSub;
+    for (int k = 0; k < nSub; ++k) {
+      const float t1 = lengthSub * k, t2 = lengthSub * (k + 1), tm = lengthSub * (k + 0.5f);
+      subPos.push_back(b0.x + b1.x * tm);
+      subPos.push_back(b0.y + b1.y * tm);
+      subPos.push_back(b0.z + b1.z * tm);
+      uint32_t bi = (uint32_t)i, fl = (k == 0 ? 1u : 0u) | (k == nSub - 1 ? 2u : 0u);
+      float bf, ff;
+      memcpy(&bf, &bi, 4);
+      memcpy(&ff, &fl, 4);
+      subRaw.push_back(make_float4(t1, t2, bf, ff));
+    }
+  }
+  const uint32_t n = (uint32_t)subRaw.size();
+  CK(cudaEventRecord(ctx->ev[0], st));
+  Tree T{};
+  T.n = n;
+  uint32_t cnt = (n + 31) / 32, total = 0;
+  int levels = 0;
+  if (n > 0) {
+    for (;;) {
+      T.cnt[levels] = cnt;
+      T.off[levels] = total;
+      total += cnt;
+      ++levels;
+      if (cnt <= 32) break;
+      if (levels >= GVPM_MAX_LEVELS) return fail(ctx, GVPM_ERR_INVALID, "too many sub-beams");
+      cnt = (cnt + 31) / 32;
+    }
+  }
+  T.levels = levels;
+  CK(ctx->beam_bounds.reserve(256));
+  if (n > 0) {
+    CK(ctx->sub_pos.reserve(12 * (size_t)n));
+    CK(ctx->sub_raw.reserve(16 * (size_t)n));
+    CK(ctx->subs.reserve(16 * (size_t)n));
+    CK(ctx->keys_in.reserve(8 * (size_t)n));
+    CK(ctx->keys_out.reserve(8 * (size_t)n));
+    CK(ctx->vals_in.reserve(4 * (size_t)n));
+    CK(ctx->vals_out.reserve(4 * (size_t)n));
+    CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
+    CK(ctx->beam_box_lo.reserve(16 * (size_t)total));
+    CK(ctx->beam_box_hi.reserve(16 * (size_t)total));
+    CK(cudaMemcpyAsync(ctx->sub_pos.p, subPos.data(), 12 * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->sub_raw.p, subRaw.data(), 16 * (size_t)n, cudaMemcpyHostToDevice, st));
+    launch_bounds(ctx->sub_pos.as<float>(), n, ctx->bounds_partial.as<float>(), ctx->beam_bounds.as<float>(), st);
+    launch_morton(ctx->sub_pos.as<float>(), n, ctx->beam_bounds.as<float>(), ctx->keys_in.as<uint64_t>(),
+                  ctx->vals_in.as<uint32_t>(), st);
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+                ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
+    launch_sub_gather(ctx->sub_raw.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->subs.as<float4>(), st);
+    float4 *lo = ctx->beam_box_lo.as<float4>(), *hi = ctx->beam_box_hi.as<float4>();
+    launch_subbeam_leaf_boxes(ctx->subs.as<float4>(), ctx->beams.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
+    for (int l = 1; l < levels; ++l)
+      launch_level_boxes(lo + T.off[l - 1], hi + T.off[l - 1], T.cnt[l - 1], T.cnt[l], lo + T.off[l], hi + T.off[l], st);
+    ctx->launches += 5 + (levels - 1) + 4;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // subPos / subRaw are stack-owned host vectors
+  } else {
+    CK(cudaMemsetAsync(ctx->beam_bounds.p, 0, 7 * sizeof(float), st));
+  }
+  T.lo = ctx->beam_box_lo.as<float4>();
+  T.hi = ctx->beam_box_hi.as<float4>();
+  ctx->beam_tree = T;
+  ctx->beam_radius = radius;
+  ctx->beams_built = true;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->timed_build = true;
+  return GVPM_OK;
+}
+
+static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
+  if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
+  if (!ctx->beams_built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_beams has not been called");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
+  if (!ctx->cfg.kernel_3d) return fail(ctx, GVPM_ERR_UNSUPPORTED, "only the beam3d kernel is implemented");
+  memset(&P, 0, sizeof(P));
+  P.tree = ctx->beam_tree;
+  P.rays = ctx->rays.as<float4>();
+  P.n_rays = ctx->n_rays;
+  const float r = ctx->beam_radius;
+  P.radius = r;
+  P.radius_sq = r * r;
+  P.kernel_vol = (float)((4.0 / 3.0) * (double)GVPM_PI * std::pow((double)r, 3));
+  P.weight_kernel = (float)(1.0 / P.kernel_vol);  // shift_volume_beams.h:272
+  P.bounds = ctx->beam_bounds.as<float>();
+  for (int i = 0; i < 3; ++i) {
+    P.sigma_s[i] = ctx->medium.sigma_s[i];
+    P.sigma_t[i] = ctx->medium.sigma_s[i] + ctx->medium.sigma_a[i];
+  }
+  P.phase_type = ctx->medium.phase_type;
+  P.hg_g = ctx->medium.hg_g;
+  P.sampling_weight = ctx->medium.sampling_weight;
+  P.cfg = ctx->cfg;
+  P.tri = ctx->tri.as<float>();
+  P.tri_plane = ctx->tri_plane.as<float4>();
+  P.n_tri = ctx->n_tri;
+  P.out = ctx->out.as<float>();
+  P.counts = ctx->counts.as<uint32_t>();
+  P.work_counter = ctx->work_counter.as<uint32_t>();
+  P.pair_counter = (unsigned long long *)(ctx->work_counter.as<char>() + 8);
+  P.dump_counter = (unsigned long long *)(ctx->work_counter.as<char>() + 16);
+  P.ray_begin = 0;
+  P.ray_end = ctx->n_rays;
+  P.beams = ctx->beams.as<float4>();
+  P.subs = ctx->subs.as<float4>();
+  P.n_beams = ctx->n_beams;
+  return GVPM_OK;
+}
+
+// traverse + shade with pair-list growth; dump != nullptr: fill the flat geometric pair list instead of shading
+static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
+  const size_t nr = ctx->n_rays;
+  if (ctx->pair_cap == 0) {
+    CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 64 * nr) * sizeof(uint2)));
+    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+  }
+  P.beam_prefilter = (want_counts || P.dump_pairs) ? 0 : 1;
+  unsigned long long total = 0;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    P.pairs = ctx->pairs.as<uint2>();
+    P.pair_cap = ctx->pair_cap;
+    CK(cudaMemsetAsync(ctx->work_counter.p, 0, 32, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(launch_beam_traverse(P, ctx->sm_count, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->launches += nr ? 1 : 0;
+    CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    total = *ctx->pair_count_host;
+    if (total <= ctx->pair_cap) break;
+    if (attempt == 3) return fail(ctx, GVPM_ERR_CUDA, "beam pair list overflow");
+    CK(ctx->pairs.reserve((total + total / 8 + 1024) * sizeof(uint2)));
+    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+  }
+  ctx->last_pairs = total;
+  if (nr) {
+    CK(cudaMemsetAsync(ctx->out.p, 0, nr * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(ctx->counts.p, 0, nr * 8, ctx->stream));
+  }
+  CK(launch_beam_shade(P, total, ctx->sm_count, ctx->stream));
+  ctx->launches += total ? 1 : 0;
+  return GVPM_OK;
+}
+
+int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  GatherParams P;
+  int rc = beam_params(ctx, P);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  rc = beams_run(ctx, P, counts != nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap) {
+  if (!ctx || !offsets) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n_rays;
+  std::vector<float> tmp(n * GVPM_OUT_FLOATS + 1);
+  std::vector<uint32_t> counts(2 * n + 2);
+  int rc = gvpm_gather_beams(ctx, tmp.data(), counts.data());
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { offsets[i] = total; total += counts[2 * i]; }
+  offsets[n] = total;
+  if (total > cap || (total && !idx)) return fail(ctx, GVPM_ERR_INVALID, "neighbour buffer too small");
+  if (total == 0) return GVPM_OK;
+  CK(ctx->nbr_idx.reserve(total * sizeof(uint2)));
+  GatherParams P;
+  rc = beam_params(ctx, P);
+  if (rc) return rc;
+  P.counts = nullptr;
+  P.dump_pairs = ctx->nbr_idx.as<uint2>();
+  P.dump_cap = total;
+  rc = beams_run(ctx, P, true);
+  if (rc) return rc;
+  std::vector<uint2> flat(total);
+  CK(cudaMemcpyAsync(flat.data(), ctx->nbr_idx.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // bucket by ray, ascending beam index inside a ray
+  std::vector<uint64_t> cursor(offsets, offsets + n);
+  for (const uint2 &p : flat) idx[cursor[p.x]++] = p.y;
+  for (size_t i = 0; i < n; ++i)
+    std::sort(idx + offsets[i], idx + offsets[i + 1],
+              [](uint32_t a, uint32_t b) { return (a & 0x7fffffffu) < (b & 0x7fffffffu); });
   return GVPM_OK;
 }
 

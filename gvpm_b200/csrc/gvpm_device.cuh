@@ -143,7 +143,32 @@ struct GatherParams {
   uint32_t *sample_counts;            // [n_samples*2] found / contributing, or null
   uint32_t *mvol;                     // [n_rays] sum of `found` over the ray's samples, or null
   float vpm_normalization;            // 1 / nbCameraSamples
+  // G-Beams: 8 float4 per beam, sub-beam records sorted in Morton order (tree = hierarchy
+  // over sub-beams): sub[i] = t1, t2, beam index (bits), flags (bit 0 first, bit 1 last sub-beam)
+  const float4 *beams;
+  const float4 *subs;
+  uint32_t n_beams;
+  float weight_kernel;                // 1.0 / kernelVol (double division rounded to Float)
+  int beam_prefilter;                 // apply the depth/mode/pathSet filters already in the traversal
+                                      // (when the caller does not ask for the geometric neighbour counts)
+  // parity dump for beams: flat list of (ray, beam | contributes << 31) + its atomic cursor
+  uint2 *dump_pairs;
+  unsigned long long *dump_counter;
+  unsigned long long dump_cap;
 };
+
+// ---- strictly rounded double (the reference's fp64 island: cylinderIntersection / solveQuadraticDouble,
+// photonmapper/beams_3d_intersections.h:100-137, src/libcore/util.cpp:487-525) ----------------------------
+struct sd {
+  double v;
+  __host__ __device__ sd() : v(0.0) {}
+  __host__ __device__ sd(double x) : v(x) {}
+};
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sd dsqrt(sd a) { return sd(__dsqrt_rn(a.v)); }
 
 #ifndef GVPM_PACKET
 #define GVPM_PACKET 4  // camera rays per traversal warp

@@ -93,6 +93,33 @@ _VPM_FIELDS = [
 ]
 
 
+_BEAM_FIELDS = [
+    ("origin", np.float32, 3), ("end", np.float32, 3), ("flux", np.float32, 3), ("prefix_flux", np.float32, 3),
+    ("parent_n", np.float32, 3), ("parent_albedo", np.float32, 3), ("pred_pos", np.float32, 3),
+    ("end_n", np.float32, 3), ("parent_pdf", np.float32, 1), ("rr_weight", np.float32, 1),
+    ("parent_type", np.uint8, 1), ("end_on_surface", np.uint8, 1), ("depth", np.uint8, 1),
+    ("path_id", np.uint32, 1),
+]
+
+
+class BeamSet(_SoA):
+    """Photon beams (LTPhotonBeam, gvpm/gvpm_beams.h:18-43) flattened with their parent-vertex data."""
+    FIELDS = _BEAM_FIELDS
+    CSTRUCT = N.BeamSoA
+
+
+def synth_beams(n, medium, seed=0xC0FFEE, max_depth=12, rr_depth=1, min_depth=0, power=100.0, threads=8):
+    """Seeded light-path random walks -> BeamSet (every medium edge); returns (beams, nbPathBeams)."""
+    s = N.load_synth()
+    bs = BeamSet(n)
+    cs = bs.as_c()
+    paths = s.gvpm_synth_beams(seed, n, C.byref(medium), max_depth, rr_depth, min_depth, power, threads,
+                               C.byref(cs))
+    if paths < 0:
+        raise RuntimeError("gvpm_synth_beams failed")
+    return bs, int(paths)
+
+
 class VpmSampleSet(_SoA):
     """Camera distance samples of the G-VPM gather (gvpm.cpp:1141-1175), one per (pixel, sample)."""
     FIELDS = _VPM_FIELDS
@@ -126,7 +153,7 @@ def make_medium(sigma_t=2.0, albedo=0.8, phase="isotropic", g=0.0, sampling_weig
 
 def make_config(film_w, film_h, max_depth=12, min_depth=0, lighting_mode=N.ALL2MEDIA, use_mis=True,
                 use_shift_null=True, path_set=True, power_heuristic=False, kernel_3d=True,
-                shadow_maxt_scale=1e-3, epsilon=1e-4):
+                shadow_maxt_scale=1e-3, epsilon=1e-4, long_beams=False, rng_seed=0):
     """Defaults = the paper presets (scripts/scene/generatorGVPM.py:44-50: useMIS=area, mixed shift,
     maxDepth 12) with pathSet at its plugin default (gvpm_struct.h:328)."""
     c = N.Config()
@@ -135,6 +162,7 @@ def make_config(film_w, film_h, max_depth=12, min_depth=0, lighting_mode=N.ALL2M
     c.power_heuristic, c.kernel_3d = int(power_heuristic), int(kernel_3d)
     c.film_w, c.film_h = film_w, film_h
     c.shadow_maxt_scale, c.epsilon = shadow_maxt_scale, epsilon
+    c.long_beams, c.rng_seed = int(long_beams), int(rng_seed) & 0xFFFFFFFF
     return c
 
 

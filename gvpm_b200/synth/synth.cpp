@@ -121,13 +121,16 @@ struct Params {
   float sigma_s, sigma_a, hg_g;
   int phase_type, max_depth, rr_depth, min_depth;
   float power;
+  bool emit_beams = false;  // emit photon beams (light-path edges) instead of volume photons
 };
 
-struct PhotonRec {
+struct PhotonRec {  // a volume photon, or (emit_beams) a photon beam: pos = end, parent = origin
   Vec pos, flux, parent, pred, pn, prefix, albedo;
   float ppdf, epdf, rr;
   uint8_t ptype, depth;
   uint32_t path;  // local path counter, fixed up on merge
+  Vec endN = {0, 0, 0};
+  uint8_t endSurf = 0;
 };
 
 struct Vtx {
@@ -198,7 +201,30 @@ int walk(uint64_t seed, uint64_t pathIdx, const Params &P, std::vector<PhotonRec
                 cur.weight.z * cur.rr * cur.edgeWeight.z};
     Vec flux = {thr.x * step.x, thr.y * step.y, thr.z * step.z};
     size_t ni = ci + 1;  // vertexId of nv
-    if (inMedium && ni >= (size_t)std::max(2, P.min_depth + 1)) {
+    if (P.emit_beams) {
+      // photon beam = edge ci (vertex ci -> ci+1) inside the medium, LTBeamMap::tryAppendLT
+      // (gvpm_beams.h:54-84): i >= max(minDepth, 1); flux excludes the edge's own transmittance (:29-35)
+      if (ci >= (size_t)std::max(1, P.min_depth)) {
+        PhotonRec r;
+        r.pos = nv.pos;       // beam end
+        r.parent = cur.pos;   // beam origin = parent vertex of the reconnection
+        r.flux = {thr.x * cur.weight.x * cur.rr, thr.y * cur.weight.y * cur.rr, thr.z * cur.weight.z * cur.rr};
+        r.pred = ci >= 2 ? v[ci - 1].pos : Vec{1, 1, 1};
+        r.pn = cur.n;
+        r.prefix = prefix;
+        r.albedo = cur.albedo;
+        r.ppdf = cur.pdfArea;
+        r.epdf = cur.edgePdf;
+        r.rr = cur.rr;
+        r.ptype = (uint8_t)cur.type;
+        r.depth = (uint8_t)ci;
+        r.path = 0;
+        r.endN = nv.n;
+        r.endSurf = inMedium ? 0 : 1;
+        out.push_back(r);
+        ++appended;
+      }
+    } else if (inMedium && ni >= (size_t)std::max(2, P.min_depth + 1)) {
       PhotonRec r;
       r.pos = nv.pos;
       r.flux = flux;
@@ -257,33 +283,20 @@ void put3(float *dst, size_t i, Vec v) { dst[3 * i] = v.x; dst[3 * i + 1] = v.y;
 
 extern "C" {
 
-// Fills the SoA arrays (caller-allocated, n entries each) with exactly n photons.
-// Returns the number of light paths traced (nbPathVolume incl. empty ones), or -1.
-long long gvpm_synth_photons(uint64_t seed, size_t n, const gvpm_medium *med, int max_depth, int rr_depth,
-                             int min_depth, float power, int threads, gvpm_photon_soa *out) {
-  Params P;
-  P.sigma_s = med->sigma_s[0];
-  P.sigma_a = med->sigma_a[0];
-  P.hg_g = med->hg_g;
-  P.phase_type = med->phase_type;
-  P.max_depth = max_depth > 0 ? max_depth : 64;
-  P.rr_depth = rr_depth;
-  P.min_depth = min_depth;
-  P.power = power;
+}  // extern "C" (re-opened below)
+
+namespace {
+// Walks light paths 0, 1, 2, ... (chunks of paths on worker threads, merged in path order so the result
+// does not depend on the thread count) until n records are stored; emit(slot, record, pathID).
+template <typename Emit>
+long long runWalks(uint64_t seed, size_t n, const Params &P, int threads, Emit &&emit) {
   if (threads < 1) threads = 1;
   const uint64_t chunk = 2048;  // paths per work item
   size_t filled = 0;
   uint64_t pathBase = 0;
   uint32_t pathIdCounter = 0;
   long long totalPaths = 0;
-  float *pos = (float *)out->pos, *flux = (float *)out->flux, *ppos = (float *)out->parent_pos,
-        *pred = (float *)out->pred_pos, *pn = (float *)out->parent_n, *prefix = (float *)out->prefix_flux,
-        *alb = (float *)out->parent_albedo, *ppdf = (float *)out->parent_pdf, *epdf = (float *)out->edge_pdf,
-        *rr = (float *)out->rr_weight;
-  uint8_t *ptype = (uint8_t *)out->parent_type, *depth = (uint8_t *)out->depth;
-  uint32_t *pid = (uint32_t *)out->path_id;
   while (filled < n) {
-    // estimate how many chunks this round (photons per path ~2-4); keep rounds bounded
     size_t remaining = n - filled;
     size_t nChunks = std::max<size_t>((size_t)threads, remaining / (chunk * 2) + 1);
     nChunks = std::min<size_t>(nChunks, 4096);
@@ -315,17 +328,12 @@ long long gvpm_synth_photons(uint64_t seed, size_t n, const gvpm_medium *med, in
         ++totalPaths;
         uint32_t stored = 0;
         for (uint32_t j = 0; j < cnt; ++j) {
-          if (filled >= n) break;  // map full: GPhotonMap::outCapacity, gvpm_accel.h:174-176
-          const PhotonRec &r = res[c][off + j];
-          put3(pos, filled, r.pos); put3(flux, filled, r.flux); put3(ppos, filled, r.parent);
-          put3(pred, filled, r.pred); put3(pn, filled, r.pn); put3(prefix, filled, r.prefix);
-          put3(alb, filled, r.albedo);
-          ppdf[filled] = r.ppdf; epdf[filled] = r.epdf; rr[filled] = r.rr;
-          ptype[filled] = r.ptype; depth[filled] = r.depth; pid[filled] = pathIdCounter;
+          if (filled >= n) break;  // map full: outCapacity, gvpm_accel.h:174-176 / beams.h tryAppend
+          emit(filled, res[c][off + j], pathIdCounter);
           ++filled;
           ++stored;
         }
-        if (stored) ++pathIdCounter;  // gvpm_accel.h:194-197
+        if (stored) ++pathIdCounter;  // gvpm_accel.h:194-197, gvpm_beams.h:77-81
         off += cnt;
         if (filled >= n) done = true;
       }
@@ -333,6 +341,62 @@ long long gvpm_synth_photons(uint64_t seed, size_t n, const gvpm_medium *med, in
     pathBase += nChunks * chunk;
   }
   return totalPaths;
+}
+
+Params makeParams(const gvpm_medium *med, int max_depth, int rr_depth, int min_depth, float power) {
+  Params P;
+  P.sigma_s = med->sigma_s[0];
+  P.sigma_a = med->sigma_a[0];
+  P.hg_g = med->hg_g;
+  P.phase_type = med->phase_type;
+  P.max_depth = max_depth > 0 ? max_depth : 64;
+  P.rr_depth = rr_depth;
+  P.min_depth = min_depth;
+  P.power = power;
+  return P;
+}
+}  // namespace
+
+extern "C" {
+
+// Fills the SoA arrays (caller-allocated, n entries each) with exactly n photons.
+// Returns the number of light paths traced (nbPathVolume incl. empty ones), or -1.
+long long gvpm_synth_photons(uint64_t seed, size_t n, const gvpm_medium *med, int max_depth, int rr_depth,
+                             int min_depth, float power, int threads, gvpm_photon_soa *out) {
+  Params P = makeParams(med, max_depth, rr_depth, min_depth, power);
+  float *pos = (float *)out->pos, *flux = (float *)out->flux, *ppos = (float *)out->parent_pos,
+        *pred = (float *)out->pred_pos, *pn = (float *)out->parent_n, *prefix = (float *)out->prefix_flux,
+        *alb = (float *)out->parent_albedo, *ppdf = (float *)out->parent_pdf, *epdf = (float *)out->edge_pdf,
+        *rr = (float *)out->rr_weight;
+  uint8_t *ptype = (uint8_t *)out->parent_type, *depth = (uint8_t *)out->depth;
+  uint32_t *pid = (uint32_t *)out->path_id;
+  return runWalks(seed, n, P, threads, [&](size_t i, const PhotonRec &r, uint32_t pathId) {
+    put3(pos, i, r.pos); put3(flux, i, r.flux); put3(ppos, i, r.parent);
+    put3(pred, i, r.pred); put3(pn, i, r.pn); put3(prefix, i, r.prefix);
+    put3(alb, i, r.albedo);
+    ppdf[i] = r.ppdf; epdf[i] = r.epdf; rr[i] = r.rr;
+    ptype[i] = r.ptype; depth[i] = r.depth; pid[i] = pathId;
+  });
+}
+
+// Same walks, emitting photon beams (every light-path edge inside the medium, LTBeamMap::tryAppendLT,
+// gvpm_beams.h:54-84).  Returns the number of light paths traced (nbPathBeams).
+long long gvpm_synth_beams(uint64_t seed, size_t n, const gvpm_medium *med, int max_depth, int rr_depth,
+                           int min_depth, float power, int threads, gvpm_beam_soa *out) {
+  Params P = makeParams(med, max_depth, rr_depth, min_depth, power);
+  P.emit_beams = true;
+  float *org = (float *)out->origin, *end = (float *)out->end, *flux = (float *)out->flux,
+        *prefix = (float *)out->prefix_flux, *pn = (float *)out->parent_n, *alb = (float *)out->parent_albedo,
+        *pred = (float *)out->pred_pos, *endn = (float *)out->end_n, *ppdf = (float *)out->parent_pdf,
+        *rr = (float *)out->rr_weight;
+  uint8_t *ptype = (uint8_t *)out->parent_type, *esurf = (uint8_t *)out->end_on_surface, *depth = (uint8_t *)out->depth;
+  uint32_t *pid = (uint32_t *)out->path_id;
+  return runWalks(seed, n, P, threads, [&](size_t i, const PhotonRec &r, uint32_t pathId) {
+    put3(org, i, r.parent); put3(end, i, r.pos); put3(flux, i, r.flux); put3(prefix, i, r.prefix);
+    put3(pn, i, r.pn); put3(alb, i, r.albedo); put3(pred, i, r.pred); put3(endn, i, r.endN);
+    ppdf[i] = r.ppdf; rr[i] = r.rr;
+    ptype[i] = r.ptype; esurf[i] = r.endSurf; depth[i] = r.depth; pid[i] = pathId;
+  });
 }
 
 // Occluder triangles of the synthetic scene: 5 walls + shelf = 12 triangles.  out: [12*9].

@@ -88,7 +88,12 @@ typedef struct gvpm_config {
                                parameter so the quirk is visible.  Default 1e-3f. */
   float epsilon;            /* Epsilon (include/mitsuba/core/constants.h:24-30, 1e-4f in single
                                precision): mint of the offset rays and of the shadow ray */
-  int32_t reserved[4];
+  int32_t long_beams;       /* photon beams were converted to long beams (convertLong, gvpm.cpp:884-887) */
+  uint32_t rng_seed;        /* G-Beams-3D draws two uniforms per (camera ray, beam) from the integrator's
+                               sampler in traversal order (shift_volume_beams.h:224,245), which no parallel
+                               gather can reproduce; they are replaced by a counter-based hash of
+                               (rng_seed, px, py, edge, beam index, dimension) — DESIGN.md §6 */
+  int32_t reserved[2];
 } gvpm_config;
 
 /* Volume photons, flattened from GPhotonNodeData + its light Path
@@ -148,6 +153,28 @@ typedef struct gvpm_vpm_sample_soa {
   const float *radius;         /* [n]   BBPourcentageCONST * gp.scaleVol of the pixel (gvpm.cpp:1131) */
 } gvpm_vpm_sample_soa;
 
+/* Photon beams, flattened from LTPhotonBeam + its light Path (gvpm/gvpm_beams.h:18-84,
+ * photonmapper/beams_struct.h:25-110).  A beam is the light-path edge i = edgeID from vertex(i) (the
+ * beam origin, which is also the PARENT vertex of the diffuse reconnection, shift_volume_beams.cpp:430-436)
+ * to vertex(i+1). */
+typedef struct gvpm_beam_soa {
+  const float *origin;        /* [n*3] vertex(i).position (p1) */
+  const float *end;           /* [n*3] vertex(i+1).position (p2); dir and length are derived as setEndPoint does */
+  const float *flux;          /* [n*3] prod_{k<i} rr*weight*edgeWeight * vertex(i).weight * rr_i, without the
+                                        transmittance of edge i (gvpm_beams.h:29-35) */
+  const float *prefix_flux;   /* [n*3] prod_{k<=i-1} weight*rr*edgeWeight (shift_volume_beams.cpp:442-449) */
+  const float *parent_n;      /* [n*3] geometric normal of a surface / emitter origin vertex */
+  const float *parent_albedo; /* [n*3] diffuse reflectance of a surface origin vertex */
+  const float *pred_pos;      /* [n*3] vertex(i-1).position, or (1,1,1) when i < 2 (:457) */
+  const float *end_n;         /* [n*3] geometric normal of vertex(i+1) when it lies on a surface */
+  const float *parent_pdf;    /* [n]   vertex(i).pdf[EImportance] (area measure) */
+  const float *rr_weight;     /* [n]   vertex(i).rrWeight */
+  const uint8_t *parent_type; /* [n]   gvpm_parent_type of vertex(i) */
+  const uint8_t *end_on_surface; /* [n] vertex(i+1).isOnSurface() */
+  const uint8_t *depth;       /* [n]   beam->depth = i */
+  const uint32_t *path_id;    /* [n]   LTPhotonBeam::pathID */
+} gvpm_beam_soa;
+
 /* Occluder triangles for the reconnection shadow ray (scene->rayIntersect,
  * shift_volume_photon.cpp:396-402), tested as Triangle::rayIntersect
  * (include/mitsuba/core/triangle.h:109-145). */
@@ -206,6 +233,18 @@ int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
  * interaction-mode / pathSet filters.  Returns GVPM_ERR_INVALID when cap is too small
  * (offsets[n_rays] then holds the needed size). */
 int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
+
+/* ---- G-Beams 3D ("beam3d"): replaces beamMap->build(EBVHAccel) + beamMap->query(radQuery) over all gather
+ *      points, gvpm.cpp:880-986 + beams_accel.h:90-243 + shift_volume_beams.cpp:139-539,748-786 ---------------
+ * gvpm_build_beams cuts the beams into sub-beams of averageLength/10 and builds the hierarchy for beam radius
+ * `radius` (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:881).  out: [n_rays*27], un-normalised (the caller
+ * divides by nbPathBeams, gvpm.cpp:958-964); counts (may be NULL, faster): [n_rays*2] = {(ray, beam) pairs
+ * with a valid kernel record, pairs that also pass the depth/mode/pathSet filters}. */
+int gvpm_upload_beams(gvpm_ctx *ctx, const gvpm_beam_soa *b, size_t n);
+int gvpm_build_beams(gvpm_ctx *ctx, float radius);
+int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts);
+/* per-ray sets of beam indices (bit 31 = contributes), CSR like gvpm_dump_neighbours_bre */
+int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
 
 /* ---- G-VPM: replaces gradientPhotonMap->evaluate(gRec, p, querySize) over all camera distance
  *      samples, gvpm.cpp:1141-1185 + kdtree.h:675-731 + shift_volume_photon.cpp:489-655 ----------------

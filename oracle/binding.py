@@ -46,8 +46,44 @@ def load():
                                     N.f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, N.f32p, N.f32p, N.u32p, N.u64p,
                                     N.u32p, C.c_size_t, C.POINTER(C.c_double)]
     lib.gvpm_oracle_vpm.restype = C.c_longlong
+    lib.gvpm_oracle_beams.argtypes = [C.POINTER(N.BeamSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                      C.POINTER(N.Medium), C.POINTER(N.Config), N.f32p, C.c_size_t, C.c_float,
+                                      C.c_int, C.c_int, N.f32p, N.u32p, N.u64p, N.u32p, C.c_size_t,
+                                      C.POINTER(C.c_double)]
+    lib.gvpm_oracle_beams.restype = C.c_longlong
     _lib = lib
     return lib
+
+
+def beams_gather(beams, rays, medium, config, tri, radius, double=False, threads=None, neighbours=False):
+    """Restated computeVolumeGradientBeams gather (gvpm.cpp:880-986), beam3d kernel, brute force over all
+    (ray, beam) pairs.  Returns a BreResult (idx = beam indices, bit 31 = contributes)."""
+    lib = load()
+    threads = hw_threads() if threads is None else threads
+    cb, cr = beams.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    ms = C.c_double(0)
+
+    def call(offp, idxp, capv):
+        r = lib.gvpm_oracle_beams(C.byref(cb), beams.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                                  tri.ctypes.data_as(N.f32p), tri.size // 9, radius, int(double), threads,
+                                  out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p), offp, idxp, capv,
+                                  C.byref(ms))
+        if r < 0:
+            raise RuntimeError(f"gvpm_oracle_beams failed: {r}")
+        return int(r)
+    offsets = idx = None
+    if neighbours:
+        offsets = np.zeros(rays.n + 1, dtype=np.uint64)
+        cap = call(offsets.ctypes.data_as(N.u64p), None, 0)
+        idx = np.zeros(max(cap, 1), dtype=np.uint32)
+        call(offsets.ctypes.data_as(N.u64p), idx.ctypes.data_as(N.u32p), cap)
+        idx = idx[:cap]
+    else:
+        call(None, None, 0)
+    return BreResult(out.reshape(rays.n, N.GVPM_OUT_FLOATS), counts.reshape(rays.n, 2), offsets, idx, ms.value, 0.0)
 
 
 def hw_threads():

@@ -545,6 +545,385 @@ template <typename Real> struct Scene {
     }
     return 2;
   }
+
+  // ---- G-Beams 3D ("beam3d" = EBeamBeam3D_Optimized) ----------------------------------------
+  struct Beam {  // LTPhotonBeam + the parent-vertex data the reconnection reads
+    V3<Real> o, dir, end, flux, prefix, pn, albedo, pred, endN;
+    Real length, parentPdf, rrWeight;
+    int parentType, depth;
+    bool endOnSurface;
+    uint32_t pathId;
+  };
+  static Beam loadBeam(const gvpm_beam_soa &s, size_t i) {
+    Beam b;
+    b.o = V3<Real>(s.origin + 3 * i);
+    b.end = V3<Real>(s.end + 3 * i);
+    b.dir = b.end - b.o;             // PhotonBeam::setEndPoint, beams_struct.h:73-81
+    b.length = b.dir.length();
+    b.dir = b.dir / b.length;
+    b.flux = V3<Real>(s.flux + 3 * i);
+    b.prefix = V3<Real>(s.prefix_flux + 3 * i);
+    b.pn = V3<Real>(s.parent_n + 3 * i);
+    b.albedo = V3<Real>(s.parent_albedo + 3 * i);
+    b.pred = V3<Real>(s.pred_pos + 3 * i);
+    b.endN = V3<Real>(s.end_n + 3 * i);
+    b.parentPdf = (Real)s.parent_pdf[i];
+    b.rrWeight = (Real)s.rr_weight[i];
+    b.parentType = s.parent_type[i];
+    b.endOnSurface = s.end_on_surface[i] != 0;
+    b.depth = s.depth[i];
+    b.pathId = s.path_id[i];
+    return b;
+  }
+
+  // coordinateSystem, src/libcore/util.cpp:600-609 (Frame(n) constructor)
+  static void coordinateSystem(const V3<Real> &a, V3<Real> &b, V3<Real> &c) {
+    if (std::abs(a.x) > std::abs(a.y)) {
+      Real invLen = (Real)1 / std::sqrt(a.x * a.x + a.z * a.z);
+      c = V3<Real>(a.z * invLen, 0, -a.x * invLen);
+    } else {
+      Real invLen = (Real)1 / std::sqrt(a.y * a.y + a.z * a.z);
+      c = V3<Real>(0, a.z * invLen, -a.y * invLen);
+    }
+    b = cross(c, a);
+  }
+
+  // solveQuadraticDouble, src/libcore/util.cpp:487-525
+  static bool solveQuadraticDouble(double a, double b, double c, double &x0, double &x1) {
+    if (a == 0) {
+      if (b != 0) { x0 = x1 = -c / b; return true; }
+      return false;
+    }
+    double discrim = b * b - 4.0f * a * c;
+    if (discrim < 0) return false;
+    double temp, sqrtDiscrim = std::sqrt(discrim);
+    if (b < 0) temp = -0.5f * (b - sqrtDiscrim); else temp = -0.5f * (b + sqrtDiscrim);
+    x0 = temp / a;
+    x1 = c / temp;
+    if (x0 > x1) std::swap(x0, x1);
+    return true;
+  }
+
+  // cylinderIntersection, photonmapper/beams_3d_intersections.h:77-140.  The cylinder is the segment
+  // (co, cd, [0, cMaxt]) with radius `radius`; the "view" ray is (vo, vd, maxt = vMaxt).  The world ->
+  // cylinder-frame transform is restated as Frame(cd).toLocal(p - co) (the reference composes 4x4
+  // matrices, Transform::translate * Transform::fromFrame, and applies the stored inverse).
+  static bool cylinderIntersection(const V3<Real> &co, const V3<Real> &cd, Real cMaxt, const V3<Real> &vo,
+                                   const V3<Real> &vd, Real vMaxt, Real radius, double &tNear, double &tFar) {
+    const V3<Real> d1d2c = cross(vd, cd);
+    const float sinThetaSqr = (float)dot(d1d2c, d1d2c);
+    const float ad = (float)dot(co - vo, d1d2c);
+    if (ad * ad >= (radius * radius) * sinThetaSqr) return false;
+    V3<Real> s, t;
+    coordinateSystem(cd, s, t);
+    const V3<Real> rel = vo - co;
+    const V3<Real> lo(dot(rel, s), dot(rel, t), dot(rel, cd)), ld(dot(vd, s), dot(vd, t), dot(vd, cd));
+    const Real lMax = cMaxt;
+    const double ox = lo.x, oy = lo.y, dx = ld.x, dy = ld.y;
+    const double A = dx * dx + dy * dy;
+    const double B = 2 * (dx * ox + dy * oy);
+    const double C = ox * ox + oy * oy - radius * radius;
+    if (!solveQuadraticDouble(A, B, C, tNear, tFar)) return false;
+    if (tNear > vMaxt || tFar < 0) return false;
+    const double zPosNear = lo.z + ld.z * tNear;
+    const double zPosFar = lo.z + ld.z * tFar;
+    if (zPosNear < 0) {
+      if (zPosFar < 0) return false;
+      float th = (float)(tNear + (tFar - tNear) * (zPosNear) / (zPosNear - zPosFar));
+      tNear = th;
+      return true;
+    } else if (zPosNear >= 0 && zPosNear < lMax) {
+      return true;
+    } else if (zPosNear > lMax) {
+      if (zPosFar > lMax) return false;
+      float th = (float)(tNear + (tFar - tNear) * (zPosNear - lMax) / (zPosNear - zPosFar));
+      tNear = th;
+      return true;
+    }
+    return false;
+  }
+
+  // The two uniforms per (camera ray, beam) that replace sampler->next1D()
+  static uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+  }
+  Real beamUniform(const CamRay<Real> &ray, uint32_t beamIndex, uint32_t dim) const {
+    uint32_t h = hash32(cfg.rng_seed ^ 0x9E3779B9u);
+    h = hash32(h ^ (uint32_t)ray.px);
+    h = hash32(h ^ ((uint32_t)ray.py * 0x85EBCA6Bu));
+    h = hash32(h ^ ((uint32_t)ray.edgeId * 0xC2B2AE35u));
+    h = hash32(h ^ beamIndex);
+    h = hash32(h ^ (dim * 0x27D4EB2Fu));
+    return (Real)((float)(h >> 8) * (1.0f / 16777216.0f));
+  }
+
+  // BeamKernelRecord, gvpm/shift/shift_volume_beams.h:24-288
+  struct BeamKernelRecord {
+    Real v = 0, w = 0, pdfKernel = 0, pdfEdgeFailure = 0, weightKernel = 0;
+    V3<Real> beamTrans, contrib;
+    bool isValid() const { return !(contrib.x == 0 && contrib.y == 0 && contrib.z == 0); }
+    Real pdf() const { return pdfEdgeFailure * pdfKernel; }
+  };
+
+  // BeamKernelRecord::eval, EBeamBeam3D_Optimized branch (shift_volume_beams.h:195-283), for the whole
+  // beam (tmin = 0, tmax = length): the per-sub-beam ownership rule (:214-220) then reads
+  // "tNear < 0 or 0 < tNear < length" (DESIGN.md §6).
+  BeamKernelRecord beamKernelEval(const Beam &beam, const V3<Real> &camO, const V3<Real> &camD, Real camMint,
+                                  Real camMaxt, Real xi1, Real xi2) const {
+    BeamKernelRecord k;
+    const Real r = radius;
+    const V3<Real> camStart = camO + camMint * camD;
+    double tNearBeam, tFarBeam;
+    if (!cylinderIntersection(camStart, camD, camMaxt - camMint, beam.o, beam.dir, beam.length, r, tNearBeam, tFarBeam))
+      return k;
+    if (tNearBeam < 0) {
+    } else if (tNearBeam > 0 && tNearBeam < beam.length) {
+    } else {
+      return k;
+    }
+    k.v = (Real)(tNearBeam + (tFarBeam - tNearBeam) * xi1);
+    k.pdfKernel = (Real)(1.0 / std::max(tFarBeam - tNearBeam, 0.0001));
+    if (k.v < 0 || k.v > beam.length) return k;
+    const V3<Real> kernelCentroid = beam.o + beam.dir * k.v;
+    const Real distToProj = dot(kernelCentroid - camO, camD);
+    const Real distSqr = ((camO + distToProj * camD) - kernelCentroid).lengthSquared();
+    const Real radSqr = r * r;
+    if (distSqr >= radSqr) return k;
+    const Real deltaT = safe_sqrt(radSqr - distSqr);
+    k.w = distToProj - deltaT + 2 * deltaT * xi2;
+    k.pdfKernel = (Real)(k.pdfKernel * (1.0 / std::max(2.0 * deltaT, 0.0001)));
+    if (k.w < camMint || k.w > camMaxt) return k;
+    typename Medium<Real>::Rec mRecBeam = medium.eval(0, k.v), mRecCamera = medium.eval(0, k.w);
+    const Real phaseTerm = medium.phase(-beam.dir, -camD);
+    const Real kernelVol = (Real)((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3));
+    k.contrib = ((((beam.flux * mRecBeam.transmittance) * medium.sigmaS) * mRecCamera.transmittance) * phaseTerm) /
+                k.pdfKernel;
+    k.weightKernel = (Real)(1.0 / kernelVol);
+    k.beamTrans = mRecBeam.transmittance;
+    if (!cfg.long_beams) {
+      k.contrib = k.contrib / mRecBeam.pdfFailure;
+      k.pdfEdgeFailure = mRecBeam.pdfFailure;
+    } else {
+      k.pdfEdgeFailure = 1;
+    }
+    return k;
+  }
+
+  // BeamKernelRecord(ori, medium, beam, cameraRay): the null-shift re-evaluation, shift_volume_beams.h:39-143
+  BeamKernelRecord beamKernelNull(const BeamKernelRecord &ori, const Beam &beam, const V3<Real> &camO,
+                                  const V3<Real> &camD, Real camMint, Real camMaxt) const {
+    BeamKernelRecord k;
+    const Real r = radius;
+    const V3<Real> camStart = camO + camMint * camD;
+    double tNearBeam, tFarBeam;
+    if (!cylinderIntersection(camStart, camD, camMaxt - camMint, beam.o, beam.dir, beam.length, r, tNearBeam, tFarBeam))
+      return k;
+    k.v = ori.v;
+    k.pdfKernel = (Real)(1.0 / std::max(tFarBeam - tNearBeam, 0.0001));
+    if (k.v < 0 || k.v > beam.length) return k;
+    const V3<Real> kernelCentroid = beam.o + beam.dir * k.v;
+    const Real distToProj = dot(kernelCentroid - camO, camD);
+    const Real distSqr = ((camO + distToProj * camD) - kernelCentroid).lengthSquared();
+    const Real radSqr = r * r;
+    if (distSqr >= radSqr) return k;
+    const Real deltaT = safe_sqrt(radSqr - distSqr);
+    k.w = ori.w;
+    k.pdfKernel = (Real)(k.pdfKernel * (1.0 / std::max(2.0 * deltaT, 0.0001)));
+    if (k.w < camMint || k.w > camMaxt) return k;
+    k.contrib = ori.contrib * (ori.pdfKernel / k.pdfKernel);
+    k.weightKernel = ori.weightKernel;
+    k.beamTrans = ori.beamTrans;
+    k.pdfEdgeFailure = cfg.long_beams ? (Real)1 : ori.pdfEdgeFailure;
+    return k;
+  }
+
+  // BeamKernelRecord::kernelPDF, shift_volume_beams.h:298-336 (3-D optimized)
+  Real beamKernelPDF(const V3<Real> &camO, const V3<Real> &camD, Real camMaxt, const V3<Real> &orgBeam,
+                     const V3<Real> &dBeam, Real newDLength) const {
+    const Real r = radius;
+    double tNearBeam, tFarBeam;
+    if (cylinderIntersection(camO, camD, camMaxt, orgBeam, dBeam, (Real)INFINITY, r, tNearBeam, tFarBeam)) {
+      Real pdfK = (Real)(1.0 / std::max(tFarBeam - tNearBeam, 0.0001));
+      const V3<Real> kernelCentroid = orgBeam + dBeam * newDLength;
+      const Real distToProj = dot(kernelCentroid - camO, camD);
+      const Real distSqr = ((camO + distToProj * camD) - kernelCentroid).lengthSquared();
+      const Real radSqr = r * r;
+      if (distSqr < radSqr) {
+        const Real deltaT = safe_sqrt(radSqr - distSqr);
+        pdfK = (Real)(pdfK * (1.0 / std::max(2.0 * deltaT, 0.0001)));
+        return pdfK;
+      }
+      return 0;
+    }
+    return 0;
+  }
+
+  // BeamGradRadianceQuery::getShiftPos, shift_volume_beams.cpp:98-137 (coherent = true)
+  V3<Real> beamShiftPos(const CamRay<Real> &ray, int k, Real w, const V3<Real> &u, Real newW) const {
+    const V3<Real> sAt = ray.offO[k] + newW * ray.offD[k];
+    V3<Real> bs, bt, ns, nt;
+    coordinateSystemCoherent(ray.d, bs, bt);
+    coordinateSystemCoherent(ray.offD[k], ns, nt);
+    const V3<Real> local(dot(u, bs), dot(u, bt), dot(u, ray.d));
+    V3<Real> newPos = sAt + ((ns * local.x + nt * local.y) + ray.offD[k] * local.z);
+    if (cfg.use_shift_null) {
+      const V3<Real> bCamW = ray.o + w * ray.d;
+      Real offDistSqr = (bCamW - newPos).lengthSquared();
+      if (offDistSqr < radius * radius) {
+        V3<Real> dShift = sAt - bCamW;
+        dShift = dShift / dShift.length();
+        const Real cosD = dot(dShift, -(newPos - sAt));
+        newPos += (dShift * cosD) * (Real)2;
+      }
+    }
+    return newPos;
+  }
+
+  // shiftBeamDiffuse + diffuseReconnectionPhotonBeam: shift_volume_beams.cpp:410-539,
+  // shift/operation/shift_diffuse.cpp:136-268
+  void shiftBeamDiffuse(const Beam &beam, const CamRay<Real> &ray, int k, Real shiftW, const BeamKernelRecord &kRec,
+                        const V3<Real> &newPos, GradientSamplingResult<Real> &res) const {
+    if (shiftW > ray.offLen[k]) { res.weight = 1; return; }                    // shiftBeam :364-367
+    if (beam.parentType == GVPM_PARENT_OTHER) return;                          // manifold: out of scope
+    V3<Real> newPBDir = newPos - beam.o;
+    const Real newPBDist = newPBDir.length();
+    newPBDir = newPBDir / newPBDist;
+    if (occ.anyHit(beam.o, newPBDir, (Real)cfg.epsilon, newPBDist)) { res.weight = 1; return; }  // :420-426
+    const V3<Real> basePos = beam.o + beam.dir * kRec.v;
+    V3<Real> shiftPhotonWeight = beam.prefix;
+    const Real pdfKernelAndDist = kRec.pdf();
+    // diffuseReconnectionPhotonBeam
+    V3<Real> thr(1, 1, 1);
+    Real pdfValueSA = 0, sPdf = 0;
+    const Real INV_PI = Consts<Real>::inv_pi;
+    bool failed = false;
+    if (beam.parentType == GVPM_PARENT_SURFACE) {
+      V3<Real> wiWorld = normalize(beam.pred - beam.o);
+      Real cosI = dot(beam.pn, wiWorld), cosO = dot(beam.pn, newPBDir);
+      if (cosI <= 0 || cosO <= 0) { thr = V3<Real>(); pdfValueSA = 0; }
+      else { thr = thr * (beam.albedo * (INV_PI * cosO)); pdfValueSA = INV_PI * cosO; }
+      if (cosI * cosI <= 0 || cosO * cosO <= 0) failed = true;
+    } else if (beam.parentType == GVPM_PARENT_MEDIUM) {
+      V3<Real> pWi = normalize(beam.pred - beam.o);
+      Real phv = medium.phase(pWi, newPBDir);
+      thr = thr * (medium.sigmaS * phv);
+      pdfValueSA = phv;
+    } else {
+      Real dp = dot(newPBDir, beam.pn);
+      if (dp < 0) dp = 0;
+      thr = thr * V3<Real>(INV_PI * dp, INV_PI * dp, INV_PI * dp);
+      pdfValueSA = INV_PI * dp;
+    }
+    if (!failed) {
+      const Real GOpNew = 1 / (newPBDist * newPBDist);
+      sPdf = pdfValueSA * GOpNew;
+      thr = thr * GOpNew;
+      Real pdfBasePos = beam.parentPdf * (beam.o - beam.end).lengthSquared();
+      if (beam.endOnSurface) pdfBasePos /= std::abs(dot(beam.endN, beam.dir));
+      const Real GOpBase = (Real)1 / (beam.o - basePos).lengthSquared();
+      pdfBasePos *= GOpBase;
+      if (pdfBasePos == 0) {
+        sPdf = 0;
+      } else {
+        thr = thr / pdfBasePos;
+        thr = thr * beam.rrWeight;
+        typename Medium<Real>::Rec m = medium.eval(0, newPBDist);
+        if (!cfg.long_beams) sPdf *= m.pdfFailure;
+        thr = thr * (m.transmittance / pdfKernelAndDist);
+      }
+    }
+    if (sPdf == 0) { res.weight = 1; return; }
+    const Real shiftKernelPDF = beamKernelPDF(ray.offO[k], ray.offD[k], ray.offLen[k], beam.o, newPBDir, newPBDist);
+    if (shiftKernelPDF == 0) { res.weight = 1; return; }
+    shiftPhotonWeight = shiftPhotonWeight * thr;
+    typename Medium<Real>::Rec mRecShift = medium.eval(0, shiftW);
+    const Real phaseTerm = medium.phase(-newPBDir, -ray.offD[k]);
+    shiftPhotonWeight = shiftPhotonWeight * ((mRecShift.transmittance * medium.sigmaS) * phaseTerm);
+    res.shiftedFlux = (shiftPhotonWeight * ray.offEye[k]) * res.jacobian;
+    res.weight = (Real)0.5;
+    if (cfg.use_mis) {
+      Real basePdf = beam.parentPdf;
+      basePdf *= (beam.o - beam.end).lengthSquared();
+      if (beam.endOnSurface) basePdf /= std::abs(dot(beam.endN, beam.dir));
+      basePdf /= (beam.o - basePos).lengthSquared();
+      basePdf *= pdfKernelAndDist;
+      Real offsetPdf = shiftKernelPDF;
+      offsetPdf *= sPdf;
+      if (offsetPdf == 0 || basePdf == 0) { res.weight = 1; return; }
+      const Real q = ray.offSensor[k] * offsetPdf * res.jacobian / basePdf;
+      res.weight = cfg.power_heuristic ? (Real)1 / ((Real)1 + q * q) : (Real)1 / ((Real)1 + q);
+    }
+  }
+
+  // BeamGradRadianceQuery::operator(), shift_volume_beams.cpp:139-353 (beam3d).
+  // 0 = no valid kernel record, 1 = valid but filtered, 2 = contributes.
+  int beamFunctor(const CamRay<Real> &ray, const Beam &beam, uint32_t beamIndex, Accum<Real> &acc) const {
+    bool filtered = false;
+    if (cfg.max_depth > 0 && ray.edgeId + beam.depth > cfg.max_depth) filtered = true;   // :143-145
+    if (!lightingModeAccepts(beam.parentType)) filtered = true;                         // :148-150
+    Real rrGlobalWeight = 1;
+    if (cfg.path_set) {                                                                 // :180-187
+      if (beam.pathId % 2 != (uint32_t)((ray.px + ray.py) % 2)) filtered = true;
+      rrGlobalWeight = 2;
+    }
+    const Real xi1 = beamUniform(ray, beamIndex, 0), xi2 = beamUniform(ray, beamIndex, 1);
+    const BeamKernelRecord kRec = beamKernelEval(beam, ray.o, ray.d, ray.mint, ray.maxt, xi1, xi2);
+    if (!kRec.isValid()) return 0;
+    if (filtered) return 1;
+    const Real r = radius;
+    const V3<Real> baseContrib = (ray.eye * kRec.contrib) * kRec.weightKernel;          // :205
+    acc.mediumFlux += baseContrib * rrGlobalWeight;
+    for (int k = 0; k < 4; ++k) {
+      GradientSamplingResult<Real> res;
+      if (ray.offValid[k]) {
+        const Real shiftDistMAX = ray.offLen[k], shiftW = kRec.w;
+        bool alreadyShift = false;
+        if (cfg.use_shift_null) {                                                       // :254-289
+          const V3<Real> kernelPos = beam.o + beam.dir * kRec.v;
+          const Real ZPtoY = ((ray.offO[k] + shiftW * ray.offD[k]) - kernelPos).lengthSquared();
+          if (ZPtoY < r * r && kRec.w <= shiftDistMAX) {
+            BeamKernelRecord kS = beamKernelNull(kRec, beam, ray.offO[k], ray.offD[k], (Real)cfg.epsilon, shiftDistMAX);
+            if (kS.isValid()) {
+              // shiftNull3D, :748-786
+              kS.contrib = kS.contrib * (kS.pdf() / kRec.pdf());
+              res.jacobian = 1;
+              res.shiftedFlux = (kS.contrib * ray.offEye[k]) * res.jacobian;
+              res.weight = (Real)0.5;
+              if (cfg.use_mis) {
+                const Real basePdf = kRec.pdf(), offsetPdf = kS.pdf();
+                if (offsetPdf == 0 || basePdf == 0) {
+                  res.weight = 1;
+                } else {
+                  const Real q = ray.offSensor[k] * res.jacobian * (offsetPdf / basePdf);
+                  res.weight = cfg.power_heuristic ? (Real)1 / ((Real)1 + q * q) : (Real)1 / ((Real)1 + q);
+                }
+              }
+              alreadyShift = true;
+            }
+          }
+        }
+        if (!alreadyShift && kRec.w <= shiftDistMAX) {                                  // :293-316
+          const Real dd = dot(beam.o - ray.offO[k], ray.offD[k]);
+          const Real minDistSqr = (beam.o - (ray.offO[k] + dd * ray.offD[k])).lengthSquared();
+          if (minDistSqr > 0) {  // kRec.u == 0 for the 3-D kernel
+            const V3<Real> u = (beam.o + beam.dir * kRec.v) - (ray.o + kRec.w * ray.d);
+            const V3<Real> offsetPos = beamShiftPos(ray, k, kRec.w, u, shiftW);
+            shiftBeamDiffuse(beam, ray, k, shiftW, kRec, offsetPos, res);
+          } else {
+            res.weight = 1;
+          }
+        }
+      } else {
+        res.weight = 1;
+      }
+      res.shiftedFlux = res.shiftedFlux * kRec.weightKernel;                            // :337
+      if ((k == 1 && ray.px == cfg.film_w - 1) || (k == 2 && ray.py == cfg.film_h - 1)) res.weight = 1;
+      acc.shifted[k] += (res.weight * res.shiftedFlux) * rrGlobalWeight;
+      acc.weighted[k] += (res.weight * baseContrib) * rrGlobalWeight;
+    }
+    return 2;
+  }
 };
 
 // ---------------------------------------------------------------------------------------

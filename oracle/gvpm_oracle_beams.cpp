@@ -1,0 +1,87 @@
+// gvpm_oracle_beams.cpp — TEST INFRASTRUCTURE (see gvpm_oracle.hpp).  G-Beams 3D gather over every
+// (camera ray, photon beam) pair: the functor BeamGradRadianceQuery::operator() restated in
+// gvpm_oracle.hpp, driven like computeVolumeGradientBeams (gvpm/gvpm.cpp:880-986).  This entry point is
+// the tree-independent brute force (every beam offered to every ray with tmin = 0, tmax = length), which
+// is what the reference's SubBeamBVH traversal (photonmapper/beams_accel.h:169-203) selects up to
+// measure-zero coincidences of tNear with a sub-beam boundary.
+#include "gvpm_oracle.hpp"
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+using namespace gvpm_oracle;
+
+namespace {
+template <typename Real>
+void beamsRange(const gvpm_beam_soa &bs, size_t nBeams, const gvpm_ray_soa &rays, size_t nRays, const Scene<Real> &sc,
+                int threads, float *out, uint32_t *counts, std::vector<std::vector<uint32_t>> *nbr) {
+  std::vector<typename Scene<Real>::Beam> beams(nBeams);
+  for (size_t i = 0; i < nBeams; ++i) beams[i] = Scene<Real>::loadBeam(bs, i);
+  const size_t tile = 64;
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      size_t b = next.fetch_add(tile);
+      if (b >= nRays) break;
+      size_t e = std::min(nRays, b + tile);
+      for (size_t i = b; i < e; ++i) {
+        CamRay<Real> ray = loadRay<Real>(rays, i);
+        Accum<Real> acc;
+        uint32_t nGeom = 0, nContrib = 0;
+        if (ray.edgeLen >= ray.mint) {
+          for (size_t j = 0; j < nBeams; ++j) {
+            int r = sc.beamFunctor(ray, beams[j], (uint32_t)j, acc);
+            if (r >= 1) {
+              ++nGeom;
+              if (r == 2) ++nContrib;
+              if (nbr) (*nbr)[i].push_back((uint32_t)j | (r == 2 ? 0x80000000u : 0u));
+            }
+          }
+        }
+        acc.store(out + GVPM_OUT_FLOATS * i);
+        if (counts) { counts[2 * i] = nGeom; counts[2 * i + 1] = nContrib; }
+      }
+    }
+  };
+  if (threads <= 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+}
+}  // namespace
+
+extern "C" long long gvpm_oracle_beams(const gvpm_beam_soa *beams, size_t nBeams, const gvpm_ray_soa *rays,
+                                       size_t nRays, const gvpm_medium *med, const gvpm_config *cfg,
+                                       const float *tri, size_t n_tri, float radius, int use_double, int threads,
+                                       float *out, uint32_t *counts, uint64_t *nbr_offsets, uint32_t *nbr_idx,
+                                       size_t cap, double *gather_ms) {
+  std::vector<std::vector<uint32_t>> nbr;
+  if (nbr_offsets) nbr.resize(nRays);
+  auto t0 = std::chrono::steady_clock::now();
+  if (use_double) {
+    Scene<double> sc(*med, *cfg, (double)radius);
+    sc.occ.set(tri, n_tri);
+    beamsRange<double>(*beams, nBeams, *rays, nRays, sc, threads, out, counts, nbr_offsets ? &nbr : nullptr);
+  } else {
+    Scene<float> sc(*med, *cfg, radius);
+    sc.occ.set(tri, n_tri);
+    beamsRange<float>(*beams, nBeams, *rays, nRays, sc, threads, out, counts, nbr_offsets ? &nbr : nullptr);
+  }
+  if (gather_ms)
+    *gather_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  long long total = 0;
+  if (nbr_offsets) {
+    for (size_t i = 0; i < nbr.size(); ++i) {
+      nbr_offsets[i] = (uint64_t)total;
+      for (uint32_t v : nbr[i]) {
+        if ((size_t)total < cap && nbr_idx) nbr_idx[total] = v;
+        ++total;
+      }
+    }
+    nbr_offsets[nbr.size()] = (uint64_t)total;
+  }
+  return total;
+}
