@@ -59,6 +59,11 @@ class BeamSoA(C.Structure):
                 ("path_id", u32p)]
 
 
+class PlaneSoA(C.Structure):
+    _fields_ = [("origin", f32p), ("w0", f32p), ("length0", f32p), ("w1", f32p), ("length1", f32p),
+                ("flux", f32p), ("edge_id", i32p)]
+
+
 class VpmSampleSoA(C.Structure):
     _fields_ = [("ray", u32p), ("t", f32p), ("transmittance", f32p), ("pdf_success", f32p),
                 ("pdf_sel", f32p), ("radius", f32p)]
@@ -74,6 +79,7 @@ ABI_SYMBOLS = [
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
     "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
+    "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_dump_neighbours_planes",
 ]
 
 _lib = None
@@ -119,6 +125,10 @@ def load_lib():
     lib.gvpm_build_beams.argtypes = [vp, C.c_float]
     lib.gvpm_gather_beams.argtypes = [vp, f32p, u32p]
     lib.gvpm_dump_neighbours_beams.argtypes = [vp, u64p, u32p, C.c_size_t]
+    lib.gvpm_upload_planes.argtypes = [vp, C.POINTER(PlaneSoA), C.c_size_t]
+    lib.gvpm_build_planes.argtypes = [vp]
+    lib.gvpm_gather_planes.argtypes = [vp, f32p, u32p]
+    lib.gvpm_dump_neighbours_planes.argtypes = [vp, u64p, u32p, C.c_size_t]
     lib.gvpm_upload_vpm_samples.argtypes = [vp, C.POINTER(VpmSampleSoA), C.c_size_t]
     lib.gvpm_gather_vpm.argtypes = [vp, C.c_int, f32p, u32p, u32p]
     lib.gvpm_dump_neighbours_vpm.argtypes = [vp, C.c_int, u64p, u32p, C.c_size_t]
@@ -153,5 +163,8 @@ def load_synth():
     s.gvpm_synth_beams.argtypes = [C.c_uint64, C.c_size_t, C.POINTER(Medium), C.c_int, C.c_int, C.c_int,
                                    C.c_float, C.c_int, C.POINTER(BeamSoA)]
     s.gvpm_synth_beams.restype = C.c_longlong
+    s.gvpm_synth_planes.argtypes = [C.c_uint64, C.POINTER(BeamSoA), C.c_size_t, C.POINTER(Medium),
+                                    C.POINTER(PlaneSoA)]
+    s.gvpm_synth_planes.restype = C.c_size_t
     _synth = s
     return s

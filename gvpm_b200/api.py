@@ -160,6 +160,36 @@ class Context:
                      "gvpm_dump_neighbours_beams")
         return offsets, idx[:total]
 
+    # ---- G-Planes 0D
+    def upload_planes(self, planes):
+        cs = planes.as_c()
+        self._ck(self.lib.gvpm_upload_planes(self.h, C.byref(cs), planes.n), "gvpm_upload_planes")
+
+    def build_planes(self):
+        self._ck(self.lib.gvpm_build_planes(self.h), "gvpm_build_planes")
+
+    def gather_planes(self, counts=True):
+        n = self.n_rays
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
+        self._ck(self.lib.gvpm_gather_planes(self.h, out.ctypes.data_as(N.f32p),
+                                             cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_planes")
+        return out.reshape(n, N.GVPM_OUT_FLOATS), (cnt.reshape(n, 2) if counts else None)
+
+    def dump_neighbours_planes(self):
+        n = self.n_rays
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        rc = self.lib.gvpm_dump_neighbours_planes(self.h, offsets.ctypes.data_as(N.u64p), None, 0)
+        total = int(offsets[n])
+        if rc != 0 and total == 0:
+            self._ck(rc, "gvpm_dump_neighbours_planes")
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            self._ck(self.lib.gvpm_dump_neighbours_planes(self.h, offsets.ctypes.data_as(N.u64p),
+                                                          idx.ctypes.data_as(N.u32p), total),
+                     "gvpm_dump_neighbours_planes")
+        return offsets, idx[:total]
+
     # ---- G-VPM
     def upload_vpm_samples(self, samples):
         cs = samples.as_c()

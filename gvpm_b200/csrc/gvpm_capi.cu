@@ -31,6 +31,10 @@ void launch_subbeam_leaf_boxes(const float4 *subs, const float4 *beams, uint32_t
                                float4 *lo, float4 *hi, cudaStream_t st);
 cudaError_t launch_beam_traverse(const GatherParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
+void launch_plane_pack_sorted(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *planes, uint32_t *orig,
+                              cudaStream_t st);
+void launch_plane_leaf_boxes(const float4 *planes, uint32_t n, uint32_t nLeaves, float4 *lo, float4 *hi, cudaStream_t st);
+cudaError_t launch_plane_gather(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
@@ -103,6 +107,12 @@ struct gvpm_ctx {
   bool beams_loaded = false, beams_built = false;
   Tree beam_tree{};
   float beam_radius = 0.f;
+  // G-Planes
+  DevBuf plane_raw, plane_pos, plane_rec, plane_orig, plane_box_lo, plane_box_hi, plane_bounds;
+  std::vector<float4> plane_host;
+  std::vector<float> plane_centres;
+  uint32_t n_planes = 0;
+  bool planes_loaded = false, planes_built = false;
   DevBuf samples, sample_counts, mvol;  // G-VPM distance samples
   uint32_t n_samples = 0;
   bool samples_loaded = false;
@@ -620,6 +630,165 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   ctx->launches += 1;
   CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+// ---- G-Planes 0D -------------------------------------------------------------------------------
+int gvpm_upload_planes(gvpm_ctx *ctx, const gvpm_plane_soa *p, size_t n) {
+  if (!ctx || (n && !p) || n > 0x0ffffff0u) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ctx->n_planes = (uint32_t)n;
+  ctx->planes_loaded = true;
+  ctx->planes_built = false;
+  ctx->plane_host.assign(GVPM_PLANE_PLANES * n, make_float4(0.f, 0.f, 0.f, 0.f));
+  ctx->plane_centres.assign(3 * n, 0.f);
+  if (n == 0) return GVPM_OK;
+  if (!p->origin || !p->w0 || !p->length0 || !p->w1 || !p->length1 || !p->flux || !p->edge_id)
+    return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_plane_soa");
+  for (size_t i = 0; i < n; ++i) {
+    const float *o = p->origin + 3 * i, *w0 = p->w0 + 3 * i, *w1 = p->w1 + 3 * i;
+    const float l0 = p->length0[i], l1 = p->length1[i];
+    // PhotonPlane ctor asserts (plane_struct.h:45-46)
+    if (!(l0 != 0.f && std::isfinite(l0) && l1 != 0.f && std::isfinite(l1)))
+      return fail(ctx, GVPM_ERR_INVALID, "photon plane with zero or non-finite edge length");
+    // e0 = _w0 * _length0, e1 = _w1 * _length1 exactly as intersectPlane0D forms them (plane_struct.h:107-108)
+    const float e0[3] = {w0[0] * l0, w0[1] * l0, w0[2] * l0}, e1[3] = {w1[0] * l1, w1[1] * l1, w1[2] * l1};
+    uint32_t eid = (uint32_t)p->edge_id[i];
+    float ef;
+    memcpy(&ef, &eid, 4);
+    float4 *r = &ctx->plane_host[GVPM_PLANE_PLANES * i];
+    r[0] = make_float4(o[0], o[1], o[2], l0);
+    r[1] = make_float4(e0[0], e0[1], e0[2], l1);
+    r[2] = make_float4(e1[0], e1[1], e1[2], ef);
+    r[3] = make_float4(p->flux[3 * i], p->flux[3 * i + 1], p->flux[3 * i + 2], 0.f);
+    r[4] = make_float4(w0[0], w0[1], w0[2], 0.f);
+    r[5] = make_float4(w1[0], w1[1], w1[2], 0.f);
+    for (int a = 0; a < 3; ++a) ctx->plane_centres[3 * i + a] = o[a] + 0.5f * e0[a] + 0.5f * e1[a];  // getCenter
+  }
+  CK(ctx->plane_raw.reserve(GVPM_PLANE_PLANES * n * sizeof(float4)));
+  CK(ctx->plane_pos.reserve(12 * n));
+  CK(cudaMemcpyAsync(ctx->plane_raw.p, ctx->plane_host.data(), GVPM_PLANE_PLANES * n * sizeof(float4),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->plane_pos.p, ctx->plane_centres.data(), 12 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_build_planes(gvpm_ctx *ctx) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (!ctx->planes_loaded) return fail(ctx, GVPM_ERR_INVALID, "no planes uploaded");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = ctx->n_planes;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  const uint32_t nLeaves = (n + 31) / 32;
+  if (n > 0) {
+    CK(ctx->plane_bounds.reserve(256));
+    CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
+    CK(ctx->keys_in.reserve(8 * (size_t)n));
+    CK(ctx->keys_out.reserve(8 * (size_t)n));
+    CK(ctx->vals_in.reserve(4 * (size_t)n));
+    CK(ctx->vals_out.reserve(4 * (size_t)n));
+    CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
+    CK(ctx->plane_rec.reserve(GVPM_PLANE_PLANES * (size_t)n * sizeof(float4)));
+    CK(ctx->plane_orig.reserve(4 * (size_t)n));
+    CK(ctx->plane_box_lo.reserve(16 * (size_t)nLeaves));
+    CK(ctx->plane_box_hi.reserve(16 * (size_t)nLeaves));
+    launch_bounds(ctx->plane_pos.as<float>(), n, ctx->bounds_partial.as<float>(), ctx->plane_bounds.as<float>(), st);
+    launch_morton(ctx->plane_pos.as<float>(), n, ctx->plane_bounds.as<float>(), ctx->keys_in.as<uint64_t>(),
+                  ctx->vals_in.as<uint32_t>(), st);
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+                ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
+    launch_plane_pack_sorted(ctx->plane_raw.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->plane_rec.as<float4>(),
+                             ctx->plane_orig.as<uint32_t>(), st);
+    launch_plane_leaf_boxes(ctx->plane_rec.as<float4>(), n, nLeaves, ctx->plane_box_lo.as<float4>(),
+                            ctx->plane_box_hi.as<float4>(), st);
+    ctx->launches += 4 + 4;
+    CK(cudaGetLastError());
+  }
+  ctx->planes_built = true;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->timed_build = true;
+  return GVPM_OK;
+}
+
+static int plane_params(gvpm_ctx *ctx, GatherParams &P) {
+  if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
+  if (!ctx->planes_built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_planes has not been called");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
+  memset(&P, 0, sizeof(P));
+  P.tree.lo = ctx->plane_box_lo.as<float4>();
+  P.tree.hi = ctx->plane_box_hi.as<float4>();
+  P.tree.n = ctx->n_planes;
+  P.rays = ctx->rays.as<float4>();
+  P.n_rays = ctx->n_rays;
+  for (int i = 0; i < 3; ++i) {
+    P.sigma_s[i] = ctx->medium.sigma_s[i];
+    P.sigma_t[i] = ctx->medium.sigma_s[i] + ctx->medium.sigma_a[i];
+  }
+  P.phase_type = ctx->medium.phase_type;
+  P.hg_g = ctx->medium.hg_g;
+  P.sampling_weight = ctx->medium.sampling_weight;
+  P.cfg = ctx->cfg;
+  P.out = ctx->out.as<float>();
+  P.counts = ctx->counts.as<uint32_t>();
+  P.work_counter = ctx->work_counter.as<uint32_t>();
+  P.plane_rec = ctx->plane_rec.as<float4>();
+  P.plane_orig = ctx->plane_orig.as<uint32_t>();
+  P.n_planes = ctx->n_planes;
+  return GVPM_OK;
+}
+
+int gvpm_gather_planes(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  GatherParams P;
+  int rc = plane_params(ctx, P);
+  if (rc) return rc;
+  if (!counts) P.counts = nullptr;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(cudaMemsetAsync(ctx->work_counter.p, 0, 32, ctx->stream));
+  CK(launch_plane_gather(P, false, ctx->sm_count, ctx->stream));
+  ctx->launches += ctx->n_rays ? 1 : 0;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_dump_neighbours_planes(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap) {
+  if (!ctx || !offsets) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n_rays;
+  std::vector<float> tmp(n * GVPM_OUT_FLOATS + 1);
+  std::vector<uint32_t> counts(2 * n + 2);
+  int rc = gvpm_gather_planes(ctx, tmp.data(), counts.data());
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { offsets[i] = total; total += counts[2 * i]; }
+  offsets[n] = total;
+  if (total > cap || (total && !idx)) return fail(ctx, GVPM_ERR_INVALID, "neighbour buffer too small");
+  if (total == 0) return GVPM_OK;
+  CK(ctx->nbr_offsets.reserve((n + 1) * 8));
+  CK(ctx->nbr_idx.reserve(total * 4));
+  CK(cudaMemcpyAsync(ctx->nbr_offsets.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GatherParams P;
+  rc = plane_params(ctx, P);
+  if (rc) return rc;
+  P.counts = nullptr;
+  P.nbr_offsets = ctx->nbr_offsets.as<uint64_t>();
+  P.nbr_idx = ctx->nbr_idx.as<uint32_t>();
+  CK(cudaMemsetAsync(ctx->work_counter.p, 0, 32, ctx->stream));
+  CK(launch_plane_gather(P, true, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; ++i) std::sort(idx + offsets[i], idx + offsets[i + 1]);
   return GVPM_OK;
 }
 

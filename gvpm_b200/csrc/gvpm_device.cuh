@@ -72,6 +72,7 @@ __device__ __forceinline__ sf max3(v3 a) { return smax(a.x, smax(a.y, a.z)); }
 //   P6 = parent_albedo.xyz, -
 // meta: bits 0-1 parent type, bits 2-9 depth, bit 10 pathID & 1.
 #define GVPM_PHOTON_PLANES 7
+#define GVPM_PLANE_PLANES 6  // float4 planes per photon-plane record (plane_device.cuh)
 __host__ __device__ inline uint32_t pack_meta(uint32_t type, uint32_t depth, uint32_t path_id) {
   return (type & 3u) | ((depth & 255u) << 2) | ((path_id & 1u) << 10);
 }
@@ -151,6 +152,10 @@ struct GatherParams {
   float weight_kernel;                // 1.0 / kernelVol (double division rounded to Float)
   int beam_prefilter;                 // apply the depth/mode/pathSet filters already in the traversal
                                       // (when the caller does not ask for the geometric neighbour counts)
+  // G-Planes: 6 float4 planes of n_planes entries in Morton order (plane_device.cuh), tree.lo/hi = leaf boxes
+  const float4 *plane_rec;
+  const uint32_t *plane_orig;         // [n_planes] caller's plane index of sorted slot
+  uint32_t n_planes;
   // parity dump for beams: flat list of (ray, beam | contributes << 31) + its atomic cursor
   uint2 *dump_pairs;
   unsigned long long *dump_counter;

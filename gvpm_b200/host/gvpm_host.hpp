@@ -5,6 +5,9 @@
 // drivers change.  This header restates those driver bodies with the CPU gather replaced by calls
 // into include/gvpm_b200.h, using the reference's names:
 //     computeVolumeGradientPhotonBRE    gvpm/gvpm.cpp:988-1079
+//     computeVolumeGradientPhoton       gvpm/gvpm.cpp:1081-1203   (G-VPM)
+//     computeVolumeGradientBeams        gvpm/gvpm.cpp:880-986     (G-Beams)
+//     computeVolumeGradientPlanes       gvpm/gvpm.cpp:782-878     (G-Planes 0D) + LTPhotonPlane::transformBeam
 //     scaleVolumeAPA                    gvpm/gvpm.cpp:181-215
 //     computeGradient                   gvpm/gvpm.cpp:1205-1306
 // A patched gvpm.cpp would hold one VolumeGatherB200 next to m_gatherBlocks and call it from
@@ -22,7 +25,7 @@
 namespace gvpm_host {
 
 // EVolumeTechnique values the gather supports (src/integrators/volume_utils.h:55-93)
-enum EVolumeTechnique { EVolBRE2D = 0, EVolBRE3D = 1 };
+enum EVolumeTechnique { EVolBRE2D = 0, EVolBRE3D = 1, EVolVPM = 2, EVolBeam3D = 3, EVolPlane0D = 4 };
 
 // The GPMConfig fields the volume gather path reads (gvpm/gvpm_struct.h:181-333), same names.
 struct GPMConfig {
@@ -56,6 +59,55 @@ inline void scaleVolumeAPA(double &globalScaleVolume, int it, const GPMConfig &c
   }
 }
 
+// LTPhotonPlane::transformBeam, gvpm/gvpm_plane.h:53-73: extends a photon beam (origin, unit dir) to a photon plane
+// by sampling a free-flight distance (HomogeneousMedium::sampleDistance with EDistanceNormal on Ray(o, d, time):
+// mint = Epsilon, maxt = inf; balance strategy => density sigma_t[1], src/medium/homogeneous.cpp:293-352) and a
+// scattering direction from the phase function (isotropic: squareToUniformSphere, src/libcore/warp.cpp:25-31;
+// HG: src/phase/hg.cpp:73-96 in FrameCoherent(dir)), rejecting directions parallel to the beam.  This consumes the
+// integrator's sampler on the host, exactly like the reference (gvpm.cpp:793-797), so the planes that cross the
+// C ABI are bit-identical inputs.  Sampler: float next1D(); void next2D(float &x, float &y).
+template <typename Sampler>
+inline void transformBeam(const float dir[3], const gvpm_medium &m, Sampler &sampler, float w1[3], float &length1) {
+  const float Epsilon = 1e-4f, TWO_PI_F = 2.0f * 3.14159265358979323846f;
+  float rand = sampler.next1D();
+  if (!(rand < m.sampling_weight))
+    // the reference reads an unset mRecNew.t in this case; volume-only renders force the weight to 1 (gvpm.cpp:135-141)
+    throw std::runtime_error("transformBeam: mediumSamplingWeight must be 1 for photon planes");
+  rand /= m.sampling_weight;
+  const float samplingDensity = m.sigma_s[1] + m.sigma_a[1];
+  const float sampledDistance = -std::log(1 - rand) / samplingDensity;
+  length1 = sampledDistance + Epsilon;  // mRec.t = sampledDistance + ray.mint
+  for (;;) {
+    float sx, sy;
+    sampler.next2D(sx, sy);
+    if (m.phase_type == GVPM_PHASE_ISOTROPIC) {
+      const float z = 1.0f - 2.0f * sy;
+      const float r = std::sqrt(std::max(0.0f, 1.0f - z * z));
+      const float phi = TWO_PI_F * sx;
+      w1[0] = r * std::cos(phi); w1[1] = r * std::sin(phi); w1[2] = z;
+    } else {
+      const float g = m.hg_g;
+      float cosTheta;
+      if (std::fabs(g) < Epsilon) cosTheta = 1 - 2 * sx;
+      else {
+        const float sqrTerm = (1 - g * g) / (1 - g + 2 * g * sx);
+        cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+      }
+      const float sinTheta = std::sqrt(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+      const float phi = TWO_PI_F * sy;
+      const float lx = sinTheta * std::cos(phi), ly = sinTheta * std::sin(phi), lz = cosTheta;
+      // FrameCoherent(-pRec.wi) with pRec.wi = -dir: coordinateSystemCoherent (src/libcore/util.cpp:592-599)
+      const float sign = std::copysign(1.0f, dir[2]);
+      const float a = -1.0f / (sign + dir[2]);
+      const float b = dir[0] * dir[1] * a;
+      const float s[3] = {1.0f + sign * dir[0] * dir[0] * a, sign * b, -sign * dir[0]};
+      const float t[3] = {b, sign + dir[1] * dir[1] * a, -dir[1]};
+      for (int i = 0; i < 3; ++i) w1[i] = s[i] * lx + t[i] * ly + dir[i] * lz;
+    }
+    if (std::fabs(dir[0] * w1[0] + dir[1] * w1[1] + dir[2] * w1[2]) != 1.0f) break;
+  }
+}
+
 // GatherPoint's volume accumulators (gvpm/gvpm_struct.h:421-455), one per pixel, SoA of 27 floats:
 // mediumFlux[3], shiftedMediumFlux[4][3], weightedMediumFlux[4][3].
 class VolumeGatherB200 {
@@ -75,7 +127,7 @@ class VolumeGatherB200 {
     c.use_shift_null = config.useShiftNull;
     c.path_set = config.pathSet;
     c.power_heuristic = config.powerHeuristic;
-    c.kernel_3d = config.volTechnique == EVolBRE3D;
+    c.kernel_3d = config.volTechnique != EVolBRE2D;
     c.film_w = width;
     c.film_h = height;
     c.shadow_maxt_scale = 1e-3f;  // ShadowEpsilon, shift_volume_photon.cpp:396
@@ -99,21 +151,63 @@ class VolumeGatherB200 {
     check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
     m_iter.assign(nRays * GVPM_OUT_FLOATS, 0.f);
     check(gvpm_gather_bre(m_ctx, m_iter.data(), nullptr), "gvpm_gather_bre");
-    // sum the medium edges of each pixel, normalise, fold into the APA running mean (:1054-1069)
-    std::vector<float> pix(m_acc.size(), 0.f);
+    foldIteration(it, rays, nRays, (float)nbPathVolume);  // :1054-1069
+    scaleVolumeAPA(it);
+  }
+
+  // gvpm.cpp:880-986 (beam3d).  beamRadius = bsphereR * globalScaleVolume * POURCENTAGE_BS (:881).
+  void computeVolumeGradientBeams(int it, const gvpm_beam_soa *beams, size_t nBeams, const gvpm_ray_soa *rays,
+                                  size_t nRays, size_t nbPathBeams) {
+    check(gvpm_upload_beams(m_ctx, beams, nBeams), "gvpm_upload_beams");
+    check(gvpm_build_beams(m_ctx, currentRadius()), "gvpm_build_beams");
+    check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
+    m_iter.assign(nRays * GVPM_OUT_FLOATS, 0.f);
+    check(gvpm_gather_beams(m_ctx, m_iter.data(), nullptr), "gvpm_gather_beams");
+    foldIteration(it, rays, nRays, (float)nbPathBeams);  // :958-976
+    scaleVolumeAPA(it);
+  }
+
+  // gvpm.cpp:782-878.  `planes` were produced on the host by transformBeam from the iteration's beams (:793-797).
+  void computeVolumeGradientPlanes(int it, const gvpm_plane_soa *planes, size_t nPlanes, const gvpm_ray_soa *rays,
+                                   size_t nRays, size_t nbPathBeams) {
+    check(gvpm_upload_planes(m_ctx, planes, nPlanes), "gvpm_upload_planes");
+    check(gvpm_build_planes(m_ctx), "gvpm_build_planes");
+    check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
+    m_iter.assign(nRays * GVPM_OUT_FLOATS, 0.f);
+    check(gvpm_gather_planes(m_ctx, m_iter.data(), nullptr), "gvpm_gather_planes");
+    foldIteration(it, rays, nRays, (float)nbPathBeams);  // :850-868
+    scaleVolumeAPA(it);
+  }
+
+  // gvpm.cpp:1081-1203 (G-VPM).  The distance samples are drawn on the host (:1141-1175); their radius is
+  // BBPourcentageCONST * gp.scaleVol per pixel (:1131), `maxRadius` bounds them for the hierarchy.  mvol (may be
+  // null) receives MVol per ray for the per-pixel radius update (:1191-1195), which stays with the caller.
+  void computeVolumeGradientPhoton(int it, const gvpm_photon_soa *photons, size_t nPhotons, const gvpm_ray_soa *rays,
+                                   size_t nRays, const gvpm_vpm_sample_soa *samples, size_t nSamples,
+                                   int nbCameraSamples, float maxRadius, size_t nbPathVolume, uint32_t *mvol) {
+    check(gvpm_upload_photons(m_ctx, photons, nPhotons), "gvpm_upload_photons");
+    check(gvpm_build_points(m_ctx, maxRadius), "gvpm_build_points");
+    check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
+    check(gvpm_upload_vpm_samples(m_ctx, samples, nSamples), "gvpm_upload_vpm_samples");
+    m_iter.assign(nRays * GVPM_OUT_FLOATS, 0.f);
+    check(gvpm_gather_vpm(m_ctx, nbCameraSamples, m_iter.data(), mvol, nullptr), "gvpm_gather_vpm");
+    // VPM is not an APA estimator: the gather adds onto gp.mediumFlux (:1176-1181) and the image assembly divides
+    // by m_totalEmittedVolume (:487-491, isAPAVolumeEstimator() false)
+    (void)it;
     for (size_t r = 0; r < nRays; ++r) {
       const int x = rays->px[r], y = rays->py[r];
       if (x < 0 || y < 0 || x >= m_w || y >= m_h) continue;
       const size_t p = (size_t)y * m_w + x;
       m_haveSmoke[p] = 1;
-      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) pix[p * GVPM_OUT_FLOATS + j] += m_iter[r * GVPM_OUT_FLOATS + j];
+      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) m_acc[p * GVPM_OUT_FLOATS + j] += m_iter[r * GVPM_OUT_FLOATS + j];
     }
-    const float nb = (float)nbPathVolume;
-    for (size_t i = 0; i < m_acc.size(); ++i) {
-      const float fluxVolIter = pix[i] / nb;
-      m_acc[i] = (m_acc[i] * (float)(it - 1) + fluxVolIter) / (float)it;  // APA estimator
-    }
-    scaleVolumeAPA(it);
+    totalEmittedVolume += nbPathVolume;
+  }
+  // accumulators of the non-APA estimator divided by m_totalEmittedVolume (gvpm.cpp:487-491)
+  std::vector<float> normalizedAccumulators() const {
+    std::vector<float> a(m_acc);
+    if (totalEmittedVolume) for (float &v : a) v /= (float)totalEmittedVolume;
+    return a;
   }
 
   void scaleVolumeAPA(int it) { gvpm_host::scaleVolumeAPA(globalScaleVolume, it, m_config); }
@@ -128,8 +222,24 @@ class VolumeGatherB200 {
   const std::vector<uint8_t> &haveSmoke() const { return m_haveSmoke; }
   gvpm_ctx *context() { return m_ctx; }
   double globalScaleVolume;
+  size_t totalEmittedVolume = 0;
 
  private:
+  // sum the medium edges of each pixel, normalise, fold into the APA running mean (gvpm.cpp:1054-1069)
+  void foldIteration(int it, const gvpm_ray_soa *rays, size_t nRays, float nb) {
+    std::vector<float> pix(m_acc.size(), 0.f);
+    for (size_t r = 0; r < nRays; ++r) {
+      const int x = rays->px[r], y = rays->py[r];
+      if (x < 0 || y < 0 || x >= m_w || y >= m_h) continue;
+      const size_t p = (size_t)y * m_w + x;
+      m_haveSmoke[p] = 1;
+      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) pix[p * GVPM_OUT_FLOATS + j] += m_iter[r * GVPM_OUT_FLOATS + j];
+    }
+    for (size_t i = 0; i < m_acc.size(); ++i) {
+      const float fluxVolIter = pix[i] / nb;
+      m_acc[i] = (m_acc[i] * (float)(it - 1) + fluxVolIter) / (float)it;  // APA estimator
+    }
+  }
   void check(int rc, const char *what) {
     if (rc != GVPM_OK)
       throw std::runtime_error(std::string(what) + " failed: " + gvpm_last_error(m_ctx));

@@ -120,6 +120,28 @@ def synth_beams(n, medium, seed=0xC0FFEE, max_depth=12, rr_depth=1, min_depth=0,
     return bs, int(paths)
 
 
+_PLANE_FIELDS = [
+    ("origin", np.float32, 3), ("w0", np.float32, 3), ("length0", np.float32, 1), ("w1", np.float32, 3),
+    ("length1", np.float32, 1), ("flux", np.float32, 3), ("edge_id", np.int32, 1),
+]
+
+
+class PlaneSet(_SoA):
+    """Photon planes (LTPhotonPlane, gvpm/gvpm_plane.h:18-46)."""
+    FIELDS = _PLANE_FIELDS
+    CSTRUCT = N.PlaneSoA
+
+
+def synth_planes(beams, medium, seed=0xC0FFEE):
+    """Beams -> planes through the host mirror of LTPhotonPlane::transformBeam (one sampler, beam order)."""
+    s = N.load_synth()
+    ps = PlaneSet(beams.n)
+    cb, cp = beams.as_c(), ps.as_c()
+    got = s.gvpm_synth_planes(seed, C.byref(cb), beams.n, C.byref(medium), C.byref(cp))
+    assert got == beams.n
+    return ps
+
+
 class VpmSampleSet(_SoA):
     """Camera distance samples of the G-VPM gather (gvpm.cpp:1141-1175), one per (pixel, sample)."""
     FIELDS = _VPM_FIELDS

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/gvpm_b200.h"
+#include "../host/gvpm_host.hpp"
 
 namespace {
 
@@ -399,6 +400,41 @@ long long gvpm_synth_beams(uint64_t seed, size_t n, const gvpm_medium *med, int 
   });
 }
 
+// Photon planes from photon beams, as computeVolumeGradientPlanes converts them (gvpm.cpp:790-797): one sampler
+// (the block-0 sampler) consumed beam by beam through LTPhotonPlane::transformBeam (host mirror in
+// ../host/gvpm_host.hpp).  edge_id = the beam's edge index (= depth).  Returns n.
+size_t gvpm_synth_planes(uint64_t seed, const gvpm_beam_soa *beams, size_t n, const gvpm_medium *med,
+                         gvpm_plane_soa *out) {
+  struct Sampler {
+    Rng rng;
+    float next1D() { return rng.uniform(); }
+    void next2D(float &x, float &y) { x = rng.uniform(); y = rng.uniform(); }
+  } sampler{Rng(seed ^ 0xA0761D6478BD642FULL, 0)};
+  float *org = (float *)out->origin, *w0 = (float *)out->w0, *l0 = (float *)out->length0, *w1 = (float *)out->w1,
+        *l1 = (float *)out->length1, *flux = (float *)out->flux;
+  int32_t *eid = (int32_t *)out->edge_id;
+  for (size_t i = 0; i < n; ++i) {
+    const float *o = beams->origin + 3 * i, *e = beams->end + 3 * i;
+    // PhotonBeam::setEndPoint (beams_struct.h:73-81)
+    float d[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
+    const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float rcp = 1.0f / len;
+    d[0] *= rcp; d[1] *= rcp; d[2] *= rcp;
+    float nw[3], nl;
+    gvpm_host::transformBeam(d, *med, sampler, nw, nl);
+    for (int a = 0; a < 3; ++a) {
+      org[3 * i + a] = o[a];
+      w0[3 * i + a] = d[a];
+      w1[3 * i + a] = nw[a];
+      flux[3 * i + a] = beams->flux[3 * i + a];
+    }
+    l0[i] = len;
+    l1[i] = nl;
+    eid[i] = beams->depth[i];
+  }
+  return n;
+}
+
 // Occluder triangles of the synthetic scene: 5 walls + shelf = 12 triangles.  out: [12*9].
 size_t gvpm_synth_occluders(float *out) {
   const float q[6][12] = {
@@ -434,10 +470,20 @@ size_t gvpm_synth_rays(uint64_t seed, int w, int h, int block, int y0, int y1, f
   uint8_t *ov = (uint8_t *)out->off_valid;
   float *oo = (float *)out->off_o, *od = (float *)out->off_d, *ol = (float *)out->off_len,
         *oe = (float *)out->off_eye, *os = (float *)out->off_sensor;
+  // cam_dist < 0: the sensor sits INSIDE the medium at z = -cam_dist (photon planes need it, gvpm.cpp:785-787);
+  // the medium segment is then edge 1 starting at the sensor position and `cover` is tan(fov/2)
+  const bool inside = cam_dist < 0.f;
   const Vec cam = {0.5f, 0.5f, -cam_dist};
-  const float tx = 0.5f * cover / cam_dist, ty = tx * (float)h / (float)w;
+  const float tx = inside ? cover : 0.5f * cover / cam_dist, ty = tx * (float)h / (float)w;
   auto makeRay = [&](float sx, float sy, Vec &ro, Vec &rd, float &rl) -> bool {
     Vec dir = norm(Vec{(sx / w - 0.5f) * 2 * tx, (sy / h - 0.5f) * 2 * ty, 1.0f});
+    if (inside) {
+      ro = cam;
+      rd = dir;
+      Hit hit = intersectScene(ro, rd);
+      rl = hit.t;
+      return hit.t > 4 * epsilon && !hit.escaped;
+    }
     float tIn = cam_dist / dir.z;
     ro = cam + dir * tIn;
     ro.z = 0.f;
@@ -482,7 +528,7 @@ size_t gvpm_synth_rays(uint64_t seed, int w, int h, int block, int y0, int y1, f
           xi[n] = rng.uniform();
           px[n] = x;
           py[n] = y;
-          eid[n] = 2;
+          eid[n] = inside ? 1 : 2;
           for (int k = 0; k < 4; ++k) {
             Vec ko, kd;
             float kl;

@@ -175,6 +175,20 @@ typedef struct gvpm_beam_soa {
   const uint32_t *path_id;    /* [n]   LTPhotonBeam::pathID */
 } gvpm_beam_soa;
 
+/* Photon planes (0D kernel), flattened from LTPhotonPlane (gvpm/gvpm_plane.h:18-46, photonmapper/plane_struct.h:18-58):
+ * the photon beam of light-path edge i extended by a second sampled direction/length on the host
+ * (LTPhotonPlane::transformBeam, gvpm_plane.h:53-73; mirrored by gvpm_host::transformBeam).  The plane functor
+ * reads no parent-vertex data (its shift keeps origin and w0, shift_volume_planes.h:263-416). */
+typedef struct gvpm_plane_soa {
+  const float *origin;    /* [n*3] _ori = vertex(i).position */
+  const float *w0;        /* [n*3] _w0 = edge(i).d (unit) */
+  const float *length0;   /* [n]   _length0 = edge(i).length */
+  const float *w1;        /* [n*3] _w1 = sampled scattering direction (unit) */
+  const float *length1;   /* [n]   _length1 = sampled distance */
+  const float *flux;      /* [n*3] _flux, as the beam flux (gvpm_plane.h:36-44) */
+  const int32_t *edge_id; /* [n]   edgeID = i (the t0 Jacobian factor is skipped for i == 1, :357-359) */
+} gvpm_plane_soa;
+
 /* Occluder triangles for the reconnection shadow ray (scene->rayIntersect,
  * shift_volume_photon.cpp:396-402), tested as Triangle::rayIntersect
  * (include/mitsuba/core/triangle.h:109-145). */
@@ -245,6 +259,19 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius);
 int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts);
 /* per-ray sets of beam indices (bit 31 = contributes), CSR like gvpm_dump_neighbours_bre */
 int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
+
+/* ---- G-Planes 0D ("plane0d"): replaces PhotonPlaneBVH construction + planeBVH->query(radQuery) over all gather
+ *      points, gvpm.cpp:782-878 + plane_accel.h:84-211 + plane_struct.h:104-192 + shift_volume_planes.h:57-101,
+ *      263-453 ----------------------------------------------------------------------------------------------
+ * Rays as for the other gathers (the camera must be inside the medium, gvpm.cpp:785-787; ray.maxt = edge length
+ * - Epsilon, :833-837).  The functor uses neither eyeContrib nor the depth / mode / pathSet filters, and has no
+ * right/top border rule (shift_volume_planes.h:57-101) - restated as is.  out: [n_rays*27], un-normalised (the
+ * caller divides by nbPathBeams, :850-856); counts (may be NULL): [n_rays*2] = {planes intersected, same}. */
+int gvpm_upload_planes(gvpm_ctx *ctx, const gvpm_plane_soa *p, size_t n);
+int gvpm_build_planes(gvpm_ctx *ctx);
+int gvpm_gather_planes(gvpm_ctx *ctx, float *out, uint32_t *counts);
+/* per-ray sets of plane indices (bit 31 always set: every intersected plane contributes), CSR */
+int gvpm_dump_neighbours_planes(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
 
 /* ---- G-VPM: replaces gradientPhotonMap->evaluate(gRec, p, querySize) over all camera distance
  *      samples, gvpm.cpp:1141-1185 + kdtree.h:675-731 + shift_volume_photon.cpp:489-655 ----------------

@@ -51,8 +51,45 @@ def load():
                                       C.c_int, C.c_int, N.f32p, N.u32p, N.u64p, N.u32p, C.c_size_t,
                                       C.POINTER(C.c_double)]
     lib.gvpm_oracle_beams.restype = C.c_longlong
+    lib.gvpm_oracle_planes.argtypes = [C.POINTER(N.PlaneSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                       C.POINTER(N.Medium), C.POINTER(N.Config), C.c_int, C.c_int, C.c_int, N.f32p,
+                                       N.u32p, N.u64p, N.u32p, C.c_size_t, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]
+    lib.gvpm_oracle_planes.restype = C.c_longlong
     _lib = lib
     return lib
+
+
+def planes_gather(planes, rays, medium, config, mode="brute", double=False, threads=None, neighbours=False):
+    """Restated computeVolumeGradientPlanes gather (gvpm.cpp:782-878), plane0d kernel.  mode "brute": every
+    (ray, plane) pair; "kdtree": the reference's balanced kd-tree + AABB hierarchy + DFS (plane_accel.h).
+    Returns a BreResult (idx = plane indices with bit 31 set)."""
+    lib = load()
+    threads = hw_threads() if threads is None else threads
+    cp, cr = planes.as_c(), rays.as_c()
+    out = np.zeros(rays.n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    ms, bms = C.c_double(0), C.c_double(0)
+    m = {"brute": 0, "kdtree": 1}[mode]
+
+    def call(offp, idxp, capv):
+        r = lib.gvpm_oracle_planes(C.byref(cp), planes.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config), m,
+                                   int(double), threads, out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p),
+                                   offp, idxp, capv, C.byref(ms), C.byref(bms))
+        if r < 0:
+            raise RuntimeError(f"gvpm_oracle_planes failed: {r}")
+        return int(r)
+    offsets = idx = None
+    if neighbours:
+        offsets = np.zeros(rays.n + 1, dtype=np.uint64)
+        cap = call(offsets.ctypes.data_as(N.u64p), None, 0)
+        idx = np.zeros(max(cap, 1), dtype=np.uint32)
+        call(offsets.ctypes.data_as(N.u64p), idx.ctypes.data_as(N.u32p), cap)
+        idx = idx[:cap]
+    else:
+        call(None, None, 0)
+    return BreResult(out.reshape(rays.n, N.GVPM_OUT_FLOATS), counts.reshape(rays.n, 2), offsets, idx, ms.value,
+                     bms.value)
 
 
 def beams_gather(beams, rays, medium, config, tri, radius, double=False, threads=None, neighbours=False):

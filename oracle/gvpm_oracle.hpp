@@ -924,6 +924,143 @@ template <typename Real> struct Scene {
     }
     return 2;
   }
+
+  // ---- G-Planes 0D ("plane0d") -------------------------------------------------------------
+  struct Plane {  // LTPhotonPlane, gvpm/gvpm_plane.h:18-46 + PhotonPlane, photonmapper/plane_struct.h:18-58
+    V3<Real> ori, w0, w1, flux;
+    Real length0, length1;
+    int edgeID;
+  };
+  static Plane loadPlane(const gvpm_plane_soa &s, size_t i) {
+    Plane p;
+    p.ori = V3<Real>(s.origin + 3 * i);
+    p.w0 = V3<Real>(s.w0 + 3 * i);
+    p.w1 = V3<Real>(s.w1 + 3 * i);
+    p.flux = V3<Real>(s.flux + 3 * i);
+    p.length0 = (Real)s.length0[i];
+    p.length1 = (Real)s.length1[i];
+    p.edgeID = s.edge_id[i];
+    return p;
+  }
+  struct PlaneIts { Real tCam, t0, t1, invDet; };  // PhotonPlane::IntersectionRecord, plane_struct.h:20-22
+  static Real absDot(const V3<Real> &a, const V3<Real> &b) { return std::abs(dot(a, b)); }
+  static V3<Real> cdiv(const V3<Real> &a, const V3<Real> &b) { return V3<Real>(a.x / b.x, a.y / b.y, a.z / b.z); }
+
+  // PhotonPlane::intersectPlane0D, plane_struct.h:104-135 (`det` is a float whatever Float is)
+  static bool intersectPlane0D(const Plane &pl, const V3<Real> &o, const V3<Real> &d, Real mint, Real maxt,
+                               PlaneIts &r) {
+    const V3<Real> e0 = pl.w0 * pl.length0, e1 = pl.w1 * pl.length1;
+    const V3<Real> P = cross(d, e1);
+    const float det = (float)dot(e0, P);
+    if (std::abs(det) < 1e-5f) return false;
+    r.invDet = (Real)(1.0f / det);
+    const V3<Real> T = o - pl.ori;
+    r.t0 = dot(T, P) * r.invDet;
+    if (r.t0 < 0 || r.t0 > 1) return false;
+    const V3<Real> Q = cross(T, e0);
+    r.t1 = dot(d, Q) * r.invDet;
+    if (r.t1 < 0 || r.t1 > 1) return false;
+    r.tCam = dot(e1, Q) * r.invDet;
+    if (r.tCam <= mint || r.tCam >= maxt) return false;
+    r.t1 *= pl.length1;
+    r.t0 *= pl.length0;
+    return true;
+  }
+  // PhotonPlane::invJacobian, plane_struct.h:194-196 (1.0 / Float evaluated in double, rounded to Float)
+  static Real planeInvJacobian(const Plane &pl, const V3<Real> &k) {
+    return (Real)(1.0 / (double)absDot(pl.w0, cross(pl.w1, k)));
+  }
+  // PhotonPlane::getContrib0D, plane_struct.h:150-192
+  V3<Real> planeContrib0D(const Plane &pl, const PlaneIts &its, const typename Medium<Real>::Rec &mRecCamera,
+                          const V3<Real> &d) const {
+    const Real phaseTerm = medium.phase(-pl.w1, -d);
+    const typename Medium<Real>::Rec mRec0 = medium.eval(0, its.t0), mRec1 = medium.eval(0, its.t1);
+    V3<Real> contrib = (((mRecCamera.transmittance * medium.sigmaS) * medium.sigmaS) * pl.flux) * phaseTerm;
+    contrib = contrib * (mRec1.transmittance * mRec0.transmittance);
+    contrib = contrib / mRec0.pdfFailure;
+    contrib = contrib / mRec1.pdfFailure;
+    contrib = contrib * planeInvJacobian(pl, d);
+    return contrib;
+  }
+  // PlaneGradRadianceQuery::intersection, shift_volume_planes.h:426-453 (unit w0 / w1, no upper bound on t0, t1)
+  static bool planeShiftIntersection(const V3<Real> &o, const V3<Real> &d, Real mint, Real maxt, const V3<Real> &ori,
+                                     const V3<Real> &w0, const V3<Real> &w1, Real &tCam, Real &t0, Real &t1,
+                                     Real &invDet) {
+    const V3<Real> P = cross(d, w1);
+    const Real det = dot(w0, P);
+    if (std::abs(det) < 1e-8f) return false;
+    invDet = 1.0f / det;
+    const V3<Real> T = o - ori;
+    t0 = dot(T, P) * invDet;
+    if (t0 < 0.0f) return false;
+    const V3<Real> Q = cross(T, w0);
+    t1 = dot(d, Q) * invDet;
+    if (t1 < 0.0f) return false;
+    tCam = dot(w1, Q) * invDet;
+    return !(tCam <= mint || tCam >= maxt);
+  }
+  // PlaneGradRadianceQuery::specularShift, shift_volume_planes.h:263-416 (BETTERSHIFT 0): origin and w0 of the
+  // plane are kept, w1 is rotated so that the plane passes through the offset camera point at equal tCam.
+  void planeSpecularShift(const Plane &pl, const CamRay<Real> &ray, int k, const PlaneIts &bRec,
+                          const V3<Real> &baseContrib, GradientSamplingResult<Real> &res) const {
+    const V3<Real> &so = ray.offO[k], &sd = ray.offD[k];
+    const Real sMint = (Real)cfg.epsilon, sMaxt = ray.offLen[k];  // Ray(o, d, Epsilon, shiftDist, 0) :272-273
+    const V3<Real> newIntersection = so + sd * bRec.tCam;
+    V3<Real> orthNewW1 = newIntersection - (pl.ori + pl.w0 * dot(newIntersection - pl.ori, pl.w0));
+    orthNewW1 = orthNewW1 / orthNewW1.length();
+    const Real w0Dot = dot(pl.w0, pl.w1);
+    const V3<Real> newW1 = std::sqrt(1 - (w0Dot * w0Dot)) * orthNewW1 + pl.w0 * w0Dot;
+    Real t0New, t1New, tCamNew, invDetNew;
+    if (!planeShiftIntersection(so, sd, sMint, sMaxt, pl.ori, pl.w0, newW1, tCamNew, t0New, t1New, invDetNew)) {
+      res.weight = 1;
+      return;
+    }
+    const typename Medium<Real>::Rec mRec1 = medium.eval(0, bRec.t1), mRec0 = medium.eval(0, bRec.t0),
+                                     mRec1Shift = medium.eval(0, t1New), mRec0Shift = medium.eval(0, t0New);
+    V3<Real> throughputShift = baseContrib;
+    throughputShift = throughputShift * cdiv(mRec0Shift.transmittance, mRec0.transmittance);
+    throughputShift = throughputShift * cdiv(mRec1Shift.transmittance, mRec1.transmittance);
+    throughputShift = throughputShift / planeInvJacobian(pl, ray.d);
+    throughputShift = throughputShift * (Real)(1.0 / (double)absDot(pl.w0, cross(newW1, sd)));
+    res.jacobian = planeInvJacobian(pl, ray.d);
+    res.jacobian *= absDot(pl.w0, cross(newW1, sd));
+    res.jacobian /= t1New / bRec.t1;
+    if (pl.edgeID != 1) res.jacobian /= t0New / bRec.t0;
+    const Real phaseBase = medium.phase(-pl.w1, -ray.d), phaseNew = medium.phase(-newW1, -sd);
+    throughputShift = throughputShift * phaseNew;
+    throughputShift = throughputShift / phaseBase;
+    res.weight = (Real)0.5;
+    res.shiftedFlux = res.jacobian * throughputShift;
+    if (cfg.use_mis) {
+      Real basePdf = mRec0.pdfSuccess;
+      basePdf *= mRec1.pdfSuccess;
+      basePdf *= phaseBase;  // pdf == eval for the isotropic and HG phase functions
+      Real offsetPdf = mRec0Shift.pdfSuccess;
+      offsetPdf *= mRec1Shift.pdfSuccess;
+      offsetPdf *= phaseNew;
+      if (offsetPdf == 0 || basePdf == 0) {  // "Invalid path": weight 1, shiftedFlux is kept (:401-405)
+        res.weight = 1;
+        return;
+      }
+      res.weight = (Real)1 / ((Real)1 + ray.offSensor[k] * res.jacobian * offsetPdf / basePdf);
+    }
+  }
+  // PlaneGradRadianceQuery::operator(), shift_volume_planes.h:57-101.  No eyeContrib, no depth / mode /
+  // pathSet filter and no border rule in the reference functor.  Returns whether the plane was intersected.
+  bool planeFunctor(const CamRay<Real> &ray, const Plane &pl, Accum<Real> &acc) const {
+    PlaneIts bRec;
+    if (!intersectPlane0D(pl, ray.o, ray.d, ray.mint, ray.maxt, bRec)) return false;
+    const typename Medium<Real>::Rec mRecCam = medium.eval(0, bRec.tCam);
+    const V3<Real> baseContrib = planeContrib0D(pl, bRec, mRecCam, ray.d);
+    acc.mediumFlux += baseContrib;
+    for (int k = 0; k < 4; ++k) {
+      GradientSamplingResult<Real> res;
+      if (ray.offValid[k]) planeSpecularShift(pl, ray, k, bRec, baseContrib, res);
+      acc.shifted[k] += res.weight * res.shiftedFlux;
+      acc.weighted[k] += res.weight * baseContrib;
+    }
+    return true;
+  }
 };
 
 // ---------------------------------------------------------------------------------------

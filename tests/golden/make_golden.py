@@ -22,3 +22,11 @@ res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "bre_small.npz"), out=res.out, counts=res.counts,
                     offsets=res.offsets, idx=res.idx, **P)
 print("neighbours", int(res.counts[:, 0].sum()), "contributing", int(res.counts[:, 1].sum()))
+
+# G-Planes 0D (tests/test_oracle_planes.py)
+PP = dict(n_planes=400, w=20, h=12, seed=4321)
+c = H.make_plane_case(**PP)
+res = ob.planes_gather(c.planes, c.rays, c.medium, c.config, neighbours=True, threads=2)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "planes_small.npz"), out=res.out, counts=res.counts,
+                    offsets=res.offsets, idx=res.idx, **PP)
+print("plane hits", int(res.counts[:, 0].sum()))

@@ -27,6 +27,31 @@ def make_case(n_photons=20000, w=48, h=32, scale=1.0, seed=0xC0FFEE, phase="isot
     return c
 
 
+def make_plane_case(n_planes=1200, w=40, h=24, seed=0xC0FFEE, phase="isotropic", hg_g=0.0, inside=True, sheet=False,
+                    **cfg_kw):
+    """G-Planes 0D case: beams of the seeded light paths extended to planes by the host
+    mirror of transformBeam; sensor inside the medium at (0.5, 0.5, 0.05) (gvpm.cpp:785-787)."""
+    from gvpm_b200 import records as R
+    c = Case()
+    c.medium = g.make_medium(phase=phase, g=hg_g)
+    c.beams, c.n_paths = R.synth_beams(n_planes, c.medium, seed=seed, threads=4)
+    c.planes = R.synth_planes(c.beams, c.medium, seed=seed + 7)
+    if sheet:
+        # collimated emitter: origins squeezed into a 0.02-wide sheet around x = 0.5, first edges along -y
+        o = c.planes.view("origin")
+        o[:, 0] = 0.5 + (o[:, 0] - 0.5) * 0.02
+        c.planes.length1[:] *= 0.05
+    if inside:
+        c.rays = g.synth_rays(w, h, seed=seed + 1, cam_dist=-0.05, cover=0.45)
+    else:
+        c.rays = g.synth_rays(w, h, seed=seed + 1)
+    rng = np.random.default_rng(seed)
+    c.rays.off_sensor[:] = rng.uniform(0.7, 1.3, c.rays.off_sensor.shape).astype(np.float32)
+    c.config = g.make_config(w, h, **cfg_kw)
+    c.w, c.h = w, h
+    return c
+
+
 def gpu_context(case, device=0):
     from gvpm_b200.api import Context
     ctx = Context(device)
