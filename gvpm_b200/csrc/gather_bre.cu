@@ -1,15 +1,17 @@
 // gather_bre.cu — G-BRE gather in two kernels.
 //
-// k_bre_traverse: one warp per PACKET of 4 consecutive camera rays.  The warp walks the implicit
-//   32-ary AABB hierarchy over the Morton-sorted photons without a node stack (one ballot mask per
-//   level is the whole traversal state): lane c tests child c of the current node against the
-//   packet's central ray, fattened by the packet's spread (two coalesced 128-bit loads per lane).  At
-//   a leaf, lane c holds photon c (one 128-bit load) and tests it against each ray of the packet:
-//   first a relaxed FMA pre-test, then — for the rare candidates — the reference's predicate in
-//   strictly rounded arithmetic (gvpm_accel.h:293-301, shift_volume_photon.cpp:707-724).  Photons that
-//   pass the depth/mode/pathSet filters are compacted through a per-warp shared-memory queue into a
-//   global (ray, photon) pair list, 32 pairs per coalesced store.  Incoherent packets fall back to
-//   one traversal per ray; results never depend on the packeting.
+// k_bre_traverse: one warp per TILE of 32 consecutive camera rays, one ray per lane.  The warp walks the
+//   implicit 32-ary AABB hierarchy over the Morton-sorted photons without a node stack (one ballot mask per
+//   level is the whole traversal state): lane c tests child c of the current node against the tile's central
+//   ray fattened by the tile's spread (two coalesced 128-bit loads per lane), so the cost of the walk is
+//   shared by 32 rays.  At a leaf, lane c holds photon c (one 128-bit load) and tests it ONCE against the fat
+//   ray; the few photons inside are then broadcast one by one and every lane tests its own ray with a relaxed
+//   FMA predicate, pushing candidates into its own shared-memory queue.  When a queue fills (and at the end of
+//   the tile) every lane runs the reference's predicate in strictly rounded arithmetic (gvpm_accel.h:293-301,
+//   shift_volume_photon.cpp:707-724) and the depth/mode/pathSet filters on its queued candidates with all
+//   lanes busy, and the survivors go to the global (ray, photon) pair list as one contiguous run per ray.
+//   Tiles whose rays are not coherent fall back to quads of 4 lanes, then to single rays; results never
+//   depend on the grouping.
 // k_bre_shade: one THREAD per (ray, photon) pair, so the divergent shift code (null shift, diffuse
 //   reconnection, MIS; bre_device.cuh) always runs with full warps whatever the number of
 //   neighbours per ray.  27 accumulators per thread in registers, a segmented warp scan by ray id
@@ -23,7 +25,7 @@ namespace gvpm {
 #define GVPM_TRAV_WARPS 4
 #endif
 #ifndef GVPM_TRAV_MIN_BLOCKS
-#define GVPM_TRAV_MIN_BLOCKS 8
+#define GVPM_TRAV_MIN_BLOCKS 6
 #endif
 #ifndef GVPM_SHADE_THREADS
 #define GVPM_SHADE_THREADS 128
@@ -31,136 +33,154 @@ namespace gvpm {
 #ifndef GVPM_SHADE_MIN_BLOCKS
 #define GVPM_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef GVPM_TILE_QUEUE
+#define GVPM_TILE_QUEUE 16
+#endif
 constexpr int kTravWarps = GVPM_TRAV_WARPS;
-constexpr int PK = GVPM_PACKET;  // rays per packet
-constexpr int kQueue = 64;
+constexpr int kTileQ = GVPM_TILE_QUEUE;  // candidate queue entries per lane
 
-struct TravShared {
-  float4 ray[PK][4];           // base record of each ray of the packet
-  uint32_t queue[PK][kQueue];  // per ray: sorted photon slots waiting to be flushed
+struct TileShared {
+  uint32_t queue[kTileQ][32];  // [entry][lane]: sorted photon slots waiting for the strict test
   uint32_t mask[GVPM_MAX_LEVELS];
   uint32_t base[GVPM_MAX_LEVELS];
 };
 
-// flush `take` entries from the top of one ray's queue to the global pair list (one ray per flush,
-// so the pairs of a ray form contiguous runs for the shading kernel's segmented reduction)
-__device__ __forceinline__ void flush_pairs(const GatherParams &P, const uint32_t *queue, uint32_t ray,
-                                            uint32_t &qn, uint32_t take, int lane) {
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)take);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  qn -= take;
-  if ((uint32_t)lane < take) {
-    const unsigned long long idx = base + lane;
-    if (idx < P.pair_cap) P.pairs[idx] = make_uint2(ray, queue[qn + lane]);
-  }
-  __syncwarp();
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+
+// per-lane view of the lane's own camera ray during the traversal
+struct LaneRay {
+  float ox, oy, oz, dx, dy, dz, mint, elen, xi;
+  int px, py, eid;
+};
 
 template <bool DUMP>
 __global__ void __launch_bounds__(kTravWarps * 32, GVPM_TRAV_MIN_BLOCKS)
 k_bre_traverse(const __grid_constant__ GatherParams P) {
-  __shared__ TravShared sh[kTravWarps];
+  __shared__ TileShared sh[kTravWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  TravShared &S = sh[w];
+  TileShared &S = sh[w];
   const Tree &T = P.tree;
   const int top = T.levels - 1;
-  const uint32_t nPackets = (P.ray_end - P.ray_begin + PK - 1) / PK;
+  const uint32_t nTiles = (P.ray_end - P.ray_begin + 31) / 32;
   const float coordMag = T.n ? __ldg(P.bounds + 6) : 0.f;
-  // packets whose rays drift apart by more than this are traversed ray by ray (performance only)
+  // groups whose rays drift apart by more than this are split (performance only)
   float spreadMax = 16.f * P.radius;
   if (T.n) {
     const float ex = __ldg(P.bounds + 3) - __ldg(P.bounds), ey = __ldg(P.bounds + 4) - __ldg(P.bounds + 1),
                 ez = __ldg(P.bounds + 5) - __ldg(P.bounds + 2);
     spreadMax = fmaxf(spreadMax, 0.01f * sqrtf(ex * ex + ey * ey + ez * ez));
   }
+  // the filters only drop photons: apply them before queueing unless the caller wants the geometric counts
+  const bool prefilter = !DUMP && P.counts == nullptr;
 
   for (;;) {
-    uint32_t pk = 0;
-    if (lane == 0) pk = atomicAdd(P.work_counter, 1u);
-    pk = __shfl_sync(0xffffffffu, pk, 0);
-    if (pk >= nPackets) break;
-    const uint32_t r0 = P.ray_begin + pk * PK;
-    const int nr = min((uint32_t)PK, P.ray_end - r0);
-    __syncwarp();
-    if (lane < 4 * nr) S.ray[lane >> 2][lane & 3] = ldg4(P.rays + (size_t)(r0 + (lane >> 2)) * GVPM_RAY_FLOAT4 + (lane & 3));
-    __syncwarp();
-
-    // per-ray state, warp-uniform registers (static indexing: loops over j are fully unrolled)
-    float ox[PK], oy[PK], oz[PK], dx[PK], dy[PK], dz[PK], mint[PK], elen[PK];
-    uint32_t nGeom[PK], nContrib[PK], qn[PK];
-    uint32_t actMask = 0;
-#pragma unroll
-    for (int j = 0; j < PK; ++j) {
-      qn[j] = 0;
-      const int jj = j < nr ? j : 0;
-      const float4 b0 = S.ray[jj][0], b1 = S.ray[jj][1], b2 = S.ray[jj][2];
-      ox[j] = b0.x; oy[j] = b0.y; oz[j] = b0.z; mint[j] = b0.w;
-      dx[j] = b1.x; dy[j] = b1.y; dz[j] = b1.z; elen[j] = b2.w;
-      nGeom[j] = 0; nContrib[j] = 0;
-      if (j < nr && T.n > 0 && elen[j] >= mint[j]) actMask |= 1u << j;
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(P.work_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= nTiles) break;
+    const uint32_t ray = P.ray_begin + tile * 32 + lane;
+    const bool have = ray < P.ray_end;
+    LaneRay L;
+    {
+      const float4 *rec = P.rays + (size_t)(have ? ray : P.ray_begin) * GVPM_RAY_FLOAT4;
+      const float4 b0 = ldg4(rec), b1 = ldg4(rec + 1), b2 = ldg4(rec + 2), b3 = ldg4(rec + 3);
+      L.ox = b0.x; L.oy = b0.y; L.oz = b0.z; L.mint = b0.w;
+      L.dx = b1.x; L.dy = b1.y; L.dz = b1.z; L.elen = b2.w;
+      L.xi = b3.x;
+      L.px = (int)__float_as_uint(b3.y); L.py = (int)__float_as_uint(b3.z); L.eid = (int)__float_as_uint(b3.w);
     }
-    // packet spread: max distance between corresponding points of ray j and the central ray over
-    // [0, tEnd] (linear in t, so attained at an end).  Coherent packets share one traversal.
-    uint32_t groups[PK];
-    int ng = 0;
-    float spread = 0.f;
-    if (actMask) {
-      const int c0 = __ffs(actMask) - 1;
-      float cox = 0, coy = 0, coz = 0, cdx = 0, cdy = 0, cdz = 0, tEnd = 0;
-#pragma unroll
-      for (int j = 0; j < PK; ++j) {
-        if (j == c0) { cox = ox[j]; coy = oy[j]; coz = oz[j]; cdx = dx[j]; cdy = dy[j]; cdz = dz[j]; }
-        if (actMask >> j & 1) tEnd = fmaxf(tEnd, elen[j]);
-      }
-      tEnd += P.radius;
-#pragma unroll
-      for (int j = 0; j < PK; ++j)
-        if (actMask >> j & 1) {
-          const float ax = ox[j] - cox, ay = oy[j] - coy, az = oz[j] - coz;
-          const float bx = ax + tEnd * (dx[j] - cdx), by = ay + tEnd * (dy[j] - cdy), bz = az + tEnd * (dz[j] - cdz);
-          spread = fmaxf(spread, fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz)));
-        }
-      spread *= 1.0001f;
-      if (spread <= spreadMax) {
-        groups[ng++] = actMask;
-      } else {
-        spread = 0.f;
-#pragma unroll
-        for (int j = 0; j < PK; ++j)
-          if (actMask >> j & 1) groups[ng++] = 1u << j;
-      }
-    }
+    const bool active = have && T.n > 0 && L.elen >= L.mint;
+    const uint32_t actMask = __ballot_sync(0xffffffffu, active);
+    const int parity = (L.px + L.py) % 2;
+    uint32_t nGeom = 0, nContrib = 0, qn = 0;
 
-    for (int g = 0; g < ng; ++g) {
-      const uint32_t gm = groups[g];
-      const int c0 = __ffs(gm) - 1;
-      float cox = 0, coy = 0, coz = 0, cdx = 1, cdy = 1, cdz = 1, tloG = 3.4e38f, thiG = -3.4e38f, omag = 0.f;
-#pragma unroll
-      for (int j = 0; j < PK; ++j) {
-        if (j == c0) { cox = ox[j]; coy = oy[j]; coz = oz[j]; cdx = dx[j]; cdy = dy[j]; cdz = dz[j]; }
-        if (gm >> j & 1) {
-          tloG = fminf(tloG, mint[j]);
-          thiG = fmaxf(thiG, elen[j]);
-          omag = fmaxf(omag, fmaxf(fmaxf(fabsf(ox[j]), fabsf(oy[j])), fabsf(oz[j])));
+    // strict predicate + filters on the queued candidates of every lane, survivors -> pair list / dump
+    auto flush = [&]() {
+      const uint32_t maxq = __reduce_max_sync(0xffffffffu, qn);
+      BaseRay R;
+      R.o = v3(L.ox, L.oy, L.oz); R.d = v3(L.dx, L.dy, L.dz);
+      R.mint = sf(L.mint); R.edgeLen = sf(L.elen); R.xi = sf(L.xi);
+      R.px = L.px; R.py = L.py; R.edgeId = L.eid;
+      uint32_t keep = 0;
+      for (uint32_t k = 0; k < maxq; ++k) {
+        if (k < qn) {
+          const uint32_t slot = S.queue[k][lane];
+          const float4 q0 = ldg4(P.planes + slot);
+          sf tB, pc;
+          const bool geom = base_distance(P, R, v3(q0.x, q0.y, q0.z), tB, pc);
+          const bool contrib = geom && filters_pass(P, R, __float_as_uint(q0.w));
+          if (DUMP && geom)
+            P.nbr_idx[P.nbr_offsets[ray] + nGeom] = __ldg(P.orig + slot) | (contrib ? 0x80000000u : 0u);
+          nGeom += geom ? 1u : 0u;
+          nContrib += contrib ? 1u : 0u;
+          if (!DUMP && contrib) S.queue[keep++][lane] = slot;
         }
       }
+      qn = 0;
+      if (!DUMP) {
+        uint32_t incl = keep;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)total);
+          base = __shfl_sync(0xffffffffu, base, 0) + (incl - keep);
+          for (uint32_t k = 0; k < keep; ++k)
+            if (base + k < P.pair_cap) P.pairs[base + k] = make_uint2(ray, S.queue[k][lane]);
+        }
+      }
+      __syncwarp();
+    };
+
+    // one stackless walk for the lanes of `gm`, sharing the fat ray (co, cd) of half-width `spread`
+    auto traverse_group = [&](uint32_t gm, float cox, float coy, float coz, float cdx, float cdy, float cdz,
+                              float spread, float tloG, float thiG, float omag) {
       // conservative culling: relaxed arithmetic made safe by `fpad` (a few ulp of the coordinate
-      // magnitudes: rounding of the slab test and of the strict predicate) plus the packet spread
-      const float fpad = (omag + coordMag + fabsf(thiG) + P.radius) * 3.8147e-6f;  // 2^-18
-      const float pad = fpad + ((gm & (gm - 1)) ? spread : 0.f);
+      // magnitudes: rounding of the slab test and of the strict predicate) plus the group spread
+      const float fpad = (omag + coordMag + fabsf(thiG) + P.radius + spread) * 3.8147e-6f;  // 2^-18
+      const float pad = fpad + spread;
       const float oxp = cox + pad, oxm = cox - pad, oyp = coy + pad, oym = coy - pad, ozp = coz + pad,
                   ozm = coz - pad;
       const float ix = 1.f / cdx, iy = 1.f / cdy, iz = 1.f / cdz;
-      const float tlo = tloG - 4.f * fpad;
-      const float thi = thiG + P.radius + 4.f * fpad;
+      const float tloBox = tloG - 4.f * fpad - spread;                 // axial range of the fat ray
+      const float thiBox = thiG + P.radius + 4.f * fpad + spread;
+      const float tloRay = tloG - 4.f * fpad;                          // per-ray disk distance bound
       const float rpad2 = (P.radius + fpad) * (P.radius + fpad);
+      const float fat2 = (P.radius + pad + fpad) * (P.radius + pad + fpad);
+      const float tloFat = tloBox - P.radius, thiFat = thiBox;
+      const bool mine = gm >> lane & 1u;
 
       uint32_t cur, base = 0;
       int l = top;
       cur = __ballot_sync(0xffffffffu, (uint32_t)lane < T.cnt[top] &&
                                            box_hit(T, T.off[top] + lane, oxp, oxm, oyp, oym, ozp, ozm, ix, iy,
-                                                   iz, tlo, thi));
+                                                   iz, tloBox, thiBox));
       for (;;) {
         if (cur == 0) {
           if (l == top) break;
@@ -179,65 +199,120 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
           base = node << 5;
           const uint32_t idx = base + lane;
           cur = __ballot_sync(0xffffffffu, idx < T.cnt[l] && box_hit(T, T.off[l] + idx, oxp, oxm, oyp, oym, ozp,
-                                                                       ozm, ix, iy, iz, tlo, thi));
+                                                                       ozm, ix, iy, iz, tloBox, thiBox));
           continue;
         }
-        // ---- leaf: lane holds photon (node*32 + lane) ----
+        // ---- leaf: lane holds photon (node*32 + lane), tested once against the fat ray ----
         const uint32_t pi = (node << 5) + lane;
-        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t cand = 0;
+        bool inFat = false;
         if (pi < T.n) {
-          q0 = ldg4(P.planes + pi);
-#pragma unroll
-          for (int j = 0; j < PK; ++j) {
-            // relaxed (FMA) pre-test, conservative by fpad
-            const float cx = q0.x - ox[j], cy = q0.y - oy[j], cz = q0.z - oz[j];
-            const float dd = cx * dx[j] + cy * dy[j] + cz * dz[j];
-            const float qx = cx - dd * dx[j], qy = cy - dd * dy[j], qz = cz - dd * dz[j];
-            if ((gm >> j & 1) && (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tlo) cand |= 1u << j;
-          }
+          const float4 q0 = ldg4(P.planes + pi);
+          const float cx = q0.x - cox, cy = q0.y - coy, cz = q0.z - coz;
+          const float dd = cx * cdx + cy * cdy + cz * cdz;
+          const float qx = cx - dd * cdx, qy = cy - dd * cdy, qz = cz - dd * cdz;
+          inFat = (qx * qx + qy * qy + qz * qz) < fat2 && dd > tloFat && dd < thiFat;
         }
-        const uint32_t anyc = __reduce_or_sync(0xffffffffu, cand);
-        if (anyc == 0) continue;
-#pragma unroll
-        for (int j = 0; j < PK; ++j) {
-          if (!(anyc >> j & 1)) continue;  // warp-uniform
-          bool geom = false, contrib = false;
-          if (cand >> j & 1) {
-            const BaseRay R = load_base_ray(S.ray[j]);
-            sf tB, pc;
-            geom = base_distance(P, R, v3(q0.x, q0.y, q0.z), tB, pc);
-            contrib = geom && filters_pass(P, R, __float_as_uint(q0.w));
-          }
-          const uint32_t gmask = __ballot_sync(0xffffffffu, geom), cmask = __ballot_sync(0xffffffffu, contrib);
-          if (DUMP) {
-            if (geom) {
-              const uint32_t rank = __popc(gmask & ((1u << lane) - 1u));
-              P.nbr_idx[P.nbr_offsets[r0 + j] + nGeom[j] + rank] = P.orig[pi] | (contrib ? 0x80000000u : 0u);
+        uint32_t pm = __ballot_sync(0xffffffffu, inFat);
+        while (pm) {
+          const int b = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const uint32_t slot = (node << 5) + b;
+          const float4 ph = ldg4(P.planes + slot);  // warp-uniform address
+          bool cand = false;
+          if (mine) {
+            // relaxed (FMA) pre-test of the lane's own ray, conservative by fpad
+            const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
+            const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
+            const float qx = cx - dd * L.dx, qy = cy - dd * L.dy, qz = cz - dd * L.dz;
+            cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tloRay;
+            if (prefilter && cand) {
+              const uint32_t meta = __float_as_uint(ph.w);
+              if (P.cfg.path_set && (int)((meta >> 10) & 1u) != parity) cand = false;
+              const int pathLen = (int)((meta >> 2) & 255u) + L.eid;
+              if (P.cfg.max_depth > 0 && pathLen > P.cfg.max_depth) cand = false;
             }
+            if (cand) S.queue[qn++][lane] = slot;
           }
-          nGeom[j] += __popc(gmask);
-          nContrib[j] += __popc(cmask);
-          if (DUMP || cmask == 0) continue;
-          if (contrib) S.queue[j][qn[j] + __popc(cmask & ((1u << lane) - 1u))] = pi;
-          qn[j] += __popc(cmask);
-          __syncwarp();
-          if (qn[j] >= 32) flush_pairs(P, S.queue[j], r0 + j, qn[j], 32, lane);
+          if (__any_sync(0xffffffffu, qn == (uint32_t)kTileQ)) flush();
         }
       }
+    };
+
+    if (actMask) {
+      // tile centre: mean origin / mean direction of the active rays
+      const float cnt = (float)__popc(actMask), inv = 1.f / cnt;
+      const float mox = warp_sum(active ? L.ox : 0.f) * inv, moy = warp_sum(active ? L.oy : 0.f) * inv,
+                  moz = warp_sum(active ? L.oz : 0.f) * inv;
+      float mdx = warp_sum(active ? L.dx : 0.f), mdy = warp_sum(active ? L.dy : 0.f), mdz = warp_sum(active ? L.dz : 0.f);
+      const float mlen = sqrtf(mdx * mdx + mdy * mdy + mdz * mdz);
+      const float tEnd = warp_max(active ? L.elen : 0.f) + P.radius;
+      float dev = 0.f;
+      bool okDir = mlen > 0.5f * cnt;  // nearly parallel rays only
+      if (okDir) {
+        const float il = 1.f / mlen;
+        mdx *= il; mdy *= il; mdz *= il;
+        if (active) {
+          // distance between corresponding points of the lane's ray and the central ray over [0, tEnd]
+          // (linear in t, so attained at an end)
+          const float ax = L.ox - mox, ay = L.oy - moy, az = L.oz - moz;
+          const float bx = ax + tEnd * (L.dx - mdx), by = ay + tEnd * (L.dy - mdy), bz = az + tEnd * (L.dz - mdz);
+          dev = fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz));
+        }
+      }
+      const float spread32 = warp_max(dev) * 1.0001f;
+      const float amag = active ? fmaxf(fmaxf(fabsf(L.ox), fabsf(L.oy)), fabsf(L.oz)) : 0.f;
+      if (okDir && spread32 <= spreadMax) {
+        const float tloG = warp_min(active ? L.mint : 3.4e38f), thiG = warp_max(active ? L.elen : -3.4e38f);
+        traverse_group(actMask, mox, moy, moz, mdx, mdy, mdz, spread32, tloG, thiG, warp_max(amag));
+      } else {
+        // quads of 4 consecutive lanes, then single rays
+        const float qc = quad_sum(active ? 1.f : 0.f), qi = qc > 0.f ? 1.f / qc : 0.f;
+        const float qox = quad_sum(active ? L.ox : 0.f) * qi, qoy = quad_sum(active ? L.oy : 0.f) * qi,
+                    qoz = quad_sum(active ? L.oz : 0.f) * qi;
+        float qdx = quad_sum(active ? L.dx : 0.f), qdy = quad_sum(active ? L.dy : 0.f), qdz = quad_sum(active ? L.dz : 0.f);
+        const float qlen = sqrtf(qdx * qdx + qdy * qdy + qdz * qdz);
+        const bool qok = qlen > 0.5f * qc && qc > 0.f;
+        float qdev = 0.f;
+        if (qok) {
+          const float il = 1.f / qlen;
+          qdx *= il; qdy *= il; qdz *= il;
+          if (active) {
+            const float ax = L.ox - qox, ay = L.oy - qoy, az = L.oz - qoz;
+            const float bx = ax + tEnd * (L.dx - qdx), by = ay + tEnd * (L.dy - qdy), bz = az + tEnd * (L.dz - qdz);
+            qdev = fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz));
+          }
+        }
+        const float qspread = quad_max(qdev) * 1.0001f;
+        const float qtlo = -quad_max(active ? -L.mint : -3.4e38f), qthi = quad_max(active ? L.elen : -3.4e38f);
+        const float qmag = quad_max(amag);
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t gm = actMask & (0xFu << (4 * q));
+          if (!gm) continue;
+          const int ld = __ffs(gm) - 1;
+          const bool useQuad = __shfl_sync(0xffffffffu, qok && qspread <= spreadMax, ld);
+          if (useQuad) {
+            traverse_group(gm, __shfl_sync(0xffffffffu, qox, ld), __shfl_sync(0xffffffffu, qoy, ld),
+                           __shfl_sync(0xffffffffu, qoz, ld), __shfl_sync(0xffffffffu, qdx, ld),
+                           __shfl_sync(0xffffffffu, qdy, ld), __shfl_sync(0xffffffffu, qdz, ld),
+                           __shfl_sync(0xffffffffu, qspread, ld), __shfl_sync(0xffffffffu, qtlo, ld),
+                           __shfl_sync(0xffffffffu, qthi, ld), __shfl_sync(0xffffffffu, qmag, ld));
+          } else {
+            for (uint32_t m = gm; m; m &= m - 1) {
+              const int j = __ffs(m) - 1;
+              traverse_group(1u << j, __shfl_sync(0xffffffffu, L.ox, j), __shfl_sync(0xffffffffu, L.oy, j),
+                             __shfl_sync(0xffffffffu, L.oz, j), __shfl_sync(0xffffffffu, L.dx, j),
+                             __shfl_sync(0xffffffffu, L.dy, j), __shfl_sync(0xffffffffu, L.dz, j), 0.f,
+                             __shfl_sync(0xffffffffu, L.mint, j), __shfl_sync(0xffffffffu, L.elen, j),
+                             __shfl_sync(0xffffffffu, amag, j));
+            }
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, qn > 0)) flush();
     }
-    if (!DUMP) {
-#pragma unroll
-      for (int j = 0; j < PK; ++j)
-        if (qn[j] > 0) flush_pairs(P, S.queue[j], r0 + j, qn[j], qn[j], lane);
-    }
-    if (P.counts && lane < nr) {
-      uint32_t g = 0, c = 0;
-#pragma unroll
-      for (int j = 0; j < PK; ++j)
-        if (lane == j) { g = nGeom[j]; c = nContrib[j]; }
-      P.counts[2 * (size_t)(r0 + lane)] = g;
-      P.counts[2 * (size_t)(r0 + lane) + 1] = c;
+    if (P.counts && have) {
+      P.counts[2 * (size_t)ray] = nGeom;
+      P.counts[2 * (size_t)ray + 1] = nContrib;
     }
   }
 }
@@ -292,10 +367,10 @@ cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, 
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bre_traverse<false>, kTravWarps * 32, 0);
     if (bps < 1) bps = 1;
   }
-  // persistent grid: a whole number of resident CTAs per SM; warps pull packets from a counter
+  // persistent grid: a whole number of resident CTAs per SM; warps pull tiles from a counter
   unsigned grid = (unsigned)(sm_count * bps);
-  const unsigned packets = (P.ray_end - P.ray_begin + PK - 1) / PK;
-  const unsigned need = (packets + kTravWarps - 1) / kTravWarps;
+  const unsigned tiles = (P.ray_end - P.ray_begin + 31) / 32;
+  const unsigned need = (tiles + kTravWarps - 1) / kTravWarps;
   if (grid > need) grid = need;
   if (dump) k_bre_traverse<true><<<grid, kTravWarps * 32, 0, stream>>>(P);
   else k_bre_traverse<false><<<grid, kTravWarps * 32, 0, stream>>>(P);
