@@ -11,13 +11,13 @@
 
 namespace gvpm {
 size_t sort_temp_bytes(uint32_t n);
-cudaError_t run_sort(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
+cudaError_t run_sort(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                      uint32_t *vout, uint32_t n, cudaStream_t st);
 int bounds_blocks(uint32_t n);
 void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st);
-void launch_morton(const float *pos, uint32_t n, const float *bounds, uint64_t *keys, uint32_t *vals,
+void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st);
-void launch_pack_sorted(const PhotonStaging &S, const uint32_t *sorted, uint32_t n, float4 *planes,
+void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sorted, uint32_t n, float4 *planes,
                         uint32_t *orig, cudaStream_t st);
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st);
@@ -86,7 +86,7 @@ struct gvpm_ctx {
   DevBuf ph_staging;
   uint32_t n_photons = 0;
   bool photons_loaded = false;
-  DevBuf keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
+  DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
   Tree tree{};
   float radius = 0.f;
   bool built = false;
@@ -358,7 +358,9 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
                     &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs,
                     &ctx->samples, &ctx->sample_counts, &ctx->mvol, &ctx->beams, &ctx->beam_bounds, &ctx->sub_pos,
-                    &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi};
+                    &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
+                    &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
+                    &ctx->plane_bounds};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -499,15 +501,17 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     CK(ctx->box_hi.reserve(16 * (size_t)total));
     PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
     launch_bounds(S.pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st);
-    launch_morton(S.pos, n, ctx->bounds.as<float>(), ctx->keys_in.as<uint64_t>(), ctx->vals_in.as<uint32_t>(), st);
-    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+    launch_morton(S.pos, n, ctx->bounds.as<float>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), st);
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                 ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
-    launch_pack_sorted(S, ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(), ctx->orig.as<uint32_t>(), st);
+    CK(ctx->aos.reserve(128 * (size_t)n));
+    launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
+                       ctx->orig.as<uint32_t>(), st);
     float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
     launch_leaf_boxes(ctx->planes.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
     for (int l = 1; l < levels; ++l)
       launch_level_boxes(lo + T.off[l - 1], hi + T.off[l - 1], T.cnt[l - 1], T.cnt[l], lo + T.off[l], hi + T.off[l], st);
-    ctx->launches += 5 + (levels - 1) + 4;  // + the radix sort's own passes (library, ~4 launches)
+    ctx->launches += 6 + (levels - 1) + 4;  // + the radix sort's own passes (library, ~4 launches)
     CK(cudaGetLastError());
   } else {
     CK(cudaMemsetAsync(ctx->bounds.p, 0, 7 * sizeof(float), st));
@@ -695,9 +699,9 @@ int gvpm_build_planes(gvpm_ctx *ctx) {
     CK(ctx->plane_box_lo.reserve(16 * (size_t)nLeaves));
     CK(ctx->plane_box_hi.reserve(16 * (size_t)nLeaves));
     launch_bounds(ctx->plane_pos.as<float>(), n, ctx->bounds_partial.as<float>(), ctx->plane_bounds.as<float>(), st);
-    launch_morton(ctx->plane_pos.as<float>(), n, ctx->plane_bounds.as<float>(), ctx->keys_in.as<uint64_t>(),
+    launch_morton(ctx->plane_pos.as<float>(), n, ctx->plane_bounds.as<float>(), ctx->keys_in.as<uint32_t>(),
                   ctx->vals_in.as<uint32_t>(), st);
-    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                 ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
     launch_plane_pack_sorted(ctx->plane_raw.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->plane_rec.as<float4>(),
                              ctx->plane_orig.as<uint32_t>(), st);
@@ -894,9 +898,9 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
     CK(cudaMemcpyAsync(ctx->sub_pos.p, subPos.data(), 12 * (size_t)n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->sub_raw.p, subRaw.data(), 16 * (size_t)n, cudaMemcpyHostToDevice, st));
     launch_bounds(ctx->sub_pos.as<float>(), n, ctx->bounds_partial.as<float>(), ctx->beam_bounds.as<float>(), st);
-    launch_morton(ctx->sub_pos.as<float>(), n, ctx->beam_bounds.as<float>(), ctx->keys_in.as<uint64_t>(),
+    launch_morton(ctx->sub_pos.as<float>(), n, ctx->beam_bounds.as<float>(), ctx->keys_in.as<uint32_t>(),
                   ctx->vals_in.as<uint32_t>(), st);
-    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint64_t>(), ctx->keys_out.as<uint64_t>(),
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                 ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
     launch_sub_gather(ctx->sub_raw.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->subs.as<float4>(), st);
     float4 *lo = ctx->beam_box_lo.as<float4>(), *hi = ctx->beam_box_hi.as<float4>();

@@ -1,9 +1,11 @@
 // tree_build.cu — GPU build of the photon-point hierarchy.  Replaces PointKDTree::build
 // (include/mitsuba/core/kdtree.h:326-378,921-1037; single-threaded sliding-midpoint recursion) and
 // GradientBeamRadianceEstimator's constructor + buildHierarchy (gvpm/gvpm_accel.cpp:10-55;
-// single-threaded bottom-up AABB recursion) with: bounds reduction -> 63-bit Morton keys ->
-// radix sort -> gather of the raw SoA into Morton-ordered 128-bit record planes -> bottom-up
-// 32-ary box levels (one warp per node, shuffle reductions).  Every step is a streaming pass.
+// single-threaded bottom-up AABB recursion) with: bounds reduction -> 30-bit Morton keys (1024^3 cells:
+// far finer than a leaf of 32 photons, and half the radix passes of a 63-bit key) -> radix sort -> raw SoA
+// packed into 128-byte records (streaming) -> records gathered into Morton-ordered 128-bit planes (every
+// random read is one aligned 128-byte record) -> bottom-up 32-ary box levels (one warp per node, shuffle
+// reductions).
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gvpm_device.cuh"
@@ -70,18 +72,17 @@ __global__ void k_bounds_final(const float *__restrict__ partial, int nblocks, f
   }
 }
 
-__device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits -> every third bit
-  uint64_t x = v & 0x1fffffu;
-  x = (x | x << 32) & 0x1f00000000ffffULL;
-  x = (x | x << 16) & 0x1f0000ff0000ffULL;
-  x = (x | x << 8) & 0x100f00f00f00f00fULL;
-  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
-  x = (x | x << 2) & 0x1249249249249249ULL;
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+  uint32_t x = v & 0x3ffu;
+  x = (x | x << 16) & 0x030000ffu;
+  x = (x | x << 8) & 0x0300f00fu;
+  x = (x | x << 4) & 0x030c30c3u;
+  x = (x | x << 2) & 0x09249249u;
   return x;
 }
 
 __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float *__restrict__ bounds,
-                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                         uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t q[3];
@@ -90,28 +91,43 @@ __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float 
     const float lo = bounds[a], ext = bounds[3 + a] - lo;
     float u = ext > 0.f ? (pos[3 * (size_t)i + a] - lo) / ext : 0.f;
     u = fminf(fmaxf(u, 0.f), 1.f);
-    q[a] = min((uint32_t)(u * 2097152.f), 2097151u);
+    q[a] = min((uint32_t)(u * 1024.f), 1023u);
   }
-  keys[i] = spread21(q[0]) | (spread21(q[1]) << 1) | (spread21(q[2]) << 2);
+  keys[i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
   vals[i] = i;
 }
 
-// gather raw SoA -> Morton-ordered float4 planes
-__global__ void k_pack_sorted(const PhotonStaging S, const uint32_t *__restrict__ sorted, uint32_t n,
-                              float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t s = sorted[i];
+// raw SoA -> 128-byte records in the caller's order (streaming reads, each thread writes its own record)
+//   A0 pos, meta | A1 flux, parent_pdf | A2 parent_pos, edge_pdf | A3 pred_pos, rr_weight | A4 parent_n
+//   A5 prefix_flux | A6 parent_albedo | A7 unused
+#define GVPM_AOS_FLOAT4 8
+__global__ void k_pack_aos(const PhotonStaging S, uint32_t n, float4 *__restrict__ aos) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
   const size_t s3 = 3 * (size_t)s;
   auto ld3 = [&](const float *p, float w) { return make_float4(p[s3], p[s3 + 1], p[s3 + 2], w); };
   const uint32_t meta = pack_meta(S.parent_type[s], S.depth[s], S.path_id[s]);
-  planes[i] = ld3(S.pos, __uint_as_float(meta));
-  planes[(size_t)n + i] = ld3(S.flux, S.parent_pdf[s]);
-  planes[2 * (size_t)n + i] = ld3(S.parent_pos, S.edge_pdf[s]);
-  planes[3 * (size_t)n + i] = ld3(S.pred_pos, S.rr_weight[s]);
-  planes[4 * (size_t)n + i] = ld3(S.parent_n, 0.f);
-  planes[5 * (size_t)n + i] = ld3(S.prefix_flux, 0.f);
-  planes[6 * (size_t)n + i] = ld3(S.parent_albedo, 0.f);
+  float4 *r = aos + (size_t)s * GVPM_AOS_FLOAT4;
+  r[0] = ld3(S.pos, __uint_as_float(meta));
+  r[1] = ld3(S.flux, S.parent_pdf[s]);
+  r[2] = ld3(S.parent_pos, S.edge_pdf[s]);
+  r[3] = ld3(S.pred_pos, S.rr_weight[s]);
+  r[4] = ld3(S.parent_n, 0.f);
+  r[5] = ld3(S.prefix_flux, 0.f);
+  r[6] = ld3(S.parent_albedo, 0.f);
+}
+// records -> Morton-ordered float4 planes: one aligned 128-byte random read per photon, coalesced writes
+__global__ void k_gather_sorted(const float4 *__restrict__ aos, const uint32_t *__restrict__ sorted, uint32_t n,
+                                float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = sorted[i];
+  const float4 *r = aos + (size_t)s * GVPM_AOS_FLOAT4;
+  float4 v[GVPM_PHOTON_PLANES];
+#pragma unroll
+  for (int k = 0; k < GVPM_PHOTON_PLANES; ++k) v[k] = __ldg(r + k);
+#pragma unroll
+  for (int k = 0; k < GVPM_PHOTON_PLANES; ++k) planes[(size_t)k * n + i] = v[k];
   orig[i] = s;
 }
 
@@ -189,14 +205,14 @@ __global__ void k_pack_rays(const RayStaging S, uint32_t n, float4 *__restrict__
 // ---- host-side drivers ---------------------------------------------------------------------
 size_t sort_temp_bytes(uint32_t n) {
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 63);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 30);
   return bytes;
 }
 
-cudaError_t run_sort(void *temp, size_t temp_bytes, const uint64_t *kin, uint64_t *kout, const uint32_t *vin,
+cudaError_t run_sort(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                      uint32_t *vout, uint32_t n, cudaStream_t st) {
-  return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 63, st);
+  return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, 30, st);
 }
 
 int bounds_blocks(uint32_t n) {
@@ -209,13 +225,14 @@ void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, 
   k_bounds_partial<<<nb, 256, 0, st>>>(pos, n, partial);
   k_bounds_final<<<1, 32, 0, st>>>(partial, nb, bounds);
 }
-void launch_morton(const float *pos, uint32_t n, const float *bounds, uint64_t *keys, uint32_t *vals,
+void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st) {
   k_morton<<<(n + 255) / 256, 256, 0, st>>>(pos, n, bounds, keys, vals);
 }
-void launch_pack_sorted(const PhotonStaging &S, const uint32_t *sorted, uint32_t n, float4 *planes,
+void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sorted, uint32_t n, float4 *planes,
                         uint32_t *orig, cudaStream_t st) {
-  k_pack_sorted<<<(n + 255) / 256, 256, 0, st>>>(S, sorted, n, planes, orig);
+  k_pack_aos<<<(n + 255) / 256, 256, 0, st>>>(S, n, aos);
+  k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(aos, sorted, n, planes, orig);
 }
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st) {
