@@ -61,14 +61,27 @@ __device__ __forceinline__ sf phase_eval(const GatherParams &P, v3 wi, v3 wo) {
   return sf(GVPM_INV_FOURPI) * (sf(1.f) - g * g) / (temp * ssqrt(temp));
 }
 
-// any-hit over the occluder list, preceded by a conservative plane-distance cull (|d| = 1, so
-// t >= distance from the origin to the triangle's plane)
+// any-hit over the occluder list.  Two conservative culls precede the strictly rounded Moller-Trumbore test
+// (|d| = 1): (1) the origin is farther from the triangle's plane than maxt; (2) the ray meets the plane at a
+// parameter that is outside [mint, maxt] by more than the rounding of the strict test (the parent vertex of a
+// reconnection usually lies ON a wall, whose plane it then meets at t ~ 0 < mint).  Single exit, so the lanes of a
+// warp reconverge right after the loop.
 __device__ __forceinline__ bool occluded(const GatherParams &P, v3 o, v3 d, sf mint, sf maxt) {
+  bool hit = false;
   if (maxt < mint) return false;
-  for (uint32_t t = 0; t < P.n_tri; ++t) {
-    float4 pl = ldg4(P.tri_plane + t);
-    float dist = fabsf(pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w);
-    if (dist > maxt.v * 1.001f + 1e-5f) continue;
+  const float omag = fmaxf(fmaxf(fabsf(o.x.v), fabsf(o.y.v)), fabsf(o.z.v));
+  for (uint32_t t = 0; t < P.n_tri && !hit; ++t) {
+    const float4 pl = ldg4(P.tri_plane + t);
+    const float sdist = pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w;
+    if (fabsf(sdist) > maxt.v * 1.001f + 1e-5f) continue;
+    const float nd = pl.x * d.x.v + pl.y * d.y.v + pl.z * d.z.v;
+    const float and_ = fabsf(nd);
+    if (and_ > 1e-3f) {
+      // plane parameter tp = -sdist/nd; the strict tt differs from it by < aux.x * |o - p0| / |nd| (+ relative)
+      const float2 aux = __ldg(P.tri_aux + t);
+      const float tp = -sdist / nd, slack = aux.x * (omag + aux.y + 1e-3f) * 1.7321f / and_ + 2e-6f * fabsf(tp);
+      if (tp + slack < mint.v || tp - slack > maxt.v) continue;
+    }
     const float *tv = P.tri + 9 * t;
     v3 p0(__ldg(tv), __ldg(tv + 1), __ldg(tv + 2)), p1(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5)),
         p2(__ldg(tv + 6), __ldg(tv + 7), __ldg(tv + 8));
@@ -84,10 +97,10 @@ __device__ __forceinline__ bool occluded(const GatherParams &P, v3 o, v3 d, sf m
     sf v = dot(d, qvec) * inv_det;
     if (v.v >= 0.f && (u + v).v <= 1.f) {
       sf tt = dot(edge2, qvec) * inv_det;
-      if (tt >= mint && tt <= maxt) return true;
+      if (tt >= mint && tt <= maxt) hit = true;
     }
   }
-  return false;
+  return hit;
 }
 
 // coordinateSystemCoherent, src/libcore/util.cpp:592-599
@@ -168,14 +181,11 @@ struct PhotonRec {
   int ptype;
 };
 __device__ __forceinline__ PhotonRec load_photon(const GatherParams &P, uint32_t pi) {
-  const uint32_t n = P.tree.n;
-  const float4 q0 = ldg4(P.planes + pi);
-  const float4 q1 = ldg4(P.planes + (size_t)n + pi);
-  const float4 q2 = ldg4(P.planes + 2 * (size_t)n + pi);
-  const float4 q3 = ldg4(P.planes + 3 * (size_t)n + pi);
-  const float4 q4 = ldg4(P.planes + 4 * (size_t)n + pi);
-  const float4 q5 = ldg4(P.planes + 5 * (size_t)n + pi);
-  const float4 q6 = ldg4(P.planes + 6 * (size_t)n + pi);
+  // one aligned 128-byte record in the caller's order (tree_build.cu k_pack_aos), reached through the sorted
+  // slot's original index: 4 sectors per photon instead of 7 half-used ones from per-field planes
+  const float4 *r = P.aos + (size_t)__ldg(P.orig + pi) * 8;
+  const float4 q0 = ldg4(r), q1 = ldg4(r + 1), q2 = ldg4(r + 2), q3 = ldg4(r + 3), q4 = ldg4(r + 4), q5 = ldg4(r + 5),
+               q6 = ldg4(r + 6);
   PhotonRec ph;
   ph.p = v3(q0.x, q0.y, q0.z); ph.flux = v3(q1.x, q1.y, q1.z); ph.parent = v3(q2.x, q2.y, q2.z);
   ph.pred = v3(q3.x, q3.y, q3.z); ph.pn = v3(q4.x, q4.y, q4.z); ph.prefix = v3(q5.x, q5.y, q5.z);
@@ -194,7 +204,7 @@ __device__ __forceinline__ void shift_null(const GatherParams &P, const PhotonRe
   weight = sf(0.5f);
   if (P.cfg.use_mis) {
     if (pdfShift.v == 0.f || pdfBase.v == 0.f) weight = sf(1.f);
-    else weight = sf(1.f) / (sf(1.f) + sensor * pdfShift / pdfBase);
+    else weight = frcp(sf(1.f) + sensor * fdiv(pdfShift, pdfBase));
   }
 }
 
@@ -224,78 +234,82 @@ __device__ __forceinline__ v3 get_shift_pos(const GatherParams &P, sf rr2, v3 p,
 
 // shiftPhoton -> shiftPhotonDiffuse (shift_volume_photon.cpp:49-117,382-486) with diffuseReconnection
 // (shift_diffuse.cpp:11-134) inlined for {area emitter, diffuse surface, medium} parents.
-// S, weight keep their defaults (0, 1) when the shift fails.
+// S, weight keep their defaults (0, 1) when the shift fails.  Written without early returns so that the lanes of a
+// warp reconverge after every decision (the reference's `return false` paths are the untaken branches).
 __device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, const PhotonRec &ph, v3 offsetPos,
                                                      v3 dk, v3 eyeK, sf sensor, sf Tshift, sf pdfBase,
                                                      sf pdfShift, v3 &S, sf &weight) {
-  if (ph.ptype == GVPM_PARENT_OTHER) return;  // manifold shift: out of scope, fails like useManifold=false
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
   v3 dProj = offsetPos - ph.parent;
-  sf lProj = length(dProj);
+  const sf lProj = length(dProj);
   dProj = dProj / lProj;
-  if (occluded(P, ph.parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale))) return;
-  if (ph.ptype != GVPM_PARENT_MEDIUM) {  // :404-412
-    v3 edgeD = normalize(ph.p - ph.parent);
-    sf signDot = dot(ph.pn, dProj) / dot(ph.pn, edgeD);
-    if (signDot.v < 0.f) return;
-  }
-  // diffuseReconnection
+  // manifold shift (glossy parent): out of scope, fails like useManifold=false
+  bool ok = ph.ptype != GVPM_PARENT_OTHER;
+  if (ok) ok = !occluded(P, ph.parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale));
+  // type-specific terms of diffuseReconnection, evaluated branch-free where cheap
+  const v3 wiW = normalize(ph.pred - ph.parent);  // incoming direction at a surface / medium parent
+  const sf cosO = dot(ph.pn, dProj);
   v3 thr(1.f, 1.f, 1.f);
   sf pdfValue(0.f);
   bool early = false;
-  if (ph.ptype == GVPM_PARENT_SURFACE) {  // bsdfs/diffuse.cpp:110-127
-    v3 wiW = normalize(ph.pred - ph.parent);
-    sf cosI = dot(ph.pn, wiW), cosO = dot(ph.pn, dProj);
-    if (cosI.v <= 0.f || cosO.v <= 0.f) {
-      thr = v3(0.f, 0.f, 0.f);
-    } else {
-      thr = thr * (ph.albedo * (sf(GVPM_INV_PI) * cosO));
-      pdfValue = sf(GVPM_INV_PI) * cosO;
-    }
-    if ((cosI * cosI).v <= 0.f || (cosO * cosO).v <= 0.f) early = true;
-  } else if (ph.ptype == GVPM_PARENT_MEDIUM) {
-    v3 pWi = normalize(ph.pred - ph.parent);
-    sf phv = phase_eval(P, pWi, dProj);
-    thr = thr * (sigS * phv);
+  if (ph.ptype == GVPM_PARENT_MEDIUM) {
+    const sf phv = phase_eval(P, wiW, dProj);
+    thr = sigS * phv;
     pdfValue = phv;
-  } else {  // emitter sample, emitters/area.cpp:132-150
-    sf dp = dot(dProj, ph.pn);
-    if (dp.v < 0.f) dp = sf(0.f);
-    sf e = sf(GVPM_INV_PI) * dp;
-    thr = thr * v3(e, e, e);
-    pdfValue = e;
+  } else {
+    // side test on surface / emitter parents, :404-412 (the sign of a quotient is the sign test the reference does)
+    const v3 edgeD = normalize(ph.p - ph.parent);
+    const sf signDot = cosO / dot(ph.pn, edgeD);
+    if (signDot.v < 0.f) ok = false;
+    if (ph.ptype == GVPM_PARENT_SURFACE) {  // bsdfs/diffuse.cpp:110-127
+      const sf cosI = dot(ph.pn, wiW);
+      if (cosI.v <= 0.f || cosO.v <= 0.f) {
+        thr = v3(0.f, 0.f, 0.f);
+      } else {
+        thr = ph.albedo * (sf(GVPM_INV_PI) * cosO);
+        pdfValue = sf(GVPM_INV_PI) * cosO;
+      }
+      if ((cosI * cosI).v <= 0.f || (cosO * cosO).v <= 0.f) early = true;
+    } else {  // emitter sample, emitters/area.cpp:132-150
+      sf dp = cosO;
+      if (dp.v < 0.f) dp = sf(0.f);
+      const sf e = sf(GVPM_INV_PI) * dp;
+      thr = v3(e, e, e);
+      pdfValue = e;
+    }
   }
   sf sPdf(0.f);
   if (!early) {
-    sf GOp = sf(1.f) / (lProj * lProj);
+    const sf GOp = sf(1.f) / (lProj * lProj);
     sPdf = pdfValue * GOp;
     thr = thr * GOp;
     if (ph.parentPdf.v == 0.f) {
       sPdf = sf(0.f);
     } else {
-      thr = thr / ph.parentPdf;
-      thr = thr * ph.rrW;
-      MediumRec mr = medium_eval(P, sf(0.f), lProj);
+      const MediumRec mr = medium_eval(P, sf(0.f), lProj);
       sPdf = sPdf * mr.pdfSuccess;
-      sf te = mr.T * (sf(1.f) / ph.edgePdf);  // Spectrum / Float = * (1/f), spectrum.h:415-425
-      thr = thr * te;
+      // thr / parentPdf * rrW * (T / edgePdf): radiometric only
+      thr = thr * (fdiv(ph.rrW, ph.parentPdf) * fdiv(mr.T, ph.edgePdf));
     }
   }
-  if (sPdf.v == 0.f) { weight = sf(1.f); return; }
-  v3 photonWeight = ph.prefix * thr;
-  v3 c = (sigS * photonWeight) * phase_eval(P, -dProj, -dk);
-  S = (c * Tshift) * eyeK;
-  weight = sf(0.5f);
-  if (P.cfg.use_mis) {
-    sf basePdf = pdfBase;
-    basePdf = basePdf * ph.parentPdf;
-    basePdf = basePdf * ph.edgePdf;
-    sf offsetPdf = sPdf * pdfShift;
-    if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
+  if (ok) {
+    if (sPdf.v == 0.f) {
       weight = sf(1.f);
     } else {
-      sf q = sensor * (offsetPdf / basePdf);
-      weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
+      const v3 photonWeight = ph.prefix * thr;
+      const v3 c = (sigS * photonWeight) * phase_eval(P, -dProj, -dk);
+      S = (c * Tshift) * eyeK;
+      weight = sf(0.5f);
+      if (P.cfg.use_mis) {
+        const sf basePdf = (pdfBase * ph.parentPdf) * ph.edgePdf;
+        const sf offsetPdf = sPdf * pdfShift;
+        if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
+          weight = sf(1.f);
+        } else {
+          const sf q = sensor * fdiv(offsetPdf, basePdf);
+          weight = P.cfg.power_heuristic ? frcp(sf(1.f) + q * q) : frcp(sf(1.f) + q);
+        }
+      }
     }
   }
 }
@@ -317,15 +331,14 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
   const v3 contrib = (sigS * ph.flux) * phase_eval(P, wi, -R.d);
   const v3 baseContrib = (contrib * mBase.T) * R.eye;
   const sf norm = sf(P.kernel_vol) * pdfCam;
-  const sf recip = sf(1.f) / norm;
+  const sf recip = frcp(norm);
   acc_add(a, 0, (baseContrib * recip) * rrG);
 
   const MediumRec mShift = medium_eval(P, sf(P.cfg.epsilon), tBase);
   const v3 zBase = R.o + tBase * R.d;
 
-  // The offset loop is kept rolled (one copy of the shift code); its 4 x (S, weight) results go
-  // through a 16-float local array, and the accumulation below uses static indices.
-  float Sx[4], Sy[4], Sz[4], Wk[4];
+  // The offset loop is kept rolled (one copy of the shift code); k is warp-uniform, so the accumulation goes
+  // through a switch with static register indices instead of a local-memory staging array.
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     const float4 s0 = ldg4(rec + 4 * (k + 1)), s1 = ldg4(rec + 4 * (k + 1) + 1), s2 = ldg4(rec + 4 * (k + 1) + 2);
@@ -358,13 +371,14 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
       }
     }
     if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);
-    Sx[k] = S.x.v; Sy[k] = S.y.v; Sz[k] = S.z.v; Wk[k] = weight.v;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const sf rw = rrG * sf(Wk[k]);
-    acc_add(a, 5 + k, (baseContrib * rw) * recip);
-    acc_add(a, 1 + k, (v3(Sx[k], Sy[k], Sz[k]) * rw) * recip);
+    const sf rw = rrG * weight;
+    const v3 wB = (baseContrib * rw) * recip, wS = (S * rw) * recip;
+    switch (k) {
+      case 0: acc_add(a, 5, wB); acc_add(a, 1, wS); break;
+      case 1: acc_add(a, 6, wB); acc_add(a, 2, wS); break;
+      case 2: acc_add(a, 7, wB); acc_add(a, 3, wS); break;
+      default: acc_add(a, 8, wB); acc_add(a, 4, wS); break;
+    }
   }
 }
 

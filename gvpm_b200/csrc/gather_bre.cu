@@ -25,7 +25,7 @@ namespace gvpm {
 #define GVPM_TRAV_WARPS 4
 #endif
 #ifndef GVPM_TRAV_MIN_BLOCKS
-#define GVPM_TRAV_MIN_BLOCKS 6
+#define GVPM_TRAV_MIN_BLOCKS 8
 #endif
 #ifndef GVPM_SHADE_THREADS
 #define GVPM_SHADE_THREADS 128

@@ -80,7 +80,7 @@ struct gvpm_ctx {
   gvpm_config cfg{};
   bool have_cfg = false;
 
-  DevBuf tri, tri_plane;
+  DevBuf tri, tri_plane, tri_aux;
   uint32_t n_tri = 0;
 
   DevBuf ph_staging;
@@ -206,6 +206,7 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   memset(&P, 0, sizeof(P));
   P.tree = ctx->tree;
   P.planes = ctx->planes.as<float4>();
+  P.aos = ctx->aos.as<float4>();
   P.orig = ctx->orig.as<uint32_t>();
   P.rays = ctx->rays.as<float4>();
   P.n_rays = ctx->n_rays;
@@ -228,6 +229,7 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   P.cfg = ctx->cfg;
   P.tri = ctx->tri.as<float>();
   P.tri_plane = ctx->tri_plane.as<float4>();
+  P.tri_aux = ctx->tri_aux.as<float2>();
   P.n_tri = ctx->n_tri;
   P.out = out_dev;
   P.counts = counts_dev;
@@ -353,7 +355,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
   if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
+  DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->tri_aux, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
                     &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
                     &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs,
@@ -408,7 +410,7 @@ int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz, size_t n_tri) {
   cudaSetDevice(ctx->device);
   ctx->n_tri = (uint32_t)n_tri;
   if (n_tri == 0) return GVPM_OK;
-  std::vector<float> planes(4 * n_tri);
+  std::vector<float> planes(4 * n_tri), aux(2 * n_tri);
   for (size_t t = 0; t < n_tri; ++t) {
     const float *p = tri_xyz + 9 * t;
     double e1[3], e2[3], n[3];
@@ -417,6 +419,16 @@ int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz, size_t n_tri) {
     n[1] = e1[2] * e2[0] - e1[0] * e2[2];
     n[2] = e1[0] * e2[1] - e1[1] * e2[0];
     double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    {
+      // rounding slack of the strict ray-triangle parameter (bre_device.cuh occluded()): ~16 eps * |e1||e2|/|e1 x e2|
+      // per unit of |o - p0| / |n.d|; aux = (that coefficient, largest |vertex coordinate|)
+      const double l1 = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]),
+                   l2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+      double vmag = 0;
+      for (int a = 0; a < 9; ++a) vmag = std::max(vmag, (double)std::fabs(p[a]));
+      aux[2 * t] = (float)(len > 0 ? 2e-6 * (l1 * l2 / len) : 0.0);
+      aux[2 * t + 1] = (float)vmag;
+    }
     if (len > 0) {
       for (int a = 0; a < 3; ++a) n[a] /= len;
       planes[4 * t] = (float)n[0]; planes[4 * t + 1] = (float)n[1]; planes[4 * t + 2] = (float)n[2];
@@ -427,6 +439,8 @@ int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz, size_t n_tri) {
   }
   CK(ctx->tri.reserve(9 * n_tri * sizeof(float)));
   CK(ctx->tri_plane.reserve(4 * n_tri * sizeof(float)));
+  CK(ctx->tri_aux.reserve(2 * n_tri * sizeof(float)));
+  CK(cudaMemcpyAsync(ctx->tri_aux.p, aux.data(), 2 * n_tri * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->tri.p, tri_xyz, 9 * n_tri * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->tri_plane.p, planes.data(), 4 * n_tri * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -495,7 +509,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     CK(ctx->vals_out.reserve(4 * (size_t)n));
     const size_t tb = sort_temp_bytes(n);
     CK(ctx->sort_temp.reserve(tb));
-    CK(ctx->planes.reserve(GVPM_PHOTON_PLANES * 16 * (size_t)n));
+    CK(ctx->planes.reserve(16 * (size_t)n));
     CK(ctx->orig.reserve(4 * (size_t)n));
     CK(ctx->box_lo.reserve(16 * (size_t)total));
     CK(ctx->box_hi.reserve(16 * (size_t)total));
@@ -948,6 +962,7 @@ static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
   P.cfg = ctx->cfg;
   P.tri = ctx->tri.as<float>();
   P.tri_plane = ctx->tri_plane.as<float4>();
+  P.tri_aux = ctx->tri_aux.as<float2>();
   P.n_tri = ctx->n_tri;
   P.out = ctx->out.as<float>();
   P.counts = ctx->counts.as<uint32_t>();

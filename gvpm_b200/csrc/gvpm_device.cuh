@@ -30,6 +30,10 @@ __device__ __forceinline__ bool operator>(sf a, sf b) { return a.v > b.v; }
 __device__ __forceinline__ bool operator<=(sf a, sf b) { return a.v <= b.v; }
 __device__ __forceinline__ bool operator>=(sf a, sf b) { return a.v >= b.v; }
 __device__ __forceinline__ bool operator==(sf a, sf b) { return a.v == b.v; }
+// radiometric-only quotients (never feed a decision): MUFU.RCP + FMUL, 2 ulp — the 1e-4 radiance bar is 3 orders
+// of magnitude above that; __fdiv_rn costs ~8 instructions + a slow path
+__device__ __forceinline__ sf fdiv(sf a, sf b) { return sf(__fdividef(a.v, b.v)); }
+__device__ __forceinline__ sf frcp(sf a) { return sf(__fdividef(1.f, a.v)); }
 __device__ __forceinline__ sf ssqrt(sf a) { return sf(__fsqrt_rn(a.v)); }
 __device__ __forceinline__ sf smax(sf a, sf b) { return sf(fmaxf(a.v, b.v)); }
 __device__ __forceinline__ sf safe_sqrt(sf a) { return ssqrt(smax(sf(0.f), a)); }
@@ -62,14 +66,16 @@ __device__ __forceinline__ sf max3(v3 a) { return smax(a.x, smax(a.y, a.z)); }
 #define GVPM_PI 3.14159265358979323846f
 
 // ---- device record layout -----------------------------------------------------
-// Photons: 7 float4 planes of n entries each, in Morton order after the build.
-//   P0 = pos.xyz,           meta bits   (leaf test touches only this plane)
-//   P1 = flux.xyz,          parent_pdf
-//   P2 = parent_pos.xyz,    edge_pdf
-//   P3 = pred_pos.xyz,      rr_weight
-//   P4 = parent_n.xyz,      -
-//   P5 = prefix_flux.xyz,   -
-//   P6 = parent_albedo.xyz, -
+// Photons: one 128-byte record (8 float4) per photon in the caller's order (`aos`), plus the Morton-sorted
+// plane P0 (`planes`) the traversal reads and `orig` (sorted slot -> caller index).
+//   A0 = pos.xyz,           meta bits   (P0 is the sorted copy of this field)
+//   A1 = flux.xyz,          parent_pdf
+//   A2 = parent_pos.xyz,    edge_pdf
+//   A3 = pred_pos.xyz,      rr_weight
+//   A4 = parent_n.xyz,      -
+//   A5 = prefix_flux.xyz,   -
+//   A6 = parent_albedo.xyz, -
+//   A7 = unused (keeps the record one aligned 128-byte line = 4 sectors)
 // meta: bits 0-1 parent type, bits 2-9 depth, bit 10 pathID & 1.
 #define GVPM_PHOTON_PLANES 7
 #define GVPM_PLANE_PLANES 6  // float4 planes per photon-plane record (plane_device.cuh)
@@ -110,7 +116,8 @@ struct Tree {
 
 struct GatherParams {
   Tree tree;
-  const float4 *planes;  // [7][n] sorted
+  const float4 *planes;  // [n] sorted P0 = pos.xyz, meta (the only per-photon data the traversal reads)
+  const float4 *aos;     // [n][8] full records in the caller's order (shading reads aos[orig[slot]])
   const uint32_t *orig;  // [n] original photon index of sorted slot
   const float4 *rays;    // [n_rays][20]
   uint32_t n_rays;
@@ -123,6 +130,7 @@ struct GatherParams {
   gvpm_config cfg;
   const float *tri;  // [n_tri*9]
   const float4 *tri_plane;  // [n_tri] unit plane (n, d) for the conservative cull
+  const float2 *tri_aux;    // [n_tri] (rounding-slack coefficient, largest |vertex coordinate|)
   uint32_t n_tri;
   // outputs
   float *out;        // [n_rays*27]

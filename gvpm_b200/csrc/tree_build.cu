@@ -116,18 +116,13 @@ __global__ void k_pack_aos(const PhotonStaging S, uint32_t n, float4 *__restrict
   r[5] = ld3(S.prefix_flux, 0.f);
   r[6] = ld3(S.parent_albedo, 0.f);
 }
-// records -> Morton-ordered float4 planes: one aligned 128-byte random read per photon, coalesced writes
+// sorted position plane P0 (pos.xyz, meta) + original index: the only sorted copies the gather needs
 __global__ void k_gather_sorted(const float4 *__restrict__ aos, const uint32_t *__restrict__ sorted, uint32_t n,
                                 float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t s = sorted[i];
-  const float4 *r = aos + (size_t)s * GVPM_AOS_FLOAT4;
-  float4 v[GVPM_PHOTON_PLANES];
-#pragma unroll
-  for (int k = 0; k < GVPM_PHOTON_PLANES; ++k) v[k] = __ldg(r + k);
-#pragma unroll
-  for (int k = 0; k < GVPM_PHOTON_PLANES; ++k) planes[(size_t)k * n + i] = v[k];
+  planes[i] = __ldg(aos + (size_t)s * GVPM_AOS_FLOAT4);
   orig[i] = s;
 }
 
