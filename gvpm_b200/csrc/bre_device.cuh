@@ -66,40 +66,66 @@ __device__ __forceinline__ sf phase_eval(const GatherParams &P, v3 wi, v3 wo) {
 // parameter that is outside [mint, maxt] by more than the rounding of the strict test (the parent vertex of a
 // reconnection usually lies ON a wall, whose plane it then meets at t ~ 0 < mint).  Single exit, so the lanes of a
 // warp reconverge right after the loop.
+__device__ __forceinline__ bool occluder_hit(const GatherParams &P, uint32_t t, v3 o, v3 d, sf mint, sf maxt,
+                                             float omag) {
+  const float4 pl = ldg4(P.tri_plane + t);
+  const float sdist = pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w;
+  if (fabsf(sdist) > maxt.v * 1.001f + 1e-5f) return false;
+  const float nd = pl.x * d.x.v + pl.y * d.y.v + pl.z * d.z.v;
+  const float and_ = fabsf(nd);
+  if (and_ > 1e-3f) {
+    // plane parameter tp = -sdist/nd; the strict tt differs from it by < aux.x * |o - p0| / |nd| (+ relative)
+    const float2 aux = __ldg(P.tri_aux + t);
+    const float tp = -sdist / nd, slack = aux.x * (omag + aux.y + 1e-3f) * 1.7321f / and_ + 2e-6f * fabsf(tp);
+    if (tp + slack < mint.v || tp - slack > maxt.v) return false;
+  }
+  const float *tv = P.tri + 9 * t;
+  v3 p0(__ldg(tv), __ldg(tv + 1), __ldg(tv + 2)), p1(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5)),
+      p2(__ldg(tv + 6), __ldg(tv + 7), __ldg(tv + 8));
+  v3 edge1 = p1 - p0, edge2 = p2 - p0;
+  v3 pvec = cross(d, edge2);
+  sf det = dot(edge1, pvec);
+  if (det.v == 0.f) return false;
+  sf inv_det = sf(1.f) / det;
+  v3 tvec = o - p0;
+  sf u = dot(tvec, pvec) * inv_det;
+  if (u.v < 0.f || u.v > 1.f) return false;
+  v3 qvec = cross(tvec, edge1);
+  sf v = dot(d, qvec) * inv_det;
+  if (v.v >= 0.f && (u + v).v <= 1.f) {
+    sf tt = dot(edge2, qvec) * inv_det;
+    if (tt >= mint && tt <= maxt) return true;
+  }
+  return false;
+}
 __device__ __forceinline__ bool occluded(const GatherParams &P, v3 o, v3 d, sf mint, sf maxt) {
   bool hit = false;
   if (maxt < mint) return false;
   const float omag = fmaxf(fmaxf(fabsf(o.x.v), fabsf(o.y.v)), fabsf(o.z.v));
-  for (uint32_t t = 0; t < P.n_tri && !hit; ++t) {
-    const float4 pl = ldg4(P.tri_plane + t);
-    const float sdist = pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w;
-    if (fabsf(sdist) > maxt.v * 1.001f + 1e-5f) continue;
-    const float nd = pl.x * d.x.v + pl.y * d.y.v + pl.z * d.z.v;
-    const float and_ = fabsf(nd);
-    if (and_ > 1e-3f) {
-      // plane parameter tp = -sdist/nd; the strict tt differs from it by < aux.x * |o - p0| / |nd| (+ relative)
-      const float2 aux = __ldg(P.tri_aux + t);
-      const float tp = -sdist / nd, slack = aux.x * (omag + aux.y + 1e-3f) * 1.7321f / and_ + 2e-6f * fabsf(tp);
-      if (tp + slack < mint.v || tp - slack > maxt.v) continue;
+  for (uint32_t t = 0; t < P.n_tri && !hit; ++t) hit = occluder_hit(P, t, o, d, mint, maxt, omag);
+  return hit;
+}
+// Shadow rays of one (ray, photon) pair share their origin (the parent vertex): the triangles whose plane lies
+// within `bound` of it are found once per pair (bit t of the mask, n_tri <= 32); a shadow ray whose plane-distance
+// cull radius fits inside `bound` then visits only those.
+struct OccluderNear { uint32_t mask; float bound; };
+__device__ __forceinline__ OccluderNear occluders_near(const GatherParams &P, v3 o, float bound) {
+  OccluderNear n;
+  n.mask = 0u;
+  n.bound = P.n_tri <= 32u ? bound : -1.f;
+  if (P.n_tri <= 32u)
+    for (uint32_t t = 0; t < P.n_tri; ++t) {
+      const float4 pl = ldg4(P.tri_plane + t);
+      if (fabsf(pl.x * o.x.v + pl.y * o.y.v + pl.z * o.z.v + pl.w) <= bound) n.mask |= 1u << t;
     }
-    const float *tv = P.tri + 9 * t;
-    v3 p0(__ldg(tv), __ldg(tv + 1), __ldg(tv + 2)), p1(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5)),
-        p2(__ldg(tv + 6), __ldg(tv + 7), __ldg(tv + 8));
-    v3 edge1 = p1 - p0, edge2 = p2 - p0;
-    v3 pvec = cross(d, edge2);
-    sf det = dot(edge1, pvec);
-    if (det.v == 0.f) continue;
-    sf inv_det = sf(1.f) / det;
-    v3 tvec = o - p0;
-    sf u = dot(tvec, pvec) * inv_det;
-    if (u.v < 0.f || u.v > 1.f) continue;
-    v3 qvec = cross(tvec, edge1);
-    sf v = dot(d, qvec) * inv_det;
-    if (v.v >= 0.f && (u + v).v <= 1.f) {
-      sf tt = dot(edge2, qvec) * inv_det;
-      if (tt >= mint && tt <= maxt) hit = true;
-    }
-  }
+  return n;
+}
+__device__ __forceinline__ bool occluded_near(const GatherParams &P, const OccluderNear &n, v3 o, v3 d, sf mint, sf maxt) {
+  if (!(maxt.v * 1.001f + 1e-5f <= n.bound)) return occluded(P, o, d, mint, maxt);
+  bool hit = false;
+  if (maxt < mint) return false;
+  const float omag = fmaxf(fmaxf(fabsf(o.x.v), fabsf(o.y.v)), fabsf(o.z.v));
+  for (uint32_t m = n.mask; m != 0u && !hit; m &= m - 1u) hit = occluder_hit(P, __ffs(m) - 1, o, d, mint, maxt, omag);
   return hit;
 }
 
@@ -236,8 +262,27 @@ __device__ __forceinline__ v3 get_shift_pos(const GatherParams &P, sf rr2, v3 p,
 // (shift_diffuse.cpp:11-134) inlined for {area emitter, diffuse surface, medium} parents.
 // S, weight keep their defaults (0, 1) when the shift fails.  Written without early returns so that the lanes of a
 // warp reconverge after every decision (the reference's `return false` paths are the untaken branches).
-__device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, const PhotonRec &ph, v3 offsetPos,
-                                                     v3 dk, v3 eyeK, sf sensor, sf Tshift, sf pdfBase,
+// terms of the reconnection that do not depend on the offset: computed once per (ray, photon) pair
+struct PairCtx {
+  v3 wiW;            // normalize(pred - parent): incoming direction at a surface / medium parent
+  sf cosI, nEdge;    // dot(pn, wiW); dot(pn, normalize(p - parent))
+  OccluderNear near;
+};
+// wi = normalize(parent - p)
+__device__ __forceinline__ PairCtx make_pair_ctx(const GatherParams &P, const PhotonRec &ph, v3 wi) {
+  PairCtx C;
+  C.wiW = normalize(ph.pred - ph.parent);
+  C.cosI = dot(ph.pn, C.wiW);
+  // normalize(p - parent) == -wi bit for bit (negation commutes with every rounding involved)
+  C.nEdge = dot(ph.pn, -wi);
+  // shadow rays run from the parent towards the offset photon over maxt = lProj * shadow_maxt_scale; twice the
+  // base edge length bounds lProj for every coherent offset (longer ones fall back to the full occluder loop)
+  const sf lBase = length(ph.p - ph.parent);
+  C.near = occluders_near(P, ph.parent, 2.f * (lBase.v * P.cfg.shadow_maxt_scale * 1.001f + 1e-5f));
+  return C;
+}
+__device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, const PhotonRec &ph, const PairCtx &C,
+                                                     v3 offsetPos, v3 dk, v3 eyeK, sf sensor, sf Tshift, sf pdfBase,
                                                      sf pdfShift, v3 &S, sf &weight) {
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
   v3 dProj = offsetPos - ph.parent;
@@ -245,9 +290,9 @@ __device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, cons
   dProj = dProj / lProj;
   // manifold shift (glossy parent): out of scope, fails like useManifold=false
   bool ok = ph.ptype != GVPM_PARENT_OTHER;
-  if (ok) ok = !occluded(P, ph.parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale));
-  // type-specific terms of diffuseReconnection, evaluated branch-free where cheap
-  const v3 wiW = normalize(ph.pred - ph.parent);  // incoming direction at a surface / medium parent
+  if (ok) ok = !occluded_near(P, C.near, ph.parent, dProj, sf(P.cfg.epsilon), lProj * sf(P.cfg.shadow_maxt_scale));
+  // type-specific terms of diffuseReconnection
+  const v3 wiW = C.wiW;
   const sf cosO = dot(ph.pn, dProj);
   v3 thr(1.f, 1.f, 1.f);
   sf pdfValue(0.f);
@@ -258,11 +303,10 @@ __device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, cons
     pdfValue = phv;
   } else {
     // side test on surface / emitter parents, :404-412 (the sign of a quotient is the sign test the reference does)
-    const v3 edgeD = normalize(ph.p - ph.parent);
-    const sf signDot = cosO / dot(ph.pn, edgeD);
+    const sf signDot = cosO / C.nEdge;
     if (signDot.v < 0.f) ok = false;
     if (ph.ptype == GVPM_PARENT_SURFACE) {  // bsdfs/diffuse.cpp:110-127
-      const sf cosI = dot(ph.pn, wiW);
+      const sf cosI = C.cosI;
       if (cosI.v <= 0.f || cosO.v <= 0.f) {
         thr = v3(0.f, 0.f, 0.f);
       } else {
@@ -336,6 +380,7 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
 
   const MediumRec mShift = medium_eval(P, sf(P.cfg.epsilon), tBase);
   const v3 zBase = R.o + tBase * R.d;
+  const PairCtx C = make_pair_ctx(P, ph, wi);
 
   // The offset loop is kept rolled (one copy of the shift code); k is warp-uniform, so the accumulation goes
   // through a switch with static register indices instead of a local-memory staging array.
@@ -367,7 +412,7 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
           sf ds = length_sq((ok + dd * dk) - offsetPos);
           pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
         }
-        shift_photon_diffuse(P, ph, offsetPos, dk, eyeK, sensor, mShift.T, pdfCam, pdfShift, S, weight);
+        shift_photon_diffuse(P, ph, C, offsetPos, dk, eyeK, sensor, mShift.T, pdfCam, pdfShift, S, weight);
       }
     }
     if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);

@@ -31,7 +31,7 @@ namespace gvpm {
 #define GVPM_SHADE_THREADS 128
 #endif
 #ifndef GVPM_SHADE_MIN_BLOCKS
-#define GVPM_SHADE_MIN_BLOCKS 4
+#define GVPM_SHADE_MIN_BLOCKS 6
 #endif
 #ifndef GVPM_TILE_QUEUE
 #define GVPM_TILE_QUEUE 16

@@ -157,6 +157,7 @@ __device__ __forceinline__ void vpm_photon(const GatherParams &P, const float4 *
   const sf pdfBase = pdfSuccess * pdfSel;
   const sf recip = sf(1.f) / (kernelVol * pdfBase);
   acc_add(a, 0, baseContrib * recip);
+  const PairCtx C = make_pair_ctx(P, ph, wi);
 
   float Sx[4], Sy[4], Sz[4], Wk[4];
 #pragma unroll 1
@@ -181,7 +182,7 @@ __device__ __forceinline__ void vpm_photon(const GatherParams &P, const float4 *
         shift_null(P, ph, wi, dk, eyeK, sensor, Tk, pdfBase, pdfShift, S, weight);
       } else {  // :604-639
         const v3 offsetPos = get_shift_pos(P, rr2, ph.p, q, zShift, R.d, dk, false);
-        shift_photon_diffuse(P, ph, offsetPos, dk, eyeK, sensor, Tk, pdfBase, pdfShift, S, weight);
+        shift_photon_diffuse(P, ph, C, offsetPos, dk, eyeK, sensor, Tk, pdfBase, pdfShift, S, weight);
       }
     }
     if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);
