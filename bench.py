@@ -319,20 +319,17 @@ def main():
             collect()
 
     def step_e2e():
+        """host buffers in, host buffers out, through the C ABI: H2D photons (rank 0) + broadcast + build, then the
+        pipelined gvpm_gather_bre_host (ray chunks go up while earlier chunks are gathered and their results come
+        down).  Every rank lands its own tiles in (pinned) host memory of the box, which is where a one-process host
+        integrator with one context per GPU reads them; the NCCL gather to rank 0 belongs to the `value` leg."""
         with torch.cuda.stream(stream):
             if rank == 0:
                 ctx.upload_photons(inp["photons"])
             exchange_photons()
             ctx.photon_staging(n_ph)
             ctx.build_points(inp["radius"])
-            ctx.upload_rays(rays)
-            ctx.gather_bre_into(out_dev.data_ptr(), None)
-            collect()
-            if rank == 0 and world > 1:
-                for r in range(world):
-                    out_host_t[r * n_pad * 27:(r + 1) * n_pad * 27].copy_(gathered[r], non_blocking=True)
-            else:
-                out_host_t[:n_pad * 27].copy_(out_dev, non_blocking=True)
+            ctx.gather_bre_host(rays, out_host[:n_local * 27])
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

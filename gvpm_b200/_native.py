@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre",
-    "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_dump_neighbours_bre",
+    "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
     "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
@@ -117,6 +117,7 @@ def load_lib():
     lib.gvpm_gather_bre.argtypes = [vp, f32p, u32p]
     lib.gvpm_gather_bre_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.gvpm_gather_bre_into.argtypes = [vp, vp, vp]
+    lib.gvpm_gather_bre_host.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t, f32p]
     lib.gvpm_dump_neighbours_bre.argtypes = [vp, u64p, u32p, C.c_size_t]
     lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]

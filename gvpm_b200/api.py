@@ -109,6 +109,16 @@ class Context:
                                                C.c_void_p(counts_dev_ptr) if counts_dev_ptr else None),
                  "gvpm_gather_bre_into")
 
+    def gather_bre_host(self, rays, out=None):
+        """upload_rays + gather_bre + download, pipelined (rays / out should be pinned host memory)."""
+        cs = rays.as_c()
+        self.n_rays = rays.n
+        if out is None:
+            out = np.empty(rays.n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        self._ck(self.lib.gvpm_gather_bre_host(self.h, C.byref(cs), rays.n, out.ctypes.data_as(N.f32p)),
+                 "gvpm_gather_bre_host")
+        return out.reshape(rays.n, N.GVPM_OUT_FLOATS)
+
     def dump_neighbours_bre(self):
         """-> (offsets [n_rays+1] uint64, idx uint32 with bit 31 = contributes), per-ray sorted."""
         n = self.n_rays

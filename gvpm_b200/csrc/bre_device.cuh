@@ -74,10 +74,12 @@ __device__ __forceinline__ bool occluder_hit(const GatherParams &P, uint32_t t, 
   const float nd = pl.x * d.x.v + pl.y * d.y.v + pl.z * d.z.v;
   const float and_ = fabsf(nd);
   if (and_ > 1e-3f) {
-    // plane parameter tp = -sdist/nd; the strict tt differs from it by < aux.x * |o - p0| / |nd| (+ relative)
+    // plane parameter tp = -sdist/nd; the strict tt differs from it by < aux.x * |o - p0| / |nd| (+ relative).
+    // Compared after multiplying through by |nd| (no division).
     const float2 aux = __ldg(P.tri_aux + t);
-    const float tp = -sdist / nd, slack = aux.x * (omag + aux.y + 1e-3f) * 1.7321f / and_ + 2e-6f * fabsf(tp);
-    if (tp + slack < mint.v || tp - slack > maxt.v) return false;
+    const float num = nd < 0.f ? sdist : -sdist;  // tp * |nd|
+    const float slack = aux.x * (omag + aux.y + 1e-3f) * 1.7321f + 2e-6f * fabsf(num);
+    if (num + slack < mint.v * and_ || num - slack > maxt.v * and_) return false;
   }
   const float *tv = P.tri + 9 * t;
   v3 p0(__ldg(tv), __ldg(tv + 1), __ldg(tv + 2)), p1(__ldg(tv + 3), __ldg(tv + 4), __ldg(tv + 5)),

@@ -24,6 +24,7 @@ void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float rad
 void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, uint32_t nParent, float4 *plo,
                         float4 *phi, cudaStream_t st);
 void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st);
+void launch_pack_rays_range(const RayStaging &S, uint32_t r0, uint32_t r1, float4 *rays, cudaStream_t st);
 cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_bre_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_sub_gather(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *out, cudaStream_t st);
@@ -70,7 +71,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct gvpm_ctx {
   int device = 0, sm_count = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;  // compute, H2D, D2H
+  cudaEvent_t pipe_ev[2 * 32 + 1] = {};  // per chunk: inputs landed / results ready; [64]: staging free
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
@@ -343,6 +345,9 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
     return GVPM_ERR_CUDA;
   }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+  for (auto &ev : ctx->pipe_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   ctx->work_counter.reserve(256);
   cudaHostAlloc((void **)&ctx->pair_count_host, sizeof(unsigned long long), cudaHostAllocDefault);
   ctx->bounds.reserve(256);
@@ -366,6 +371,9 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->pipe_ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamDestroy(ctx->copy_in); }
+  if (ctx->copy_out) { cudaStreamSynchronize(ctx->copy_out); cudaStreamDestroy(ctx->copy_out); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return GVPM_OK;
@@ -614,6 +622,75 @@ int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
     if (counts)
       CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+// Pipelined iteration tail: rays are uploaded in chunks on a copy stream while earlier chunks are packed, traversed
+// and shaded on the compute stream and their results stream back on a third one, so PCIe (both directions) and the
+// SMs work at the same time.  Equivalent to gvpm_upload_rays + gvpm_gather_bre.
+int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *out) {
+  if (!ctx || (n && (!r || !out))) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = gvpm_ray_staging(ctx, n, nullptr, nullptr);
+  if (rc) return rc;
+  CK(ctx->rays.reserve((size_t)n * GVPM_RAY_FLOAT4 * 16 + 256));
+  CK(ctx->out.reserve((size_t)n * GVPM_OUT_FLOATS * 4 + 256));
+  CK(ctx->counts.reserve((size_t)n * 8 + 256));
+  ctx->rays_loaded = true;
+  GatherParams P;
+  rc = fill_params(ctx, P, ctx->out.as<float>(), nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->last_pairs = 0;
+  if (n) {
+    const void *src[16] = {r->o, r->d, r->mint, r->maxt, r->edge_len, r->eye_contrib, r->xi, r->px, r->py,
+                           r->edge_id, r->off_valid, r->off_o, r->off_d, r->off_len, r->off_eye, r->off_sensor};
+    const size_t elt[16] = {12, 12, 4, 4, 4, 12, 4, 4, 4, 4, 4, 48, 48, 16, 48, 16};
+    for (int i = 0; i < 16; ++i)
+      if (!src[i]) return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_ray_soa");
+    if (ctx->pair_cap == 0) {
+      CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 16 * n) * sizeof(uint2)));
+      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    }
+    // chunks of whole 32-ray tiles, ~256k rays each
+    int nChunks = (int)std::min<size_t>(32, std::max<size_t>(1, n / 262144));
+    size_t per = ((n + nChunks - 1) / nChunks + 31) & ~(size_t)31;
+    RayLayout L(n);
+    char *stg = (char *)ctx->ray_staging.p;
+    const RayStaging S = ray_staging_ptrs(ctx->ray_staging.p, n);
+    // the staging buffer may still be read by work queued earlier on the compute stream
+    CK(cudaEventRecord(ctx->pipe_ev[64], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->pipe_ev[64], 0));
+    CK(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[64], 0));
+    int used = 0;
+    for (int c = 0; c < nChunks; ++c) {
+      const size_t r0 = (size_t)c * per, r1 = std::min(n, r0 + per);
+      if (r0 >= r1) break;
+      for (int i = 0; i < 16; ++i)
+        CK(cudaMemcpyAsync(stg + L.off[i] + r0 * elt[i], (const char *)src[i] + r0 * elt[i], (r1 - r0) * elt[i],
+                           cudaMemcpyHostToDevice, ctx->copy_in));
+      CK(cudaEventRecord(ctx->pipe_ev[2 * c], ctx->copy_in));
+      used = c + 1;
+    }
+    for (int c = 0; c < used; ++c) {
+      const size_t r0 = (size_t)c * per, r1 = std::min(n, r0 + per);
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * c], 0));
+      launch_pack_rays_range(S, (uint32_t)r0, (uint32_t)r1, ctx->rays.as<float4>(), ctx->stream);
+      ctx->launches += 1;
+      CK(cudaMemsetAsync(ctx->out.as<float>() + r0 * GVPM_OUT_FLOATS, 0, (r1 - r0) * GVPM_OUT_FLOATS * sizeof(float),
+                         ctx->stream));
+      rc = gather_range(ctx, P, (uint32_t)r0, (uint32_t)r1, 0);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[2 * c + 1], 0));
+      CK(cudaMemcpyAsync(out + r0 * GVPM_OUT_FLOATS, ctx->out.as<float>() + r0 * GVPM_OUT_FLOATS,
+                         (r1 - r0) * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  CK(cudaStreamSynchronize(ctx->copy_out));
   CK(cudaStreamSynchronize(ctx->stream));
   return GVPM_OK;
 }

@@ -176,8 +176,8 @@ __global__ void k_level_boxes(const float4 *__restrict__ clo, const float4 *__re
 }
 
 // raw ray SoA -> 5 x 64 B records per ray
-__global__ void k_pack_rays(const RayStaging S, uint32_t n, float4 *__restrict__ rays) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_pack_rays(const RayStaging S, uint32_t r0, uint32_t n, float4 *__restrict__ rays) {
+  const uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 *r = rays + (size_t)i * GVPM_RAY_FLOAT4;
   const size_t i3 = 3 * (size_t)i;
@@ -238,7 +238,10 @@ void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, u
   k_level_boxes<<<(nParent + 7) / 8, 256, 0, st>>>(clo, chi, nChild, nParent, plo, phi);
 }
 void launch_pack_rays(const RayStaging &S, uint32_t n, float4 *rays, cudaStream_t st) {
-  k_pack_rays<<<(n + 255) / 256, 256, 0, st>>>(S, n, rays);
+  k_pack_rays<<<(n + 255) / 256, 256, 0, st>>>(S, 0u, n, rays);
+}
+void launch_pack_rays_range(const RayStaging &S, uint32_t r0, uint32_t r1, float4 *rays, cudaStream_t st) {
+  if (r1 > r0) k_pack_rays<<<(r1 - r0 + 255) / 256, 256, 0, st>>>(S, r0, r1, rays);
 }
 
 }  // namespace gvpm

@@ -242,6 +242,12 @@ int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t 
 /* same, written to caller-provided device memory (e.g. a peer-mapped / NCCL buffer) */
 int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
 
+/* The whole per-iteration tail in one call: gvpm_upload_rays + gvpm_gather_bre, pipelined - rays go up in chunks on a
+ * copy stream while earlier chunks are traversed and shaded and their results stream back, so both PCIe directions
+ * and the SMs are busy at once.  r and out should be page-locked (cudaHostAlloc / cudaHostRegister) for the copies
+ * to overlap; pageable memory works but serialises.  out: [n*27] host floats, un-normalised. */
+int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *out);
+
 /* Parity aid: neighbour index sets in CSR form.  offsets: [n_rays+1]; idx: capacity `cap`
  * entries, original photon index with bit 31 set when the photon also passes the depth /
  * interaction-mode / pathSet filters.  Returns GVPM_ERR_INVALID when cap is too small

@@ -75,3 +75,20 @@ def test_ragged_and_empty(built):
     out, counts = ctx.gather_bre()
     assert out.shape == (0, 27)
     ctx.close()
+
+
+@pytest.mark.parametrize("order", ["random", "zorder", "strided"])
+def test_ray_order_does_not_matter(built, order):
+    """The tile traversal groups 32 consecutive rays; incoherent tiles fall back to quads of 4 lanes and to single
+    rays.  Whatever the order of the ray list, every ray must gather exactly its own neighbour set."""
+    import gvpm_b200 as g
+    case = H.make_case(n_photons=30000, w=48, h=32, scale=2.0)
+    if order == "zorder":
+        case.rays = g.synth_rays(48, 32, seed=0xC0FFEE + 1, block=-16)
+    elif order == "random":
+        case.rays = case.rays.take(np.random.default_rng(3).permutation(case.rays.n))
+    else:  # neighbours in a quad are coherent, quads are far apart
+        idx = np.arange(case.rays.n).reshape(-1, 4)
+        case.rays = case.rays.take(idx[np.random.default_rng(4).permutation(len(idx))].reshape(-1))
+    ref, _ = _check(case, f"ray order {order}")
+    assert ref.counts[:, 0].sum() > 1000

@@ -159,3 +159,19 @@ def test_properties_at_scale(built):
     assert same.mean() > 0.999  # the reference tree's Epsilon sliver at the ray end
     H.assert_radiance_close(out[sel][same], ref.out[same], 1e-4, "sampled rays vs oracle kd-tree")
     ctx.close()
+
+
+@pytest.mark.parametrize("w,h", [(48, 32), (1024, 576)])
+def test_pipelined_host_gather(built, w, h):
+    """gvpm_gather_bre_host (chunked upload / gather / download on three streams) == upload_rays + gather_bre.
+    1024x576 rays span several chunks."""
+    c = H.make_case(n_photons=100_000, w=w, h=h, scale=1.0 if w > 100 else 3.0)
+    ctx = H.gpu_context(c)
+    out, counts = ctx.gather_bre()
+    assert counts[:, 1].sum() > 1000
+    piped = ctx.gather_bre_host(c.rays)
+    H.assert_radiance_close(piped, out, 1e-5, "pipelined vs plain")
+    # a second iteration through the same context (staging reuse across the copy / compute streams)
+    piped2 = ctx.gather_bre_host(c.rays)
+    H.assert_radiance_close(piped2, out, 1e-5, "pipelined, second call")
+    ctx.close()
