@@ -25,7 +25,7 @@ namespace gvpm {
 #define GVPM_TRAV_WARPS 4
 #endif
 #ifndef GVPM_TRAV_MIN_BLOCKS
-#define GVPM_TRAV_MIN_BLOCKS 8
+#define GVPM_TRAV_MIN_BLOCKS 6
 #endif
 #ifndef GVPM_SHADE_THREADS
 #define GVPM_SHADE_THREADS 128
@@ -34,12 +34,22 @@ namespace gvpm {
 #define GVPM_SHADE_MIN_BLOCKS 6
 #endif
 #ifndef GVPM_TILE_QUEUE
-#define GVPM_TILE_QUEUE 16
+#define GVPM_TILE_QUEUE 32
 #endif
 constexpr int kTravWarps = GVPM_TRAV_WARPS;
 constexpr int kTileQ = GVPM_TILE_QUEUE;  // candidate queue entries per lane
+#ifndef GVPM_LEAF_BATCH
+#define GVPM_LEAF_BATCH 2
+#endif
+constexpr int kLeafBatch = GVPM_LEAF_BATCH;  // leaves whose photon loads are in flight together
+#ifndef GVPM_TILE_BATCH
+#define GVPM_TILE_BATCH 16
+#endif
+constexpr int kTileBatch = GVPM_TILE_BATCH;  // photons tested between queue-room checks
+static_assert(kTileBatch <= kTileQ, "a batch must fit in an empty queue");
 
 struct TileShared {
+  float4 ph[32 * kLeafBatch];  // photons of the current leaf batch that lie inside the fat ray
   uint32_t queue[kTileQ][32];  // [entry][lane]: sorted photon slots waiting for the strict test
   uint32_t mask[GVPM_MAX_LEVELS];
   uint32_t base[GVPM_MAX_LEVELS];
@@ -160,19 +170,26 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
 
     // one stackless walk for the lanes of `gm`, sharing the fat ray (co, cd) of half-width `spread`
     auto traverse_group = [&](uint32_t gm, float cox, float coy, float coz, float cdx, float cdy, float cdz,
-                              float spread, float tloG, float thiG, float omag) {
-      // conservative culling: relaxed arithmetic made safe by `fpad` (a few ulp of the coordinate
-      // magnitudes: rounding of the slab test and of the strict predicate) plus the group spread
+                              float sx, float sy, float sz, float tloG, float thiG, float omag) {
+      // (sx, sy, sz): per-axis bound of |ray_j(t) - axis(t)| over the group and t in [0, tEnd]: the fat ray is the
+      // axis swept by that box (much tighter than a sphere for the usual wide-and-flat pixel tile).
+      // Conservative culling: relaxed arithmetic made safe by `fpad` (a few ulp of the coordinate magnitudes:
+      // rounding of the slab test and of the strict predicate) plus the group spread.
+      const float spread = sqrtf(sx * sx + sy * sy + sz * sz);
       const float fpad = (omag + coordMag + fabsf(thiG) + P.radius + spread) * 3.8147e-6f;  // 2^-18
-      const float pad = fpad + spread;
-      const float oxp = cox + pad, oxm = cox - pad, oyp = coy + pad, oym = coy - pad, ozp = coz + pad,
-                  ozm = coz - pad;
+      const float oxp = cox + (sx + fpad), oxm = cox - (sx + fpad), oyp = coy + (sy + fpad), oym = coy - (sy + fpad),
+                  ozp = coz + (sz + fpad), ozm = coz - (sz + fpad);
       const float ix = 1.f / cdx, iy = 1.f / cdy, iz = 1.f / cdz;
       const float tloBox = tloG - 4.f * fpad - spread;                 // axial range of the fat ray
       const float thiBox = thiG + P.radius + 4.f * fpad + spread;
       const float tloRay = tloG - 4.f * fpad;                          // per-ray disk distance bound
       const float rpad2 = (P.radius + fpad) * (P.radius + fpad);
-      const float fat2 = (P.radius + pad + fpad) * (P.radius + pad + fpad);
+      // a photon within r of ray j at parameter t_j: q = p - axis(dd) (dd = its own axial coordinate) differs from
+      // p - axis(t_j) by (dd - t_j) * cd with |dd - t_j| <= spread + r, so per axis
+      //   |q_a| <= s_a + r + (spread + r) * |cd_a|
+      const float slop = spread + P.radius + 2.f * fpad;
+      const float fx = sx + P.radius + 2.f * fpad + slop * fabsf(cdx), fy = sy + P.radius + 2.f * fpad + slop * fabsf(cdy),
+                  fz = sz + P.radius + 2.f * fpad + slop * fabsf(cdz);
       const float tloFat = tloBox - P.radius, thiFat = thiBox;
       const bool mine = gm >> lane & 1u;
 
@@ -189,10 +206,10 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
           base = S.base[l];
           continue;
         }
-        const int c = __ffs(cur) - 1;
-        cur &= cur - 1;
-        const uint32_t node = base + c;
         if (l > 0) {
+          const int c = __ffs(cur) - 1;
+          cur &= cur - 1;
+          const uint32_t node = base + c;
           S.mask[l] = cur;
           S.base[l] = base;
           --l;
@@ -202,38 +219,68 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
                                                                        ozm, ix, iy, iz, tloBox, thiBox));
           continue;
         }
-        // ---- leaf: lane holds photon (node*32 + lane), tested once against the fat ray ----
-        const uint32_t pi = (node << 5) + lane;
-        bool inFat = false;
-        if (pi < T.n) {
-          const float4 q0 = ldg4(P.planes + pi);
+        // ---- leaves: `cur` lists the hit leaves of one parent.  Their photon loads are independent, so they are
+        // issued kLeafBatch at a time (the walk is otherwise one long chain of dependent L2-latency loads).
+        // Lane holds photon (leaf*32 + lane), tested once against the fat ray.
+        int leafC[kLeafBatch];
+        float4 leafQ[kLeafBatch];
+#pragma unroll
+        for (int b = 0; b < kLeafBatch; ++b) {
+          leafC[b] = -1;
+          leafQ[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cur) {
+            const int c = __ffs(cur) - 1;
+            cur &= cur - 1;
+            const uint32_t pi = ((base + (uint32_t)c) << 5) + lane;
+            if (pi < T.n) {
+              leafC[b] = c;
+              leafQ[b] = ldg4(P.planes + pi);
+            }
+          }
+        }
+        // the photons inside the fat ray are compacted into shared memory (all leaves of the batch together) and
+        // broadcast from there; w = lane | leaf-in-parent << 5 | meta << 10
+        __syncwarp();
+        uint32_t total = 0;
+#pragma unroll
+        for (int b = 0; b < kLeafBatch; ++b) {
+          const float4 q0 = leafQ[b];
           const float cx = q0.x - cox, cy = q0.y - coy, cz = q0.z - coz;
           const float dd = cx * cdx + cy * cdy + cz * cdz;
           const float qx = cx - dd * cdx, qy = cy - dd * cdy, qz = cz - dd * cdz;
-          inFat = (qx * qx + qy * qy + qz * qz) < fat2 && dd > tloFat && dd < thiFat;
+          const bool inFat = leafC[b] >= 0 && fabsf(qx) < fx && fabsf(qy) < fy && fabsf(qz) < fz && dd > tloFat &&
+                             dd < thiFat;
+          const uint32_t pm = __ballot_sync(0xffffffffu, inFat);
+          if (inFat)
+            S.ph[total + __popc(pm & ((1u << lane) - 1u))] = make_float4(
+                q0.x, q0.y, q0.z,
+                __uint_as_float((uint32_t)lane | ((uint32_t)leafC[b] << 5) | (__float_as_uint(q0.w) << 10)));
+          total += __popc(pm);
         }
-        uint32_t pm = __ballot_sync(0xffffffffu, inFat);
-        while (pm) {
-          const int b = __ffs(pm) - 1;
-          pm &= pm - 1;
-          const uint32_t slot = (node << 5) + b;
-          const float4 ph = ldg4(P.planes + slot);  // warp-uniform address
-          bool cand = false;
+        __syncwarp();
+        const uint32_t slot0 = base << 5;
+        for (uint32_t i0 = 0; i0 < total; i0 += kTileBatch) {
+          const uint32_t i1 = min(total, i0 + (uint32_t)kTileBatch);
+          // a lane pushes at most one entry per photon: make room for the whole batch up front
+          if (__any_sync(0xffffffffu, qn + (i1 - i0) > (uint32_t)kTileQ)) flush();
           if (mine) {
-            // relaxed (FMA) pre-test of the lane's own ray, conservative by fpad
-            const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
-            const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
-            const float qx = cx - dd * L.dx, qy = cy - dd * L.dy, qz = cz - dd * L.dz;
-            cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tloRay;
-            if (prefilter && cand) {
-              const uint32_t meta = __float_as_uint(ph.w);
-              if (P.cfg.path_set && (int)((meta >> 10) & 1u) != parity) cand = false;
-              const int pathLen = (int)((meta >> 2) & 255u) + L.eid;
-              if (P.cfg.max_depth > 0 && pathLen > P.cfg.max_depth) cand = false;
+#pragma unroll 2
+            for (uint32_t i = i0; i < i1; ++i) {
+              const float4 ph = S.ph[i];
+              // relaxed (FMA) pre-test of the lane's own ray, conservative by fpad
+              const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
+              const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
+              const float qx = cx - dd * L.dx, qy = cy - dd * L.dy, qz = cz - dd * L.dz;
+              bool cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tloRay;
+              const uint32_t w = __float_as_uint(ph.w);
+              if (prefilter) {
+                // meta << 10: bit 20 = pathID parity, bits 12-19 = depth
+                if (P.cfg.path_set && (int)((w >> 20) & 1u) != parity) cand = false;
+                if (P.cfg.max_depth > 0 && (int)((w >> 12) & 255u) + L.eid > P.cfg.max_depth) cand = false;
+              }
+              if (cand) S.queue[qn++][lane] = slot0 + (w & 1023u);
             }
-            if (cand) S.queue[qn++][lane] = slot;
           }
-          if (__any_sync(0xffffffffu, qn == (uint32_t)kTileQ)) flush();
         }
       }
     };
@@ -246,24 +293,25 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
       float mdx = warp_sum(active ? L.dx : 0.f), mdy = warp_sum(active ? L.dy : 0.f), mdz = warp_sum(active ? L.dz : 0.f);
       const float mlen = sqrtf(mdx * mdx + mdy * mdy + mdz * mdz);
       const float tEnd = warp_max(active ? L.elen : 0.f) + P.radius;
-      float dev = 0.f;
+      float dvx = 0.f, dvy = 0.f, dvz = 0.f;
       bool okDir = mlen > 0.5f * cnt;  // nearly parallel rays only
       if (okDir) {
         const float il = 1.f / mlen;
         mdx *= il; mdy *= il; mdz *= il;
         if (active) {
-          // distance between corresponding points of the lane's ray and the central ray over [0, tEnd]
+          // per-axis distance between corresponding points of the lane's ray and the central ray over [0, tEnd]
           // (linear in t, so attained at an end)
           const float ax = L.ox - mox, ay = L.oy - moy, az = L.oz - moz;
           const float bx = ax + tEnd * (L.dx - mdx), by = ay + tEnd * (L.dy - mdy), bz = az + tEnd * (L.dz - mdz);
-          dev = fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz));
+          dvx = fmaxf(fabsf(ax), fabsf(bx)); dvy = fmaxf(fabsf(ay), fabsf(by)); dvz = fmaxf(fabsf(az), fabsf(bz));
         }
       }
-      const float spread32 = warp_max(dev) * 1.0001f;
+      const float s32x = warp_max(dvx) * 1.0001f, s32y = warp_max(dvy) * 1.0001f, s32z = warp_max(dvz) * 1.0001f;
+      const float spread32 = sqrtf(s32x * s32x + s32y * s32y + s32z * s32z);
       const float amag = active ? fmaxf(fmaxf(fabsf(L.ox), fabsf(L.oy)), fabsf(L.oz)) : 0.f;
       if (okDir && spread32 <= spreadMax) {
         const float tloG = warp_min(active ? L.mint : 3.4e38f), thiG = warp_max(active ? L.elen : -3.4e38f);
-        traverse_group(actMask, mox, moy, moz, mdx, mdy, mdz, spread32, tloG, thiG, warp_max(amag));
+        traverse_group(actMask, mox, moy, moz, mdx, mdy, mdz, s32x, s32y, s32z, tloG, thiG, warp_max(amag));
       } else {
         // quads of 4 consecutive lanes, then single rays
         const float qc = quad_sum(active ? 1.f : 0.f), qi = qc > 0.f ? 1.f / qc : 0.f;
@@ -272,17 +320,18 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
         float qdx = quad_sum(active ? L.dx : 0.f), qdy = quad_sum(active ? L.dy : 0.f), qdz = quad_sum(active ? L.dz : 0.f);
         const float qlen = sqrtf(qdx * qdx + qdy * qdy + qdz * qdz);
         const bool qok = qlen > 0.5f * qc && qc > 0.f;
-        float qdev = 0.f;
+        float qvx = 0.f, qvy = 0.f, qvz = 0.f;
         if (qok) {
           const float il = 1.f / qlen;
           qdx *= il; qdy *= il; qdz *= il;
           if (active) {
             const float ax = L.ox - qox, ay = L.oy - qoy, az = L.oz - qoz;
             const float bx = ax + tEnd * (L.dx - qdx), by = ay + tEnd * (L.dy - qdy), bz = az + tEnd * (L.dz - qdz);
-            qdev = fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz));
+            qvx = fmaxf(fabsf(ax), fabsf(bx)); qvy = fmaxf(fabsf(ay), fabsf(by)); qvz = fmaxf(fabsf(az), fabsf(bz));
           }
         }
-        const float qspread = quad_max(qdev) * 1.0001f;
+        const float qsx = quad_max(qvx) * 1.0001f, qsy = quad_max(qvy) * 1.0001f, qsz = quad_max(qvz) * 1.0001f;
+        const float qspread = sqrtf(qsx * qsx + qsy * qsy + qsz * qsz);
         const float qtlo = -quad_max(active ? -L.mint : -3.4e38f), qthi = quad_max(active ? L.elen : -3.4e38f);
         const float qmag = quad_max(amag);
         for (int q = 0; q < 8; ++q) {
@@ -294,14 +343,15 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
             traverse_group(gm, __shfl_sync(0xffffffffu, qox, ld), __shfl_sync(0xffffffffu, qoy, ld),
                            __shfl_sync(0xffffffffu, qoz, ld), __shfl_sync(0xffffffffu, qdx, ld),
                            __shfl_sync(0xffffffffu, qdy, ld), __shfl_sync(0xffffffffu, qdz, ld),
-                           __shfl_sync(0xffffffffu, qspread, ld), __shfl_sync(0xffffffffu, qtlo, ld),
+                           __shfl_sync(0xffffffffu, qsx, ld), __shfl_sync(0xffffffffu, qsy, ld),
+                           __shfl_sync(0xffffffffu, qsz, ld), __shfl_sync(0xffffffffu, qtlo, ld),
                            __shfl_sync(0xffffffffu, qthi, ld), __shfl_sync(0xffffffffu, qmag, ld));
           } else {
             for (uint32_t m = gm; m; m &= m - 1) {
               const int j = __ffs(m) - 1;
               traverse_group(1u << j, __shfl_sync(0xffffffffu, L.ox, j), __shfl_sync(0xffffffffu, L.oy, j),
                              __shfl_sync(0xffffffffu, L.oz, j), __shfl_sync(0xffffffffu, L.dx, j),
-                             __shfl_sync(0xffffffffu, L.dy, j), __shfl_sync(0xffffffffu, L.dz, j), 0.f,
+                             __shfl_sync(0xffffffffu, L.dy, j), __shfl_sync(0xffffffffu, L.dz, j), 0.f, 0.f, 0.f,
                              __shfl_sync(0xffffffffu, L.mint, j), __shfl_sync(0xffffffffu, L.elen, j),
                              __shfl_sync(0xffffffffu, amag, j));
             }
