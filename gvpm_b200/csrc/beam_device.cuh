@@ -79,8 +79,11 @@ __device__ __forceinline__ bool cylinder_intersection(v3 co, v3 cd, sf cMaxt, v3
   if ((ad * ad).v >= ((radius * radius) * sinThetaSqr).v) return false;
   v3 s, t;
   coordinate_system(cd, s, t);
-  const v3 rel = vo - co;
-  const v3 lo(dot(rel, s), dot(rel, t), dot(rel, cd)), ld(dot(vd, s), dot(vd, t), dot(vd, cd));
+  // worldToObject = (translate(co) * fromFrame(Frame(cd))).inverse() applied to the view ray: the 4x4 product
+  // leaves the rotation rows untouched and puts -dot(axis, co) in the last column (matrix.h:744-756,
+  // transform.cpp:28-45,216-227), so a point maps to dot(axis, p) + (-dot(axis, co)) (transform.h:108-125)
+  const v3 lo(dot(vo, s) - dot(co, s), dot(vo, t) - dot(co, t), dot(vo, cd) - dot(co, cd)),
+      ld(dot(vd, s), dot(vd, t), dot(vd, cd));
   const sd ox((double)lo.x.v), oy((double)lo.y.v), dx((double)ld.x.v), dy((double)ld.y.v);
   const sd A = dx * dx + dy * dy;
   const sd B = sd(2.0) * (dx * ox + dy * oy);

@@ -5,10 +5,17 @@
 // cpu_baseline / --impl reference legs of bench.py as the checker and the timed CPU baseline.
 // The product path (gvpm_b200/csrc) never includes, links or calls anything in oracle/.
 //
-// PARITY UNPINNED: the reference ships no test, golden vector or fixture for this path
-//  and its Mitsuba build cannot be produced in this image (Boost, Eigen,
-// Xerces, OpenEXR ... are absent), so this restatement is pinned only by
-// self-consistency checks (tests/test_oracle_*.py), not by reference outputs.
+// PARITY PARTLY PINNED: the reference ships no test, golden vector or fixture for this path (SURVEY.md §4,
+// §8c) and Mitsuba as a whole cannot be built in this image (Boost, Eigen, Xerces, OpenEXR ... are absent,
+// DESIGN.md §5).  What CAN be compiled from the reference tree is: PointKDTree build + range query, the AABB
+// slab test, GPhotonMap + GradientBeamRadianceEstimator (hierarchy + traversal + neighbour predicate),
+// SubBeamBVH, PhotonPlaneBVH, cylinderIntersection, intersectPlane0D, rayIntersectInternal1D,
+// Triangle::rayIntersect, coordinateSystem(Coherent), solveQuadraticDouble (oracle/ref_harness.cpp ->
+// oracle/_ref/libgvpm_ref.so).  Those parts of this file are pinned BIT-EXACTLY against that code and against
+// golden vectors generated from it (tests/test_oracle_ref_pin.py, tests/golden/ref_pins.npz): everything that
+// decides a neighbour index set.  The shift functors (gvpm/shift/*.cpp: contributions, Jacobians, MIS
+// weights) need libmitsuba-render / libbidir objects and stay restated-only - PARITY UNPINNED for the
+// radiance values, checked by self-consistency (tests/test_oracle*.py).
 //
 // Template parameter Real = float restates the SINGLE_PRECISION build
 // (build/config-linux-gcc.py:7); Real = double is the error-budget variant.  Compile with
@@ -606,8 +613,8 @@ template <typename Real> struct Scene {
 
   // cylinderIntersection, photonmapper/beams_3d_intersections.h:77-140.  The cylinder is the segment
   // (co, cd, [0, cMaxt]) with radius `radius`; the "view" ray is (vo, vd, maxt = vMaxt).  The world ->
-  // cylinder-frame transform is restated as Frame(cd).toLocal(p - co) (the reference composes 4x4
-  // matrices, Transform::translate * Transform::fromFrame, and applies the stored inverse).
+  // cylinder-frame transform follows the reference's 4x4 arithmetic (Transform::translate * Transform::fromFrame,
+  // stored inverse applied to the view ray) so that tNear / tFar are bit-identical (tests/test_oracle_ref_pin.py).
   static bool cylinderIntersection(const V3<Real> &co, const V3<Real> &cd, Real cMaxt, const V3<Real> &vo,
                                    const V3<Real> &vd, Real vMaxt, Real radius, double &tNear, double &tFar) {
     const V3<Real> d1d2c = cross(vd, cd);
@@ -616,8 +623,11 @@ template <typename Real> struct Scene {
     if (ad * ad >= (radius * radius) * sinThetaSqr) return false;
     V3<Real> s, t;
     coordinateSystem(cd, s, t);
-    const V3<Real> rel = vo - co;
-    const V3<Real> lo(dot(rel, s), dot(rel, t), dot(rel, cd)), ld(dot(vd, s), dot(vd, t), dot(vd, cd));
+    // worldToObject = (translate(co) * fromFrame(Frame(cd))).inverse(): the 4x4 product (matrix.h:744-756,
+    // transform.cpp:28-45,216-227) keeps the rotation rows and puts -dot(axis, co) in the last column, and
+    // Transform::operator()(Point) (transform.h:108-125) adds that column last
+    const V3<Real> lo(dot(vo, s) - dot(co, s), dot(vo, t) - dot(co, t), dot(vo, cd) - dot(co, cd)),
+        ld(dot(vd, s), dot(vd, t), dot(vd, cd));
     const Real lMax = cMaxt;
     const double ox = lo.x, oy = lo.y, dx = ld.x, dy = ld.y;
     const double A = dx * dx + dy * dy;

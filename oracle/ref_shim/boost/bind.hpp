@@ -1,0 +1,5 @@
+// Shim: boost::bind -> std::bind (+ the global _1.. placeholders Boost.Bind exports).
+#pragma once
+#include <functional>
+namespace boost { using std::bind; using std::ref; using std::cref; }
+using namespace std::placeholders;
