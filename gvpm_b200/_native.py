@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("use_mis", C.c_int32), ("use_shift_null", C.c_int32), ("path_set", C.c_int32),
                 ("power_heuristic", C.c_int32), ("kernel_3d", C.c_int32), ("film_w", C.c_int32),
                 ("film_h", C.c_int32), ("shadow_maxt_scale", C.c_float), ("epsilon", C.c_float),
-                ("long_beams", C.c_int32), ("rng_seed", C.c_uint32), ("reserved", C.c_int32 * 2)]
+                ("long_beams", C.c_int32), ("rng_seed", C.c_uint32), ("beam_kernel_1d", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class PhotonSoA(C.Structure):

@@ -1,5 +1,8 @@
-// beam_device.cuh — device functions of the G-Beams 3D gather ("beam3d" = EBeamBeam3D_Optimized).
+// beam_device.cuh — device functions of the G-Beams gather: "beam3d" (EBeamBeam3D_Optimized) and "beam1d"
+// (EBeamBeam1D with newShiftBeam, gvpm.cpp:96-98).
 // Reference lines restated here:
+//   PhotonBeam::rayIntersectInternal1D, getContrib          photonmapper/beams_struct.h:136-185,250-311
+//   shift(), localMatrix(), getShiftPos1D                   gvpm/shift/shift_volume_beams.cpp:36-96
 //   BeamKernelRecord::eval / null-shift ctor / kernelPDF   gvpm/shift/shift_volume_beams.h:39-143,195-283,298-336
 //   cylinderIntersection                                    photonmapper/beams_3d_intersections.h:77-140
 //   solveQuadraticDouble, coordinateSystem                  src/libcore/util.cpp:487-525,600-609
@@ -133,7 +136,7 @@ __device__ __forceinline__ float beam_uniform(const GatherParams &P, const BaseR
 }
 
 struct BeamKernelRec {
-  sf v, w, pdfKernel, pdfEdgeFailure, weightKernel;
+  sf v, w, pdfKernel, pdfEdgeFailure, weightKernel, u;
   v3 contrib;
   bool valid;
   __device__ sf pdf() const { return pdfEdgeFailure * pdfKernel; }
@@ -166,7 +169,7 @@ __device__ __forceinline__ BeamKernelRec beam_kernel_eval(const GatherParams &P,
   BeamKernelRec k;
   k.valid = false;
   k.contrib = v3(0.f, 0.f, 0.f);
-  k.v = k.w = k.pdfKernel = k.pdfEdgeFailure = k.weightKernel = sf(0.f);
+  k.v = k.w = k.pdfKernel = k.pdfEdgeFailure = k.weightKernel = k.u = sf(0.f);
   const sf r(P.radius);
   const v3 camStart = R.o + R.mint * R.d;
   double tFarBeam;
@@ -197,6 +200,81 @@ __device__ __forceinline__ BeamKernelRec beam_kernel_eval(const GatherParams &P,
   return k;
 }
 
+// PhotonBeam::rayIntersectInternal1D: closest approach of the camera line and the beam line, strictly rounded fp32
+// in the reference's operation order (this decides the (ray, beam) index set of the 1-D kernel)
+__device__ __forceinline__ bool beam_intersect_1d(v3 p1, v3 bdir, sf blen, sf radius, v3 ro, v3 rd, sf rmint, sf rmaxt,
+                                                  sf tminBeam, sf tmaxBeam, sf &u, sf &v, sf &w, sf &sinTheta) {
+  const v3 d1d2c = cross(rd, bdir);
+  const sf sinThetaSqr = dot(d1d2c, d1d2c);
+  const sf ad = dot(p1 - ro, d1d2c);
+  if ((ad * ad).v >= ((radius * radius) * sinThetaSqr).v) return false;
+  const sf d1d2 = dot(rd, bdir);
+  const sf d1d2Sqr = d1d2 * d1d2;
+  const sf d1d2SqrMinus1 = d1d2Sqr - sf(1.0f);
+  if (d1d2SqrMinus1.v < 1e-5f && d1d2SqrMinus1.v > -1e-5f) return false;
+  const sf d1O1 = dot(rd, ro);
+  const sf d1O2 = dot(rd, p1);
+  w = (d1O1 - d1O2 - d1d2 * (dot(bdir, ro) - dot(bdir, p1))) / d1d2SqrMinus1;
+  if (w.v <= rmint.v || w.v >= rmaxt.v) return false;
+  v = (w + d1O1 - d1O2) / d1d2;
+  if (v.v <= 0.f || v.v >= blen.v || isnan(v.v)) return false;
+  if (tminBeam.v >= v.v || tmaxBeam.v < v.v) return false;
+  const sf sinThetaConst = ssqrt(sinThetaSqr);
+  u = sf(fabsf(ad.v)) / sinThetaConst;
+  sinTheta = sinThetaConst;
+  return true;
+}
+
+// BeamKernelRecord::eval, EBeamBeam1D branch + PhotonBeam::getContrib, for the whole beam (tmin = 0, tmax = length)
+__device__ __forceinline__ BeamKernelRec beam_kernel_eval_1d(const GatherParams &P, const BeamRec &beam,
+                                                             const BaseRay &R) {
+  BeamKernelRec k;
+  k.valid = false;
+  k.contrib = v3(0.f, 0.f, 0.f);
+  k.v = k.w = k.pdfKernel = k.pdfEdgeFailure = k.weightKernel = k.u = sf(0.f);
+  if (!beam_intersect_1d(beam.o, beam.dir, beam.length, sf(P.radius), R.o, R.d, R.mint, R.maxt, sf(0.f), beam.length,
+                         k.u, k.v, k.w, k.pdfKernel))
+    return k;
+  const MediumRec mRecCamera = medium_eval(P, sf(0.f), k.w), mRec = medium_eval(P, sf(0.f), k.v);
+  k.weightKernel = sf(P.weight_kernel);
+  const sf phaseTerm = phase_eval(P, -beam.dir, -R.d);
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+  v3 beamContrib = (((mRec.T * mRecCamera.T) * sigS) * beam.flux) * phaseTerm;
+  if (!P.cfg.long_beams) {
+    k.pdfEdgeFailure = mRec.pdfFailure;
+    if (mRec.pdfFailure.v == 0.f && mRec.T.v != 0.f) return k;
+    beamContrib = beamContrib / mRec.pdfFailure;
+  } else {
+    k.pdfEdgeFailure = sf(1.f);
+  }
+  k.contrib = beamContrib;
+  if (!is_zero(k.contrib)) k.contrib = k.contrib / k.pdfKernel;
+  k.valid = !is_zero(k.contrib);
+  return k;
+}
+
+// shift() + localMatrix(): the point at distance u from the camera ray (at camera distance w) in the plane through
+// the beam origin a.  Radiance-only arithmetic (asinf / cosf / sinf within a few ulp of libm).
+__device__ __forceinline__ v3 beam_shift_1d(v3 ro, v3 rd, v3 a, sf u, sf w, bool flip) {
+  const sf d = dot(a - ro, rd);
+  const v3 tD = ro + d * rd;
+  const v3 s = normalize(a - tD);
+  const v3 t = cross(rd, s);
+  const sf localAy = dot(a - tD, s);
+  const float q = fminf(1.f, fmaxf(-1.f, (u / sf(fabsf(localAy.v))).v));
+  float phi = (float)(1.57079632679489661923 - (double)asinf(q));
+  if (flip) phi = -phi;
+  const sf ly = u * sf(cosf(phi)), lz = u * sf(sinf(phi));
+  const v3 worldU = (rd * sf(0.f) + s * ly) + t * lz;
+  return (ro + w * rd) + worldU;
+}
+// BeamGradRadianceQuery::getShiftPos1D
+__device__ __forceinline__ v3 beam_shift_pos_1d(const BaseRay &R, v3 ok, v3 dk, v3 a, v3 bBeamDir, sf w, sf u) {
+  const v3 back = normalize(beam_shift_1d(R.o, R.d, a, u, w, false) - a);
+  const bool flipAngle = length_sq(back - bBeamDir).v > 0.001f;
+  return beam_shift_1d(ok, dk, a, u, w, flipAngle);
+}
+
 // BeamKernelRecord(ori, medium, beam, cameraRay): the null-shift re-evaluation on the offset ray
 __device__ __forceinline__ BeamKernelRec beam_kernel_null(const GatherParams &P, const BeamKernelRec &ori,
                                                           const BeamRec &beam, v3 camO, v3 camD, sf camMint,
@@ -204,7 +282,7 @@ __device__ __forceinline__ BeamKernelRec beam_kernel_null(const GatherParams &P,
   BeamKernelRec k;
   k.valid = false;
   k.contrib = v3(0.f, 0.f, 0.f);
-  k.v = k.w = k.pdfKernel = k.pdfEdgeFailure = k.weightKernel = sf(0.f);
+  k.v = k.w = k.pdfKernel = k.pdfEdgeFailure = k.weightKernel = k.u = sf(0.f);
   const sf r(P.radius);
   const v3 camStart = camO + camMint * camD;
   double tNearBeam, tFarBeam;
@@ -223,6 +301,7 @@ __device__ __forceinline__ BeamKernelRec beam_kernel_null(const GatherParams &P,
 // BeamKernelRecord::kernelPDF (3-D optimized): infinite beam from orgBeam along dBeam
 __device__ __forceinline__ sf beam_kernel_pdf(const GatherParams &P, v3 camO, v3 camD, sf camMaxt, v3 orgBeam,
                                               v3 dBeam, sf newDLength) {
+  if (P.cfg.beam_kernel_1d) return ssqrt(length_sq(cross(camD, dBeam)));
   const sf r(P.radius);
   double tNearBeam, tFarBeam;
   if (!cylinder_intersection(camO, camD, camMaxt, orgBeam, dBeam, INFINITY, r, tNearBeam, tFarBeam)) return sf(0.f);
@@ -358,7 +437,7 @@ __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4
       const v3 ok(s0.x, s0.y, s0.z), dk(s1.x, s1.y, s1.z), eyeK(s2.x, s2.y, s2.z);
       const sf lenK(s0.w), sensor(s1.w), shiftW = kRec.w;
       bool alreadyShift = false;
-      if (P.cfg.use_shift_null) {
+      if (P.cfg.use_shift_null && !P.cfg.beam_kernel_1d) {   // "Ignored in case of Beam 1D kernel", :264-265
         const v3 kernelPos = beam.o + beam.dir * kRec.v;
         const sf ZPtoY = length_sq((ok + shiftW * dk) - kernelPos);
         if (ZPtoY < r * r && kRec.w <= lenK) {
@@ -381,7 +460,10 @@ __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4
           }
         }
       }
-      if (!alreadyShift && kRec.w <= lenK) {
+      if (!alreadyShift && kRec.w <= lenK && P.cfg.beam_kernel_1d) {   // newShiftBeam, :311-317
+        const v3 offsetPos = beam_shift_pos_1d(R, ok, dk, beam.o, beam.dir, kRec.w, kRec.u);
+        shift_beam_diffuse(P, beam, ok, dk, lenK, eyeK, sensor, shiftW, kRec, offsetPos, S, weight);
+      } else if (!alreadyShift && kRec.w <= lenK) {
         const sf dd = dot(beam.o - ok, dk);
         const sf minDistSqr = length_sq(beam.o - (ok + dd * dk));
         if (minDistSqr.v > 0.f) {

@@ -1,4 +1,4 @@
-// gather_beams.cu — G-Beams 3D gather.  Replaces, per iteration,
+// gather_beams.cu — G-Beams gather, beam3d and beam1d kernels.  Replaces, per iteration,
 //   SubBeamBVH construction + buildHierarchy + query   photonmapper/beams_accel.h:90-243
 //   BeamGradRadianceQuery::operator() and its shifts   gvpm/shift/shift_volume_beams.cpp:139-539,748-786
 //   the gather loop of computeVolumeGradientBeams      gvpm/gvpm.cpp:880-986
@@ -273,9 +273,18 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
       const BeamRec beam = load_beam(P, bi);
       double tNear = 0.0;
       const uint32_t origBeam = bi;  // beam records keep the caller's order; only sub-beams are sorted
-      const BeamKernelRec kRec = beam_kernel_eval(P, beam, R, origBeam, tNear);
-      // sub-beam ownership: half-open [t1, t2), first sub-beam also owns tNear < 0, last one the tail
-      const bool owner = ((flags & 1u) || tNear >= (double)sb.x) && ((flags & 2u) || tNear < (double)sb.y);
+      BeamKernelRec kRec;
+      bool owner;
+      if (P.cfg.beam_kernel_1d) {
+        // 1-D kernel: the sub-beam [t1, t2] accepts v in (t1, t2] (beams_struct.h:299-301); first / last sub-beam
+        // take the rest of (0, length)
+        kRec = beam_kernel_eval_1d(P, beam, R);
+        owner = ((flags & 1u) || kRec.v.v > sb.x) && ((flags & 2u) || kRec.v.v <= sb.y);
+      } else {
+        kRec = beam_kernel_eval(P, beam, R, origBeam, tNear);
+        // sub-beam ownership: half-open [t1, t2), first sub-beam also owns tNear < 0, last one the tail
+        owner = ((flags & 1u) || tNear >= (double)sb.x) && ((flags & 2u) || tNear < (double)sb.y);
+      }
       if (kRec.valid && owner) {
         const uint32_t meta = __float_as_uint(__ldg(&P.beams[(size_t)bi * GVPM_BEAM_FLOAT4 + 1].w));
         // depth / interaction-mode / pathSet filters of the beam functor (shift_volume_beams.cpp:143-187;

@@ -1018,7 +1018,6 @@ static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
   if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
   if (!ctx->beams_built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_beams has not been called");
   if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
-  if (!ctx->cfg.kernel_3d) return fail(ctx, GVPM_ERR_UNSUPPORTED, "only the beam3d kernel is implemented");
   memset(&P, 0, sizeof(P));
   P.tree = ctx->beam_tree;
   P.rays = ctx->rays.as<float4>();
@@ -1028,6 +1027,7 @@ static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
   P.radius_sq = r * r;
   P.kernel_vol = (float)((4.0 / 3.0) * (double)GVPM_PI * std::pow((double)r, 3));
   P.weight_kernel = (float)(1.0 / P.kernel_vol);  // shift_volume_beams.h:272
+  if (ctx->cfg.beam_kernel_1d) P.weight_kernel = 0.5f / r;  // :188
   P.bounds = ctx->beam_bounds.as<float>();
   for (int i = 0; i < 3; ++i) {
     P.sigma_s[i] = ctx->medium.sigma_s[i];

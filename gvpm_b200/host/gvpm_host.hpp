@@ -25,7 +25,7 @@
 namespace gvpm_host {
 
 // EVolumeTechnique values the gather supports (src/integrators/volume_utils.h:55-93)
-enum EVolumeTechnique { EVolBRE2D = 0, EVolBRE3D = 1, EVolVPM = 2, EVolBeam3D = 3, EVolPlane0D = 4 };
+enum EVolumeTechnique { EVolBRE2D = 0, EVolBRE3D = 1, EVolVPM = 2, EVolBeam3D = 3, EVolPlane0D = 4, EVolBeam1D = 5 };
 
 // The GPMConfig fields the volume gather path reads (gvpm/gvpm_struct.h:181-333), same names.
 struct GPMConfig {
@@ -128,6 +128,7 @@ class VolumeGatherB200 {
     c.path_set = config.pathSet;
     c.power_heuristic = config.powerHeuristic;
     c.kernel_3d = config.volTechnique != EVolBRE2D;
+    c.beam_kernel_1d = config.volTechnique == EVolBeam1D;  // "beam1d": newShiftBeam is forced on, gvpm.cpp:96-98
     c.film_w = width;
     c.film_h = height;
     c.shadow_maxt_scale = 1e-3f;  // ShadowEpsilon, shift_volume_photon.cpp:396
@@ -155,7 +156,7 @@ class VolumeGatherB200 {
     scaleVolumeAPA(it);
   }
 
-  // gvpm.cpp:880-986 (beam3d).  beamRadius = bsphereR * globalScaleVolume * POURCENTAGE_BS (:881).
+  // gvpm.cpp:880-986 (beam3d / beam1d).  beamRadius = bsphereR * globalScaleVolume * POURCENTAGE_BS (:881).
   void computeVolumeGradientBeams(int it, const gvpm_beam_soa *beams, size_t nBeams, const gvpm_ray_soa *rays,
                                   size_t nRays, size_t nbPathBeams) {
     check(gvpm_upload_beams(m_ctx, beams, nBeams), "gvpm_upload_beams");

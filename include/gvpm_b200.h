@@ -93,7 +93,9 @@ typedef struct gvpm_config {
                                sampler in traversal order (shift_volume_beams.h:224,245), which no parallel
                                gather can reproduce; they are replaced by a counter-based hash of
                                (rng_seed, px, py, edge, beam index, dimension) — DESIGN.md §6 */
-  int32_t reserved[2];
+  int32_t beam_kernel_1d;   /* G-Beams: 0 = "beam3d" (EBeamBeam3D_Optimized), 1 = "beam1d" (EBeamBeam1D, for which
+                               GPMIntegrator forces newShiftBeam = true, gvpm.cpp:96-98) */
+  int32_t reserved[1];
 } gvpm_config;
 
 /* Volume photons, flattened from GPhotonNodeData + its light Path
@@ -254,7 +256,7 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
  * (offsets[n_rays] then holds the needed size). */
 int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
 
-/* ---- G-Beams 3D ("beam3d"): replaces beamMap->build(EBVHAccel) + beamMap->query(radQuery) over all gather
+/* ---- G-Beams ("beam3d", or "beam1d" with gvpm_config.beam_kernel_1d): replaces beamMap->build(EBVHAccel) + beamMap->query(radQuery) over all gather
  *      points, gvpm.cpp:880-986 + beams_accel.h:90-243 + shift_volume_beams.cpp:139-539,748-786 ---------------
  * gvpm_build_beams cuts the beams into sub-beams of averageLength/10 and builds the hierarchy for beam radius
  * `radius` (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:881).  out: [n_rays*27], un-normalised (the caller

@@ -670,11 +670,92 @@ template <typename Real> struct Scene {
 
   // BeamKernelRecord, gvpm/shift/shift_volume_beams.h:24-288
   struct BeamKernelRecord {
-    Real v = 0, w = 0, pdfKernel = 0, pdfEdgeFailure = 0, weightKernel = 0;
+    Real v = 0, w = 0, pdfKernel = 0, pdfEdgeFailure = 0, weightKernel = 0, u = 0;
     V3<Real> beamTrans, contrib;
     bool isValid() const { return !(contrib.x == 0 && contrib.y == 0 && contrib.z == 0); }
     Real pdf() const { return pdfEdgeFailure * pdfKernel; }
   };
+
+  // PhotonBeam::rayIntersectInternal1D, photonmapper/beams_struct.h:250-311 (code "taken from smallUPDT"): closest
+  // approach of the camera line and the beam line.  The intermediates are `float` whatever Float is.
+  static bool beamIntersect1D(const V3<Real> &p1, const V3<Real> &bdir, Real blen, Real radius, const V3<Real> &ro,
+                              const V3<Real> &rd, Real rmint, Real rmaxt, Real tminBeam, Real tmaxBeam, Real &u, Real &v,
+                              Real &w, Real &sinTheta) {
+    const V3<Real> d1d2c = cross(rd, bdir);
+    const float sinThetaSqr = (float)dot(d1d2c, d1d2c);
+    const float ad = (float)dot(p1 - ro, d1d2c);
+    if (ad * ad >= (radius * radius) * sinThetaSqr) return false;
+    const float d1d2 = (float)dot(rd, bdir);
+    const float d1d2Sqr = d1d2 * d1d2;
+    const float d1d2SqrMinus1 = d1d2Sqr - 1.0f;
+    if (d1d2SqrMinus1 < 1e-5f && d1d2SqrMinus1 > -1e-5f) return false;
+    const float d1O1 = (float)dot(rd, ro);
+    const float d1O2 = (float)dot(rd, p1);
+    w = (d1O1 - d1O2 - d1d2 * (dot(bdir, ro) - dot(bdir, p1))) / d1d2SqrMinus1;
+    if (w <= rmint || w >= rmaxt) return false;
+    v = (w + d1O1 - d1O2) / d1d2;
+    if (v <= 0.0 || v >= blen || std::isnan(v)) return false;
+    if (tminBeam >= v || tmaxBeam < v) return false;
+    const float sinThetaConst = std::sqrt(sinThetaSqr);
+    u = std::abs(ad) / sinThetaConst;
+    sinTheta = sinThetaConst;
+    return true;
+  }
+
+  // BeamKernelRecord::eval, EBeamBeam1D branch (shift_volume_beams.h:169-194) + PhotonBeam::getContrib
+  // (beams_struct.h:136-185), for the whole beam (tmin = 0, tmax = length): every sub-beam accepts v in (t1, t2],
+  // so exactly one of them owns the hit.
+  BeamKernelRecord beamKernelEval1D(const Beam &beam, const V3<Real> &camO, const V3<Real> &camD, Real camMint,
+                                    Real camMaxt) const {
+    BeamKernelRecord k;
+    if (!beamIntersect1D(beam.o, beam.dir, beam.length, radius, camO, camD, camMint, camMaxt, (Real)0, beam.length,
+                         k.u, k.v, k.w, k.pdfKernel))
+      return k;
+    typename Medium<Real>::Rec mRecCamera = medium.eval(0, k.w), mRec = medium.eval(0, k.v);
+    k.weightKernel = (Real)0.5f / radius;
+    k.beamTrans = mRec.transmittance;
+    const Real phaseTerm = medium.phase(-beam.dir, -camD);
+    V3<Real> beamContrib = (((mRec.transmittance * mRecCamera.transmittance) * medium.sigmaS) * beam.flux) * phaseTerm;
+    if (!cfg.long_beams) {
+      if (mRec.pdfFailure == 0 && !(mRec.transmittance.x == 0 && mRec.transmittance.y == 0 && mRec.transmittance.z == 0)) {
+        k.pdfEdgeFailure = mRec.pdfFailure;
+        return k;  // contrib stays 0: invalid record
+      }
+      beamContrib = beamContrib / mRec.pdfFailure;
+      k.pdfEdgeFailure = mRec.pdfFailure;
+    } else {
+      k.pdfEdgeFailure = 1;
+    }
+    k.contrib = beamContrib;
+    if (!(k.contrib.x == 0 && k.contrib.y == 0 && k.contrib.z == 0)) k.contrib = k.contrib / k.pdfKernel;
+    return k;
+  }
+
+  // shift() + localMatrix(), shift_volume_beams.cpp:36-80: the point at distance u from the camera ray (at camera
+  // distance w) in the plane through the beam origin `a`; Frame{r.d, s, t} is brace-initialised, so its (s, t, n)
+  // are (r.d, s, t).
+  static V3<Real> beamShift1D(const V3<Real> &ro, const V3<Real> &rd, const V3<Real> &a, Real u, Real w, bool flip) {
+    const Real d0 = dot(a - ro, rd);
+    const V3<Real> s = normalize(a - (ro + d0 * rd));
+    const V3<Real> t = cross(rd, s);
+    const Real d = dot(a - ro, rd);
+    const V3<Real> tD = ro + d * rd;
+    const V3<Real> rel = a - tD;
+    const Real localAy = dot(rel, s);
+    const Real q = u / std::abs(localAy);
+    Real phi = (Real)(1.57079632679489661923 - (double)std::asin(std::min((Real)1, std::max((Real)-1, q))));
+    if (flip) phi = -phi;
+    const Real ly = u * std::cos(phi), lz = u * std::sin(phi);
+    const V3<Real> worldU = (rd * (Real)0 + s * ly) + t * lz;
+    return (ro + w * rd) + worldU;
+  }
+  // BeamGradRadianceQuery::getShiftPos1D, shift_volume_beams.cpp:81-96
+  static V3<Real> beamShiftPos1D(const V3<Real> &bo, const V3<Real> &bd, const V3<Real> &so, const V3<Real> &sd,
+                                 const V3<Real> &a, const V3<Real> &bBeamDir, Real w, Real u) {
+    const V3<Real> baseShiftedBack = normalize(beamShift1D(bo, bd, a, u, w, false) - a);
+    const bool flipAngle = (baseShiftedBack - bBeamDir).lengthSquared() > (Real)0.001;
+    return beamShift1D(so, sd, a, u, w, flipAngle);
+  }
 
   // BeamKernelRecord::eval, EBeamBeam3D_Optimized branch (shift_volume_beams.h:195-283), for the whole
   // beam (tmin = 0, tmax = length): the per-sub-beam ownership rule (:214-220) then reads
@@ -751,6 +832,7 @@ template <typename Real> struct Scene {
   // BeamKernelRecord::kernelPDF, shift_volume_beams.h:298-336 (3-D optimized)
   Real beamKernelPDF(const V3<Real> &camO, const V3<Real> &camD, Real camMaxt, const V3<Real> &orgBeam,
                      const V3<Real> &dBeam, Real newDLength) const {
+    if (cfg.beam_kernel_1d) return std::sqrt(cross(camD, dBeam).lengthSquared());   // :299-300
     const Real r = radius;
     double tNearBeam, tFarBeam;
     if (cylinderIntersection(camO, camD, camMaxt, orgBeam, dBeam, (Real)INFINITY, r, tNearBeam, tFarBeam)) {
@@ -866,7 +948,7 @@ template <typename Real> struct Scene {
     }
   }
 
-  // BeamGradRadianceQuery::operator(), shift_volume_beams.cpp:139-353 (beam3d).
+  // BeamGradRadianceQuery::operator(), shift_volume_beams.cpp:139-353 (beam3d, or beam1d with newShiftBeam).
   // 0 = no valid kernel record, 1 = valid but filtered, 2 = contributes.
   int beamFunctor(const CamRay<Real> &ray, const Beam &beam, uint32_t beamIndex, Accum<Real> &acc) const {
     bool filtered = false;
@@ -877,8 +959,10 @@ template <typename Real> struct Scene {
       if (beam.pathId % 2 != (uint32_t)((ray.px + ray.py) % 2)) filtered = true;
       rrGlobalWeight = 2;
     }
+    const bool k1d = cfg.beam_kernel_1d != 0;
     const Real xi1 = beamUniform(ray, beamIndex, 0), xi2 = beamUniform(ray, beamIndex, 1);
-    const BeamKernelRecord kRec = beamKernelEval(beam, ray.o, ray.d, ray.mint, ray.maxt, xi1, xi2);
+    const BeamKernelRecord kRec = k1d ? beamKernelEval1D(beam, ray.o, ray.d, ray.mint, ray.maxt)
+                                      : beamKernelEval(beam, ray.o, ray.d, ray.mint, ray.maxt, xi1, xi2);
     if (!kRec.isValid()) return 0;
     if (filtered) return 1;
     const Real r = radius;
@@ -889,7 +973,7 @@ template <typename Real> struct Scene {
       if (ray.offValid[k]) {
         const Real shiftDistMAX = ray.offLen[k], shiftW = kRec.w;
         bool alreadyShift = false;
-        if (cfg.use_shift_null) {                                                       // :254-289
+        if (cfg.use_shift_null && !k1d) {                               // :254-289 ("Ignored in case of Beam 1D kernel")
           const V3<Real> kernelPos = beam.o + beam.dir * kRec.v;
           const Real ZPtoY = ((ray.offO[k] + shiftW * ray.offD[k]) - kernelPos).lengthSquared();
           if (ZPtoY < r * r && kRec.w <= shiftDistMAX) {
@@ -913,7 +997,10 @@ template <typename Real> struct Scene {
             }
           }
         }
-        if (!alreadyShift && kRec.w <= shiftDistMAX) {                                  // :293-316
+        if (!alreadyShift && kRec.w <= shiftDistMAX && k1d) {                           // newShiftBeam, :311-317
+          const V3<Real> offsetPos = beamShiftPos1D(ray.o, ray.d, ray.offO[k], ray.offD[k], beam.o, beam.dir, kRec.w, kRec.u);
+          shiftBeamDiffuse(beam, ray, k, shiftW, kRec, offsetPos, res);
+        } else if (!alreadyShift && kRec.w <= shiftDistMAX) {                           // :293-310
           const Real dd = dot(beam.o - ray.offO[k], ray.offD[k]);
           const Real minDistSqr = (beam.o - (ray.offO[k] + dd * ray.offD[k])).lengthSquared();
           if (minDistSqr > 0) {  // kRec.u == 0 for the 3-D kernel

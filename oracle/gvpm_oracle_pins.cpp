@@ -125,6 +125,21 @@ void gvpm_oracle_pin_plane0d(const float *ori, const float *w0, const float *len
   }
 }
 
+void gvpm_oracle_pin_beam1d(const float *origin, const float *end, const float *radius, const float *ro, const float *rd,
+                            const float *rmint, const float *rmaxt, const float *tmin, const float *tmax, size_t m,
+                            uint8_t *hit, float *uvws) {
+  for (size_t i = 0; i < m; ++i) {
+    const V3<float> o(origin + 3 * i), e(end + 3 * i);
+    V3<float> dir = e - o;                 // PhotonBeam::setEndPoint, beams_struct.h:73-81
+    const float len = dir.length();
+    dir = dir / len;
+    float u = 0, v = 0, w = 0, s = 0;
+    hit[i] = Scene<float>::beamIntersect1D(o, dir, len, radius[i], V3<float>(ro + 3 * i), V3<float>(rd + 3 * i), rmint[i],
+                                           rmaxt[i], tmin[i], tmax[i], u, v, w, s) ? 1 : 0;
+    uvws[4 * i] = u; uvws[4 * i + 1] = v; uvws[4 * i + 2] = w; uvws[4 * i + 3] = s;
+  }
+}
+
 // Occluders::anyHit on ONE triangle per query with the interval [mint, maxt]
 void gvpm_oracle_pin_triangle(const float *tri, const float *ro, const float *rd, const float *mint, const float *maxt,
                               size_t m, uint8_t *hit) {

@@ -84,6 +84,11 @@ def run(side, inp):
     hit, o4 = side.plane0d(inp["pl_ori"][pp], inp["pl_w0"][pp], inp["pl_len0"][pp], inp["pl_w1"][pp],
                            inp["pl_len1"][pp], ro, rd, mint, maxt)
     out.update(pl_hit=hit, pl_out_bits=np.where(hit[:, None], o4, 0).astype(np.float32).view(np.uint32))
+    # rayIntersectInternal1D on (ray, sub-beam [tmin, tmax]) pairs: half of them with the whole beam as the range
+    tmin = np.where(np.arange(len(pr)) % 2 == 0, 0, 0.3 * bl).astype(np.float32)
+    tmax = np.where(np.arange(len(pr)) % 2 == 0, bl, 0.7 * bl).astype(np.float32)
+    hit, o4 = side.beam1d(bo, be, np.full(len(pr), inp["radius"] * 3, np.float32), ro, rd, mint, maxt, tmin, tmax)
+    out.update(b1d_hit=hit, b1d_out_bits=np.where(hit[:, None], o4, 0).astype(np.float32).view(np.uint32))
     out["tri_hit"] = side.triangle_any_hit(inp["tri"], ro, rd, mint, maxt)
     for coh in (0, 1):
         b, c = side.coordsys(inp["vecs"], coh)

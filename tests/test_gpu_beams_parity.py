@@ -54,6 +54,24 @@ def test_beams3d_matches_oracle(built, kw):
     assert ref.counts[:, 0].sum() > 3000
 
 
+@pytest.mark.parametrize("kw", [
+    {},
+    {"use_mis": False, "max_depth": 6},
+    {"power_heuristic": True, "path_set": False},
+    {"lighting_mode": 1 << 2, "use_shift_null": False},
+    {"long_beams": True},
+])
+def test_beams1d_matches_oracle(built, kw):
+    """beam1d kernel (EBeamBeam1D, newShiftBeam): line-line closest approach, 1/(2r)/sin(theta), getShiftPos1D."""
+    c = _case(beam_kernel_1d=True, **kw)
+    ref = _check(c, f"beams1d {kw}")
+    assert ref.counts[:, 0].sum() > 3000
+
+
+def test_beams1d_hg_small_radius(built):
+    _check(_case(scale=1.0, n_beams=20000, phase="hg", hg_g=0.5, beam_kernel_1d=True), "beams1d hg")
+
+
 def test_beams3d_hg_small_radius(built):
     _check(_case(scale=1.0, n_beams=20000, phase="hg", hg_g=0.5), "beams hg")
 
@@ -61,3 +79,4 @@ def test_beams3d_hg_small_radius(built):
 def test_beams_single_and_ragged(built):
     for n in (1, 3, 33):
         _check(_case(n_beams=n, scale=8.0), f"beams n={n}")
+        _check(_case(n_beams=n, scale=8.0, beam_kernel_1d=True), f"beams1d n={n}")

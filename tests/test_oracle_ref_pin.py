@@ -42,7 +42,7 @@ def _same(a, b, what):
 def test_golden_is_not_trivial(golden):
     # the vectors exercise every routine: hits and misses on both sides of each predicate
     assert golden["bre_idx"].size > 1000 and golden["range_idx"].size > 30
-    for k in ("cyl_hit", "pl_hit", "tri_hit", "quad_ok"):
+    for k in ("cyl_hit", "pl_hit", "b1d_hit", "tri_hit", "quad_ok"):
         assert 0 < golden[k].sum() < golden[k].size, k
     assert golden["kd_leaf"].sum() > 100 and golden["kd_depth"] > 10
 
@@ -53,6 +53,7 @@ def test_golden_is_not_trivial(golden):
     "range_off", "range_idx",                                                # PointKDTree::executeQuery
     "cyl_hit", "cyl_tnear_bits", "cyl_tfar_bits",                            # cylinderIntersection
     "pl_hit", "pl_out_bits",                                                 # PhotonPlane::intersectPlane0D
+    "b1d_hit", "b1d_out_bits",                                               # PhotonBeam::rayIntersectInternal1D
     "tri_hit",                                                               # Triangle::rayIntersect + interval
     "cs0_b_bits", "cs0_c_bits", "cs1_b_bits", "cs1_c_bits",                  # coordinateSystem / Coherent
     "quad_ok", "quad_x0_bits", "quad_x1_bits"])                              # solveQuadraticDouble
