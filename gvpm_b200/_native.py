@@ -35,7 +35,7 @@ class Config(C.Structure):
                 ("use_mis", C.c_int32), ("use_shift_null", C.c_int32), ("path_set", C.c_int32),
                 ("power_heuristic", C.c_int32), ("kernel_3d", C.c_int32), ("film_w", C.c_int32),
                 ("film_h", C.c_int32), ("shadow_maxt_scale", C.c_float), ("epsilon", C.c_float),
-                ("long_beams", C.c_int32), ("rng_seed", C.c_uint32), ("beam_kernel_1d", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("long_beams", C.c_int32), ("rng_seed", C.c_uint32), ("beam_kernel_1d", C.c_int32), ("sppm_primal", C.c_int32)]
 
 
 class PhotonSoA(C.Structure):
@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points",
-    "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre",
+    "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
@@ -115,6 +115,7 @@ def load_lib():
     lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_commit_rays.argtypes = [vp]
     lib.gvpm_gather_bre.argtypes = [vp, f32p, u32p]
+    lib.gvpm_gather_sppm_bre.argtypes = [vp, f32p, u32p]
     lib.gvpm_gather_bre_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.gvpm_gather_bre_into.argtypes = [vp, vp, vp]
     lib.gvpm_gather_bre_host.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t, f32p]

@@ -98,6 +98,15 @@ class Context:
                                           cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_bre")
         return out.reshape(n, N.GVPM_OUT_FLOATS), (cnt.reshape(n, 2) if counts else None)
 
+    def gather_sppm_bre(self, counts=True):
+        """sppm primal BRE (needs config.sppm_primal): -> (out [n_rays,3] float32, counts [n_rays,2] or None)."""
+        n = self.n_rays
+        out = np.empty(n * 3, dtype=np.float32)
+        cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
+        self._ck(self.lib.gvpm_gather_sppm_bre(self.h, out.ctypes.data_as(N.f32p),
+                                               cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_sppm_bre")
+        return out.reshape(n, 3), (cnt.reshape(n, 2) if counts else None)
+
     def gather_bre_device(self):
         """Launch only; returns device pointers (out, counts) owned by the context."""
         o, c = C.c_void_p(), C.c_void_p()

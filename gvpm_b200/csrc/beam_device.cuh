@@ -119,10 +119,6 @@ __device__ __forceinline__ bool cylinder_intersection(v3 co, v3 cd, sf cMaxt, v3
 // 1.0 / std::max(x, 0.0001) in double
 __device__ __forceinline__ sd inv_max_double(sd x) { return sd(1.0) / sd(fmax(x.v, 0.0001)); }
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
 // the two uniforms per (camera ray, beam) that replace sampler->next1D()
 __device__ __forceinline__ float beam_uniform(const GatherParams &P, const BaseRay &R, uint32_t beamIndex,
                                               uint32_t dim) {

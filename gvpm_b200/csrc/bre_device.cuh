@@ -159,10 +159,56 @@ __device__ __forceinline__ BaseRay load_base_ray(const float4 *rec) {
   return R;
 }
 
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+// sppm's primal BeamRadianceEstimator::query (photonmapper/bre.cpp:167-259): the ray is re-based at ray(mint)
+// (:169), the predicate is diskDistance > 0 && distSqr < r^2 (:204), the 3-D kernel stops early when
+// diskDistance - 2r > maxt (:206), draws its uniform PER PHOTON (:217; here a counter-based hash of the ray and
+// the caller's photon index) and keeps t' in [0, maxt]; the 2-D kernel keeps diskDistance <= maxt (:240).
+// tBase is the distance from the re-based origin, pdfCam returns 1 / invPdfSampling.
+__device__ __forceinline__ float sppm_uniform(const GatherParams &P, const BaseRay &R, uint32_t photonIndex) {
+  uint32_t h = hash32(P.cfg.rng_seed ^ 0x9E3779B9u);
+  h = hash32(h ^ (uint32_t)R.px);
+  h = hash32(h ^ ((uint32_t)R.py * 0x85EBCA6Bu));
+  h = hash32(h ^ ((uint32_t)R.edgeId * 0xC2B2AE35u));
+  h = hash32(h ^ photonIndex);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ bool sppm_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t slot, sf &tBase,
+                                              sf &invPdf) {
+  const v3 ro = R.o + R.mint * R.d;
+  const sf rmaxt = R.maxt - R.mint;
+  const v3 oc = p - ro;
+  const sf dd = dot(oc, R.d);
+  const sf r(P.radius), radSqr = r * r;
+  const sf distSqr = length_sq((ro + dd * R.d) - p);
+  if (!(dd.v > 0.f && distSqr < radSqr)) return false;
+  if (P.cfg.kernel_3d) {
+    if (dd - (r * sf(2.f)) > rmaxt) return false;
+    const sf deltaT = ssqrt(radSqr - distSqr);
+    const sf tminKernel = dd - deltaT;
+    const sf tRand = tminKernel + (sf(2.f) * deltaT) * sf(sppm_uniform(P, R, __ldg(P.orig + slot)));
+    if (tRand.v < 0.f || tRand > rmaxt) return false;
+    tBase = tRand;
+    invPdf = smax(sf(2.0f) * deltaT, sf(0.0001f));
+  } else {
+    if (dd > rmaxt) return false;
+    tBase = dd;
+    invPdf = sf(1.f);
+  }
+  return true;
+}
+
 // Neighbour predicate + kernel-chord sampling of the 3-D kernel (gvpm_accel.h:297-301,
 // shift_volume_photon.cpp:707-724).  False when the photon is outside the geometric neighbour set.
-__device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseRay &R, v3 p, sf &tBase,
-                                              sf &pdfCam) {
+// SPPM (compile-time, so the gvpm kernels carry none of it): sppm's primal query instead, see sppm_distance.
+template <bool SPPM>
+__device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t slot,
+                                              sf &tBase, sf &pdfCam) {
+  if (SPPM) return sppm_distance(P, R, p, slot, tBase, pdfCam);
   v3 oc = p - R.o;
   sf dd = dot(oc, R.d);
   sf distSqr = length_sq((R.o + dd * R.d) - p);
@@ -184,9 +230,12 @@ __device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseR
 }
 
 // depth / interaction-mode / pathSet filters, shift_volume_photon.cpp:670-697
+template <bool SPPM>
 __device__ __forceinline__ bool filters_pass(const GatherParams &P, const BaseRay &R, uint32_t meta) {
   int type = meta & 3, depth = (meta >> 2) & 255, parity = (meta >> 10) & 1;
   int pathLen = depth + R.edgeId;
+  if (SPPM)  // bre.cpp:195-198 with maxDepth = m_maxDepth - beam.depth (sppm.cpp:978); nothing else
+    return !(P.cfg.max_depth != -1 && depth > P.cfg.max_depth - R.edgeId);
   if (P.cfg.max_depth > 0 && pathLen > P.cfg.max_depth) return false;
   if (P.cfg.min_depth != 0 && pathLen < P.cfg.min_depth) return false;
   int m = P.cfg.lighting_mode;
@@ -362,6 +411,7 @@ __device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, cons
 
 // One contributing (ray, photon) pair: VolumeGradientBREQuery::operator() after the filters.
 // rec: the ray's 20 float4 (base + 4 offsets); a: 27 accumulators (registers of the caller).
+template <bool SPPM>
 __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *__restrict__ rec, uint32_t pi,
                                            float *a) {
   const BaseRay R = load_base_ray(rec);
@@ -370,7 +420,16 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
 
   sf tBase, pdfCam;
-  if (!base_distance(P, R, ph.p, tBase, pdfCam)) return;  // cannot happen for an emitted pair
+  if (!base_distance<SPPM>(P, R, ph.p, pi, tBase, pdfCam)) return;  // cannot happen for an emitted pair
+  if (SPPM) {
+    // result += T(0..t') * power * phase(wi, -d) * weight * invPdfSampling (bre.cpp:224-233,244-252), * beam.weight
+    const v3 wi = normalize(ph.parent - ph.p);
+    const MediumRec mB = medium_eval(P, sf(0.f), tBase);
+    const sf weight = sf(1.f) / sf(P.kernel_vol);
+    const v3 c = ((ph.flux * mB.T) * phase_eval(P, wi, -R.d)) * (weight * pdfCam);
+    acc_add(a, 0, c * R.eye);
+    return;
+  }
   const sf rrG = P.cfg.path_set ? sf(2.f) : sf(1.f);
   const v3 wi = normalize(ph.parent - ph.p);
   const MediumRec mBase = medium_eval(P, R.mint, tBase);

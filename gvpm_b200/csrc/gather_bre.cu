@@ -85,9 +85,11 @@ struct LaneRay {
   int px, py, eid;
 };
 
-template <bool DUMP>
+// MODE bit 0: dump the neighbour sets instead of emitting pairs; bit 1: sppm's primal predicate (bre_device.cuh)
+template <int MODE>
 __global__ void __launch_bounds__(kTravWarps * 32, GVPM_TRAV_MIN_BLOCKS)
 k_bre_traverse(const __grid_constant__ GatherParams P) {
+  constexpr bool DUMP = (MODE & 1) != 0, SPPM = (MODE & 2) != 0;
   __shared__ TileShared sh[kTravWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   TileShared &S = sh[w];
@@ -133,14 +135,16 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
       R.o = v3(L.ox, L.oy, L.oz); R.d = v3(L.dx, L.dy, L.dz);
       R.mint = sf(L.mint); R.edgeLen = sf(L.elen); R.xi = sf(L.xi);
       R.px = L.px; R.py = L.py; R.edgeId = L.eid;
+      R.maxt = sf(0.f);
+      if (SPPM && have) R.maxt = sf(__ldg(&P.rays[(size_t)ray * GVPM_RAY_FLOAT4 + 1].w));
       uint32_t keep = 0;
       for (uint32_t k = 0; k < maxq; ++k) {
         if (k < qn) {
           const uint32_t slot = S.queue[k][lane];
           const float4 q0 = ldg4(P.planes + slot);
           sf tB, pc;
-          const bool geom = base_distance(P, R, v3(q0.x, q0.y, q0.z), tB, pc);
-          const bool contrib = geom && filters_pass(P, R, __float_as_uint(q0.w));
+          const bool geom = base_distance<SPPM>(P, R, v3(q0.x, q0.y, q0.z), slot, tB, pc);
+          const bool contrib = geom && filters_pass<SPPM>(P, R, __float_as_uint(q0.w));
           if (DUMP && geom)
             P.nbr_idx[P.nbr_offsets[ray] + nGeom] = __ldg(P.orig + slot) | (contrib ? 0x80000000u : 0u);
           nGeom += geom ? 1u : 0u;
@@ -367,6 +371,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
   }
 }
 
+template <bool SPPM>
 __global__ void __launch_bounds__(GVPM_SHADE_THREADS, GVPM_SHADE_MIN_BLOCKS)
 k_bre_shade(const __grid_constant__ GatherParams P) {
   const int lane = threadIdx.x & 31;
@@ -382,7 +387,7 @@ k_bre_shade(const __grid_constant__ GatherParams P) {
     float a[GVPM_OUT_FLOATS];
 #pragma unroll
     for (int j = 0; j < GVPM_OUT_FLOATS; ++j) a[j] = 0.f;
-    if (valid) bre_photon(P, P.rays + (size_t)pr.x * GVPM_RAY_FLOAT4, pr.y, a);
+    if (valid) bre_photon<SPPM>(P, P.rays + (size_t)pr.x * GVPM_RAY_FLOAT4, pr.y, a);
     // segmented inclusive scan over RUNS of equal ray id (a ray's pairs arrive in contiguous runs,
     // one per flush; the same ray may own several runs, each adds its own partial sum)
     const uint32_t key = pr.x;
@@ -407,14 +412,11 @@ k_bre_shade(const __grid_constant__ GatherParams P) {
 }
 
 // ---- host-side launchers (called from gvpm_capi.cu) -------------------------------------------
-static int g_trav_blocks[2] = {0, 0}, g_shade_blocks = 0;
+static int g_trav_blocks[4] = {0, 0, 0, 0}, g_shade_blocks[2] = {0, 0};
 
-cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream) {
-  if (P.ray_end <= P.ray_begin) return cudaSuccess;
-  int &bps = g_trav_blocks[dump ? 1 : 0];
+template <int MODE> static void launch_traverse_mode(const GatherParams &P, int &bps, int sm_count, cudaStream_t stream) {
   if (bps == 0) {
-    if (dump) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bre_traverse<true>, kTravWarps * 32, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bre_traverse<false>, kTravWarps * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bre_traverse<MODE>, kTravWarps * 32, 0);
     if (bps < 1) bps = 1;
   }
   // persistent grid: a whole number of resident CTAs per SM; warps pull tiles from a counter
@@ -422,21 +424,36 @@ cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, 
   const unsigned tiles = (P.ray_end - P.ray_begin + 31) / 32;
   const unsigned need = (tiles + kTravWarps - 1) / kTravWarps;
   if (grid > need) grid = need;
-  if (dump) k_bre_traverse<true><<<grid, kTravWarps * 32, 0, stream>>>(P);
-  else k_bre_traverse<false><<<grid, kTravWarps * 32, 0, stream>>>(P);
+  k_bre_traverse<MODE><<<grid, kTravWarps * 32, 0, stream>>>(P);
+}
+template <bool SPPM> static void launch_shade_mode(const GatherParams &P, unsigned long long total, int &blocks,
+                                                   int sm_count, cudaStream_t stream) {
+  if (blocks == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_bre_shade<SPPM>, GVPM_SHADE_THREADS, 0);
+    if (blocks < 1) blocks = 1;
+  }
+  unsigned long long need = (total + GVPM_SHADE_THREADS - 1) / GVPM_SHADE_THREADS;
+  unsigned long long grid = (unsigned long long)sm_count * blocks * 4;  // a few waves, grid-stride
+  if (grid > need) grid = need;
+  k_bre_shade<SPPM><<<(unsigned)grid, GVPM_SHADE_THREADS, 0, stream>>>(P);
+}
+
+cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream) {
+  if (P.ray_end <= P.ray_begin) return cudaSuccess;
+  const int mode = (dump ? 1 : 0) | (P.cfg.sppm_primal ? 2 : 0);
+  switch (mode) {
+    case 0: launch_traverse_mode<0>(P, g_trav_blocks[0], sm_count, stream); break;
+    case 1: launch_traverse_mode<1>(P, g_trav_blocks[1], sm_count, stream); break;
+    case 2: launch_traverse_mode<2>(P, g_trav_blocks[2], sm_count, stream); break;
+    default: launch_traverse_mode<3>(P, g_trav_blocks[3], sm_count, stream); break;
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_bre_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream) {
   if (total == 0) return cudaSuccess;
-  if (g_shade_blocks == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_shade_blocks, k_bre_shade, GVPM_SHADE_THREADS, 0);
-    if (g_shade_blocks < 1) g_shade_blocks = 1;
-  }
-  unsigned long long need = (total + GVPM_SHADE_THREADS - 1) / GVPM_SHADE_THREADS;
-  unsigned long long grid = (unsigned long long)sm_count * g_shade_blocks * 4;  // a few waves, grid-stride
-  if (grid > need) grid = need;
-  k_bre_shade<<<(unsigned)grid, GVPM_SHADE_THREADS, 0, stream>>>(P);
+  if (P.cfg.sppm_primal) launch_shade_mode<true>(P, total, g_shade_blocks[1], sm_count, stream);
+  else launch_shade_mode<false>(P, total, g_shade_blocks[0], sm_count, stream);
   return cudaGetLastError();
 }
 

@@ -405,7 +405,7 @@ int gvpm_set_medium(gvpm_ctx *ctx, const gvpm_medium *m) {
 
 int gvpm_set_config(gvpm_ctx *ctx, const gvpm_config *c) {
   if (!ctx || !c) return GVPM_ERR_INVALID;
-  if (c->use_shift_null && !c->kernel_3d)
+  if (c->use_shift_null && !c->kernel_3d && !c->sppm_primal)
     // gvpm_struct.h:305-308: "Not possible to shift null without using 3D kernel"
     return fail(ctx, GVPM_ERR_UNSUPPORTED, "useShiftNull requires the 3D kernel");
   ctx->cfg = *c;
@@ -619,6 +619,26 @@ int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
   const size_t n = ctx->n_rays;
   if (n) {
     CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts)
+      CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+// sppm's primal BRE (bre.cpp:167-259 driven as sppm.cpp:926-981): same traverse + shade kernels with
+// gvpm_config.sppm_primal set; only the primal (first) spectrum of every ray is produced.
+int gvpm_gather_sppm_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  if (!ctx->have_cfg || !ctx->cfg.sppm_primal)
+    return fail(ctx, GVPM_ERR_INVALID, "gvpm_gather_sppm_bre needs gvpm_config.sppm_primal = 1");
+  cudaSetDevice(ctx->device);
+  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  if (rc) return rc;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    CK(cudaMemcpy2DAsync(out, 3 * sizeof(float), ctx->out.p, GVPM_OUT_FLOATS * sizeof(float), 3 * sizeof(float), n,
+                         cudaMemcpyDeviceToHost, ctx->stream));
     if (counts)
       CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }

@@ -175,7 +175,7 @@ def make_medium(sigma_t=2.0, albedo=0.8, phase="isotropic", g=0.0, sampling_weig
 
 def make_config(film_w, film_h, max_depth=12, min_depth=0, lighting_mode=N.ALL2MEDIA, use_mis=True,
                 use_shift_null=True, path_set=True, power_heuristic=False, kernel_3d=True,
-                shadow_maxt_scale=1e-3, epsilon=1e-4, long_beams=False, rng_seed=0, beam_kernel_1d=False):
+                shadow_maxt_scale=1e-3, epsilon=1e-4, long_beams=False, rng_seed=0, beam_kernel_1d=False, sppm_primal=False):
     """Defaults = the paper presets (scripts/scene/generatorGVPM.py:44-50: useMIS=area, mixed shift,
     maxDepth 12) with pathSet at its plugin default (gvpm_struct.h:328)."""
     c = N.Config()
@@ -186,6 +186,7 @@ def make_config(film_w, film_h, max_depth=12, min_depth=0, lighting_mode=N.ALL2M
     c.shadow_maxt_scale, c.epsilon = shadow_maxt_scale, epsilon
     c.long_beams, c.rng_seed = int(long_beams), int(rng_seed) & 0xFFFFFFFF
     c.beam_kernel_1d = int(beam_kernel_1d)
+    c.sppm_primal = int(sppm_primal)
     return c
 
 

@@ -95,7 +95,8 @@ typedef struct gvpm_config {
                                (rng_seed, px, py, edge, beam index, dimension) — DESIGN.md §6 */
   int32_t beam_kernel_1d;   /* G-Beams: 0 = "beam3d" (EBeamBeam3D_Optimized), 1 = "beam1d" (EBeamBeam1D, for which
                                GPMIntegrator forces newShiftBeam = true, gvpm.cpp:96-98) */
-  int32_t reserved[1];
+  int32_t sppm_primal;      /* 1: the point gather runs sppm's primal BeamRadianceEstimator::query
+                               (photonmapper/bre.cpp:167-259) instead of gvpm's gradient functor: see gvpm_gather_sppm_bre */
 } gvpm_config;
 
 /* Volume photons, flattened from GPhotonNodeData + its light Path
@@ -249,6 +250,19 @@ int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
  * and the SMs are busy at once.  r and out should be page-locked (cudaHostAlloc / cudaHostRegister) for the copies
  * to overlap; pageable memory works but serialises.  out: [n*27] host floats, un-normalised. */
 int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *out);
+
+/* ---- sppm primal BRE: replaces `new BeamRadianceEstimator(photonMap, 120, breInitSize, true)` + bre->query(ray, medium,
+ *      maxDepth - beam.depth, use3DKernel, sampler) * beam.weight over all gather-point beams, sppm.cpp:926-981 +
+ *      bre.cpp:29-55,167-259.  Requires gvpm_config.sppm_primal = 1 (checked).  Inputs are the same containers:
+ *      photons: pos, flux = photon.getPower(), parent_pos = pos - photon.getDirection() (so that wi = -direction),
+ *      depth = photon.getDepth(); the other arrays are not read.  rays: o = beam.p1, d, mint = Epsilon, maxt =
+ *      distTotal - Epsilon, eye_contrib = beam.weight, edge_id = beam.depth (maxDepth - beam.depth is formed from
+ *      gvpm_config.max_depth; -1 = unbounded); offsets are ignored.  The 3-D kernel's per-PHOTON sampler->next1D()
+ *      (bre.cpp:217) is replaced by the counter-based hash of (rng_seed, px, py, edge, photon index).
+ *      out: [n_rays*3] = sum of the query results * beam.weight WITHOUT m_scaleFactor (the caller multiplies by
+ *      1 / shotParticles, sppm.cpp:922).  counts (may be NULL): [n_rays*2] = {photons passing the geometric tests,
+ *      same after the depth filter}. */
+int gvpm_gather_sppm_bre(gvpm_ctx *ctx, float *out, uint32_t *counts);
 
 /* Parity aid: neighbour index sets in CSR form.  offsets: [n_rays+1]; idx: capacity `cap`
  * entries, original photon index with bit 31 set when the photon also passes the depth /

@@ -56,6 +56,10 @@ def load():
                                        N.u32p, N.u64p, N.u32p, C.c_size_t, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]
     lib.gvpm_oracle_planes.restype = C.c_longlong
+    lib.gvpm_oracle_sppm_bre.argtypes = [vp, C.POINTER(N.PhotonSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                         C.POINTER(N.Medium), C.POINTER(N.Config), C.c_float, C.c_int, N.f32p, N.u32p,
+                                         N.u64p, N.u32p, C.c_size_t, C.POINTER(C.c_double)]
+    lib.gvpm_oracle_sppm_bre.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -184,6 +188,39 @@ def bre_gather(photons, rays, medium, config, tri, radius, mode="kdtree", double
             lib.gvpm_oracle_tree_free(tree)
     return BreResult(out.reshape(m, N.GVPM_OUT_FLOATS), counts.reshape(m, 2), offsets,
                      idx[:cap] if neighbours else None, ms.value, build_ms)
+
+
+def sppm_bre_gather(photons, rays, medium, config, radius, mode="kdtree", threads=None, neighbours=False):
+    """Restated sppm primal BRE (sppm.cpp:926-981 + bre.cpp:167-259).  Returns a BreResult with out [n_rays,3]."""
+    lib = load()
+    threads = hw_threads() if threads is None else threads
+    cph, cr = photons.as_c(), rays.as_c()
+    tree = lib.gvpm_oracle_tree_build(C.byref(cph), photons.n, radius, 0) if mode == "kdtree" else None
+    out = np.zeros(rays.n * 3, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    ms = C.c_double(0)
+
+    def call(offp, idxp, capv):
+        r = lib.gvpm_oracle_sppm_bre(tree, C.byref(cph), photons.n, C.byref(cr), rays.n, C.byref(medium),
+                                     C.byref(config), radius, threads, out.ctypes.data_as(N.f32p),
+                                     counts.ctypes.data_as(N.u32p), offp, idxp, capv, C.byref(ms))
+        if r < 0:
+            raise RuntimeError(f"gvpm_oracle_sppm_bre failed: {r}")
+        return int(r)
+    offsets = idx = None
+    try:
+        if neighbours:
+            offsets = np.zeros(rays.n + 1, dtype=np.uint64)
+            cap = call(offsets.ctypes.data_as(N.u64p), None, 0)
+            idx = np.zeros(max(cap, 1), dtype=np.uint32)
+            call(offsets.ctypes.data_as(N.u64p), idx.ctypes.data_as(N.u32p), cap)
+            idx = idx[:cap]
+        else:
+            call(None, None, 0)
+    finally:
+        if tree:
+            lib.gvpm_oracle_tree_free(tree)
+    return BreResult(out.reshape(rays.n, 3), counts.reshape(rays.n, 2), offsets, idx, ms.value, 0.0)
 
 
 class VpmResult:

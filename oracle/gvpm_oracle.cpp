@@ -139,6 +139,77 @@ long long gvpm_oracle_bre(void *tree, const gvpm_photon_soa *ph, size_t n, const
 
 }  // extern "C"
 
+// ---- sppm primal BRE (sppm.cpp:926-981 + bre.cpp:167-259) over rays [0, nRays).  tree == NULL: brute force.
+// out: [nRays*3]; counts: [nRays*2] {geometric, contributing}; optional CSR dump like gvpm_oracle_bre.
+extern "C" long long gvpm_oracle_sppm_bre(void *tree, const gvpm_photon_soa *ph, size_t n, const gvpm_ray_soa *rays,
+                                          size_t nRays, const gvpm_medium *med, const gvpm_config *cfg, float radius,
+                                          int threads, float *out, uint32_t *counts, uint64_t *nbr_offsets,
+                                          uint32_t *nbr_idx, size_t cap, double *gather_ms) {
+  TreeHandle *h = (TreeHandle *)tree;
+  if (h && (h->dbl || h->n != n)) return -2;
+  std::vector<std::vector<uint32_t>> nbr;
+  if (nbr_offsets) nbr.resize(nRays);
+  auto t0 = std::chrono::steady_clock::now();
+  Scene<float> sc(*med, *cfg, radius);
+  const size_t tile = 256;
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      size_t b = next.fetch_add(tile);
+      if (b >= nRays) break;
+      size_t e = std::min(nRays, b + tile);
+      for (size_t i = b; i < e; ++i) {
+        CamRay<float> ray = loadRay<float>(*rays, i);
+        V3<float> result;
+        uint32_t nGeom = 0, nContrib = 0;
+        auto visit = [&](uint32_t orig) {
+          Photon<float> p = loadPhoton<float>(*ph, orig);
+          int r = sc.sppmBreFunctor(ray, p, orig, result);
+          if (r >= 1) {
+            ++nGeom;
+            if (r == 2) ++nContrib;
+            if (nbr_offsets) nbr[i].push_back(orig | (r == 2 ? 0x80000000u : 0u));
+          }
+        };
+        if (h) {
+          // const Ray ray(r(r.mint), r.d, 0, r.maxt - r.mint, r.time), bre.cpp:169: same stack DFS as the gvpm query
+          CamRay<float> rb = ray;
+          rb.o = ray.o + ray.mint * ray.d;
+          rb.maxt = ray.maxt - ray.mint;
+          rb.mint = 0;
+          h->tf.query(sc, rb, [&](uint32_t nodeIdx, float) { visit(h->tf.nodes[nodeIdx].orig); });
+        } else {
+          for (size_t j = 0; j < n; ++j) visit((uint32_t)j);
+        }
+        out[3 * i] = result.x; out[3 * i + 1] = result.y; out[3 * i + 2] = result.z;
+        if (counts) { counts[2 * i] = nGeom; counts[2 * i + 1] = nContrib; }
+      }
+    }
+  };
+  if (threads <= 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+  if (gather_ms)
+    *gather_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  long long total = 0;
+  if (nbr_offsets) {
+    for (size_t i = 0; i < nbr.size(); ++i) {
+      nbr_offsets[i] = (uint64_t)total;
+      std::sort(nbr[i].begin(), nbr[i].end(),
+                [](uint32_t a, uint32_t b) { return (a & 0x7fffffffu) < (b & 0x7fffffffu); });
+      for (uint32_t v : nbr[i]) {
+        if ((size_t)total < cap && nbr_idx) nbr_idx[total] = v;
+        ++total;
+      }
+    }
+    nbr_offsets[nbr.size()] = (uint64_t)total;
+  }
+  return total;
+}
+
 // ---- G-VPM: computeVolumeGradientPhoton's per-sample range queries (gvpm.cpp:1141-1185) -------------
 namespace {
 template <typename Real>

@@ -384,6 +384,54 @@ template <typename Real> struct Scene {
     return diskDistance > ray.mint && distSqr < radSqr;
   }
 
+  // ---- sppm primal BRE: BeamRadianceEstimator::query, photonmapper/bre.cpp:167-259, driven as sppm.cpp:960-981 -----
+  // The per-photon sampler->next1D() of the 3-D kernel (:217) is replaced by a counter-based hash of the ray and the
+  // caller's photon index (traversal-order independent); m_scaleFactor is left to the caller.
+  static uint32_t sppmHash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+  }
+  Real sppmUniform(const CamRay<Real> &ray, uint32_t photonIndex) const {
+    uint32_t h = sppmHash32(cfg.rng_seed ^ 0x9E3779B9u);
+    h = sppmHash32(h ^ (uint32_t)ray.px);
+    h = sppmHash32(h ^ ((uint32_t)ray.py * 0x85EBCA6Bu));
+    h = sppmHash32(h ^ ((uint32_t)ray.edgeId * 0xC2B2AE35u));
+    h = sppmHash32(h ^ photonIndex);
+    return (Real)((float)(h >> 8) * (1.0f / 16777216.0f));
+  }
+  // One photon of the query loop (:195-254) on the ray re-based at r(r.mint) (:169).  0 = rejected by the geometric
+  // tests, 1 = passes them but is dropped by the depth filter (:195-198), 2 = contributes (result += ...).
+  int sppmBreFunctor(const CamRay<Real> &ray, const Photon<Real> &ph, uint32_t photonIndex, V3<Real> &result) const {
+    const V3<Real> ro = ray.o + ray.mint * ray.d;
+    const Real rmaxt = ray.maxt - ray.mint;
+    const Real r = radius;
+    const V3<Real> originToCenter = ph.pos - ro;
+    const Real diskDistance = dot(originToCenter, ray.d), radSqr = r * r;
+    const Real distSqr = ((ro + diskDistance * ray.d) - ph.pos).lengthSquared();
+    if (!(diskDistance > 0 && distSqr < radSqr)) return 0;
+    Real tEval, scale;
+    if (cfg.kernel_3d) {
+      if (diskDistance - (r * 2) > rmaxt) return 0;
+      const Real weight = (Real)(1 / ((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3)));
+      const Real deltaT = std::sqrt(radSqr - distSqr);
+      const Real tminKernel = diskDistance - deltaT;
+      const Real diskDistanceRand = tminKernel + 2 * deltaT * sppmUniform(ray, photonIndex);
+      if (diskDistanceRand < 0 || diskDistanceRand > rmaxt) return 0;
+      const Real invPdfSampling = std::max((Real)(2.0f * deltaT), (Real)0.0001f);
+      tEval = diskDistanceRand;
+      scale = weight * invPdfSampling;
+    } else {
+      if (diskDistance > rmaxt) return 0;
+      tEval = diskDistance;
+      scale = (Real)(1 / ((double)Consts<Real>::pi * std::pow((double)r, 2)));
+    }
+    if (cfg.max_depth != -1 && ph.depth > cfg.max_depth - ray.edgeId) return 1;
+    const V3<Real> wi = normalize(ph.parentPos - ph.pos);   // = -photon.getDirection()
+    typename Medium<Real>::Rec mRecBase = medium.eval(0, tEval);
+    result += (((mRecBase.transmittance * ph.flux) * medium.phase(wi, -ray.d)) * scale) * ray.eye;
+    return 2;
+  }
+
   // VolumeGradientBREQuery::operator(), shift_volume_photon.cpp:658-856.
   // Returns 0 = not in the geometric set, 1 = geometric only (filtered), 2 = contributes.
   int breFunctor(const CamRay<Real> &ray, const Photon<Real> &ph, Real diskDistance, Accum<Real> &acc) const {
