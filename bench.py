@@ -8,13 +8,16 @@ Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M phot
 G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
 A step = accel build + gather of every camera-ray medium segment of the image (primal + 4 gradient
 contributions = 27 floats per ray).  N > 1: strong scaling — 32x32 image tiles dealt round-robin to
-the ranks, the iteration's photon set broadcast from rank 0 over NCCL, every rank builds the
-hierarchy and gathers its tiles, results gathered to rank 0 (north_star).  No data-path collective
-other than that broadcast/gather.
+the ranks; the iteration's photon set, of which every rank holds 1/N (what it uploaded over its own
+PCIe link), is all-gathered over NVLink via NCCL into every rank's staging buffer; every rank builds
+the hierarchy and gathers its tiles; results are gathered to rank 0 (north_star).  The photon
+exchange of iteration k+1 is double-buffered behind the build + gather of iteration k (a renderer
+traces the next iteration's photons while the current one is gathered); the K timed steps contain
+K exchanges.  No other data-path collective.
 
-value  = rays / s with the photon SoA and the rays already resident in HBM.
-e2e    = same through the C ABI with HOST (pinned) buffers: H2D of photons and rays, build, gather,
-         D2H of the 27 planes, every step.
+value  = rays / s with the rays and each rank's photon slice already resident in HBM.
+e2e    = same through the C ABI with HOST (pinned) buffers: H2D of the photon slice (gvpm_upload_photons_slice)
+         and of the rays, all-gather, build, gather, D2H of the 27 planes (gvpm_gather_bre_host), every step.
 """
 import argparse
 import ctypes as C
@@ -298,56 +301,146 @@ def main():
         gathered = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     out_host_t, out_host = pinned((n_pad * 27) * (world if rank == 0 else 1), torch.float32)
 
-    ph_ptr, ph_bytes = ctx.photon_staging(n_ph)
-    ph_view = torch.as_tensor(DevView(ph_ptr, ph_bytes), device="cuda")
+    # ---- photon staging: two buffers (double buffering), torch views for NCCL ----------------------------------
+    assert n_ph % world == 0, "the photon set is split evenly over the ranks"
+    n_slice, s_begin = n_ph // world, rank * (n_ph // world)
+    stage_t = []
+    for b in (0, 1):
+        ctx.photon_staging_select(b)
+        ptr, nbytes = ctx.photon_staging(n_ph)
+        stage_t.append(torch.as_tensor(DevView(ptr, nbytes), device="cuda"))
+    f_off, f_elt = ctx.photon_staging_layout(n_ph)
 
-    def exchange_photons():
+    def field_views(b):
+        """per field: (whole array, this rank's slice) as byte views of staging buffer b"""
+        out = []
+        for off, elt in zip(f_off, f_elt):
+            whole = stage_t[b][off:off + n_ph * elt]
+            out.append((whole, whole[s_begin * elt:(s_begin + n_slice) * elt]))
+        return out
+    views = [field_views(0), field_views(1)]
+
+    # untimed set-up: rank 0 uploads the set, broadcast, every rank keeps its slice in pinned host memory (the e2e
+    # leg's source) and both staging buffers hold the rank's slice (the value leg's resident input)
+    ctx.photon_staging_select(0)
+    ctx.photon_staging(n_ph)
+    with torch.cuda.stream(stream):
+        if rank == 0:
+            ctx.upload_photons(inp["photons"])
         if world > 1:
-            dist.broadcast(ph_view, src=0)
+            dist.broadcast(stage_t[0], src=0)
+        stage_t[1].copy_(stage_t[0])
+        ctx.upload_rays(rays)
+    ctx.sync()
+    torch.cuda.synchronize()
+    from gvpm_b200 import records as REC
+    host_fields, keep_host = {}, []
+    for (name, dt, wd), (whole, mine) in zip(REC._PHOTON_FIELDS, views[0]):
+        t = torch.empty(mine.numel(), dtype=torch.uint8, pin_memory=True)
+        t.copy_(mine)
+        keep_host.append(t)
+        host_fields[name] = t.numpy().view(dt)
+    torch.cuda.synchronize()
+    host_slice = REC.PhotonSet(n_slice, **host_fields)
+
+    comm = torch.cuda.Stream(device=local)      # issues the photon all-gathers
+    h2d = torch.cuda.Stream(device=local)       # uploads the next iteration's photon slice (e2e leg)
+    pg_photons = dist.new_group(backend="nccl") if world > 1 else None
+    inplace_ok = True
+    if world > 1:   # NCCL all-gathers in place when the input is the rank's segment of the output; probe torch's checks
+        try:
+            probe = torch.zeros(world * 256, device="cuda", dtype=torch.uint8)
+            dist.all_gather_into_tensor(probe, probe[rank * 256:(rank + 1) * 256], group=pg_photons)
+            torch.cuda.synchronize()
+        except Exception:
+            inplace_ok = False
+    slice_dev = None
+    if world > 1 and not inplace_ok:
+        slice_dev = [mine.clone() for _, mine in views[0]]
+    ready = [None, None]   # per staging buffer: what the compute stream must wait for before building from it
+
+    def prefetch(b, from_host):
+        """start filling staging buffer b with the NEXT iteration's photon set: (H2D of this rank's slice) + all-gather"""
+        ev = torch.cuda.Event()
+        ev.record(stream)                       # buffer b was last read by the build two steps ago (stream order)
+        waits = []
+        if from_host:
+            h2d.wait_event(ev)
+            ctx.photon_staging_select(b)
+            ctx.upload_photons_slice(host_slice, n_ph, s_begin, stream=h2d.cuda_stream)
+            up = torch.cuda.Event()
+            up.record(h2d)
+            waits.append(up)
+            comm.wait_event(up)
+        else:
+            comm.wait_event(ev)
+        if world > 1:
+            with torch.cuda.stream(comm):
+                for i, (whole, mine) in enumerate(views[b]):
+                    src = mine if inplace_ok else slice_dev[i]
+                    if from_host and not inplace_ok:
+                        src.copy_(mine, non_blocking=True)
+                    waits.append(dist.all_gather_into_tensor(whole, src, group=pg_photons, async_op=True))
+        ready[b] = waits
+
+    def wait_ready(b):
+        for w in ready[b] or []:
+            if isinstance(w, torch.cuda.Event):
+                stream.wait_event(w)
+            else:
+                with torch.cuda.stream(stream):
+                    w.wait()
+        ready[b] = None
 
     def collect():
         if world > 1:
             dist.gather(out_dev, gathered, dst=0)
 
-    def step_resident():
-        """inputs resident in HBM: (broadcast) + build + gather (+ result gather)"""
+    def step_resident(k):
+        """value leg: (photon all-gather of step k+1 in flight) + build + gather (+ result gather)"""
+        b = k & 1
+        wait_ready(b)
+        if world > 1:
+            prefetch(1 - b, from_host=False)
+        ctx.photon_staging_select(b)
+        ctx.photon_staging(n_ph)
         with torch.cuda.stream(stream):
-            exchange_photons()
-            ctx.photon_staging(n_ph)
             ctx.build_points(inp["radius"])
             ctx.gather_bre_into(out_dev.data_ptr(), None)
             collect()
 
-    def step_e2e():
-        """host buffers in, host buffers out, through the C ABI: H2D photons (rank 0) + broadcast + build, then the
-        pipelined gvpm_gather_bre_host (ray chunks go up while earlier chunks are gathered and their results come
-        down).  Every rank lands its own tiles in (pinned) host memory of the box, which is where a one-process host
+    def step_e2e(k):
+        """host buffers in, host buffers out, through the C ABI: the photon slice of step k+1 goes up (and is
+        all-gathered) while step k is built from the other staging buffer and gathered by the pipelined
+        gvpm_gather_bre_host (ray chunks go up while earlier chunks are gathered and their results come down).
+        Every rank lands its own tiles in (pinned) host memory of the box, which is where a one-process host
         integrator with one context per GPU reads them; the NCCL gather to rank 0 belongs to the `value` leg."""
+        b = k & 1
+        wait_ready(b)
+        prefetch(1 - b, from_host=True)
+        ctx.photon_staging_select(b)
+        ctx.photon_staging(n_ph)
         with torch.cuda.stream(stream):
-            if rank == 0:
-                ctx.upload_photons(inp["photons"])
-            exchange_photons()
-            ctx.photon_staging(n_ph)
             ctx.build_points(inp["radius"])
             ctx.gather_bre_host(rays, out_host[:n_local * 27])
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def timed(fn, steps, warmup, from_host):
+        if world > 1 or from_host:
+            prefetch(0, from_host)              # step 0's photon set (untimed priming)
+        for k in range(warmup):
+            fn(k)
         ctx.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        builds, gathers = [], []
         l0 = ctx.launch_count()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-        for _ in range(steps):
-            fn()
-        with torch.cuda.stream(stream):
-            e1.record(stream)
+        e0.record(stream)
+        for k in range(warmup, warmup + steps):
+            fn(k)
+        wait_ready((warmup + steps) & 1)        # the K-th exchange issued inside the timed region ends inside it
+        e1.record(stream)
         ctx.sync()
         torch.cuda.synchronize()
         if world > 1:
@@ -359,22 +452,26 @@ def main():
         b, g = ctx.last_timings()
         return float(ms.item()), ctx.launch_count() - l0, b, g
 
-    # residency: upload once (untimed) for the `value` leg
-    with torch.cuda.stream(stream):
-        if rank == 0:
-            ctx.upload_photons(inp["photons"])
-        ctx.upload_rays(rays)
-    ctx.sync()
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches, build_ms, gather_ms = timed(step_resident, args.steps, max(3, args.warmup))
+    W = max(3, args.warmup)
+    ms_total, launches, build_ms, gather_ms = timed(step_resident, args.steps, W, False)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, W, True)
     clocks = sampler.stop() if rank == 0 else None
+    # every exchange must have rebuilt the full photon set in both staging buffers
+    staging_ok = bool(torch.equal(stage_t[0], stage_t[1]))
+    ctx.photon_staging_select(0)
+    ctx.photon_staging(n_ph)
+
+    def step_plain():
+        with torch.cuda.stream(stream):
+            ctx.build_points(inp["radius"])
+            ctx.gather_bre_into(out_dev.data_ptr(), None)
     # gather-kernel duration averaged over a few launches on the launching stream (CUDA events)
     kt, kd = [], []
     for _ in range(3):
-        step_resident()
+        step_plain()
         kt.append(ctx.last_timings())
         kd.append(ctx.last_gather_detail())
     gather_ms = float(np.mean([k[1] for k in kt]))
@@ -390,7 +487,6 @@ def main():
     if world > 1:
         dist.all_reduce(h_geom)
         dist.all_reduce(gk, op=dist.ReduceOp.MAX)
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
 
     if rank == 0:
         R = inp["rays_full_n"]
@@ -402,7 +498,7 @@ def main():
         # R*(320+108) + H*112 over this rank's rays (the N*112 term belongs to the build kernels)
         alg = (R / world) * 428.0 + (H / world) * 112.0
         achieved = alg / (float(gk.item()) * 1e-3) / 1e9
-        h2d = (inp["photons"].nbytes() if inp["photons"] is not None else 0) + rays.nbytes() * world
+        h2d_bytes = (inp["photons"].nbytes() if inp["photons"] is not None else 0) + rays.nbytes() * world
         line = {"metric": "camera-ray gathers/sec (primal+4 gradients)", "value": value, "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -410,7 +506,12 @@ def main():
                 "config": workload_config(args, inp, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(R * 27 * 4)},
+                        "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(R * 27 * 4),
+                        "note": "every rank uploads 1/N of the photon set and its own rays over its own PCIe link; "
+                                "the upload + all-gather of step k+1 overlaps the build + gather of step k"},
+                "photon_exchange": {"collective": "none" if world == 1 else "all_gather (13 field arrays, in place)"
+                                    if inplace_ok else "all_gather (13 field arrays)", "double_buffered": True,
+                                    "staging_buffers_identical_after_run": staging_ok},
                 "gpu_launches": int(launches),
                 # the gather is two launches: k_bre_traverse (dominant) + k_bre_shade; SURVEY §8(d)'s
                 # per-ray figure covers both, so the roofline is quoted over the pair
@@ -432,7 +533,8 @@ def main():
     # tensors allocated on the context's stream must go before the stream does
     # (device tensors and pinned host buffers that were used on it record events on that stream when
     # they are freed)
-    del out_dev, cnt_dev, gathered, ph_view, counts_max, h_geom, gk, out_host_t, out_host, rays
+    del out_dev, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk
+    del out_host_t, out_host, rays
     inp.clear()
     import gc
     gc.collect()

@@ -74,6 +74,7 @@ ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points",
+    "gvpm_photon_staging_select", "gvpm_photon_staging_layout", "gvpm_upload_photons_slice",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
@@ -111,6 +112,9 @@ def load_lib():
     lib.gvpm_upload_photons.argtypes = [vp, C.POINTER(PhotonSoA), C.c_size_t]
     lib.gvpm_photon_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_build_points.argtypes = [vp, C.c_float]
+    lib.gvpm_photon_staging_select.argtypes = [vp, C.c_int]
+    lib.gvpm_photon_staging_layout.argtypes = [C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.gvpm_upload_photons_slice.argtypes = [vp, C.POINTER(PhotonSoA), C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gvpm_upload_rays.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t]
     lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_commit_rays.argtypes = [vp]

@@ -69,6 +69,22 @@ class Context:
         self.n_photons = n
         return dev.value, nbytes.value
 
+    def photon_staging_select(self, which):
+        self._ck(self.lib.gvpm_photon_staging_select(self.h, int(which)), "gvpm_photon_staging_select")
+
+    def photon_staging_layout(self, n):
+        """-> (offsets[13], elem_bytes[13]) of the field arrays inside the staging buffer."""
+        off = (C.c_size_t * 13)()
+        elt = (C.c_size_t * 13)()
+        self._ck(self.lib.gvpm_photon_staging_layout(n, off, elt), "gvpm_photon_staging_layout")
+        return list(off), list(elt)
+
+    def upload_photons_slice(self, photons_slice, n_total, begin, stream=None):
+        """photons_slice: a PhotonSet holding photons [begin, begin + photons_slice.n) of a set of n_total."""
+        cs = photons_slice.as_c()
+        self._ck(self.lib.gvpm_upload_photons_slice(self.h, C.byref(cs), n_total, begin, photons_slice.n, stream),
+                 "gvpm_upload_photons_slice")
+
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 

@@ -85,7 +85,8 @@ struct gvpm_ctx {
   DevBuf tri, tri_plane, tri_aux;
   uint32_t n_tri = 0;
 
-  DevBuf ph_staging;
+  DevBuf ph_staging, ph_staging_alt;  // the selected photon staging buffer and the other one (double buffering)
+  int ph_staging_sel = 0;
   uint32_t n_photons = 0;
   bool photons_loaded = false;
   DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
@@ -360,7 +361,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
   if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->tri_aux, &ctx->ph_staging, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
+  DevBuf *bufs[] = {&ctx->tri, &ctx->tri_plane, &ctx->tri_aux, &ctx->ph_staging, &ctx->ph_staging_alt, &ctx->keys_in, &ctx->keys_out, &ctx->vals_in,
                     &ctx->vals_out, &ctx->sort_temp, &ctx->planes, &ctx->orig, &ctx->box_lo, &ctx->box_hi,
                     &ctx->bounds_partial, &ctx->bounds, &ctx->ray_staging, &ctx->rays, &ctx->out, &ctx->counts,
                     &ctx->nbr_offsets, &ctx->nbr_idx, &ctx->work_counter, &ctx->grad_in, &ctx->grad_out, &ctx->pairs,
@@ -465,6 +466,46 @@ int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   ctx->built = false;
   if (dev) *dev = ctx->ph_staging.p;
   if (bytes) *bytes = L.bytes;
+  return GVPM_OK;
+}
+
+int gvpm_photon_staging_select(gvpm_ctx *ctx, int which) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  if (which != ctx->ph_staging_sel) {
+    std::swap(ctx->ph_staging, ctx->ph_staging_alt);
+    ctx->ph_staging_sel = which;
+    ctx->built = false;
+  }
+  return GVPM_OK;
+}
+
+int gvpm_photon_staging_layout(size_t n, size_t field_offset[13], size_t field_elem_bytes[13]) {
+  PhotonLayout L(n);
+  const size_t elt[13] = {12, 12, 12, 12, 12, 12, 12, 4, 4, 4, 1, 1, 4};
+  for (int i = 0; i < 13; ++i) {
+    if (field_offset) field_offset[i] = L.off[i];
+    if (field_elem_bytes) field_elem_bytes[i] = elt[i];
+  }
+  return GVPM_OK;
+}
+
+int gvpm_upload_photons_slice(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n_total, size_t begin, size_t count,
+                              void *stream) {
+  if (!ctx || (count && !p) || begin + count > n_total) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->n_photons != n_total || !ctx->ph_staging.p || ctx->ph_staging.cap < PhotonLayout(n_total).bytes)
+    return fail(ctx, GVPM_ERR_INVALID, "gvpm_photon_staging(n_total) must be called first for the selected buffer");
+  if (count == 0) return GVPM_OK;
+  PhotonLayout L(n_total);
+  char *b = (char *)ctx->ph_staging.p;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const void *src[13] = {p->pos, p->flux, p->parent_pos, p->pred_pos, p->parent_n, p->prefix_flux, p->parent_albedo,
+                         p->parent_pdf, p->edge_pdf, p->rr_weight, p->parent_type, p->depth, p->path_id};
+  const size_t elt[13] = {12, 12, 12, 12, 12, 12, 12, 4, 4, 4, 1, 1, 4};
+  for (int i = 0; i < 13; ++i) {
+    if (!src[i]) return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_photon_soa");
+    CK(cudaMemcpyAsync(b + L.off[i] + begin * elt[i], src[i], count * elt[i], cudaMemcpyHostToDevice, st));
+  }
   return GVPM_OK;
 }
 

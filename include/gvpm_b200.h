@@ -223,6 +223,18 @@ int gvpm_upload_photons(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n);
  * gvpm_photon_soa).  Rank 0 fills it with gvpm_upload_photons, the host broadcasts `bytes`
  * bytes at `dev` over NCCL, and every rank then calls gvpm_build_points. */
 int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes);
+/* Multi-GPU / pipelined use.  The context owns TWO photon staging buffers; gvpm_photon_staging_select chooses the
+ * one that gvpm_photon_staging, gvpm_upload_photons(_slice) and gvpm_build_points work on, so that the photon set
+ * of iteration k+1 can be uploaded / all-gathered into one buffer while iteration k is built and gathered from the
+ * other.  gvpm_upload_photons_slice copies `count` photons (the host arrays point at the slice's first element)
+ * into elements [begin, begin+count) of the selected buffer, sized for n_total by a previous gvpm_photon_staging
+ * call, asynchronously on `stream` (a cudaStream_t; NULL = the context's stream): every rank uploads 1/G of the set
+ * over its own PCIe link and the ranks all-gather the 13 field arrays in place over NVLink.
+ * gvpm_photon_staging_layout gives each field's byte offset in the staging buffer and its bytes per photon. */
+int gvpm_photon_staging_select(gvpm_ctx *ctx, int which /* 0 or 1 */);
+int gvpm_photon_staging_layout(size_t n, size_t field_offset[13], size_t field_elem_bytes[13]);
+int gvpm_upload_photons_slice(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n_total, size_t begin, size_t count,
+                              void *stream);
 /* Morton sort + implicit 32-ary AABB hierarchy for search radius `radius`
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
