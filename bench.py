@@ -259,6 +259,75 @@ def workload_config(args, inp, world):
             "l2": "inputs larger than L2 (photon records 1.1 GB, rays 0.66 GB): no flush needed"}
 
 
+def diag_phases(v):
+    """GVPM_BENCH_DIAG=1: isolated timings of the pieces of a step (max over ranks, ms), to stderr."""
+    import torch
+    import torch.distributed as dist
+    world, rank, stream, ctx = v["world"], v["rank"], v["stream"], v["ctx"]
+    views, pg, comm = v["views"], v["pg_photons"], v["comm"]
+    res = {}
+
+    def run(name, fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / reps], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[name] = round(float(ms.item()), 3)
+
+    if world > 1:
+        def ag13():
+            ws = [dist.all_gather_into_tensor(w, m, group=pg, async_op=True) for w, m in views[1]]
+            for w in ws:
+                w.wait()
+        run("allgather_13_calls", ag13)
+
+        def agc():
+            with dist._coalescing_manager(group=pg, device=torch.device("cuda", v["local"]), async_ops=True) as cm:
+                for w, m in views[1]:
+                    dist.all_gather_into_tensor(w, m, group=pg)
+            cm.wait()
+        try:
+            run("allgather_coalesced", agc)
+        except Exception as e:  # noqa: BLE001
+            res["allgather_coalesced"] = f"failed: {type(e).__name__}: {e}"[:200]
+        big = v["stage_t"][1]
+        nb = (big.numel() // world // 256) * 256
+        run("allgather_1_call_same_bytes", lambda: dist.all_gather_into_tensor(big[:nb * world], big[rank * nb:(rank + 1) * nb], group=pg))
+        run("result_gather", lambda: dist.gather(v["out_dev"], v["gathered"], dst=0))
+
+    def up():
+        ctx.photon_staging_select(1)
+        ctx.upload_photons_slice(v["host_slice"], v["n_ph"], v["s_begin"], stream=v["h2d"].cuda_stream)
+    run("h2d_photon_slice", up)
+
+    def bld():
+        ctx.photon_staging_select(0)
+        ctx.photon_staging(v["n_ph"])
+        with torch.cuda.stream(stream):
+            ctx.build_points(v["inp"]["radius"])
+    run("build", bld)
+
+    def gh():
+        with torch.cuda.stream(stream):
+            ctx.gather_bre_host(v["rays"], v["out_host"][:v["n_local"] * 27])
+    run("gather_bre_host", gh)
+
+    def gi():
+        with torch.cuda.stream(stream):
+            ctx.gather_bre_into(v["out_dev"].data_ptr(), None)
+    run("gather_bre_into", gi)
+    if rank == 0:
+        print("DIAG " + json.dumps(res), file=sys.stderr, flush=True)
+
+
 # --------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -468,6 +537,8 @@ def main():
         with torch.cuda.stream(stream):
             ctx.build_points(inp["radius"])
             ctx.gather_bre_into(out_dev.data_ptr(), None)
+    if os.environ.get("GVPM_BENCH_DIAG"):
+        diag_phases(locals())
     # gather-kernel duration averaged over a few launches on the launching stream (CUDA events)
     kt, kd = [], []
     for _ in range(3):
