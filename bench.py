@@ -172,6 +172,18 @@ class DevView:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+def measured_traffic(workload, world):
+    """DRAM bytes per launch of the dominant kernels from the committed ncu capture (profiles/traffic.json)."""
+    if world != 1:
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[workload]
+        return float(e["bytes_per_launch"]), e["source"]
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -569,6 +581,7 @@ def main():
         # R*(320+108) + H*112 over this rank's rays (the N*112 term belongs to the build kernels)
         alg = (R / world) * 428.0 + (H / world) * 112.0
         achieved = alg / (float(gk.item()) * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(args.workload if not (args.photons or args.scale) else "", world)
         h2d_bytes = (inp["photons"].nbytes() if inp["photons"] is not None else 0) + rays.nbytes() * world
         line = {"metric": "camera-ray gathers/sec (primal+4 gradients)", "value": value, "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -587,8 +600,8 @@ def main():
                 # the gather is two launches: k_bre_traverse (dominant) + k_bre_shade; SURVEY §8(d)'s
                 # per-ray figure covers both, so the roofline is quoted over the pair
                 "roofline": {"bound": "hbm", "kernel": "k_bre_traverse + k_bre_shade", "achieved": achieved,
-                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": src, "algorithmic_bytes_per_launch": alg,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "traffic_source": traffic_src, "peak_source": src, "algorithmic_bytes_per_launch": alg,
                              "kernel_ms": float(gk.item()), "traverse_ms": trav_ms, "shade_ms": shade_ms,
                              "neighbours_H": H, "contributing_pairs": n_pairs,
                              "note": "instruction-bound tree traversal: DRAM traffic is below the algorithmic "

@@ -177,8 +177,8 @@ __device__ __forceinline__ float sppm_uniform(const GatherParams &P, const BaseR
   h = hash32(h ^ photonIndex);
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
-__device__ __forceinline__ bool sppm_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t slot, sf &tBase,
-                                              sf &invPdf) {
+__device__ __forceinline__ bool sppm_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t photonIndex,
+                                              sf &tBase, sf &invPdf) {
   const v3 ro = R.o + R.mint * R.d;
   const sf rmaxt = R.maxt - R.mint;
   const v3 oc = p - ro;
@@ -190,7 +190,7 @@ __device__ __forceinline__ bool sppm_distance(const GatherParams &P, const BaseR
     if (dd - (r * sf(2.f)) > rmaxt) return false;
     const sf deltaT = ssqrt(radSqr - distSqr);
     const sf tminKernel = dd - deltaT;
-    const sf tRand = tminKernel + (sf(2.f) * deltaT) * sf(sppm_uniform(P, R, __ldg(P.orig + slot)));
+    const sf tRand = tminKernel + (sf(2.f) * deltaT) * sf(sppm_uniform(P, R, photonIndex));
     if (tRand.v < 0.f || tRand > rmaxt) return false;
     tBase = tRand;
     invPdf = smax(sf(2.0f) * deltaT, sf(0.0001f));
@@ -206,9 +206,9 @@ __device__ __forceinline__ bool sppm_distance(const GatherParams &P, const BaseR
 // shift_volume_photon.cpp:707-724).  False when the photon is outside the geometric neighbour set.
 // SPPM (compile-time, so the gvpm kernels carry none of it): sppm's primal query instead, see sppm_distance.
 template <bool SPPM>
-__device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t slot,
+__device__ __forceinline__ bool base_distance(const GatherParams &P, const BaseRay &R, v3 p, uint32_t photonIndex,
                                               sf &tBase, sf &pdfCam) {
-  if (SPPM) return sppm_distance(P, R, p, slot, tBase, pdfCam);
+  if (SPPM) return sppm_distance(P, R, p, photonIndex, tBase, pdfCam);  // photonIndex: the caller's (original) index
   v3 oc = p - R.o;
   sf dd = dot(oc, R.d);
   sf distSqr = length_sq((R.o + dd * R.d) - p);
@@ -257,10 +257,15 @@ struct PhotonRec {
   sf parentPdf, edgePdf, rrW;
   int ptype;
 };
+__device__ __forceinline__ PhotonRec load_photon_orig(const GatherParams &P, uint32_t origIndex);
 __device__ __forceinline__ PhotonRec load_photon(const GatherParams &P, uint32_t pi) {
+  return load_photon_orig(P, __ldg(P.orig + pi));
+}
+// same, by the caller's photon index (the BRE pair list carries it, so the shading kernel can prefetch the record)
+__device__ __forceinline__ PhotonRec load_photon_orig(const GatherParams &P, uint32_t origIndex) {
   // one aligned 128-byte record in the caller's order (tree_build.cu k_pack_aos), reached through the sorted
   // slot's original index: 4 sectors per photon instead of 7 half-used ones from per-field planes
-  const float4 *r = P.aos + (size_t)__ldg(P.orig + pi) * 8;
+  const float4 *r = P.aos + (size_t)origIndex * 8;
   const float4 q0 = ldg4(r), q1 = ldg4(r + 1), q2 = ldg4(r + 2), q3 = ldg4(r + 3), q4 = ldg4(r + 4), q5 = ldg4(r + 5),
                q6 = ldg4(r + 6);
   PhotonRec ph;
@@ -410,12 +415,13 @@ __device__ __forceinline__ void shift_photon_diffuse(const GatherParams &P, cons
 }
 
 // One contributing (ray, photon) pair: VolumeGradientBREQuery::operator() after the filters.
-// rec: the ray's 20 float4 (base + 4 offsets); a: 27 accumulators (registers of the caller).
+// rec: the ray's 20 float4 (base + 4 offsets); pi: the photon's ORIGINAL index; a: 27 accumulators (registers of the
+// caller).
 template <bool SPPM>
 __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *__restrict__ rec, uint32_t pi,
                                            float *a) {
   const BaseRay R = load_base_ray(rec);
-  const PhotonRec ph = load_photon(P, pi);
+  const PhotonRec ph = load_photon_orig(P, pi);
   const sf r(P.radius), rr2 = r * r;
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
 
@@ -486,6 +492,166 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
       default: acc_add(a, 8, wB); acc_add(a, 4, wS); break;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative form of bre_photon<false> (same arithmetic, same accumulation order, bit-identical results).
+// In a warp of 32 pairs roughly half of the (pair, offset) combinations take the cheap null shift and half the
+// expensive diffuse reconnection, so the per-lane offset loop ran the reconnection four times with ~18 of 32 lanes
+// busy.  Here phase A (lane = pair) does the base term, classifies the four offsets, finishes null shifts and
+// invalid offsets on the spot and queues the reconnections as (pair, k) tasks; phase B hands the tasks out 32 at a
+// time, so the reconnection code always runs with full lanes (the pair's context travels through shared memory);
+// phase C (lane = pair) folds the four results in k order.
+#define GVPM_CTX_STRIDE 35
+struct ShadeShared {               // per warp
+  float ctx[32][GVPM_CTX_STRIDE];  // odd stride: lanes reading one field of 32 different pairs hit 32 banks
+  float4 res[32][4];               // (S.xyz, weight) per (pair, k)
+  uint8_t tasks[128];              // (pair << 2) | k
+};
+enum {  // float slots of ctx[pair]
+  CX_P = 0, CX_PARENT = 3, CX_PN = 6, CX_PREFIX = 9, CX_ALBEDO = 12, CX_PARENTPDF = 15, CX_EDGEPDF = 16, CX_RRW = 17,
+  CX_PTYPE = 18, CX_WIW = 19, CX_COSI = 22, CX_NEDGE = 23, CX_NEARMASK = 24, CX_NEARBOUND = 25, CX_ZBASE = 26,
+  CX_TBASE = 29, CX_PDFCAM = 30, CX_TSHIFT = 31, CX_RAY = 32, CX_RD = 33  // CX_RD: 2 floats (d.x, d.y) + sign in ray slot
+};
+
+__device__ __forceinline__ void bre_pairs_warp(const GatherParams &P, uint2 pr, bool valid, float *a, ShadeShared &W,
+                                               int lane) {
+  const sf r(P.radius), rr2 = r * r;
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+  const sf rrG = P.cfg.path_set ? sf(2.f) : sf(1.f);
+  const float4 *rec = P.rays + (size_t)(valid ? pr.x : 0u) * GVPM_RAY_FLOAT4;
+  BaseRay R;
+  v3 baseContrib(0.f, 0.f, 0.f);
+  sf recip(0.f), tBase(0.f), pdfCam(1.f);
+  bool live = valid;
+  uint32_t nTasks = 0;
+  // ---- phase A ------------------------------------------------------------------------------------------------
+  PhotonRec ph;
+  v3 wi(0.f, 0.f, 0.f);
+  sf Tshift(0.f);
+  v3 zBase(0.f, 0.f, 0.f);
+  if (live) {
+    R = load_base_ray(rec);
+    ph = load_photon_orig(P, pr.y);
+    live = base_distance<false>(P, R, ph.p, pr.y, tBase, pdfCam);  // always true for an emitted pair
+  }
+  if (live) {
+    wi = normalize(ph.parent - ph.p);
+    const MediumRec mBase = medium_eval(P, R.mint, tBase);
+    const v3 contrib = (sigS * ph.flux) * phase_eval(P, wi, -R.d);
+    baseContrib = (contrib * mBase.T) * R.eye;
+    const sf norm = sf(P.kernel_vol) * pdfCam;
+    recip = frcp(norm);
+    acc_add(a, 0, (baseContrib * recip) * rrG);
+    Tshift = medium_eval(P, sf(P.cfg.epsilon), tBase).T;
+    zBase = R.o + tBase * R.d;
+    const PairCtx C = make_pair_ctx(P, ph, wi);
+    float *c = W.ctx[lane];
+    c[CX_P] = ph.p.x.v; c[CX_P + 1] = ph.p.y.v; c[CX_P + 2] = ph.p.z.v;
+    c[CX_PARENT] = ph.parent.x.v; c[CX_PARENT + 1] = ph.parent.y.v; c[CX_PARENT + 2] = ph.parent.z.v;
+    c[CX_PN] = ph.pn.x.v; c[CX_PN + 1] = ph.pn.y.v; c[CX_PN + 2] = ph.pn.z.v;
+    c[CX_PREFIX] = ph.prefix.x.v; c[CX_PREFIX + 1] = ph.prefix.y.v; c[CX_PREFIX + 2] = ph.prefix.z.v;
+    c[CX_ALBEDO] = ph.albedo.x.v; c[CX_ALBEDO + 1] = ph.albedo.y.v; c[CX_ALBEDO + 2] = ph.albedo.z.v;
+    c[CX_PARENTPDF] = ph.parentPdf.v; c[CX_EDGEPDF] = ph.edgePdf.v; c[CX_RRW] = ph.rrW.v;
+    c[CX_PTYPE] = __int_as_float(ph.ptype);
+    c[CX_WIW] = C.wiW.x.v; c[CX_WIW + 1] = C.wiW.y.v; c[CX_WIW + 2] = C.wiW.z.v;
+    c[CX_COSI] = C.cosI.v; c[CX_NEDGE] = C.nEdge.v;
+    c[CX_NEARMASK] = __uint_as_float(C.near.mask); c[CX_NEARBOUND] = C.near.bound;
+    c[CX_ZBASE] = zBase.x.v; c[CX_ZBASE + 1] = zBase.y.v; c[CX_ZBASE + 2] = zBase.z.v;
+    c[CX_TBASE] = tBase.v; c[CX_PDFCAM] = pdfCam.v; c[CX_TSHIFT] = Tshift.v;
+    c[CX_RAY] = __uint_as_float(pr.x);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    bool reconnect = false;
+    if (live) {
+      const float4 s0 = ldg4(rec + 4 * (k + 1)), s1 = ldg4(rec + 4 * (k + 1) + 1), s2 = ldg4(rec + 4 * (k + 1) + 2);
+      sf weight(1.f);
+      v3 S(0.f, 0.f, 0.f);
+      if (__float_as_uint(s2.w) != 0u) {  // validVolumeEdge, shift_cameraPath.h:135-140
+        const v3 ok(s0.x, s0.y, s0.z), dk(s1.x, s1.y, s1.z), eyeK(s2.x, s2.y, s2.z);
+        const sf lenK(s0.w), sensor(s1.w);
+        const v3 zShift = ok + tBase * dk;
+        bool done = false;
+        if (P.cfg.use_shift_null && P.cfg.kernel_3d) {  // :776-802
+          sf ZPtoY = length_sq(zShift - ph.p);
+          if (ZPtoY < rr2 && tBase < lenK) {
+            sf dd = dot(ph.p - ok, dk);
+            sf ds = length_sq((ok + dd * dk) - ph.p);
+            sf pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
+            shift_null(P, ph, wi, dk, eyeK, sensor, Tshift, pdfCam, pdfShift, S, weight);
+            done = true;
+          }
+        }
+        reconnect = !done && lenK >= tBase;  // :809-838
+      }
+      if (!reconnect) W.res[lane][k] = make_float4(S.x.v, S.y.v, S.z.v, weight.v);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, reconnect);
+    if (reconnect) W.tasks[nTasks + __popc(m & ((1u << lane) - 1u))] = (uint8_t)((lane << 2) | k);
+    nTasks += __popc(m);
+  }
+  __syncwarp();
+  // ---- phase B: one reconnection per lane, 32 at a time -------------------------------------------------------------
+  for (uint32_t t0 = 0; t0 < nTasks; t0 += 32) {
+    if (t0 + lane < nTasks) {
+      const uint32_t task = W.tasks[t0 + lane];
+      const int owner = task >> 2, k = task & 3;
+      const float *c = W.ctx[owner];
+      PhotonRec q;
+      q.p = v3(c[CX_P], c[CX_P + 1], c[CX_P + 2]);
+      q.parent = v3(c[CX_PARENT], c[CX_PARENT + 1], c[CX_PARENT + 2]);
+      q.pn = v3(c[CX_PN], c[CX_PN + 1], c[CX_PN + 2]);
+      q.prefix = v3(c[CX_PREFIX], c[CX_PREFIX + 1], c[CX_PREFIX + 2]);
+      q.albedo = v3(c[CX_ALBEDO], c[CX_ALBEDO + 1], c[CX_ALBEDO + 2]);
+      q.parentPdf = sf(c[CX_PARENTPDF]); q.edgePdf = sf(c[CX_EDGEPDF]); q.rrW = sf(c[CX_RRW]);
+      q.ptype = __float_as_int(c[CX_PTYPE]);
+      q.flux = v3(0.f, 0.f, 0.f); q.pred = v3(0.f, 0.f, 0.f);  // not read by the reconnection
+      PairCtx C;
+      C.wiW = v3(c[CX_WIW], c[CX_WIW + 1], c[CX_WIW + 2]);
+      C.cosI = sf(c[CX_COSI]); C.nEdge = sf(c[CX_NEDGE]);
+      C.near.mask = __float_as_uint(c[CX_NEARMASK]); C.near.bound = c[CX_NEARBOUND];
+      const v3 zB(c[CX_ZBASE], c[CX_ZBASE + 1], c[CX_ZBASE + 2]);
+      const sf tB(c[CX_TBASE]), pC(c[CX_PDFCAM]), Ts(c[CX_TSHIFT]);
+      const float4 *orec = P.rays + (size_t)__float_as_uint(c[CX_RAY]) * GVPM_RAY_FLOAT4;
+      const float4 s0 = ldg4(orec + 4 * (k + 1)), s1 = ldg4(orec + 4 * (k + 1) + 1), s2 = ldg4(orec + 4 * (k + 1) + 2);
+      const v3 ok(s0.x, s0.y, s0.z), dk(s1.x, s1.y, s1.z), eyeK(s2.x, s2.y, s2.z);
+      const sf sensor(s1.w);
+      const v3 zShift = ok + tB * dk;
+      v3 dBase(0.f, 0.f, 0.f);
+      if (!P.cfg.kernel_3d) {  // the 2-D kernel's coherent frames need the base direction
+        const float4 b1 = ldg4(orec + 1);
+        dBase = v3(b1.x, b1.y, b1.z);
+      }
+      const v3 offsetPos = get_shift_pos(P, rr2, q.p, zB, zShift, dBase, dk, !P.cfg.kernel_3d);
+      sf pdfShift(1.f);
+      if (P.cfg.kernel_3d) {
+        sf dd = dot(offsetPos - ok, dk);
+        sf ds = length_sq((ok + dd * dk) - offsetPos);
+        pdfShift = chord_pdf(safe_sqrt(rr2 - ds));
+      }
+      sf weight(1.f);
+      v3 S(0.f, 0.f, 0.f);
+      shift_photon_diffuse(P, q, C, offsetPos, dk, eyeK, sensor, Ts, pC, pdfShift, S, weight);
+      W.res[owner][k] = make_float4(S.x.v, S.y.v, S.z.v, weight.v);
+    }
+  }
+  __syncwarp();
+  // ---- phase C: fold the four offsets in k order ------------------------------------------------------------------------
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 rs = W.res[lane][k];
+      sf weight(rs.w);
+      const v3 S(rs.x, rs.y, rs.z);
+      if ((k == 1 && R.px == P.cfg.film_w - 1) || (k == 2 && R.py == P.cfg.film_h - 1)) weight = sf(1.f);
+      const sf rw = rrG * weight;
+      const v3 wB = (baseContrib * rw) * recip, wS = (S * rw) * recip;
+      acc_add(a, 5 + k, wB);
+      acc_add(a, 1 + k, wS);
+    }
+  }
+  __syncwarp();
 }
 
 }  // namespace gvpm

@@ -143,7 +143,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
           const uint32_t slot = S.queue[k][lane];
           const float4 q0 = ldg4(P.planes + slot);
           sf tB, pc;
-          const bool geom = base_distance<SPPM>(P, R, v3(q0.x, q0.y, q0.z), slot, tB, pc);
+          const bool geom = base_distance<SPPM>(P, R, v3(q0.x, q0.y, q0.z), SPPM ? __ldg(P.orig + slot) : 0u, tB, pc);
           const bool contrib = geom && filters_pass<SPPM>(P, R, __float_as_uint(q0.w));
           if (DUMP && geom)
             P.nbr_idx[P.nbr_offsets[ray] + nGeom] = __ldg(P.orig + slot) | (contrib ? 0x80000000u : 0u);
@@ -166,7 +166,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
           if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)total);
           base = __shfl_sync(0xffffffffu, base, 0) + (incl - keep);
           for (uint32_t k = 0; k < keep; ++k)
-            if (base + k < P.pair_cap) P.pairs[base + k] = make_uint2(ray, S.queue[k][lane]);
+            if (base + k < P.pair_cap) P.pairs[base + k] = make_uint2(ray, __ldg(P.orig + S.queue[k][lane]));
         }
       }
       __syncwarp();
@@ -374,20 +374,37 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
 template <bool SPPM>
 __global__ void __launch_bounds__(GVPM_SHADE_THREADS, GVPM_SHADE_MIN_BLOCKS)
 k_bre_shade(const __grid_constant__ GatherParams P) {
+  __shared__ ShadeShared shade_sh[SPPM ? 1 : GVPM_SHADE_THREADS / 32];
   const int lane = threadIdx.x & 31;
   unsigned long long total = *P.pair_counter;
   if (total > P.pair_cap) total = P.pair_cap;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total;
-       i0 += stride) {
+  // software pipeline over the grid-stride loop: the pair of the NEXT iteration is already in registers, so its
+  // 128-byte photon record (a random HBM line) is prefetched while the current pair is shaded, and the pair of the
+  // iteration after that is requested
+  const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  const uint2 none = make_uint2(0xffffffffu, 0u);
+  uint2 cur = none, nxt = none;
+  if (first + lane < total) cur = P.pairs[first + lane];
+  if (first + stride + lane < total) nxt = P.pairs[first + stride + lane];
+  for (unsigned long long i0 = first; i0 < total; i0 += stride) {
     const unsigned long long i = i0 + lane;
     const bool valid = i < total;
-    uint2 pr = make_uint2(0xffffffffu, 0u);
-    if (valid) pr = P.pairs[i];
+    const uint2 pr = cur;
+    if (nxt.x != 0xffffffffu) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.aos + (size_t)nxt.y * 8));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rays + (size_t)nxt.x * GVPM_RAY_FLOAT4));
+    }
+    cur = nxt;
+    nxt = (i + 2 * stride < total) ? P.pairs[i + 2 * stride] : none;
     float a[GVPM_OUT_FLOATS];
 #pragma unroll
     for (int j = 0; j < GVPM_OUT_FLOATS; ++j) a[j] = 0.f;
-    if (valid) bre_photon<SPPM>(P, P.rays + (size_t)pr.x * GVPM_RAY_FLOAT4, pr.y, a);
+    if (SPPM) {
+      if (valid) bre_photon<SPPM>(P, P.rays + (size_t)pr.x * GVPM_RAY_FLOAT4, pr.y, a);
+    } else {
+      bre_pairs_warp(P, pr, valid, a, shade_sh[threadIdx.x >> 5], lane);
+    }
     // segmented inclusive scan over RUNS of equal ray id (a ray's pairs arrive in contiguous runs,
     // one per flush; the same ray may own several runs, each adds its own partial sum)
     const uint32_t key = pr.x;

@@ -101,20 +101,37 @@ __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float 
 //   A0 pos, meta | A1 flux, parent_pdf | A2 parent_pos, edge_pdf | A3 pred_pos, rr_weight | A4 parent_n
 //   A5 prefix_flux | A6 parent_albedo | A7 unused
 #define GVPM_AOS_FLOAT4 8
-__global__ void k_pack_aos(const PhotonStaging S, uint32_t n, float4 *__restrict__ aos) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const size_t s3 = 3 * (size_t)s;
-  auto ld3 = [&](const float *p, float w) { return make_float4(p[s3], p[s3 + 1], p[s3 + 2], w); };
-  const uint32_t meta = pack_meta(S.parent_type[s], S.depth[s], S.path_id[s]);
-  float4 *r = aos + (size_t)s * GVPM_AOS_FLOAT4;
-  r[0] = ld3(S.pos, __uint_as_float(meta));
-  r[1] = ld3(S.flux, S.parent_pdf[s]);
-  r[2] = ld3(S.parent_pos, S.edge_pdf[s]);
-  r[3] = ld3(S.pred_pos, S.rr_weight[s]);
-  r[4] = ld3(S.parent_n, 0.f);
-  r[5] = ld3(S.prefix_flux, 0.f);
-  r[6] = ld3(S.parent_albedo, 0.f);
+// Each thread assembles its photon's record in registers; the warp then transposes through a padded shared tile so
+// that every store instruction writes 512 contiguous bytes (4 whole records) instead of 32 scattered 16-byte pieces.
+__global__ void __launch_bounds__(256) k_pack_aos(const PhotonStaging S, uint32_t n, float4 *__restrict__ aos) {
+  __shared__ float4 tile[8][32 * 9];   // per warp: 32 records x 8 float4, row stride 9 float4 (conflict-free both ways)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t warpBase = blockIdx.x * blockDim.x + (w << 5);
+  const uint32_t s = warpBase + lane;
+  float4 *t = tile[w];
+  if (s < n) {
+    const size_t s3 = 3 * (size_t)s;
+    auto ld3 = [&](const float *p, float ww) { return make_float4(__ldg(p + s3), __ldg(p + s3 + 1), __ldg(p + s3 + 2), ww); };
+    const uint32_t meta = pack_meta(S.parent_type[s], S.depth[s], S.path_id[s]);
+    float4 *r = t + lane * 9;
+    r[0] = ld3(S.pos, __uint_as_float(meta));
+    r[1] = ld3(S.flux, __ldg(S.parent_pdf + s));
+    r[2] = ld3(S.parent_pos, __ldg(S.edge_pdf + s));
+    r[3] = ld3(S.pred_pos, __ldg(S.rr_weight + s));
+    r[4] = ld3(S.parent_n, 0.f);
+    r[5] = ld3(S.prefix_flux, 0.f);
+    r[6] = ld3(S.parent_albedo, 0.f);
+    r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  if (warpBase >= n) return;
+  const uint32_t nRec = min(32u, n - warpBase);
+  float4 *dst = aos + (size_t)warpBase * GVPM_AOS_FLOAT4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t q = 32u * j + lane;          // float4 index inside the warp's 4 KB of records
+    if ((q >> 3) < nRec) dst[q] = t[(q >> 3) * 9 + (q & 7u)];
+  }
 }
 // sorted position plane P0 (pos.xyz, meta) + original index: the only sorted copies the gather needs
 __global__ void k_gather_sorted(const float4 *__restrict__ aos, const uint32_t *__restrict__ sorted, uint32_t n,
