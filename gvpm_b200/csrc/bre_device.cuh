@@ -502,16 +502,16 @@ __device__ __forceinline__ void bre_photon(const GatherParams &P, const float4 *
 // invalid offsets on the spot and queues the reconnections as (pair, k) tasks; phase B hands the tasks out 32 at a
 // time, so the reconnection code always runs with full lanes (the pair's context travels through shared memory);
 // phase C (lane = pair) folds the four results in k order.
-#define GVPM_CTX_STRIDE 35
+#define GVPM_CTX_STRIDE 33
 struct ShadeShared {               // per warp
   float ctx[32][GVPM_CTX_STRIDE];  // odd stride: lanes reading one field of 32 different pairs hit 32 banks
-  float4 res[32][4];               // (S.xyz, weight) per (pair, k)
+  float4 res[32][5];               // (S.xyz, weight) per (pair, k); row stride 5 float4: conflict-free 128-bit access
   uint8_t tasks[128];              // (pair << 2) | k
 };
 enum {  // float slots of ctx[pair]
   CX_P = 0, CX_PARENT = 3, CX_PN = 6, CX_PREFIX = 9, CX_ALBEDO = 12, CX_PARENTPDF = 15, CX_EDGEPDF = 16, CX_RRW = 17,
   CX_PTYPE = 18, CX_WIW = 19, CX_COSI = 22, CX_NEDGE = 23, CX_NEARMASK = 24, CX_NEARBOUND = 25, CX_ZBASE = 26,
-  CX_TBASE = 29, CX_PDFCAM = 30, CX_TSHIFT = 31, CX_RAY = 32, CX_RD = 33  // CX_RD: 2 floats (d.x, d.y) + sign in ray slot
+  CX_TBASE = 29, CX_PDFCAM = 30, CX_TSHIFT = 31, CX_RAY = 32
 };
 
 __device__ __forceinline__ void bre_pairs_warp(const GatherParams &P, uint2 pr, bool valid, float *a, ShadeShared &W,

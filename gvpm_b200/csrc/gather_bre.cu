@@ -105,7 +105,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
     spreadMax = fmaxf(spreadMax, 0.01f * sqrtf(ex * ex + ey * ey + ez * ez));
   }
   // the filters only drop photons: apply them before queueing unless the caller wants the geometric counts
-  const bool prefilter = !DUMP && P.counts == nullptr;
+  const bool prefilter = !DUMP && !SPPM && P.counts == nullptr;   // (sppm's own filter is applied at the flush only)
 
   for (;;) {
     uint32_t tile = 0;

@@ -81,6 +81,38 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every 
   return x;
 }
 
+// 30-bit 3-D Hilbert index of a 1024^3 cell (Skilling, "Programming the Hilbert curve", 2004: axes -> transpose, then
+// the bits are interleaved).  Unlike the Z-order curve the Hilbert curve never jumps: ANY run of consecutive keys is a
+// connected blob, so the boxes of 32 consecutive photons (and of 32 consecutive boxes, ...) have no outliers that
+// straddle a Z-curve discontinuity, and fewer of them are hit per ray.
+__device__ __forceinline__ uint32_t hilbert30(uint32_t x0, uint32_t x1, uint32_t x2) {
+  uint32_t X[3] = {x0, x1, x2};
+  const uint32_t M = 1u << 9;
+#pragma unroll
+  for (uint32_t Q = M; Q > 1u; Q >>= 1) {   // inverse undo
+    const uint32_t Pm = Q - 1u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= Pm;
+      } else {
+        const uint32_t t = (X[0] ^ X[i]) & Pm;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];                              // Gray encode
+  X[2] ^= X[1];
+  uint32_t t = 0u;
+#pragma unroll
+  for (uint32_t Q = M; Q > 1u; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1u;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  // transpose -> index: bit b of X[0] is the most significant of the triple
+  return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
+}
+
 __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float *__restrict__ bounds,
                          uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +125,7 @@ __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float 
     u = fminf(fmaxf(u, 0.f), 1.f);
     q[a] = min((uint32_t)(u * 1024.f), 1023u);
   }
-  keys[i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+  keys[i] = hilbert30(q[0], q[1], q[2]);
   vals[i] = i;
 }
 
