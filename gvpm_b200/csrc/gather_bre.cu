@@ -49,7 +49,7 @@ constexpr int kTileBatch = GVPM_TILE_BATCH;  // photons tested between queue-roo
 static_assert(kTileBatch <= kTileQ, "a batch must fit in an empty queue");
 
 struct TileShared {
-  float4 ph[32 * kLeafBatch];  // photons of the current leaf batch that lie inside the fat ray
+  float4 ph[2 * 32 * kLeafBatch];  // photons of the current leaf batch inside the fat ray: entry i of list b at [2i + b]
   uint32_t queue[kTileQ][32];  // [entry][lane]: sorted photon slots waiting for the strict test
   uint32_t mask[GVPM_MAX_LEVELS];
   uint32_t base[GVPM_MAX_LEVELS];
@@ -106,6 +106,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
   }
   // the filters only drop photons: apply them before queueing unless the caller wants the geometric counts
   const bool prefilter = !DUMP && !SPPM && P.counts == nullptr;   // (sppm's own filter is applied at the flush only)
+  const bool split = prefilter && P.cfg.path_set;                 // per-parity photon lists (see the leaf code)
 
   for (;;) {
     uint32_t tile = 0;
@@ -245,7 +246,10 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
         // the photons inside the fat ray are compacted into shared memory (all leaves of the batch together) and
         // broadcast from there; w = lane | leaf-in-parent << 5 | meta << 10
         __syncwarp();
-        uint32_t total = 0;
+        // With the pathSet checkerboard a photon only ever matches rays of its own pixel parity: the in-fat photons go
+        // to two lists (interleaved, so that lanes of either parity read different banks) and every lane walks only
+        // the list of its parity - half the per-ray tests.  Without the prefilter everything goes to list 0.
+        uint32_t total0 = 0, total1 = 0;
 #pragma unroll
         for (int b = 0; b < kLeafBatch; ++b) {
           const float4 q0 = leafQ[b];
@@ -254,23 +258,33 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
           const float qx = cx - dd * cdx, qy = cy - dd * cdy, qz = cz - dd * cdz;
           const bool inFat = leafC[b] >= 0 && fabsf(qx) < fx && fabsf(qy) < fy && fabsf(qz) < fz && dd > tloFat &&
                              dd < thiFat;
-          const uint32_t pm = __ballot_sync(0xffffffffu, inFat);
-          if (inFat)
-            S.ph[total + __popc(pm & ((1u << lane) - 1u))] = make_float4(
+          const uint32_t pb = split ? ((__float_as_uint(q0.w) >> 10) & 1u) : 0u;   // meta bit 10 = pathID parity
+          const uint32_t pm0 = __ballot_sync(0xffffffffu, inFat && pb == 0u);
+          const uint32_t pm1 = __ballot_sync(0xffffffffu, inFat && pb != 0u);
+          if (inFat) {
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t pos = pb ? total1 + __popc(pm1 & lt) : total0 + __popc(pm0 & lt);
+            S.ph[2u * pos + pb] = make_float4(
                 q0.x, q0.y, q0.z,
                 __uint_as_float((uint32_t)lane | ((uint32_t)leafC[b] << 5) | (__float_as_uint(q0.w) << 10)));
-          total += __popc(pm);
+          }
+          total0 += __popc(pm0);
+          total1 += __popc(pm1);
         }
         __syncwarp();
         const uint32_t slot0 = base << 5;
+        const uint32_t total = max(total0, total1);
+        const uint32_t myList = split ? (uint32_t)parity : 0u;
+        const uint32_t myTotal = myList ? total1 : total0;
         for (uint32_t i0 = 0; i0 < total; i0 += kTileBatch) {
           const uint32_t i1 = min(total, i0 + (uint32_t)kTileBatch);
           // a lane pushes at most one entry per photon: make room for the whole batch up front
           if (__any_sync(0xffffffffu, qn + (i1 - i0) > (uint32_t)kTileQ)) flush();
           if (mine) {
+            const uint32_t e1 = min(i1, myTotal);
 #pragma unroll 2
-            for (uint32_t i = i0; i < i1; ++i) {
-              const float4 ph = S.ph[i];
+            for (uint32_t i = i0; i < e1; ++i) {
+              const float4 ph = S.ph[2u * i + myList];
               // relaxed (FMA) pre-test of the lane's own ray, conservative by fpad
               const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
               const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
@@ -278,8 +292,8 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
               bool cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tloRay;
               const uint32_t w = __float_as_uint(ph.w);
               if (prefilter) {
-                // meta << 10: bit 20 = pathID parity, bits 12-19 = depth
-                if (P.cfg.path_set && (int)((w >> 20) & 1u) != parity) cand = false;
+                // meta << 10: bit 20 = pathID parity (already matched through the list when split), bits 12-19 = depth
+                if (!split && P.cfg.path_set && (int)((w >> 20) & 1u) != parity) cand = false;
                 if (P.cfg.max_depth > 0 && (int)((w >> 12) & 255u) + L.eid > P.cfg.max_depth) cand = false;
               }
               if (cand) S.queue[qn++][lane] = slot0 + (w & 1023u);
