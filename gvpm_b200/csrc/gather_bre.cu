@@ -31,7 +31,7 @@ namespace gvpm {
 #define GVPM_SHADE_THREADS 128
 #endif
 #ifndef GVPM_SHADE_MIN_BLOCKS
-#define GVPM_SHADE_MIN_BLOCKS 6
+#define GVPM_SHADE_MIN_BLOCKS 5   // 96 registers; tuned on cfg5: 4: 2.90 ms, 5: 2.63, 6: 2.69, 8: 2.82
 #endif
 #ifndef GVPM_TILE_QUEUE
 #define GVPM_TILE_QUEUE 32
@@ -39,7 +39,7 @@ namespace gvpm {
 constexpr int kTravWarps = GVPM_TRAV_WARPS;
 constexpr int kTileQ = GVPM_TILE_QUEUE;  // candidate queue entries per lane
 #ifndef GVPM_LEAF_BATCH
-#define GVPM_LEAF_BATCH 2
+#define GVPM_LEAF_BATCH 4   // tuned on cfg5 (tools/build_variants.sh + tools/time_gather.py): 1: 3.22 ms, 2: 2.45, 4: 2.32
 #endif
 constexpr int kLeafBatch = GVPM_LEAF_BATCH;  // leaves whose photon loads are in flight together
 #ifndef GVPM_TILE_BATCH

@@ -21,7 +21,8 @@ ap.add_argument("--scale", type=float, default=0.1)
 ap.add_argument("--w", type=int, default=1920)
 ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--block", type=int, default=32)
+ap.add_argument("--block", type=int, default=-32, help="negative: Z-order inside 32x32 blocks (bench.py layout)")
+ap.add_argument("--counts", action="store_true", help="time the gather WITH per-ray counts (no traversal prefilter)")
 a = ap.parse_args()
 
 med = g.make_medium()
@@ -35,9 +36,15 @@ ctx.upload_photons(ph)
 ctx.upload_rays(rays)
 r = g.bre_radius(a.scale)
 bs, gs, ts, ss = [], [], [], []
+ctx.build_points(r)
+out_ptr, _ = ctx.gather_bre_device()
 for i in range(a.reps + 1):
     ctx.build_points(r)
-    ctx.gather_bre_device()
+    if a.counts:
+        ctx.gather_bre_device()
+    else:
+        ctx.gather_bre_into(out_ptr, None)   # what bench.py times: filters applied in the traversal
+        ctx.sync()
     b, gm = ctx.last_timings()
     t, s, pairs = ctx.last_gather_detail()
     if i:
