@@ -32,7 +32,7 @@ __device__ __forceinline__ bool box_hit(const Tree &t, uint32_t i, float oxp, fl
 // (shift_volume_photon.cpp:723): identical to this fp32 form (checked exhaustively-ish in tests/).
 __device__ __forceinline__ sf chord_pdf(sf deltaT) {
   sf x2 = deltaT * sf(2.f);
-  return (x2.v <= 0.0001f) ? sf(10000.f) : sf(1.f) / x2;
+  return (x2.v <= 0.0001f) ? sf(10000.f) : frcp(x2);   // a pdf: radiometric only (2 ulp)
 }
 
 struct MediumRec { sf T, pdfSuccess, pdfFailure; };
@@ -561,11 +561,19 @@ __device__ __forceinline__ void bre_pairs_warp(const GatherParams &P, uint2 pr, 
     c[CX_TBASE] = tBase.v; c[CX_PDFCAM] = pdfCam.v; c[CX_TSHIFT] = Tshift.v;
     c[CX_RAY] = __uint_as_float(pr.x);
   }
+  // the offset records are requested one iteration ahead (the loop is rolled: their L1/L2 latency was exposed at
+  // the top of every iteration)
+  float4 n0 = ldg4(rec + 4), n1 = ldg4(rec + 5), n2 = ldg4(rec + 6);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     bool reconnect = false;
+    const float4 s0 = n0, s1 = n1, s2 = n2;
+    if (k < 3) {
+      n0 = ldg4(rec + 4 * (k + 2));
+      n1 = ldg4(rec + 4 * (k + 2) + 1);
+      n2 = ldg4(rec + 4 * (k + 2) + 2);
+    }
     if (live) {
-      const float4 s0 = ldg4(rec + 4 * (k + 1)), s1 = ldg4(rec + 4 * (k + 1) + 1), s2 = ldg4(rec + 4 * (k + 1) + 2);
       sf weight(1.f);
       v3 S(0.f, 0.f, 0.f);
       if (__float_as_uint(s2.w) != 0u) {  // validVolumeEdge, shift_cameraPath.h:135-140
