@@ -294,7 +294,7 @@ def diag_phases(v):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         res[name] = round(float(ms.item()), 3)
 
-    if world > 1:
+    if world > 1 and pg is not None:
         def ag13():
             ws = [dist.all_gather_into_tensor(w, m, group=pg, async_op=True) for w, m in views[1]]
             for w in ws:
@@ -313,6 +313,7 @@ def diag_phases(v):
         big = v["stage_t"][1]
         nb = (big.numel() // world // 256) * 256
         run("allgather_1_call_same_bytes", lambda: dist.all_gather_into_tensor(big[:nb * world], big[rank * nb:(rank + 1) * nb], group=pg))
+    if world > 1:
         run("result_gather", lambda: dist.gather(v["out_dev"], v["gathered"], dst=0))
 
     def up():
@@ -424,50 +425,75 @@ def main():
     torch.cuda.synchronize()
     host_slice = REC.PhotonSet(n_slice, **host_fields)
 
-    comm = torch.cuda.Stream(device=local)      # issues the photon all-gathers
+    comm = torch.cuda.Stream(device=local)      # issues the photon all-gathers (NCCL fallback)
     h2d = torch.cuda.Stream(device=local)       # uploads the next iteration's photon slice (e2e leg)
-    pg_photons = dist.new_group(backend="nccl") if world > 1 else None
+    # Photon exchange between the ranks.  "peer" (default): every rank pushes its slice into the peers' staging
+    # buffers with cudaMemcpyAsync over NVLink (copy engines, CUDA IPC mappings: gvpm_peer_*), which overlaps the
+    # persistent gather kernels; "nccl": in-place all-gather of the 13 field arrays (SM-based, starved by them).
+    exchange = os.environ.get("GVPM_EXCHANGE", "peer") if world > 1 else "none"
+    pg_photons = host_pg = None
     inplace_ok = True
-    if world > 1:   # NCCL all-gathers in place when the input is the rank's segment of the output; probe torch's checks
-        try:
+    slice_dev = None
+    if exchange == "peer":
+        blob = torch.frombuffer(bytearray(ctx.peer_export()), dtype=torch.uint8).cuda()
+        blobs = [torch.empty_like(blob) for _ in range(world)]
+        dist.all_gather(blobs, blob)
+        ctx.peer_connect([bytes(b.cpu().numpy().tobytes()) for b in blobs], rank)
+        host_pg = dist.new_group(backend="gloo")   # host-side ordering of the interprocess event records / waits
+    elif exchange == "nccl":
+        pg_photons = dist.new_group(backend="nccl")
+        try:   # NCCL all-gathers in place when the input is the rank's segment of the output; probe torch's checks
             probe = torch.zeros(world * 256, device="cuda", dtype=torch.uint8)
             dist.all_gather_into_tensor(probe, probe[rank * 256:(rank + 1) * 256], group=pg_photons)
             torch.cuda.synchronize()
         except Exception:
             inplace_ok = False
-    slice_dev = None
-    if world > 1 and not inplace_ok:
-        slice_dev = [mine.clone() for _, mine in views[0]]
+        if not inplace_ok:
+            slice_dev = [mine.clone() for _, mine in views[0]]
     ready = [None, None]   # per staging buffer: what the compute stream must wait for before building from it
 
+    def host_barrier():
+        if host_pg is not None:
+            dist.barrier(group=host_pg)
+
     def prefetch(b, from_host):
-        """start filling staging buffer b with the NEXT iteration's photon set: (H2D of this rank's slice) + all-gather"""
-        ev = torch.cuda.Event()
-        ev.record(stream)                       # buffer b was last read by the build two steps ago (stream order)
+        """start filling staging buffer b with the NEXT iteration's photon set: (H2D of this rank's slice) + exchange"""
         waits = []
         if from_host:
+            ev = torch.cuda.Event()
+            ev.record(stream)                   # buffer b was last read by this rank's build two steps ago
             h2d.wait_event(ev)
             ctx.photon_staging_select(b)
             ctx.upload_photons_slice(host_slice, n_ph, s_begin, stream=h2d.cuda_stream)
             up = torch.cuda.Event()
             up.record(h2d)
             waits.append(up)
-            comm.wait_event(up)
-        else:
-            comm.wait_event(ev)
-        if world > 1:
+        if exchange == "peer":
+            ctx.peer_push_photon_slice(b, n_ph, s_begin, n_slice, after_stream=h2d.cuda_stream)
+            waits.append("peer")
+        elif exchange == "nccl":
+            if from_host:
+                comm.wait_event(waits[0])
+            else:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                comm.wait_event(ev)
             with torch.cuda.stream(comm):
                 for i, (whole, mine) in enumerate(views[b]):
                     src = mine if inplace_ok else slice_dev[i]
                     if from_host and not inplace_ok:
                         src.copy_(mine, non_blocking=True)
                     waits.append(dist.all_gather_into_tensor(whole, src, group=pg_photons, async_op=True))
-        ready[b] = waits
+        ready[b] = (b, waits)
 
     def wait_ready(b):
-        for w in ready[b] or []:
+        if ready[b] is None:
+            return
+        for w in ready[b][1]:
             if isinstance(w, torch.cuda.Event):
                 stream.wait_event(w)
+            elif w == "peer":
+                ctx.peer_wait_photons(b)
             else:
                 with torch.cuda.stream(stream):
                     w.wait()
@@ -489,6 +515,7 @@ def main():
             ctx.build_points(inp["radius"])
             ctx.gather_bre_into(out_dev.data_ptr(), None)
             collect()
+        host_barrier()
 
     def step_e2e(k):
         """host buffers in, host buffers out, through the C ABI: the photon slice of step k+1 goes up (and is
@@ -504,10 +531,12 @@ def main():
         with torch.cuda.stream(stream):
             ctx.build_points(inp["radius"])
             ctx.gather_bre_host(rays, out_host[:n_local * 27])
+        host_barrier()
 
     def timed(fn, steps, warmup, from_host):
         if world > 1 or from_host:
             prefetch(0, from_host)              # step 0's photon set (untimed priming)
+            host_barrier()
         for k in range(warmup):
             fn(k)
         ctx.sync()
@@ -593,8 +622,11 @@ def main():
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(R * 27 * 4),
                         "note": "every rank uploads 1/N of the photon set and its own rays over its own PCIe link; "
                                 "the upload + all-gather of step k+1 overlaps the build + gather of step k"},
-                "photon_exchange": {"collective": "none" if world == 1 else "all_gather (13 field arrays, in place)"
-                                    if inplace_ok else "all_gather (13 field arrays)", "double_buffered": True,
+                "photon_exchange": {"how": {"none": "single GPU", "peer": "slices pushed into the peers' staging "
+                                            "buffers over NVLink copy engines (CUDA IPC, gvpm_peer_*)",
+                                            "nccl": "NCCL all_gather of the 13 field arrays"
+                                            + (", in place" if inplace_ok else "")}[exchange],
+                                    "double_buffered": True,
                                     "staging_buffers_identical_after_run": staging_ok},
                 "gpu_launches": int(launches),
                 # the gather is two launches: k_bre_traverse (dominant) + k_bre_shade; SURVEY §8(d)'s

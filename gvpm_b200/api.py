@@ -85,6 +85,24 @@ class Context:
         self._ck(self.lib.gvpm_upload_photons_slice(self.h, C.byref(cs), n_total, begin, photons_slice.n, stream),
                  "gvpm_upload_photons_slice")
 
+    def peer_export(self):
+        """-> bytes: this context's IPC blob (staging buffers + events) for gvpm_peer_connect on the other ranks."""
+        buf = (C.c_ubyte * N.GVPM_PEER_BLOB_BYTES)()
+        self._ck(self.lib.gvpm_peer_export(self.h, buf), "gvpm_peer_export")
+        return bytes(buf)
+
+    def peer_connect(self, blobs, self_index):
+        raw = b"".join(blobs)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.lib.gvpm_peer_connect(self.h, buf, len(blobs), self_index), "gvpm_peer_connect")
+
+    def peer_push_photon_slice(self, which, n_total, begin, count, after_stream=None):
+        self._ck(self.lib.gvpm_peer_push_photon_slice(self.h, which, n_total, begin, count, after_stream),
+                 "gvpm_peer_push_photon_slice")
+
+    def peer_wait_photons(self, which):
+        self._ck(self.lib.gvpm_peer_wait_photons(self.h, which), "gvpm_peer_wait_photons")
+
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 

@@ -87,6 +87,15 @@ struct gvpm_ctx {
 
   DevBuf ph_staging, ph_staging_alt;  // the selected photon staging buffer and the other one (double buffering)
   int ph_staging_sel = 0;
+  // peer exchange over NVLink copy engines (gvpm_peer_*): interprocess events + peer mappings of the staging buffers
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};   // staging buffer b has been consumed by this context's last build
+  cudaEvent_t ev_pushed[2] = {nullptr, nullptr}; // this context's slice has landed in every peer's staging buffer b
+  cudaStream_t push_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t push_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..3] push stream done, [4] slice ready
+  int n_peers = 0, peer_self = -1;
+  std::vector<void *> peer_staging[2];
+  std::vector<cudaEvent_t> peer_free[2], peer_pushed[2];
+  void *staging_ptr(int which) const { return which == ph_staging_sel ? ph_staging.p : ph_staging_alt.p; }
   uint32_t n_photons = 0;
   bool photons_loaded = false;
   DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
@@ -349,6 +358,12 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
   for (auto &ev : ctx->pipe_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (int b = 0; b < 2; ++b) {
+    cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming | cudaEventInterprocess);
+    cudaEventCreateWithFlags(&ctx->ev_pushed[b], cudaEventDisableTiming | cudaEventInterprocess);
+  }
+  for (auto &ps : ctx->push_streams) cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking);
+  for (auto &ev : ctx->push_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   ctx->work_counter.reserve(256);
   cudaHostAlloc((void **)&ctx->pair_count_host, sizeof(unsigned long long), cudaHostAllocDefault);
   ctx->bounds.reserve(256);
@@ -370,6 +385,18 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
+  for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
+  for (auto &ev : ctx->push_ev) if (ev) cudaEventDestroy(ev);
+  for (int b = 0; b < 2; ++b) {
+    for (int p = 0; p < ctx->n_peers; ++p) {
+      if (p == ctx->peer_self) continue;
+      if (ctx->peer_staging[b][p]) cudaIpcCloseMemHandle(ctx->peer_staging[b][p]);
+      if (ctx->peer_free[b][p]) cudaEventDestroy(ctx->peer_free[b][p]);
+      if (ctx->peer_pushed[b][p]) cudaEventDestroy(ctx->peer_pushed[b][p]);
+    }
+    if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+    if (ctx->ev_pushed[b]) cudaEventDestroy(ctx->ev_pushed[b]);
+  }
   for (DevBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->pipe_ev) if (ev) cudaEventDestroy(ev);
@@ -509,6 +536,94 @@ int gvpm_upload_photons_slice(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n_
   return GVPM_OK;
 }
 
+// ---- peer exchange of photon slices over NVLink copy engines ------------------------------------------------------
+struct IpcBlob {  // what gvpm_peer_export writes (GVPM_PEER_BLOB_BYTES)
+  cudaIpcMemHandle_t staging[2];
+  cudaIpcEventHandle_t free_ev[2], pushed_ev[2];
+};
+static_assert(sizeof(IpcBlob) == GVPM_PEER_BLOB_BYTES, "blob size");
+
+int gvpm_peer_export(gvpm_ctx *ctx, void *blob) {
+  if (!ctx || !blob) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (!ctx->ph_staging.p || !ctx->ph_staging_alt.p)
+    return fail(ctx, GVPM_ERR_INVALID, "size both photon staging buffers (gvpm_photon_staging) before exporting them");
+  IpcBlob *B = (IpcBlob *)blob;
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaIpcGetMemHandle(&B->staging[b], ctx->staging_ptr(b)));
+    CK(cudaIpcGetEventHandle(&B->free_ev[b], ctx->ev_free[b]));
+    CK(cudaIpcGetEventHandle(&B->pushed_ev[b], ctx->ev_pushed[b]));
+    // make both events "recorded" so that a first wait on them is well defined
+    CK(cudaEventRecord(ctx->ev_free[b], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_pushed[b], ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_peer_connect(gvpm_ctx *ctx, const void *blobs, int n_peers, int self_index) {
+  if (!ctx || !blobs || n_peers < 1 || self_index < 0 || self_index >= n_peers) return GVPM_ERR_INVALID;
+  if (ctx->n_peers) return fail(ctx, GVPM_ERR_INVALID, "peers already connected");
+  cudaSetDevice(ctx->device);
+  const IpcBlob *B = (const IpcBlob *)blobs;
+  for (int b = 0; b < 2; ++b) {
+    ctx->peer_staging[b].assign(n_peers, nullptr);
+    ctx->peer_free[b].assign(n_peers, nullptr);
+    ctx->peer_pushed[b].assign(n_peers, nullptr);
+  }
+  ctx->n_peers = n_peers;
+  ctx->peer_self = self_index;
+  for (int p = 0; p < n_peers; ++p) {
+    if (p == self_index) continue;
+    for (int b = 0; b < 2; ++b) {
+      CK(cudaIpcOpenMemHandle(&ctx->peer_staging[b][p], B[p].staging[b], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenEventHandle(&ctx->peer_free[b][p], B[p].free_ev[b]));
+      CK(cudaIpcOpenEventHandle(&ctx->peer_pushed[b][p], B[p].pushed_ev[b]));
+    }
+  }
+  return GVPM_OK;
+}
+
+int gvpm_peer_push_photon_slice(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count, void *after_stream) {
+  if (!ctx || (which != 0 && which != 1) || begin + count > n_total) return GVPM_ERR_INVALID;
+  if (!ctx->n_peers) return fail(ctx, GVPM_ERR_INVALID, "gvpm_peer_connect has not been called");
+  cudaSetDevice(ctx->device);
+  PhotonLayout L(n_total);
+  const size_t elt[13] = {12, 12, 12, 12, 12, 12, 12, 4, 4, 4, 1, 1, 4};
+  const char *mine = (const char *)ctx->staging_ptr(which);
+  // the slice must be complete on this rank (work queued on after_stream, e.g. its H2D upload) ...
+  cudaEvent_t src_ready = ctx->push_ev[4];
+  CK(cudaEventRecord(src_ready, after_stream ? (cudaStream_t)after_stream : ctx->stream));
+  int si = 0;
+  for (int p = 0; p < ctx->n_peers; ++p) {
+    if (p == ctx->peer_self) continue;
+    cudaStream_t ps = ctx->push_streams[si++ & 3];
+    CK(cudaStreamWaitEvent(ps, src_ready, 0));
+    // ... and the peer must have consumed what its buffer held (its last build from it)
+    CK(cudaStreamWaitEvent(ps, ctx->peer_free[which][p], 0));
+    char *dst = (char *)ctx->peer_staging[which][p];
+    for (int f = 0; f < 13; ++f)
+      CK(cudaMemcpyAsync(dst + L.off[f] + begin * elt[f], mine + L.off[f] + begin * elt[f], count * elt[f],
+                         cudaMemcpyDeviceToDevice, ps));
+  }
+  // ev_pushed[which] = all push streams done: funnel them through stream 0
+  for (int i = 1; i < 4; ++i) {
+    CK(cudaEventRecord(ctx->push_ev[i], ctx->push_streams[i]));
+    CK(cudaStreamWaitEvent(ctx->push_streams[0], ctx->push_ev[i], 0));
+  }
+  CK(cudaEventRecord(ctx->ev_pushed[which], ctx->push_streams[0]));
+  return GVPM_OK;
+}
+
+int gvpm_peer_wait_photons(gvpm_ctx *ctx, int which) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  if (!ctx->n_peers) return fail(ctx, GVPM_ERR_INVALID, "gvpm_peer_connect has not been called");
+  cudaSetDevice(ctx->device);
+  for (int p = 0; p < ctx->n_peers; ++p)
+    if (p != ctx->peer_self) CK(cudaStreamWaitEvent(ctx->stream, ctx->peer_pushed[which][p], 0));
+  return GVPM_OK;
+}
+
 int gvpm_upload_photons(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n) {
   if (!ctx || (n && !p)) return GVPM_ERR_INVALID;
   int rc = gvpm_photon_staging(ctx, n, nullptr, nullptr);
@@ -570,6 +685,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     CK(ctx->aos.reserve(128 * (size_t)n));
     launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
                        ctx->orig.as<uint32_t>(), st);
+    CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
     float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
     launch_leaf_boxes(ctx->planes.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
     for (int l = 1; l < levels; ++l)

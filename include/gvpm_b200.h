@@ -235,7 +235,28 @@ int gvpm_photon_staging_select(gvpm_ctx *ctx, int which /* 0 or 1 */);
 int gvpm_photon_staging_layout(size_t n, size_t field_offset[13], size_t field_elem_bytes[13]);
 int gvpm_upload_photons_slice(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n_total, size_t begin, size_t count,
                               void *stream);
-/* Morton sort + implicit 32-ary AABB hierarchy for search radius `radius`
+/* Peer exchange of the photon slices over NVLink COPY ENGINES (no SMs: the transfers overlap the gather kernels,
+ * which an SM-based collective cannot while persistent kernels fill the machine).  For contexts in different
+ * processes (one per GPU) the staging buffers and four events are shared through CUDA IPC:
+ *   gvpm_peer_export   writes this context's GVPM_PEER_BLOB_BYTES-byte blob (both staging buffers must have been
+ *                      sized with gvpm_photon_staging and must not grow afterwards);
+ *   gvpm_peer_connect  takes the blobs of all n_peers contexts (rank order, own one included) and maps them;
+ *   gvpm_peer_push_photon_slice  copies photons [begin, begin+count) of staging buffer `which` into the same place of
+ *                      every peer's buffer `which` with cudaMemcpyAsync on internal streams, after the work queued
+ *                      on `after_stream` (NULL = the context's stream; e.g. the slice's H2D upload) and after each
+ *                      peer's last build from that buffer;
+ *   gvpm_peer_wait_photons       makes the context's stream wait until every peer's slice has landed in buffer
+ *                      `which`.
+ * Interprocess events order work only with respect to records already ISSUED: the host processes must pass a
+ * barrier once per iteration between a rank's push / build calls and the other ranks' waits on them (bench.py). */
+#define GVPM_PEER_BLOB_BYTES 384
+int gvpm_peer_export(gvpm_ctx *ctx, void *blob /* [GVPM_PEER_BLOB_BYTES] */);
+int gvpm_peer_connect(gvpm_ctx *ctx, const void *blobs /* [n_peers * GVPM_PEER_BLOB_BYTES] */, int n_peers,
+                      int self_index);
+int gvpm_peer_push_photon_slice(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count,
+                                void *after_stream);
+int gvpm_peer_wait_photons(gvpm_ctx *ctx, int which);
+/* Hilbert sort + implicit 32-ary AABB hierarchy for search radius `radius`
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
 
