@@ -438,9 +438,17 @@ def main():
         blob = torch.frombuffer(bytearray(ctx.peer_export()), dtype=torch.uint8).cuda()
         blobs = [torch.empty_like(blob) for _ in range(world)]
         dist.all_gather(blobs, blob)
-        ctx.peer_connect([bytes(b.cpu().numpy().tobytes()) for b in blobs], rank)
+        ok = torch.ones(1, device="cuda", dtype=torch.int32)
+        try:
+            ctx.peer_connect([bytes(b.cpu().numpy().tobytes()) for b in blobs], rank)
+        except Exception as e:  # noqa: BLE001 - e.g. no P2P between two devices: every rank falls back together
+            print(f"[rank {rank}] peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         host_pg = dist.new_group(backend="gloo")   # host-side ordering of the interprocess event records / waits
-    elif exchange == "nccl":
+        if int(ok.item()) == 0:
+            exchange, host_pg = "nccl", None
+    if exchange == "nccl":
         pg_photons = dist.new_group(backend="nccl")
         try:   # NCCL all-gathers in place when the input is the rank's segment of the output; probe torch's checks
             probe = torch.zeros(world * 256, device="cuda", dtype=torch.uint8)

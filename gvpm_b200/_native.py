@@ -70,6 +70,9 @@ class VpmSampleSoA(C.Structure):
                 ("pdf_sel", f32p), ("radius", f32p)]
 
 
+# gvpm_beam_technique (volTechnique strings of sppm.cpp:208-209)
+BEAM_TECHNIQUES = {"beam1d": 0, "beam3d_naive": 1, "beam3d_egsr": 2, "beam3d": 3}
+
 # every symbol include/gvpm_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
@@ -82,6 +85,7 @@ ABI_SYMBOLS = [
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
     "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
+    "gvpm_gather_sppm_beams", "gvpm_dump_neighbours_sppm_beams",
     "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_dump_neighbours_planes",
 ]
 
@@ -137,6 +141,8 @@ def load_lib():
     lib.gvpm_build_beams.argtypes = [vp, C.c_float]
     lib.gvpm_gather_beams.argtypes = [vp, f32p, u32p]
     lib.gvpm_dump_neighbours_beams.argtypes = [vp, u64p, u32p, C.c_size_t]
+    lib.gvpm_gather_sppm_beams.argtypes = [vp, C.c_int, f32p, u32p]
+    lib.gvpm_dump_neighbours_sppm_beams.argtypes = [vp, C.c_int, u64p, u32p, C.c_size_t]
     lib.gvpm_upload_planes.argtypes = [vp, C.POINTER(PlaneSoA), C.c_size_t]
     lib.gvpm_build_planes.argtypes = [vp]
     lib.gvpm_gather_planes.argtypes = [vp, f32p, u32p]

@@ -213,6 +213,34 @@ class Context:
                      "gvpm_dump_neighbours_beams")
         return offsets, idx[:total]
 
+    # ---- sppm primal photon beams
+    def gather_sppm_beams(self, technique, counts=True):
+        """sppm primal beam gather (volTechnique beam1d | beam3d_naive | beam3d_egsr | beam3d):
+        -> (out [n_rays,3] float32, counts [n_rays,2] or None)."""
+        tech = N.BEAM_TECHNIQUES[technique] if isinstance(technique, str) else int(technique)
+        n = self.n_rays
+        out = np.empty(n * 3, dtype=np.float32)
+        cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
+        self._ck(self.lib.gvpm_gather_sppm_beams(self.h, tech, out.ctypes.data_as(N.f32p),
+                                                 cnt.ctypes.data_as(N.u32p) if counts else None),
+                 "gvpm_gather_sppm_beams")
+        return out.reshape(n, 3), (cnt.reshape(n, 2) if counts else None)
+
+    def dump_neighbours_sppm_beams(self, technique):
+        tech = N.BEAM_TECHNIQUES[technique] if isinstance(technique, str) else int(technique)
+        n = self.n_rays
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        rc = self.lib.gvpm_dump_neighbours_sppm_beams(self.h, tech, offsets.ctypes.data_as(N.u64p), None, 0)
+        total = int(offsets[n])
+        if rc != 0 and total == 0:
+            self._ck(rc, "gvpm_dump_neighbours_sppm_beams")
+        idx = np.zeros(max(total, 1), dtype=np.uint32)
+        if total:
+            self._ck(self.lib.gvpm_dump_neighbours_sppm_beams(self.h, tech, offsets.ctypes.data_as(N.u64p),
+                                                              idx.ctypes.data_as(N.u32p), total),
+                     "gvpm_dump_neighbours_sppm_beams")
+        return offsets, idx[:total]
+
     # ---- G-Planes 0D
     def upload_planes(self, planes):
         cs = planes.as_c()

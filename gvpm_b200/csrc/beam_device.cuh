@@ -483,4 +483,93 @@ __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4
   }
 }
 
+// ---- sppm primal photon beams: BeamRadianceQuery::operator(), photonmapper/beams.h:29-223 ---------------------------
+// One (camera beam, sub-beam) visit for technique P.sppm_beam_technique (gvpm_beam_technique).  sb = sub-beam record
+// (t1, t2, beam index, flags: bit 0 first, bit 1 last, bits 2.. ordinal).  Every value that decides acceptance is
+// strictly rounded in the reference's operation order.  Returns 0 = rejected, 1 = accepted; Li is the
+// contribution (without beam.weight) when accepted.
+__device__ __forceinline__ int sppm_beam_functor(const GatherParams &P, const BaseRay &R, const BeamRec &beam,
+                                                 uint32_t beamIndex, float4 sb, v3 &Li) {
+  const uint32_t flags = __float_as_uint(sb.w);
+  const bool first = flags & 1u, last = flags & 2u;
+  const sf tmin(sb.x);
+  sf tmax(sb.y);
+  if (tmax > beam.length) tmax = beam.length;                                            // :30-32
+  const sf r(P.radius), eps(P.cfg.epsilon);
+  const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
+  const int technique = P.sppm_beam_technique;
+  Li = v3(0.f, 0.f, 0.f);
+  if (technique == GVPM_BEAM_1D) {                                                       // :41-68
+    sf u, v, w, sinTheta;
+    if (!beam_intersect_1d(beam.o, beam.dir, beam.length, r, R.o, R.d, R.mint, R.maxt, first ? sf(0.f) : tmin,
+                           last ? beam.length : tmax, u, v, w, sinTheta))
+      return 0;
+    if (r <= u) return 0;
+    const MediumRec mRecCamera = medium_eval(P, eps, w), mRec = medium_eval(P, sf(0.f), v);
+    const sf weightKernel = sf(0.5f) / r;
+    v3 beamContrib = (((mRec.T * mRecCamera.T) * sigS) * beam.flux) * phase_eval(P, -beam.dir, -R.d);
+    if (!P.cfg.long_beams) {                                                            // getContrib, beams_struct.h:157-172
+      if (mRec.pdfFailure.v == 0.f && mRec.T.v != 0.f) return 1;
+      beamContrib = beamContrib / mRec.pdfFailure;
+    }
+    Li = (beamContrib * weightKernel) / sinTheta;
+    return 1;
+  }
+  sf beamSegmentRand, cameraSegmentRand, invPDF;
+  const sf radSqr = r * r;
+  if (technique == GVPM_BEAM_3D_NAIVE) {                                                 // :77-102
+    const uint32_t k = flags >> 2;
+    const sf xi1(beam_uniform(P, R, beamIndex, 2u + 2u * k)), xi2(beam_uniform(P, R, beamIndex, 3u + 2u * k));
+    beamSegmentRand = tmin + (tmax - tmin) * xi1;
+    invPDF = tmax - tmin;
+    const v3 kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+    const sf distToProj = dot(kernelCentroid - R.o, R.d);
+    const sf distSqr = length_sq((R.o + distToProj * R.d) - kernelCentroid);
+    if (distSqr >= radSqr) return 0;
+    const sf deltaT = safe_sqrt(radSqr - distSqr);
+    cameraSegmentRand = (distToProj - deltaT) + sf(2.f) * deltaT * xi2;
+    invPDF = sf((float)(sd((double)invPDF.v) * sd(fmax((sd(2.0) * sd((double)deltaT.v)).v, 0.0001))).v);
+    if (cameraSegmentRand < R.mint || cameraSegmentRand > R.maxt) return 0;
+  } else {
+    const sf xi1(beam_uniform(P, R, beamIndex, 0)), xi2(beam_uniform(P, R, beamIndex, 1));
+    const v3 camStart = R.o + R.mint * R.d;                                              // _cam, :106-107
+    const sf camLen = R.maxt - R.mint;
+    double tNearBeam, tFarBeam;
+    if (!cylinder_intersection(camStart, R.d, camLen, beam.o, beam.dir, beam.length.v, r, tNearBeam, tFarBeam)) return 0;
+    if (!((first || tNearBeam >= (double)tmin.v) && (last || tNearBeam < (double)tmax.v))) return 0;   // :122-128
+    if (!(tNearBeam < 0.0 || (tNearBeam > 0.0 && tNearBeam < (double)beam.length.v))) return 0;
+    const sd span = sd(tFarBeam) - sd(tNearBeam);
+    beamSegmentRand = sf((float)(sd(tNearBeam) + span * sd((double)xi1.v)).v);
+    invPDF = sf((float)fmax(span.v, 0.0001));
+    if (beamSegmentRand.v < 0.f || beamSegmentRand > beam.length) return 0;
+    if (technique == GVPM_BEAM_3D_EGSR) {                                                // :138-150
+      double tNearCam, tFarCam;
+      if (!cylinder_intersection(beam.o, beam.dir, beam.length, camStart, R.d, camLen.v, r, tNearCam, tFarCam)) return 0;
+      const sd spanCam = sd(tFarCam) - sd(tNearCam);
+      cameraSegmentRand = sf((float)(sd(tNearCam) + spanCam * sd((double)xi2.v)).v);
+      invPDF = sf((float)(sd((double)invPDF.v) * sd(fmax(spanCam.v, 0.0001))).v);
+    } else {                                                                             // :151-170
+      const v3 kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+      const sf distToProj = dot(kernelCentroid - R.o, R.d);
+      const sf distSqr = length_sq((R.o + distToProj * R.d) - kernelCentroid);
+      if (distSqr >= radSqr) return 0;
+      const sf deltaT = safe_sqrt(radSqr - distSqr);
+      cameraSegmentRand = distToProj - deltaT + sf(2.f) * deltaT * xi2;
+      invPDF = sf((float)(sd((double)invPDF.v) * sd(fmax((sd(2.0) * sd((double)deltaT.v)).v, 0.0001))).v);
+    }
+    if (cameraSegmentRand < R.mint || cameraSegmentRand > R.maxt) return 0;              // :173-175
+    if (technique == GVPM_BEAM_3D_EGSR) {                                                // :178-187
+      const v3 kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+      const sf distSqr = length_sq((R.o + cameraSegmentRand * R.d) - kernelCentroid);
+      if (distSqr >= radSqr) return 0;
+    }
+  }
+  const MediumRec mRecBeam = medium_eval(P, sf(0.f), beamSegmentRand), mRecCamera = medium_eval(P, eps, cameraSegmentRand);
+  const sf phaseTerm = phase_eval(P, -beam.dir, -R.d);
+  v3 beamContrib = ((((beam.flux * mRecBeam.T) * sigS) * mRecCamera.T) * phaseTerm) * (invPDF / sf(P.kernel_vol));
+  if (!P.cfg.long_beams) beamContrib = beamContrib / mRecBeam.pdfFailure;                // :213-217
+  Li = beamContrib;
+  return 1;
+}
+
 }  // namespace gvpm

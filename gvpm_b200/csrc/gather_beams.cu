@@ -334,6 +334,74 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
   }
 }
 
+// sppm primal photon beams (volumePhotonBeamPass, sppm.cpp:823-860): one thread per (camera beam, sub-beam) candidate
+// of the same traversal; the functor of technique P.sppm_beam_technique, the depth window of sppm.cpp:853-854,
+// Li * beam.weight reduced per ray by a segmented warp scan, 3 float atomics per run.  P.out is [n_rays][3].
+__global__ void __launch_bounds__(128, 4) k_beam_shade_sppm(const __grid_constant__ GatherParams P) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long total = *P.pair_counter;
+  if (total > P.pair_cap) total = P.pair_cap;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total;
+       i0 += stride) {
+    const unsigned long long i = i0 + lane;
+    const bool valid = i < total;
+    float a[3] = {0.f, 0.f, 0.f};
+    uint32_t key = 0xffffffffu;
+    if (valid) {
+      const uint2 pr = P.pairs[i];
+      key = pr.x;
+      const float4 sb = ldg4(P.subs + pr.y);
+      const uint32_t bi = __float_as_uint(sb.z);
+      const BaseRay R = load_base_ray(P.rays + (size_t)key * GVPM_RAY_FLOAT4);
+      // only origin / direction / length / flux / depth of the record are read
+      const float4 *b = P.beams + (size_t)bi * GVPM_BEAM_FLOAT4;
+      const float4 b0 = ldg4(b), b1 = ldg4(b + 1), b2 = ldg4(b + 2);
+      BeamRec beam;
+      beam.o = v3(b0.x, b0.y, b0.z); beam.length = sf(b0.w);
+      beam.dir = v3(b1.x, b1.y, b1.z);
+      beam.flux = v3(b2.x, b2.y, b2.z);
+      const int depth = (__float_as_uint(b1.w) >> 2) & 255;
+      v3 Li;
+      if (sppm_beam_functor(P, R, beam, bi, sb, Li)) {
+        const int maxDepthQ = P.cfg.max_depth == -1 ? -1 : P.cfg.max_depth - R.edgeId;
+        const int minDepthQ = max(0, P.cfg.min_depth - R.edgeId);
+        const bool contributes = !(maxDepthQ != -1 && depth > maxDepthQ) && !(minDepthQ != 0 && depth < minDepthQ);
+        if (P.counts) {
+          atomicAdd(P.counts + 2 * (size_t)key, 1u);
+          if (contributes) atomicAdd(P.counts + 2 * (size_t)key + 1, 1u);
+        }
+        if (P.dump_pairs) {
+          const unsigned long long slot = atomicAdd(P.dump_counter, 1ull);
+          if (slot < P.dump_cap) P.dump_pairs[slot] = make_uint2(key, bi | (contributes ? 0x80000000u : 0u));
+        } else if (contributes) {
+          const v3 c = Li * R.eye;
+          a[0] = c.x.v; a[1] = c.y.v; a[2] = c.z.v;
+        }
+      }
+    }
+    if (P.dump_pairs) continue;
+    const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key);
+    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const bool same = lane - off >= start;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float vu = __shfl_up_sync(0xffffffffu, a[j], off);
+        if (same) a[j] += vu;
+      }
+    }
+    if (valid && (lane == 31 || (heads >> (lane + 1) & 1u))) {
+      float *o = P.out + (size_t)key * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (a[j] != 0.f) atomicAdd(o + j, a[j]);
+    }
+  }
+}
+
 // ---- host-side launchers -----------------------------------------------------------------------
 void launch_sub_gather(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *out, cudaStream_t st) {
   if (n) k_sub_gather<<<(n + 255) / 256, 256, 0, st>>>(raw, sorted, n, out);
@@ -367,6 +435,20 @@ cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, i
   unsigned long long grid = (unsigned long long)sm_count * g_bs_blocks * 4;
   if (grid > need) grid = need;
   k_beam_shade<<<(unsigned)grid, 128, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_beam_shade_sppm(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream) {
+  if (total == 0) return cudaSuccess;
+  static int blocks = 0;
+  if (blocks == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_beam_shade_sppm, 128, 0);
+    if (blocks < 1) blocks = 1;
+  }
+  unsigned long long need = (total + 127) / 128;
+  unsigned long long grid = (unsigned long long)sm_count * blocks * 4;
+  if (grid > need) grid = need;
+  k_beam_shade_sppm<<<(unsigned)grid, 128, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

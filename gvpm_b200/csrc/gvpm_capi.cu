@@ -32,6 +32,7 @@ void launch_subbeam_leaf_boxes(const float4 *subs, const float4 *beams, uint32_t
                                float4 *lo, float4 *hi, cudaStream_t st);
 cudaError_t launch_beam_traverse(const GatherParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
+cudaError_t launch_beam_shade_sppm(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_plane_pack_sorted(const float4 *raw, const uint32_t *sorted, uint32_t n, float4 *planes, uint32_t *orig,
                               cudaStream_t st);
 void launch_plane_leaf_boxes(const float4 *planes, uint32_t n, uint32_t nLeaves, float4 *lo, float4 *hi, cudaStream_t st);
@@ -1126,7 +1127,8 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
       subPos.push_back(b0.x + b1.x * tm);
       subPos.push_back(b0.y + b1.y * tm);
       subPos.push_back(b0.z + b1.z * tm);
-      uint32_t bi = (uint32_t)i, fl = (k == 0 ? 1u : 0u) | (k == nSub - 1 ? 2u : 0u);
+      // flags: bit 0 first, bit 1 last sub-beam of its beam, bits 2.. ordinal (the naive sppm technique's RNG dimension)
+      uint32_t bi = (uint32_t)i, fl = (k == 0 ? 1u : 0u) | (k == nSub - 1 ? 2u : 0u) | ((uint32_t)k << 2);
       float bf, ff;
       memcpy(&bf, &bi, 4);
       memcpy(&ff, &fl, 4);
@@ -1228,6 +1230,7 @@ static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
   P.beams = ctx->beams.as<float4>();
   P.subs = ctx->subs.as<float4>();
   P.n_beams = ctx->n_beams;
+  P.sppm_beam_technique = -1;
   return GVPM_OK;
 }
 
@@ -1238,7 +1241,8 @@ static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
     CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 64 * nr) * sizeof(uint2)));
     ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
   }
-  P.beam_prefilter = (want_counts || P.dump_pairs) ? 0 : 1;
+  const bool sppm = P.sppm_beam_technique >= 0;
+  P.beam_prefilter = (want_counts || P.dump_pairs || sppm) ? 0 : 1;
   unsigned long long total = 0;
   for (int attempt = 0; attempt < 4; ++attempt) {
     P.pairs = ctx->pairs.as<uint2>();
@@ -1261,7 +1265,8 @@ static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
     CK(cudaMemsetAsync(ctx->out.p, 0, nr * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
     CK(cudaMemsetAsync(ctx->counts.p, 0, nr * 8, ctx->stream));
   }
-  CK(launch_beam_shade(P, total, ctx->sm_count, ctx->stream));
+  CK(sppm ? launch_beam_shade_sppm(P, total, ctx->sm_count, ctx->stream)
+          : launch_beam_shade(P, total, ctx->sm_count, ctx->stream));
   ctx->launches += total ? 1 : 0;
   return GVPM_OK;
 }
@@ -1317,6 +1322,73 @@ int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, 
   for (size_t i = 0; i < n; ++i)
     std::sort(idx + offsets[i], idx + offsets[i + 1],
               [](uint32_t a, uint32_t b) { return (a & 0x7fffffffu) < (b & 0x7fffffffu); });
+  return GVPM_OK;
+}
+
+// ---- sppm primal photon beams (sppm.cpp:823-860 + beams.h:29-223) ------------------------------------------------
+static int sppm_beam_params(gvpm_ctx *ctx, int technique, GatherParams &P) {
+  if (technique < GVPM_BEAM_1D || technique > GVPM_BEAM_3D_OPTIMIZED)
+    return fail(ctx, GVPM_ERR_INVALID, "unknown gvpm_beam_technique");
+  int rc = beam_params(ctx, P);
+  if (rc) return rc;
+  P.sppm_beam_technique = technique;
+  return GVPM_OK;
+}
+
+int gvpm_gather_sppm_beams(gvpm_ctx *ctx, int technique, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  GatherParams P;
+  int rc = sppm_beam_params(ctx, technique, P);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  rc = beams_run(ctx, P, counts != nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed_gather = true;
+  const size_t n = ctx->n_rays;
+  if (n) {
+    CK(cudaMemcpyAsync(out, ctx->out.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_dump_neighbours_sppm_beams(gvpm_ctx *ctx, int technique, uint64_t *offsets, uint32_t *idx, size_t cap) {
+  if (!ctx || !offsets) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->n_rays;
+  std::vector<float> tmp(n * 3 + 1);
+  std::vector<uint32_t> counts(2 * n + 2);
+  int rc = gvpm_gather_sppm_beams(ctx, technique, tmp.data(), counts.data());
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) { offsets[i] = total; total += counts[2 * i]; }
+  offsets[n] = total;
+  if (total > cap || (total && !idx)) return fail(ctx, GVPM_ERR_INVALID, "neighbour buffer too small");
+  if (total == 0) return GVPM_OK;
+  CK(ctx->nbr_idx.reserve(total * sizeof(uint2)));
+  GatherParams P;
+  rc = sppm_beam_params(ctx, technique, P);
+  if (rc) return rc;
+  P.counts = nullptr;
+  P.dump_pairs = ctx->nbr_idx.as<uint2>();
+  P.dump_cap = total;
+  rc = beams_run(ctx, P, true);
+  if (rc) return rc;
+  std::vector<uint2> flat(total);
+  CK(cudaMemcpyAsync(flat.data(), ctx->nbr_idx.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> cursor(offsets, offsets + n);
+  for (const uint2 &p : flat) idx[cursor[p.x]++] = p.y;
+  // ascending beam index inside a ray; the naive technique can list a beam once per accepted sub-beam, entries of
+  // one beam ordered by the filter bit so that the list is canonical
+  for (size_t i = 0; i < n; ++i)
+    std::sort(idx + offsets[i], idx + offsets[i + 1], [](uint32_t a, uint32_t b) {
+      const uint32_t ai = a & 0x7fffffffu, bi = b & 0x7fffffffu;
+      return ai != bi ? ai < bi : a < b;
+    });
   return GVPM_OK;
 }
 

@@ -158,6 +158,7 @@ struct GatherParams {
   const float4 *subs;
   uint32_t n_beams;
   float weight_kernel;                // 1.0 / kernelVol (double division rounded to Float)
+  int sppm_beam_technique;            // gvpm_beam_technique of k_beam_shade_sppm (sppm primal beams)
   int beam_prefilter;                 // apply the depth/mode/pathSet filters already in the traversal
                                       // (when the caller does not ask for the geometric neighbour counts)
   // G-Planes: 6 float4 planes of n_planes entries in Morton order (plane_device.cuh), tree.lo/hi = leaf boxes

@@ -297,6 +297,29 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
  *      same after the depth filter}. */
 int gvpm_gather_sppm_bre(gvpm_ctx *ctx, float *out, uint32_t *counts);
 
+/* ---- sppm primal photon beams: replaces beamMap->build(EBVHAccel) + BeamRadianceQuery + beamMap->query(bRadQuery) over
+ *      all gather-point beams, sppm.cpp:803,823-860 + photonmapper/beams.h:29-223 + beams_accel.h:90-243, for the four
+ *      beam x beam techniques of EVolumeTechnique (volTechnique = beam1d | beam3d_naive | beam3d_egsr | beam3d).
+ *      Call order: gvpm_upload_beams (origin, end, flux, depth are read; the parent arrays may hold anything),
+ *      gvpm_build_beams(radius), gvpm_upload_rays (o = beam.p1, d, mint = Epsilon, maxt = distTotal - Epsilon,
+ *      edge_len = distTotal, eye_contrib = beam.weight, edge_id = camera beam.depth; offsets ignored).  The depth
+ *      window is formed like sppm.cpp:853-854 from gvpm_config.max_depth (-1 = unbounded) and min_depth.  The
+ *      sampler->next1D() draws are replaced by the counter-based hash of (rng_seed, px, py, edge, beam index, dimension);
+ *      the naive technique samples per sub-beam (dimension = 2 + 2*sub-beam ordinal, +1).
+ *      out: [n_rays*3] = sum of bRadQuery.Li * beam.weight, WITHOUT the 1 / shotParticles normalisation (:863).
+ *      counts (may be NULL): [n_rays*2] = {accepted (ray, beam) pairs - (ray, sub-beam) for the naive technique -,
+ *      same after the depth filters}. */
+enum gvpm_beam_technique {
+  GVPM_BEAM_1D = 0,          /* EBeamBeam1D */
+  GVPM_BEAM_3D_NAIVE = 1,    /* EBeamBeam3D_Naive */
+  GVPM_BEAM_3D_EGSR = 2,     /* EBeamBeam3D_EGSR */
+  GVPM_BEAM_3D_OPTIMIZED = 3 /* EBeamBeam3D_Optimized */
+};
+int gvpm_gather_sppm_beams(gvpm_ctx *ctx, int technique, float *out, uint32_t *counts);
+/* per-ray lists of accepted beam indices (bit 31 = passes the depth filters; one entry per accepted sub-beam for the
+ * naive technique), CSR like gvpm_dump_neighbours_bre */
+int gvpm_dump_neighbours_sppm_beams(gvpm_ctx *ctx, int technique, uint64_t *offsets, uint32_t *idx, size_t cap);
+
 /* Parity aid: neighbour index sets in CSR form.  offsets: [n_rays+1]; idx: capacity `cap`
  * entries, original photon index with bit 31 set when the photon also passes the depth /
  * interaction-mode / pathSet filters.  Returns GVPM_ERR_INVALID when cap is too small

@@ -60,6 +60,12 @@ def load():
                                          C.POINTER(N.Medium), C.POINTER(N.Config), C.c_float, C.c_int, N.f32p, N.u32p,
                                          N.u64p, N.u32p, C.c_size_t, C.POINTER(C.c_double)]
     lib.gvpm_oracle_sppm_bre.restype = C.c_longlong
+    lib.gvpm_oracle_sppm_beams.argtypes = [C.POINTER(N.BeamSoA), C.c_size_t, C.POINTER(N.RaySoA), C.c_size_t,
+                                           C.POINTER(N.Medium), C.POINTER(N.Config), C.c_float, C.c_int, C.c_int,
+                                           C.c_int, N.f32p, N.u32p, N.u64p, N.u32p, C.c_size_t]
+    lib.gvpm_oracle_sppm_beams.restype = C.c_longlong
+    lib.gvpm_oracle_subbeams.argtypes = [C.POINTER(N.BeamSoA), C.c_size_t, N.f32p, N.u32p, C.c_size_t]
+    lib.gvpm_oracle_subbeams.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -125,6 +131,49 @@ def beams_gather(beams, rays, medium, config, tri, radius, double=False, threads
     else:
         call(None, None, 0)
     return BreResult(out.reshape(rays.n, N.GVPM_OUT_FLOATS), counts.reshape(rays.n, 2), offsets, idx, ms.value, 0.0)
+
+
+BEAM_TECHNIQUES = {"beam1d": 0, "beam3d_naive": 1, "beam3d_egsr": 2, "beam3d": 3}
+
+
+def sppm_beams_gather(beams, rays, medium, config, radius, technique, double=False, threads=None, neighbours=False):
+    """Restated sppm primal beam gather (BeamRadianceQuery, beams.h:29-223; sppm.cpp:823-860), brute force over all
+    (camera beam, sub-beam) pairs.  technique: key of BEAM_TECHNIQUES.  Returns a BreResult with out [n_rays,3]."""
+    lib = load()
+    threads = hw_threads() if threads is None else threads
+    cb, cr = beams.as_c(), rays.as_c()
+    out = np.zeros(rays.n * 3, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    tech = BEAM_TECHNIQUES[technique] if isinstance(technique, str) else int(technique)
+
+    def call(offp, idxp, capv):
+        r = lib.gvpm_oracle_sppm_beams(C.byref(cb), beams.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                                       radius, tech, int(double), threads, out.ctypes.data_as(N.f32p),
+                                       counts.ctypes.data_as(N.u32p), offp, idxp, capv)
+        if r < 0:
+            raise RuntimeError(f"gvpm_oracle_sppm_beams failed: {r}")
+        return int(r)
+    offsets = idx = None
+    if neighbours:
+        offsets = np.zeros(rays.n + 1, dtype=np.uint64)
+        cap = call(offsets.ctypes.data_as(N.u64p), None, 0)
+        idx = np.zeros(max(cap, 1), dtype=np.uint32)
+        call(offsets.ctypes.data_as(N.u64p), idx.ctypes.data_as(N.u32p), cap)
+        idx = idx[:cap]
+    else:
+        call(None, None, 0)
+    return BreResult(out.reshape(rays.n, 3), counts.reshape(rays.n, 2), offsets, idx, 0.0, 0.0)
+
+
+def subbeams(beams):
+    """The reference's sub-beam split (beams_accel.h:98-124): (t12 [n,2] float32, beam [n] uint32)."""
+    lib = load()
+    cb = beams.as_c()
+    n = int(lib.gvpm_oracle_subbeams(C.byref(cb), beams.n, None, None, 0))
+    t12 = np.zeros(max(n, 1) * 2, dtype=np.float32)
+    bi = np.zeros(max(n, 1), dtype=np.uint32)
+    lib.gvpm_oracle_subbeams(C.byref(cb), beams.n, t12.ctypes.data_as(N.f32p), bi.ctypes.data_as(N.u32p), n)
+    return t12[:2 * n].reshape(n, 2), bi[:n]
 
 
 def hw_threads():

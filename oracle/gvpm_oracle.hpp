@@ -1070,6 +1070,103 @@ template <typename Real> struct Scene {
     return 2;
   }
 
+  // ---- sppm primal photon beams: BeamRadianceQuery::operator(), photonmapper/beams.h:29-223, driven as
+  // volumePhotonBeamPass (sppm.cpp:823-860); all four techniques of EVolumeTechnique (1D, 3D naive, 3D EGSR,
+  // 3D optimized).  One call = one (camera beam, sub-beam [tmin, tmax]) visit of SubBeamBVH::query
+  // (beams_accel.h:169-203).  `first` / `last` mark the beam's first / last sub-beam; `subIndex` its ordinal.
+  // The sampler->next1D() draws are replaced by the counter-based hash (dims 0,1 per (ray, beam); the naive
+  // technique samples per sub-beam: dims 2+2k, 3+2k).  Deviations: sub-beam ownership half-open
+  // as in the gvpm restatement; the naive branch, which the reference lets through without a camera range test
+  // (so that its result depends on which subtree boxes the ray happens to cross), gets the same
+  // [mint, maxt] test as the other two 3-D branches (:160-162).
+  // 0 = rejected, 1 = accepted but dropped by the depth filters (:34-39), 2 = contributes (Li += ...).
+  int sppmBeamFunctor(const CamRay<Real> &ray, const Beam &beam, uint32_t beamIndex, Real tmin, Real tmax, bool first,
+                      bool last, uint32_t subIndex, int technique, V3<Real> &Li) const {
+    if (tmax > beam.length) tmax = beam.length;                                          // :30-32
+    const int maxDepthQ = cfg.max_depth == -1 ? -1 : cfg.max_depth - ray.edgeId;         // sppm.cpp:853
+    const int minDepthQ = std::max(0, cfg.min_depth - ray.edgeId);                       // sppm.cpp:854
+    bool filtered = false;
+    if (maxDepthQ != -1 && beam.depth > maxDepthQ) filtered = true;
+    if (minDepthQ != 0 && beam.depth < minDepthQ) filtered = true;
+    const Real r = radius, eps = (Real)cfg.epsilon;
+    if (technique == GVPM_BEAM_1D) {                                                     // :41-68
+      Real u, v, w, sinTheta;
+      if (!beamIntersect1D(beam.o, beam.dir, beam.length, r, ray.o, ray.d, ray.mint, ray.maxt, first ? (Real)0 : tmin,
+                           last ? beam.length : tmax, u, v, w, sinTheta))
+        return 0;
+      if (r <= u) return 0;
+      if (filtered) return 1;
+      typename Medium<Real>::Rec mRecCamera = medium.eval(eps, w), mRec = medium.eval(0, v);
+      const Real weightKernel = (Real)0.5f / r;
+      V3<Real> beamContrib =
+          (((mRec.transmittance * mRecCamera.transmittance) * medium.sigmaS) * beam.flux) * medium.phase(-beam.dir, -ray.d);
+      if (!cfg.long_beams) {                                                            // getContrib, beams_struct.h:157-172
+        const bool tZero = mRec.transmittance.x == 0 && mRec.transmittance.y == 0 && mRec.transmittance.z == 0;
+        if (mRec.pdfFailure == 0 && !tZero) return 2;   // contributes Spectrum(0)
+        beamContrib = beamContrib / mRec.pdfFailure;
+      }
+      Li += ((beamContrib * weightKernel) / sinTheta) * ray.eye;
+      return 2;
+    }
+    Real beamSegmentRand, cameraSegmentRand, invPDF;
+    const Real radSqr = r * r;
+    if (technique == GVPM_BEAM_3D_NAIVE) {                                               // :77-102
+      const Real xi1 = beamUniform(ray, beamIndex, 2 + 2 * subIndex), xi2 = beamUniform(ray, beamIndex, 3 + 2 * subIndex);
+      beamSegmentRand = tmin + (tmax - tmin) * xi1;
+      invPDF = tmax - tmin;
+      const V3<Real> kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+      const Real distToProj = dot(kernelCentroid - ray.o, ray.d);
+      const Real distSqr = ((ray.o + distToProj * ray.d) - kernelCentroid).lengthSquared();
+      if (distSqr >= radSqr) return 0;
+      const Real deltaT = safe_sqrt(radSqr - distSqr);
+      cameraSegmentRand = (distToProj - deltaT) + 2 * deltaT * xi2;
+      invPDF = (Real)(invPDF * std::max(2.0 * deltaT, 0.0001));
+      if (cameraSegmentRand < ray.mint || cameraSegmentRand > ray.maxt) return 0;       // deviation, see above
+    } else {
+      const Real xi1 = beamUniform(ray, beamIndex, 0), xi2 = beamUniform(ray, beamIndex, 1);
+      const V3<Real> camStart = ray.o + ray.mint * ray.d;                                // _cam, :106-107
+      double tNearBeam, tFarBeam;
+      if (!cylinderIntersection(camStart, ray.d, ray.maxt - ray.mint, beam.o, beam.dir, beam.length, r, tNearBeam, tFarBeam))
+        return 0;
+      // ownership (:122-128) with half-open cuts: [tmin, tmax), the first sub-beam also takes tNear < 0
+      if (!((first || tNearBeam >= (double)tmin) && (last || tNearBeam < (double)tmax))) return 0;
+      if (!(tNearBeam < 0 || (tNearBeam > 0 && tNearBeam < beam.length))) return 0;
+      beamSegmentRand = (Real)(tNearBeam + (tFarBeam - tNearBeam) * xi1);
+      invPDF = (Real)std::max(tFarBeam - tNearBeam, 0.0001);
+      if (beamSegmentRand < 0 || beamSegmentRand > beam.length) return 0;
+      if (technique == GVPM_BEAM_3D_EGSR) {                                              // :138-150
+        double tNearCam, tFarCam;
+        if (!cylinderIntersection(beam.o, beam.dir, beam.length, camStart, ray.d, ray.maxt - ray.mint, r, tNearCam, tFarCam))
+          return 0;
+        cameraSegmentRand = (Real)(tNearCam + (tFarCam - tNearCam) * xi2);
+        invPDF = (Real)(invPDF * std::max(tFarCam - tNearCam, 0.0001));
+      } else {                                                                           // :151-170
+        const V3<Real> kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+        const Real distToProj = dot(kernelCentroid - ray.o, ray.d);
+        const Real distSqr = ((ray.o + distToProj * ray.d) - kernelCentroid).lengthSquared();
+        if (distSqr >= radSqr) return 0;
+        const Real deltaT = safe_sqrt(radSqr - distSqr);
+        cameraSegmentRand = distToProj - deltaT + 2 * deltaT * xi2;
+        invPDF = (Real)(invPDF * std::max(2.0 * deltaT, 0.0001));
+      }
+      if (cameraSegmentRand < ray.mint || cameraSegmentRand > ray.maxt) return 0;       // :173-175
+      if (technique == GVPM_BEAM_3D_EGSR) {                                              // :178-187
+        const V3<Real> kernelCentroid = beam.o + beam.dir * beamSegmentRand;
+        const Real distSqr = ((ray.o + cameraSegmentRand * ray.d) - kernelCentroid).lengthSquared();
+        if (distSqr >= radSqr) return 0;
+      }
+    }
+    if (filtered) return 1;
+    typename Medium<Real>::Rec mRecBeam = medium.eval(0, beamSegmentRand), mRecCamera = medium.eval(eps, cameraSegmentRand);
+    const Real phaseTerm = medium.phase(-beam.dir, -ray.d);
+    const Real kernelVol = (Real)((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3));
+    V3<Real> beamContrib =
+        ((((beam.flux * mRecBeam.transmittance) * medium.sigmaS) * mRecCamera.transmittance) * phaseTerm) * (invPDF / kernelVol);
+    if (!cfg.long_beams) beamContrib = beamContrib / mRecBeam.pdfFailure;                // :213-217
+    Li += beamContrib * ray.eye;                                                         // sppm.cpp:858
+    return 2;
+  }
+
   // ---- G-Planes 0D ("plane0d") -------------------------------------------------------------
   struct Plane {  // LTPhotonPlane, gvpm/gvpm_plane.h:18-46 + PhotonPlane, photonmapper/plane_struct.h:18-58
     V3<Real> ori, w0, w1, flux;
