@@ -7,10 +7,11 @@
 Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M photons per iteration,
 G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
 A step = accel build + gather of every camera-ray medium segment of the image (primal + 4 gradient
-contributions = 27 floats per ray).  N > 1: strong scaling — 32x32 image tiles dealt round-robin to
-the ranks; the iteration's photon set, of which every rank holds 1/N (what it uploaded over its own
-PCIe link), is all-gathered over NVLink via NCCL into every rank's staging buffer; every rank builds
-the hierarchy and gathers its tiles; results are gathered to rank 0 (north_star).  The photon
+contributions = 27 floats per ray).  N > 1: strong scaling — the 32x32 gather blocks are dealt to the ranks in
+column bands of the image (gvpm_b200/shard.py); the iteration's photon set, of which every rank holds 1/N (what it
+uploaded over its own PCIe link), is exchanged over NVLink into every rank's staging buffer (peer copies, or an NCCL
+all-gather); every rank builds its hierarchy over the photons its own rays can reach (gvpm_build_points_for_rays)
+and gathers its blocks; results are gathered to rank 0 (north_star).  The photon
 exchange of iteration k+1 is double-buffered behind the build + gather of iteration k (a renderer
 traces the next iteration's photons while the current one is gathered); the K timed steps contain
 K exchanges.  No other data-path collective.
@@ -99,10 +100,14 @@ def make_inputs(args, rank, world, pin=True):
     # 32x32 gather blocks like the reference (gvpm.cpp:271-290), walked in Z-order inside a block so that
     # consecutive rays are 2x2 pixel quads (the traversal kernel packets 4 consecutive rays)
     full = g.synth_rays(w, h, seed=seed + 1, block=-32)
-    # 32x32 tiles (block-major order from the generator) dealt round-robin to the ranks
-    tiles_x = (w + 31) // 32
-    tile_id = (full.py // 32) * tiles_x + (full.px // 32)
-    mine = np.nonzero(tile_id % world == rank)[0]
+    # 32x32 gather blocks -> ranks.  "band" (default): column bands of the image, dealt cyclically, so that a rank's
+    # rays cross only a few wedges of the scene and gvpm_build_points_for_rays can leave the rest of the photon set out
+    # of that rank's hierarchy; "tile": round robin over the blocks (every rank sees the whole scene).
+    from gvpm_b200 import shard
+    if shard_mode(world) == "band":
+        mine = shard.band_indices(full.px, full.py, w, h, world, rank, band_cycles())
+    else:
+        mine = shard.local_indices(full.px, full.py, w, world, rank)
     sub = full.take(mine)
     rays = R.RaySet(sub.n, **alloc(R._RAY_FIELDS, sub.n))
     for name, _, _ in R._RAY_FIELDS:
@@ -111,6 +116,19 @@ def make_inputs(args, rank, world, pin=True):
     return dict(w=w, h=h, n_ph=n_ph, scale=scale, medium=medium, photons=photons, n_paths=int(n_paths),
                 rays=rays, rays_full_n=full.n, cfg=cfg, tri=g.synth_occluders(), radius=g.bre_radius(scale),
                 keep=keep, full_rays=full if (rank == 0) else None)
+
+
+def shard_mode(world):
+    return os.environ.get("GVPM_SHARD", "band") if world > 1 else "tile"
+
+
+def band_cycles():
+    return int(os.environ.get("GVPM_BAND_CYCLES", "2"))
+
+
+def prune_build(world):
+    """value leg: build the hierarchy only over the photons this rank's rays can reach (N > 1, band sharding)"""
+    return world > 1 and shard_mode(world) == "band" and os.environ.get("GVPM_PRUNE", "1") != "0"
 
 
 class ClockSampler:
@@ -266,8 +284,12 @@ def workload_config(args, inp, world):
     return {"workload": f"{args.workload}: {inp['w']}x{inp['h']} homogeneous-medium Cornell box, "
                         f"{inp['n_ph']} photons/iteration, gvpm G-BRE 3D kernel, mixed shift, area MIS, pathSet",
             "rays": inp["rays_full_n"], "photons": inp["n_ph"], "initialScaleVolume": inp["scale"],
-            "radius": inp["radius"], "parallelism": f"image tiles (32x32) round-robin over {world} GPU(s), "
-                                                    "photon set broadcast, results gathered to rank 0",
+            "radius": inp["radius"],
+            "parallelism": (f"32x32 gather blocks in {band_cycles()} column bands per GPU over {world} GPU(s), "
+                            "photon set exchanged to every GPU, each hierarchy built over the photons its bands "
+                            "reach, results gathered to rank 0" if shard_mode(world) == "band" else
+                            f"image tiles (32x32) round-robin over {world} GPU(s), photon set broadcast, results "
+                            "gathered to rank 0"),
             "l2": "inputs larger than L2 (photon records 1.1 GB, rays 0.66 GB): no flush needed"}
 
 
@@ -511,6 +533,14 @@ def main():
         if world > 1:
             dist.gather(out_dev, gathered, dst=0)
 
+    kept = [n_ph]
+
+    def build_resident():
+        if prune_build(world):
+            kept[0] = ctx.build_points_for_rays(inp["radius"])
+        else:
+            ctx.build_points(inp["radius"])
+
     def step_resident(k):
         """value leg: (photon all-gather of step k+1 in flight) + build + gather (+ result gather)"""
         b = k & 1
@@ -520,7 +550,7 @@ def main():
         ctx.photon_staging_select(b)
         ctx.photon_staging(n_ph)
         with torch.cuda.stream(stream):
-            ctx.build_points(inp["radius"])
+            build_resident()
             ctx.gather_bre_into(out_dev.data_ptr(), None)
             collect()
         host_barrier()
@@ -584,7 +614,7 @@ def main():
 
     def step_plain():
         with torch.cuda.stream(stream):
-            ctx.build_points(inp["radius"])
+            build_resident()
             ctx.gather_bre_into(out_dev.data_ptr(), None)
     if os.environ.get("GVPM_BENCH_DIAG"):
         diag_phases(locals())
@@ -604,9 +634,17 @@ def main():
     ctx.sync()
     h_geom = torch.tensor([int(cnt_dev.view(-1, 2)[:n_local, 0].to(torch.int64).sum().item())], device="cuda")
     gk = torch.tensor([gather_ms], device="cuda", dtype=torch.float64)
+    bk = torch.tensor([build_ms], device="cuda", dtype=torch.float64)
+    kept_t = torch.tensor([kept[0], n_local], device="cuda", dtype=torch.int64)
+    kept_all = [torch.empty_like(kept_t) for _ in range(world)]
     if world > 1:
         dist.all_reduce(h_geom)
         dist.all_reduce(gk, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bk, op=dist.ReduceOp.MAX)
+        dist.all_gather(kept_all, kept_t)
+    else:
+        kept_all = [kept_t]
+    build_ms = float(bk.item())
 
     if rank == 0:
         R = inp["rays_full_n"]
@@ -648,6 +686,10 @@ def main():
                                      "bytes (profiles/), the HBM fraction is reported as the contract asks"},
                 "phases_ms": {"build": build_ms, "gather": float(gk.item()), "traverse": trav_ms,
                               "shade": shade_ms},
+                "shards": {"mode": shard_mode(world), "band_cycles": band_cycles() if shard_mode(world) == "band" else None,
+                           "pruned_build": prune_build(world),
+                           "rays_per_rank": [int(k[1].item()) for k in kept_all],
+                           "photons_in_hierarchy_per_rank": [int(k[0].item()) for k in kept_all]},
                 "light_paths": inp["n_paths"]}
         if world == 1 and not args.no_cpu_baseline:
             inp["full_rays"] = inp["rays"]
@@ -657,7 +699,7 @@ def main():
     # tensors allocated on the context's stream must go before the stream does
     # (device tensors and pinned host buffers that were used on it record events on that stream when
     # they are freed)
-    del out_dev, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk
+    del out_dev, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk, bk, kept_t, kept_all
     del out_host_t, out_host, rays
     inp.clear()
     import gc

@@ -106,6 +106,13 @@ class Context:
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 
+    def build_points_for_rays(self, radius):
+        """Hierarchy over the photons the uploaded rays can reach only; -> number of photons kept."""
+        kept = C.c_uint32(0)
+        self._ck(self.lib.gvpm_build_points_for_rays(self.h, C.c_float(radius), C.byref(kept)),
+                 "gvpm_build_points_for_rays")
+        return int(kept.value)
+
     # ---- rays
     def upload_rays(self, rays):
         cs = rays.as_c()

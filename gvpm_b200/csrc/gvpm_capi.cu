@@ -17,6 +17,15 @@ int bounds_blocks(uint32_t n);
 void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st);
 void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st);
+size_t ray_grid_bytes();
+size_t ray_mask_bytes();
+void launch_ray_region(const float4 *rays, uint32_t nRays, float radius, float *box, void *grid, uint32_t *mask,
+                       float *bounds, int sm_count, cudaStream_t st);
+void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *vals,
+                        uint32_t *keepmask, uint32_t *counter, cudaStream_t st);
+void launch_keys_kept(const float *pos, const uint32_t *vals, uint32_t m, const void *grid, uint32_t *keys, cudaStream_t st);
+void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
+                        float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st);
 void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sorted, uint32_t n, float4 *planes,
                         uint32_t *orig, cudaStream_t st);
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
@@ -104,6 +113,12 @@ struct gvpm_ctx {
   float radius = 0.f;
   bool built = false;
   float extent_hint = 1.f;  // diagonal of the photon AABB (host copy, refreshed lazily)
+  // gvpm_build_points_for_rays: occupancy grid of the uploaded rays; the hierarchy then holds only the photons they can
+  // reach and is valid for that ray set (rays_gen) alone
+  DevBuf ray_region;        // [0,32): ray box, [32,64): kept-photon counter, [64,..): RayGrid, the 32 KB cell mask, one keep bit per photon
+  uint64_t rays_gen = 0, pruned_for_gen = 0;
+  bool pruned = false;
+  uint32_t n_kept = 0;
 
   DevBuf ray_staging, rays;
   uint32_t n_rays = 0;
@@ -216,6 +231,8 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
   if (!ctx->built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points has not been called");
   if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
+  if (ctx->pruned && ctx->pruned_for_gen != ctx->rays_gen)
+    return fail(ctx, GVPM_ERR_INVALID, "the hierarchy was built by gvpm_build_points_for_rays for another ray set: rebuild");
   memset(&P, 0, sizeof(P));
   P.tree = ctx->tree;
   P.planes = ctx->planes.as<float4>();
@@ -384,7 +401,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->samples, &ctx->sample_counts, &ctx->mvol, &ctx->beams, &ctx->beam_bounds, &ctx->sub_pos,
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
-                    &ctx->plane_bounds};
+                    &ctx->plane_bounds, &ctx->ray_region};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
   for (auto &ev : ctx->push_ev) if (ev) cudaEventDestroy(ev);
@@ -701,6 +718,96 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
   ctx->tree = T;
   ctx->radius = radius;
   ctx->built = true;
+  ctx->pruned = false;
+  ctx->n_kept = n;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->timed_build = true;
+  return GVPM_OK;
+}
+
+// Same hierarchy, over the photons the uploaded rays can reach only (tree_build.cu, "ray-region pruning").
+int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (!ctx->photons_loaded) return fail(ctx, GVPM_ERR_INVALID, "no photons uploaded");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points_for_rays needs the rays first (gvpm_upload_rays)");
+  if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->n_photons;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  const size_t gridOff = 64, maskOff = align256(gridOff + ray_grid_bytes()), keepOff = align256(maskOff + ray_mask_bytes());
+  CK(ctx->ray_region.reserve(keepOff + 4 * ((size_t)n / 32 + 1)));
+  char *rr = ctx->ray_region.as<char>();
+  float *box = (float *)rr;
+  uint32_t *counter = (uint32_t *)(rr + 32);
+  uint32_t *mask = (uint32_t *)(rr + maskOff), *keepmask = (uint32_t *)(rr + keepOff);
+  const float boxInit[8] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.f, 0.f};
+  CK(cudaMemcpyAsync(box, boxInit, sizeof(boxInit), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(counter, 0, 32, st));
+  CK(cudaMemsetAsync(mask, 0, ray_mask_bytes(), st));
+  launch_ray_region(ctx->rays.as<float4>(), ctx->n_rays, radius, box, rr + gridOff, mask, ctx->bounds.as<float>(),
+                    ctx->sm_count, st);
+  ctx->launches += ctx->n_rays ? 3 : 1;
+  uint32_t kept = 0;
+  if (n > 0) {
+    CK(ctx->keys_in.reserve(8 * (size_t)n));
+    CK(ctx->keys_out.reserve(8 * (size_t)n));
+    CK(ctx->vals_in.reserve(4 * (size_t)n));
+    CK(ctx->vals_out.reserve(4 * (size_t)n));
+    CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
+    CK(ctx->planes.reserve(16 * (size_t)n));
+    CK(ctx->orig.reserve(4 * (size_t)n));
+    CK(ctx->aos.reserve(128 * (size_t)n));
+    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    launch_keep_pruned(S.pos, n, rr + gridOff, mask, ctx->vals_in.as<uint32_t>(), keepmask, counter, st);
+    ctx->launches += 1;
+    // the number of kept photons sizes the sort and the hierarchy levels: one 4-byte read-back
+    CK(cudaMemcpyAsync(ctx->pair_count_host, counter, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    kept = *(const uint32_t *)ctx->pair_count_host;
+  }
+  Tree T{};
+  T.n = kept;
+  uint32_t cnt = (kept + 31) / 32, total = 0;
+  int levels = 0;
+  if (kept > 0) {
+    for (;;) {
+      T.cnt[levels] = cnt;
+      T.off[levels] = total;
+      total += cnt;
+      ++levels;
+      if (cnt <= 32) break;
+      if (levels >= GVPM_MAX_LEVELS) return fail(ctx, GVPM_ERR_INVALID, "too many photons");
+      cnt = (cnt + 31) / 32;
+    }
+  }
+  T.levels = levels;
+  if (kept > 0) {
+    CK(ctx->box_lo.reserve(16 * (size_t)total));
+    CK(ctx->box_hi.reserve(16 * (size_t)total));
+    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    launch_keys_kept(S.pos, ctx->vals_in.as<uint32_t>(), kept, rr + gridOff, ctx->keys_in.as<uint32_t>(), st);
+    CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
+                ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), kept, st));
+    launch_pack_pruned(S, n, keepmask, ctx->vals_out.as<uint32_t>(), kept, ctx->aos.as<float4>(),
+                       ctx->planes.as<float4>(), ctx->orig.as<uint32_t>(), st);
+    float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
+    launch_leaf_boxes(ctx->planes.as<float4>(), kept, T.cnt[0], radius, lo, hi, st);
+    for (int l = 1; l < levels; ++l)
+      launch_level_boxes(lo + T.off[l - 1], hi + T.off[l - 1], T.cnt[l - 1], T.cnt[l], lo + T.off[l], hi + T.off[l], st);
+    ctx->launches += 4 + (levels - 1) + 4;
+    CK(cudaGetLastError());
+  }
+  if (n > 0) CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
+  T.lo = ctx->box_lo.as<float4>();
+  T.hi = ctx->box_hi.as<float4>();
+  ctx->tree = T;
+  ctx->radius = radius;
+  ctx->built = true;
+  ctx->pruned = true;
+  ctx->pruned_for_gen = ctx->rays_gen;
+  ctx->n_kept = kept;
+  if (n_kept) *n_kept = kept;
   CK(cudaEventRecord(ctx->ev[1], st));
   ctx->timed_build = true;
   return GVPM_OK;
@@ -713,6 +820,7 @@ int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   CK(ctx->ray_staging.reserve(L.bytes ? L.bytes : 256));
   ctx->n_rays = (uint32_t)n;
   ctx->rays_loaded = false;
+  ++ctx->rays_gen;
   if (dev) *dev = ctx->ray_staging.p;
   if (bytes) *bytes = L.bytes;
   return GVPM_OK;

@@ -6,6 +6,8 @@
 // packed into 128-byte records (streaming) -> records gathered into Morton-ordered 128-bit planes (every
 // random read is one aligned 128-byte record) -> bottom-up 32-ary box levels (one warp per node, shuffle
 // reductions).
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gvpm_device.cuh"
@@ -224,6 +226,236 @@ __global__ void k_level_boxes(const float4 *__restrict__ clo, const float4 *__re
   }
 }
 
+// ---- ray-region pruning (gvpm_build_points_for_rays) ---------------------------------------------------------------
+// When the image is sharded over GPUs a rank gathers only its own camera rays, which cross only a part of the
+// scene; photons that no uploaded ray can reach need neither be sorted nor boxed.  The ray segments, dilated by the
+// search radius, mark the cells of a 64^3 occupancy grid over their own bounding box; the key pass drops every photon
+// whose cell is unmarked.  Conservative by construction (see k_ray_mask), so the gather is unchanged: a dropped
+// photon fails the neighbour predicate (gvpm_accel.h:297-301) for every uploaded ray.
+constexpr int kGridRes = 64;                                  // cells per axis
+constexpr int kGridWords = kGridRes * kGridRes * kGridRes / 32;  // 8192 words = 32 KB: fits a CTA's shared memory
+struct RayGrid {       // device-resident, written by k_ray_box_final
+  float lo[3], hi[3];  // grid box = AABB of the dilated ray segments
+  float inv[3];        // cells per unit length
+  float cmin, cmax;    // smallest / largest cell edge
+  float mag;           // largest |coordinate| of the box (rounding slack)
+  int valid;           // 0: no ray
+};
+
+__device__ __forceinline__ void atomic_min_float(float *a, float v) {
+  if (v >= 0.f) atomicMin((int *)a, __float_as_int(v)); else atomicMax((unsigned *)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float *a, float v) {
+  if (v >= 0.f) atomicMax((int *)a, __float_as_int(v)); else atomicMin((unsigned *)a, __float_as_uint(v));
+}
+// the part of ray i's supporting line that can hold the projection of a neighbour: t in [-r, edge_len + r]
+// (the 3-D kernel samples t' in [disk - r, disk + r] and needs mint <= t' <= edge_len, shift_volume_photon.cpp:707-721)
+__device__ __forceinline__ bool ray_segment(const float4 *__restrict__ rays, uint32_t i, float r, float p0[3], float p1[3]) {
+  const float4 q0 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4), q1 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 1),
+               q2 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 2);
+  const float t0 = -r, t1 = q2.w + r;
+  p0[0] = q0.x + q1.x * t0; p0[1] = q0.y + q1.y * t0; p0[2] = q0.z + q1.z * t0;
+  p1[0] = q0.x + q1.x * t1; p1[1] = q0.y + q1.y * t1; p1[2] = q0.z + q1.z * t1;
+  return q2.w >= q0.w;   // edge_len >= mint: the gather skips the others
+}
+__global__ void k_ray_box(const float4 *__restrict__ rays, uint32_t n, float r, float *__restrict__ box) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float p0[3], p1[3];
+    if (!ray_segment(rays, i, r, p0, p1)) continue;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fminf(lo[a], fminf(p0[a], p1[a]));
+      hi[a] = fmaxf(hi[a], fmaxf(p0[a], p1[a]));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (lo[a] <= hi[a]) { atomic_min_float(box + a, lo[a]); atomic_max_float(box + 3 + a, hi[a]); }
+    }
+  }
+}
+// box[0..5] -> grid parameters + the 7-float bounds block the traversal reads (min, max, max |coordinate|)
+__global__ void k_ray_box_final(const float *__restrict__ box, float r, RayGrid *__restrict__ g, float *__restrict__ bounds) {
+  RayGrid G;
+  G.valid = box[0] <= box[3] && box[1] <= box[4] && box[2] <= box[5];
+  float mag = 0.f, cmin = INFINITY, cmax = 0.f;
+  for (int a = 0; a < 3; ++a) {
+    float lo = G.valid ? box[a] : 0.f, hi = G.valid ? box[3 + a] : 0.f;
+    const float pad = 1.01f * r + 1e-5f * (fabsf(lo) + fabsf(hi) + (hi - lo)) + 1e-30f;
+    lo -= pad; hi += pad;
+    G.lo[a] = lo; G.hi[a] = hi;
+    const float c = (hi - lo) / kGridRes;
+    G.inv[a] = 1.f / c;
+    cmin = fminf(cmin, c);
+    cmax = fmaxf(cmax, c);
+    mag = fmaxf(mag, fmaxf(fabsf(lo), fabsf(hi)));
+  }
+  G.cmin = cmin; G.cmax = cmax; G.mag = mag;
+  *g = G;
+  for (int a = 0; a < 3; ++a) { bounds[a] = G.lo[a]; bounds[3 + a] = G.hi[a]; }
+  bounds[6] = mag;
+}
+__device__ __forceinline__ int grid_cell(const RayGrid &G, int a, float x) {
+  const int c = (int)floorf((x - G.lo[a]) * G.inv[a]);
+  return min(max(c, 0), kGridRes - 1);
+}
+// mark every cell that meets the cube [p - h, p + h] in the CTA's shared mask
+__device__ __forceinline__ void mark_cube(uint32_t *mask, const RayGrid &G, const float p[3], float h) {
+  const int x0 = grid_cell(G, 0, p[0] - h), x1 = grid_cell(G, 0, p[0] + h);
+  const int y0 = grid_cell(G, 1, p[1] - h), y1 = grid_cell(G, 1, p[1] + h);
+  const int z0 = grid_cell(G, 2, p[2] - h), z1 = grid_cell(G, 2, p[2] + h);
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y) {
+      const int row = (z * kGridRes + y) * (kGridRes / 32);
+      for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+        const int b0 = max(x0 - 32 * w, 0), b1 = min(x1 - 32 * w, 31);
+        const uint32_t bits = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
+        if ((mask[row + w] & bits) != bits) atomicOr(mask + row + w, bits);
+      }
+    }
+}
+// One warp per 32 consecutive rays (neighbouring pixels: gvpm_upload_rays keeps the caller's block order).  Any point
+// within r of a segment lies within r + s/2 of one of its samples spaced s apart, hence inside the sample's cube of
+// half-width h >= r + s/2; cell indices are monotone in the coordinate, so a photon inside the cube falls in a marked
+// cell.  Coherent warps mark only the first ray's segment, dilated by the largest end-point distance to the other
+// segments (points at equal fractions of two segments are never farther apart than the farther pair of end points).
+__global__ void __launch_bounds__(256) k_ray_mask(const float4 *__restrict__ rays, uint32_t n, float r,
+                                                   const RayGrid *__restrict__ gp, uint32_t *__restrict__ gmask) {
+  __shared__ uint32_t mask[kGridWords];
+  for (int w = threadIdx.x; w < kGridWords; w += blockDim.x) mask[w] = 0u;
+  __syncthreads();
+  const RayGrid G = *gp;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nWarpJobs = (n + 31) / 32, warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); G.valid && job < nWarpJobs; job += warpsPerGrid) {
+    const uint32_t i = job * 32 + lane;
+    float p0[3] = {0.f, 0.f, 0.f}, p1[3] = {0.f, 0.f, 0.f};
+    const bool act = i < n && ray_segment(rays, i, r, p0, p1);
+    const uint32_t am = __ballot_sync(0xffffffffu, act);
+    if (am == 0u) continue;
+    const int c = __ffs(am) - 1;
+    float c0[3], c1[3], spread = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { c0[a] = __shfl_sync(0xffffffffu, p0[a], c); c1[a] = __shfl_sync(0xffffffffu, p1[a], c); }
+    if (act) {
+      const float ax = p0[0] - c0[0], ay = p0[1] - c0[1], az = p0[2] - c0[2];
+      const float bx = p1[0] - c1[0], by = p1[1] - c1[1], bz = p1[2] - c1[2];
+      spread = fmaxf(sqrtf(ax * ax + ay * ay + az * az), sqrtf(bx * bx + by * by + bz * bz));
+    }
+    for (int o = 16; o > 0; o >>= 1) spread = fmaxf(spread, __shfl_xor_sync(0xffffffffu, spread, o));
+    // (a bundle a few cells wide: the rays of a pixel patch fill the dilated region anyway, so nothing is over-marked)
+    const bool coherent = spread <= 4.f * G.cmax;
+    if (coherent) {  // all lanes work on the first segment
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { p0[a] = c0[a]; p1[a] = c1[a]; }
+    }
+    if (!coherent && !act) continue;
+    const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    const int nS = min(128, (int)ceilf(len / G.cmin) + 2);
+    const float s = len / (float)(nS - 1);
+    const float h = (r + (coherent ? spread * 1.001f : 0.f) + 0.5f * s) * 1.002f + 4e-6f * (G.mag + len);
+    for (int k = coherent ? lane : 0; k < nS; k += coherent ? 32 : 1) {
+      const float u = (float)k / (float)(nS - 1);
+      const float p[3] = {p0[0] + dx * u, p0[1] + dy * u, p0[2] + dz * u};
+      mark_cube(mask, G, p, h);
+    }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < kGridWords; w += blockDim.x)
+    if (mask[w]) atomicOr(gmask + w, mask[w]);
+}
+// Pass 1 over all photons: keep test (cell of the photon marked?) and compaction of the kept indices with one atomic per
+// CTA; keepmask gets one bit per photon (word = 32 consecutive photons) for the record packing pass.  Memory-bound: the
+// Hilbert keys are computed afterwards, for the kept photons only (k_keys_kept).
+__global__ void __launch_bounds__(256) k_keep_pruned(const float *__restrict__ pos, uint32_t n, const RayGrid *__restrict__ gp,
+                              const uint32_t *__restrict__ gmask, uint32_t *__restrict__ vals,
+                              uint32_t *__restrict__ keepmask, uint32_t *__restrict__ counter) {
+  __shared__ uint32_t warpCount[8], blockBase;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  bool keep = false;
+  if (i < n) {
+    const RayGrid &G = *gp;
+    const float x = pos[3 * (size_t)i], y = pos[3 * (size_t)i + 1], z = pos[3 * (size_t)i + 2];
+    if (G.valid && x >= G.lo[0] && x <= G.hi[0] && y >= G.lo[1] && y <= G.hi[1] && z >= G.lo[2] && z <= G.hi[2]) {
+      const int cx = grid_cell(G, 0, x), cy = grid_cell(G, 1, y), cz = grid_cell(G, 2, z);
+      const uint32_t bit = (uint32_t)((cz * kGridRes + cy) * kGridRes + cx);
+      keep = (__ldg(gmask + (bit >> 5)) >> (bit & 31u)) & 1u;
+    }
+  }
+  const uint32_t km = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) {
+    warpCount[w] = __popc(km);
+    if (i < n) keepmask[i >> 5] = km;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t c = warpCount[k]; warpCount[k] = tot; tot += c; }
+    blockBase = tot ? atomicAdd(counter, tot) : 0u;
+  }
+  __syncthreads();
+  if (keep) vals[blockBase + warpCount[w] + __popc(km & ((1u << lane) - 1u))] = i;
+}
+// Pass 2 over the m kept photons: 30-bit Hilbert key, quantised in the grid box
+__global__ void k_keys_kept(const float *__restrict__ pos, const uint32_t *__restrict__ vals, uint32_t m,
+                            const RayGrid *__restrict__ gp, uint32_t *__restrict__ keys) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= m) return;
+  const RayGrid &G = *gp;
+  const size_t i3 = 3 * (size_t)vals[slot];
+  uint32_t q[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float u = (__ldg(pos + i3 + a) - G.lo[a]) / (G.hi[a] - G.lo[a]);
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    q[a] = min((uint32_t)(u * 1024.f), 1023u);
+  }
+  keys[slot] = hilbert30(q[0], q[1], q[2]);
+}
+// k_pack_aos for the kept photons only: same streaming layout (the photon set arrives in the caller's order, so the kept
+// ones are scattered evenly), loads and the transposed stores predicated by the keep bits
+__global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, uint32_t n, const uint32_t *__restrict__ keepmask,
+                                                        float4 *__restrict__ aos) {
+  __shared__ float4 tile[8][32 * 9];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t warpBase = blockIdx.x * blockDim.x + (w << 5);
+  if (warpBase >= n) return;
+  const uint32_t km = __ldg(keepmask + (warpBase >> 5));
+  if (km == 0u) return;
+  const uint32_t s = warpBase + lane;
+  float4 *t = tile[w];
+  if (km >> lane & 1u) {
+    const size_t s3 = 3 * (size_t)s;
+    auto ld3 = [&](const float *p, float ww) { return make_float4(__ldg(p + s3), __ldg(p + s3 + 1), __ldg(p + s3 + 2), ww); };
+    const uint32_t meta = pack_meta(S.parent_type[s], S.depth[s], S.path_id[s]);
+    float4 *r = t + lane * 9;
+    r[0] = ld3(S.pos, __uint_as_float(meta));
+    r[1] = ld3(S.flux, __ldg(S.parent_pdf + s));
+    r[2] = ld3(S.parent_pos, __ldg(S.edge_pdf + s));
+    r[3] = ld3(S.pred_pos, __ldg(S.rr_weight + s));
+    r[4] = ld3(S.parent_n, 0.f);
+    r[5] = ld3(S.prefix_flux, 0.f);
+    r[6] = ld3(S.parent_albedo, 0.f);
+    r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  float4 *dst = aos + (size_t)warpBase * GVPM_AOS_FLOAT4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t q = 32u * j + lane;          // float4 index inside the warp's 4 KB of records
+    if (km >> (q >> 3) & 1u) dst[q] = t[(q >> 3) * 9 + (q & 7u)];
+  }
+}
+
 // raw ray SoA -> 5 x 64 B records per ray
 __global__ void k_pack_rays(const RayStaging S, uint32_t r0, uint32_t n, float4 *__restrict__ rays) {
   const uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,6 +509,32 @@ void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sor
                         uint32_t *orig, cudaStream_t st) {
   k_pack_aos<<<(n + 255) / 256, 256, 0, st>>>(S, n, aos);
   k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(aos, sorted, n, planes, orig);
+}
+size_t ray_grid_bytes() { return sizeof(RayGrid); }
+size_t ray_mask_bytes() { return (size_t)kGridWords * 4; }
+// box: 6 floats (+inf x3, -inf x3 on entry); grid: RayGrid; mask: zeroed kGridWords words; counter: zeroed
+void launch_ray_region(const float4 *rays, uint32_t nRays, float radius, float *box, void *grid, uint32_t *mask,
+                       float *bounds, int sm_count, cudaStream_t st) {
+  if (nRays) k_ray_box<<<std::min<uint32_t>((nRays + 255) / 256, 1024u), 256, 0, st>>>(rays, nRays, radius, box);
+  k_ray_box_final<<<1, 1, 0, st>>>(box, radius, (RayGrid *)grid, bounds);
+  if (nRays) {
+    const uint32_t need = (nRays + 255) / 256;
+    k_ray_mask<<<std::min<uint32_t>(need, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, nRays, radius, (const RayGrid *)grid, mask);
+  }
+}
+void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *vals,
+                        uint32_t *keepmask, uint32_t *counter, cudaStream_t st) {
+  if (n) k_keep_pruned<<<(n + 255) / 256, 256, 0, st>>>(pos, n, (const RayGrid *)grid, mask, vals, keepmask, counter);
+}
+void launch_keys_kept(const float *pos, const uint32_t *vals, uint32_t m, const void *grid, uint32_t *keys, cudaStream_t st) {
+  if (m) k_keys_kept<<<(m + 255) / 256, 256, 0, st>>>(pos, vals, m, (const RayGrid *)grid, keys);
+}
+// records of the kept photons (caller's order) + sorted position plane / index map of the m kept ones
+void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
+                        float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st) {
+  if (!m) return;
+  k_pack_aos_kept<<<(n + 255) / 256, 256, 0, st>>>(S, n, keepmask, aos);
+  k_gather_sorted<<<(m + 255) / 256, 256, 0, st>>>(aos, sorted, m, planes, orig);
 }
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st) {

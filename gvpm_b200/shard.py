@@ -20,6 +20,25 @@ def local_indices(px, py, width, world, rank, block=BLOCK):
     return np.nonzero(tile_owner(px, py, width, world, block) == rank)[0]
 
 
+def band_owner(px, py, width, height, world, cycles=2, block=BLOCK):
+    """Rank owning each ray under the column-band partition: the gather blocks, numbered column-major, are cut into
+    cycles*world runs of (almost) equal block count - vertical bands of the image - and run j goes to rank
+    j % world.  A rank's rays then cross only `cycles` wedges of the scene, which is what lets
+    gvpm_build_points_for_rays leave most of the photon set out of that rank's hierarchy, while the cyclic
+    deal pairs a band near the image centre with one near the edge (load balance under a centre-weighted
+    photon density).  cycles*world == number of blocks degenerates into tile_owner's round-robin deal."""
+    tiles_x = (width + block - 1) // block
+    tiles_y = (height + block - 1) // block
+    n_tiles = tiles_x * tiles_y
+    runs = max(1, min(n_tiles, cycles * world))
+    t = (np.asarray(px) // block).astype(np.int64) * tiles_y + (np.asarray(py) // block)
+    return (t * runs // n_tiles) % world
+
+
+def band_indices(px, py, width, height, world, rank, cycles=2, block=BLOCK):
+    return np.nonzero(band_owner(px, py, width, height, world, cycles, block) == rank)[0]
+
+
 def assemble(parts, index_lists, n_total, width=27):
     """Scatter per-rank result rows back to the global ray order.  parts[r]: [>=len(idx_r), width]."""
     out = np.zeros((n_total, width), dtype=np.float32)

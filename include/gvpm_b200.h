@@ -260,6 +260,15 @@ int gvpm_peer_wait_photons(gvpm_ctx *ctx, int which);
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
 
+/* gvpm_build_points restricted to the photons the currently uploaded rays can reach (call gvpm_upload_rays first).
+ * Meant for image-tile sharding over GPUs: a rank that gathers only its own tiles' rays sorts and
+ * boxes only the part of the photon set those rays cross.  The ray segments, dilated by `radius`, mark the cells of a
+ * 64^3 occupancy grid over their bounding box; photons in unmarked cells are left out.  Conservative: the left-out
+ * photons fail the neighbour predicate (gvpm_accel.h:297-301) of every uploaded ray, so every gather returns what
+ * it returns after gvpm_build_points.  The hierarchy is valid for this ray set only - the gathers fail with
+ * GVPM_ERR_INVALID once other rays are uploaded, until the next build.  n_kept (may be NULL): photons kept. */
+int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept);
+
 /* ---- camera rays --------------------------------------------------------------------- */
 int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n);
 /* same idea for rays: staging buffer (16 SoA arrays, 256-byte aligned, field order of

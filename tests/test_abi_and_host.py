@@ -123,6 +123,31 @@ def test_tile_sharding_partitions_every_ray_once():
     assert img.shape == (h, w, 27) and img[3, 5, 0] == 3 * w + 5
 
 
+def test_band_sharding_partitions_every_ray_once_in_compact_bands():
+    from gvpm_b200 import shard
+    w, h = 1920, 1080
+    py, px = np.mgrid[0:h:8, 0:w:8]          # one ray per 8x8 pixels is enough to see every block
+    px, py = px.ravel(), py.ravel()
+    for world in (1, 2, 4, 8):
+        for cycles in (1, 2, 4):
+            owner = shard.band_owner(px, py, w, h, world, cycles)
+            sizes = np.bincount(owner, minlength=world)
+            assert sizes.sum() == px.size and sizes.min() > 0
+            # equal block counts up to one block per run (the last block row / column is partial)
+            assert sizes.max() - sizes.min() <= (cycles + 1) * 16 + 0.03 * sizes.mean()
+            seen = np.zeros(px.size, dtype=int)
+            for r in range(world):
+                idx = shard.band_indices(px, py, w, h, world, r, cycles)
+                seen[idx] += 1
+                # a rank's rays lie in at most cycles + 1 vertical bands: few distinct block columns
+                cols = np.unique(px[idx] // 32)
+                assert len(cols) <= (60 // (cycles * world) + 2) * cycles
+            assert (seen == 1).all()
+    # degenerate deal: one run per block = round robin over the column-major block list
+    o = shard.band_owner(px, py, w, h, 2, cycles=60 * 34)
+    assert set(np.unique(o)) == {0, 1}
+
+
 GLOO_WORKER = r"""
 import os, sys
 import numpy as np
