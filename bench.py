@@ -122,6 +122,12 @@ def shard_mode(world):
     return os.environ.get("GVPM_SHARD", "band") if world > 1 else "tile"
 
 
+def default_push_ctas(world):
+    """photon exchange: the copy engines keep up with one or two peers; beyond that the many-small-copies pattern
+    (13 fields x N-1 peers) tops out near 220 GB/s per GPU and a 12-CTA store kernel takes over (profiles/r1j)"""
+    return 12 if world > 2 else 0
+
+
 def band_cycles():
     return int(os.environ.get("GVPM_BAND_CYCLES", "2"))
 
@@ -468,6 +474,8 @@ def main():
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         host_pg = dist.new_group(backend="gloo")   # host-side ordering of the interprocess event records / waits
+        push_ctas = int(os.environ.get("GVPM_PUSH_CTAS", str(default_push_ctas(world))))
+        ctx.peer_push_mode(push_ctas)
         if int(ok.item()) == 0:
             exchange, host_pg = "nccl", None
     if exchange == "nccl":
@@ -529,9 +537,34 @@ def main():
                     w.wait()
         ready[b] = None
 
-    def collect():
-        if world > 1:
-            dist.gather(out_dev, gathered, dst=0)
+    # Result gather to rank 0 (north_star): issued from a side stream so that it overlaps the next step's hierarchy
+    # build; the gather kernels therefore alternate between two result buffers.  GVPM_COLLECT=inline keeps it on the
+    # compute stream.
+    coll = torch.cuda.Stream(device=local)
+    overlap_collect = world > 1 and os.environ.get("GVPM_COLLECT", "overlap") == "overlap"
+    with torch.cuda.stream(stream):
+        out_bufs = [out_dev, torch.zeros_like(out_dev) if overlap_collect else out_dev]
+    coll_done = [None, None]
+
+    def collect(k):
+        if world == 1:
+            return
+        if not overlap_collect:
+            dist.gather(out_bufs[0], gathered, dst=0)
+            return
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        coll.wait_event(ev)
+        with torch.cuda.stream(coll):
+            dist.gather(out_bufs[k & 1], gathered, dst=0)
+        coll_done[k & 1] = torch.cuda.Event()
+        coll_done[k & 1].record(coll)
+
+    def wait_collects():
+        for i in (0, 1):
+            if coll_done[i] is not None:
+                stream.wait_event(coll_done[i])
+                coll_done[i] = None
 
     kept = [n_ph]
 
@@ -549,10 +582,13 @@ def main():
             prefetch(1 - b, from_host=False)
         ctx.photon_staging_select(b)
         ctx.photon_staging(n_ph)
+        if coll_done[b] is not None:            # the result buffer of step k - 2 has been gathered
+            stream.wait_event(coll_done[b])
+            coll_done[b] = None
         with torch.cuda.stream(stream):
             build_resident()
-            ctx.gather_bre_into(out_dev.data_ptr(), None)
-            collect()
+            ctx.gather_bre_into(out_bufs[b].data_ptr(), None)
+            collect(k)
         host_barrier()
 
     def step_e2e(k):
@@ -577,6 +613,7 @@ def main():
             host_barrier()
         for k in range(warmup):
             fn(k)
+        wait_collects()
         ctx.sync()
         torch.cuda.synchronize()
         if world > 1:
@@ -588,6 +625,7 @@ def main():
         for k in range(warmup, warmup + steps):
             fn(k)
         wait_ready((warmup + steps) & 1)        # the K-th exchange issued inside the timed region ends inside it
+        wait_collects()                         # ... and so do the result gathers
         e1.record(stream)
         ctx.sync()
         torch.cuda.synchronize()
@@ -668,8 +706,11 @@ def main():
                         "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(R * 27 * 4),
                         "note": "every rank uploads 1/N of the photon set and its own rays over its own PCIe link; "
                                 "the upload + all-gather of step k+1 overlaps the build + gather of step k"},
-                "photon_exchange": {"how": {"none": "single GPU", "peer": "slices pushed into the peers' staging "
-                                            "buffers over NVLink copy engines (CUDA IPC, gvpm_peer_*)",
+                "photon_exchange": {"how": {"none": "single GPU", "peer": "slices pushed into the peers' staging buffers over NVLink "
+                                            + (f"by a {os.environ.get('GVPM_PUSH_CTAS', str(default_push_ctas(world)))}-CTA store kernel"
+                                               if os.environ.get("GVPM_PUSH_CTAS", str(default_push_ctas(world))) != "0"
+                                               else "copy engines")
+                                            + " (CUDA IPC peer mappings, gvpm_peer_*)",
                                             "nccl": "NCCL all_gather of the 13 field arrays"
                                             + (", in place" if inplace_ok else "")}[exchange],
                                     "double_buffered": True,
@@ -699,7 +740,7 @@ def main():
     # tensors allocated on the context's stream must go before the stream does
     # (device tensors and pinned host buffers that were used on it record events on that stream when
     # they are freed)
-    del out_dev, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk, bk, kept_t, kept_all
+    del out_dev, out_bufs, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk, bk, kept_t, kept_all
     del out_host_t, out_host, rays
     inp.clear()
     import gc

@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays",
     "gvpm_photon_staging_select", "gvpm_photon_staging_layout", "gvpm_upload_photons_slice",
-    "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons",
+    "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons", "gvpm_peer_push_mode",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
@@ -126,6 +126,7 @@ def load_lib():
     lib.gvpm_peer_connect.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.gvpm_peer_push_photon_slice.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gvpm_peer_wait_photons.argtypes = [vp, C.c_int]
+    lib.gvpm_peer_push_mode.argtypes = [vp, C.c_int]
     lib.gvpm_upload_rays.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t]
     lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_commit_rays.argtypes = [vp]

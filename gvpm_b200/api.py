@@ -103,6 +103,10 @@ class Context:
     def peer_wait_photons(self, which):
         self._ck(self.lib.gvpm_peer_wait_photons(self.h, which), "gvpm_peer_wait_photons")
 
+    def peer_push_mode(self, sm_ctas):
+        """sm_ctas > 0: push kernel of that many CTAs (stores through the peer mappings); 0: copy engines."""
+        self._ck(self.lib.gvpm_peer_push_mode(self.h, int(sm_ctas)), "gvpm_peer_push_mode")
+
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 

@@ -101,6 +101,8 @@ struct gvpm_ctx {
   cudaEvent_t ev_free[2] = {nullptr, nullptr};   // staging buffer b has been consumed by this context's last build
   cudaEvent_t ev_pushed[2] = {nullptr, nullptr}; // this context's slice has landed in every peer's staging buffer b
   cudaStream_t push_streams[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t push_kernel_stream = nullptr;  // highest priority: the SM push kernel takes its CTA slots as soon as they free
+  int push_ctas = 32;                         // 0: copy engines (cudaMemcpyAsync per field and peer)
   cudaEvent_t push_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..3] push stream done, [4] slice ready
   int n_peers = 0, peer_self = -1;
   std::vector<void *> peer_staging[2];
@@ -381,6 +383,11 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_pushed[b], cudaEventDisableTiming | cudaEventInterprocess);
   }
   for (auto &ps : ctx->push_streams) cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&ctx->push_kernel_stream, cudaStreamNonBlocking, hi);
+  }
   for (auto &ev : ctx->push_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   ctx->work_counter.reserve(256);
   cudaHostAlloc((void **)&ctx->pair_count_host, sizeof(unsigned long long), cudaHostAllocDefault);
@@ -404,6 +411,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->plane_bounds, &ctx->ray_region};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
+  if (ctx->push_kernel_stream) { cudaStreamSynchronize(ctx->push_kernel_stream); cudaStreamDestroy(ctx->push_kernel_stream); }
   for (auto &ev : ctx->push_ev) if (ev) cudaEventDestroy(ev);
   for (int b = 0; b < 2; ++b) {
     for (int p = 0; p < ctx->n_peers; ++p) {
@@ -602,6 +610,46 @@ int gvpm_peer_connect(gvpm_ctx *ctx, const void *blobs, int n_peers, int self_in
   return GVPM_OK;
 }
 
+// SM push: one kernel reads this rank's slice of the 13 field arrays once (128-bit loads) and stores every word into
+// the same place of every peer's staging buffer over NVLink (peer-mapped pointers), so the 7 outgoing streams of an
+// 8-GPU box are fed in parallel.  It runs on a highest-priority stream with a small grid: the copy engines top out
+// near 220 GB/s per GPU on this many-small-copies pattern (13 fields x 7 peers), a few SMs' worth of stores do not.
+struct PushParams {
+  const char *src;
+  char *dst[8];
+  int n_dst;
+  unsigned long long off[13];   // byte offset of each field's slice inside a staging buffer
+  unsigned long long cum[14];   // prefix sums of the slice sizes in 16-byte words
+};
+__global__ void __launch_bounds__(512) k_peer_push(const __grid_constant__ PushParams P) {
+  const unsigned long long total = P.cum[13], stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long w0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w0 < total; w0 += 4 * stride) {
+    uint4 v[4];
+    unsigned long long byte[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned long long w = w0 + u * stride;
+      byte[u] = ~0ull;
+      if (w < total) {
+        int f = 0;
+        while (w >= P.cum[f + 1]) ++f;
+        byte[u] = P.off[f] + (w - P.cum[f]) * 16ull;
+        v[u] = __ldcs((const uint4 *)(P.src + byte[u]));
+      }
+    }
+    for (int d = 0; d < P.n_dst; ++d)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (byte[u] != ~0ull) __stcs((uint4 *)(P.dst[d] + byte[u]), v[u]);
+  }
+}
+
+int gvpm_peer_push_mode(gvpm_ctx *ctx, int sm_ctas) {
+  if (!ctx || sm_ctas < 0 || sm_ctas > 1024) return GVPM_ERR_INVALID;
+  ctx->push_ctas = sm_ctas;
+  return GVPM_OK;
+}
+
 int gvpm_peer_push_photon_slice(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count, void *after_stream) {
   if (!ctx || (which != 0 && which != 1) || begin + count > n_total) return GVPM_ERR_INVALID;
   if (!ctx->n_peers) return fail(ctx, GVPM_ERR_INVALID, "gvpm_peer_connect has not been called");
@@ -612,6 +660,28 @@ int gvpm_peer_push_photon_slice(gvpm_ctx *ctx, int which, size_t n_total, size_t
   // the slice must be complete on this rank (work queued on after_stream, e.g. its H2D upload) ...
   cudaEvent_t src_ready = ctx->push_ev[4];
   CK(cudaEventRecord(src_ready, after_stream ? (cudaStream_t)after_stream : ctx->stream));
+  bool aligned = ctx->n_peers <= 9;
+  for (int f = 0; f < 13; ++f) aligned = aligned && (begin * elt[f]) % 16 == 0 && (count * elt[f]) % 16 == 0;
+  if (ctx->push_ctas > 0 && aligned && count > 0) {
+    PushParams PP{};
+    PP.src = mine;
+    cudaStream_t ks = ctx->push_kernel_stream;
+    CK(cudaStreamWaitEvent(ks, src_ready, 0));
+    for (int p = 0; p < ctx->n_peers; ++p) {
+      if (p == ctx->peer_self) continue;
+      CK(cudaStreamWaitEvent(ks, ctx->peer_free[which][p], 0));
+      PP.dst[PP.n_dst++] = (char *)ctx->peer_staging[which][p];
+    }
+    for (int f = 0; f < 13; ++f) {
+      PP.off[f] = L.off[f] + begin * elt[f];
+      PP.cum[f + 1] = PP.cum[f] + count * elt[f] / 16;
+    }
+    k_peer_push<<<ctx->push_ctas, 512, 0, ks>>>(PP);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaEventRecord(ctx->ev_pushed[which], ks));
+    return GVPM_OK;
+  }
   int si = 0;
   for (int p = 0; p < ctx->n_peers; ++p) {
     if (p == ctx->peer_self) continue;

@@ -256,6 +256,11 @@ int gvpm_peer_connect(gvpm_ctx *ctx, const void *blobs /* [n_peers * GVPM_PEER_B
 int gvpm_peer_push_photon_slice(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count,
                                 void *after_stream);
 int gvpm_peer_wait_photons(gvpm_ctx *ctx, int which);
+/* How gvpm_peer_push_photon_slice moves the bytes: sm_ctas > 0 (default 32) = one kernel of that many CTAs on a
+ * highest-priority stream that reads the slice once and stores it into every peer's buffer through the peer mappings;
+ * 0 = cudaMemcpyAsync per field and peer on the copy engines (also the fallback for slices that are not 16-byte
+ * aligned in every field). */
+int gvpm_peer_push_mode(gvpm_ctx *ctx, int sm_ctas);
 /* Hilbert sort + implicit 32-ary AABB hierarchy for search radius `radius`
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
