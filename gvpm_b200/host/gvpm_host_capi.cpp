@@ -2,6 +2,7 @@
 // driven from tests (ctypes).  A Mitsuba build would include gvpm_host.hpp directly.
 #include <cstring>
 
+#include "gvpm_fixture.hpp"
 #include "gvpm_host.hpp"
 
 using namespace gvpm_host;
@@ -55,5 +56,18 @@ int gvpm_host_gradient(void *h, float *thr, float *gx, float *gy, int useAbs, ch
 double gvpm_host_scale(void *h) { return ((VolumeGatherB200 *)h)->globalScaleVolume; }
 float gvpm_host_radius(void *h) { return ((VolumeGatherB200 *)h)->currentRadius(); }
 const float *gvpm_host_accumulators(void *h) { return ((VolumeGatherB200 *)h)->accumulators().data(); }
+
+// the fixture writer a Mitsuba-side dump hook uses (gvpm_fixture.hpp), reachable from the tests
+int gvpm_host_write_bre_fixture(const char *path, const gvpm_medium *m, const gvpm_config *c, float radius,
+                                const float *tris, size_t nTris, const gvpm_photon_soa *ph, size_t nPhotons,
+                                const gvpm_ray_soa *rays, size_t nRays, const float *expectedOut,
+                                const uint64_t *nbrOffsets, const uint32_t *nbrIdx, const char *producer, char *err,
+                                size_t errlen) {
+  try {
+    gvpm_fixture::write_bre_fixture(path, *m, *c, radius, tris, nTris, *ph, nPhotons, *rays, nRays, expectedOut,
+                                    nbrOffsets, nbrIdx, producer);
+    return 0;
+  } catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
 
 }  // extern "C"

@@ -118,3 +118,42 @@ def test_pruned_needs_rays(built):
     with pytest.raises(GvpmError):
         ctx.build_points_for_rays(case.radius)
     ctx.close()
+
+
+def test_cfg5_full_size_properties(built):
+    """BASELINE.json configs[4] at full size (1920x1080 rays, 10 M photons, scale 0.1), through size-independent
+    properties: (1) every 997th ray matches the oracle's reference-shaped kd-tree gather (counts bit-exact up to the
+    reference tree's Epsilon sliver, radiance 1e-4); (2) two band shards gathered through pruned hierarchies return
+    exactly the rows of the full gather's neighbour counts and the same radiance; (3) totals: the geometric
+    neighbour count is the sum over the shards."""
+    import os
+    from oracle import binding as ob
+    w, h, n = 1920, 1080, 10_000_000
+    med = g.make_medium()
+    ph, _ = g.synth_photons(n, med, seed=0xC0FFEE + 5, threads=os.cpu_count() or 8)
+    rays = g.synth_rays(w, h, seed=0xC0FFEE + 6, block=-32)
+    case = H.Case()
+    case.medium, case.photons, case.rays, case.tri = med, ph, rays, g.synth_occluders()
+    case.config, case.radius, case.w, case.h = g.make_config(w, h), g.bre_radius(0.1), w, h
+    ctx = H.gpu_context(case)
+    out, counts = ctx.gather_bre()
+    assert counts[:, 0].sum() > 30_000_000
+    # (1)
+    sel = np.arange(0, rays.n, 997)
+    ref = ob.bre_gather(ph, rays.take(sel), med, case.config, case.tri, case.radius, mode="kdtree")
+    same = (ref.counts == counts[sel]).all(axis=1)
+    assert same.mean() > 0.999
+    H.assert_radiance_close(out[sel][same], ref.out[same], 1e-4, "cfg5 sampled rays vs oracle kd-tree")
+    # (2) + (3)
+    total = 0
+    for rank in (1, 6):
+        idx = shard.band_indices(rays.px, rays.py, w, h, 8, rank, 2)
+        ctx.upload_rays(rays.take(idx))
+        kept = ctx.build_points_for_rays(case.radius)
+        assert kept < 0.3 * n
+        o, c = ctx.gather_bre()
+        np.testing.assert_array_equal(c, counts[idx])
+        H.assert_radiance_close(o, out[idx], 1e-5, f"cfg5 band shard {rank}")
+        total += int(c[:, 0].sum())
+    assert 0 < total < counts[:, 0].sum()
+    ctx.close()
