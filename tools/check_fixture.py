@@ -26,6 +26,21 @@ def rel_err(got, ref):
     return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor if floor > 0 else 1.0)).max()) if ref.size else 0.0
 
 
+def differing_rays(off_a, idx_a, off_b, idx_b):
+    """ray indices whose neighbour lists differ (bit 31 ignored)"""
+    a, b = idx_a & 0x7fffffff, idx_b & 0x7fffffff
+    bad = []
+    for i in range(len(off_a) - 1):
+        if not np.array_equal(np.sort(a[int(off_a[i]):int(off_a[i + 1])]), np.sort(b[int(off_b[i]):int(off_b[i + 1])])):
+            bad.append(i)
+    return bad
+
+
+def report_sets(what, bad):
+    print(f"{what}: " + ("identical" if not bad else f"{len(bad)} rays DIFFER (first: {bad[:8]})"))
+    return not bad
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("fixture")
@@ -43,10 +58,8 @@ def main():
         print(f"oracle vs expected radiance: max rel err {e:.3e}")
         ok &= e <= a.rtol
     if fx.expected_offsets is not None:
-        same = np.array_equal(ref.offsets, fx.expected_offsets) and \
-            np.array_equal(ref.idx & 0x7fffffff, fx.expected_idx & 0x7fffffff)
-        print(f"oracle vs expected neighbour sets: {'identical' if same else 'DIFFERENT'}")
-        ok &= same
+        ok &= report_sets("oracle vs expected neighbour sets",
+                          differing_rays(ref.offsets, ref.idx, fx.expected_offsets, fx.expected_idx))
     if not a.no_gpu:
         from gvpm_b200.api import Context
         ctx = Context(0)
@@ -68,10 +81,8 @@ def main():
             print(f"GPU vs expected radiance: max rel err {e:.3e}")
             ok &= e <= a.rtol
         if fx.expected_offsets is not None:
-            same = np.array_equal(offsets, fx.expected_offsets) and \
-                np.array_equal(idx & 0x7fffffff, fx.expected_idx & 0x7fffffff)
-            print(f"GPU vs expected neighbour sets: {'identical' if same else 'DIFFERENT'}")
-            ok &= same
+            ok &= report_sets("GPU vs expected neighbour sets",
+                              differing_rays(offsets, idx, fx.expected_offsets, fx.expected_idx))
     print("PASS" if ok else "FAIL")
     return 0 if ok else 1
 
