@@ -10,6 +10,10 @@
 //     computeVolumeGradientPlanes       gvpm/gvpm.cpp:782-878     (G-Planes 0D) + LTPhotonPlane::transformBeam
 //     scaleVolumeAPA                    gvpm/gvpm.cpp:181-215
 //     computeGradient                   gvpm/gvpm.cpp:1205-1306
+// and, for the sppm plugin's primal volume passes (class SPPMVolumeGatherB200):
+//     volumePhotonPassBRE               sppm.cpp:905-1001
+//     volumePhotonBeamPass              sppm.cpp:765-880          (beam1d / beam3d_naive / beam3d_egsr / beam3d)
+//     scaleVolumeAPA                    sppm.cpp:255-290
 // A patched gvpm.cpp would hold one VolumeGatherB200 next to m_gatherBlocks and call it from
 // photonMapPass.  Errors: the reference raises through SLog(EError) (a
 // std::runtime_error); so does this shim, carrying gvpm_last_error().
@@ -251,6 +255,135 @@ class VolumeGatherB200 {
   float m_bsphereR;
   std::vector<float> m_acc, m_iter;
   std::vector<uint8_t> m_haveSmoke;
+};
+
+// ---- sppm plugin: primal volume passes --------------------------------------------------------------------------
+// volTechnique strings of sppm.cpp:208-209 / volume_utils.h:54-92 that the gather serves
+enum ESPPMVolumeTechnique { ESppmBRE2D = 0, ESppmBRE3D = 1, ESppmBeam1D = 2, ESppmBeam3DNaive = 3, ESppmBeam3DEGSR = 4,
+                            ESppmBeam3DOptimized = 5 };
+
+struct SPPMConfig {   // the SPPMIntegrator members the volume passes read (sppm.cpp:163-241), same names
+  int maxDepth = -1, minDepth = 0;
+  double alpha = 0.7;
+  double initialScaleVolume = 1.0;
+  int volTechnique = ESppmBRE3D;
+  std::string forceAPA;
+  unsigned rngSeed = 0;   // replaces the per-thread Sampler of the 3-D kernels (counter-based hash)
+};
+
+// SPPMIntegrator::scaleVolumeAPA, sppm.cpp:255-290 (m_independentScale = false)
+inline void scaleVolumeAPA(double &globalScaleVolume, int it, const SPPMConfig &config) {
+  it -= 1;
+  const double ratioVolAPA = (it + config.alpha) / (it + 1);
+  const int t = config.volTechnique;
+  const bool use3D = t == ESppmBRE3D || t == ESppmBeam3DNaive || t == ESppmBeam3DEGSR || t == ESppmBeam3DOptimized;
+  if (config.forceAPA.empty()) {
+    if (use3D) globalScaleVolume *= std::cbrt(ratioVolAPA);
+    else if (t == ESppmBRE2D) globalScaleVolume *= std::sqrt(ratioVolAPA);
+    else globalScaleVolume *= ratioVolAPA;
+  } else if (config.forceAPA == "1D") {
+    globalScaleVolume *= ratioVolAPA;
+  } else if (config.forceAPA == "2D") {
+    globalScaleVolume *= std::sqrt(ratioVolAPA);
+  } else if (config.forceAPA == "3D") {
+    globalScaleVolume *= std::cbrt(ratioVolAPA);
+  } else {
+    throw std::runtime_error("No Force APA: " + config.forceAPA);
+  }
+}
+
+// One Spectrum per pixel: GatherPoint::fluxVol (photonmapper/gatherpoint.h), the APA running mean of sppm.cpp:871,992.
+class SPPMVolumeGatherB200 {
+ public:
+  SPPMVolumeGatherB200(int device, int width, int height, const SPPMConfig &config, const gvpm_medium &medium,
+                       float mediumBSphereRadius)
+      : globalScaleVolume(config.initialScaleVolume), m_config(config), m_w(width), m_h(height),
+        m_bsphereR(mediumBSphereRadius), m_fluxVol((size_t)width * height * 3, 0.f) {
+    check(gvpm_ctx_create(device, &m_ctx), "gvpm_ctx_create");
+    check(gvpm_set_medium(m_ctx, &medium), "gvpm_set_medium");
+    gvpm_config c{};
+    c.max_depth = config.maxDepth;
+    c.min_depth = config.minDepth;
+    c.lighting_mode = GVPM_ALL2MEDIA;
+    c.kernel_3d = config.volTechnique != ESppmBRE2D;
+    c.sppm_primal = 1;
+    c.film_w = width;
+    c.film_h = height;
+    c.shadow_maxt_scale = 1e-3f;
+    c.epsilon = 1e-4f;
+    c.rng_seed = config.rngSeed;
+    check(gvpm_set_config(m_ctx, &c), "gvpm_set_config");
+    check(gvpm_set_occluders(m_ctx, nullptr, 0), "gvpm_set_occluders");   // the primal passes cast no shadow ray
+  }
+  ~SPPMVolumeGatherB200() { if (m_ctx) gvpm_ctx_destroy(m_ctx); }
+  SPPMVolumeGatherB200(const SPPMVolumeGatherB200 &) = delete;
+  SPPMVolumeGatherB200 &operator=(const SPPMVolumeGatherB200 &) = delete;
+
+  // breInitSize / beamInitSize = m_smokeAABB.getBSphere().radius * globalScaleVolume * POURCENTAGE_BS (sppm.cpp:770,924)
+  float currentRadius() const { return (float)(m_bsphereR * (float)globalScaleVolume * 0.01f); }
+
+  // sppm.cpp:905-1001.  photons: pos, flux = getPower(), parent_pos = pos - getDirection(), depth; rays: one record per
+  // (gather point, camera beam): o = beam.p1, d, mint = Epsilon, maxt = distTotal - Epsilon, eye_contrib = beam.weight,
+  // edge_id = beam.depth.  shotParticles = proc->getShotParticles() (photonMap->setScaleFactor, :921).
+  void volumePhotonPassBRE(int it, const gvpm_photon_soa *photons, size_t nPhotons, const gvpm_ray_soa *rays,
+                           size_t nRays, size_t shotParticles) {
+    check(gvpm_upload_photons(m_ctx, photons, nPhotons), "gvpm_upload_photons");
+    check(gvpm_build_points(m_ctx, currentRadius()), "gvpm_build_points");
+    check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
+    m_iter.assign(nRays * 3, 0.f);
+    check(gvpm_gather_sppm_bre(m_ctx, m_iter.data(), nullptr), "gvpm_gather_sppm_bre");
+    foldIteration(it, rays, nRays, (float)shotParticles);   // :976-992
+    scaleVolumeAPA(it);                                      // :997
+  }
+
+  // sppm.cpp:765-880.  beams: origin, end, flux, depth of the iteration's PhotonBeams; rays as above with
+  // edge_len = distTotal.
+  void volumePhotonBeamPass(int it, const gvpm_beam_soa *beams, size_t nBeams, const gvpm_ray_soa *rays, size_t nRays,
+                            size_t shotParticles) {
+    int technique;
+    switch (m_config.volTechnique) {
+      case ESppmBeam1D: technique = GVPM_BEAM_1D; break;
+      case ESppmBeam3DNaive: technique = GVPM_BEAM_3D_NAIVE; break;
+      case ESppmBeam3DEGSR: technique = GVPM_BEAM_3D_EGSR; break;
+      case ESppmBeam3DOptimized: technique = GVPM_BEAM_3D_OPTIMIZED; break;
+      default: throw std::runtime_error("Not supported kernel type");   // beams.h:219
+    }
+    check(gvpm_upload_beams(m_ctx, beams, nBeams), "gvpm_upload_beams");
+    check(gvpm_build_beams(m_ctx, currentRadius()), "gvpm_build_beams");
+    check(gvpm_upload_rays(m_ctx, rays, nRays), "gvpm_upload_rays");
+    m_iter.assign(nRays * 3, 0.f);
+    check(gvpm_gather_sppm_beams(m_ctx, technique, m_iter.data(), nullptr), "gvpm_gather_sppm_beams");
+    foldIteration(it, rays, nRays, (float)shotParticles);   // :863-871
+    scaleVolumeAPA(it);                                      // :876
+  }
+
+  void scaleVolumeAPA(int it) { gvpm_host::scaleVolumeAPA(globalScaleVolume, it, m_config); }
+  const std::vector<float> &fluxVol() const { return m_fluxVol; }
+  gvpm_ctx *context() { return m_ctx; }
+  double globalScaleVolume;
+
+ private:
+  // sum the camera beams of each gather point, normalise by the shot particles, APA running mean - for EVERY pixel,
+  // "even if there is no photon collected" (sppm.cpp:866-871)
+  void foldIteration(int it, const gvpm_ray_soa *rays, size_t nRays, float shot) {
+    std::vector<float> pix(m_fluxVol.size(), 0.f);
+    for (size_t r = 0; r < nRays; ++r) {
+      const int x = rays->px[r], y = rays->py[r];
+      if (x < 0 || y < 0 || x >= m_w || y >= m_h) continue;
+      const size_t p = ((size_t)y * m_w + x) * 3;
+      for (int j = 0; j < 3; ++j) pix[p + j] += m_iter[r * 3 + j];
+    }
+    for (size_t i = 0; i < m_fluxVol.size(); ++i)
+      m_fluxVol[i] = (m_fluxVol[i] * (float)(it - 1) + pix[i] / shot) / (float)it;
+  }
+  void check(int rc, const char *what) {
+    if (rc != GVPM_OK) throw std::runtime_error(std::string(what) + " failed: " + gvpm_last_error(m_ctx));
+  }
+  SPPMConfig m_config;
+  gvpm_ctx *m_ctx = nullptr;
+  int m_w, m_h;
+  float m_bsphereR;
+  std::vector<float> m_fluxVol, m_iter;
 };
 
 }  // namespace gvpm_host

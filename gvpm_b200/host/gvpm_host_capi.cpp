@@ -57,6 +57,44 @@ double gvpm_host_scale(void *h) { return ((VolumeGatherB200 *)h)->globalScaleVol
 float gvpm_host_radius(void *h) { return ((VolumeGatherB200 *)h)->currentRadius(); }
 const float *gvpm_host_accumulators(void *h) { return ((VolumeGatherB200 *)h)->accumulators().data(); }
 
+// ---- sppm mirror -----------------------------------------------------------------------------------------------------
+struct gvpm_host_sppm_params {
+  int maxDepth, minDepth;
+  double alpha, initialScaleVolume;
+  int volTechnique;
+  unsigned rngSeed;
+  char forceAPA[8];
+};
+static SPPMConfig to_sppm(const gvpm_host_sppm_params *p) {
+  SPPMConfig c;
+  c.maxDepth = p->maxDepth; c.minDepth = p->minDepth; c.alpha = p->alpha; c.initialScaleVolume = p->initialScaleVolume;
+  c.volTechnique = p->volTechnique; c.rngSeed = p->rngSeed; c.forceAPA = p->forceAPA;
+  return c;
+}
+int gvpm_host_sppm_scale_apa(double *scale, int it, const gvpm_host_sppm_params *p, char *err, size_t errlen) {
+  try { scaleVolumeAPA(*scale, it, to_sppm(p)); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+void *gvpm_host_sppm_create(int device, int w, int h, const gvpm_host_sppm_params *p, const gvpm_medium *m,
+                            float bsphereR, char *err, size_t errlen) {
+  try { return new SPPMVolumeGatherB200(device, w, h, to_sppm(p), *m, bsphereR); }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return nullptr; }
+}
+void gvpm_host_sppm_destroy(void *h) { delete (SPPMVolumeGatherB200 *)h; }
+int gvpm_host_sppm_bre_pass(void *h, int it, const gvpm_photon_soa *ph, size_t n, const gvpm_ray_soa *rays, size_t nRays,
+                            size_t shotParticles, char *err, size_t errlen) {
+  try { ((SPPMVolumeGatherB200 *)h)->volumePhotonPassBRE(it, ph, n, rays, nRays, shotParticles); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+int gvpm_host_sppm_beam_pass(void *h, int it, const gvpm_beam_soa *beams, size_t n, const gvpm_ray_soa *rays,
+                             size_t nRays, size_t shotParticles, char *err, size_t errlen) {
+  try { ((SPPMVolumeGatherB200 *)h)->volumePhotonBeamPass(it, beams, n, rays, nRays, shotParticles); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+double gvpm_host_sppm_scale(void *h) { return ((SPPMVolumeGatherB200 *)h)->globalScaleVolume; }
+float gvpm_host_sppm_radius(void *h) { return ((SPPMVolumeGatherB200 *)h)->currentRadius(); }
+const float *gvpm_host_sppm_flux_vol(void *h) { return ((SPPMVolumeGatherB200 *)h)->fluxVol().data(); }
+
 // the fixture writer a Mitsuba-side dump hook uses (gvpm_fixture.hpp), reachable from the tests
 int gvpm_host_write_bre_fixture(const char *path, const gvpm_medium *m, const gvpm_config *c, float radius,
                                 const float *tris, size_t nTris, const gvpm_photon_soa *ph, size_t nPhotons,

@@ -102,6 +102,29 @@ def test_scale_volume_apa_schedule(tech, force, expo):
     assert b"No Force APA" in err.value
 
 
+class SppmHostParams(C.Structure):
+    _fields_ = [("maxDepth", C.c_int), ("minDepth", C.c_int), ("alpha", C.c_double), ("initialScaleVolume", C.c_double),
+                ("volTechnique", C.c_int), ("rngSeed", C.c_uint), ("forceAPA", C.c_char * 8)]
+
+
+@pytest.mark.parametrize("tech,force,expo", [(1, b"", 1 / 3), (0, b"", 1 / 2), (2, b"", 1.0), (3, b"", 1 / 3),
+                                             (5, b"", 1 / 3), (2, b"3D", 1 / 3)])
+def test_sppm_scale_volume_apa_schedule(tech, force, expo):
+    """sppm.cpp:255-290: 3-D kernels (bre3d, the three 3-D beam techniques) shrink by the cube root, bre2d by the
+    square root, beam1d linearly; forceAPA overrides."""
+    h = _host()
+    h.gvpm_host_sppm_scale_apa.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(SppmHostParams), C.c_char_p, C.c_size_t]
+    p = SppmHostParams(maxDepth=-1, minDepth=0, alpha=0.7, initialScaleVolume=0.3, volTechnique=tech, rngSeed=0, forceAPA=force)
+    s, want = C.c_double(0.3), 0.3
+    err = C.create_string_buffer(256)
+    for it in range(1, 20):
+        assert h.gvpm_host_sppm_scale_apa(C.byref(s), it, C.byref(p), err, 256) == 0
+        want *= ((it - 1 + 0.7) / it) ** expo
+        assert abs(s.value - want) < 1e-14
+    p.forceAPA = b"9D"
+    assert h.gvpm_host_sppm_scale_apa(C.byref(s), 1, C.byref(p), err, 256) == -1 and b"No Force APA" in err.value
+
+
 def test_tile_sharding_partitions_every_ray_once():
     from gvpm_b200 import shard
     w, h = 100, 70
@@ -162,14 +185,17 @@ py, px = np.mgrid[0:h, 0:w]; px, py = px.ravel(), py.ravel()
 photons = torch.arange(1000, dtype=torch.float32) if rank == 0 else torch.zeros(1000)
 dist.broadcast(photons, src=0)
 assert float(photons.sum()) == 999 * 1000 / 2
-idx = shard.local_indices(px, py, w, world, rank)
+mode = sys.argv[2] if len(sys.argv) > 2 else "tile"
+def indices(r):
+    return shard.band_indices(px, py, w, h, world, r, 2) if mode == "band" else shard.local_indices(px, py, w, world, r)
+idx = indices(rank)
 n_pad = torch.tensor([len(idx)]); dist.all_reduce(n_pad, op=dist.ReduceOp.MAX); n_pad = int(n_pad)
 out = torch.zeros(n_pad, 27)
 out[:len(idx)] = torch.from_numpy((px[idx] * 1000 + py[idx]).astype(np.float32))[:, None] + torch.arange(27.0)
 gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
 dist.gather(out, gathered, dst=0)
 if rank == 0:
-    lists = [shard.local_indices(px, py, w, world, r) for r in range(world)]
+    lists = [indices(r) for r in range(world)]
     full = shard.assemble([g.numpy() for g in gathered], lists, px.size)
     want = (px * 1000 + py).astype(np.float32)[:, None] + np.arange(27, dtype=np.float32)
     assert np.array_equal(full, want)
@@ -178,13 +204,14 @@ dist.destroy_process_group()
 """
 
 
-def test_sharded_gather_world2_gloo(tmp_path):
-    """The N > 1 plumbing of bench.py (broadcast photons, gather per-rank results, reassemble) on
-    2 CPU ranks over gloo."""
+@pytest.mark.parametrize("mode", ["tile", "band"])
+def test_sharded_gather_world2_gloo(tmp_path, mode):
+    """The N > 1 plumbing of bench.py (broadcast photons, gather per-rank results of unequal size, reassemble) on
+    2 CPU ranks over gloo, for the round-robin and the column-band partition."""
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), ROOT]
+           "--master-addr", "127.0.0.1", "--master-port", "29533" if mode == "tile" else "29534", str(script), ROOT, mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "GLOO_OK" in res.stdout

@@ -87,3 +87,63 @@ def test_sppm_beams_errors_and_empty(built):
     out, counts = ctx.gather_sppm_beams("beam3d")
     assert not out.any() and not counts.any()
     ctx.close()
+
+
+@pytest.mark.parametrize("tech_id,tech", [(5, "beam3d"), (3, "beam3d_naive"), (1, "bre3d")])
+def test_sppm_host_mirror_two_iterations(built, tech_id, tech):
+    """gvpm_host::SPPMVolumeGatherB200 (volumePhotonBeamPass / volumePhotonPassBRE, sppm.cpp:765-1001) == oracle gather
+    + the reference's per-pixel sum over camera beams, 1 / shotParticles, APA running mean and radius reduction."""
+    import ctypes as C
+    import os
+    import gvpm_b200 as g
+    from gvpm_b200 import _native as N
+    from oracle import binding as ob
+    from test_abi_and_host import ROOT, SppmHostParams
+    hl = C.CDLL(os.path.join(ROOT, "gvpm_b200", "host", "libgvpm_host.so"))
+    hl.gvpm_host_sppm_create.restype = C.c_void_p
+    hl.gvpm_host_sppm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(SppmHostParams), C.POINTER(N.Medium),
+                                         C.c_float, C.c_char_p, C.c_size_t]
+    hl.gvpm_host_sppm_beam_pass.argtypes = [C.c_void_p, C.c_int, C.POINTER(N.BeamSoA), C.c_size_t, C.POINTER(N.RaySoA),
+                                            C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t]
+    hl.gvpm_host_sppm_bre_pass.argtypes = [C.c_void_p, C.c_int, C.POINTER(N.PhotonSoA), C.c_size_t, C.POINTER(N.RaySoA),
+                                           C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t]
+    hl.gvpm_host_sppm_radius.restype = C.c_float
+    hl.gvpm_host_sppm_radius.argtypes = [C.c_void_p]
+    hl.gvpm_host_sppm_scale.restype = C.c_double
+    hl.gvpm_host_sppm_scale.argtypes = [C.c_void_p]
+    hl.gvpm_host_sppm_flux_vol.restype = N.f32p
+    hl.gvpm_host_sppm_flux_vol.argtypes = [C.c_void_p]
+    hl.gvpm_host_sppm_destroy.argtypes = [C.c_void_p]
+    w, h, scale0, shot = 32, 24, 3.0, 5000
+    err = C.create_string_buffer(512)
+    p = SppmHostParams(maxDepth=8, minDepth=0, alpha=0.7, initialScaleVolume=scale0, volTechnique=tech_id, rngSeed=4321,
+                       forceAPA=b"")
+    med = g.make_medium()
+    hd = hl.gvpm_host_sppm_create(0, w, h, C.byref(p), C.byref(med), g.records.SYNTH_BSPHERE_R, err, 512)
+    assert hd, err.value
+    flux_ref = np.zeros((h, w, 3), dtype=np.float32)
+    scale = scale0
+    for it in (1, 2):
+        c = _case(n_beams=3000, w=w, h=h, scale=scale, seed=7 * it, max_depth=8, sppm_primal=True)
+        radius = hl.gvpm_host_sppm_radius(hd)
+        assert abs(radius - g.bre_radius(scale)) <= 1e-9
+        cr = c.rays.as_c()
+        if tech == "bre3d":
+            c.photons, _ = g.synth_photons(20000, c.medium, seed=3 * it, threads=4)
+            cph = c.photons.as_c()
+            rc = hl.gvpm_host_sppm_bre_pass(hd, it, C.byref(cph), c.photons.n, C.byref(cr), c.rays.n, shot, err, 512)
+            ref = ob.sppm_bre_gather(c.photons, c.rays, c.medium, c.config, radius, mode="brute")
+        else:
+            cb = c.beams.as_c()
+            rc = hl.gvpm_host_sppm_beam_pass(hd, it, C.byref(cb), c.beams.n, C.byref(cr), c.rays.n, shot, err, 512)
+            ref = ob.sppm_beams_gather(c.beams, c.rays, c.medium, c.config, radius, tech)
+        assert rc == 0, err.value
+        assert ref.counts[:, 1].sum() > 500
+        pix = np.zeros((h, w, 3), dtype=np.float32)
+        np.add.at(pix, (c.rays.py, c.rays.px), ref.out)
+        flux_ref = (flux_ref * np.float32(it - 1) + pix / np.float32(shot)) / np.float32(it)
+        scale *= ((it - 1 + 0.7) / it) ** (1 / 3)
+        assert abs(hl.gvpm_host_sppm_scale(hd) - scale) < 1e-12
+    got = np.ctypeslib.as_array(hl.gvpm_host_sppm_flux_vol(hd), shape=(h * w * 3,)).reshape(h, w, 3).copy()
+    H.assert_radiance_close(got, flux_ref, 1e-4, f"sppm host mirror {tech}")
+    hl.gvpm_host_sppm_destroy(hd)
