@@ -324,6 +324,21 @@ class Context:
                                                 gy.ctypes.data_as(N.f32p)), "gvpm_compute_gradient")
         return thr.reshape(h, w, 3), gx.reshape(h, w, 3), gy.reshape(h, w, 3)
 
+    def poisson_solve(self, throughput, dx, dy, direct=None, preset="L2D", **params):
+        """Screened-Poisson reconstruction (poisson::Solver).  Planes [h, w, 3] float32; throughput / direct may be
+        None.  preset: L1D | L1Q | L1L | L2D | L2Q; params override its fields (alpha, cg_iter_max, ...)."""
+        p = poisson_params(preset, **params)
+        h, w, _ = dx.shape
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (throughput, dx, dy, direct)]
+        ptr = [None if a is None else a.ctypes.data_as(N.f32p) for a in arrs]
+        rec = np.empty((h, w, 3), dtype=np.float32)
+        self._ck(self.lib.gvpm_poisson_solve(self.h, w, h, ptr[0], ptr[1], ptr[2], ptr[3], C.byref(p),
+                                             rec.ctypes.data_as(N.f32p)), "gvpm_poisson_solve")
+        return rec
+
+    def last_poisson_ms(self):
+        return float(self.lib.gvpm_last_poisson_ms(self.h))
+
     def sync(self):
         self._ck(self.lib.gvpm_sync(self.h), "gvpm_sync")
 
@@ -344,3 +359,15 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.gvpm_launch_count(self.h))
+
+
+def poisson_params(preset="L2D", **params):
+    """gvpm_poisson_preset + field overrides -> PoissonParams"""
+    p = N.PoissonParams()
+    if N.load_lib().gvpm_poisson_preset(preset.encode(), C.byref(p)) != 0:
+        raise ValueError(f"unknown Poisson preset {preset!r}")
+    for k, v in params.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p

@@ -50,6 +50,11 @@ cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, 
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
                      cudaStream_t st);
+size_t poisson_workspace_floats(size_t n);
+long long poisson_solve_device(const float *tp, const float *dx, const float *dy, const float *direct, int W, int H,
+                               float alpha, int irlsIterMax, float irlsRegInit, float irlsRegIter, int cgIterMax,
+                               int cgIterCheck, float cgTolerance, float *ws, float *host_rz, float *rec,
+                               cudaStream_t st);
 }  // namespace gvpm
 
 using namespace gvpm;
@@ -148,6 +153,8 @@ struct gvpm_ctx {
   bool samples_loaded = false;
   float sample_radius_max = 0.f;
   DevBuf grad_in, grad_out;
+  DevBuf poisson_io, poisson_ws;   // device copies of the four input planes + the result; solver workspace
+  float poisson_ms = 0.f;
   float build_ms = 0.f, gather_ms = 0.f;
   bool timed_build = false, timed_gather = false;
 };
@@ -408,7 +415,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->samples, &ctx->sample_counts, &ctx->mvol, &ctx->beams, &ctx->beam_bounds, &ctx->sub_pos,
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
-                    &ctx->plane_bounds, &ctx->ray_region};
+                    &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
   if (ctx->push_kernel_stream) { cudaStreamSynchronize(ctx->push_kernel_stream); cudaStreamDestroy(ctx->push_kernel_stream); }
@@ -1708,6 +1715,61 @@ int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use
   CK(cudaStreamSynchronize(ctx->stream));
   return GVPM_OK;
 }
+
+// ---- screened-Poisson reconstruction (row f-3): poisson::Solver of the reference, gvpm.cpp:610-690 -------------------
+int gvpm_poisson_preset(const char *preset, gvpm_poisson_params *p) {
+  if (!preset || !p) return GVPM_ERR_INVALID;
+  // Solver::Params::Params + setConfigPreset, Solver.cpp:59-158
+  p->alpha = 0.2f;
+  p->irls_iter_max = 1; p->irls_reg_init = 0.f; p->irls_reg_iter = 0.f;
+  p->cg_iter_max = 1; p->cg_iter_check = 100; p->cg_precond = 0; p->cg_tolerance = 0.f;
+  if (!strcmp(preset, "L1D")) { p->irls_iter_max = 20; p->irls_reg_init = 0.05f; p->irls_reg_iter = 0.5f; p->cg_iter_max = 50; }
+  else if (!strcmp(preset, "L1Q")) { p->irls_iter_max = 64; p->irls_reg_init = 1.0f; p->irls_reg_iter = 0.7f; p->cg_iter_max = 1000; }
+  else if (!strcmp(preset, "L1L")) { p->irls_iter_max = 7; p->irls_reg_init = 1.0e-4f; p->irls_reg_iter = 1.0e-1f; p->cg_iter_max = 20000; p->cg_tolerance = 1.0e-20f; }
+  else if (!strcmp(preset, "L2D")) { p->cg_iter_max = 50; }
+  else if (!strcmp(preset, "L2Q")) { p->cg_iter_max = 500; }
+  else return GVPM_ERR_INVALID;
+  return GVPM_OK;
+}
+
+int gvpm_poisson_solve(gvpm_ctx *ctx, int w, int h, const float *throughput, const float *dx, const float *dy,
+                       const float *direct, const gvpm_poisson_params *params, float *reconstruction) {
+  if (!ctx || w <= 0 || h <= 0 || !dx || !dy || !params || !reconstruction) return GVPM_ERR_INVALID;
+  if (params->cg_precond)
+    return fail(ctx, GVPM_ERR_UNSUPPORTED, "the preconditioned CG branch (cgPrecond, enabled by no preset) is not built");
+  cudaSetDevice(ctx->device);
+  // Solver::Params::sanitize, Solver.cpp:162-172
+  const float alpha = std::max(params->alpha, 0.0f);
+  const int irlsIterMax = std::max(params->irls_iter_max, 1), cgIterMax = std::max(params->cg_iter_max, 1),
+            cgIterCheck = std::max(params->cg_iter_check, 1);
+  const float irlsRegInit = std::max(params->irls_reg_init, 0.0f), irlsRegIter = std::max(params->irls_reg_iter, 0.0f),
+              cgTolerance = std::max(params->cg_tolerance, 0.0f);
+  const size_t n = (size_t)w * h, plane = 3 * n * sizeof(float);
+  CK(ctx->poisson_io.reserve(5 * plane));
+  CK(ctx->poisson_ws.reserve(poisson_workspace_floats(n) * sizeof(float)));
+  float *io = ctx->poisson_io.as<float>();
+  float *d_tp = io, *d_dx = io + 3 * n, *d_dy = io + 6 * n, *d_direct = io + 9 * n, *d_rec = io + 12 * n;
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[2], st));
+  if (throughput) CK(cudaMemcpyAsync(d_tp, throughput, plane, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dx, dx, plane, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_dy, dy, plane, cudaMemcpyHostToDevice, st));
+  if (direct) CK(cudaMemcpyAsync(d_direct, direct, plane, cudaMemcpyHostToDevice, st));
+  const long long launched = poisson_solve_device(throughput ? d_tp : nullptr, d_dx, d_dy, direct ? d_direct : nullptr, w, h,
+                                                  alpha, irlsIterMax, irlsRegInit, irlsRegIter, cgIterMax, cgIterCheck,
+                                                  cgTolerance, ctx->poisson_ws.as<float>(), (float *)ctx->pair_count_host,
+                                                  d_rec, st);
+  if (launched < 0) return fail(ctx, GVPM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += (uint64_t)launched;
+  CK(cudaMemcpyAsync(reconstruction, d_rec, plane, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->poisson_ms, ctx->ev[2], ctx->ev[3]));
+  ctx->timed_gather = false;
+  return GVPM_OK;
+}
+
+float gvpm_last_poisson_ms(const gvpm_ctx *ctx) { return ctx ? ctx->poisson_ms : 0.f; }
 
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {
   if (!ctx) return GVPM_ERR_INVALID;

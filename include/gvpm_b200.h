@@ -385,6 +385,27 @@ int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *off
 int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs,
                           float *throughput, float *gx, float *gy);
 
+/* ---- next step of the hand-off: screened-Poisson reconstruction (gvpm.cpp:610-690) -----------------------------
+ * Replaces poisson::Solver (src/integrators/poisson_solver/Solver.cpp: importImagesMTS + setupBackend +
+ * solveIndirect + exportImagesMTS) on the three planes gvpm_compute_gradient returns: iteratively reweighted least
+ * squares around conjugate gradients on P' W^2 P, P = [alpha I; Dx; Dy].  gvpm_poisson_preset fills the parameters of
+ * Solver::Params::setConfigPreset ("L1D", "L1Q", "L1L", "L2D", "L2Q"; the integrator uses L1D and L2D with
+ * alpha = reconstructAlpha).  throughput, dx, dy, direct, reconstruction: host [h*w*3], interleaved RGB, row-major;
+ * throughput and direct may be NULL (then alpha = 0, x starts at 0 / nothing is added: Solver.cpp:323,338-343,559-563).
+ * The preconditioned branch (cg_precond, which no preset enables) returns GVPM_ERR_UNSUPPORTED. */
+typedef struct gvpm_poisson_params {
+  float alpha;            /* weight of the throughput image against the gradients */
+  int32_t irls_iter_max;  /* 1 = plain L2 */
+  float irls_reg_init, irls_reg_iter;
+  int32_t cg_iter_max, cg_iter_check, cg_precond;
+  float cg_tolerance;
+} gvpm_poisson_params;
+int gvpm_poisson_preset(const char *preset, gvpm_poisson_params *p);
+int gvpm_poisson_solve(gvpm_ctx *ctx, int w, int h, const float *throughput, const float *dx, const float *dy,
+                       const float *direct, const gvpm_poisson_params *params, float *reconstruction);
+/* device time of the last gvpm_poisson_solve, copies included (CUDA events, ms) */
+float gvpm_last_poisson_ms(const gvpm_ctx *ctx);
+
 /* ---- timing of the last build / gather on the context's stream (CUDA events, ms) ----- */
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms);
 /* split of the last gather: traversal kernel, shading kernel (of the last ray range), and the number of
