@@ -397,7 +397,7 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   }
   for (auto &ev : ctx->push_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   ctx->work_counter.reserve(256);
-  cudaHostAlloc((void **)&ctx->pair_count_host, sizeof(unsigned long long), cudaHostAllocDefault);
+  cudaHostAlloc((void **)&ctx->pair_count_host, 64, cudaHostAllocDefault);  // pair / kept-photon counters, the solver's 3-float residual
   ctx->bounds.reserve(256);
   ctx->bounds_partial.reserve(1024 * 6 * sizeof(float));
   *out = ctx;

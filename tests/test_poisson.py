@@ -4,7 +4,8 @@ tests/golden/poisson_small.npz were produced by it, tests/golden/make_poisson_go
 
 Tolerances: every per-element operation is the reference's, only the summation order of the CG / IRLS reductions
 differs.  The reference's own two CPU backends (naive vs OpenMP) differ by 1e-6 (L2) to 5e-5 (L1D, 1000 CG iterations
-through 1 / (|e| + reg) weights) on these images; the bar is 1e-4 relative for L2 and 1e-3 for the L1 / early-stop cases."""
+through 1 / (|e| + reg) weights) on these images; measured on a B200 the CUDA solver is within 3e-7 (L2) and 1.3e-5
+(L1D) of the reference.  The bar: 1e-5 relative for L2, 1e-4 (north_star's radiance tolerance) for L1 / early stop."""
 import ctypes as C
 import importlib.util
 import os
@@ -21,8 +22,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "poisson_small.npz")
 _spec = importlib.util.spec_from_file_location("make_poisson_golden", os.path.join(ROOT, "tests", "golden", "make_poisson_golden.py"))
 G = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(G)
-TOL = {"L2D": 1e-4, "L2D_alpha05": 1e-4, "L2D_no_throughput": 1e-4, "L2D_no_direct": 1e-4, "L1D": 1e-3, "L1_short": 1e-3,
-       "L2_tol": 1e-3}
+TOL = {"L2D": 1e-5, "L2D_alpha05": 1e-5, "L2D_no_throughput": 1e-5, "L2D_no_direct": 1e-5, "L1D": 1e-4, "L1_short": 1e-4,
+       "L2_tol": 1e-4}
 needs_ref = pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libgvpm_poisson_ref.so not built (no /root/reference)")
 
 
