@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons", "gvpm_peer_push_mode",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
-    "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
+    "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_reconstruct", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
     "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
     "gvpm_gather_sppm_beams", "gvpm_dump_neighbours_sppm_beams",
@@ -145,6 +145,7 @@ def load_lib():
     lib.gvpm_compute_gradient.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p]
     lib.gvpm_poisson_preset.argtypes = [C.c_char_p, C.POINTER(PoissonParams)]
     lib.gvpm_poisson_solve.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, f32p, C.POINTER(PoissonParams), f32p]
+    lib.gvpm_reconstruct.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int, f32p, C.POINTER(PoissonParams), f32p, f32p, f32p, f32p]
     lib.gvpm_last_poisson_ms.argtypes = [vp]
     lib.gvpm_last_poisson_ms.restype = C.c_float
     lib.gvpm_last_timings.argtypes = [vp, f32p, f32p]

@@ -336,6 +336,19 @@ class Context:
                                              rec.ctypes.data_as(N.f32p)), "gvpm_poisson_solve")
         return rec
 
+    def reconstruct(self, acc, w, h, direct=None, preset="L2D", use_abs=False, **params):
+        """computeGradient + Poisson reconstruction in one call -> (throughput, gx, gy, reconstruction), [h, w, 3]."""
+        p = poisson_params(preset, **params)
+        acc = np.ascontiguousarray(acc, dtype=np.float32).reshape(-1)
+        assert acc.size == w * h * N.GVPM_OUT_FLOATS
+        d = None if direct is None else np.ascontiguousarray(direct, dtype=np.float32)
+        thr, gx, gy, rec = (np.empty((h, w, 3), dtype=np.float32) for _ in range(4))
+        self._ck(self.lib.gvpm_reconstruct(self.h, acc.ctypes.data_as(N.f32p), w, h, int(use_abs),
+                                           None if d is None else d.ctypes.data_as(N.f32p), C.byref(p),
+                                           thr.ctypes.data_as(N.f32p), gx.ctypes.data_as(N.f32p),
+                                           gy.ctypes.data_as(N.f32p), rec.ctypes.data_as(N.f32p)), "gvpm_reconstruct")
+        return thr, gx, gy, rec
+
     def last_poisson_ms(self):
         return float(self.lib.gvpm_last_poisson_ms(self.h))
 

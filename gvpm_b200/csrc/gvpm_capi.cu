@@ -1769,6 +1769,44 @@ int gvpm_poisson_solve(gvpm_ctx *ctx, int w, int h, const float *throughput, con
   return GVPM_OK;
 }
 
+// computeGradient + reconstruction in one call: the three planes never leave the device (gvpm.cpp:554-690)
+int gvpm_reconstruct(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, const float *direct,
+                     const gvpm_poisson_params *params, float *throughput, float *gx, float *gy, float *reconstruction) {
+  if (!ctx || !acc || w <= 0 || h <= 0 || !params || !reconstruction) return GVPM_ERR_INVALID;
+  if (params->cg_precond)
+    return fail(ctx, GVPM_ERR_UNSUPPORTED, "the preconditioned CG branch (cgPrecond, enabled by no preset) is not built");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)w * h, plane = 3 * n * sizeof(float);
+  CK(ctx->grad_in.reserve(n * GVPM_OUT_FLOATS * 4));
+  CK(ctx->grad_out.reserve(n * 9 * 4));
+  CK(ctx->poisson_io.reserve(5 * plane));
+  CK(ctx->poisson_ws.reserve(poisson_workspace_floats(n) * sizeof(float)));
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[2], st));
+  CK(cudaMemcpyAsync(ctx->grad_in.p, acc, n * GVPM_OUT_FLOATS * 4, cudaMemcpyHostToDevice, st));
+  float *o = ctx->grad_out.as<float>(), *io = ctx->poisson_io.as<float>();
+  float *d_direct = io + 9 * n, *d_rec = io + 12 * n;
+  if (direct) CK(cudaMemcpyAsync(d_direct, direct, plane, cudaMemcpyHostToDevice, st));
+  launch_gradient(ctx->grad_in.as<float>(), w, h, use_abs, o, o + 3 * n, o + 6 * n, st);
+  ctx->launches += 1;
+  const long long launched = poisson_solve_device(
+      o, o + 3 * n, o + 6 * n, direct ? d_direct : nullptr, w, h, std::max(params->alpha, 0.0f),
+      std::max(params->irls_iter_max, 1), std::max(params->irls_reg_init, 0.0f), std::max(params->irls_reg_iter, 0.0f),
+      std::max(params->cg_iter_max, 1), std::max(params->cg_iter_check, 1), std::max(params->cg_tolerance, 0.0f),
+      ctx->poisson_ws.as<float>(), (float *)ctx->pair_count_host, d_rec, st);
+  if (launched < 0) return fail(ctx, GVPM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += (uint64_t)launched;
+  if (throughput) CK(cudaMemcpyAsync(throughput, o, plane, cudaMemcpyDeviceToHost, st));
+  if (gx) CK(cudaMemcpyAsync(gx, o + 3 * n, plane, cudaMemcpyDeviceToHost, st));
+  if (gy) CK(cudaMemcpyAsync(gy, o + 6 * n, plane, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(reconstruction, d_rec, plane, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->poisson_ms, ctx->ev[2], ctx->ev[3]));
+  ctx->timed_gather = false;
+  return GVPM_OK;
+}
+
 float gvpm_last_poisson_ms(const gvpm_ctx *ctx) { return ctx ? ctx->poisson_ms : 0.f; }
 
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {

@@ -403,7 +403,11 @@ typedef struct gvpm_poisson_params {
 int gvpm_poisson_preset(const char *preset, gvpm_poisson_params *p);
 int gvpm_poisson_solve(gvpm_ctx *ctx, int w, int h, const float *throughput, const float *dx, const float *dy,
                        const float *direct, const gvpm_poisson_params *params, float *reconstruction);
-/* device time of the last gvpm_poisson_solve, copies included (CUDA events, ms) */
+/* gvpm_compute_gradient + gvpm_poisson_solve in one call: the accumulators go up once, throughput / gx / gy stay on
+ * the device between the two steps (each may be NULL when the caller does not want the plane back). */
+int gvpm_reconstruct(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, const float *direct,
+                     const gvpm_poisson_params *params, float *throughput, float *gx, float *gy, float *reconstruction);
+/* device time of the last gvpm_poisson_solve / gvpm_reconstruct, copies included (CUDA events, ms) */
 float gvpm_last_poisson_ms(const gvpm_ctx *ctx);
 
 /* ---- timing of the last build / gather on the context's stream (CUDA events, ms) ----- */

@@ -126,3 +126,24 @@ def test_gpu_solver_errors(built):
     with pytest.raises(ValueError):
         ctx.poisson_solve(z["throughput"], z["dx"], z["dy"], None, preset="nope")
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reconstruct_fuses_gradient_and_solve(built):
+    """gvpm_reconstruct == gvpm_compute_gradient followed by gvpm_poisson_solve, bit for bit (same kernels, the planes
+    just stay on the device)."""
+    from gvpm_b200.api import Context
+    rng = np.random.default_rng(9)
+    w, h = 52, 36
+    acc = rng.uniform(0.0, 2.0, (h, w, 27)).astype(np.float32)
+    direct = rng.uniform(0.0, 0.2, (h, w, 3)).astype(np.float32)
+    ctx = Context(0)
+    thr, gx, gy = ctx.compute_gradient(acc, w, h)
+    for preset in ("L2D", "L1D"):
+        want = ctx.poisson_solve(thr, gx, gy, direct, preset=preset, alpha=0.25)
+        t2, x2, y2, rec = ctx.reconstruct(acc, w, h, direct, preset=preset, alpha=0.25)
+        np.testing.assert_array_equal(t2, thr)
+        np.testing.assert_array_equal(x2, gx)
+        np.testing.assert_array_equal(y2, gy)
+        np.testing.assert_array_equal(rec, want)
+    ctx.close()
