@@ -296,7 +296,10 @@ def workload_config(args, inp, world):
                             "reach, results gathered to rank 0" if shard_mode(world) == "band" else
                             f"image tiles (32x32) round-robin over {world} GPU(s), photon set broadcast, results "
                             "gathered to rank 0"),
-            "l2": "inputs larger than L2 (photon records 1.1 GB, rays 0.66 GB): no flush needed"}
+            "l2": (f"photon records {inp['n_ph'] * 128 / 1e9:.2f} GB + rays {inp['rays_full_n'] * 320 / 1e9:.2f} GB per step "
+                   "against a 126 MB L2: " + ("inputs larger than L2, no flush needed"
+                                              if inp["n_ph"] * 128 + inp["rays_full_n"] * 320 > 4 * 126e6
+                                              else "SMALLER than 4x L2 - parity-sized workload, not a bench configuration"))}
 
 
 def diag_phases(v):
