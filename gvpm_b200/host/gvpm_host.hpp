@@ -223,6 +223,17 @@ class VolumeGatherB200 {
           "gvpm_compute_gradient");
   }
 
+  // gvpm.cpp:554-690: computeGradient + poisson::Solver (preset "L2D" for reconstructL2, "L1D" for reconstructL1,
+  // alpha = reconstructAlpha) in one device round trip.  direct may be null; throughput / gX / gY may be null.
+  void reconstruct(const char *preset, float reconstructAlpha, bool useAbs, const float *direct, float *throughput,
+                   float *gX, float *gY, float *reconstruction) {
+    gvpm_poisson_params p;
+    check(gvpm_poisson_preset(preset, &p), "gvpm_poisson_preset");
+    p.alpha = reconstructAlpha;
+    check(gvpm_reconstruct(m_ctx, m_acc.data(), m_w, m_h, useAbs ? 1 : 0, direct, &p, throughput, gX, gY, reconstruction),
+          "gvpm_reconstruct");
+  }
+
   const std::vector<float> &accumulators() const { return m_acc; }
   const std::vector<uint8_t> &haveSmoke() const { return m_haveSmoke; }
   gvpm_ctx *context() { return m_ctx; }

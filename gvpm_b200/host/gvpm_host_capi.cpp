@@ -53,6 +53,11 @@ int gvpm_host_gradient(void *h, float *thr, float *gx, float *gy, int useAbs, ch
   try { ((VolumeGatherB200 *)h)->computeGradient(thr, gx, gy, useAbs != 0); return 0; }
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
 }
+int gvpm_host_reconstruct(void *h, const char *preset, float alpha, int useAbs, const float *direct, float *thr, float *gx,
+                          float *gy, float *rec, char *err, size_t errlen) {
+  try { ((VolumeGatherB200 *)h)->reconstruct(preset, alpha, useAbs != 0, direct, thr, gx, gy, rec); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
 double gvpm_host_scale(void *h) { return ((VolumeGatherB200 *)h)->globalScaleVolume; }
 float gvpm_host_radius(void *h) { return ((VolumeGatherB200 *)h)->currentRadius(); }
 const float *gvpm_host_accumulators(void *h) { return ((VolumeGatherB200 *)h)->accumulators().data(); }
