@@ -18,9 +18,11 @@
 // photonMapPass.  Errors: the reference raises through SLog(EError) (a
 // std::runtime_error); so does this shim, carrying gvpm_last_error().
 #pragma once
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -42,6 +44,140 @@ struct GPMConfig {
   bool use3DKernelReduction = false;
   std::string forceAPA;               // "", "1D", "2D", "3D"
 };
+
+// Stand-in for mitsuba::Properties as GPMConfig::load uses it (include/mitsuba/core/properties.h): typed getters with
+// a default, values kept as the strings of the scene XML.  A Mitsuba build passes its own Properties instead.
+class Properties {
+ public:
+  void set(const std::string &key, const std::string &value) { m_values[key] = value; }
+  bool has(const std::string &key) const { return m_values.count(key) != 0; }
+  std::string getString(const std::string &key, const std::string &def) const {
+    auto it = m_values.find(key);
+    return it == m_values.end() ? def : it->second;
+  }
+  bool getBoolean(const std::string &key, bool def) const {
+    if (!has(key)) return def;
+    const std::string v = getString(key, "");
+    if (v == "true") return true;
+    if (v == "false") return false;
+    throw std::runtime_error("Property \"" + key + "\" has the wrong type (expected <boolean>).");
+  }
+  long getInteger(const std::string &key, long def) const {
+    if (!has(key)) return def;
+    size_t used = 0;
+    const std::string v = getString(key, "");
+    long r = 0;
+    try { r = std::stol(v, &used); } catch (...) { used = 0; }
+    if (used != v.size() || v.empty()) throw std::runtime_error("Property \"" + key + "\" has the wrong type (expected <integer>).");
+    return r;
+  }
+  double getFloat(const std::string &key, double def) const {
+    if (!has(key)) return def;
+    size_t used = 0;
+    const std::string v = getString(key, "");
+    double r = 0;
+    try { r = std::stod(v, &used); } catch (...) { used = 0; }
+    if (used != v.size() || v.empty()) throw std::runtime_error("Property \"" + key + "\" has the wrong type (expected <float>).");
+    return r;
+  }
+
+ private:
+  std::map<std::string, std::string> m_values;
+};
+
+// The further GPMConfig members that GPMConfig::load reads next to the gather's own (gvpm_struct.h:106-176), for the
+// host code around the gather: same names, same defaults.
+struct GPMConfigExtra {
+  int rrDepth = 12, photonCount = 250000, volumePhotonCount = 250000, maxPasses = -1, dumpIteration = 5;
+  bool reconstructL1 = false, reconstructL2 = true;
+  double reconstructAlpha = 0.2;
+  bool useManifold = true, noMediumShift = true, convertLong = false, newShiftBeam = false, deterministic = false;
+  int nbCameraSamples = 40;
+  long minCameraDepth = 0;
+  int maxCameraDepth = -1;
+  double cameraSphere = 1.0;
+};
+
+// parseVolumeTechnique (src/integrators/volume_utils.h:54-92) restricted to what the gvpm gather serves:
+// "distance" is the point-photon (G-VPM) path of computeVolumeGradientPhoton, gvpm.cpp:1081-1203; BeamKernelRecord::eval
+// has no naive / EGSR branch in gvpm (shift_volume_beams.h:169,195,285-287).
+inline int parseVolumeTechnique(const std::string &volRenderingTech) {
+  if (volRenderingTech == "distance") return EVolVPM;
+  if (volRenderingTech == "bre" || volRenderingTech == "bre3d") return EVolBRE3D;
+  if (volRenderingTech == "bre2d") return EVolBRE2D;
+  if (volRenderingTech == "beam" || volRenderingTech == "beam1d") return EVolBeam1D;
+  if (volRenderingTech == "beam3d" || volRenderingTech == "beam3d_optimized") return EVolBeam3D;
+  if (volRenderingTech == "beam3d_naive" || volRenderingTech == "beam3d_egsr") throw std::runtime_error("Not supported kernel type");
+  if (volRenderingTech == "plane0d") return EVolPlane0D;
+  throw std::runtime_error("Unknow vol technique: " + volRenderingTech);
+}
+// parseMediaInteractionMode, volume_utils.h:109-128 (ELightingEffects bits)
+inline int parseMediaInteractionMode(const std::string &m) {
+  if (m == "all2media") return (1 << 2) | (1 << 4);
+  if (m == "all2surf") return (1 << 1) | (1 << 3);
+  if (m == "surf2surf") return 1 << 1;
+  if (m == "media2surf") return 1 << 3;
+  if (m == "surf2media") return 1 << 2;
+  if (m == "media2media") return 1 << 4;
+  if (m == "all2all") return (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4);
+  throw std::runtime_error("Invalid media interaction mode: " + m);
+}
+
+// GPMConfig::load (gvpm_struct.h:181-333) + the GPMIntegrator constructor's fix-up (gvpm.cpp:93-98): the plugin's XML
+// parameters, their defaults and their error conditions.  SLog(EError, ...) throws, as in the reference.
+inline void loadGPMConfig(const Properties &props, GPMConfig &c, GPMConfigExtra &x) {
+  auto lower = [](std::string s) { for (char &ch : s) ch = (char)std::tolower((unsigned char)ch); return s; };
+  x.newShiftBeam = props.getBoolean("newShiftBeam", false);
+  c.initialScaleVolume = props.getFloat("initialScaleVolume", 1.0);
+  c.use3DKernelReduction = props.getBoolean("use3DKernelReduction", false);
+  c.forceAPA = props.getString("forceAPA", "");
+  x.noMediumShift = props.getBoolean("noMediumShift", true);
+  c.powerHeuristic = props.getBoolean("powerHeuristic", false);
+  const double relaxME = props.getFloat("relaxME", 1.0);
+  if (relaxME != 0.0 && relaxME != 1.0) throw std::runtime_error("relaxME options need to be 0 or 1.");
+  c.alpha = props.getFloat("alpha", .7);
+  x.photonCount = (int)props.getInteger("photonCount", 250000);
+  x.volumePhotonCount = (int)props.getInteger("volumePhotonCount", 250000);
+  c.maxDepth = (int)props.getInteger("maxDepth", -1);
+  c.minDepth = (int)props.getInteger("minDepth", 0);
+  x.rrDepth = (int)props.getInteger("rrDepth", 12);
+  x.maxPasses = (int)props.getInteger("maxPasses", -1);
+  if (c.maxDepth <= 1 && c.maxDepth != -1) throw std::runtime_error("Maximum depth must be set to \"2\" or higher!");
+  if (x.maxPasses <= 0 && x.maxPasses != -1)
+    throw std::runtime_error("Maximum number of passes must either be set to \"-1\" or \"1\" or higher!");
+  x.dumpIteration = (int)props.getInteger("dumpIteration", 5);
+  x.reconstructL1 = props.getBoolean("reconstructL1", false);
+  x.reconstructL2 = props.getBoolean("reconstructL2", true);
+  x.reconstructAlpha = props.getFloat("reconstructAlpha", 0.2);
+  const double bounceRoughness = props.getFloat("bounceRoughness", 0.001);
+  if (bounceRoughness <= 0.0 || bounceRoughness > 1.0) throw std::runtime_error("Bad roughtness constant: " + std::to_string(bounceRoughness));
+  x.useManifold = props.getBoolean("useManifold", true);
+  const std::string mis = lower(props.getString("useMIS", "area"));
+  if (mis == "area") c.useMIS = true;
+  else if (mis == "none") c.useMIS = false;
+  else throw std::runtime_error("useMIS: need to be 'none' or 'area'");
+  std::string strLightingMode = props.getString("lightingInteractionMode", "");
+  if (strLightingMode.empty()) strLightingMode = props.getString("interactionMode", "all2all");
+  c.lightingInteractionMode = parseMediaInteractionMode(strLightingMode);
+  x.convertLong = props.getBoolean("convertLong", false);
+  c.volTechnique = parseVolumeTechnique(props.getString("volTechnique", "distance"));
+  if (!(c.lightingInteractionMode & ((1 << 1) | (1 << 3)))) x.photonCount = 0;         // !needSurfaceRendering()
+  if (!(c.lightingInteractionMode & ((1 << 2) | (1 << 4)))) x.volumePhotonCount = 0;   // !needVolumeRendering()
+  c.useShiftNull = props.getBoolean("useShiftNull", false);
+  x.nbCameraSamples = (int)props.getInteger("nbCameraSamples", 40);
+  const bool use3DKernel = c.volTechnique == EVolVPM || c.volTechnique == EVolBRE3D || c.volTechnique == EVolBeam3D;
+  if (c.useShiftNull && !use3DKernel && c.volTechnique != EVolBeam1D)
+    throw std::runtime_error("Not possible to shift null without using 3D kernel");
+  x.minCameraDepth = props.getInteger("minCameraDepth", 0);
+  if (x.minCameraDepth < 0) throw std::runtime_error("minCamera depth need to be null or positive");
+  x.maxCameraDepth = (int)props.getInteger("maxCameraDepth", -1);
+  x.deterministic = props.getBoolean("deterministic", false);
+  x.cameraSphere = props.getFloat("cameraSphere", 1.0);
+  c.pathSet = props.getBoolean("pathSet", true);
+  if (c.pathSet && x.deterministic)
+    throw std::runtime_error("It is not possible to use pathSet and deterministic option at the same time");
+  if (c.volTechnique == EVolBeam1D) x.newShiftBeam = true;   // "Use the correct fix here", gvpm.cpp:96-98
+}
 
 // GPMIntegrator::scaleVolumeAPA, gvpm.cpp:181-215 (m_independentScale = false): host-side, double.
 inline void scaleVolumeAPA(double &globalScaleVolume, int it, const GPMConfig &config) {

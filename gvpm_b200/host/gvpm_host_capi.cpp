@@ -31,6 +31,46 @@ static GPMConfig to_cfg(const gvpm_host_params *p) {
   return c;
 }
 
+// GPMConfig::load on "key=value" lines (what the scene XML's <integrator type="gvpm"> block holds): no device needed
+struct gvpm_host_extra {
+  int rrDepth, photonCount, volumePhotonCount, maxPasses, dumpIteration, reconstructL1, reconstructL2;
+  double reconstructAlpha;
+  int useManifold, noMediumShift, convertLong, newShiftBeam, deterministic, nbCameraSamples, minCameraDepth, maxCameraDepth;
+  double cameraSphere;
+};
+int gvpm_host_config_load(const char *text, gvpm_host_params *out, gvpm_host_extra *extra, char *err, size_t errlen) {
+  try {
+    Properties props;
+    std::string all(text ? text : ""), line;
+    size_t pos = 0;
+    while (pos <= all.size()) {
+      const size_t nl = all.find('\n', pos);
+      line = all.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+      pos = nl == std::string::npos ? all.size() + 1 : nl + 1;
+      const size_t eq = line.find('=');
+      if (eq != std::string::npos) props.set(line.substr(0, eq), line.substr(eq + 1));
+    }
+    GPMConfig c;
+    GPMConfigExtra x;
+    loadGPMConfig(props, c, x);
+    out->maxDepth = c.maxDepth; out->minDepth = c.minDepth; out->alpha = c.alpha;
+    out->initialScaleVolume = c.initialScaleVolume; out->volTechnique = c.volTechnique;
+    out->lightingInteractionMode = c.lightingInteractionMode; out->useMIS = c.useMIS; out->useShiftNull = c.useShiftNull;
+    out->pathSet = c.pathSet; out->powerHeuristic = c.powerHeuristic; out->use3DKernelReduction = c.use3DKernelReduction;
+    memset(out->forceAPA, 0, sizeof(out->forceAPA));
+    strncpy(out->forceAPA, c.forceAPA.c_str(), sizeof(out->forceAPA) - 1);
+    if (extra) {
+      extra->rrDepth = x.rrDepth; extra->photonCount = x.photonCount; extra->volumePhotonCount = x.volumePhotonCount;
+      extra->maxPasses = x.maxPasses; extra->dumpIteration = x.dumpIteration; extra->reconstructL1 = x.reconstructL1;
+      extra->reconstructL2 = x.reconstructL2; extra->reconstructAlpha = x.reconstructAlpha; extra->useManifold = x.useManifold;
+      extra->noMediumShift = x.noMediumShift; extra->convertLong = x.convertLong; extra->newShiftBeam = x.newShiftBeam;
+      extra->deterministic = x.deterministic; extra->nbCameraSamples = x.nbCameraSamples;
+      extra->minCameraDepth = (int)x.minCameraDepth; extra->maxCameraDepth = x.maxCameraDepth; extra->cameraSphere = x.cameraSphere;
+    }
+    return 0;
+  } catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+
 // the radius-reduction schedule alone (no device needed)
 int gvpm_host_scale_apa(double *scale, int it, const gvpm_host_params *p, char *err, size_t errlen) {
   try { scaleVolumeAPA(*scale, it, to_cfg(p)); return 0; }

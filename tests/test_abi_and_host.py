@@ -102,6 +102,69 @@ def test_scale_volume_apa_schedule(tech, force, expo):
     assert b"No Force APA" in err.value
 
 
+class HostExtra(C.Structure):
+    _fields_ = [("rrDepth", C.c_int), ("photonCount", C.c_int), ("volumePhotonCount", C.c_int), ("maxPasses", C.c_int),
+                ("dumpIteration", C.c_int), ("reconstructL1", C.c_int), ("reconstructL2", C.c_int),
+                ("reconstructAlpha", C.c_double), ("useManifold", C.c_int), ("noMediumShift", C.c_int),
+                ("convertLong", C.c_int), ("newShiftBeam", C.c_int), ("deterministic", C.c_int),
+                ("nbCameraSamples", C.c_int), ("minCameraDepth", C.c_int), ("maxCameraDepth", C.c_int),
+                ("cameraSphere", C.c_double)]
+
+
+def _load_config(text):
+    h = _host()
+    p, x = HostParams(), HostExtra()
+    err = C.create_string_buffer(512)
+    rc = h.gvpm_host_config_load(text.encode(), C.byref(p), C.byref(x), err, 512)
+    return rc, p, x, err.value.decode()
+
+
+def test_gpm_config_load_defaults_and_paper_preset():
+    """GPMConfig::load (gvpm_struct.h:181-333): XML parameter names, defaults, string parsing."""
+    rc, p, x, err = _load_config("")
+    assert rc == 0, err
+    # plugin defaults: volTechnique "distance" (point photons), all2all, MIS by area, no mixed shift, pathSet on
+    assert (p.maxDepth, p.minDepth, p.volTechnique, p.useMIS, p.useShiftNull, p.pathSet, p.powerHeuristic) == (-1, 0, 2, 1, 0, 1, 0)
+    assert p.lightingInteractionMode == 0b11110 and p.alpha == pytest.approx(0.7) and p.initialScaleVolume == 1.0
+    assert (x.rrDepth, x.photonCount, x.volumePhotonCount, x.maxPasses, x.nbCameraSamples) == (12, 250000, 250000, -1, 40)
+    assert (x.reconstructL1, x.reconstructL2, x.newShiftBeam) == (0, 1, 0) and x.reconstructAlpha == pytest.approx(0.2)
+    # the paper's generator script (scripts/scene/generatorGVPM.py:44-76): G-BRE 3D, mixed shift, volume only
+    rc, p, x, err = _load_config("volTechnique=bre\nuseShiftNull=true\nuseMIS=Area\nmaxDepth=12\nrrDepth=1\n"
+                                 "interactionMode=all2media\ninitialScaleVolume=0.1\nvolumePhotonCount=10000000")
+    assert rc == 0, err
+    assert (p.volTechnique, p.useShiftNull, p.useMIS, p.maxDepth, x.rrDepth) == (1, 1, 1, 12, 1)
+    assert p.lightingInteractionMode == (1 << 2) | (1 << 4) and p.initialScaleVolume == pytest.approx(0.1)
+    assert x.photonCount == 0 and x.volumePhotonCount == 10000000      # surface photons forced to 0 (:304-306)
+    for name, tech in (("bre2d", 0), ("bre3d", 1), ("distance", 2), ("beam3d", 3), ("beam3d_optimized", 3),
+                       ("plane0d", 4), ("beam", 5), ("beam1d", 5)):
+        rc, p, x, err = _load_config(f"volTechnique={name}")
+        assert rc == 0 and p.volTechnique == tech, (name, err)
+        assert x.newShiftBeam == (1 if tech == 5 else 0)               # gvpm.cpp:96-98
+    rc, p, x, err = _load_config("lightingInteractionMode=media2media\ninteractionMode=all2surf")
+    assert rc == 0 and p.lightingInteractionMode == 1 << 4               # the first key wins (:291-294)
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("maxDepth=1", "Maximum depth must be set"),
+    ("maxPasses=0", "Maximum number of passes"),
+    ("useMIS=balance", "useMIS: need to be 'none' or 'area'"),
+    ("relaxME=0.5", "relaxME options need to be 0 or 1."),
+    ("volTechnique=bre2d\nuseShiftNull=true", "Not possible to shift null without using 3D kernel"),
+    ("volTechnique=raymarching", "Unknow vol technique"),
+    ("volTechnique=beam3d_egsr", "Not supported kernel type"),
+    ("interactionMode=some2all", "Invalid media interaction mode"),
+    ("deterministic=true", "pathSet and deterministic"),
+    ("minCameraDepth=-1", "minCamera depth"),
+    ("bounceRoughness=0", "Bad roughtness constant"),
+    ("pathSet=maybe", "wrong type"),
+    ("maxDepth=twelve", "wrong type"),
+])
+def test_gpm_config_load_errors(text, msg):
+    """SLog(EError, ...) of GPMConfig::load becomes an exception with the reference's message."""
+    rc, _, _, err = _load_config(text)
+    assert rc == -1 and msg in err, (text, err)
+
+
 class SppmHostParams(C.Structure):
     _fields_ = [("maxDepth", C.c_int), ("minDepth", C.c_int), ("alpha", C.c_double), ("initialScaleVolume", C.c_double),
                 ("volTechnique", C.c_int), ("rngSeed", C.c_uint), ("forceAPA", C.c_char * 8)]
