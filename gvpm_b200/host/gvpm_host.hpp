@@ -423,7 +423,8 @@ inline void scaleVolumeAPA(double &globalScaleVolume, int it, const SPPMConfig &
   it -= 1;
   const double ratioVolAPA = (it + config.alpha) / (it + 1);
   const int t = config.volTechnique;
-  const bool use3D = t == ESppmBRE3D || t == ESppmBeam3DNaive || t == ESppmBeam3DEGSR || t == ESppmBeam3DOptimized;
+  const bool use3D = t == ESppmBRE3D || t == ESppmBeam3DNaive || t == ESppmBeam3DEGSR || t == ESppmBeam3DOptimized ||
+                     t == 6 /* ESppmDistance: EVolumeTechniqueHelper::use3DKernel counts EDistance */;
   if (config.forceAPA.empty()) {
     if (use3D) globalScaleVolume *= std::cbrt(ratioVolAPA);
     else if (t == ESppmBRE2D) globalScaleVolume *= std::sqrt(ratioVolAPA);
@@ -437,6 +438,59 @@ inline void scaleVolumeAPA(double &globalScaleVolume, int it, const SPPMConfig &
   } else {
     throw std::runtime_error("No Force APA: " + config.forceAPA);
   }
+}
+
+// SPPMIntegrator's constructor (sppm.cpp:163-241): the plugin's XML parameters, defaults and error conditions.
+struct SPPMConfigExtra {
+  int photonCount = 250000, volumePhotonCount = 250000, rrDepth = 3, maxPasses = -1, dumpIteration = 5, nbCameraSamples = 40;
+  bool surfaceRendering = true, volumeRendering = true, convertLong = false, deterministic = false;
+  long minCameraDepth = 0;
+  int maxCameraDepth = -1;
+  double cameraSphere = 1.0;
+};
+// techniques the sppm plugin parses but this mirror has no pass for (the calls exist in the C ABI: gvpm_gather_vpm /
+// gvpm_gather_planes without offsets)
+enum { ESppmDistance = 6, ESppmPlane0D = 7 };
+inline void loadSPPMConfig(const Properties &props, SPPMConfig &c, SPPMConfigExtra &x) {
+  c.initialScaleVolume = props.getFloat("initialScaleVolume", 1.0);
+  c.alpha = props.getFloat("alpha", .7);
+  x.photonCount = (int)props.getInteger("photonCount", 250000);
+  x.volumePhotonCount = (int)props.getInteger("volumePhotonCount", 250000);
+  c.maxDepth = (int)props.getInteger("maxDepth", -1);
+  c.minDepth = (int)props.getInteger("minDepth", 0);
+  x.rrDepth = (int)props.getInteger("rrDepth", 3);
+  x.maxPasses = (int)props.getInteger("maxPasses", -1);
+  if (c.maxDepth <= 1 && c.maxDepth != -1) throw std::runtime_error("Maximum depth must be set to \"2\" or higher!");
+  if (x.maxPasses <= 0 && x.maxPasses != -1)
+    throw std::runtime_error("Maximum number of Passes must either be set to \"-1\" or \"1\" or higher!");
+  const long maxRenderingTime = props.getInteger("maxRenderingTime", 2147483647L);
+  x.dumpIteration = (int)props.getInteger("dumpIteration", 5);
+  if (maxRenderingTime != 2147483647L && x.maxPasses != 2147483647)   // as written (:196-198)
+    throw std::runtime_error("Max pass and time is incompatible!");
+  x.surfaceRendering = props.getBoolean("surfaceRendering", true);
+  x.volumeRendering = props.getBoolean("volumeRendering", true);
+  // the default "raymarching" is not a name parseVolumeTechnique knows: the scene has to choose one (:208-209)
+  const std::string t = props.getString("volTechnique", "raymarching");
+  if (t == "distance") c.volTechnique = ESppmDistance;
+  else if (t == "bre" || t == "bre3d") c.volTechnique = ESppmBRE3D;
+  else if (t == "bre2d") c.volTechnique = ESppmBRE2D;
+  else if (t == "beam" || t == "beam1d") c.volTechnique = ESppmBeam1D;
+  else if (t == "beam3d" || t == "beam3d_optimized") c.volTechnique = ESppmBeam3DOptimized;
+  else if (t == "beam3d_naive") c.volTechnique = ESppmBeam3DNaive;
+  else if (t == "beam3d_egsr") c.volTechnique = ESppmBeam3DEGSR;
+  else if (t == "plane0d") c.volTechnique = ESppmPlane0D;
+  else throw std::runtime_error("Unknow vol technique: " + t);
+  x.convertLong = props.getBoolean("convertLong", false);
+  x.deterministic = props.getBoolean("deterministic", false);
+  x.nbCameraSamples = (int)props.getInteger("nbCameraSamples", 40);
+  if (x.surfaceRendering && x.photonCount == 0) throw std::runtime_error("No surface photons and need to render surfaces LT");
+  if (x.volumeRendering && x.volumePhotonCount == 0)
+    throw std::runtime_error("No volume photons/beams and need to render volume LT");
+  x.minCameraDepth = props.getInteger("minCameraDepth", 0);
+  if (x.minCameraDepth < 0) throw std::runtime_error("minCamera depth need to be null or positive");
+  x.maxCameraDepth = (int)props.getInteger("maxCameraDepth", -1);
+  x.cameraSphere = props.getFloat("cameraSphere", 1.0);
+  c.forceAPA = props.getString("forceAPA", "");
 }
 
 // One Spectrum per pixel: GatherPoint::fluxVol (photonmapper/gatherpoint.h), the APA running mean of sppm.cpp:871,992.

@@ -116,6 +116,45 @@ static SPPMConfig to_sppm(const gvpm_host_sppm_params *p) {
   c.volTechnique = p->volTechnique; c.rngSeed = p->rngSeed; c.forceAPA = p->forceAPA;
   return c;
 }
+struct gvpm_host_sppm_extra {
+  int photonCount, volumePhotonCount, rrDepth, maxPasses, dumpIteration, nbCameraSamples, surfaceRendering, volumeRendering,
+      convertLong, deterministic, minCameraDepth, maxCameraDepth;
+  double cameraSphere;
+};
+static Properties parse_props(const char *text) {
+  Properties props;
+  std::string all(text ? text : "");
+  size_t pos = 0;
+  while (pos <= all.size()) {
+    const size_t nl = all.find('\n', pos);
+    const std::string line = all.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+    pos = nl == std::string::npos ? all.size() + 1 : nl + 1;
+    const size_t eq = line.find('=');
+    if (eq != std::string::npos) props.set(line.substr(0, eq), line.substr(eq + 1));
+  }
+  return props;
+}
+int gvpm_host_sppm_config_load(const char *text, gvpm_host_sppm_params *out, gvpm_host_sppm_extra *extra, char *err,
+                               size_t errlen) {
+  try {
+    SPPMConfig c;
+    SPPMConfigExtra x;
+    loadSPPMConfig(parse_props(text), c, x);
+    out->maxDepth = c.maxDepth; out->minDepth = c.minDepth; out->alpha = c.alpha;
+    out->initialScaleVolume = c.initialScaleVolume; out->volTechnique = c.volTechnique; out->rngSeed = c.rngSeed;
+    memset(out->forceAPA, 0, sizeof(out->forceAPA));
+    strncpy(out->forceAPA, c.forceAPA.c_str(), sizeof(out->forceAPA) - 1);
+    if (extra) {
+      extra->photonCount = x.photonCount; extra->volumePhotonCount = x.volumePhotonCount; extra->rrDepth = x.rrDepth;
+      extra->maxPasses = x.maxPasses; extra->dumpIteration = x.dumpIteration; extra->nbCameraSamples = x.nbCameraSamples;
+      extra->surfaceRendering = x.surfaceRendering; extra->volumeRendering = x.volumeRendering;
+      extra->convertLong = x.convertLong; extra->deterministic = x.deterministic;
+      extra->minCameraDepth = (int)x.minCameraDepth; extra->maxCameraDepth = x.maxCameraDepth;
+      extra->cameraSphere = x.cameraSphere;
+    }
+    return 0;
+  } catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
 int gvpm_host_sppm_scale_apa(double *scale, int it, const gvpm_host_sppm_params *p, char *err, size_t errlen) {
   try { scaleVolumeAPA(*scale, it, to_sppm(p)); return 0; }
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }

@@ -188,6 +188,43 @@ def test_sppm_scale_volume_apa_schedule(tech, force, expo):
     assert h.gvpm_host_sppm_scale_apa(C.byref(s), 1, C.byref(p), err, 256) == -1 and b"No Force APA" in err.value
 
 
+class SppmHostExtra(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("photonCount", "volumePhotonCount", "rrDepth", "maxPasses", "dumpIteration",
+                                       "nbCameraSamples", "surfaceRendering", "volumeRendering", "convertLong",
+                                       "deterministic", "minCameraDepth", "maxCameraDepth")] + [("cameraSphere", C.c_double)]
+
+
+def _load_sppm(text):
+    h = _host()
+    p, x = SppmHostParams(), SppmHostExtra()
+    err = C.create_string_buffer(512)
+    rc = h.gvpm_host_sppm_config_load(text.encode(), C.byref(p), C.byref(x), err, 512)
+    return rc, p, x, err.value.decode()
+
+
+def test_sppm_config_load():
+    """SPPMIntegrator's constructor (sppm.cpp:163-241): names, defaults, technique strings, error messages."""
+    rc, p, x, err = _load_sppm("volTechnique=beam3d_egsr\nmaxDepth=8\ninitialScaleVolume=0.5\nforceAPA=2D")
+    assert rc == 0, err
+    assert (p.volTechnique, p.maxDepth, p.minDepth, p.forceAPA) == (4, 8, 0, b"2D") and p.initialScaleVolume == 0.5
+    assert (x.rrDepth, x.photonCount, x.volumePhotonCount, x.nbCameraSamples, x.surfaceRendering) == (3, 250000, 250000, 40, 1)
+    for name, tech in (("bre2d", 0), ("bre", 1), ("bre3d", 1), ("beam", 2), ("beam1d", 2), ("beam3d_naive", 3),
+                       ("beam3d_egsr", 4), ("beam3d", 5), ("beam3d_optimized", 5), ("distance", 6), ("plane0d", 7)):
+        rc, p, _, err = _load_sppm(f"volTechnique={name}")
+        assert rc == 0 and p.volTechnique == tech, (name, err)
+    for text, msg in (("", "Unknow vol technique: raymarching"),            # the default is not a known name (:208-209)
+                      ("volTechnique=bre\nmaxDepth=0", "Maximum depth must be set"),
+                      ("volTechnique=bre\nmaxPasses=-3", "Maximum number of Passes"),
+                      ("volTechnique=bre\nmaxRenderingTime=60", "Max pass and time is incompatible!"),
+                      ("volTechnique=bre\nvolumePhotonCount=0", "No volume photons/beams"),
+                      ("volTechnique=bre\nphotonCount=0", "No surface photons"),
+                      ("volTechnique=bre\nminCameraDepth=-2", "minCamera depth")):
+        rc, _, _, err = _load_sppm(text)
+        assert rc == -1 and msg in err, (text, err)
+    rc, _, _, err = _load_sppm("volTechnique=bre\nphotonCount=0\nsurfaceRendering=false")
+    assert rc == 0, err
+
+
 def test_tile_sharding_partitions_every_ray_once():
     from gvpm_b200 import shard
     w, h = 100, 70
