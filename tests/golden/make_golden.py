@@ -30,3 +30,17 @@ res = ob.planes_gather(c.planes, c.rays, c.medium, c.config, neighbours=True, th
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "planes_small.npz"), out=res.out, counts=res.counts,
                     offsets=res.offsets, idx=res.idx, **PP)
 print("plane hits", int(res.counts[:, 0].sum()))
+
+# sppm primal photon beams, four techniques (tests/test_oracle_sppm_beams.py)
+from gvpm_b200 import records as R  # noqa: E402
+
+PB = dict(n_beams=800, w=20, h=12, scale=4.0, seed=77)
+c = H.make_case(n_photons=64, w=PB["w"], h=PB["h"], scale=PB["scale"], rng_seed=99, path_set=False, max_depth=7,
+                min_depth=2)
+c.beams, _ = R.synth_beams(PB["n_beams"], c.medium, seed=PB["seed"], threads=2)
+out = {}
+for tech in sorted(ob.BEAM_TECHNIQUES):
+    r = ob.sppm_beams_gather(c.beams, c.rays, c.medium, c.config, c.radius, tech, threads=2, neighbours=True)
+    out["out_" + tech], out["counts_" + tech], out["offsets_" + tech], out["idx_" + tech] = r.out, r.counts, r.offsets, r.idx
+    print("sppm beams", tech, "accepted", int(r.counts[:, 0].sum()), "contributing", int(r.counts[:, 1].sum()))
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "sppm_beams_small.npz"), **out, **PB)

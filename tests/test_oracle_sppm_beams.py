@@ -122,3 +122,20 @@ def test_empty_inputs(built):
     empty = R.synth_beams(8, c.medium, seed=1, threads=1)[0].take(np.zeros(0, dtype=np.int64))
     r = ob.sppm_beams_gather(empty, c.rays, c.medium, c.config, c.radius, "beam3d", threads=2)
     assert not r.out.any() and not r.counts.any()
+
+
+def test_committed_regression_vectors(built):
+    """tests/golden/sppm_beams_small.npz (tests/golden/make_golden.py; self-generated, guards the restatement against
+    drift): accepted-beam lists and counts bit-exact, radiance to 1e-6."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sppm_beams_small.npz"))
+    c = H.make_case(n_photons=64, w=int(z["w"]), h=int(z["h"]), scale=float(z["scale"]), rng_seed=99, path_set=False,
+                    max_depth=7, min_depth=2)
+    c.beams, _ = R.synth_beams(int(z["n_beams"]), c.medium, seed=int(z["seed"]), threads=2)
+    for tech in sorted(ob.BEAM_TECHNIQUES):
+        r = ob.sppm_beams_gather(c.beams, c.rays, c.medium, c.config, c.radius, tech, threads=3, neighbours=True)
+        np.testing.assert_array_equal(r.counts, z["counts_" + tech])
+        np.testing.assert_array_equal(r.offsets, z["offsets_" + tech])
+        np.testing.assert_array_equal(r.idx, z["idx_" + tech])
+        H.assert_radiance_close(r.out, z["out_" + tech], 1e-6, tech)
+        assert r.counts[:, 1].sum() > 50
