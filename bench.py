@@ -754,9 +754,15 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     sys.stdout.flush()
-    # the context (and its stream) is deliberately left to process exit: torch's caching allocators
-    # may still hold blocks tagged with that stream
-    os._exit(0)
+    # every tensor that lived on the context's stream is gone and torch's caches are empty: destroy the context
+    # (gvpm_ctx_destroy) and leave through the interpreter's normal exit, so that exit hooks see libgvpm_b200.so
+    del stream
+    gc.collect()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:  # noqa: BLE001 - older torch: the pinned cache only queries events, never the stream
+        pass
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -89,10 +89,10 @@ ABI_SYMBOLS = [
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_reconstruct", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
-    "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_dump_neighbours_vpm",
-    "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_dump_neighbours_beams",
+    "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_gather_vpm_device", "gvpm_dump_neighbours_vpm",
+    "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_gather_beams_device", "gvpm_dump_neighbours_beams",
     "gvpm_gather_sppm_beams", "gvpm_dump_neighbours_sppm_beams",
-    "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_dump_neighbours_planes",
+    "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_gather_planes_device", "gvpm_dump_neighbours_planes",
 ]
 
 _lib = None
@@ -153,6 +153,9 @@ def load_lib():
     lib.gvpm_upload_beams.argtypes = [vp, C.POINTER(BeamSoA), C.c_size_t]
     lib.gvpm_build_beams.argtypes = [vp, C.c_float]
     lib.gvpm_gather_beams.argtypes = [vp, f32p, u32p]
+    lib.gvpm_gather_beams_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.gvpm_gather_planes_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.gvpm_gather_vpm_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     lib.gvpm_dump_neighbours_beams.argtypes = [vp, u64p, u32p, C.c_size_t]
     lib.gvpm_gather_sppm_beams.argtypes = [vp, C.c_int, f32p, u32p]
     lib.gvpm_dump_neighbours_sppm_beams.argtypes = [vp, C.c_int, u64p, u32p, C.c_size_t]

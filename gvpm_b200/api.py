@@ -202,9 +202,16 @@ class Context:
     def build_beams(self, radius):
         self._ck(self.lib.gvpm_build_beams(self.h, C.c_float(radius)), "gvpm_build_beams")
 
-    def gather_beams(self, counts=True):
+    def gather_beams_device(self, counts=False):
+        """asynchronous, results stay on the device: -> (out pointer, counts pointer or None)"""
+        o, c = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.gvpm_gather_beams_device(self.h, C.byref(o), C.byref(c) if counts else None),
+                 "gvpm_gather_beams_device")
+        return o.value, (c.value if counts else None)
+
+    def gather_beams(self, counts=True, out=None):
         n = self.n_rays
-        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32) if out is None else out.reshape(-1)
         cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
         self._ck(self.lib.gvpm_gather_beams(self.h, out.ctypes.data_as(N.f32p),
                                             cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_beams")
@@ -260,9 +267,15 @@ class Context:
     def build_planes(self):
         self._ck(self.lib.gvpm_build_planes(self.h), "gvpm_build_planes")
 
-    def gather_planes(self, counts=True):
+    def gather_planes_device(self, counts=False):
+        o, c = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.gvpm_gather_planes_device(self.h, C.byref(o), C.byref(c) if counts else None),
+                 "gvpm_gather_planes_device")
+        return o.value, (c.value if counts else None)
+
+    def gather_planes(self, counts=True, out=None):
         n = self.n_rays
-        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32) if out is None else out.reshape(-1)
         cnt = np.empty(n * 2, dtype=np.uint32) if counts else None
         self._ck(self.lib.gvpm_gather_planes(self.h, out.ctypes.data_as(N.f32p),
                                              cnt.ctypes.data_as(N.u32p) if counts else None), "gvpm_gather_planes")
@@ -288,15 +301,22 @@ class Context:
         self._ck(self.lib.gvpm_upload_vpm_samples(self.h, C.byref(cs), samples.n), "gvpm_upload_vpm_samples")
         self.n_samples = samples.n
 
-    def gather_vpm(self, nb_camera_samples):
-        """-> (out [n_rays,27], mvol [n_rays] uint32, sample_counts [n_samples,2] uint32), on the host."""
+    def gather_vpm_device(self, nb_camera_samples):
+        o, m = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.gvpm_gather_vpm_device(self.h, nb_camera_samples, C.byref(o), C.byref(m)),
+                 "gvpm_gather_vpm_device")
+        return o.value, m.value
+
+    def gather_vpm(self, nb_camera_samples, out=None, mvol=None, sample_counts=True):
+        """-> (out [n_rays,27], mvol [n_rays] uint32, sample_counts [n_samples,2] uint32 or None), on the host."""
         n, ns = self.n_rays, self.n_samples
-        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32)
-        mvol = np.empty(n, dtype=np.uint32)
-        sc = np.empty(ns * 2, dtype=np.uint32)
+        out = np.empty(n * N.GVPM_OUT_FLOATS, dtype=np.float32) if out is None else out.reshape(-1)
+        mvol = np.empty(n, dtype=np.uint32) if mvol is None else mvol
+        sc = np.empty(ns * 2, dtype=np.uint32) if sample_counts else None
         self._ck(self.lib.gvpm_gather_vpm(self.h, nb_camera_samples, out.ctypes.data_as(N.f32p),
-                                          mvol.ctypes.data_as(N.u32p), sc.ctypes.data_as(N.u32p)), "gvpm_gather_vpm")
-        return out.reshape(n, N.GVPM_OUT_FLOATS), mvol, sc.reshape(ns, 2)
+                                          mvol.ctypes.data_as(N.u32p), sc.ctypes.data_as(N.u32p) if sample_counts else None),
+                 "gvpm_gather_vpm")
+        return out.reshape(n, N.GVPM_OUT_FLOATS), mvol, (sc.reshape(ns, 2) if sample_counts else None)
 
     def dump_neighbours_vpm(self, nb_camera_samples):
         ns = self.n_samples

@@ -121,6 +121,9 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
       const float4 b0 = ldg4(rec), b1 = ldg4(rec + 1), b2 = ldg4(rec + 2), b3 = ldg4(rec + 3);
       L.ox = b0.x; L.oy = b0.y; L.oz = b0.z; L.mint = b0.w;
       L.dx = b1.x; L.dy = b1.y; L.dz = b1.z; L.elen = b2.w;
+      // sppm's primal query reads maxt, not edge_len (bre.cpp:206,240): a caller that leaves edge_len unset still gets
+      // the whole segment walked
+      if (SPPM) L.elen = fmaxf(L.elen, b1.w);
       L.xi = b3.x;
       L.px = (int)__float_as_uint(b3.y); L.py = (int)__float_as_uint(b3.z); L.eid = (int)__float_as_uint(b3.w);
     }
@@ -463,7 +466,10 @@ template <bool SPPM> static void launch_shade_mode(const GatherParams &P, unsign
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_bre_shade<SPPM>, GVPM_SHADE_THREADS, 0);
     if (blocks < 1) blocks = 1;
   }
+  // total == ~0: the count is only known on the device (the kernel reads it): size the grid for a full pair list
+  if (total == ~0ull || total > P.pair_cap) total = P.pair_cap;
   unsigned long long need = (total + GVPM_SHADE_THREADS - 1) / GVPM_SHADE_THREADS;
+  if (need == 0) need = 1;
   unsigned long long grid = (unsigned long long)sm_count * blocks * 4;  // a few waves, grid-stride
   if (grid > need) grid = need;
   k_bre_shade<SPPM><<<(unsigned)grid, GVPM_SHADE_THREADS, 0, stream>>>(P);

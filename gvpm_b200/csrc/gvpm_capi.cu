@@ -50,6 +50,13 @@ cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, 
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
                      cudaStream_t st);
+void launch_pack_beams(const BeamStaging &S, uint32_t n, float4 *rec, float *len, cudaStream_t st);
+void launch_beam_subsize_seq(const float *len, uint32_t n, float *subsize, cudaStream_t st);
+void launch_sub_count(const float *len, uint32_t n, const float *subsize, uint32_t *block_tot, uint32_t *total, cudaStream_t st);
+void launch_sub_emit(const float4 *rec, const float *len, uint32_t n, const float *subsize, const uint32_t *block_off,
+                     uint32_t cap, float *sub_pos, float4 *sub_raw, cudaStream_t st);
+void launch_pack_planes(const PlaneStaging &S, uint32_t n, float4 *rec, float *centre, uint32_t *flag, cudaStream_t st);
+void launch_pack_samples(const SampleStaging &S, uint32_t n, uint32_t n_rays, float4 *packed, uint32_t *stats, cudaStream_t st);
 size_t poisson_workspace_floats(size_t n);
 long long poisson_solve_device(const float *tp, const float *dx, const float *dy, const float *direct, int W, int H,
                                float alpha, int irlsIterMax, float irlsRegInit, float irlsRegIter, int cgIterMax,
@@ -64,15 +71,28 @@ namespace {
 struct DevBuf {  // grow-only device allocation
   void *p = nullptr;
   size_t cap = 0;
+  bool pinned = false;  // exported to peers (CUDA IPC): the allocation must not move any more
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
+    if (pinned) return cudaErrorInvalidValue;
+    // the old block stays valid until the new one exists; if memory is too tight for both, give the old one up
+    // first and leave the buffer empty (cap = 0) when the allocation still fails
+    const size_t want = bytes + bytes / 8 + 256;
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      if (p) cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      e = cudaMalloc(&q, want);
+      if (e != cudaSuccess) return e;
+    } else if (p) {
+      cudaFree(p);
+    }
+    p = q;
+    cap = want;
+    return cudaSuccess;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T *as() const { return (T *)p; }
@@ -135,20 +155,28 @@ struct gvpm_ctx {
   unsigned long long pair_cap = 0;         // capacity of `pairs` in entries
   unsigned long long *pair_count_host = nullptr;  // pinned read-back of the pair counter
   unsigned long long last_pairs = 0;
+  // asynchronous BRE gathers in flight (pending_check): pair count slot = pair_count_host[8 + index]
+  struct AsyncGather { cudaEvent_t done = nullptr; uint64_t gen = 0; float *out = nullptr; uint32_t *counts = nullptr; unsigned long long cap = 0; };
+  static constexpr int kRing = 8;
+  AsyncGather ring[kRing];
+  int ring_tail = 0, ring_n = 0;
+  uint64_t state_gen = 0;   // bumped by everything a gather's result depends on (photons, build, rays, medium, config)
   // G-Beams
   DevBuf beams, beam_bounds, sub_pos, sub_raw, subs, beam_box_lo, beam_box_hi;
-  std::vector<float4> beam_host;
+  DevBuf beam_staging, beam_len, beam_aux;  // raw gvpm_beam_soa arrays; beam lengths; [0] subbeamSize, [1] sub-beam total, [16..] block offsets
+  float beam_subsize = 0.f;                 // avgLength / 10 (host copy when the beams came through gvpm_upload_beams)
+  uint32_t n_subs = 0;                      // sub-beams of the uploaded beam set
   uint32_t n_beams = 0;
   bool beams_loaded = false, beams_built = false;
   Tree beam_tree{};
   float beam_radius = 0.f;
   // G-Planes
   DevBuf plane_raw, plane_pos, plane_rec, plane_orig, plane_box_lo, plane_box_hi, plane_bounds;
-  std::vector<float4> plane_host;
-  std::vector<float> plane_centres;
+  DevBuf plane_staging;                     // raw gvpm_plane_soa arrays
   uint32_t n_planes = 0;
   bool planes_loaded = false, planes_built = false;
-  DevBuf samples, sample_counts, mvol;  // G-VPM distance samples
+  DevBuf samples, sample_counts, mvol, sample_staging;  // G-VPM distance samples (+ their raw SoA arrays)
+  uint32_t *sample_stats_host = nullptr;  // pinned: [0] max sample radius (float bits), [1] bad ray index seen; [2] plane flag
   uint32_t n_samples = 0;
   bool samples_loaded = false;
   float sample_radius_max = 0.f;
@@ -283,9 +311,29 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   return GVPM_OK;
 }
 
-// Traverse rays [r0, r1) into the pair list and shade them.  If the pair list overflows, grow it
-// (up to a memory budget) and re-traverse; past the budget, split the ray range.
-int gather_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int depth) {
+// ---- G-BRE gather: traverse + shade without a host round trip in between ---------------------------------------------
+// The shading kernel reads the pair count on the device, so a ray range is two back-to-back launches; the count is
+// copied to a pinned slot behind them and looked at later (gather_finish / pending_poll).  If the pair list turns out to
+// have overflowed, the range is run again the slow way (gather_range_sync: grow the list or split the range, one host
+// sync per attempt).  The list is grow-only, so after the first iteration of a render this does not happen again.
+int enqueue_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, unsigned long long *host_slot) {
+  if (r1 <= r0) { *host_slot = 0; return GVPM_OK; }
+  P.ray_begin = r0;
+  P.ray_end = r1;
+  P.pairs = ctx->pairs.as<uint2>();
+  P.pair_cap = ctx->pair_cap;
+  CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(launch_bre_traverse(P, false, ctx->sm_count, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  CK(launch_bre_shade(P, ~0ull, ctx->sm_count, ctx->stream));
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(host_slot, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return GVPM_OK;
+}
+
+// the slow path: one host sync per attempt.  Rows [r0, r1) of P.out are cleared first.
+int gather_range_sync(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int depth) {
   if (r1 <= r0) return GVPM_OK;
   for (;;) {
     P.ray_begin = r0;
@@ -293,6 +341,7 @@ int gather_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int d
     P.pairs = ctx->pairs.as<uint2>();
     P.pair_cap = ctx->pair_cap;
     CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
+    CK(cudaMemsetAsync(P.out + (size_t)r0 * GVPM_OUT_FLOATS, 0, (size_t)(r1 - r0) * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(launch_bre_traverse(P, false, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -312,36 +361,133 @@ int gather_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int d
     const unsigned long long want = total + total / 8 + 1024;
     const unsigned long long budget = (freeB / 2 + ctx->pairs.cap) / sizeof(uint2);
     if (want <= budget) {
-      CK(ctx->pairs.reserve(want * sizeof(uint2)));
-      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+      cudaError_t e = ctx->pairs.reserve(want * sizeof(uint2));
+      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);   // 0 when the allocation failed: nothing is stored through a stale pointer
+      if (e != cudaSuccess) return fail(ctx, GVPM_ERR_CUDA, std::string("pair list: ") + cudaGetErrorString(e));
       continue;
     }
     if (r1 - r0 <= 1 || depth > 40) return fail(ctx, GVPM_ERR_CUDA, "pair list does not fit in device memory");
     const uint32_t mid = r0 + (r1 - r0) / 2;
-    int rc = gather_range(ctx, P, r0, mid, depth + 1);
+    int rc = gather_range_sync(ctx, P, r0, mid, depth + 1);
     if (rc) return rc;
-    return gather_range(ctx, P, mid, r1, depth + 1);
+    return gather_range_sync(ctx, P, mid, r1, depth + 1);
   }
 }
 
-int gather_common(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
+int reserve_pairs(gvpm_ctx *ctx, size_t entries) {
+  if (ctx->pair_cap >= entries) return GVPM_OK;
+  cudaError_t e = ctx->pairs.reserve(entries * sizeof(uint2));
+  ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+  if (e != cudaSuccess) return fail(ctx, GVPM_ERR_CUDA, std::string("pair list: ") + cudaGetErrorString(e));
+  return GVPM_OK;
+}
+
+// Asynchronous gathers (gvpm_gather_bre_into / _device) in flight: their pair counts are looked at without blocking when
+// the next call comes in, and for good at gvpm_sync, which re-runs the latest gather if its list overflowed and nothing
+// it depends on has changed since.
+int pending_check(gvpm_ctx *ctx, bool block) {
+  while (ctx->ring_n > 0) {
+    gvpm_ctx::AsyncGather &g = ctx->ring[ctx->ring_tail];
+    if (!block) {
+      cudaError_t q = cudaEventQuery(g.done);
+      if (q == cudaErrorNotReady) break;
+      if (q != cudaSuccess) return fail(ctx, GVPM_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+    } else {
+      CK(cudaEventSynchronize(g.done));
+    }
+    const unsigned long long total = ctx->pair_count_host[8 + ctx->ring_tail];
+    ctx->ring_tail = (ctx->ring_tail + 1) % gvpm_ctx::kRing;
+    --ctx->ring_n;
+    ctx->last_pairs = total;
+    if (total <= g.cap) continue;
+    // overflow: make the list large enough for the next one
+    cudaStreamSynchronize(ctx->stream);
+    int rc = reserve_pairs(ctx, total + total / 8 + 1024);
+    if (rc) return rc;
+    const bool latest = ctx->ring_n == 0 && g.gen == ctx->state_gen;
+    if (block && latest) {  // same photons, rays and output buffers: run it again, the slow and safe way
+      GatherParams P;
+      rc = fill_params(ctx, P, g.out, g.counts);
+      if (rc) return rc;
+      ctx->last_pairs = 0;
+      rc = gather_range_sync(ctx, P, 0, ctx->n_rays, 0);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+      return fail(ctx, GVPM_ERR_INVALID,
+                  "an asynchronous gather (gvpm_gather_bre_into / _device) overflowed its pair list and its inputs have "
+                  "been replaced since: its results are incomplete.  Call gvpm_sync after such a gather before the next "
+                  "upload / build / gather (the list has been enlarged)");
+    }
+  }
+  return GVPM_OK;
+}
+
+int gather_common(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev, unsigned long long *host_slot) {
   GatherParams P;
   int rc = fill_params(ctx, P, out_dev, counts_dev);
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   const size_t n = ctx->n_rays;
+  *host_slot = 0;
   if (n) {
     if (ctx->pair_cap == 0) {
-      CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 16 * n) * sizeof(uint2)));
-      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+      rc = reserve_pairs(ctx, std::max<size_t>(1u << 20, 16 * n));
+      if (rc) return rc;
+      P.pairs = ctx->pairs.as<uint2>();
+      P.pair_cap = ctx->pair_cap;
     }
     CK(cudaMemsetAsync(out_dev, 0, n * GVPM_OUT_FLOATS * sizeof(float), ctx->stream));
-    ctx->last_pairs = 0;
-    rc = gather_range(ctx, P, 0, (uint32_t)n, 0);
+    rc = enqueue_range(ctx, P, 0, (uint32_t)n, host_slot);
     if (rc) return rc;
   }
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed_gather = true;
+  return GVPM_OK;
+}
+
+// blocking tail of a gather whose results the caller reads right away: wait, check the pair count, re-run on overflow.
+int gather_finish(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev, const unsigned long long *host_slot, bool *redone) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (redone) *redone = false;
+  const unsigned long long total = *host_slot;
+  ctx->last_pairs = total;
+  if (total <= ctx->pair_cap) return GVPM_OK;
+  int rc = reserve_pairs(ctx, total + total / 8 + 1024);
+  if (rc) return rc;
+  GatherParams P;
+  rc = fill_params(ctx, P, out_dev, counts_dev);
+  if (rc) return rc;
+  ctx->last_pairs = 0;
+  rc = gather_range_sync(ctx, P, 0, ctx->n_rays, 0);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (redone) *redone = true;
+  return GVPM_OK;
+}
+
+// asynchronous variant: the count goes to a ring slot that pending_check looks at later
+int gather_async(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
+  int rc = pending_check(ctx, false);
+  if (rc) return rc;
+  if (ctx->ring_n == gvpm_ctx::kRing) {       // ring full: wait for the oldest
+    gvpm_ctx::AsyncGather &g = ctx->ring[ctx->ring_tail];
+    CK(cudaEventSynchronize(g.done));
+    rc = pending_check(ctx, false);
+    if (rc) return rc;
+  }
+  const int slot = (ctx->ring_tail + ctx->ring_n) % gvpm_ctx::kRing;
+  gvpm_ctx::AsyncGather &g = ctx->ring[slot];
+  rc = gather_common(ctx, out_dev, counts_dev, ctx->pair_count_host + 8 + slot);
+  if (rc) return rc;
+  g.gen = ctx->state_gen;
+  g.out = out_dev;
+  g.counts = counts_dev;
+  g.cap = ctx->pair_cap;
+  CK(cudaEventRecord(g.done, ctx->stream));
+  ++ctx->ring_n;
   return GVPM_OK;
 }
 
@@ -397,7 +543,12 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   }
   for (auto &ev : ctx->push_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   ctx->work_counter.reserve(256);
-  cudaHostAlloc((void **)&ctx->pair_count_host, 64, cudaHostAllocDefault);  // pair / kept-photon counters, the solver's 3-float residual
+  // [0,8): pair / kept-photon counters, the solver's 3-float residual; [8,16): async gather ring; [16,48): ray chunks
+  cudaHostAlloc((void **)&ctx->pair_count_host, 48 * sizeof(unsigned long long), cudaHostAllocDefault);
+  memset(ctx->pair_count_host, 0, 48 * sizeof(unsigned long long));
+  for (auto &g : ctx->ring) cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming);
+  cudaHostAlloc((void **)&ctx->sample_stats_host, 64, cudaHostAllocDefault);
+  memset(ctx->sample_stats_host, 0, 64);
   ctx->bounds.reserve(256);
   ctx->bounds_partial.reserve(1024 * 6 * sizeof(float));
   *out = ctx;
@@ -415,8 +566,11 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->samples, &ctx->sample_counts, &ctx->mvol, &ctx->beams, &ctx->beam_bounds, &ctx->sub_pos,
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
-                    &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws};
+                    &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
+  if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
+  for (auto &g : ctx->ring) if (g.done) cudaEventDestroy(g.done);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
   if (ctx->push_kernel_stream) { cudaStreamSynchronize(ctx->push_kernel_stream); cudaStreamDestroy(ctx->push_kernel_stream); }
   for (auto &ev : ctx->push_ev) if (ev) cudaEventDestroy(ev);
@@ -444,8 +598,9 @@ const char *gvpm_last_error(const gvpm_ctx *ctx) { return ctx ? ctx->err.c_str()
 
 int gvpm_sync(gvpm_ctx *ctx) {
   if (!ctx) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
-  return GVPM_OK;
+  return pending_check(ctx, true);   // an asynchronous gather whose pair list overflowed is re-run here
 }
 
 void *gvpm_stream(gvpm_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -461,6 +616,7 @@ int gvpm_set_medium(gvpm_ctx *ctx, const gvpm_medium *m) {
     return fail(ctx, GVPM_ERR_UNSUPPORTED, "phase function must be isotropic or hg");
   ctx->medium = *m;
   ctx->have_medium = true;
+  ++ctx->state_gen;
   return GVPM_OK;
 }
 
@@ -471,6 +627,7 @@ int gvpm_set_config(gvpm_ctx *ctx, const gvpm_config *c) {
     return fail(ctx, GVPM_ERR_UNSUPPORTED, "useShiftNull requires the 3D kernel");
   ctx->cfg = *c;
   ctx->have_cfg = true;
+  ++ctx->state_gen;
   return GVPM_OK;
 }
 
@@ -478,6 +635,7 @@ int gvpm_set_occluders(gvpm_ctx *ctx, const float *tri_xyz, size_t n_tri) {
   if (!ctx || (n_tri && !tri_xyz)) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   ctx->n_tri = (uint32_t)n_tri;
+  ++ctx->state_gen;
   if (n_tri == 0) return GVPM_OK;
   std::vector<float> planes(4 * n_tri), aux(2 * n_tri);
   for (size_t t = 0; t < n_tri; ++t) {
@@ -520,10 +678,14 @@ int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   if (!ctx || n > 0xfffffff0u) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   PhotonLayout L(n);
+  if (ctx->ph_staging.pinned && (L.bytes ? L.bytes : 256) > ctx->ph_staging.cap)
+    return fail(ctx, GVPM_ERR_INVALID, "the photon staging buffers were exported to peers (gvpm_peer_export) and cannot grow: "
+                                        "size them for the largest iteration before exporting");
   CK(ctx->ph_staging.reserve(L.bytes ? L.bytes : 256));
   ctx->n_photons = (uint32_t)n;
   ctx->photons_loaded = true;
   ctx->built = false;
+  ++ctx->state_gen;
   if (dev) *dev = ctx->ph_staging.p;
   if (bytes) *bytes = L.bytes;
   return GVPM_OK;
@@ -535,6 +697,7 @@ int gvpm_photon_staging_select(gvpm_ctx *ctx, int which) {
     std::swap(ctx->ph_staging, ctx->ph_staging_alt);
     ctx->ph_staging_sel = which;
     ctx->built = false;
+    ++ctx->state_gen;
   }
   return GVPM_OK;
 }
@@ -582,6 +745,7 @@ int gvpm_peer_export(gvpm_ctx *ctx, void *blob) {
   if (!ctx->ph_staging.p || !ctx->ph_staging_alt.p)
     return fail(ctx, GVPM_ERR_INVALID, "size both photon staging buffers (gvpm_photon_staging) before exporting them");
   IpcBlob *B = (IpcBlob *)blob;
+  ctx->ph_staging.pinned = ctx->ph_staging_alt.pinned = true;
   for (int b = 0; b < 2; ++b) {
     CK(cudaIpcGetMemHandle(&B->staging[b], ctx->staging_ptr(b)));
     CK(cudaIpcGetEventHandle(&B->free_ev[b], ctx->ev_free[b]));
@@ -795,6 +959,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
   ctx->tree = T;
   ctx->radius = radius;
   ctx->built = true;
+  ++ctx->state_gen;
   ctx->pruned = false;
   ctx->n_kept = n;
   CK(cudaEventRecord(ctx->ev[1], st));
@@ -881,6 +1046,7 @@ int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   ctx->tree = T;
   ctx->radius = radius;
   ctx->built = true;
+  ++ctx->state_gen;
   ctx->pruned = true;
   ctx->pruned_for_gen = ctx->rays_gen;
   ctx->n_kept = kept;
@@ -898,6 +1064,7 @@ int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   ctx->n_rays = (uint32_t)n;
   ctx->rays_loaded = false;
   ++ctx->rays_gen;
+  ++ctx->state_gen;
   if (dev) *dev = ctx->ray_staging.p;
   if (bytes) *bytes = L.bytes;
   return GVPM_OK;
@@ -941,13 +1108,13 @@ int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n) {
 int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev) {
   if (!ctx || !out_dev) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  return gather_common(ctx, out_dev, counts_dev);
+  return gather_async(ctx, out_dev, counts_dev);
 }
 
 int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev) {
   if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  int rc = gather_async(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
   if (rc) return rc;
   if (out_dev) *out_dev = ctx->out.as<float>();
   if (counts_dev) *counts_dev = ctx->counts.as<uint32_t>();
@@ -957,15 +1124,23 @@ int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t 
 int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
   if (!ctx || !out) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  int rc = pending_check(ctx, true);
+  if (rc) return rc;
+  rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host);
   if (rc) return rc;
   const size_t n = ctx->n_rays;
-  if (n) {
-    CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (counts)
-      CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  for (int pass = 0; pass < 2; ++pass) {   // second pass only if the pair list overflowed and the gather was re-run
+    if (n) {
+      CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      if (counts)
+        CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    bool redone = false;
+    if (pass == 0) rc = gather_finish(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host, &redone);
+    else CK(cudaStreamSynchronize(ctx->stream));
+    if (rc) return rc;
+    if (!redone) break;
   }
-  CK(cudaStreamSynchronize(ctx->stream));
   return GVPM_OK;
 }
 
@@ -976,7 +1151,11 @@ int gvpm_gather_sppm_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
   if (!ctx->have_cfg || !ctx->cfg.sppm_primal)
     return fail(ctx, GVPM_ERR_INVALID, "gvpm_gather_sppm_bre needs gvpm_config.sppm_primal = 1");
   cudaSetDevice(ctx->device);
-  int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+  int rc = pending_check(ctx, true);
+  if (rc) return rc;
+  rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host);
+  if (rc) return rc;
+  rc = gather_finish(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host, nullptr);
   if (rc) return rc;
   const size_t n = ctx->n_rays;
   if (n) {
@@ -1004,8 +1183,12 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
   GatherParams P;
   rc = fill_params(ctx, P, ctx->out.as<float>(), nullptr);
   if (rc) return rc;
+  rc = pending_check(ctx, true);
+  if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->last_pairs = 0;
+  int used = 0;
+  size_t per = 0;
   if (n) {
     const void *src[16] = {r->o, r->d, r->mint, r->maxt, r->edge_len, r->eye_contrib, r->xi, r->px, r->py,
                            r->edge_id, r->off_valid, r->off_o, r->off_d, r->off_len, r->off_eye, r->off_sensor};
@@ -1013,12 +1196,12 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
     for (int i = 0; i < 16; ++i)
       if (!src[i]) return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_ray_soa");
     if (ctx->pair_cap == 0) {
-      CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 16 * n) * sizeof(uint2)));
-      ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+      rc = reserve_pairs(ctx, std::max<size_t>(1u << 20, 16 * n));
+      if (rc) return rc;
     }
     // chunks of whole 32-ray tiles, ~256k rays each
     int nChunks = (int)std::min<size_t>(32, std::max<size_t>(1, n / 262144));
-    size_t per = ((n + nChunks - 1) / nChunks + 31) & ~(size_t)31;
+    per = ((n + nChunks - 1) / nChunks + 31) & ~(size_t)31;
     RayLayout L(n);
     char *stg = (char *)ctx->ray_staging.p;
     const RayStaging S = ray_staging_ptrs(ctx->ray_staging.p, n);
@@ -1026,7 +1209,6 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
     CK(cudaEventRecord(ctx->pipe_ev[64], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_in, ctx->pipe_ev[64], 0));
     CK(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[64], 0));
-    int used = 0;
     for (int c = 0; c < nChunks; ++c) {
       const size_t r0 = (size_t)c * per, r1 = std::min(n, r0 + per);
       if (r0 >= r1) break;
@@ -1043,7 +1225,7 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
       ctx->launches += 1;
       CK(cudaMemsetAsync(ctx->out.as<float>() + r0 * GVPM_OUT_FLOATS, 0, (r1 - r0) * GVPM_OUT_FLOATS * sizeof(float),
                          ctx->stream));
-      rc = gather_range(ctx, P, (uint32_t)r0, (uint32_t)r1, 0);
+      rc = enqueue_range(ctx, P, (uint32_t)r0, (uint32_t)r1, ctx->pair_count_host + 16 + c);
       if (rc) return rc;
       CK(cudaEventRecord(ctx->pipe_ev[2 * c + 1], ctx->stream));
       CK(cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_ev[2 * c + 1], 0));
@@ -1055,6 +1237,19 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
   ctx->timed_gather = true;
   CK(cudaStreamSynchronize(ctx->copy_out));
   CK(cudaStreamSynchronize(ctx->stream));
+  // chunks whose pair list overflowed are run again the slow way (first iteration of a render at most)
+  for (int c = 0; c < used; ++c) {
+    const unsigned long long total = ctx->pair_count_host[16 + c];
+    if (total <= ctx->pair_cap) { ctx->last_pairs += total; continue; }
+    const size_t r0 = (size_t)c * per, r1 = std::min(n, r0 + per);
+    rc = reserve_pairs(ctx, total + total / 8 + 1024);
+    if (rc) return rc;
+    rc = gather_range_sync(ctx, P, (uint32_t)r0, (uint32_t)r1, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out + r0 * GVPM_OUT_FLOATS, ctx->out.as<float>() + r0 * GVPM_OUT_FLOATS,
+                       (r1 - r0) * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return GVPM_OK;
 }
 
@@ -1064,7 +1259,11 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   const size_t n = ctx->n_rays;
   // pass 1: counts
   {
-    int rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>());
+    int rc = pending_check(ctx, true);
+    if (rc) return rc;
+    rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host);
+    if (rc) return rc;
+    rc = gather_finish(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host, nullptr);
     if (rc) return rc;
   }
   std::vector<uint32_t> counts(2 * n + 2);
@@ -1092,43 +1291,49 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
 }
 
 // ---- G-Planes 0D -------------------------------------------------------------------------------
+struct PlaneLayout {
+  size_t off[7], bytes;
+  explicit PlaneLayout(size_t n) {
+    const size_t sz[7] = {12 * n, 12 * n, 4 * n, 12 * n, 4 * n, 12 * n, 4 * n};
+    size_t o = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = o; o += align256(sz[i]); }
+    bytes = o;
+  }
+};
 int gvpm_upload_planes(gvpm_ctx *ctx, const gvpm_plane_soa *p, size_t n) {
   if (!ctx || (n && !p) || n > 0x0ffffff0u) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   ctx->n_planes = (uint32_t)n;
   ctx->planes_loaded = true;
   ctx->planes_built = false;
-  ctx->plane_host.assign(GVPM_PLANE_PLANES * n, make_float4(0.f, 0.f, 0.f, 0.f));
-  ctx->plane_centres.assign(3 * n, 0.f);
+  ++ctx->state_gen;
   if (n == 0) return GVPM_OK;
   if (!p->origin || !p->w0 || !p->length0 || !p->w1 || !p->length1 || !p->flux || !p->edge_id)
     return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_plane_soa");
-  for (size_t i = 0; i < n; ++i) {
-    const float *o = p->origin + 3 * i, *w0 = p->w0 + 3 * i, *w1 = p->w1 + 3 * i;
-    const float l0 = p->length0[i], l1 = p->length1[i];
-    // PhotonPlane ctor asserts (plane_struct.h:45-46)
-    if (!(l0 != 0.f && std::isfinite(l0) && l1 != 0.f && std::isfinite(l1)))
-      return fail(ctx, GVPM_ERR_INVALID, "photon plane with zero or non-finite edge length");
-    // e0 = _w0 * _length0, e1 = _w1 * _length1 exactly as intersectPlane0D forms them (plane_struct.h:107-108)
-    const float e0[3] = {w0[0] * l0, w0[1] * l0, w0[2] * l0}, e1[3] = {w1[0] * l1, w1[1] * l1, w1[2] * l1};
-    uint32_t eid = (uint32_t)p->edge_id[i];
-    float ef;
-    memcpy(&ef, &eid, 4);
-    float4 *r = &ctx->plane_host[GVPM_PLANE_PLANES * i];
-    r[0] = make_float4(o[0], o[1], o[2], l0);
-    r[1] = make_float4(e0[0], e0[1], e0[2], l1);
-    r[2] = make_float4(e1[0], e1[1], e1[2], ef);
-    r[3] = make_float4(p->flux[3 * i], p->flux[3 * i + 1], p->flux[3 * i + 2], 0.f);
-    r[4] = make_float4(w0[0], w0[1], w0[2], 0.f);
-    r[5] = make_float4(w1[0], w1[1], w1[2], 0.f);
-    for (int a = 0; a < 3; ++a) ctx->plane_centres[3 * i + a] = o[a] + 0.5f * e0[a] + 0.5f * e1[a];  // getCenter
-  }
+  PlaneLayout L(n);
+  CK(ctx->plane_staging.reserve(L.bytes));
   CK(ctx->plane_raw.reserve(GVPM_PLANE_PLANES * n * sizeof(float4)));
   CK(ctx->plane_pos.reserve(12 * n));
-  CK(cudaMemcpyAsync(ctx->plane_raw.p, ctx->plane_host.data(), GVPM_PLANE_PLANES * n * sizeof(float4),
-                     cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->plane_pos.p, ctx->plane_centres.data(), 12 * n, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  const void *src[7] = {p->origin, p->w0, p->length0, p->w1, p->length1, p->flux, p->edge_id};
+  const size_t sz[7] = {12 * n, 12 * n, 4 * n, 12 * n, 4 * n, 12 * n, 4 * n};
+  char *stg = (char *)ctx->plane_staging.p;
+  for (int i = 0; i < 7; ++i) CK(cudaMemcpyAsync(stg + L.off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+  PlaneStaging S;
+  S.origin = (const float *)(stg + L.off[0]); S.w0 = (const float *)(stg + L.off[1]); S.length0 = (const float *)(stg + L.off[2]);
+  S.w1 = (const float *)(stg + L.off[3]); S.length1 = (const float *)(stg + L.off[4]); S.flux = (const float *)(stg + L.off[5]);
+  S.edge_id = (const int32_t *)(stg + L.off[6]);
+  uint32_t *flag = ctx->work_counter.as<uint32_t>() + 12;   // word 12 of the counter block
+  CK(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+  launch_pack_planes(S, (uint32_t)n, ctx->plane_raw.as<float4>(), ctx->plane_pos.as<float>(), flag, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->sample_stats_host + 2, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's arrays are only read during the call
+  if (ctx->sample_stats_host[2]) {
+    // PhotonPlane ctor asserts (plane_struct.h:45-46)
+    ctx->planes_loaded = false;
+    return fail(ctx, GVPM_ERR_INVALID, "photon plane with zero or non-finite edge length");
+  }
   return GVPM_OK;
 }
 
@@ -1197,19 +1402,29 @@ static int plane_params(gvpm_ctx *ctx, GatherParams &P) {
   return GVPM_OK;
 }
 
-int gvpm_gather_planes(gvpm_ctx *ctx, float *out, uint32_t *counts) {
-  if (!ctx || !out) return GVPM_ERR_INVALID;
+int gvpm_gather_planes_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev) {
+  if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   GatherParams P;
   int rc = plane_params(ctx, P);
   if (rc) return rc;
-  if (!counts) P.counts = nullptr;
+  if (!counts_dev) P.counts = nullptr;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaMemsetAsync(ctx->work_counter.p, 0, 32, ctx->stream));
   CK(launch_plane_gather(P, false, ctx->sm_count, ctx->stream));
   ctx->launches += ctx->n_rays ? 1 : 0;
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed_gather = true;
+  if (out_dev) *out_dev = ctx->out.as<float>();
+  if (counts_dev) *counts_dev = ctx->counts.as<uint32_t>();
+  return GVPM_OK;
+}
+
+int gvpm_gather_planes(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  const uint32_t *cd = nullptr;
+  int rc = gvpm_gather_planes_device(ctx, nullptr, counts ? &cd : nullptr);
+  if (rc) return rc;
   const size_t n = ctx->n_rays;
   if (n) {
     CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1251,40 +1466,80 @@ int gvpm_dump_neighbours_planes(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx,
 }
 
 // ---- G-Beams 3D --------------------------------------------------------------------------------
+// raw gvpm_beam_soa arrays back to back in one device buffer, each 256-byte aligned
+struct BeamLayout {
+  size_t off[14], bytes;
+  explicit BeamLayout(size_t n) {
+    const size_t sz[14] = {12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 4 * n, 4 * n, n, n, n, 4 * n};
+    size_t o = 0;
+    for (int i = 0; i < 14; ++i) { off[i] = o; o += align256(sz[i]); }
+    bytes = o;
+  }
+};
+static BeamStaging beam_staging_ptrs(const void *base, size_t n) {
+  BeamLayout L(n);
+  const char *b = (const char *)base;
+  BeamStaging S;
+  S.origin = (const float *)(b + L.off[0]); S.end = (const float *)(b + L.off[1]); S.flux = (const float *)(b + L.off[2]);
+  S.prefix_flux = (const float *)(b + L.off[3]); S.parent_n = (const float *)(b + L.off[4]);
+  S.parent_albedo = (const float *)(b + L.off[5]); S.pred_pos = (const float *)(b + L.off[6]);
+  S.end_n = (const float *)(b + L.off[7]); S.parent_pdf = (const float *)(b + L.off[8]);
+  S.rr_weight = (const float *)(b + L.off[9]); S.parent_type = (const uint8_t *)(b + L.off[10]);
+  S.end_on_surface = (const uint8_t *)(b + L.off[11]); S.depth = (const uint8_t *)(b + L.off[12]);
+  S.path_id = (const uint32_t *)(b + L.off[13]);
+  return S;
+}
+
+// The 14 arrays go up as they are and a kernel assembles the 128-byte beam records (pack_prims.cu).  While the DMA
+// runs the host does the one thing that has to be sequential: the fp32 running sum of the beam lengths that fixes the
+// sub-beam size (beams_accel.h:98-104), and with it the number of sub-beams (sizes the sort without a read-back).
 int gvpm_upload_beams(gvpm_ctx *ctx, const gvpm_beam_soa *b, size_t n) {
   if (!ctx || (n && !b) || n > 0x0ffffff0u) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   ctx->n_beams = (uint32_t)n;
   ctx->beams_loaded = true;
   ctx->beams_built = false;
-  ctx->beam_host.assign(8 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+  ctx->n_subs = 0;
+  ctx->beam_subsize = 0.f;
+  ++ctx->state_gen;
   if (n == 0) return GVPM_OK;
   if (!b->origin || !b->end || !b->flux || !b->prefix_flux || !b->parent_n || !b->parent_albedo || !b->pred_pos ||
       !b->end_n || !b->parent_pdf || !b->rr_weight || !b->parent_type || !b->end_on_surface || !b->depth || !b->path_id)
     return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_beam_soa");
+  BeamLayout L(n);
+  CK(ctx->beam_staging.reserve(L.bytes));
+  CK(ctx->beams.reserve(8 * n * sizeof(float4)));
+  CK(ctx->beam_len.reserve(4 * n));
+  CK(ctx->beam_aux.reserve(64 + 4 * ((n + 255) / 256 + 1)));
+  const void *src[14] = {b->origin, b->end, b->flux, b->prefix_flux, b->parent_n, b->parent_albedo, b->pred_pos, b->end_n,
+                         b->parent_pdf, b->rr_weight, b->parent_type, b->end_on_surface, b->depth, b->path_id};
+  const size_t sz[14] = {12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 12 * n, 4 * n, 4 * n, n, n, n, 4 * n};
+  char *stg = (char *)ctx->beam_staging.p;
+  for (int i = 0; i < 14; ++i) CK(cudaMemcpyAsync(stg + L.off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+  launch_pack_beams(beam_staging_ptrs(stg, n), (uint32_t)n, ctx->beams.as<float4>(), ctx->beam_len.as<float>(), ctx->stream);
+  ctx->launches += 1;
+  // host, under the DMA: PhotonBeam::setEndPoint lengths, sequential sum, sub-beam count (SubBeamBVH ctor)
+  std::vector<float> len(n);
+  float avgSize = 0.f;
   for (size_t i = 0; i < n; ++i) {
     const float *o = b->origin + 3 * i, *e = b->end + 3 * i;
-    // PhotonBeam::setEndPoint (beams_struct.h:73-81): dir = p2 - p1; length = |dir|; dir /= length
-    float d[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
-    const float len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    const float rcp = 1.0f / len;
-    d[0] *= rcp; d[1] *= rcp; d[2] *= rcp;
-    uint32_t meta = pack_meta(b->parent_type[i], b->depth[i], b->path_id[i]) | ((b->end_on_surface[i] ? 1u : 0u) << 11);
-    float mf;
-    memcpy(&mf, &meta, 4);
-    float4 *r = &ctx->beam_host[8 * i];
-    r[0] = make_float4(o[0], o[1], o[2], len);
-    r[1] = make_float4(d[0], d[1], d[2], mf);
-    r[2] = make_float4(b->flux[3 * i], b->flux[3 * i + 1], b->flux[3 * i + 2], b->parent_pdf[i]);
-    r[3] = make_float4(b->prefix_flux[3 * i], b->prefix_flux[3 * i + 1], b->prefix_flux[3 * i + 2], b->rr_weight[i]);
-    r[4] = make_float4(b->parent_n[3 * i], b->parent_n[3 * i + 1], b->parent_n[3 * i + 2], e[0]);
-    r[5] = make_float4(b->parent_albedo[3 * i], b->parent_albedo[3 * i + 1], b->parent_albedo[3 * i + 2], e[1]);
-    r[6] = make_float4(b->pred_pos[3 * i], b->pred_pos[3 * i + 1], b->pred_pos[3 * i + 2], e[2]);
-    r[7] = make_float4(b->end_n[3 * i], b->end_n[3 * i + 1], b->end_n[3 * i + 2], 0.f);
+    const float d[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
+    len[i] = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    avgSize += len[i];
   }
-  CK(ctx->beams.reserve(8 * n * sizeof(float4)));
-  CK(cudaMemcpyAsync(ctx->beams.p, ctx->beam_host.data(), 8 * n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  avgSize /= (float)n;
+  const float subbeamSize = avgSize / 10;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    int nSub = subbeamSize > 0.f ? (int)std::ceil(len[i] / subbeamSize) : 1;
+    total += (uint64_t)(nSub < 1 ? 1 : nSub);
+  }
+  if (total > 0xfffffff0ull) return fail(ctx, GVPM_ERR_INVALID, "too many sub-beams");
+  ctx->beam_subsize = subbeamSize;
+  ctx->n_subs = (uint32_t)total;
+  CK(cudaMemcpyAsync(ctx->beam_aux.p, &ctx->beam_subsize, 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's arrays are only read during the call
   return GVPM_OK;
 }
 
@@ -1294,33 +1549,7 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
   if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  const size_t nb = ctx->n_beams;
-  // sub-beam split, SubBeamBVH ctor (beams_accel.h:98-124): size = average length / 10
-  float avgSize = 0.f;
-  for (size_t i = 0; i < nb; ++i) avgSize += ctx->beam_host[8 * i].w;
-  if (nb) avgSize /= (float)nb;
-  const float subbeamSize = avgSize / 10;
-  std::vector<float> subPos;
-  std::vector<float4> subRaw;
-  for (size_t i = 0; i < nb; ++i) {
-    const float4 b0 = ctx->beam_host[8 * i], b1 = ctx->beam_host[8 * i + 1];
-    int nSub = subbeamSize > 0.f ? (int)std::ceil(b0.w / subbeamSize) : 1;
-    if (nSub < 1) nSub = 1;
-    const float lengthSub = b0.w / nSub;
-    for (int k = 0; k < nSub; ++k) {
-      const float t1 = lengthSub * k, t2 = lengthSub * (k + 1), tm = lengthSub * (k + 0.5f);
-      subPos.push_back(b0.x + b1.x * tm);
-      subPos.push_back(b0.y + b1.y * tm);
-      subPos.push_back(b0.z + b1.z * tm);
-      // flags: bit 0 first, bit 1 last sub-beam of its beam, bits 2.. ordinal (the naive sppm technique's RNG dimension)
-      uint32_t bi = (uint32_t)i, fl = (k == 0 ? 1u : 0u) | (k == nSub - 1 ? 2u : 0u) | ((uint32_t)k << 2);
-      float bf, ff;
-      memcpy(&bf, &bi, 4);
-      memcpy(&ff, &fl, 4);
-      subRaw.push_back(make_float4(t1, t2, bf, ff));
-    }
-  }
-  const uint32_t n = (uint32_t)subRaw.size();
+  const uint32_t nb = ctx->n_beams, n = ctx->n_subs;
   CK(cudaEventRecord(ctx->ev[0], st));
   Tree T{};
   T.n = n;
@@ -1348,10 +1577,15 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
     CK(ctx->vals_in.reserve(4 * (size_t)n));
     CK(ctx->vals_out.reserve(4 * (size_t)n));
     CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
+    CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
     CK(ctx->beam_box_lo.reserve(16 * (size_t)total));
     CK(ctx->beam_box_hi.reserve(16 * (size_t)total));
-    CK(cudaMemcpyAsync(ctx->sub_pos.p, subPos.data(), 12 * (size_t)n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->sub_raw.p, subRaw.data(), 16 * (size_t)n, cudaMemcpyHostToDevice, st));
+    // sub-beam cuts on the device (pack_prims.cu): per-beam counts -> offsets -> (midpoint, t1, t2, beam, flags)
+    const float *subsize = ctx->beam_aux.as<float>();
+    uint32_t *aux = ctx->beam_aux.as<uint32_t>();
+    launch_sub_count(ctx->beam_len.as<float>(), nb, subsize, aux + 16, aux + 1, st);
+    launch_sub_emit(ctx->beams.as<float4>(), ctx->beam_len.as<float>(), nb, subsize, aux + 16, n, ctx->sub_pos.as<float>(),
+                    ctx->sub_raw.as<float4>(), st);
     launch_bounds(ctx->sub_pos.as<float>(), n, ctx->bounds_partial.as<float>(), ctx->beam_bounds.as<float>(), st);
     launch_morton(ctx->sub_pos.as<float>(), n, ctx->beam_bounds.as<float>(), ctx->keys_in.as<uint32_t>(),
                   ctx->vals_in.as<uint32_t>(), st);
@@ -1362,9 +1596,8 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
     launch_subbeam_leaf_boxes(ctx->subs.as<float4>(), ctx->beams.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
     for (int l = 1; l < levels; ++l)
       launch_level_boxes(lo + T.off[l - 1], hi + T.off[l - 1], T.cnt[l - 1], T.cnt[l], lo + T.off[l], hi + T.off[l], st);
-    ctx->launches += 5 + (levels - 1) + 4;
+    ctx->launches += 8 + (levels - 1) + 4;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));  // subPos / subRaw are stack-owned host vectors
   } else {
     CK(cudaMemsetAsync(ctx->beam_bounds.p, 0, 7 * sizeof(float), st));
   }
@@ -1373,6 +1606,7 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
   ctx->beam_tree = T;
   ctx->beam_radius = radius;
   ctx->beams_built = true;
+  ++ctx->state_gen;
   CK(cudaEventRecord(ctx->ev[1], st));
   ctx->timed_build = true;
   return GVPM_OK;
@@ -1423,8 +1657,8 @@ static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
 static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
   const size_t nr = ctx->n_rays;
   if (ctx->pair_cap == 0) {
-    CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 64 * nr) * sizeof(uint2)));
-    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    int rc = reserve_pairs(ctx, std::max<size_t>(1u << 20, 64 * nr));
+    if (rc) return rc;
   }
   const bool sppm = P.sppm_beam_technique >= 0;
   P.beam_prefilter = (want_counts || P.dump_pairs || sppm) ? 0 : 1;
@@ -1442,8 +1676,8 @@ static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
     total = *ctx->pair_count_host;
     if (total <= ctx->pair_cap) break;
     if (attempt == 3) return fail(ctx, GVPM_ERR_CUDA, "beam pair list overflow");
-    CK(ctx->pairs.reserve((total + total / 8 + 1024) * sizeof(uint2)));
-    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    int rc = reserve_pairs(ctx, total + total / 8 + 1024);
+    if (rc) return rc;
   }
   ctx->last_pairs = total;
   if (nr) {
@@ -1456,17 +1690,27 @@ static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
   return GVPM_OK;
 }
 
-int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts) {
-  if (!ctx || !out) return GVPM_ERR_INVALID;
+int gvpm_gather_beams_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev) {
+  if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   GatherParams P;
   int rc = beam_params(ctx, P);
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  rc = beams_run(ctx, P, counts != nullptr);
+  rc = beams_run(ctx, P, counts_dev != nullptr);
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed_gather = true;
+  if (out_dev) *out_dev = ctx->out.as<float>();
+  if (counts_dev) *counts_dev = ctx->counts.as<uint32_t>();
+  return GVPM_OK;
+}
+
+int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  const uint32_t *cd = nullptr;
+  int rc = gvpm_gather_beams_device(ctx, nullptr, counts ? &cd : nullptr);
+  if (rc) return rc;
   const size_t n = ctx->n_rays;
   if (n) {
     CK(cudaMemcpyAsync(out, ctx->out.p, n * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1578,30 +1822,51 @@ int gvpm_dump_neighbours_sppm_beams(gvpm_ctx *ctx, int technique, uint64_t *offs
 }
 
 // ---- G-VPM -------------------------------------------------------------------------------------
+struct SampleLayout {
+  size_t off[6], bytes;
+  explicit SampleLayout(size_t n) {
+    const size_t sz[6] = {4 * n, 4 * n, 12 * n, 4 * n, 4 * n, 4 * n};
+    size_t o = 0;
+    for (int i = 0; i < 6; ++i) { off[i] = o; o += align256(sz[i]); }
+    bytes = o;
+  }
+};
+// The six arrays go up as they are and one kernel packs them (2 float4 per sample), finds the largest sample radius and
+// checks the ray indices (pack_prims.cu); both are looked at after the copy of two words at the end of this call.
 int gvpm_upload_vpm_samples(gvpm_ctx *ctx, const gvpm_vpm_sample_soa *s, size_t n) {
   if (!ctx || (n && !s) || n > 0xfffffff0u) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   ctx->n_samples = (uint32_t)n;
   ctx->samples_loaded = true;
+  ctx->sample_radius_max = 0.f;
+  ++ctx->state_gen;
   if (n == 0) return GVPM_OK;
   if (!s->ray || !s->t || !s->transmittance || !s->pdf_success || !s->pdf_sel || !s->radius)
     return fail(ctx, GVPM_ERR_INVALID, "null array in gvpm_vpm_sample_soa");
-  std::vector<float4> packed(2 * n);
-  float rmax = 0.f;
-  for (size_t i = 0; i < n; ++i) {
-    if (s->ray[i] >= ctx->n_rays) return fail(ctx, GVPM_ERR_INVALID, "sample refers to a ray that is not uploaded");
-    packed[2 * i] = make_float4(s->t[i], s->pdf_success[i], s->pdf_sel[i], s->radius[i]);
-    uint32_t rb = s->ray[i];
-    float rf;
-    memcpy(&rf, &rb, 4);
-    packed[2 * i + 1] = make_float4(s->transmittance[3 * i], s->transmittance[3 * i + 1], s->transmittance[3 * i + 2], rf);
-    rmax = std::max(rmax, s->radius[i]);
-  }
-  ctx->sample_radius_max = rmax;
+  SampleLayout L(n);
+  CK(ctx->sample_staging.reserve(L.bytes));
   CK(ctx->samples.reserve(2 * n * sizeof(float4)));
   CK(ctx->sample_counts.reserve(2 * n * sizeof(uint32_t)));
-  CK(cudaMemcpyAsync(ctx->samples.p, packed.data(), 2 * n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  const void *src[6] = {s->ray, s->t, s->transmittance, s->pdf_success, s->pdf_sel, s->radius};
+  const size_t sz[6] = {4 * n, 4 * n, 12 * n, 4 * n, 4 * n, 4 * n};
+  char *stg = (char *)ctx->sample_staging.p;
+  for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(stg + L.off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->stream));
+  SampleStaging S;
+  S.ray = (const uint32_t *)(stg + L.off[0]); S.t = (const float *)(stg + L.off[1]);
+  S.transmittance = (const float *)(stg + L.off[2]); S.pdf_success = (const float *)(stg + L.off[3]);
+  S.pdf_sel = (const float *)(stg + L.off[4]); S.radius = (const float *)(stg + L.off[5]);
+  uint32_t *stats = ctx->work_counter.as<uint32_t>() + 8;   // words 8, 9 of the counter block
+  CK(cudaMemsetAsync(stats, 0, 8, ctx->stream));
+  launch_pack_samples(S, (uint32_t)n, ctx->n_rays, ctx->samples.as<float4>(), stats, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->sample_stats_host, stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's arrays are only read during the call
+  if (ctx->sample_stats_host[1]) {
+    ctx->samples_loaded = false;
+    return fail(ctx, GVPM_ERR_INVALID, "sample refers to a ray that is not uploaded");
+  }
+  memcpy(&ctx->sample_radius_max, &ctx->sample_stats_host[0], 4);
   return GVPM_OK;
 }
 
@@ -1619,8 +1884,8 @@ static int vpm_params(gvpm_ctx *ctx, GatherParams &P, int nb_camera_samples) {
   return GVPM_OK;
 }
 
-int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *mvol, uint32_t *sample_counts) {
-  if (!ctx || !out) return GVPM_ERR_INVALID;
+int gvpm_gather_vpm_device(gvpm_ctx *ctx, int nb_camera_samples, const float **out_dev, const uint32_t **mvol_dev) {
+  if (!ctx) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   GatherParams P;
   int rc = vpm_params(ctx, P, nb_camera_samples);
@@ -1630,8 +1895,8 @@ int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *
   P.mvol = ctx->mvol.as<uint32_t>();
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (ctx->pair_cap == 0) {
-    CK(ctx->pairs.reserve(std::max<size_t>(1u << 20, 8 * ns) * sizeof(uint2)));
-    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
+    rc = reserve_pairs(ctx, std::max<size_t>(1u << 20, 8 * ns));
+    if (rc) return rc;
   }
   unsigned long long total = 0;
   for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1648,15 +1913,25 @@ int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *
     CK(cudaStreamSynchronize(ctx->stream));
     total = *ctx->pair_count_host;
     if (total <= ctx->pair_cap) break;
-    CK(ctx->pairs.reserve((total + total / 8 + 1024) * sizeof(uint2)));
-    ctx->pair_cap = ctx->pairs.cap / sizeof(uint2);
     if (attempt == 2) return fail(ctx, GVPM_ERR_CUDA, "VPM pair list overflow");
+    rc = reserve_pairs(ctx, total + total / 8 + 1024);
+    if (rc) return rc;
   }
   ctx->last_pairs = total;
   CK(launch_vpm_shade(P, total, ctx->sm_count, ctx->stream));
   ctx->launches += total ? 1 : 0;
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed_gather = true;
+  if (out_dev) *out_dev = ctx->out.as<float>();
+  if (mvol_dev) *mvol_dev = ctx->mvol.as<uint32_t>();
+  return GVPM_OK;
+}
+
+int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *mvol, uint32_t *sample_counts) {
+  if (!ctx || !out) return GVPM_ERR_INVALID;
+  int rc = gvpm_gather_vpm_device(ctx, nb_camera_samples, nullptr, nullptr);
+  if (rc) return rc;
+  const size_t nr = ctx->n_rays, ns = ctx->n_samples;
   if (nr) {
     CK(cudaMemcpyAsync(out, ctx->out.p, nr * GVPM_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (mvol) CK(cudaMemcpyAsync(mvol, ctx->mvol.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1812,6 +2087,7 @@ float gvpm_last_poisson_ms(const gvpm_ctx *ctx) { return ctx ? ctx->poisson_ms :
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {
   if (!ctx) return GVPM_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));
+  { int rc = pending_check(ctx, true); if (rc) return rc; }
   if (ctx->timed_build) CK(cudaEventElapsedTime(&ctx->build_ms, ctx->ev[0], ctx->ev[1]));
   if (ctx->timed_gather) CK(cudaEventElapsedTime(&ctx->gather_ms, ctx->ev[2], ctx->ev[3]));
   if (build_ms) *build_ms = ctx->build_ms;
@@ -1822,6 +2098,7 @@ int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms) {
 int gvpm_last_gather_detail(gvpm_ctx *ctx, float *traverse_ms, float *shade_ms, uint64_t *pairs) {
   if (!ctx) return GVPM_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));
+  { int rc = pending_check(ctx, true); if (rc) return rc; }
   float t = 0.f, s = 0.f;
   if (ctx->timed_gather && ctx->n_rays) {
     CK(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));

@@ -102,6 +102,20 @@ struct RayStaging {
   const float *off_o, *off_d, *off_len, *off_eye, *off_sensor;
 };
 
+struct BeamStaging {   // raw gvpm_beam_soa arrays on the device
+  const float *origin, *end, *flux, *prefix_flux, *parent_n, *parent_albedo, *pred_pos, *end_n, *parent_pdf, *rr_weight;
+  const uint8_t *parent_type, *end_on_surface, *depth;
+  const uint32_t *path_id;
+};
+struct PlaneStaging {  // raw gvpm_plane_soa arrays on the device
+  const float *origin, *w0, *length0, *w1, *length1, *flux;
+  const int32_t *edge_id;
+};
+struct SampleStaging { // raw gvpm_vpm_sample_soa arrays on the device
+  const uint32_t *ray;
+  const float *t, *transmittance, *pdf_success, *pdf_sel, *radius;
+};
+
 // implicit 32-ary hierarchy over Morton-sorted photons: level 0 = leaves of 32 photons,
 // level l+1 node j = union of level l nodes [32j, 32j+32).  Boxes already inflated by the radius
 // (+ conservative pad).  lo/hi: float4 arrays holding all levels, level l starts at off[l].

@@ -253,10 +253,12 @@ __device__ __forceinline__ void atomic_max_float(float *a, float v) {
 __device__ __forceinline__ bool ray_segment(const float4 *__restrict__ rays, uint32_t i, float r, float p0[3], float p1[3]) {
   const float4 q0 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4), q1 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 1),
                q2 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 2);
-  const float t0 = -r, t1 = q2.w + r;
+  // sppm's primal query is bounded by maxt (q1.w), gvpm's by edge_len >= maxt: the larger of the two covers both
+  const float tEnd = fmaxf(q2.w, q1.w);
+  const float t0 = -r, t1 = tEnd + r;
   p0[0] = q0.x + q1.x * t0; p0[1] = q0.y + q1.y * t0; p0[2] = q0.z + q1.z * t0;
   p1[0] = q0.x + q1.x * t1; p1[1] = q0.y + q1.y * t1; p1[2] = q0.z + q1.z * t1;
-  return q2.w >= q0.w;   // edge_len >= mint: the gather skips the others
+  return tEnd >= q0.w;   // edge_len >= mint: the gather skips the others
 }
 __global__ void k_ray_box(const float4 *__restrict__ rays, uint32_t n, float r, float *__restrict__ box) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};

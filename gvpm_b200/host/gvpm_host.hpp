@@ -183,7 +183,10 @@ inline void loadGPMConfig(const Properties &props, GPMConfig &c, GPMConfigExtra 
 inline void scaleVolumeAPA(double &globalScaleVolume, int it, const GPMConfig &config) {
   it -= 1;  // "Fix the bug as it == 1 at the first iteration."
   const double ratioVolAPA = (it + config.alpha) / (it + 1);
-  const bool k3 = config.volTechnique == EVolBRE3D, k2 = config.volTechnique == EVolBRE2D;
+  // EVolumeTechniqueHelper::use3DKernel (volume_utils.h:35-41): EDistance, EVolBRE3D and every EBeamBeam3D_*;
+  // beam1d and plane0d reduce linearly, bre2d by the square root
+  const bool k3 = config.volTechnique == EVolVPM || config.volTechnique == EVolBRE3D || config.volTechnique == EVolBeam3D,
+             k2 = config.volTechnique == EVolBRE2D;
   if (config.forceAPA.empty()) {
     if (k3 || config.use3DKernelReduction) globalScaleVolume *= std::cbrt(ratioVolAPA);
     else if (k2) globalScaleVolume *= std::sqrt(ratioVolAPA);

@@ -239,7 +239,8 @@ int gvpm_upload_photons_slice(gvpm_ctx *ctx, const gvpm_photon_soa *p, size_t n_
  * which an SM-based collective cannot while persistent kernels fill the machine).  For contexts in different
  * processes (one per GPU) the staging buffers and four events are shared through CUDA IPC:
  *   gvpm_peer_export   writes this context's GVPM_PEER_BLOB_BYTES-byte blob (both staging buffers must have been
- *                      sized with gvpm_photon_staging and must not grow afterwards);
+ *                      sized with gvpm_photon_staging for the largest iteration: once exported they cannot grow, and a
+ *                      gvpm_photon_staging / gvpm_upload_photons call that needs more fails with GVPM_ERR_INVALID);
  *   gvpm_peer_connect  takes the blobs of all n_peers contexts (rank order, own one included) and maps them;
  *   gvpm_peer_push_photon_slice  copies photons [begin, begin+count) of staging buffer `which` into the same place of
  *                      every peer's buffer `which` with cudaMemcpyAsync on internal streams, after the work queued
@@ -291,6 +292,12 @@ int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts);
 int gvpm_gather_bre_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev);
 /* same, written to caller-provided device memory (e.g. a peer-mapped / NCCL buffer) */
 int gvpm_gather_bre_into(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev);
+/* gvpm_gather_bre_device and gvpm_gather_bre_into are ASYNCHRONOUS: the traversal and shading kernels are queued on the
+ * context's stream with no host round trip in between.  The (ray, photon) pair list between the two kernels is grow-only
+ * and sized from earlier gathers; if it overflows (first iteration of a render, or a sudden growth of the neighbour
+ * count) the gather is incomplete: gvpm_sync() detects that and re-runs it, so results are final once gvpm_sync has
+ * returned GVPM_OK.  Consuming them earlier on the stream is safe whenever an earlier gather of similar size has
+ * completed.  The host-returning gathers (gvpm_gather_bre, _host, gvpm_gather_sppm_bre) do this check themselves. */
 
 /* The whole per-iteration tail in one call: gvpm_upload_rays + gvpm_gather_bre, pipelined - rays go up in chunks on a
  * copy stream while earlier chunks are traversed and shaded and their results stream back, so both PCIe directions
@@ -304,7 +311,8 @@ int gvpm_gather_bre_host(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n, float *
  *      photons: pos, flux = photon.getPower(), parent_pos = pos - photon.getDirection() (so that wi = -direction),
  *      depth = photon.getDepth(); the other arrays are not read.  rays: o = beam.p1, d, mint = Epsilon, maxt =
  *      distTotal - Epsilon, eye_contrib = beam.weight, edge_id = beam.depth (maxDepth - beam.depth is formed from
- *      gvpm_config.max_depth; -1 = unbounded); offsets are ignored.  The 3-D kernel's per-PHOTON sampler->next1D()
+ *      gvpm_config.max_depth; -1 = unbounded); offsets are ignored.  edge_len is not part of sppm's predicate: the
+ *      traversal is bounded by max(edge_len, maxt), so it may be left at 0.  The 3-D kernel's per-PHOTON sampler->next1D()
  *      (bre.cpp:217) is replaced by the counter-based hash of (rng_seed, px, py, edge, photon index).
  *      out: [n_rays*3] = sum of the query results * beam.weight WITHOUT m_scaleFactor (the caller multiplies by
  *      1 / shotParticles, sppm.cpp:922).  counts (may be NULL): [n_rays*2] = {photons passing the geometric tests,
@@ -349,6 +357,9 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
 int gvpm_upload_beams(gvpm_ctx *ctx, const gvpm_beam_soa *b, size_t n);
 int gvpm_build_beams(gvpm_ctx *ctx, float radius);
 int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts);
+/* same, results left on the device (pointers owned by the context, valid until the next gather; the work is queued on the
+ * context's stream, call gvpm_sync before reading them from another stream).  counts_dev NULL: no counts (faster). */
+int gvpm_gather_beams_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev);
 /* per-ray sets of beam indices (bit 31 = contributes), CSR like gvpm_dump_neighbours_bre */
 int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
 
@@ -362,6 +373,7 @@ int gvpm_dump_neighbours_beams(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, 
 int gvpm_upload_planes(gvpm_ctx *ctx, const gvpm_plane_soa *p, size_t n);
 int gvpm_build_planes(gvpm_ctx *ctx);
 int gvpm_gather_planes(gvpm_ctx *ctx, float *out, uint32_t *counts);
+int gvpm_gather_planes_device(gvpm_ctx *ctx, const float **out_dev, const uint32_t **counts_dev); /* as gvpm_gather_beams_device */
 /* per-ray sets of plane indices (bit 31 always set: every intersected plane contributes), CSR */
 int gvpm_dump_neighbours_planes(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, size_t cap);
 
@@ -375,6 +387,7 @@ int gvpm_dump_neighbours_planes(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx,
  * sample_counts (may be NULL): [n_samples*2] = {found, contributing}. */
 int gvpm_upload_vpm_samples(gvpm_ctx *ctx, const gvpm_vpm_sample_soa *s, size_t n);
 int gvpm_gather_vpm(gvpm_ctx *ctx, int nb_camera_samples, float *out, uint32_t *mvol, uint32_t *sample_counts);
+int gvpm_gather_vpm_device(gvpm_ctx *ctx, int nb_camera_samples, const float **out_dev, const uint32_t **mvol_dev);
 /* per-SAMPLE neighbour index sets, same CSR convention as gvpm_dump_neighbours_bre */
 int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *offsets, uint32_t *idx, size_t cap);
 

@@ -84,7 +84,8 @@ def host_params(**kw):
     return p
 
 
-@pytest.mark.parametrize("tech,force,expo", [(1, b"", 1 / 3), (0, b"", 1 / 2), (1, b"1D", 1.0), (0, b"3D", 1 / 3)])
+@pytest.mark.parametrize("tech,force,expo", [(1, b"", 1 / 3), (0, b"", 1 / 2), (1, b"1D", 1.0), (0, b"3D", 1 / 3),
+                                             (3, b"", 1 / 3), (2, b"", 1 / 3), (5, b"", 1.0), (4, b"", 1.0)])
 def test_scale_volume_apa_schedule(tech, force, expo):
     """r_{i+1} = r_i * ((i-1+alpha)/i)^(1/d)  (gvpm.cpp:181-215), d by kernel dimension / forceAPA."""
     h = _host()
