@@ -39,6 +39,13 @@ WORKLOADS = {
     "cfg5": (1920, 1080, 10_000_000, 0.1),
     "cfg1": (256, 256, 100_000, 1.0),
 }
+# The other techniques of BASELINE.json's configs (technique_main): (technique, w, h, primitives, initialScaleVolume)
+TECHNIQUES = {
+    "cfg2": ("vpm", 512, 512, 1_000_000, 1.0),          # G-VPM, 40 distance samples per pixel, unit = pixel
+    "cfg3": ("beams", 1280, 720, 500_000, 0.1),         # G-Beams 3D kernel
+    "cfg4": ("planes", 1280, 720, 200_000, 0.1),        # G-Planes 0D, LASER-style sheet, sensor inside the medium
+    "beams1080": ("beams", 1920, 1080, 1_000_000, 0.1), # north_star's second target: G-Beams-3D at 1920x1080
+}
 
 
 def parse():
@@ -47,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + sorted(TECHNIQUES))
     ap.add_argument("--scale", type=float, default=None, help="initialScaleVolume (paper preset 0.1)")
     ap.add_argument("--photons", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU-baseline sample time")
@@ -133,8 +140,14 @@ def band_cycles():
 
 
 def prune_build(world):
-    """value leg: build the hierarchy only over the photons this rank's rays can reach (N > 1, band sharding)"""
-    return world > 1 and shard_mode(world) == "band" and os.environ.get("GVPM_PRUNE", "1") != "0"
+    """build the acceleration structure for the uploaded rays (gvpm_build_points_for_rays): the perspective grid for
+    the concurrent primary rays of this workload (any N), or the pruned hierarchy under GVPM_ACCEL=bvh (N > 1, band
+    sharding).  GVPM_PRUNE=0: plain gvpm_build_points."""
+    if os.environ.get("GVPM_PRUNE", "1") == "0":
+        return False
+    if os.environ.get("GVPM_ACCEL", "") == "bvh":
+        return world > 1 and shard_mode(world) == "band"
+    return True
 
 
 class ClockSampler:
@@ -206,6 +219,11 @@ def measured_traffic(workload, world):
         return float(e["bytes_per_launch"]), e["source"]
     except Exception:
         return None, None
+
+
+def _native_lib_path():
+    from gvpm_b200 import _native as NAT
+    return NAT.LIB_PATH
 
 
 def peaks():
@@ -372,9 +390,352 @@ def diag_phases(v):
         print("DIAG " + json.dumps(res), file=sys.stderr, flush=True)
 
 
+
+# --------------------------------------------------------------------------------------------
+# cfg2 / cfg3 / cfg4 / beams1080: the other gathers of the path, same JSON contract.  A step = accel build + gather of
+# every camera ray; `value` from device-resident raw arrays, `e2e` through upload_* + build_* + gather_* with pinned
+# host arrays in and out.  N > 1: the 32x32 ray blocks are dealt to the ranks in contiguous runs, the primitive set is
+# replicated (every rank holds / uploads all of it), results are gathered to rank 0.
+def technique_inputs(args, rank, world):
+    import gvpm_b200 as g
+    from gvpm_b200 import records as R
+    tech, w, h, n_prim, scale = TECHNIQUES[args.workload]
+    if args.photons:
+        n_prim = args.photons
+    if args.scale:
+        scale = args.scale
+    seed = 0xC0FFEE + {"cfg2": 2, "cfg3": 3, "cfg4": 4, "beams1080": 6}[args.workload]
+    threads = max(1, min(32, (os.cpu_count() or 8) // max(1, world)))
+    medium = g.make_medium()
+    d = dict(tech=tech, w=w, h=h, n_prim=n_prim, scale=scale, medium=medium, tri=g.synth_occluders(),
+             radius=g.bre_radius(scale), cfg=g.make_config(w, h), nb=40)
+    if tech == "planes":
+        full = g.synth_rays(w, h, seed=seed + 1, block=-32, cam_dist=-0.05, cover=0.45)   # sensor inside the medium
+    else:
+        full = g.synth_rays(w, h, seed=seed + 1, block=-32)
+    per = ((full.n + world - 1) // world + 1023) // 1024 * 1024
+    lo, hi = min(full.n, rank * per), min(full.n, (rank + 1) * per)
+    d["rays"] = full.take(np.arange(lo, hi)) if world > 1 else full
+    d["rays_full_n"] = full.n
+    d["full_rays"] = full if rank == 0 else None
+    if tech == "vpm":
+        d["photons"], d["n_paths"] = g.synth_photons(n_prim, medium, seed=seed, threads=threads)
+        rad = np.full(d["rays"].n, d["radius"], dtype=np.float32)
+        d["samples"] = g.synth_vpm_samples(d["rays"], medium, rad, nb_camera_samples=d["nb"], seed=seed + 2)
+    elif tech == "beams":
+        d["beams"], d["n_paths"] = R.synth_beams(n_prim, medium, seed=seed, threads=threads)
+    else:
+        beams, d["n_paths"] = R.synth_beams(n_prim, medium, seed=seed, threads=threads)
+        planes = R.synth_planes(beams, medium, seed=seed + 7)
+        o = planes.view("origin")   # LASER-style: collimated 0.02-wide emitter
+        o[:, 0] = 0.5 + (o[:, 0] - 0.5) * 0.02
+        planes.length1[:] *= 0.05
+        d["planes"] = planes
+    return d
+
+
+def pin_soa(soa):
+    """copy of a records SoA in page-locked memory (the e2e leg's source)"""
+    import torch
+    keep, arrs = [], {}
+    for name, dt, wd in soa.FIELDS:
+        a = getattr(soa, name)
+        t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+        v = t.numpy().view(dt)
+        v[:] = a.reshape(-1)
+        keep.append(t)
+        arrs[name] = v
+    out = type(soa)(soa.n, **arrs)
+    out._keep = keep
+    return out
+
+
+TECH_TEXT = {"vpm": "gvpm G-VPM point photons, uniform 3D kernel, 40 camera distance samples per pixel",
+             "beams": "gvpm G-Beams 3D kernel (photon beams x camera beams)",
+             "planes": "gvpm G-Planes 0D kernel, LASER-style sheet emitter, sensor inside the medium"}
+PRIM_BYTES = {"vpm": 112, "beams": 128, "planes": 64}   # SURVEY.md 8(d) record sizes
+
+
+def technique_config(args, d, world):
+    prim = {"vpm": "photons", "beams": "beams", "planes": "planes"}[d["tech"]]
+    fits = d["n_prim"] * PRIM_BYTES[d["tech"]] + d["rays_full_n"] * 320
+    return {"workload": f"{args.workload}: {d['w']}x{d['h']} homogeneous-medium Cornell box, {d['n_prim']} {prim}/iteration, "
+                        f"{TECH_TEXT[d['tech']]}, mixed shift, area MIS, pathSet",
+            "rays": d["rays_full_n"], prim: d["n_prim"], "initialScaleVolume": d["scale"], "radius": d["radius"],
+            "parallelism": f"32x32 ray blocks in contiguous runs over {world} GPU(s), {prim} replicated, results gathered to rank 0",
+            "l2": f"records {d['n_prim'] * PRIM_BYTES[d['tech']] / 1e6:.0f} MB + rays {d['rays_full_n'] * 320 / 1e6:.0f} MB per step "
+                  "against a 126 MB L2: " + ("larger than L2, no flush" if fits > 2 * 126e6 else
+                                             "comparable to L2: a 256 MB buffer is written between timed steps (L2 flush)")}
+
+
+def technique_cpu_arm(args, d, seconds):
+    """the oracle restatement of the same gather on all host cores, on a bounded sample of whole 1024-ray tiles"""
+    from oracle import binding as ob
+    cores = ob.hw_threads()
+    rays = d["full_rays"] if d.get("full_rays") is not None else d["rays"]
+    n_tiles = max(1, rays.n // 1024)
+    tech = d["tech"]
+
+    def run(n_t):
+        tiles = np.unique(np.linspace(0, n_tiles - 1, num=max(1, n_t), dtype=np.int64))
+        idx = (tiles[:, None] * 1024 + np.arange(1024)[None, :]).reshape(-1)
+        idx = idx[idx < rays.n]
+        sub = rays.take(idx)
+        t0 = time.perf_counter()
+        if tech == "vpm":
+            import gvpm_b200 as g
+            rad = np.full(sub.n, d["radius"], dtype=np.float32)
+            smp = g.synth_vpm_samples(sub, d["medium"], rad, nb_camera_samples=d["nb"], seed=11)
+            t0 = time.perf_counter()
+            r = ob.vpm_gather(d["photons"], sub, smp, d["medium"], d["cfg"], d["tri"], d["nb"], mode="kdtree", threads=cores)
+            how = "kd-tree range queries (reference structure), kd build included"
+        elif tech == "beams":
+            r = ob.beams_gather(d["beams"], sub, d["medium"], d["cfg"], d["tri"], d["radius"], threads=cores)
+            how = "BRUTE FORCE over all beams (the oracle has no sub-beam BVH: slower than the reference's traversal)"
+        else:
+            r = ob.planes_gather(d["planes"], sub, d["medium"], d["cfg"], mode="brute", threads=cores)
+            how = "brute force over all planes"
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = max(r.gather_ms, 1e-3)
+        return sub.n, ms, wall, len(tiles), how
+
+    n0, ms0, wall0, _, _ = run(1)
+    want = int(min(n_tiles, max(1, seconds * 1e3 / max(wall0, 1e-3))))
+    n1, ms1, wall1, nt, how = run(want)
+    return {"value": n1 / ms1 * 1e3, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n1} rays ({nt} of {n_tiles} 1024-ray tiles spread over the image) against all {d['n_prim']} "
+                      f"primitives; {how}; gather {ms1:.0f} ms (wall {wall1:.0f} ms)"}, ms1, n1
+
+
+def technique_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build_cpu_libs()
+    d = technique_inputs(args, 0, 1)
+    per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    vals, cb = [], None
+    for i in range(args.warmup + args.steps):
+        cb, ms, n = technique_cpu_arm(args, d, per)
+        if i >= args.warmup:
+            vals.append((n, ms))
+    n_tot, ms_tot = sum(v[0] for v in vals), sum(v[1] for v in vals)
+    value = n_tot / ms_tot * 1e3
+    cb["value"] = value
+    print(json.dumps({"impl": "reference", "metric": "camera-ray gathers/sec (primal+4 gradients)", "value": value,
+                      "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms_tot / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": technique_config(args, d, args.gpus), "cpu_baseline": cb,
+                      "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def technique_main(args):
+    if args.impl == "reference":
+        return technique_reference(args)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from gvpm_b200.api import Context
+    from gvpm_b200 import _native as NAT
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gvpm_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build_cpu_libs()
+    if world > 1:
+        dist.barrier()
+    d = technique_inputs(args, rank, world)
+    tech = d["tech"]
+    ctx = Context(local)
+    ctx.set_medium(d["medium"])
+    ctx.set_config(d["cfg"])
+    ctx.set_occluders(d["tri"])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    rays = pin_soa(d["rays"])
+    n_local = rays.n
+    prim = pin_soa(d["photons"] if tech == "vpm" else d["beams"] if tech == "beams" else d["planes"])
+    samples = pin_soa(d["samples"]) if tech == "vpm" else None
+    out_t, out_host = pinned(max(1, n_local) * 27, torch.float32)
+    mvol_t, mvol_host = pinned(max(1, n_local), torch.int32)
+    n_pad = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(n_pad, op=dist.ReduceOp.MAX)
+    n_pad = int(n_pad.item())
+    gathered = [torch.empty(n_pad * 27, device="cuda", dtype=torch.float32) for _ in range(world)] \
+        if (world > 1 and rank == 0) else None
+    send = torch.zeros(n_pad * 27, device="cuda", dtype=torch.float32) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def upload_prims():
+        if tech == "vpm":
+            ctx.upload_photons(prim)
+        elif tech == "beams":
+            ctx.upload_beams(prim)
+        else:
+            ctx.upload_planes(prim)
+
+    def build():
+        if tech == "vpm":
+            ctx.build_points(d["radius"])
+        elif tech == "beams":
+            ctx.build_beams(d["radius"])
+        else:
+            ctx.build_planes()
+
+    def gather_device():
+        if tech == "vpm":
+            return ctx.gather_vpm_device(d["nb"])[0]
+        if tech == "beams":
+            return ctx.gather_beams_device(False)[0]
+        return ctx.gather_planes_device(False)[0]
+
+    def collect(ptr):
+        if world == 1:
+            return
+        with torch.cuda.stream(stream):
+            view = torch.as_tensor(DevView(ptr, n_local * 27 * 4), device="cuda").view(torch.float32)
+            send[:n_local * 27].copy_(view)
+            dist.gather(send, gathered, dst=0)
+
+    def step_resident(k):
+        with torch.cuda.stream(stream):
+            flush.fill_(k & 255)          # L2 flush between timed steps (untimed work would be nicer; it is 256 MB at HBM speed: ~40 us)
+        build()
+        collect(gather_device())
+
+    def step_e2e(k):
+        upload_prims()
+        build()
+        ctx.upload_rays(rays)
+        if tech == "vpm":
+            ctx.upload_vpm_samples(samples)
+            ctx.gather_vpm(d["nb"], out=out_host[:n_local * 27], mvol=mvol_host[:n_local].view(np.uint32), sample_counts=False)
+        elif tech == "beams":
+            ctx.gather_beams(counts=False, out=out_host[:n_local * 27])
+        else:
+            ctx.gather_planes(counts=False, out=out_host[:n_local * 27])
+
+    # untimed set-up: everything resident
+    upload_prims()
+    build()
+    ctx.upload_rays(rays)
+    if tech == "vpm":
+        ctx.upload_vpm_samples(samples)
+    ctx.sync()
+
+    def timed(fn, steps, warmup):
+        for k in range(warmup):
+            fn(k)
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for k in range(warmup, warmup + steps):
+            fn(k)
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ctx.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    W = max(3, args.warmup)
+    ms_total, launches = timed(step_resident, args.steps, W)
+    ms_e2e, _ = timed(step_e2e, args.steps, W)
+    clocks = sampler.stop() if rank == 0 else None
+    # phases + the roofline numerator H (neighbour pairs) from untimed runs
+    kt, kd = [], []
+    for _ in range(3):
+        build()
+        gather_device()
+        kt.append(ctx.last_timings())
+        kd.append(ctx.last_gather_detail())
+    build_ms, gather_ms = float(np.mean([k[0] for k in kt])), float(np.mean([k[1] for k in kt]))
+    trav_ms, shade_ms, n_pairs = float(np.mean([k[0] for k in kd])), float(np.mean([k[1] for k in kd])), int(kd[-1][2])
+    if tech == "vpm":
+        _, mv, sc = ctx.gather_vpm(d["nb"])
+        H = int(sc[:, 0].astype(np.int64).sum())
+    elif tech == "beams":
+        _, cnt = ctx.gather_beams(counts=True)
+        H = int(cnt[:, 0].astype(np.int64).sum())
+    else:
+        _, cnt = ctx.gather_planes(counts=True)
+        H = int(cnt[:, 0].astype(np.int64).sum())
+    stats = torch.tensor([float(H), 0.0], device="cuda", dtype=torch.float64)
+    mx = torch.tensor([build_ms, gather_ms, trav_ms, shade_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        R_ = d["rays_full_n"]
+        H = int(stats[0].item())
+        build_ms, gather_ms, trav_ms, shade_ms = [float(x) for x in mx.tolist()]
+        peak, src = peaks()
+        rec = PRIM_BYTES[tech]
+        per_ray = 428.0 + (d["nb"] * 32.0 if tech == "vpm" else 0.0)
+        alg = (R_ / world) * per_ray + (H / world) * rec
+        achieved = alg / (gather_ms * 1e-3) / 1e9
+        kern = {"vpm": "k_vpm_traverse + k_vpm_shade", "beams": "k_beam_traverse + k_beam_shade", "planes": "k_plane_gather"}[tech]
+        h2d = prim.nbytes() + rays.nbytes() * world + (samples.nbytes() * world if samples is not None else 0)
+        line = {"metric": "camera-ray gathers/sec (primal+4 gradients)", "value": R_ * args.steps / (ms_total * 1e-3),
+                "unit": "rays/s" if tech != "vpm" else "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": technique_config(args, d, world), "clocks": clocks,
+                "e2e": {"value": R_ * args.steps / (ms_e2e * 1e-3), "unit": "rays/s" if tech != "vpm" else "pixels/s",
+                        "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(R_ * 27 * 4),
+                        "note": "upload_* + build_* + upload_rays + gather_* with pinned host arrays, serial (no overlap of the copies with the kernels yet)"},
+                "gpu_launches": int(launches), "native_lib": NAT.LIB_PATH,
+                "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": src,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": gather_ms, "traverse_ms": trav_ms,
+                             "shade_ms": shade_ms, "neighbours_H": H, "pairs_shaded": n_pairs,
+                             "note": f"SURVEY 8(d): R*{per_ray:.0f} + H*{rec} bytes over the gather kernels; H = accepted (ray, primitive) pairs"},
+                "phases_ms": {"build": build_ms, "gather": gather_ms, "traverse": trav_ms, "shade": shade_ms},
+                "light_paths": d["n_paths"]}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = technique_cpu_arm(args, d, args.cpu_seconds)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    del out_t, mvol_t, gathered, send, flush, stream, n_pad, stats, mx
+    prim._keep = rays._keep = None
+    if samples is not None:
+        samples._keep = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:  # noqa: BLE001
+        pass
+    ctx.close()
+
 # --------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.workload in TECHNIQUES:
+        return technique_main(args)
     if args.impl == "reference":
         return reference_main(args)
     import torch
@@ -573,7 +934,7 @@ def main():
 
     def build_resident():
         if prune_build(world):
-            kept[0] = ctx.build_points_for_rays(inp["radius"])
+            ctx.build_points_for_rays(inp["radius"], want_kept=False)
         else:
             ctx.build_points(inp["radius"])
 
@@ -667,6 +1028,10 @@ def main():
         kd.append(ctx.last_gather_detail())
     gather_ms = float(np.mean([k[1] for k in kt]))
     build_ms = float(np.mean([k[0] for k in kt]))
+    accel = ctx.accel_kind()
+    if prune_build(world):
+        with torch.cuda.stream(stream):
+            kept[0] = ctx.build_points_for_rays(inp["radius"], want_kept=True)
     trav_ms, shade_ms, n_pairs = float(np.mean([k[0] for k in kd])), float(np.mean([k[1] for k in kd])), kd[-1][2]
     # geometric neighbour counts H (the roofline's numerator) come from one extra, untimed gather: the reference's
     # gather produces no counts, so the timed steps do not either
@@ -718,7 +1083,7 @@ def main():
                                             + (", in place" if inplace_ok else "")}[exchange],
                                     "double_buffered": True,
                                     "staging_buffers_identical_after_run": staging_ok},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "native_lib": _native_lib_path(),
                 # the gather is two launches: k_bre_traverse (dominant) + k_bre_shade; SURVEY §8(d)'s
                 # per-ray figure covers both, so the roofline is quoted over the pair
                 "roofline": {"bound": "hbm", "kernel": "k_bre_traverse + k_bre_shade", "achieved": achieved,
@@ -731,7 +1096,7 @@ def main():
                 "phases_ms": {"build": build_ms, "gather": float(gk.item()), "traverse": trav_ms,
                               "shade": shade_ms},
                 "shards": {"mode": shard_mode(world), "band_cycles": band_cycles() if shard_mode(world) == "band" else None,
-                           "pruned_build": prune_build(world),
+                           "pruned_build": prune_build(world), "accel": accel,
                            "rays_per_rank": [int(k[1].item()) for k in kept_all],
                            "photons_in_hierarchy_per_rank": [int(k[0].item()) for k in kept_all]},
                 "light_paths": inp["n_paths"]}

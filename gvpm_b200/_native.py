@@ -83,14 +83,14 @@ BEAM_TECHNIQUES = {"beam1d": 0, "beam3d_naive": 1, "beam3d_egsr": 2, "beam3d": 3
 ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
-    "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays",
+    "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays", "gvpm_accel_kind",
     "gvpm_photon_staging_select", "gvpm_photon_staging_layout", "gvpm_upload_photons_slice",
     "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons", "gvpm_peer_push_mode",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_reconstruct", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_gather_vpm_device", "gvpm_dump_neighbours_vpm",
-    "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_gather_beams_device", "gvpm_dump_neighbours_beams",
+    "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_gather_beams_device", "gvpm_dump_neighbours_beams", "gvpm_beam_subbeam_count",
     "gvpm_gather_sppm_beams", "gvpm_dump_neighbours_sppm_beams",
     "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_gather_planes_device", "gvpm_dump_neighbours_planes",
 ]
@@ -125,6 +125,7 @@ def load_lib():
     lib.gvpm_photon_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_build_points.argtypes = [vp, C.c_float]
     lib.gvpm_build_points_for_rays.argtypes = [vp, C.c_float, u32p]
+    lib.gvpm_accel_kind.argtypes = [vp]
     lib.gvpm_photon_staging_select.argtypes = [vp, C.c_int]
     lib.gvpm_photon_staging_layout.argtypes = [C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.gvpm_upload_photons_slice.argtypes = [vp, C.POINTER(PhotonSoA), C.c_size_t, C.c_size_t, C.c_size_t, vp]
@@ -153,6 +154,8 @@ def load_lib():
     lib.gvpm_upload_beams.argtypes = [vp, C.POINTER(BeamSoA), C.c_size_t]
     lib.gvpm_build_beams.argtypes = [vp, C.c_float]
     lib.gvpm_gather_beams.argtypes = [vp, f32p, u32p]
+    lib.gvpm_beam_subbeam_count.argtypes = [vp]
+    lib.gvpm_beam_subbeam_count.restype = C.c_uint64
     lib.gvpm_gather_beams_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.gvpm_gather_planes_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.gvpm_gather_vpm_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]

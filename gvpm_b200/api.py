@@ -110,12 +110,17 @@ class Context:
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 
-    def build_points_for_rays(self, radius):
-        """Hierarchy over the photons the uploaded rays can reach only; -> number of photons kept."""
+    def build_points_for_rays(self, radius, want_kept=True):
+        """Acceleration structure over the photons the uploaded rays can reach only (perspective grid when the rays
+        are concurrent, pruned box hierarchy otherwise); -> number of photons kept (want_kept=False: no read-back)."""
         kept = C.c_uint32(0)
-        self._ck(self.lib.gvpm_build_points_for_rays(self.h, C.c_float(radius), C.byref(kept)),
+        self._ck(self.lib.gvpm_build_points_for_rays(self.h, C.c_float(radius), C.byref(kept) if want_kept else None),
                  "gvpm_build_points_for_rays")
-        return int(kept.value)
+        return int(kept.value) if want_kept else None
+
+    def accel_kind(self):
+        """'bvh' or 'frustum': what the last point build produced"""
+        return {0: "bvh", 1: "frustum"}[int(self.lib.gvpm_accel_kind(self.h))]
 
     # ---- rays
     def upload_rays(self, rays):
@@ -201,6 +206,10 @@ class Context:
 
     def build_beams(self, radius):
         self._ck(self.lib.gvpm_build_beams(self.h, C.c_float(radius)), "gvpm_build_beams")
+
+    def n_subbeams(self):
+        """sub-beams the uploaded beam set is cut into (SubBeamBVH, beams_accel.h:98-124)"""
+        return int(self.lib.gvpm_beam_subbeam_count(self.h))
 
     def gather_beams_device(self, counts=False):
         """asynchronous, results stay on the device: -> (out pointer, counts pointer or None)"""

@@ -85,6 +85,54 @@ struct LaneRay {
   int px, py, eid;
 };
 
+// strict predicate + filters on the queued candidates of every lane (all lanes busy), survivors -> pair list / dump.
+// Warp-collective: every lane of the warp must call it.
+template <int MODE>
+__device__ __forceinline__ void flush_candidates(const GatherParams &P, uint32_t (*queue)[32], int lane, const LaneRay &L,
+                                                 bool have, uint32_t ray, uint32_t &qn, uint32_t &nGeom, uint32_t &nContrib) {
+  constexpr bool DUMP = (MODE & 1) != 0, SPPM = (MODE & 2) != 0;
+  const uint32_t maxq = __reduce_max_sync(0xffffffffu, qn);
+  BaseRay R;
+  R.o = v3(L.ox, L.oy, L.oz); R.d = v3(L.dx, L.dy, L.dz);
+  R.mint = sf(L.mint); R.edgeLen = sf(L.elen); R.xi = sf(L.xi);
+  R.px = L.px; R.py = L.py; R.edgeId = L.eid;
+  R.maxt = sf(0.f);
+  if (SPPM && have) R.maxt = sf(__ldg(&P.rays[(size_t)ray * GVPM_RAY_FLOAT4 + 1].w));
+  uint32_t keep = 0;
+  for (uint32_t k = 0; k < maxq; ++k) {
+    if (k < qn) {
+      const uint32_t slot = queue[k][lane];
+      const float4 q0 = ldg4(P.planes + slot);
+      sf tB, pc;
+      const bool geom = base_distance<SPPM>(P, R, v3(q0.x, q0.y, q0.z), SPPM ? __ldg(P.orig + slot) : 0u, tB, pc);
+      const bool contrib = geom && filters_pass<SPPM>(P, R, __float_as_uint(q0.w));
+      if (DUMP && geom)
+        P.nbr_idx[P.nbr_offsets[ray] + nGeom] = __ldg(P.orig + slot) | (contrib ? 0x80000000u : 0u);
+      nGeom += geom ? 1u : 0u;
+      nContrib += contrib ? 1u : 0u;
+      if (!DUMP && contrib) queue[keep++][lane] = slot;
+    }
+  }
+  qn = 0;
+  if (!DUMP) {
+    uint32_t incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)total);
+      base = __shfl_sync(0xffffffffu, base, 0) + (incl - keep);
+      for (uint32_t k = 0; k < keep; ++k)
+        if (base + k < P.pair_cap) P.pairs[base + k] = make_uint2(ray, __ldg(P.orig + queue[k][lane]));
+    }
+  }
+  __syncwarp();
+}
+
 // MODE bit 0: dump the neighbour sets instead of emitting pairs; bit 1: sppm's primal predicate (bre_device.cuh)
 template <int MODE>
 __global__ void __launch_bounds__(kTravWarps * 32, GVPM_TRAV_MIN_BLOCKS)
@@ -132,49 +180,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
     const int parity = (L.px + L.py) % 2;
     uint32_t nGeom = 0, nContrib = 0, qn = 0;
 
-    // strict predicate + filters on the queued candidates of every lane, survivors -> pair list / dump
-    auto flush = [&]() {
-      const uint32_t maxq = __reduce_max_sync(0xffffffffu, qn);
-      BaseRay R;
-      R.o = v3(L.ox, L.oy, L.oz); R.d = v3(L.dx, L.dy, L.dz);
-      R.mint = sf(L.mint); R.edgeLen = sf(L.elen); R.xi = sf(L.xi);
-      R.px = L.px; R.py = L.py; R.edgeId = L.eid;
-      R.maxt = sf(0.f);
-      if (SPPM && have) R.maxt = sf(__ldg(&P.rays[(size_t)ray * GVPM_RAY_FLOAT4 + 1].w));
-      uint32_t keep = 0;
-      for (uint32_t k = 0; k < maxq; ++k) {
-        if (k < qn) {
-          const uint32_t slot = S.queue[k][lane];
-          const float4 q0 = ldg4(P.planes + slot);
-          sf tB, pc;
-          const bool geom = base_distance<SPPM>(P, R, v3(q0.x, q0.y, q0.z), SPPM ? __ldg(P.orig + slot) : 0u, tB, pc);
-          const bool contrib = geom && filters_pass<SPPM>(P, R, __float_as_uint(q0.w));
-          if (DUMP && geom)
-            P.nbr_idx[P.nbr_offsets[ray] + nGeom] = __ldg(P.orig + slot) | (contrib ? 0x80000000u : 0u);
-          nGeom += geom ? 1u : 0u;
-          nContrib += contrib ? 1u : 0u;
-          if (!DUMP && contrib) S.queue[keep++][lane] = slot;
-        }
-      }
-      qn = 0;
-      if (!DUMP) {
-        uint32_t incl = keep;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)total);
-          base = __shfl_sync(0xffffffffu, base, 0) + (incl - keep);
-          for (uint32_t k = 0; k < keep; ++k)
-            if (base + k < P.pair_cap) P.pairs[base + k] = make_uint2(ray, __ldg(P.orig + S.queue[k][lane]));
-        }
-      }
-      __syncwarp();
-    };
+    auto flush = [&]() { flush_candidates<MODE>(P, S.queue, lane, L, have, ray, qn, nGeom, nContrib); };
 
     // one stackless walk for the lanes of `gm`, sharing the fat ray (co, cd) of half-width `spread`
     auto traverse_group = [&](uint32_t gm, float cox, float coy, float coz, float cdx, float cdy, float cdz,
@@ -388,6 +394,130 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
   }
 }
 
+
+// ---- frustum-grid traversal (gvpm_device.cuh FrustumGrid; built by gvpm_build_points_for_rays when every uploaded ray's
+// line passes through one point) ---------------------------------------------------------------------------------------
+// One ray per lane, one tile of 32 consecutive rays per warp.  No hierarchy walk: the ray's projected direction gives its
+// cell in every footprint class, the 3x3 cells around it hold every photon that can be a neighbour (three contiguous
+// slot ranges per class, one per cell row), and each candidate costs one 128-bit load (neighbouring pixels read the
+// same cells: L1) plus the relaxed pre-test.  Candidate queues, the strict predicate and the pair emission are the ones
+// of k_bre_traverse (flush_candidates), so the neighbour sets are bit-identical.
+#ifndef GVPM_GRID_MIN_BLOCKS
+#define GVPM_GRID_MIN_BLOCKS 8
+#endif
+struct GridShared {
+  uint32_t queue[kTileQ][32];
+};
+template <int MODE>
+__global__ void __launch_bounds__(kTravWarps * 32, GVPM_GRID_MIN_BLOCKS)
+k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
+  constexpr bool DUMP = (MODE & 1) != 0, SPPM = (MODE & 2) != 0;
+  __shared__ GridShared sh[kTravWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  GridShared &S = sh[w];
+  const FrustumGrid &G = P.grid;
+  const uint32_t nTiles = (P.ray_end - P.ray_begin + 31) / 32;
+  const float coordMag = __ldg(P.bounds + 6);
+  const bool prefilter = !DUMP && !SPPM && P.counts == nullptr;
+  const uint32_t nearBeg = __ldg(P.cell_start + G.n_cells), nearEnd = __ldg(P.cell_start + G.n_cells + 1);
+
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(P.work_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= nTiles) break;
+    const uint32_t ray = P.ray_begin + tile * 32 + lane;
+    const bool have = ray < P.ray_end;
+    LaneRay L;
+    {
+      const float4 *rec = P.rays + (size_t)(have ? ray : P.ray_begin) * GVPM_RAY_FLOAT4;
+      const float4 b0 = ldg4(rec), b1 = ldg4(rec + 1), b2 = ldg4(rec + 2), b3 = ldg4(rec + 3);
+      L.ox = b0.x; L.oy = b0.y; L.oz = b0.z; L.mint = b0.w;
+      L.dx = b1.x; L.dy = b1.y; L.dz = b1.z; L.elen = b2.w;
+      if (SPPM) L.elen = fmaxf(L.elen, b1.w);
+      L.xi = b3.x;
+      L.px = (int)__float_as_uint(b3.y); L.py = (int)__float_as_uint(b3.z); L.eid = (int)__float_as_uint(b3.w);
+    }
+    const bool active = have && P.tree.n > 0 && L.elen >= L.mint;
+    const int parity = (L.px + L.py) % 2;
+    uint32_t nGeom = 0, nContrib = 0, qn = 0;
+    auto flush = [&]() { flush_candidates<MODE>(P, S.queue, lane, L, have, ray, qn, nGeom, nContrib); };
+    if (__any_sync(0xffffffffu, active)) {
+      // relaxed pre-test constants of the lane's own ray (conservative by fpad, as in k_bre_traverse)
+      const float omag = fmaxf(fmaxf(fabsf(L.ox), fabsf(L.oy)), fabsf(L.oz));
+      const float fpad = (omag + coordMag + fabsf(L.elen) + P.radius) * 3.8147e-6f;  // 2^-18
+      const float rpad2 = (P.radius + fpad) * (P.radius + fpad);
+      const float tloRay = L.mint - 4.f * fpad;
+      auto test = [&](uint32_t slot) {
+        const float4 ph = ldg4(P.planes + slot);
+        const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
+        const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
+        const float qx = cx - dd * L.dx, qy = cy - dd * L.dy, qz = cz - dd * L.dz;
+        bool cand = (qx * qx + qy * qy + qz * qz) < rpad2 && dd > tloRay;
+        if (prefilter) {
+          const uint32_t meta = __float_as_uint(ph.w);
+          if (P.cfg.path_set && (int)((meta >> 10) & 1u) != parity) cand = false;
+          if (P.cfg.max_depth > 0 && (int)((meta >> 2) & 255u) + L.eid > P.cfg.max_depth) cand = false;
+        }
+        if (cand) S.queue[qn++][lane] = slot;
+      };
+      float x = 0.f, y = 0.f, z = 1.f;
+      if (active) {
+        z = L.dx * G.m[0] + L.dy * G.m[1] + L.dz * G.m[2];
+        const float iz = 1.f / z;
+        x = (L.dx * G.u[0] + L.dy * G.u[1] + L.dz * G.u[2]) * iz;
+        y = (L.dx * G.v[0] + L.dy * G.v[1] + L.dz * G.v[2]) * iz;
+      }
+      float cell = G.cell;
+      for (int c = 0; c < G.classes; ++c, cell *= 2.f) {
+        const uint32_t nx = G.nx[c], ny = G.ny[c], base = G.base[c];
+        // empty class: nothing to do (warp-uniform)
+        if (__ldg(P.cell_start + base) == __ldg(P.cell_start + base + nx * ny)) continue;
+        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, n0 = 0u, n1 = 0u, n2 = 0u;
+        if (active) {
+          const float ic = 1.f / cell;
+          int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
+          cx = min(max(cx, 0), (int)nx - 1);
+          cy = min(max(cy, 0), (int)ny - 1);
+          const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)nx - 1);
+          const int y0 = max(cy - 1, 0), y1 = min(cy + 1, (int)ny - 1);
+          auto row = [&](int yy, uint32_t &sr, uint32_t &nr) {
+            const uint32_t rowBase = base + (uint32_t)yy * nx;
+            sr = __ldg(P.cell_start + rowBase + x0);
+            nr = __ldg(P.cell_start + rowBase + x1 + 1) - sr;
+          };
+          row(y0, s0, n0);
+          if (y0 + 1 <= y1) row(y0 + 1, s1, n1);
+          if (y0 + 2 <= y1) row(y0 + 2, s2, n2);
+        }
+        const uint32_t n01 = n0 + n1, tot = n01 + n2;
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, tot);
+        for (uint32_t j0 = 0; j0 < wmax; j0 += kTileBatch) {
+          if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
+          const uint32_t je = min(j0 + (uint32_t)kTileBatch, tot);
+#pragma unroll 4
+          for (uint32_t j = j0; j < je; ++j) {
+            const uint32_t slot = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
+            test(slot);
+          }
+        }
+      }
+      // photons too close to C for any footprint class: every ray tests them
+      for (uint32_t j0 = nearBeg; j0 < nearEnd; j0 += kTileBatch) {
+        if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
+        const uint32_t je = min(j0 + (uint32_t)kTileBatch, nearEnd);
+        if (active)
+          for (uint32_t j = j0; j < je; ++j) test(j);
+      }
+      if (__any_sync(0xffffffffu, qn > 0)) flush();
+    }
+    if (P.counts && have) {
+      P.counts[2 * (size_t)ray] = nGeom;
+      P.counts[2 * (size_t)ray + 1] = nContrib;
+    }
+  }
+}
+
 template <bool SPPM>
 __global__ void __launch_bounds__(GVPM_SHADE_THREADS, GVPM_SHADE_MIN_BLOCKS)
 k_bre_shade(const __grid_constant__ GatherParams P) {
@@ -446,7 +576,7 @@ k_bre_shade(const __grid_constant__ GatherParams P) {
 }
 
 // ---- host-side launchers (called from gvpm_capi.cu) -------------------------------------------
-static int g_trav_blocks[4] = {0, 0, 0, 0}, g_shade_blocks[2] = {0, 0};
+static int g_trav_blocks[4] = {0, 0, 0, 0}, g_grid_blocks[4] = {0, 0, 0, 0}, g_shade_blocks[2] = {0, 0};
 
 template <int MODE> static void launch_traverse_mode(const GatherParams &P, int &bps, int sm_count, cudaStream_t stream) {
   if (bps == 0) {
@@ -459,6 +589,17 @@ template <int MODE> static void launch_traverse_mode(const GatherParams &P, int 
   const unsigned need = (tiles + kTravWarps - 1) / kTravWarps;
   if (grid > need) grid = need;
   k_bre_traverse<MODE><<<grid, kTravWarps * 32, 0, stream>>>(P);
+}
+template <int MODE> static void launch_grid_mode(const GatherParams &P, int &bps, int sm_count, cudaStream_t stream) {
+  if (bps == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_bre_grid_traverse<MODE>, kTravWarps * 32, 0);
+    if (bps < 1) bps = 1;
+  }
+  unsigned grid = (unsigned)(sm_count * bps);
+  const unsigned tiles = (P.ray_end - P.ray_begin + 31) / 32;
+  const unsigned need = (tiles + kTravWarps - 1) / kTravWarps;
+  if (grid > need) grid = need;
+  k_bre_grid_traverse<MODE><<<grid, kTravWarps * 32, 0, stream>>>(P);
 }
 template <bool SPPM> static void launch_shade_mode(const GatherParams &P, unsigned long long total, int &blocks,
                                                    int sm_count, cudaStream_t stream) {
@@ -478,6 +619,15 @@ template <bool SPPM> static void launch_shade_mode(const GatherParams &P, unsign
 cudaError_t launch_bre_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream) {
   if (P.ray_end <= P.ray_begin) return cudaSuccess;
   const int mode = (dump ? 1 : 0) | (P.cfg.sppm_primal ? 2 : 0);
+  if (P.cell_start != nullptr) {   // frustum grid built for this ray set
+    switch (mode) {
+      case 0: launch_grid_mode<0>(P, g_grid_blocks[0], sm_count, stream); break;
+      case 1: launch_grid_mode<1>(P, g_grid_blocks[1], sm_count, stream); break;
+      case 2: launch_grid_mode<2>(P, g_grid_blocks[2], sm_count, stream); break;
+      default: launch_grid_mode<3>(P, g_grid_blocks[3], sm_count, stream); break;
+    }
+    return cudaGetLastError();
+  }
   switch (mode) {
     case 0: launch_traverse_mode<0>(P, g_trav_blocks[0], sm_count, stream); break;
     case 1: launch_traverse_mode<1>(P, g_trav_blocks[1], sm_count, stream); break;

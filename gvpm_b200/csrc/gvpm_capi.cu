@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,12 @@ int bounds_blocks(uint32_t n);
 void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st);
 void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st);
+int pinhole_blocks(uint32_t n);
+void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st);
+void launch_frustum_keys(const float *pos, uint32_t n, const FrustumGrid &G, uint32_t *keys, uint32_t *vals, cudaStream_t st);
+void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, cudaStream_t st);
+cudaError_t run_sort_bits(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
+                          uint32_t *vout, uint32_t n, int bits, cudaStream_t st);
 size_t ray_grid_bytes();
 size_t ray_mask_bytes();
 void launch_ray_region(const float4 *rays, uint32_t nRays, float radius, float *box, void *grid, uint32_t *mask,
@@ -146,6 +153,15 @@ struct gvpm_ctx {
   uint64_t rays_gen = 0, pruned_for_gen = 0;
   bool pruned = false;
   uint32_t n_kept = 0;
+  // frustum grid (gvpm_device.cuh FrustumGrid): chosen by gvpm_build_points_for_rays when the uploaded rays are concurrent
+  enum { ACCEL_BVH = 0, ACCEL_FRUSTUM = 1 };
+  int accel = ACCEL_BVH;
+  bool force_bvh = false;            // GVPM_ACCEL=bvh: A/B switch for kernel experiments
+  FrustumGrid grid{};
+  DevBuf cell_start, pin_scratch;    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
+  uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
+  struct RayFit { bool concurrent = false; float C[3], m[3], u[3], v[3], delta, cosmin, xmin, xmax, ymin, ymax, count; } pin;
+  float *pin_host = nullptr;         // pinned: 16 fit floats + 8 stats words
 
   DevBuf ray_staging, rays;
   uint32_t n_rays = 0;
@@ -185,6 +201,7 @@ struct gvpm_ctx {
   float poisson_ms = 0.f;
   float build_ms = 0.f, gather_ms = 0.f;
   bool timed_build = false, timed_gather = false;
+  bool split_timed = false;   // the last gather recorded ev[4] / ev[5] around its traversal kernel
 };
 
 namespace {
@@ -272,6 +289,10 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
     return fail(ctx, GVPM_ERR_INVALID, "the hierarchy was built by gvpm_build_points_for_rays for another ray set: rebuild");
   memset(&P, 0, sizeof(P));
   P.tree = ctx->tree;
+  if (ctx->accel == gvpm_ctx::ACCEL_FRUSTUM) {
+    P.grid = ctx->grid;
+    P.cell_start = ctx->cell_start.as<uint32_t>();
+  }
   P.planes = ctx->planes.as<float4>();
   P.aos = ctx->aos.as<float4>();
   P.orig = ctx->orig.as<uint32_t>();
@@ -326,6 +347,7 @@ int enqueue_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, unsi
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   CK(launch_bre_traverse(P, false, ctx->sm_count, ctx->stream));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->split_timed = true;
   CK(launch_bre_shade(P, ~0ull, ctx->sm_count, ctx->stream));
   ctx->launches += 2;
   CK(cudaMemcpyAsync(host_slot, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -345,6 +367,8 @@ int gather_range_sync(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, 
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(launch_bre_traverse(P, false, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->split_timed = true;
+  ctx->split_timed = true;
     ctx->launches += 1;
     CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -547,6 +571,8 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   cudaHostAlloc((void **)&ctx->pair_count_host, 48 * sizeof(unsigned long long), cudaHostAllocDefault);
   memset(ctx->pair_count_host, 0, 48 * sizeof(unsigned long long));
   for (auto &g : ctx->ring) cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming);
+  cudaHostAlloc((void **)&ctx->pin_host, 128, cudaHostAllocDefault);
+  { const char *e = getenv("GVPM_ACCEL"); ctx->force_bvh = e && !strcmp(e, "bvh"); }
   cudaHostAlloc((void **)&ctx->sample_stats_host, 64, cudaHostAllocDefault);
   memset(ctx->sample_stats_host, 0, 64);
   ctx->bounds.reserve(256);
@@ -567,9 +593,10 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
-                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging};
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->pin_scratch};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
+  if (ctx->pin_host) cudaFreeHost(ctx->pin_host);
   for (auto &g : ctx->ring) if (g.done) cudaEventDestroy(g.done);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
   if (ctx->push_kernel_stream) { cudaStreamSynchronize(ctx->push_kernel_stream); cudaStreamDestroy(ctx->push_kernel_stream); }
@@ -959,6 +986,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
   ctx->tree = T;
   ctx->radius = radius;
   ctx->built = true;
+  ctx->accel = gvpm_ctx::ACCEL_BVH;
   ++ctx->state_gen;
   ctx->pruned = false;
   ctx->n_kept = n;
@@ -968,11 +996,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
 }
 
 // Same hierarchy, over the photons the uploaded rays can reach only (tree_build.cu, "ray-region pruning").
-int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
-  if (!ctx) return GVPM_ERR_INVALID;
-  if (!ctx->photons_loaded) return fail(ctx, GVPM_ERR_INVALID, "no photons uploaded");
-  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points_for_rays needs the rays first (gvpm_upload_rays)");
-  if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
+static int build_pruned_bvh(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   cudaSetDevice(ctx->device);
   const uint32_t n = ctx->n_photons;
   cudaStream_t st = ctx->stream;
@@ -1046,6 +1070,7 @@ int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   ctx->tree = T;
   ctx->radius = radius;
   ctx->built = true;
+  ctx->accel = gvpm_ctx::ACCEL_BVH;
   ++ctx->state_gen;
   ctx->pruned = true;
   ctx->pruned_for_gen = ctx->rays_gen;
@@ -1055,6 +1080,142 @@ int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   ctx->timed_build = true;
   return GVPM_OK;
 }
+
+
+// ---- frustum grid (gvpm_device.cuh FrustumGrid) -------------------------------------------------------------------------
+static float decode_max_key(unsigned key) {
+  const unsigned b = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+// Are the uploaded rays concurrent (do their lines meet in one point)?  Two reductions over the packed rays and one
+// read-back, cached until other rays are uploaded.
+static int analyse_rays(gvpm_ctx *ctx) {
+  if (ctx->pin_gen == ctx->rays_gen) return GVPM_OK;
+  gvpm_ctx::RayFit &F = ctx->pin;
+  F.concurrent = false;
+  ctx->pin_gen = ctx->rays_gen;
+  const uint32_t n = ctx->n_rays;
+  if (n == 0) return GVPM_OK;
+  CK(ctx->pin_scratch.reserve(128 + (size_t)pinhole_blocks(n) * 16 * sizeof(double)));
+  char *ps = ctx->pin_scratch.as<char>();
+  launch_pinhole_fit(ctx->rays.as<float4>(), n, (double *)(ps + 128), (float *)ps, (unsigned *)(ps + 64), ctx->stream);
+  ctx->launches += 3;
+  CK(cudaMemcpyAsync(ctx->pin_host, ps, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const float *fit = ctx->pin_host;
+  const unsigned *st = (const unsigned *)(ctx->pin_host + 16);
+  F.count = fit[12];
+  if (!(F.count >= 1.f) || !(fit[13] > 0.f)) return GVPM_OK;   // no active ray, or parallel rays (no common point)
+  for (int k = 0; k < 3; ++k) { F.C[k] = fit[k]; F.m[k] = fit[3 + k]; F.u[k] = fit[6 + k]; F.v[k] = fit[9 + k]; }
+  F.delta = decode_max_key(st[0]);
+  F.cosmin = -decode_max_key(st[1]);
+  F.xmin = -decode_max_key(st[2]); F.xmax = decode_max_key(st[3]);
+  F.ymin = -decode_max_key(st[4]); F.ymax = decode_max_key(st[5]);
+  F.concurrent = std::isfinite(F.delta) && F.cosmin > 0.35f && std::isfinite(F.xmin) && std::isfinite(F.xmax) &&
+                 std::isfinite(F.ymin) && std::isfinite(F.ymax) && F.xmin <= F.xmax && F.ymin <= F.ymax;
+  return GVPM_OK;
+}
+
+static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->n_photons;
+  cudaStream_t st = ctx->stream;
+  const gvpm_ctx::RayFit &F = ctx->pin;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  FrustumGrid G{};
+  for (int k = 0; k < 3; ++k) { G.C[k] = F.C[k]; G.m[k] = F.m[k]; G.u[k] = F.u[k]; G.v[k] = F.v[k]; }
+  G.xmin = F.xmin; G.xmax = F.xmax; G.ymin = F.ymin; G.ymax = F.ymax;
+  G.pad_r = radius + F.delta;
+  // about one ray per class-0 cell, square cells, at most 4 M of them
+  const double ex = std::max((double)F.xmax - F.xmin, 1e-9), ey = std::max((double)F.ymax - F.ymin, 1e-9);
+  const double target = std::min(std::max((double)F.count, 64.0), 4.0e6);
+  double cell = std::sqrt(ex * ey / target);
+  cell = std::max(cell, std::max(ex, ey) / 4096.0);
+  G.cell = (float)cell;
+  G.gx0 = F.xmin;
+  G.gy0 = F.ymin;
+  uint32_t nx0 = (uint32_t)std::floor(ex / G.cell) + 2u, ny0 = (uint32_t)std::floor(ey / G.cell) + 2u, total = 0;
+  int classes = 0;
+  for (int c = 0; c < GVPM_GRID_CLASSES; ++c) {
+    G.nx[c] = (nx0 + (1u << c) - 1u) >> c;
+    G.ny[c] = (ny0 + (1u << c) - 1u) >> c;
+    G.base[c] = total;
+    total += G.nx[c] * G.ny[c];
+    classes = c + 1;
+    if (G.nx[c] == 1 && G.ny[c] == 1) break;
+  }
+  for (int c = classes; c < GVPM_GRID_CLASSES; ++c) { G.nx[c] = G.ny[c] = 1; G.base[c] = total; }
+  G.classes = classes;
+  G.n_cells = total;
+  const uint32_t n_keys = total + 2;   // + NEAR + DROP
+  int bits = 1;
+  while ((1ull << bits) < (unsigned long long)n_keys) ++bits;
+  CK(ctx->cell_start.reserve(((size_t)n_keys + 1) * 4));
+  if (n > 0) {
+    CK(ctx->keys_in.reserve(8 * (size_t)n));
+    CK(ctx->keys_out.reserve(8 * (size_t)n));
+    CK(ctx->vals_in.reserve(4 * (size_t)n));
+    CK(ctx->vals_out.reserve(4 * (size_t)n));
+    CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
+    CK(ctx->planes.reserve(16 * (size_t)n));
+    CK(ctx->orig.reserve(4 * (size_t)n));
+    CK(ctx->aos.reserve(128 * (size_t)n));
+    CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
+    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    launch_bounds(S.pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st);
+    launch_frustum_keys(S.pos, n, G, ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), st);
+    CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
+                     ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, bits, st));
+    launch_cell_starts(ctx->keys_out.as<uint32_t>(), n, n_keys, ctx->cell_start.as<uint32_t>(), st);
+    launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
+                       ctx->orig.as<uint32_t>(), st);
+    CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
+    ctx->launches += 8 + 4;
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemsetAsync(ctx->bounds.p, 0, 7 * sizeof(float), st));
+    CK(cudaMemsetAsync(ctx->cell_start.p, 0, ((size_t)n_keys + 1) * 4, st));
+  }
+  Tree T{};
+  T.n = n;
+  ctx->tree = T;
+  ctx->grid = G;
+  ctx->radius = radius;
+  ctx->built = true;
+  ctx->accel = gvpm_ctx::ACCEL_FRUSTUM;
+  ++ctx->state_gen;
+  ctx->pruned = true;
+  ctx->pruned_for_gen = ctx->rays_gen;
+  ctx->n_kept = n;
+  CK(cudaEventRecord(ctx->ev[1], st));
+  ctx->timed_build = true;
+  if (n_kept) {   // photons some ray can reach = everything in front of the DROP bucket (one read-back, only on request)
+    CK(cudaMemcpyAsync(ctx->pair_count_host, ctx->cell_start.as<uint32_t>() + G.n_cells + 1, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->n_kept = *(const uint32_t *)ctx->pair_count_host;
+    *n_kept = ctx->n_kept;
+  }
+  return GVPM_OK;
+}
+
+int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (!ctx->photons_loaded) return fail(ctx, GVPM_ERR_INVALID, "no photons uploaded");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_points_for_rays needs the rays first (gvpm_upload_rays)");
+  if (!(radius > 0.f)) return fail(ctx, GVPM_ERR_INVALID, "radius must be positive");
+  cudaSetDevice(ctx->device);
+  if (!ctx->force_bvh) {
+    int rc = analyse_rays(ctx);
+    if (rc) return rc;
+    // concurrent rays whose common point is sharp compared with the search radius: perspective grid, no hierarchy
+    if (ctx->pin.concurrent && ctx->pin.delta <= 0.25f * radius) return build_frustum(ctx, radius, n_kept);
+  }
+  return build_pruned_bvh(ctx, radius, n_kept);
+}
+
+int gvpm_accel_kind(const gvpm_ctx *ctx) { return ctx ? ctx->accel : 0; }
 
 int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   if (!ctx || n > 0xfffffff0u) return GVPM_ERR_INVALID;
@@ -1411,6 +1572,7 @@ int gvpm_gather_planes_device(gvpm_ctx *ctx, const float **out_dev, const uint32
   if (!counts_dev) P.counts = nullptr;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaMemsetAsync(ctx->work_counter.p, 0, 32, ctx->stream));
+  ctx->split_timed = false;
   CK(launch_plane_gather(P, false, ctx->sm_count, ctx->stream));
   ctx->launches += ctx->n_rays ? 1 : 0;
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -1612,6 +1774,8 @@ int gvpm_build_beams(gvpm_ctx *ctx, float radius) {
   return GVPM_OK;
 }
 
+uint64_t gvpm_beam_subbeam_count(const gvpm_ctx *ctx) { return ctx ? ctx->n_subs : 0; }
+
 static int beam_params(gvpm_ctx *ctx, GatherParams &P) {
   if (!ctx->have_medium || !ctx->have_cfg) return fail(ctx, GVPM_ERR_INVALID, "medium/config not set");
   if (!ctx->beams_built) return fail(ctx, GVPM_ERR_INVALID, "gvpm_build_beams has not been called");
@@ -1670,6 +1834,8 @@ static int beams_run(gvpm_ctx *ctx, GatherParams &P, bool want_counts) {
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(launch_beam_traverse(P, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->split_timed = true;
+  ctx->split_timed = true;
     ctx->launches += nr ? 1 : 0;
     CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1871,6 +2037,11 @@ int gvpm_upload_vpm_samples(gvpm_ctx *ctx, const gvpm_vpm_sample_soa *s, size_t 
 }
 
 static int vpm_params(gvpm_ctx *ctx, GatherParams &P, int nb_camera_samples) {
+  if (ctx->built && ctx->accel == gvpm_ctx::ACCEL_FRUSTUM) {
+    // the range queries walk the box hierarchy: build it (over the photons the rays can reach) in place of the grid
+    int rcb = build_pruned_bvh(ctx, ctx->radius, nullptr);
+    if (rcb) return rcb;
+  }
   int rc = fill_params(ctx, P, ctx->out.as<float>(), nullptr);
   if (rc) return rc;
   if (!ctx->samples_loaded) return fail(ctx, GVPM_ERR_INVALID, "no VPM samples uploaded");
@@ -1908,6 +2079,8 @@ int gvpm_gather_vpm_device(gvpm_ctx *ctx, int nb_camera_samples, const float **o
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(launch_vpm_traverse(P, false, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->split_timed = true;
+  ctx->split_timed = true;
     ctx->launches += ns ? 1 : 0;
     CK(cudaMemcpyAsync(ctx->pair_count_host, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2100,7 +2273,7 @@ int gvpm_last_gather_detail(gvpm_ctx *ctx, float *traverse_ms, float *shade_ms, 
   CK(cudaStreamSynchronize(ctx->stream));
   { int rc = pending_check(ctx, true); if (rc) return rc; }
   float t = 0.f, s = 0.f;
-  if (ctx->timed_gather && ctx->n_rays) {
+  if (ctx->timed_gather && ctx->n_rays && ctx->split_timed) {
     CK(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
     CK(cudaEventElapsedTime(&s, ctx->ev[5], ctx->ev[3]));
   }

@@ -128,8 +128,32 @@ struct Tree {
   uint32_t n;       // photons
 };
 
+// Perspective ("frustum") grid over the photons, for ray sets whose supporting lines all pass through one point C
+// (primary camera rays of a pinhole sensor: every medium segment of a pixel's first edge).  Directions from C are
+// projected on the plane at distance 1 along the mean ray direction m (gnomonic projection, basis u, v); a photon at
+// distance rho from C can only be a neighbour of rays whose projected direction lies within
+//   w = tan(theta + alpha) - tan(theta),  alpha = asin((r + delta) / rho),  tan(theta) = |proj(photon)|
+// of its own projection (delta = largest distance of C to a ray's line).  Photons are binned by FOOTPRINT CLASS c
+// (w <= cell * 2^c) into a grid coarsened by 2^c, so that a ray finds every neighbour in the 3x3 cells around its own
+// cell of every class; photons whose footprint exceeds the coarsest class go to the NEAR bucket (tested by every ray),
+// photons that no ray can reach are DROPPED.  Keys: [base[c] + cy * nx[c] + cx] < n_cells, n_cells = NEAR,
+// n_cells + 1 = DROP; cell_start[k] = first sorted slot with key >= k.
+#define GVPM_GRID_CLASSES 8
+struct FrustumGrid {
+  float C[3], m[3], u[3], v[3];
+  float gx0, gy0, cell;                  // plane coordinates of the grid origin, class-0 cell edge
+  float xmin, xmax, ymin, ymax;          // bounds of the rays' projected directions
+  float pad_r;                           // r + delta
+  uint32_t nx[GVPM_GRID_CLASSES], ny[GVPM_GRID_CLASSES], base[GVPM_GRID_CLASSES];
+  uint32_t n_cells;
+  int classes;
+};
+
 struct GatherParams {
   Tree tree;
+  // frustum-grid variant of the point gather (tree_build.cu / gather_bre.cu k_bre_grid_traverse)
+  FrustumGrid grid;
+  const uint32_t *cell_start;   // [n_cells + 3]
   const float4 *planes;  // [n] sorted P0 = pos.xyz, meta (the only per-photon data the traversal reads)
   const float4 *aos;     // [n][8] full records in the caller's order (shading reads aos[orig[slot]])
   const uint32_t *orig;  // [n] original photon index of sorted slot

@@ -458,6 +458,187 @@ __global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, ui
   }
 }
 
+
+// ---- perspective (frustum) grid: build side (gvpm_device.cuh FrustumGrid) ---------------------------------------------
+// Pass 1 over the active rays: normal equations of "the point closest to all lines" (A = sum(I - d d^T),
+// b = sum((I - d d^T) o)) and the direction sum, in double, one partial per block, folded in block order by
+// k_pinhole_solve (deterministic).  partial: [nb][16] doubles = A(6: xx xy xz yy yz zz), b(3), dsum(3), count.
+__device__ __forceinline__ bool ray_active(const float4 q0, const float4 q1, const float4 q2) {
+  return fmaxf(q2.w, q1.w) >= q0.w;
+}
+__global__ void __launch_bounds__(256) k_pinhole_accum(const float4 *__restrict__ rays, uint32_t n, double *__restrict__ partial) {
+  double acc[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) acc[k] = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q0 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4), q1 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 1),
+                 q2 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 2);
+    if (!ray_active(q0, q1, q2)) continue;
+    const double dx = q1.x, dy = q1.y, dz = q1.z, ox = q0.x, oy = q0.y, oz = q0.z;
+    const double od = ox * dx + oy * dy + oz * dz;
+    acc[0] += 1.0 - dx * dx; acc[1] += -dx * dy; acc[2] += -dx * dz;
+    acc[3] += 1.0 - dy * dy; acc[4] += -dy * dz; acc[5] += 1.0 - dz * dz;
+    acc[6] += ox - od * dx; acc[7] += oy - od * dy; acc[8] += oz - od * dz;
+    acc[9] += dx; acc[10] += dy; acc[11] += dz;
+    acc[12] += 1.0;
+  }
+  __shared__ double sh[8][13];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 13; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 13) {
+    double v = 0.0;
+    for (int k = 0; k < 8; ++k) v += sh[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
+  }
+}
+// fit[0..2] = C, [3..5] = m, [6..8] = u, [9..11] = v, [12] = count, [13] = conditioning (det / trace^3; 0 = no point)
+__global__ void k_pinhole_solve(const double *__restrict__ partial, int nb, float *__restrict__ fit) {
+  double a[13];
+  for (int k = 0; k < 13; ++k) {
+    double v = 0.0;
+    for (int b = 0; b < nb; ++b) v += partial[(size_t)b * 16 + k];
+    a[k] = v;
+  }
+  const double xx = a[0], xy = a[1], xz = a[2], yy = a[3], yz = a[4], zz = a[5];
+  const double det = xx * (yy * zz - yz * yz) - xy * (xy * zz - yz * xz) + xz * (xy * yz - yy * xz);
+  const double tr = xx + yy + zz;
+  double cond = tr > 0.0 ? det / (tr * tr * tr) : 0.0;
+  double C[3] = {0, 0, 0};
+  if (cond > 1e-12) {
+    const double bx = a[6], by = a[7], bz = a[8];
+    C[0] = (bx * (yy * zz - yz * yz) - xy * (by * zz - yz * bz) + xz * (by * yz - yy * bz)) / det;
+    C[1] = (xx * (by * zz - yz * bz) - bx * (xy * zz - yz * xz) + xz * (xy * bz - by * xz)) / det;
+    C[2] = (xx * (yy * bz - by * yz) - xy * (xy * bz - by * xz) + bx * (xy * yz - yy * xz)) / det;
+  } else {
+    cond = 0.0;
+  }
+  double ml = sqrt(a[9] * a[9] + a[10] * a[10] + a[11] * a[11]);
+  double m[3] = {0, 0, 1};
+  if (ml > 0.0) { m[0] = a[9] / ml; m[1] = a[10] / ml; m[2] = a[11] / ml; } else cond = 0.0;
+  // any orthonormal basis of the plane orthogonal to m
+  double t[3] = {0, 0, 0};
+  if (fabs(m[0]) <= fabs(m[1]) && fabs(m[0]) <= fabs(m[2])) t[0] = 1; else if (fabs(m[1]) <= fabs(m[2])) t[1] = 1; else t[2] = 1;
+  double u[3] = {t[1] * m[2] - t[2] * m[1], t[2] * m[0] - t[0] * m[2], t[0] * m[1] - t[1] * m[0]};
+  const double ul = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  for (int k = 0; k < 3; ++k) u[k] /= ul;
+  const double v[3] = {m[1] * u[2] - m[2] * u[1], m[2] * u[0] - m[0] * u[2], m[0] * u[1] - m[1] * u[0]};
+  for (int k = 0; k < 3; ++k) { fit[k] = (float)C[k]; fit[3 + k] = (float)m[k]; fit[6 + k] = (float)u[k]; fit[9 + k] = (float)v[k]; }
+  fit[12] = (float)a[12];
+  fit[13] = (float)cond;
+}
+// the projection both sides use (photons with q = p - C, rays with q = d): plane coordinates at distance 1 along m
+__device__ __forceinline__ void frustum_project(const float *m, const float *u, const float *v, float qx, float qy, float qz,
+                                                float &x, float &y, float &z) {
+  z = qx * m[0] + qy * m[1] + qz * m[2];
+  const float iz = 1.f / z;
+  x = (qx * u[0] + qy * u[1] + qz * u[2]) * iz;
+  y = (qx * v[0] + qy * v[1] + qz * v[2]) * iz;
+}
+// Pass 2 over the active rays: largest distance of C to a ray's line, smallest cos(d, m), bounds of the projected
+// directions.  stats: [0] delta max, [1] -cos min (as max), [2] -xmin, [3] xmax, [4] -ymin, [5] ymax  (all folded with
+// atomicMax on non-negative-biased float bits: values are stored + 4 to keep them positive)
+__global__ void __launch_bounds__(256) k_pinhole_check(const float4 *__restrict__ rays, uint32_t n, const float *__restrict__ fit,
+                                                        unsigned *__restrict__ stats) {
+  float mx[6] = {0.f, -2.f, -1e30f, -1e30f, -1e30f, -1e30f};
+  const float C[3] = {fit[0], fit[1], fit[2]}, m[3] = {fit[3], fit[4], fit[5]}, u[3] = {fit[6], fit[7], fit[8]}, v[3] = {fit[9], fit[10], fit[11]};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q0 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4), q1 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 1),
+                 q2 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 2);
+    if (!ray_active(q0, q1, q2)) continue;
+    const float cx = C[0] - q0.x, cy = C[1] - q0.y, cz = C[2] - q0.z;
+    const float t = cx * q1.x + cy * q1.y + cz * q1.z;
+    const float ex = cx - t * q1.x, ey = cy - t * q1.y, ez = cz - t * q1.z;
+    mx[0] = fmaxf(mx[0], sqrtf(ex * ex + ey * ey + ez * ez));
+    float x, y, z;
+    frustum_project(m, u, v, q1.x, q1.y, q1.z, x, y, z);
+    mx[1] = fmaxf(mx[1], -z);
+    if (z > 0.f) { mx[2] = fmaxf(mx[2], -x); mx[3] = fmaxf(mx[3], x); mx[4] = fmaxf(mx[4], -y); mx[5] = fmaxf(mx[5], y); }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float vv = mx[k];
+    for (int o = 16; o > 0; o >>= 1) vv = fmaxf(vv, __shfl_xor_sync(0xffffffffu, vv, o));
+    // monotone map float -> unsigned (handles negatives)
+    const unsigned b = __float_as_uint(vv);
+    const unsigned key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    if ((threadIdx.x & 31) == 0) atomicMax(stats + k, key);
+  }
+}
+
+// per photon: footprint class, cell, key (see FrustumGrid).  vals = photon index.
+__global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ pos, uint32_t n, const FrustumGrid G,
+                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float qx = pos[3 * (size_t)i] - G.C[0], qy = pos[3 * (size_t)i + 1] - G.C[1], qz = pos[3 * (size_t)i + 2] - G.C[2];
+  const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
+  const uint32_t NEAR = G.n_cells, DROP = G.n_cells + 1u;
+  uint32_t key;
+  float x, y, z;
+  frustum_project(G.m, G.u, G.v, qx, qy, qz, x, y, z);
+  const float pr = G.pad_r * 1.001f + 1e-6f * rho;
+  if (rho <= 2.f * pr) {
+    key = NEAR;                                   // alpha >= 30 degrees
+  } else if (z < 0.1f * rho) {
+    key = rho <= 6.f * pr ? NEAR : DROP;          // more than 84 degrees off axis: only reachable when very close
+  } else {
+    const float tanT = sqrtf(x * x + y * y);
+    const float ang = atanf(tanT) + asinf(pr / rho) * 1.0005f + 1e-6f;
+    if (ang >= 1.45f) {
+      key = NEAR;
+    } else {
+      const float wfoot = (tanf(ang) - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
+      if (x < G.xmin - wfoot || x > G.xmax + wfoot || y < G.ymin - wfoot || y > G.ymax + wfoot) {
+        key = DROP;
+      } else {
+        int c = 0;
+        float cell = G.cell;
+        while (c < G.classes && wfoot > cell) { ++c; cell *= 2.f; }
+        if (c >= G.classes) {
+          key = NEAR;
+        } else {
+          const float ic = 1.f / cell;
+          int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
+          cx = min(max(cx, 0), (int)G.nx[c] - 1);
+          cy = min(max(cy, 0), (int)G.ny[c] - 1);
+          key = G.base[c] + (uint32_t)cy * G.nx[c] + (uint32_t)cx;
+        }
+      }
+    }
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+// cell_start[k] = first sorted slot whose key is >= k, for k in [0, n_keys].  Thread i fills the gap in front of slot i
+// when it is short (the usual case: about as many photons as cells); cells of long gaps keep the 0xffffffff the array
+// was initialised with and are found by a binary search in the second pass (sparse photon sets).
+__global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t n_keys,
+                                                      uint32_t *__restrict__ cell_start) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t lo = i == 0 ? 0u : sorted_keys[i - 1] + 1u;
+  const uint32_t hi = i == n ? n_keys : min(sorted_keys[i], n_keys);   // inclusive
+  if (lo > hi || hi - lo >= 32u) return;
+  for (uint32_t k = lo; k <= hi; ++k) cell_start[k] = i;
+}
+__global__ void __launch_bounds__(256) k_cell_starts_fill(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t n_keys,
+                                                           uint32_t *__restrict__ cell_start) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_keys || cell_start[k] != 0xffffffffu) return;
+  uint32_t a = 0, b = n;   // lower_bound(k)
+  while (a < b) {
+    const uint32_t mid = a + ((b - a) >> 1);
+    if (__ldg(sorted_keys + mid) < k) a = mid + 1; else b = mid;
+  }
+  cell_start[k] = a;
+}
+
 // raw ray SoA -> 5 x 64 B records per ray
 __global__ void k_pack_rays(const RayStaging S, uint32_t r0, uint32_t n, float4 *__restrict__ rays) {
   const uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,6 +718,29 @@ void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keep
   if (!m) return;
   k_pack_aos_kept<<<(n + 255) / 256, 256, 0, st>>>(S, n, keepmask, aos);
   k_gather_sorted<<<(m + 255) / 256, 256, 0, st>>>(aos, sorted, m, planes, orig);
+}
+
+// ---- frustum grid launchers ----
+int pinhole_blocks(uint32_t n) { int b = (int)((n + 255) / 256); return b < 1 ? 1 : (b > 512 ? 512 : b); }
+// partial: [pinhole_blocks * 16] doubles; fit: 16 floats; stats: 8 words (zeroed here)
+void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st) {
+  const int nb = pinhole_blocks(n);
+  k_pinhole_accum<<<nb, 256, 0, st>>>(rays, n, partial);
+  k_pinhole_solve<<<1, 1, 0, st>>>(partial, nb, fit);
+  cudaMemsetAsync(stats, 0, 32, st);
+  k_pinhole_check<<<nb, 256, 0, st>>>(rays, n, fit, stats);
+}
+void launch_frustum_keys(const float *pos, uint32_t n, const FrustumGrid &G, uint32_t *keys, uint32_t *vals, cudaStream_t st) {
+  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, n, G, keys, vals);
+}
+void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, cudaStream_t st) {
+  cudaMemsetAsync(cell_start, 0xff, ((size_t)n_keys + 1) * 4, st);
+  k_cell_starts<<<(n + 1 + 255) / 256, 256, 0, st>>>(sorted_keys, n, n_keys, cell_start);
+  k_cell_starts_fill<<<(n_keys + 1 + 255) / 256, 256, 0, st>>>(sorted_keys, n, n_keys, cell_start);
+}
+cudaError_t run_sort_bits(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
+                          uint32_t *vout, uint32_t n, int bits, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, bits, st);
 }
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st) {

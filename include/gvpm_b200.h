@@ -274,6 +274,13 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius);
  * it returns after gvpm_build_points.  The hierarchy is valid for this ray set only - the gathers fail with
  * GVPM_ERR_INVALID once other rays are uploaded, until the next build.  n_kept (may be NULL): photons kept. */
 int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept);
+/* When the lines of ALL uploaded rays pass through one point (the primary rays of a pinhole sensor: the first medium
+ * edge of every pixel), gvpm_build_points_for_rays builds a PERSPECTIVE GRID instead of a box hierarchy: photons are
+ * binned by the direction in which that point sees them, in cells about one pixel wide (coarser cells for photons
+ * close to the point, whose search sphere covers many pixels), and a ray finds all its neighbours in the 3x3 cells
+ * around its own direction - no traversal.  Same neighbour sets, same results.  n_kept (photons some ray can reach)
+ * then costs one device read-back: pass NULL when it is not needed.  gvpm_accel_kind: 0 = box hierarchy, 1 = grid. */
+int gvpm_accel_kind(const gvpm_ctx *ctx);
 
 /* ---- camera rays --------------------------------------------------------------------- */
 int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n);
@@ -356,6 +363,8 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
  * with a valid kernel record, pairs that also pass the depth/mode/pathSet filters}. */
 int gvpm_upload_beams(gvpm_ctx *ctx, const gvpm_beam_soa *b, size_t n);
 int gvpm_build_beams(gvpm_ctx *ctx, float radius);
+/* number of sub-beams the uploaded beam set is cut into (SubBeamBVH's m_beamCount, beams_accel.h:107-110) */
+uint64_t gvpm_beam_subbeam_count(const gvpm_ctx *ctx);
 int gvpm_gather_beams(gvpm_ctx *ctx, float *out, uint32_t *counts);
 /* same, results left on the device (pointers owned by the context, valid until the next gather; the work is queued on the
  * context's stream, call gvpm_sync before reading them from another stream).  counts_dev NULL: no counts (faster). */
