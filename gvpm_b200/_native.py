@@ -70,6 +70,22 @@ class VpmSampleSoA(C.Structure):
                 ("pdf_sel", f32p), ("radius", f32p)]
 
 
+class BoxRect(C.Structure):
+    _fields_ = [("y", C.c_float), ("x0", C.c_float), ("x1", C.c_float), ("z0", C.c_float), ("z1", C.c_float),
+                ("albedo", C.c_float * 3)]
+
+
+class BoxScene(C.Structure):
+    _fields_ = [("lo", C.c_float * 3), ("hi", C.c_float * 3), ("face_albedo", (C.c_float * 3) * 5),
+                ("n_rects", C.c_int32), ("rect", BoxRect * 4), ("light_y", C.c_float), ("light_x0", C.c_float),
+                ("light_x1", C.c_float), ("light_z0", C.c_float), ("light_z1", C.c_float), ("light_power", C.c_float)]
+
+
+class PinholeCamera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("tan_half_fov_x", C.c_float), ("film_w", C.c_int32), ("film_h", C.c_int32),
+                ("inside_medium", C.c_int32)]
+
+
 class PoissonParams(C.Structure):
     _fields_ = [("alpha", C.c_float), ("irls_iter_max", C.c_int32), ("irls_reg_init", C.c_float),
                 ("irls_reg_iter", C.c_float), ("cg_iter_max", C.c_int32), ("cg_iter_check", C.c_int32),
@@ -92,6 +108,7 @@ ABI_SYMBOLS = [
     "gvpm_upload_vpm_samples", "gvpm_gather_vpm", "gvpm_gather_vpm_device", "gvpm_dump_neighbours_vpm",
     "gvpm_upload_beams", "gvpm_build_beams", "gvpm_gather_beams", "gvpm_gather_beams_device", "gvpm_dump_neighbours_beams", "gvpm_beam_subbeam_count",
     "gvpm_gather_sppm_beams", "gvpm_dump_neighbours_sppm_beams",
+    "gvpm_box_scene_default", "gvpm_generate_rays", "gvpm_trace_photons", "gvpm_read_device", "gvpm_staging_peek",
     "gvpm_upload_planes", "gvpm_build_planes", "gvpm_gather_planes", "gvpm_gather_planes_device", "gvpm_dump_neighbours_planes",
 ]
 
@@ -126,6 +143,12 @@ def load_lib():
     lib.gvpm_build_points.argtypes = [vp, C.c_float]
     lib.gvpm_build_points_for_rays.argtypes = [vp, C.c_float, u32p]
     lib.gvpm_accel_kind.argtypes = [vp]
+    lib.gvpm_box_scene_default.argtypes = [C.POINTER(BoxScene)]
+    lib.gvpm_generate_rays.argtypes = [vp, C.POINTER(BoxScene), C.POINTER(PinholeCamera), C.c_uint64, C.c_int, C.c_int,
+                                       C.c_int, C.c_float]
+    lib.gvpm_trace_photons.argtypes = [vp, C.POINTER(BoxScene), C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.c_int, u64p]
+    lib.gvpm_read_device.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.gvpm_staging_peek.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_photon_staging_select.argtypes = [vp, C.c_int]
     lib.gvpm_photon_staging_layout.argtypes = [C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.gvpm_upload_photons_slice.argtypes = [vp, C.POINTER(PhotonSoA), C.c_size_t, C.c_size_t, C.c_size_t, vp]

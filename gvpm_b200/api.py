@@ -122,6 +122,61 @@ class Context:
         """'bvh' or 'frustum': what the last point build produced"""
         return {0: "bvh", 1: "frustum"}[int(self.lib.gvpm_accel_kind(self.h))]
 
+    # ---- on-device generators (rows f-1, f-2)
+    def generate_rays(self, scene, camera, seed, block=32, y0=0, y1=None, epsilon=1e-4):
+        """camera-ray medium segments + offsets of a pinhole sensor, generated and committed on the device"""
+        y1 = camera.film_h if y1 is None else y1
+        self._ck(self.lib.gvpm_generate_rays(self.h, C.byref(scene), C.byref(camera), C.c_uint64(seed), block, y0, y1,
+                                             C.c_float(epsilon)), "gvpm_generate_rays")
+        self.n_rays = camera.film_w * (y1 - y0)
+        return self.n_rays
+
+    def trace_photons(self, scene, n, seed, max_depth=12, rr_depth=1, min_depth=0):
+        """the iteration's volume photons traced on the device into the selected staging buffer; -> light paths traced"""
+        paths = C.c_uint64(0)
+        self._ck(self.lib.gvpm_trace_photons(self.h, C.byref(scene), n, C.c_uint64(seed), max_depth, rr_depth, min_depth,
+                                             C.byref(paths)), "gvpm_trace_photons")
+        self.n_photons = n
+        return int(paths.value)
+
+    def photon_staging_peek(self, n=None):
+        dev, cnt = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.gvpm_staging_peek(self.h, 0, C.byref(dev), C.byref(cnt)), "gvpm_staging_peek")
+        return dev.value, cnt.value
+
+    def ray_staging_peek(self):
+        dev, cnt = C.c_void_p(), C.c_size_t()
+        self._ck(self.lib.gvpm_staging_peek(self.h, 1, C.byref(dev), C.byref(cnt)), "gvpm_staging_peek")
+        return dev.value, cnt.value
+
+    def download_photons(self, n):
+        """parity aid: the staged photon set as a PhotonSet"""
+        from . import records as R
+        ptr, _ = self.photon_staging_peek(n)
+        off, elt = self.photon_staging_layout(n)
+        ps = R.PhotonSet(n)
+        for (name, dt, wd), o, e in zip(R._PHOTON_FIELDS, off, elt):
+            a = getattr(ps, name)
+            self._ck(self.lib.gvpm_read_device(self.h, C.c_void_p(ptr + o), a.ctypes.data_as(C.c_void_p), a.nbytes),
+                     "gvpm_read_device")
+        return ps
+
+    def download_rays(self):
+        """parity aid: the staged (un-packed) ray arrays as a RaySet"""
+        from . import records as R
+        n = self.n_rays
+        ptr, _ = self.ray_staging_peek()
+        rs = R.RaySet(n)
+        sizes = [a * n for a in (12, 12, 4, 4, 4, 12, 4, 4, 4, 4, 4, 48, 48, 16, 48, 16)]
+        o = 0
+        for (name, dt, wd), sz in zip(R._RAY_FIELDS, sizes):
+            a = getattr(rs, name)
+            assert a.nbytes == sz, (name, a.nbytes, sz)
+            self._ck(self.lib.gvpm_read_device(self.h, C.c_void_p(ptr + o), a.ctypes.data_as(C.c_void_p), sz),
+                     "gvpm_read_device")
+            o += (sz + 255) & ~255
+        return rs
+
     # ---- rays
     def upload_rays(self, rays):
         cs = rays.as_c()

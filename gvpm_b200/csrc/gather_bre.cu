@@ -403,7 +403,7 @@ k_bre_traverse(const __grid_constant__ GatherParams P) {
 // same cells: L1) plus the relaxed pre-test.  Candidate queues, the strict predicate and the pair emission are the ones
 // of k_bre_traverse (flush_candidates), so the neighbour sets are bit-identical.
 #ifndef GVPM_GRID_MIN_BLOCKS
-#define GVPM_GRID_MIN_BLOCKS 8
+#define GVPM_GRID_MIN_BLOCKS 6
 #endif
 struct GridShared {
   uint32_t queue[kTileQ][32];
@@ -419,7 +419,11 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
   const uint32_t nTiles = (P.ray_end - P.ray_begin + 31) / 32;
   const float coordMag = __ldg(P.bounds + 6);
   const bool prefilter = !DUMP && !SPPM && P.counts == nullptr;
-  const uint32_t nearBeg = __ldg(P.cell_start + G.n_cells), nearEnd = __ldg(P.cell_start + G.n_cells + 1);
+  const uint32_t nGridsBuilt = G.parity_split ? 2u : 1u;
+  const uint32_t nearBeg = __ldg(P.cell_start + nGridsBuilt * G.n_cells), nearEnd = __ldg(P.cell_start + nGridsBuilt * G.n_cells + 1);
+  // with the pathSet prefilter a ray only ever pairs with photons of its pixel's parity: it scans that grid alone
+  const bool onlyMine = G.parity_split && prefilter && P.cfg.path_set;
+  const uint32_t nPass = onlyMine ? 1u : nGridsBuilt;
 
   for (;;) {
     uint32_t tile = 0;
@@ -448,8 +452,7 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
       const float fpad = (omag + coordMag + fabsf(L.elen) + P.radius) * 3.8147e-6f;  // 2^-18
       const float rpad2 = (P.radius + fpad) * (P.radius + fpad);
       const float tloRay = L.mint - 4.f * fpad;
-      auto test = [&](uint32_t slot) {
-        const float4 ph = ldg4(P.planes + slot);
+      auto test = [&](const float4 ph, uint32_t slot) {
         const float cx = ph.x - L.ox, cy = ph.y - L.oy, cz = ph.z - L.oz;
         const float dd = cx * L.dx + cy * L.dy + cz * L.dz;
         const float qx = cx - dd * L.dx, qy = cy - dd * L.dy, qz = cz - dd * L.dz;
@@ -468,37 +471,53 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
         x = (L.dx * G.u[0] + L.dy * G.u[1] + L.dz * G.u[2]) * iz;
         y = (L.dx * G.v[0] + L.dy * G.v[1] + L.dz * G.v[2]) * iz;
       }
-      float cell = G.cell;
-      for (int c = 0; c < G.classes; ++c, cell *= 2.f) {
+      for (int c = 0; c < G.classes; ++c) {
         const uint32_t nx = G.nx[c], ny = G.ny[c], base = G.base[c];
-        // empty class: nothing to do (warp-uniform)
-        if (__ldg(P.cell_start + base) == __ldg(P.cell_start + base + nx * ny)) continue;
-        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, n0 = 0u, n1 = 0u, n2 = 0u;
+        // empty class (in every grid): nothing to do (warp-uniform)
+        bool empty = true;
+        for (uint32_t g = 0; g < nGridsBuilt; ++g)
+          empty = empty && __ldg(P.cell_start + g * G.n_cells + base) == __ldg(P.cell_start + g * G.n_cells + base + nx * ny);
+        if (empty) continue;
+        int x0 = 0, x1 = 0, y0 = 0, y1 = -1;
         if (active) {
-          const float ic = 1.f / cell;
+          const float ic = 1.f / G.csize[c];
           int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
           cx = min(max(cx, 0), (int)nx - 1);
           cy = min(max(cy, 0), (int)ny - 1);
-          const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)nx - 1);
-          const int y0 = max(cy - 1, 0), y1 = min(cy + 1, (int)ny - 1);
+          x0 = max(cx - 1, 0); x1 = min(cx + 1, (int)nx - 1);
+          y0 = max(cy - 1, 0); y1 = min(cy + 1, (int)ny - 1);
+        }
+        for (uint32_t pass = 0; pass < nPass; ++pass) {
+          const uint32_t gbase = (onlyMine ? (uint32_t)parity : pass) * G.n_cells + base;
+          uint32_t s0 = 0u, s1 = 0u, s2 = 0u, n0 = 0u, n1 = 0u, n2 = 0u;
           auto row = [&](int yy, uint32_t &sr, uint32_t &nr) {
-            const uint32_t rowBase = base + (uint32_t)yy * nx;
+            const uint32_t rowBase = gbase + (uint32_t)yy * nx;
             sr = __ldg(P.cell_start + rowBase + x0);
             nr = __ldg(P.cell_start + rowBase + x1 + 1) - sr;
           };
-          row(y0, s0, n0);
+          if (y0 <= y1) row(y0, s0, n0);
           if (y0 + 1 <= y1) row(y0 + 1, s1, n1);
           if (y0 + 2 <= y1) row(y0 + 2, s2, n2);
-        }
-        const uint32_t n01 = n0 + n1, tot = n01 + n2;
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, tot);
-        for (uint32_t j0 = 0; j0 < wmax; j0 += kTileBatch) {
-          if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
-          const uint32_t je = min(j0 + (uint32_t)kTileBatch, tot);
-#pragma unroll 4
-          for (uint32_t j = j0; j < je; ++j) {
-            const uint32_t slot = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
-            test(slot);
+          const uint32_t n01 = n0 + n1, tot = n01 + n2;
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, tot);
+          // four candidates per step: their loads are issued together (each lane reads its own cells; neighbouring
+          // pixels share them, so most of these hit L1)
+          for (uint32_t j0 = 0; j0 < wmax; j0 += kTileBatch) {
+            if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
+#pragma unroll
+            for (uint32_t u0 = 0; u0 < (uint32_t)kTileBatch; u0 += 4) {
+              float4 ph[4];
+              uint32_t sl[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u0 + u;
+                sl[u] = j < n0 ? s0 + j : (j < n01 ? s1 + (j - n0) : s2 + (j - n01));
+                if (j < tot) ph[u] = ldg4(P.planes + sl[u]);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j0 + u0 + u < tot) test(ph[u], sl[u]);
+            }
           }
         }
       }
@@ -507,7 +526,7 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
         if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
         const uint32_t je = min(j0 + (uint32_t)kTileBatch, nearEnd);
         if (active)
-          for (uint32_t j = j0; j < je; ++j) test(j);
+          for (uint32_t j = j0; j < je; ++j) test(ldg4(P.planes + j), j);
       }
       if (__any_sync(0xffffffffu, qn > 0)) flush();
     }

@@ -20,8 +20,13 @@ void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *
                    cudaStream_t st);
 int pinhole_blocks(uint32_t n);
 void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st);
-void launch_frustum_keys(const float *pos, uint32_t n, const FrustumGrid &G, uint32_t *keys, uint32_t *vals, cudaStream_t st);
-void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, cudaStream_t st);
+size_t frustum_occ_bytes();
+void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, const uint32_t *path_id, uint32_t n,
+                         const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
+                         int sm_count, cudaStream_t st);
+size_t cell_starts_scratch_bytes(uint32_t n_keys);
+void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, void *scratch,
+                        int sm_count, cudaStream_t st);
 cudaError_t run_sort_bits(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                           uint32_t *vout, uint32_t n, int bits, cudaStream_t st);
 size_t ray_grid_bytes();
@@ -57,6 +62,11 @@ cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, 
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
                      cudaStream_t st);
+void launch_generate_rays(const RayGenParams &P, cudaStream_t st);
+void launch_trace_count(const TraceParams &P, uint8_t *counts, unsigned long long *block_tot, unsigned long long *totals,
+                        cudaStream_t st);
+void launch_trace_emit(const TraceParams &P, const uint8_t *counts, const unsigned long long *block_off,
+                       unsigned long long *last_path, cudaStream_t st);
 void launch_pack_beams(const BeamStaging &S, uint32_t n, float4 *rec, float *len, cudaStream_t st);
 void launch_beam_subsize_seq(const float *len, uint32_t n, float *subsize, cudaStream_t st);
 void launch_sub_count(const float *len, uint32_t n, const float *subsize, uint32_t *block_tot, uint32_t *total, cudaStream_t st);
@@ -158,7 +168,8 @@ struct gvpm_ctx {
   int accel = ACCEL_BVH;
   bool force_bvh = false;            // GVPM_ACCEL=bvh: A/B switch for kernel experiments
   FrustumGrid grid{};
-  DevBuf cell_start, pin_scratch;    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
+  DevBuf cell_start, grid_occ, pin_scratch, trace_scratch;
+  double trace_photons_per_path = 0.0;   // running estimate (sizes the first batch of gvpm_trace_photons)    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
   uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
   struct RayFit { bool concurrent = false; float C[3], m[3], u[3], v[3], delta, cosmin, xmin, xmax, ymin, ymax, count; } pin;
   float *pin_host = nullptr;         // pinned: 16 fit floats + 8 stats words
@@ -593,7 +604,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
-                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->pin_scratch};
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
   if (ctx->pin_host) cudaFreeHost(ctx->pin_host);
@@ -1128,28 +1139,29 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   for (int k = 0; k < 3; ++k) { G.C[k] = F.C[k]; G.m[k] = F.m[k]; G.u[k] = F.u[k]; G.v[k] = F.v[k]; }
   G.xmin = F.xmin; G.xmax = F.xmax; G.ymin = F.ymin; G.ymax = F.ymax;
   G.pad_r = radius + F.delta;
-  // about one ray per class-0 cell, square cells, at most 4 M of them
+  // about one ray per class-0 cell, square cells, at most 4 M of them; every class doubles the cell edge
   const double ex = std::max((double)F.xmax - F.xmin, 1e-9), ey = std::max((double)F.ymax - F.ymin, 1e-9);
   const double target = std::min(std::max((double)F.count, 64.0), 4.0e6);
   double cell = std::sqrt(ex * ey / target);
   cell = std::max(cell, std::max(ex, ey) / 4096.0);
-  G.cell = (float)cell;
   G.gx0 = F.xmin;
   G.gy0 = F.ymin;
-  uint32_t nx0 = (uint32_t)std::floor(ex / G.cell) + 2u, ny0 = (uint32_t)std::floor(ey / G.cell) + 2u, total = 0;
+  uint32_t total = 0;
   int classes = 0;
   for (int c = 0; c < GVPM_GRID_CLASSES; ++c) {
-    G.nx[c] = (nx0 + (1u << c) - 1u) >> c;
-    G.ny[c] = (ny0 + (1u << c) - 1u) >> c;
+    G.csize[c] = (float)(cell * std::pow(2.0, (double)c));
+    G.nx[c] = (uint32_t)std::floor(ex / G.csize[c]) + 2u;
+    G.ny[c] = (uint32_t)std::floor(ey / G.csize[c]) + 2u;
     G.base[c] = total;
     total += G.nx[c] * G.ny[c];
     classes = c + 1;
-    if (G.nx[c] == 1 && G.ny[c] == 1) break;
+    if (G.nx[c] <= 2 && G.ny[c] <= 2) break;
   }
-  for (int c = classes; c < GVPM_GRID_CLASSES; ++c) { G.nx[c] = G.ny[c] = 1; G.base[c] = total; }
+  for (int c = classes; c < GVPM_GRID_CLASSES; ++c) { G.csize[c] = G.csize[classes - 1]; G.nx[c] = G.ny[c] = 1; G.base[c] = total; }
   G.classes = classes;
   G.n_cells = total;
-  const uint32_t n_keys = total + 2;   // + NEAR + DROP
+  G.parity_split = (ctx->have_cfg && ctx->cfg.path_set && !ctx->cfg.sppm_primal) ? 1 : 0;
+  const uint32_t n_keys = (G.parity_split ? 2u : 1u) * total + 2;   // + NEAR + DROP
   int bits = 1;
   while ((1ull << bits) < (unsigned long long)n_keys) ++bits;
   CK(ctx->cell_start.reserve(((size_t)n_keys + 1) * 4));
@@ -1162,13 +1174,14 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     CK(ctx->planes.reserve(16 * (size_t)n));
     CK(ctx->orig.reserve(4 * (size_t)n));
     CK(ctx->aos.reserve(128 * (size_t)n));
-    CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
+    CK(ctx->grid_occ.reserve(frustum_occ_bytes() + cell_starts_scratch_bytes(n_keys)));
     PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
-    launch_bounds(S.pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st);
-    launch_frustum_keys(S.pos, n, G, ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), st);
+    launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, S.pos, S.path_id, n, G, ctx->grid_occ.as<uint32_t>(),
+                        ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, ctx->sm_count, st);
     CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                      ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, bits, st));
-    launch_cell_starts(ctx->keys_out.as<uint32_t>(), n, n_keys, ctx->cell_start.as<uint32_t>(), st);
+    launch_cell_starts(ctx->keys_out.as<uint32_t>(), n, n_keys, ctx->cell_start.as<uint32_t>(),
+                       ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
     launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
                        ctx->orig.as<uint32_t>(), st);
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
@@ -1192,7 +1205,7 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   CK(cudaEventRecord(ctx->ev[1], st));
   ctx->timed_build = true;
   if (n_kept) {   // photons some ray can reach = everything in front of the DROP bucket (one read-back, only on request)
-    CK(cudaMemcpyAsync(ctx->pair_count_host, ctx->cell_start.as<uint32_t>() + G.n_cells + 1, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->pair_count_host, ctx->cell_start.as<uint32_t>() + n_keys - 1, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->n_kept = *(const uint32_t *)ctx->pair_count_host;
     *n_kept = ctx->n_kept;
@@ -1213,6 +1226,147 @@ int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     if (ctx->pin.concurrent && ctx->pin.delta <= 0.25f * radius) return build_frustum(ctx, radius, n_kept);
   }
   return build_pruned_bvh(ctx, radius, n_kept);
+}
+
+
+// ---- on-device generators (csrc/generate.cu) -----------------------------------------------------
+int gvpm_box_scene_default(gvpm_box_scene *s) {
+  if (!s) return GVPM_ERR_INVALID;
+  memset(s, 0, sizeof(*s));
+  for (int a = 0; a < 3; ++a) { s->lo[a] = 0.f; s->hi[a] = 1.f; }
+  const float alb[5][3] = {{0.63f, 0.065f, 0.05f}, {0.14f, 0.45f, 0.091f}, {0.7f, 0.7f, 0.7f}, {0.7f, 0.7f, 0.7f}, {0.7f, 0.7f, 0.7f}};
+  memcpy(s->face_albedo, alb, sizeof(alb));
+  s->n_rects = 1;   // the shelf
+  s->rect[0].y = 0.5f; s->rect[0].x0 = 0.3f; s->rect[0].x1 = 0.7f; s->rect[0].z0 = 0.4f; s->rect[0].z1 = 0.8f;
+  s->rect[0].albedo[0] = s->rect[0].albedo[1] = s->rect[0].albedo[2] = 0.6f;
+  s->light_y = 0.999f; s->light_x0 = 0.35f; s->light_x1 = 0.65f; s->light_z0 = 0.35f; s->light_z1 = 0.65f;
+  s->light_power = 100.f;
+  return GVPM_OK;
+}
+
+static int check_scene(gvpm_ctx *ctx, const gvpm_box_scene *s) {
+  if (s->n_rects < 0 || s->n_rects > 4) return fail(ctx, GVPM_ERR_INVALID, "gvpm_box_scene: n_rects must be in [0, 4]");
+  for (int a = 0; a < 3; ++a)
+    if (!(s->lo[a] < s->hi[a])) return fail(ctx, GVPM_ERR_INVALID, "gvpm_box_scene: empty box");
+  return GVPM_OK;
+}
+
+int gvpm_generate_rays(gvpm_ctx *ctx, const gvpm_box_scene *scene, const gvpm_pinhole_camera *cam, uint64_t seed,
+                       int block, int y0, int y1, float epsilon) {
+  if (!ctx || !scene || !cam) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = check_scene(ctx, scene);
+  if (rc) return rc;
+  const bool zorder = block < 0;
+  const int bs = zorder ? -block : block;
+  if (bs < 1 || bs > 32 || (zorder && (bs & (bs - 1)))) return fail(ctx, GVPM_ERR_INVALID, "block must be in [1, 32] (a power of two for Z-order)");
+  if (cam->film_w <= 0 || cam->film_h <= 0 || y0 < 0 || y1 > cam->film_h || y0 > y1)
+    return fail(ctx, GVPM_ERR_INVALID, "bad film size / row range");
+  const size_t n = (size_t)cam->film_w * (size_t)(y1 - y0);
+  void *dev = nullptr;
+  rc = gvpm_ray_staging(ctx, n, &dev, nullptr);
+  if (rc) return rc;
+  if (n) {
+    RayStaging S = ray_staging_ptrs(dev, n);
+    RayGenParams P{};
+    P.scene = *scene;
+    P.cam = *cam;
+    P.seed = seed;
+    P.block = bs;
+    P.zorder = zorder ? 1 : 0;
+    P.y0 = y0;
+    P.y1 = y1;
+    P.epsilon = epsilon;
+    P.o = (float *)S.o; P.d = (float *)S.d; P.mint = (float *)S.mint; P.maxt = (float *)S.maxt;
+    P.edge_len = (float *)S.edge_len; P.eye_contrib = (float *)S.eye_contrib; P.xi = (float *)S.xi;
+    P.px = (int32_t *)S.px; P.py = (int32_t *)S.py; P.edge_id = (int32_t *)S.edge_id;
+    P.off_valid = (uint8_t *)S.off_valid; P.off_o = (float *)S.off_o; P.off_d = (float *)S.off_d;
+    P.off_len = (float *)S.off_len; P.off_eye = (float *)S.off_eye; P.off_sensor = (float *)S.off_sensor;
+    launch_generate_rays(P, ctx->stream);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+  }
+  return gvpm_commit_rays(ctx);
+}
+
+int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
+                       int min_depth, uint64_t *n_paths) {
+  if (!ctx || !scene || n > 0xfffffff0u) return GVPM_ERR_INVALID;
+  if (!ctx->have_medium) return fail(ctx, GVPM_ERR_INVALID, "gvpm_set_medium first");
+  cudaSetDevice(ctx->device);
+  int rc = check_scene(ctx, scene);
+  if (rc) return rc;
+  void *dev = nullptr;
+  rc = gvpm_photon_staging(ctx, n, &dev, nullptr);
+  if (rc) return rc;
+  if (n_paths) *n_paths = 0;
+  if (n == 0) return GVPM_OK;
+  cudaStream_t st = ctx->stream;
+  PhotonStaging S = photon_staging_ptrs(dev, n);
+  TraceParams P{};
+  P.scene = *scene;
+  P.sigma_s = ctx->medium.sigma_s[0];
+  P.sigma_a = ctx->medium.sigma_a[0];
+  P.hg_g = ctx->medium.hg_g;
+  P.phase_type = ctx->medium.phase_type;
+  P.max_depth = max_depth > 0 ? max_depth : 64;
+  P.rr_depth = rr_depth;
+  P.min_depth = min_depth;
+  P.seed = seed;
+  P.n_total = n;
+  P.pos = (float *)S.pos; P.flux = (float *)S.flux; P.parent_pos = (float *)S.parent_pos; P.pred_pos = (float *)S.pred_pos;
+  P.parent_n = (float *)S.parent_n; P.prefix_flux = (float *)S.prefix_flux; P.parent_albedo = (float *)S.parent_albedo;
+  P.parent_pdf = (float *)S.parent_pdf; P.edge_pdf = (float *)S.edge_pdf; P.rr_weight = (float *)S.rr_weight;
+  P.parent_type = (uint8_t *)S.parent_type; P.depth = (uint8_t *)S.depth; P.path_id = (uint32_t *)S.path_id;
+  // batches of paths until n photons exist; the first one is sized from the photons-per-path ratio seen so far
+  unsigned long long filled = 0, pathBase = 0, *host = ctx->pair_count_host;   // host[0] batch total, host[1] last path
+  uint32_t pidBase = 0;
+  host[1] = 0;
+  for (int batch = 0; filled < n; ++batch) {
+    if (batch > 64) return fail(ctx, GVPM_ERR_INVALID, "gvpm_trace_photons: the light paths store (almost) no photon in this scene");
+    const double ratio = ctx->trace_photons_per_path > 0.0 ? ctx->trace_photons_per_path : 1.0;
+    double want = (double)(n - filled) / ratio * 1.03 + 4096.0;
+    if (want > 2.0e9) want = 2.0e9;
+    const uint32_t np = (uint32_t)want;
+    const uint32_t nb = (np + 255) / 256;
+    const size_t offCounts = 64, offBlocks = align256(offCounts + np);
+    CK(ctx->trace_scratch.reserve(offBlocks + ((size_t)nb + 1) * 8));
+    char *sc = ctx->trace_scratch.as<char>();
+    unsigned long long *totals = (unsigned long long *)sc;   // [0] batch total, [1] last path
+    if (batch == 0) CK(cudaMemsetAsync(sc, 0, 64, st));
+    P.path_base = pathBase;
+    P.n_paths = np;
+    P.slot_base = filled;
+    P.path_id_base = pidBase;
+    launch_trace_count(P, (uint8_t *)(sc + offCounts), (unsigned long long *)(sc + offBlocks), totals, st);
+    launch_trace_emit(P, (const uint8_t *)(sc + offCounts), (const unsigned long long *)(sc + offBlocks), totals + 1, st);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, totals, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long photons = host[0] & ((1ull << 40) - 1ull), paths = host[0] >> 40;
+    filled += photons;
+    pidBase += (uint32_t)paths;
+    pathBase += np;
+    ctx->trace_photons_per_path = (double)filled / (double)pathBase;
+  }
+  if (n_paths) *n_paths = host[1];
+  return GVPM_OK;
+}
+
+int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes) {
+  if (!ctx || (bytes && (!dev || !host))) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (bytes) CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GVPM_OK;
+}
+
+int gvpm_staging_peek(gvpm_ctx *ctx, int which, void **dev, size_t *count) {
+  if (!ctx || !dev || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  *dev = which == 0 ? ctx->ph_staging.p : ctx->ray_staging.p;
+  if (count) *count = which == 0 ? ctx->n_photons : ctx->n_rays;
+  return GVPM_OK;
 }
 
 int gvpm_accel_kind(const gvpm_ctx *ctx) { return ctx ? ctx->accel : 0; }

@@ -136,24 +136,27 @@ struct Tree {
 // of its own projection (delta = largest distance of C to a ray's line).  Photons are binned by FOOTPRINT CLASS c
 // (w <= cell * 2^c) into a grid coarsened by 2^c, so that a ray finds every neighbour in the 3x3 cells around its own
 // cell of every class; photons whose footprint exceeds the coarsest class go to the NEAR bucket (tested by every ray),
-// photons that no ray can reach are DROPPED.  Keys: [base[c] + cy * nx[c] + cx] < n_cells, n_cells = NEAR,
-// n_cells + 1 = DROP; cell_start[k] = first sorted slot with key >= k.
-#define GVPM_GRID_CLASSES 8
+// photons that no ray can reach (no ray in the 3x3 cells around them) are DROPPED.  cell_start[k] = first sorted slot with key >= k.
+#define GVPM_GRID_CLASSES 16
 struct FrustumGrid {
   float C[3], m[3], u[3], v[3];
-  float gx0, gy0, cell;                  // plane coordinates of the grid origin, class-0 cell edge
+  float gx0, gy0;                        // plane coordinates of the grid origin
+  float csize[GVPM_GRID_CLASSES];        // cell edge of class c = csize[0] * 2^c
   float xmin, xmax, ymin, ymax;          // bounds of the rays' projected directions
   float pad_r;                           // r + delta
   uint32_t nx[GVPM_GRID_CLASSES], ny[GVPM_GRID_CLASSES], base[GVPM_GRID_CLASSES];
-  uint32_t n_cells;
+  uint32_t n_cells;                      // cells of ONE grid (all classes)
   int classes;
+  int parity_split;                      // 1: two grids, photons with even / odd pathID (the pathSet checkerboard pairs a
+                                         // photon with pixels of its own parity only: half the candidates per ray);
+                                         // key = parity * n_cells + cell.  NEAR = grids * n_cells, DROP = NEAR + 1
 };
 
 struct GatherParams {
   Tree tree;
   // frustum-grid variant of the point gather (tree_build.cu / gather_bre.cu k_bre_grid_traverse)
   FrustumGrid grid;
-  const uint32_t *cell_start;   // [n_cells + 3]
+  const uint32_t *cell_start;   // [grids * n_cells + 3]
   const float4 *planes;  // [n] sorted P0 = pos.xyz, meta (the only per-photon data the traversal reads)
   const float4 *aos;     // [n][8] full records in the caller's order (shading reads aos[orig[slot]])
   const uint32_t *orig;  // [n] original photon index of sorted slot
@@ -209,6 +212,34 @@ struct GatherParams {
   unsigned long long dump_cap;
 };
 
+// ---- on-device generators (generate.cu) -------------------------------------------------------------------------------
+struct RayGenParams {
+  gvpm_box_scene scene;
+  gvpm_pinhole_camera cam;
+  unsigned long long seed;
+  int block, zorder, y0, y1;
+  float epsilon;
+  // ray staging arrays (gvpm_ray_soa order)
+  float *o, *d, *mint, *maxt, *edge_len, *eye_contrib, *xi;
+  int32_t *px, *py, *edge_id;
+  uint8_t *off_valid;
+  float *off_o, *off_d, *off_len, *off_eye, *off_sensor;
+};
+struct TraceParams {
+  gvpm_box_scene scene;
+  float sigma_s, sigma_a, hg_g;
+  int phase_type, max_depth, rr_depth, min_depth;
+  unsigned long long seed, path_base;
+  uint32_t n_paths;             // paths of this batch
+  // emit pass
+  unsigned long long slot_base; // photons stored by earlier batches
+  uint32_t path_id_base;        // contributing paths of earlier batches
+  unsigned long long n_total;   // capacity (photons wanted)
+  // staging arrays (gvpm_photon_soa order)
+  float *pos, *flux, *parent_pos, *pred_pos, *parent_n, *prefix_flux, *parent_albedo, *parent_pdf, *edge_pdf, *rr_weight;
+  uint8_t *parent_type, *depth;
+  uint32_t *path_id;
+};
 // ---- strictly rounded double (the reference's fp64 island: cylinderIntersection / solveQuadraticDouble,
 // photonmapper/beams_3d_intersections.h:100-137, src/libcore/util.cpp:487-525) ----------------------------
 struct sd {

@@ -571,72 +571,142 @@ __global__ void __launch_bounds__(256) k_pinhole_check(const float4 *__restrict_
   }
 }
 
-// per photon: footprint class, cell, key (see FrustumGrid).  vals = photon index.
-__global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ pos, uint32_t n, const FrustumGrid G,
-                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+// Coarse occupancy of the rays' projected directions: kOccRes x kOccRes bits over [xmin, xmax] x [ymin, ymax], built in
+// shared memory per CTA and OR-ed into global memory.  k_frustum_keys drops a photon when no bit under its footprint
+// box is set (no ray can reach it): this is what leaves most of the photon set out of a rank's sort when the image is
+// sharded over GPUs.
+constexpr int kOccRes = 256;
+constexpr int kOccWords = kOccRes * kOccRes / 32;   // 8 KB
+__device__ __forceinline__ int occ_cell(float x, float lo, float inv) {
+  return min(max((int)floorf((x - lo) * inv), 0), kOccRes - 1);
+}
+__global__ void __launch_bounds__(256) k_frustum_mark(const float4 *__restrict__ rays, uint32_t n, const FrustumGrid G,
+                                                       uint32_t *__restrict__ occ) {
+  __shared__ uint32_t mask[kOccWords];
+  for (int w = threadIdx.x; w < kOccWords; w += blockDim.x) mask[w] = 0u;
+  __syncthreads();
+  const float ix = kOccRes / fmaxf(G.xmax - G.xmin, 1e-20f), iy = kOccRes / fmaxf(G.ymax - G.ymin, 1e-20f);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q0 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4), q1 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 1),
+                 q2 = __ldg(rays + (size_t)i * GVPM_RAY_FLOAT4 + 2);
+    if (!ray_active(q0, q1, q2)) continue;
+    float x, y, z;
+    frustum_project(G.m, G.u, G.v, q1.x, q1.y, q1.z, x, y, z);
+    const int bit = occ_cell(y, G.ymin, iy) * kOccRes + occ_cell(x, G.xmin, ix);
+    const uint32_t b = 1u << (bit & 31);
+    if (!(mask[bit >> 5] & b)) atomicOr(&mask[bit >> 5], b);
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < kOccWords; w += blockDim.x)
+    if (mask[w]) atomicOr(occ + w, mask[w]);
+}
+// per photon: footprint class, cell, key (see FrustumGrid).  vals = photon index.  coord_mag: atomicMax of the largest
+// |coordinate| (float bits; the traversal's rounding pad).
+__global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ pos, const uint32_t *__restrict__ path_id,
+                                                       uint32_t n, const FrustumGrid G, const uint32_t *__restrict__ occ,
+                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                       unsigned *__restrict__ coord_mag) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float qx = pos[3 * (size_t)i] - G.C[0], qy = pos[3 * (size_t)i + 1] - G.C[1], qz = pos[3 * (size_t)i + 2] - G.C[2];
-  const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
-  const uint32_t NEAR = G.n_cells, DROP = G.n_cells + 1u;
-  uint32_t key;
-  float x, y, z;
-  frustum_project(G.m, G.u, G.v, qx, qy, qz, x, y, z);
-  const float pr = G.pad_r * 1.001f + 1e-6f * rho;
-  if (rho <= 2.f * pr) {
-    key = NEAR;                                   // alpha >= 30 degrees
-  } else if (z < 0.1f * rho) {
-    key = rho <= 6.f * pr ? NEAR : DROP;          // more than 84 degrees off axis: only reachable when very close
-  } else {
-    const float tanT = sqrtf(x * x + y * y);
-    const float ang = atanf(tanT) + asinf(pr / rho) * 1.0005f + 1e-6f;
-    if (ang >= 1.45f) {
-      key = NEAR;
+  float mag = 0.f;
+  if (i < n) {
+    const float px = pos[3 * (size_t)i], py = pos[3 * (size_t)i + 1], pz = pos[3 * (size_t)i + 2];
+    mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
+    const float qx = px - G.C[0], qy = py - G.C[1], qz = pz - G.C[2];
+    const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
+    const uint32_t grids = G.parity_split ? 2u : 1u;
+    const uint32_t NEAR = grids * G.n_cells, DROP = NEAR + 1u;
+    uint32_t key;
+    float x, y, z;
+    frustum_project(G.m, G.u, G.v, qx, qy, qz, x, y, z);
+    const float pr = G.pad_r * 1.001f + 1e-6f * rho;
+    if (rho <= 2.f * pr) {
+      key = NEAR;                                   // alpha >= 30 degrees
+    } else if (z < 0.1f * rho) {
+      key = rho <= 6.f * pr ? NEAR : DROP;          // more than 84 degrees off axis: only reachable when very close
     } else {
-      const float wfoot = (tanf(ang) - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
-      if (x < G.xmin - wfoot || x > G.xmax + wfoot || y < G.ymin - wfoot || y > G.ymax + wfoot) {
-        key = DROP;
+      const float tanT = sqrtf(x * x + y * y);
+      const float ang = atanf(tanT) + asinf(pr / rho) * 1.0005f + 1e-6f;
+      if (ang >= 1.45f) {
+        key = NEAR;
       } else {
-        int c = 0;
-        float cell = G.cell;
-        while (c < G.classes && wfoot > cell) { ++c; cell *= 2.f; }
-        if (c >= G.classes) {
-          key = NEAR;
+        const float wfoot = (tanf(ang) - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
+        if (x < G.xmin - wfoot || x > G.xmax + wfoot || y < G.ymin - wfoot || y > G.ymax + wfoot) {
+          key = DROP;
         } else {
-          const float ic = 1.f / cell;
-          int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
-          cx = min(max(cx, 0), (int)G.nx[c] - 1);
-          cy = min(max(cy, 0), (int)G.ny[c] - 1);
-          key = G.base[c] + (uint32_t)cy * G.nx[c] + (uint32_t)cx;
+          int c = 0;
+          while (c < G.classes && wfoot > G.csize[c]) ++c;
+          if (c >= G.classes) {
+            key = NEAR;
+          } else {
+            const float ic = 1.f / G.csize[c];
+            const int nx = (int)G.nx[c], ny = (int)G.ny[c];
+            int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
+            cx = min(max(cx, 0), nx - 1);
+            cy = min(max(cy, 0), ny - 1);
+            // any ray under the photon's footprint box?  (coarse bitmask, conservative: the box is padded by one ulp-ish
+            // margin through wfoot's own 1 % pad)
+            const float oix = kOccRes / fmaxf(G.xmax - G.xmin, 1e-20f), oiy = kOccRes / fmaxf(G.ymax - G.ymin, 1e-20f);
+            const int ox0 = occ_cell(x - wfoot, G.xmin, oix), ox1 = occ_cell(x + wfoot, G.xmin, oix);
+            const int oy0 = occ_cell(y - wfoot, G.ymin, oiy), oy1 = occ_cell(y + wfoot, G.ymin, oiy);
+            bool any = false;
+            for (int yy = oy0; yy <= oy1 && !any; ++yy)
+              for (int w0 = ox0 >> 5; w0 <= (ox1 >> 5); ++w0) {
+                const int b0 = max(ox0 - 32 * w0, 0), b1 = min(ox1 - 32 * w0, 31);
+                const uint32_t bits = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
+                any = any || (__ldg(occ + yy * (kOccRes / 32) + w0) & bits) != 0u;
+              }
+            const uint32_t par = G.parity_split ? (__ldg(path_id + i) & 1u) : 0u;
+            key = any ? par * G.n_cells + G.base[c] + (uint32_t)cy * (uint32_t)nx + (uint32_t)cx : DROP;
+          }
         }
       }
     }
+    keys[i] = key;
+    vals[i] = i;
   }
-  keys[i] = key;
-  vals[i] = i;
+  for (int o = 16; o > 0; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
+  if ((threadIdx.x & 31) == 0 && mag > 0.f) atomicMax(coord_mag, __float_as_uint(mag));
 }
-// cell_start[k] = first sorted slot whose key is >= k, for k in [0, n_keys].  Thread i fills the gap in front of slot i
-// when it is short (the usual case: about as many photons as cells); cells of long gaps keep the 0xffffffff the array
-// was initialised with and are found by a binary search in the second pass (sparse photon sets).
+// cell_start[k] = first sorted slot whose key is >= k, for k in [0, n_keys].  Lane i owns the gap of keys in front of
+// slot i; the warp fills its lanes' gaps one after the other with all 32 lanes writing (coalesced).  Gaps of 4096 cells
+// and more (whole empty classes) are left to the second pass, which spreads each of them over the whole grid.
+struct BigGap { uint32_t lo, hi, val; };
 __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t n_keys,
-                                                      uint32_t *__restrict__ cell_start) {
+                                                      uint32_t *__restrict__ cell_start, BigGap *__restrict__ big,
+                                                      uint32_t *__restrict__ n_big, uint32_t big_cap) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  const uint32_t lo = i == 0 ? 0u : sorted_keys[i - 1] + 1u;
-  const uint32_t hi = i == n ? n_keys : min(sorted_keys[i], n_keys);   // inclusive
-  if (lo > hi || hi - lo >= 32u) return;
-  for (uint32_t k = lo; k <= hi; ++k) cell_start[k] = i;
-}
-__global__ void __launch_bounds__(256) k_cell_starts_fill(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t n_keys,
-                                                           uint32_t *__restrict__ cell_start) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > n_keys || cell_start[k] != 0xffffffffu) return;
-  uint32_t a = 0, b = n;   // lower_bound(k)
-  while (a < b) {
-    const uint32_t mid = a + ((b - a) >> 1);
-    if (__ldg(sorted_keys + mid) < k) a = mid + 1; else b = mid;
+  const int lane = threadIdx.x & 31;
+  uint32_t lo = 1u, hi = 0u;   // empty
+  if (i <= n) {
+    lo = i == 0 ? 0u : sorted_keys[i - 1] + 1u;
+    hi = i == n ? n_keys : min(sorted_keys[i], n_keys);   // inclusive
   }
-  cell_start[k] = a;
+  const bool has = lo <= hi;
+  if (has && hi - lo >= 4095u) {
+    const uint32_t slot = atomicAdd(n_big, 1u);
+    if (slot < big_cap) big[slot] = BigGap{lo, hi, i};
+    lo = 1u; hi = 0u;
+  } else if (has && hi == lo) {
+    cell_start[lo] = i;   // the common case: one cell per photon step
+    lo = 1u; hi = 0u;
+  }
+  uint32_t m = __ballot_sync(0xffffffffu, lo <= hi);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t glo = __shfl_sync(0xffffffffu, lo, src), ghi = __shfl_sync(0xffffffffu, hi, src),
+                   gv = __shfl_sync(0xffffffffu, i, src);
+    for (uint32_t k = glo + lane; k <= ghi; k += 32) cell_start[k] = gv;
+  }
+}
+__global__ void __launch_bounds__(256) k_cell_starts_big(uint32_t *__restrict__ cell_start, const BigGap *__restrict__ big,
+                                                          const uint32_t *__restrict__ n_big, uint32_t big_cap) {
+  const uint32_t nb = min(*n_big, big_cap);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (uint32_t g = 0; g < nb; ++g) {
+    const BigGap G = big[g];
+    for (uint32_t k = G.lo + tid; k <= G.hi; k += stride) cell_start[k] = G.val;
+  }
 }
 
 // raw ray SoA -> 5 x 64 B records per ray
@@ -730,13 +800,26 @@ void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *
   cudaMemsetAsync(stats, 0, 32, st);
   k_pinhole_check<<<nb, 256, 0, st>>>(rays, n, fit, stats);
 }
-void launch_frustum_keys(const float *pos, uint32_t n, const FrustumGrid &G, uint32_t *keys, uint32_t *vals, cudaStream_t st) {
-  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, n, G, keys, vals);
+size_t frustum_occ_bytes() { return (size_t)kOccWords * 4; }
+// occ: frustum_occ_bytes() (zeroed here); coord_mag: one word (zeroed here)
+void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, const uint32_t *path_id, uint32_t n,
+                         const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
+                         int sm_count, cudaStream_t st) {
+  cudaMemsetAsync(occ, 0, frustum_occ_bytes(), st);
+  cudaMemsetAsync(coord_mag, 0, 4, st);
+  if (n_rays) k_frustum_mark<<<std::min<uint32_t>((n_rays + 255) / 256, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, n_rays, G, occ);
+  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, path_id, n, G, occ, keys, vals, coord_mag);
 }
-void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, cudaStream_t st) {
-  cudaMemsetAsync(cell_start, 0xff, ((size_t)n_keys + 1) * 4, st);
-  k_cell_starts<<<(n + 1 + 255) / 256, 256, 0, st>>>(sorted_keys, n, n_keys, cell_start);
-  k_cell_starts_fill<<<(n_keys + 1 + 255) / 256, 256, 0, st>>>(sorted_keys, n, n_keys, cell_start);
+// scratch: cell_starts_scratch_bytes(n_keys) bytes
+size_t cell_starts_scratch_bytes(uint32_t n_keys) { return 16 + ((size_t)n_keys / 4096 + 2) * sizeof(BigGap); }
+void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, void *scratch,
+                        int sm_count, cudaStream_t st) {
+  uint32_t *n_big = (uint32_t *)scratch;
+  BigGap *big = (BigGap *)((char *)scratch + 16);
+  const uint32_t cap = n_keys / 4096 + 2;   // gaps of >= 4096 cells are disjoint: there cannot be more of them
+  cudaMemsetAsync(n_big, 0, 4, st);
+  k_cell_starts<<<(n + 1 + 255) / 256, 256, 0, st>>>(sorted_keys, n, n_keys, cell_start, big, n_big, cap);
+  k_cell_starts_big<<<2 * sm_count, 256, 0, st>>>(cell_start, big, n_big, cap);
 }
 cudaError_t run_sort_bits(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                           uint32_t *vout, uint32_t n, int bits, cudaStream_t st) {

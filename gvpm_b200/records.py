@@ -228,3 +228,22 @@ def synth_occluders():
     tri = np.zeros(n * 9, dtype=np.float32)
     s.gvpm_synth_occluders(tri.ctypes.data_as(N.f32p))
     return tri
+
+
+def box_scene_default():
+    """The Cornell box of the synthetic workloads as a gvpm_box_scene (rows f-1 / f-2: on-device generators)."""
+    sc = N.BoxScene()
+    rc = N.load_lib().gvpm_box_scene_default(C.byref(sc))
+    assert rc == 0
+    return sc
+
+
+def pinhole_camera(w, h, cam_dist=1.5, cover=0.96):
+    """The sensor of synth_rays(): at (0.5, 0.5, -cam_dist) looking down +z; cam_dist < 0: inside the medium at
+    z = -cam_dist with tan(fov/2) = cover."""
+    cam = N.PinholeCamera()
+    cam.pos[0], cam.pos[1], cam.pos[2] = 0.5, 0.5, -cam_dist
+    inside = cam_dist < 0
+    cam.tan_half_fov_x = np.float32(cover) if inside else np.float32(0.5) * np.float32(cover) / np.float32(cam_dist)
+    cam.film_w, cam.film_h, cam.inside_medium = w, h, int(inside)
+    return cam

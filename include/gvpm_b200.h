@@ -432,6 +432,61 @@ int gvpm_reconstruct(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs,
 /* device time of the last gvpm_poisson_solve / gvpm_reconstruct, copies included (CUDA events, ms) */
 float gvpm_last_poisson_ms(const gvpm_ctx *ctx);
 
+
+/* ---- next rows: the two host stages on either side of the gather, on the device -------------
+ * Scene class covered (the synthetic scenes of SURVEY.md 8d): an axis-aligned box filled with the homogeneous
+ * medium set by gvpm_set_medium, diffuse walls with one albedo per face, the face z = lo[2] OPEN (index-matched
+ * boundary towards the sensor: light paths leave through it, camera rays enter through it), up to 4 two-sided
+ * diffuse rectangles parallel to the xz plane inside the box, and a rectangular diffuse area light on the plane
+ * y = light_y pointing down (-y).  gvpm_box_scene_default() is the Cornell box of the bench / test workloads.
+ * Everything else (arbitrary meshes, glossy BSDFs, other emitters) stays with the host renderer and the upload entry
+ * points above. */
+typedef struct gvpm_box_scene {
+  float lo[3], hi[3];           /* the medium's box */
+  float face_albedo[5][3];      /* x = lo, x = hi, y = lo, y = hi, z = hi (z = lo is open) */
+  int32_t n_rects;              /* <= 4 */
+  struct { float y, x0, x1, z0, z1, albedo[3]; } rect[4];
+  float light_y, light_x0, light_x1, light_z0, light_z1, light_power;
+} gvpm_box_scene;
+int gvpm_box_scene_default(gvpm_box_scene *s);
+
+/* f-2: camera-ray medium segments + their four offset segments (what gvpm_upload_rays takes) generated on the device
+ * for a pinhole sensor at `pos` looking down +z: replaces, for this scene class, the camera sub-path tracing of
+ * GatherPointMap::generate (gvpm/gvpm_gatherpoint.h:259-486), the offset paths of ShiftGatherPoint::generate
+ * (gvpm/shift/shift_cameraPath.h:146-413; offsets at +-1 pixel, shift_utilities.h:255-261) and sensorMIS
+ * (gvpm_struct.h:608-631, = 1 for a pinhole).  One jittered sample per pixel from the counter-based RNG
+ * PCG32(seed, pixel index); rays are emitted block by block (block x block pixels like m_gatherBlocks,
+ * gvpm.cpp:271-290; block < 0: Z-order inside a block), rows [y0, y1) of the image.  tan_half_fov_x is the half width
+ * of the image plane at distance 1.  The rays are committed (as after gvpm_upload_rays); n_rays = w * (y1 - y0). */
+typedef struct gvpm_pinhole_camera {
+  float pos[3];
+  float tan_half_fov_x;
+  int32_t film_w, film_h;
+  int32_t inside_medium;        /* 1: the sensor sits in the medium (segments start at pos, edge 1); 0: in front of the
+                                   open face (segments start on it, edge 2) */
+} gvpm_pinhole_camera;
+int gvpm_generate_rays(gvpm_ctx *ctx, const gvpm_box_scene *scene, const gvpm_pinhole_camera *cam, uint64_t seed,
+                       int block, int y0, int y1, float epsilon);
+
+/* f-1: the iteration's volume photons traced on the device: replaces, for this scene class, the light-path random walk
+ * of GradientPhotonProcess (gvpm/gvpm_proc.cpp:125-210,336-350) and GPhotonMap::tryAppend (gvpm_accel.h:119-199).
+ * Light path k draws from PCG32(seed, k); free paths are exponential, scattering follows the phase function of
+ * gvpm_set_medium, walls and rectangles reflect diffusely, russian roulette from depth rr_depth with
+ * q = min(max throughput, 0.95); every medium vertex with index >= max(2, min_depth + 1) is stored until n photons
+ * exist (paths are taken in index order, so the set does not depend on the launch geometry).  log / exp / sin / cos
+ * are evaluated by fixed polynomial routines in strictly rounded fp32 (no libm), so the records are bit-reproducible
+ * and an independent CPU restatement produces the same bits.  The photons land in the selected staging buffer exactly
+ * as gvpm_upload_photons leaves them (call gvpm_build_points / _for_rays next).  n_paths: light paths traced up to and
+ * including the one that completed the set (nbPathVolume, the gather's normalisation). */
+int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
+                       int min_depth, uint64_t *n_paths);
+/* parity aid: copy `bytes` bytes at `dev` (a pointer handed out by this library, e.g. gvpm_photon_staging /
+ * gvpm_ray_staging) to host memory, after the work queued on the context's stream */
+int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes);
+/* parity aid: the selected photon staging buffer (which = 0) or the ray staging buffer (which = 1) as they are, without
+ * the side effects of gvpm_photon_staging / gvpm_ray_staging (which invalidate the build / the committed rays) */
+int gvpm_staging_peek(gvpm_ctx *ctx, int which, void **dev, size_t *count);
+
 /* ---- timing of the last build / gather on the context's stream (CUDA events, ms) ----- */
 int gvpm_last_timings(gvpm_ctx *ctx, float *build_ms, float *gather_ms);
 /* split of the last gather: traversal kernel, shading kernel (of the last ray range), and the number of

@@ -315,3 +315,29 @@ def vpm_gather(photons, rays, samples, medium, config, tri, nb_camera_samples, m
         if tree:
             lib.gvpm_oracle_tree_free(tree)
     return VpmResult(out.reshape(rays.n, N.GVPM_OUT_FLOATS), mvol, sc.reshape(samples.n, 2), offsets, idx, ms.value)
+
+
+def trace_photons(scene, medium, n, seed, max_depth=12, rr_depth=1, min_depth=0):
+    """CPU restatement of gvpm_trace_photons (oracle/gvpm_oracle_trace.cpp): -> (PhotonSet, light paths traced)"""
+    from gvpm_b200 import records as R
+    lib = load()
+    lib.gvpm_oracle_trace_photons.argtypes = [C.POINTER(N.BoxScene), C.POINTER(N.Medium), C.c_size_t, C.c_uint64, C.c_int,
+                                              C.c_int, C.c_int, C.POINTER(N.PhotonSoA)]
+    lib.gvpm_oracle_trace_photons.restype = C.c_longlong
+    ps = R.PhotonSet(n)
+    cs = ps.as_c()
+    paths = lib.gvpm_oracle_trace_photons(C.byref(scene), C.byref(medium), n, seed, max_depth, rr_depth, min_depth, C.byref(cs))
+    if paths < 0:
+        raise RuntimeError("gvpm_oracle_trace_photons failed")
+    return ps, int(paths)
+
+
+def pm_functions(x):
+    """the tracer's polynomial log(x), exp(-x), sin(2 pi frac(x)), cos(2 pi frac(x))"""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    outs = [np.zeros(x.size, np.float32) for _ in range(4)]
+    lib.gvpm_oracle_pm_functions.argtypes = [C.c_size_t] + [N.f32p] * 5
+    lib.gvpm_oracle_pm_functions.restype = None
+    lib.gvpm_oracle_pm_functions(x.size, x.ctypes.data_as(N.f32p), *[o.ctypes.data_as(N.f32p) for o in outs])
+    return outs

@@ -93,6 +93,10 @@ template <typename Real> struct Medium {
     sigmaT = sigmaS + sigmaA;
   }
   struct Rec { V3<Real> transmittance; Real pdfSuccess, pdfFailure; };
+  // math::fastexp, include/mitsuba/core/math.h:175-187: on Linux / x86_64 the single-precision build evaluates exp in
+  // DOUBLE and rounds the result to float (pinned bit-exactly against the reference's compiled HomogeneousMedium::eval,
+  // tests/test_oracle_physics_pin.py)
+  static Real fastexp(Real v) { return (Real)std::exp((double)v); }
   // eval(ray, mRec) with EDistanceNormal: distance = maxt - mint
   Rec eval(Real mint, Real maxt) const {
     Rec r;
@@ -100,14 +104,14 @@ template <typename Real> struct Medium {
     r.pdfSuccess = 0;
     r.pdfFailure = 0;
     for (int i = 0; i < 3; ++i) {  // :478-483
-      Real tmp = std::exp(-sigmaT[i] * distance);
+      Real tmp = fastexp(-sigmaT[i] * distance);
       r.pdfFailure += tmp;
       r.pdfSuccess += sigmaT[i] * tmp;
     }
     r.pdfSuccess /= 3;
     r.pdfFailure /= 3;
-    r.transmittance = V3<Real>(std::exp(sigmaT.x * (-distance)), std::exp(sigmaT.y * (-distance)),
-                               std::exp(sigmaT.z * (-distance)));  // :504
+    r.transmittance = V3<Real>(fastexp(sigmaT.x * (-distance)), fastexp(sigmaT.y * (-distance)),
+                               fastexp(sigmaT.z * (-distance)));  // :504
     r.pdfSuccess = r.pdfSuccess * samplingWeight;                    // :505
     r.pdfFailure = r.pdfFailure * samplingWeight + (1 - samplingWeight);
     if (r.transmittance.maxc() < (Real)1e-20) r.transmittance = V3<Real>();  // :511-512
@@ -258,6 +262,13 @@ template <typename Real> struct Scene {
   // medium}.  Returns throughput and pdf (pdf = 0 when the reconnection is impossible).
   void diffuseReconnection(const Photon<Real> &ph, const V3<Real> &newD, Real newDLength,
                            V3<Real> &throughput, Real &pdf) const {
+    diffuseReconnectionStatus(ph, newD, newDLength, throughput, pdf);
+  }
+  // same, returning the reference function's own return value (false: the caller treats the shift as failed); throughput
+  // and pdf hold what the reference's ShiftRecord holds at that point, which is what the pin against
+  // shift_diffuse.cpp compares (tests/test_oracle_physics_pin.py)
+  bool diffuseReconnectionStatus(const Photon<Real> &ph, const V3<Real> &newD, Real newDLength,
+                                 V3<Real> &throughput, Real &pdf) const {
     throughput = V3<Real>(1, 1, 1);
     pdf = 0;
     Real pdfValue;
@@ -273,7 +284,7 @@ template <typename Real> struct Scene {
         pdfValue = INV_PI * cosO;
       }
       // geometric == shading normal for the flattened record: :43-47
-      if (cosI * cosI <= 0 || cosO * cosO <= 0) return;
+      if (cosI * cosI <= 0 || cosO * cosO <= 0) return false;
     } else if (ph.parentType == GVPM_PARENT_MEDIUM) {
       V3<Real> pWi = normalize(ph.predPos - ph.parentPos);
       Real phv = medium.phase(pWi, newD);
@@ -285,18 +296,19 @@ template <typename Real> struct Scene {
       throughput = throughput * V3<Real>(INV_PI * dp, INV_PI * dp, INV_PI * dp);
       pdfValue = INV_PI * dp;
     } else {
-      return;  // glossy parent: manifold shift, out of scope (treated as a failed shift)
+      return false;  // glossy parent: manifold shift, out of scope (treated as a failed shift)
     }
     Real GOp = 1 / (newDLength * newDLength);  // :89-92 (isVolumeBase)
     pdf = pdfValue * GOp;
     throughput = throughput * GOp;
-    if (ph.parentPdf == 0) { pdf = 0; return; }  // :100-104
+    if (ph.parentPdf == 0) { pdf = 0; return false; }  // :100-104
     throughput = throughput / ph.parentPdf;       // :111
     throughput = throughput * ph.rrWeight;        // :112
     // edge->medium != nullptr always holds for a volume photon's last edge: :114-131
     typename Medium<Real>::Rec m = medium.eval(0, newDLength);
     pdf *= m.pdfSuccess;
     throughput = throughput * (m.transmittance / ph.edgePdf);
+    return true;
   }
 
   // AbstractVolumeGradientRecord::shiftNull, shift_volume_photon.cpp:119-158
@@ -538,15 +550,15 @@ template <typename Real> struct Scene {
         const Real maxDist = ray.offLen[k] - (Real)cfg.epsilon, distance = v.t;
         Real ps = 0;
         for (int c = 0; c < 3; ++c) {
-          const Real normalization = 1 - std::exp(-medium.sigmaT[c] * maxDist);
-          const Real tmp = std::exp(-medium.sigmaT[c] * distance);
+          const Real normalization = 1 - Medium<Real>::fastexp(-medium.sigmaT[c] * maxDist);
+          const Real tmp = Medium<Real>::fastexp(-medium.sigmaT[c] * distance);
           ps += (medium.sigmaT[c] / normalization) * tmp;
         }
         ps /= 3;
         v.shiftMRec[k].pdfSuccess = ps;
-        v.shiftMRec[k].transmittance = V3<Real>(std::exp(medium.sigmaT.x * (-distance)),
-                                                std::exp(medium.sigmaT.y * (-distance)),
-                                                std::exp(medium.sigmaT.z * (-distance)));
+        v.shiftMRec[k].transmittance = V3<Real>(Medium<Real>::fastexp(medium.sigmaT.x * (-distance)),
+                                                Medium<Real>::fastexp(medium.sigmaT.y * (-distance)),
+                                                Medium<Real>::fastexp(medium.sigmaT.z * (-distance)));
         if (v.shiftMRec[k].transmittance.maxc() < (Real)1e-20) v.shiftMRec[k].transmittance = V3<Real>();
       }
     }

@@ -170,3 +170,70 @@ void gvpm_oracle_pin_quadratic(const double *abc, size_t m, uint8_t *ok, double 
 }
 
 }  // extern "C"
+
+// ---- radiometric building blocks, same flat signatures as oracle/ref_physics.cpp (the reference's medium / phase /
+// BSDF / emitter plugins and shift_diffuse.cpp compiled from /root/reference) --------------------------------------------
+namespace {
+gvpm_medium makeMedium(const float *sigS, const float *sigA, float samplingWeight, int phaseType, float g) {
+  gvpm_medium m;
+  std::memset(&m, 0, sizeof(m));
+  for (int c = 0; c < 3; ++c) { m.sigma_s[c] = sigS[c]; m.sigma_a[c] = sigA[c]; }
+  m.sampling_weight = samplingWeight;
+  m.phase_type = phaseType;
+  m.hg_g = g;
+  return m;
+}
+}  // namespace
+
+extern "C" {
+
+// Medium<float>::eval: HomogeneousMedium::eval, src/medium/homogeneous.cpp:432-513
+void gvpm_oracle_pin_medium_eval(const float *sigS, const float *sigA, float samplingWeight, size_t n, const float *mint,
+                                 const float *maxt, float *T, float *pdfSuccess, float *pdfFailure) {
+  const Medium<float> med(makeMedium(sigS, sigA, samplingWeight, GVPM_PHASE_ISOTROPIC, 0.f));
+  for (size_t i = 0; i < n; ++i) {
+    const Medium<float>::Rec r = med.eval(mint[i], maxt[i]);
+    T[3 * i] = r.transmittance.x; T[3 * i + 1] = r.transmittance.y; T[3 * i + 2] = r.transmittance.z;
+    pdfSuccess[i] = r.pdfSuccess;
+    pdfFailure[i] = r.pdfFailure;
+  }
+}
+
+// Medium<float>::phase: phase/isotropic.cpp:76, phase/hg.cpp:107-110 (eval == pdf for both)
+void gvpm_oracle_pin_phase(int type, float g, size_t n, const float *wi, const float *wo, float *eval, float *pdf) {
+  const float one[3] = {1.f, 1.f, 1.f};
+  const Medium<float> med(makeMedium(one, one, 1.f, type, g));
+  for (size_t i = 0; i < n; ++i) eval[i] = pdf[i] = med.phase(V3<float>(wi + 3 * i), V3<float>(wo + 3 * i));
+}
+
+// Scene<float>::diffuseReconnection (shift_diffuse.cpp:11-134) on flattened parent records.  ok mirrors the reference's
+// return value: false when the surface side tests fail (:43-47), when the parent pdf is zero (:100-104), or for a
+// parent that is not in scope.
+void gvpm_oracle_pin_diffuse_reconnection(const float *sigS, const float *sigA, float samplingWeight, int phaseType, float g,
+                                          size_t n, const uint8_t *parent_type, const float *parent_pos,
+                                          const float *pred_pos, const float *parent_n, const float *albedo,
+                                          const float *parent_pdf, const float *edge_pdf, const float *rr_weight,
+                                          const float *newD, const float *newDLength, uint8_t *ok, float *throughput,
+                                          float *pdf) {
+  gvpm_config cfg = dummyConfig();
+  const Scene<float> sc(makeMedium(sigS, sigA, samplingWeight, phaseType, g), cfg, 1.f);
+  for (size_t i = 0; i < n; ++i) {
+    Photon<float> ph;
+    ph.parentType = parent_type[i];
+    ph.parentPos = V3<float>(parent_pos + 3 * i);
+    ph.predPos = V3<float>(pred_pos + 3 * i);
+    ph.parentN = V3<float>(parent_n + 3 * i);
+    ph.albedo = V3<float>(albedo + 3 * i);
+    ph.parentPdf = parent_pdf[i];
+    ph.edgePdf = edge_pdf[i];
+    ph.rrWeight = rr_weight[i];
+    V3<float> thr;
+    float p = 0.f;
+    const bool good = sc.diffuseReconnectionStatus(ph, V3<float>(newD + 3 * i), newDLength[i], thr, p);
+    ok[i] = good ? 1 : 0;
+    throughput[3 * i] = thr.x; throughput[3 * i + 1] = thr.y; throughput[3 * i + 2] = thr.z;
+    pdf[i] = p;
+  }
+}
+
+}  // extern "C"

@@ -45,7 +45,15 @@ inline Spectrum S3(const float *p) {
 }
 inline void putS(float *dst, const Spectrum &s) { dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; }
 
+// Class::staticInitialization links every registered class to its superclass (src/libcore/class.cpp); the reference
+// does this in its start-up code (mitsuba.cpp), the addChild() type checks depend on it
+void initOnce() {
+  static bool done = false;
+  if (!done) { Class::staticInitialization(); done = true; }
+}
+
 ref<PhaseFunction> makePhase(int type, float g) {
+  initOnce();
   ref<PhaseFunction> ph;
   if (type == 0) {
     ph = static_cast<PhaseFunction *>(CreateInstance_iso(Properties("isotropic")));

@@ -28,7 +28,7 @@
 
 MTS_NAMESPACE_BEGIN
 
-static void phys_unreachable(const char *what) {
+void phys_unreachable(const char *what) {
   std::fprintf(stderr, "gvpm physics ref harness: unexpected call to %s\n", what);
   std::abort();
 }
@@ -101,22 +101,25 @@ void Stream::writeUChar(unsigned char) { phys_unreachable("Stream::writeUChar");
 unsigned char Stream::readUChar() { phys_unreachable("Stream::readUChar"); return 0; }
 void Stream::writeString(const std::string &) { phys_unreachable("Stream::writeString"); }
 Properties::EPropertyType Properties::getType(const std::string &) const { phys_unreachable("Properties::getType"); return EBoolean; }
-ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &, const Transform &) const {
-  phys_unreachable("Properties::getAnimatedTransform");
-  return NULL;
-}
-AnimatedTransform::AnimatedTransform(Stream *) { phys_unreachable("AnimatedTransform(Stream*)"); }
-void AnimatedTransform::serialize(Stream *) const { phys_unreachable("AnimatedTransform::serialize"); }
+// AbstractEmitter's constructor asks for its "toWorld" transform (src/librender/emitter.cpp:28); AnimatedTransform lives in
+// src/libcore/track.cpp, which needs Eigen.  The harness' area light is never transformed (evalDirection / pdfDirection
+// only read the position record's normal): no transform object.
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &, const Transform &) const { return NULL; }
 // statistics counters of the plugins (src/libcore/statistics.cpp registers them with a global singleton): inert here
 StatsCounter::StatsCounter(const std::string &, const std::string &, EStatsType, uint64_t, uint64_t) : m_value(NULL), m_base(NULL) {}
 StatsCounter::~StatsCounter() {}
 std::string Spectrum::toString() const { return "Spectrum[harness]"; }
 Spectrum Spectrum::CIE_D65(1.0f);     // set by Spectrum::staticInitialization in src/libcore/spectrum.cpp (needs boost::filesystem); the harness always passes a radiance
 Class *Sensor::m_theClass = NULL;          // only referenced by a derivesFrom() check in Shape::addChild, never reached
-Bitmap::Bitmap(EPixelFormat, EComponentFormat, const Vector2i &, uint8_t, uint8_t *) { phys_unreachable("Bitmap"); }
-ref<Bitmap> Bitmap::arithmeticOperation(EArithmeticOperation, const Bitmap *, const Bitmap *) {
-  phys_unreachable("Bitmap::arithmeticOperation");
-  return NULL;
-}
 
 MTS_NAMESPACE_END
+
+// Symbols that are referenced from code the harness never reaches (bitmap export of a constant texture, stream
+// constructors of animated transforms): satisfied by name only, so that no Bitmap / AnimatedTransform class code (and
+// the image libraries behind it) has to be compiled.
+extern "C" {
+void _ZN7mitsuba17AnimatedTransformC1EPNS_6StreamE() { mitsuba::phys_unreachable("AnimatedTransform(Stream*)"); }
+void _ZNK7mitsuba17AnimatedTransform9serializeEPNS_6StreamE() { mitsuba::phys_unreachable("AnimatedTransform::serialize"); }
+void _ZN7mitsuba6BitmapC1ENS0_12EPixelFormatENS0_16EComponentFormatERKNS_8TVector2IiEEhPh() { mitsuba::phys_unreachable("Bitmap"); }
+void _ZN7mitsuba6Bitmap19arithmeticOperationENS0_20EArithmeticOperationEPKS0_S3_() { mitsuba::phys_unreachable("Bitmap::arithmeticOperation"); }
+}
