@@ -1008,6 +1008,42 @@ def main():
     W = max(3, args.warmup)
     ms_total, launches, build_ms, gather_ms = timed(step_resident, args.steps, W, False)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, W, True)
+    # ---- rows f-1 / f-2: the whole iteration on the device (photons traced, rays generated: nothing uploaded), results
+    # to pinned host memory.  N = 1 only; reported next to the host-buffer e2e, never instead of it.
+    traced = None
+    if world == 1 and os.environ.get("GVPM_BENCH_TRACED", "1") != "0":
+        import gvpm_b200 as g
+        scene, cam = g.box_scene_default(), g.pinhole_camera(inp["w"], inp["h"])
+        tr_paths = [0]
+
+        def step_traced(k):
+            tr_paths[0] = ctx.trace_photons(scene, n_ph, 0xC0FFEE + 100 + k, direct=True)
+            ctx.generate_rays(scene, cam, 0xC0FFEE + 200 + k, block=-32)
+            ctx.build_points_for_rays(inp["radius"], want_kept=False)
+            ctx.gather_bre(out=out_host[:n_local * 27], counts=False)
+        ms_tr, launches_tr, _, _ = timed(step_traced, args.steps, W, False)
+        # phases of one traced step (CUDA events around each call)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        evs[0].record(stream)
+        ctx.trace_photons(scene, n_ph, 0xC0FFEE + 99, direct=True); evs[1].record(stream)
+        ctx.generate_rays(scene, cam, 0xC0FFEE + 98, block=-32); evs[2].record(stream)
+        ctx.build_points_for_rays(inp["radius"], want_kept=False); evs[3].record(stream)
+        ctx.gather_bre_into(out_dev.data_ptr(), None); evs[4].record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        traced = {"ms_per_step": ms_tr / args.steps, "value": inp["rays_full_n"] * args.steps / (ms_tr * 1e-3), "unit": "rays/s",
+                  "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(inp["rays_full_n"] * 27 * 4),
+                  "phases_ms": {"trace_photons": evs[0].elapsed_time(evs[1]), "generate_rays": evs[1].elapsed_time(evs[2]),
+                                "build": evs[2].elapsed_time(evs[3]), "gather": evs[3].elapsed_time(evs[4])},
+                  "light_paths": tr_paths[0], "gpu_launches": int(launches_tr),
+                  "note": "gvpm_trace_photons_direct + gvpm_generate_rays + gvpm_build_points_for_rays + gvpm_gather_bre "
+                          "(27 planes to pinned host memory) per step: inputs are a scene / camera description, created "
+                          "on the device - by the contract's definition NOT the end-to-end number, which stays `e2e`"}
+        # back to the uploaded set for the remaining diagnostics
+        ctx.photon_staging_select(0)
+        ctx.photon_staging(n_ph)
+        with torch.cuda.stream(stream):
+            ctx.upload_rays(rays)
     clocks = sampler.stop() if rank == 0 else None
     # every exchange must have rebuilt the full photon set in both staging buffers
     staging_ok = bool(torch.equal(stage_t[0], stage_t[1]))
@@ -1100,6 +1136,8 @@ def main():
                            "rays_per_rank": [int(k[1].item()) for k in kept_all],
                            "photons_in_hierarchy_per_rank": [int(k[0].item()) for k in kept_all]},
                 "light_paths": inp["n_paths"]}
+        if traced is not None:
+            line["device_traced"] = traced
         if world == 1 and not args.no_cpu_baseline:
             inp["full_rays"] = inp["rays"]
             cb, _, _ = cpu_arm(args, inp, args.cpu_seconds)

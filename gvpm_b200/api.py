@@ -131,11 +131,13 @@ class Context:
         self.n_rays = camera.film_w * (y1 - y0)
         return self.n_rays
 
-    def trace_photons(self, scene, n, seed, max_depth=12, rr_depth=1, min_depth=0):
-        """the iteration's volume photons traced on the device into the selected staging buffer; -> light paths traced"""
+    def trace_photons(self, scene, n, seed, max_depth=12, rr_depth=1, min_depth=0, direct=False):
+        """the iteration's volume photons traced on the device into the selected staging buffer (direct: straight into
+        the gather's records); -> light paths traced"""
         paths = C.c_uint64(0)
-        self._ck(self.lib.gvpm_trace_photons(self.h, C.byref(scene), n, C.c_uint64(seed), max_depth, rr_depth, min_depth,
-                                             C.byref(paths)), "gvpm_trace_photons")
+        fn = self.lib.gvpm_trace_photons_direct if direct else self.lib.gvpm_trace_photons
+        self._ck(fn(self.h, C.byref(scene), n, C.c_uint64(seed), max_depth, rr_depth, min_depth, C.byref(paths)),
+                 "gvpm_trace_photons")
         self.n_photons = n
         return int(paths.value)
 

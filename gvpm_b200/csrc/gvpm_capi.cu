@@ -15,15 +15,21 @@ size_t sort_temp_bytes(uint32_t n);
 cudaError_t run_sort(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                      uint32_t *vout, uint32_t n, cudaStream_t st);
 int bounds_blocks(uint32_t n);
-void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st);
+void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st, uint32_t stride = 3);
 void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
-                   cudaStream_t st);
+                   cudaStream_t st, uint32_t stride = 3);
 int pinhole_blocks(uint32_t n);
 void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st);
 size_t frustum_occ_bytes();
-void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, const uint32_t *path_id, uint32_t n,
+void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, uint32_t stride, const uint32_t *par_src,
+                         uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
-                         int sm_count, cudaStream_t st);
+                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st);
+void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
+                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st);
+void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
+                             float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st, bool records_ready);
+void launch_scan_u32(uint32_t *vals, uint32_t nb, uint32_t *total, cudaStream_t st);
 size_t cell_starts_scratch_bytes(uint32_t n_keys);
 void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys, uint32_t *cell_start, void *scratch,
                         int sm_count, cudaStream_t st);
@@ -39,7 +45,7 @@ void launch_keys_kept(const float *pos, const uint32_t *vals, uint32_t m, const 
 void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
                         float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st);
 void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sorted, uint32_t n, float4 *planes,
-                        uint32_t *orig, cudaStream_t st);
+                        uint32_t *orig, cudaStream_t st, bool records_ready = false);
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st);
 void launch_level_boxes(const float4 *clo, const float4 *chi, uint32_t nChild, uint32_t nParent, float4 *plo,
@@ -152,6 +158,7 @@ struct gvpm_ctx {
   void *staging_ptr(int which) const { return which == ph_staging_sel ? ph_staging.p : ph_staging_alt.p; }
   uint32_t n_photons = 0;
   bool photons_loaded = false;
+  bool photons_direct = false;   // gvpm_trace_photons_direct: the 128-byte records in `aos` ARE the photon set (no staging, no packing)
   DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
   Tree tree{};
   float radius = 0.f;
@@ -168,7 +175,11 @@ struct gvpm_ctx {
   int accel = ACCEL_BVH;
   bool force_bvh = false;            // GVPM_ACCEL=bvh: A/B switch for kernel experiments
   FrustumGrid grid{};
-  DevBuf cell_start, grid_occ, pin_scratch, trace_scratch;
+  DevBuf cell_start, grid_occ, pin_scratch, trace_scratch, keepmask;
+  double kept_fraction_hint = 1.0;   // share of the photons the last frustum build kept (sizes the next one's sort)
+  cudaEvent_t ev_hint = nullptr;
+  bool hint_pending = false;
+  uint32_t hint_n = 0;
   double trace_photons_per_path = 0.0;   // running estimate (sizes the first batch of gvpm_trace_photons)    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
   uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
   struct RayFit { bool concurrent = false; float C[3], m[3], u[3], v[3], delta, cosmin, xmin, xmax, ymin, ymax, count; } pin;
@@ -583,6 +594,7 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   memset(ctx->pair_count_host, 0, 48 * sizeof(unsigned long long));
   for (auto &g : ctx->ring) cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming);
   cudaHostAlloc((void **)&ctx->pin_host, 128, cudaHostAllocDefault);
+  cudaEventCreateWithFlags(&ctx->ev_hint, cudaEventDisableTiming);
   { const char *e = getenv("GVPM_ACCEL"); ctx->force_bvh = e && !strcmp(e, "bvh"); }
   cudaHostAlloc((void **)&ctx->sample_stats_host, 64, cudaHostAllocDefault);
   memset(ctx->sample_stats_host, 0, 64);
@@ -604,10 +616,11 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
-                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch};
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask};
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
   if (ctx->pin_host) cudaFreeHost(ctx->pin_host);
+  if (ctx->ev_hint) cudaEventDestroy(ctx->ev_hint);
   for (auto &g : ctx->ring) if (g.done) cudaEventDestroy(g.done);
   for (auto &ps : ctx->push_streams) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
   if (ctx->push_kernel_stream) { cudaStreamSynchronize(ctx->push_kernel_stream); cudaStreamDestroy(ctx->push_kernel_stream); }
@@ -722,6 +735,7 @@ int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   CK(ctx->ph_staging.reserve(L.bytes ? L.bytes : 256));
   ctx->n_photons = (uint32_t)n;
   ctx->photons_loaded = true;
+  ctx->photons_direct = false;
   ctx->built = false;
   ++ctx->state_gen;
   if (dev) *dev = ctx->ph_staging.p;
@@ -974,14 +988,19 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     CK(ctx->orig.reserve(4 * (size_t)n));
     CK(ctx->box_lo.reserve(16 * (size_t)total));
     CK(ctx->box_hi.reserve(16 * (size_t)total));
-    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
-    launch_bounds(S.pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st);
-    launch_morton(S.pos, n, ctx->bounds.as<float>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), st);
+    const bool direct = ctx->photons_direct;
+    PhotonStaging S{};
+    if (!direct) S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    const float *pos = direct ? ctx->aos.as<float>() : S.pos;
+    const uint32_t stride = direct ? 32u : 3u;
+    CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
+    launch_bounds(pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st, stride);
+    launch_morton(pos, n, ctx->bounds.as<float>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), st, stride);
     CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                 ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
-    CK(ctx->aos.reserve(128 * (size_t)n));
+    if (!direct) CK(ctx->aos.reserve(128 * (size_t)n));
     launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
-                       ctx->orig.as<uint32_t>(), st);
+                       ctx->orig.as<uint32_t>(), st, direct);
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
     float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
     launch_leaf_boxes(ctx->planes.as<float4>(), n, T.cnt[0], radius, lo, hi, st);
@@ -1009,6 +1028,11 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
 // Same hierarchy, over the photons the uploaded rays can reach only (tree_build.cu, "ray-region pruning").
 static int build_pruned_bvh(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   cudaSetDevice(ctx->device);
+  if (ctx->photons_direct) {   // records traced in place: no staged SoA to prune from, build over all of them
+    int rc = gvpm_build_points(ctx, radius);
+    if (rc == GVPM_OK) { ctx->pruned = false; if (n_kept) *n_kept = ctx->n_photons; }
+    return rc;
+  }
   const uint32_t n = ctx->n_photons;
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev[0], st));
@@ -1165,7 +1189,15 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   int bits = 1;
   while ((1ull << bits) < (unsigned long long)n_keys) ++bits;
   CK(ctx->cell_start.reserve(((size_t)n_keys + 1) * 4));
+  // how much of the set did the previous build keep?  (read without blocking: sizes this build's sort)
+  if (ctx->hint_pending && cudaEventQuery(ctx->ev_hint) == cudaSuccess) {
+    ctx->hint_pending = false;
+    const uint32_t keptPrev = *(const uint32_t *)(ctx->pin_host + 30);
+    if (ctx->hint_n) ctx->kept_fraction_hint = (double)keptPrev / (double)ctx->hint_n;
+  }
+  uint32_t m = n;   // sorted entries
   if (n > 0) {
+    const uint32_t nb = (n + 255) / 256;
     CK(ctx->keys_in.reserve(8 * (size_t)n));
     CK(ctx->keys_out.reserve(8 * (size_t)n));
     CK(ctx->vals_in.reserve(4 * (size_t)n));
@@ -1173,26 +1205,62 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
     CK(ctx->planes.reserve(16 * (size_t)n));
     CK(ctx->orig.reserve(4 * (size_t)n));
-    CK(ctx->aos.reserve(128 * (size_t)n));
+    CK(ctx->keepmask.reserve(4 * ((size_t)n / 32 + 1) + 4 * ((size_t)nb + 2)));
+    const bool direct = ctx->photons_direct;
+    if (!direct) CK(ctx->aos.reserve(128 * (size_t)n));
     CK(ctx->grid_occ.reserve(frustum_occ_bytes() + cell_starts_scratch_bytes(n_keys)));
-    PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
-    launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, S.pos, S.path_id, n, G, ctx->grid_occ.as<uint32_t>(),
-                        ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, ctx->sm_count, st);
-    CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
-                     ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, bits, st));
-    launch_cell_starts(ctx->keys_out.as<uint32_t>(), n, n_keys, ctx->cell_start.as<uint32_t>(),
+    uint32_t *keepmask = ctx->keepmask.as<uint32_t>(), *block_kept = keepmask + (n / 32 + 1);
+    PhotonStaging S{};
+    if (!direct) S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    if (direct)   // position = first three floats of the record, path parity = bit 10 of its meta word
+      launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, ctx->aos.as<float>(), 32u, ctx->aos.as<uint32_t>() + 3, 32u, 10u, n,
+                          G, ctx->grid_occ.as<uint32_t>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(),
+                          ctx->bounds.as<unsigned>() + 6, keepmask, block_kept, ctx->sm_count, st);
+    else
+      launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, S.pos, 3u, S.path_id, 1u, 0u, n, G, ctx->grid_occ.as<uint32_t>(),
+                          ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, keepmask,
+                          block_kept, ctx->sm_count, st);
+    const uint32_t *sortedKeys, *sortedVals;
+    if (ctx->kept_fraction_hint < 0.5) {
+      // sharded image: most photons are out of this rank's reach.  Compact the kept (key, index) pairs in index order
+      // (deterministic) and sort those only; their number sizes the sort, hence one 4-byte read-back.
+      launch_scan_u32(block_kept, nb, block_kept + nb, st);
+      launch_compact_kept(ctx->keys_in.as<uint32_t>(), keepmask, block_kept, n, ctx->keys_out.as<uint32_t>(),
+                          ctx->vals_out.as<uint32_t>(), st);
+      CK(cudaMemcpyAsync(ctx->pair_count_host, block_kept + nb, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      m = *(const uint32_t *)ctx->pair_count_host;
+      ctx->kept_fraction_hint = (double)m / (double)n;
+      if (m) CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_out.as<uint32_t>(), ctx->keys_in.as<uint32_t>(),
+                              ctx->vals_out.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), m, bits, st));
+      sortedKeys = ctx->keys_in.as<uint32_t>();
+      sortedVals = ctx->vals_in.as<uint32_t>();
+      ctx->launches += 2;
+    } else {
+      CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
+                       ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, bits, st));
+      sortedKeys = ctx->keys_out.as<uint32_t>();
+      sortedVals = ctx->vals_out.as<uint32_t>();
+    }
+    launch_cell_starts(sortedKeys, m, n_keys, ctx->cell_start.as<uint32_t>(),
                        ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
-    launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
-                       ctx->orig.as<uint32_t>(), st);
+    launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->aos.as<float4>(), ctx->planes.as<float4>(),
+                            ctx->orig.as<uint32_t>(), st, direct);
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
-    ctx->launches += 8 + 4;
+    if (m == n) {   // kept count of this build -> hint of the next one (no blocking)
+      CK(cudaMemcpyAsync(ctx->pin_host + 30, ctx->cell_start.as<uint32_t>() + n_keys - 1, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(ctx->ev_hint, st));
+      ctx->hint_pending = true;
+      ctx->hint_n = n;
+    }
+    ctx->launches += 9 + 4;
     CK(cudaGetLastError());
   } else {
     CK(cudaMemsetAsync(ctx->bounds.p, 0, 7 * sizeof(float), st));
     CK(cudaMemsetAsync(ctx->cell_start.p, 0, ((size_t)n_keys + 1) * 4, st));
   }
   Tree T{};
-  T.n = n;
+  T.n = m;
   ctx->tree = T;
   ctx->grid = G;
   ctx->radius = radius;
@@ -1286,24 +1354,58 @@ int gvpm_generate_rays(gvpm_ctx *ctx, const gvpm_box_scene *scene, const gvpm_pi
     ctx->launches += 1;
     CK(cudaGetLastError());
   }
-  return gvpm_commit_rays(ctx);
+  rc = gvpm_commit_rays(ctx);
+  if (rc) return rc;
+  // The rays of a pinhole are concurrent by construction: what analyse_rays would measure on the device (and read back)
+  // follows from the camera.  Every ray is pos + t * dir up to the rounding of the entry point (a few ulp of the
+  // coordinates, bounded here by 4e-6 * (1 + |pos|)); projected directions span [-tx, tx] x rows [y0, y1).
+  {
+    gvpm_ctx::RayFit &F = ctx->pin;
+    const float tx = cam->tan_half_fov_x, ty = tx * (float)cam->film_h / (float)cam->film_w;
+    for (int k = 0; k < 3; ++k) { F.C[k] = cam->pos[k]; F.m[k] = F.u[k] = F.v[k] = 0.f; }
+    F.m[2] = 1.f; F.u[0] = 1.f; F.v[1] = 1.f;
+    F.xmin = -tx * 1.0001f; F.xmax = tx * 1.0001f;
+    F.ymin = ((float)y0 / (float)cam->film_h - 0.5f) * 2.f * ty;
+    F.ymax = ((float)y1 / (float)cam->film_h - 0.5f) * 2.f * ty;
+    const float ypad = 1e-4f * ty + 1e-7f;
+    F.ymin -= ypad; F.ymax += ypad;
+    const float amax = std::max(std::fabs(cam->pos[0]), std::max(std::fabs(cam->pos[1]), std::fabs(cam->pos[2])));
+    F.delta = 4e-6f * (1.f + amax);
+    F.cosmin = 1.f / std::sqrt(1.f + tx * tx + ty * ty);
+    F.count = (float)n;
+    F.concurrent = n > 0 && F.cosmin > 0.35f;
+    ctx->pin_gen = ctx->rays_gen;
+  }
+  return GVPM_OK;
 }
 
-int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
-                       int min_depth, uint64_t *n_paths) {
+static int trace_impl(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
+                      int min_depth, uint64_t *n_paths, bool direct) {
   if (!ctx || !scene || n > 0xfffffff0u) return GVPM_ERR_INVALID;
   if (!ctx->have_medium) return fail(ctx, GVPM_ERR_INVALID, "gvpm_set_medium first");
   cudaSetDevice(ctx->device);
   int rc = check_scene(ctx, scene);
   if (rc) return rc;
   void *dev = nullptr;
-  rc = gvpm_photon_staging(ctx, n, &dev, nullptr);
-  if (rc) return rc;
+  PhotonStaging S{};
+  if (direct) {
+    // no staging: the records are written where the gather reads them
+    CK(ctx->aos.reserve(128 * std::max<size_t>(n, 1)));
+    ctx->n_photons = (uint32_t)n;
+    ctx->photons_loaded = true;
+    ctx->photons_direct = true;
+    ctx->built = false;
+    ++ctx->state_gen;
+  } else {
+    rc = gvpm_photon_staging(ctx, n, &dev, nullptr);
+    if (rc) return rc;
+    S = photon_staging_ptrs(dev, n);
+  }
   if (n_paths) *n_paths = 0;
   if (n == 0) return GVPM_OK;
   cudaStream_t st = ctx->stream;
-  PhotonStaging S = photon_staging_ptrs(dev, n);
   TraceParams P{};
+  P.aos = direct ? ctx->aos.as<float4>() : nullptr;
   P.scene = *scene;
   P.sigma_s = ctx->medium.sigma_s[0];
   P.sigma_a = ctx->medium.sigma_a[0];
@@ -1352,6 +1454,15 @@ int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uin
   }
   if (n_paths) *n_paths = host[1];
   return GVPM_OK;
+}
+
+int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
+                       int min_depth, uint64_t *n_paths) {
+  return trace_impl(ctx, scene, n, seed, max_depth, rr_depth, min_depth, n_paths, false);
+}
+int gvpm_trace_photons_direct(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth,
+                              int rr_depth, int min_depth, uint64_t *n_paths) {
+  return trace_impl(ctx, scene, n, seed, max_depth, rr_depth, min_depth, n_paths, true);
 }
 
 int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes) {
@@ -1441,7 +1552,8 @@ int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
   cudaSetDevice(ctx->device);
   int rc = pending_check(ctx, true);
   if (rc) return rc;
-  rc = gather_common(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host);
+  uint32_t *cdev = counts ? ctx->counts.as<uint32_t>() : nullptr;   // no counts wanted: the traversal filters before queueing
+  rc = gather_common(ctx, ctx->out.as<float>(), cdev, ctx->pair_count_host);
   if (rc) return rc;
   const size_t n = ctx->n_rays;
   for (int pass = 0; pass < 2; ++pass) {   // second pass only if the pair list overflowed and the gather was re-run
@@ -1451,7 +1563,7 @@ int gvpm_gather_bre(gvpm_ctx *ctx, float *out, uint32_t *counts) {
         CK(cudaMemcpyAsync(counts, ctx->counts.p, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     bool redone = false;
-    if (pass == 0) rc = gather_finish(ctx, ctx->out.as<float>(), ctx->counts.as<uint32_t>(), ctx->pair_count_host, &redone);
+    if (pass == 0) rc = gather_finish(ctx, ctx->out.as<float>(), cdev, ctx->pair_count_host, &redone);
     else CK(cudaStreamSynchronize(ctx->stream));
     if (rc) return rc;
     if (!redone) break;

@@ -239,6 +239,7 @@ struct TraceParams {
   float *pos, *flux, *parent_pos, *pred_pos, *parent_n, *prefix_flux, *parent_albedo, *parent_pdf, *edge_pdf, *rr_weight;
   uint8_t *parent_type, *depth;
   uint32_t *path_id;
+  float4 *aos;                  // not null: write 128-byte gather records (layout above) instead of the staging arrays
 };
 // ---- strictly rounded double (the reference's fp64 island: cylinderIntersection / solveQuadraticDouble,
 // photonmapper/beams_3d_intersections.h:100-137, src/libcore/util.cpp:487-525) ----------------------------

@@ -220,6 +220,8 @@ void launch_sub_count(const float *len, uint32_t n, const float *subsize, uint32
   if (n) k_sub_count<<<nb, 256, 0, st>>>(len, n, subsize, block_tot);
   k_sub_scan<<<1, 1024, 0, st>>>(block_tot, n ? nb : 0u, total);
 }
+// in-place exclusive scan of nb words by one block (a few thousand entries); total -> total[0]
+void launch_scan_u32(uint32_t *vals, uint32_t nb, uint32_t *total, cudaStream_t st) { k_sub_scan<<<1, 1024, 0, st>>>(vals, nb, total); }
 void launch_sub_emit(const float4 *rec, const float *len, uint32_t n, const float *subsize, const uint32_t *block_off,
                      uint32_t cap, float *sub_pos, float4 *sub_raw, cudaStream_t st) {
   if (n) k_sub_emit<<<(n + 255) / 256, 256, 0, st>>>(rec, len, n, subsize, block_off, cap, sub_pos, sub_raw);

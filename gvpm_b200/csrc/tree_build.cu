@@ -15,12 +15,12 @@
 namespace gvpm {
 
 // ---- bounds: per-block partial min/max of n points, then one block folds the partials -----
-__global__ void k_bounds_partial(const float *__restrict__ pos, uint32_t n, float *__restrict__ partial) {
+__global__ void k_bounds_partial(const float *__restrict__ pos, uint32_t stride, uint32_t n, float *__restrict__ partial) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      float v = pos[3 * (size_t)i + a];
+      float v = pos[(size_t)stride * i + a];
       lo[a] = fminf(lo[a], v);
       hi[a] = fmaxf(hi[a], v);
     }
@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t hilbert30(uint32_t x0, uint32_t x1, uint32_t
   return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
 }
 
-__global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float *__restrict__ bounds,
+__global__ void k_morton(const float *__restrict__ pos, uint32_t stride, uint32_t n, const float *__restrict__ bounds,
                          uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -123,7 +123,7 @@ __global__ void k_morton(const float *__restrict__ pos, uint32_t n, const float 
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const float lo = bounds[a], ext = bounds[3 + a] - lo;
-    float u = ext > 0.f ? (pos[3 * (size_t)i + a] - lo) / ext : 0.f;
+    float u = ext > 0.f ? (pos[(size_t)stride * i + a] - lo) / ext : 0.f;
     u = fminf(fmaxf(u, 0.f), 1.f);
     q[a] = min((uint32_t)(u * 1024.f), 1023u);
   }
@@ -602,14 +602,17 @@ __global__ void __launch_bounds__(256) k_frustum_mark(const float4 *__restrict__
 }
 // per photon: footprint class, cell, key (see FrustumGrid).  vals = photon index.  coord_mag: atomicMax of the largest
 // |coordinate| (float bits; the traversal's rounding pad).
-__global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ pos, const uint32_t *__restrict__ path_id,
+__global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ pos, uint32_t stride,
+                                                       const uint32_t *__restrict__ par_src, uint32_t par_stride, uint32_t par_shift,
                                                        uint32_t n, const FrustumGrid G, const uint32_t *__restrict__ occ,
                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                                                       unsigned *__restrict__ coord_mag) {
+                                                       unsigned *__restrict__ coord_mag, uint32_t *__restrict__ keepmask,
+                                                       uint32_t *__restrict__ block_kept) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float mag = 0.f;
+  bool keep = false;
   if (i < n) {
-    const float px = pos[3 * (size_t)i], py = pos[3 * (size_t)i + 1], pz = pos[3 * (size_t)i + 2];
+    const float px = pos[(size_t)stride * i], py = pos[(size_t)stride * i + 1], pz = pos[(size_t)stride * i + 2];
     mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
     const float qx = px - G.C[0], qy = py - G.C[1], qz = pz - G.C[2];
     const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
                 const uint32_t bits = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
                 any = any || (__ldg(occ + yy * (kOccRes / 32) + w0) & bits) != 0u;
               }
-            const uint32_t par = G.parity_split ? (__ldg(path_id + i) & 1u) : 0u;
+            const uint32_t par = G.parity_split ? ((__ldg(par_src + (size_t)par_stride * i) >> par_shift) & 1u) : 0u;
             key = any ? par * G.n_cells + G.base[c] + (uint32_t)cy * (uint32_t)nx + (uint32_t)cx : DROP;
           }
         }
@@ -663,9 +666,45 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
     }
     keys[i] = key;
     vals[i] = i;
+    keep = key != DROP;
   }
+  // one keep bit per photon (word = 32 consecutive photons) and the CTA's number of kept photons: the record packing and
+  // the compaction in front of the sort (sharded images keep a small part of the set) read them
+  __shared__ uint32_t wkept[8];
+  const uint32_t km = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0) {
+    if (i < n) keepmask[i >> 5] = km;
+    wkept[threadIdx.x >> 5] = __popc(km);
+  }
+  // one atomic per CTA, and only while the CTA's maximum beats what is already there (a single hot address otherwise
+  // serialises hundreds of thousands of atomics)
+  __shared__ float wmag[8];
   for (int o = 16; o > 0; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
-  if ((threadIdx.x & 31) == 0 && mag > 0.f) atomicMax(coord_mag, __float_as_uint(mag));
+  if ((threadIdx.x & 31) == 0) wmag[threadIdx.x >> 5] = mag;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    uint32_t tot = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { m = fmaxf(m, wmag[k]); tot += wkept[k]; }
+    block_kept[blockIdx.x] = tot;
+    if (m > __uint_as_float(*(volatile unsigned *)coord_mag)) atomicMax(coord_mag, __float_as_uint(m));
+  }
+}
+// (key, index) of the kept photons, in index order, packed to the front: block_off = exclusive scan of block_kept
+__global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ keepmask,
+                                                       const uint32_t *__restrict__ block_off, uint32_t n,
+                                                       uint32_t *__restrict__ keys_c, uint32_t *__restrict__ vals_c) {
+  __shared__ uint32_t wcnt[8];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t km = i < n ? __ldg(keepmask + (i >> 5)) : 0u;   // i and its warp share the word (blockDim = 256, aligned)
+  if (lane == 0) wcnt[w] = __popc(km);
+  __syncthreads();
+  if (!(km >> lane & 1u)) return;
+  uint32_t pos = block_off[blockIdx.x] + __popc(km & ((1u << lane) - 1u));
+  for (int k = 0; k < w; ++k) pos += wcnt[k];
+  keys_c[pos] = keys[i];
+  vals_c[pos] = i;
 }
 // cell_start[k] = first sorted slot whose key is >= k, for k in [0, n_keys].  Lane i owns the gap of keys in front of
 // slot i; the warp fills its lanes' gaps one after the other with all 32 lanes writing (coalesced).  Gaps of 4096 cells
@@ -749,18 +788,18 @@ int bounds_blocks(uint32_t n) {
   return b < 1 ? 1 : (b > 1024 ? 1024 : b);
 }
 
-void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st) {
+void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, cudaStream_t st, uint32_t stride) {
   const int nb = bounds_blocks(n);
-  k_bounds_partial<<<nb, 256, 0, st>>>(pos, n, partial);
+  k_bounds_partial<<<nb, 256, 0, st>>>(pos, stride, n, partial);
   k_bounds_final<<<1, 32, 0, st>>>(partial, nb, bounds);
 }
 void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
-                   cudaStream_t st) {
-  k_morton<<<(n + 255) / 256, 256, 0, st>>>(pos, n, bounds, keys, vals);
+                   cudaStream_t st, uint32_t stride) {
+  k_morton<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, n, bounds, keys, vals);
 }
 void launch_pack_sorted(const PhotonStaging &S, float4 *aos, const uint32_t *sorted, uint32_t n, float4 *planes,
-                        uint32_t *orig, cudaStream_t st) {
-  k_pack_aos<<<(n + 255) / 256, 256, 0, st>>>(S, n, aos);
+                        uint32_t *orig, cudaStream_t st, bool records_ready) {
+  if (!records_ready) k_pack_aos<<<(n + 255) / 256, 256, 0, st>>>(S, n, aos);
   k_gather_sorted<<<(n + 255) / 256, 256, 0, st>>>(aos, sorted, n, planes, orig);
 }
 size_t ray_grid_bytes() { return sizeof(RayGrid); }
@@ -801,14 +840,24 @@ void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *
   k_pinhole_check<<<nb, 256, 0, st>>>(rays, n, fit, stats);
 }
 size_t frustum_occ_bytes() { return (size_t)kOccWords * 4; }
+void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
+                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st) {
+  if (n) k_compact_kept<<<(n + 255) / 256, 256, 0, st>>>(keys, keepmask, block_off, n, keys_c, vals_c);
+}
+// records of the kept photons only (keepmask), then the sorted position plane / index map of the first m sorted slots
+void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
+                             float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st, bool records_ready);
 // occ: frustum_occ_bytes() (zeroed here); coord_mag: one word (zeroed here)
-void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, const uint32_t *path_id, uint32_t n,
+// pos / stride: photon positions (stride in floats: 3 for the staged SoA plane, 32 for 128-byte records); parity of the
+// photon's path id = (par_src[par_stride * i] >> par_shift) & 1
+void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, uint32_t stride, const uint32_t *par_src,
+                         uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
-                         int sm_count, cudaStream_t st) {
+                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st) {
   cudaMemsetAsync(occ, 0, frustum_occ_bytes(), st);
   cudaMemsetAsync(coord_mag, 0, 4, st);
   if (n_rays) k_frustum_mark<<<std::min<uint32_t>((n_rays + 255) / 256, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, n_rays, G, occ);
-  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, path_id, n, G, occ, keys, vals, coord_mag);
+  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, par_src, par_stride, par_shift, n, G, occ, keys, vals, coord_mag, keepmask, block_kept);
 }
 // scratch: cell_starts_scratch_bytes(n_keys) bytes
 size_t cell_starts_scratch_bytes(uint32_t n_keys) { return 16 + ((size_t)n_keys / 4096 + 2) * sizeof(BigGap); }
@@ -824,6 +873,11 @@ void launch_cell_starts(const uint32_t *sorted_keys, uint32_t n, uint32_t n_keys
 cudaError_t run_sort_bits(void *temp, size_t temp_bytes, const uint32_t *kin, uint32_t *kout, const uint32_t *vin,
                           uint32_t *vout, uint32_t n, int bits, cudaStream_t st) {
   return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, (int)n, 0, bits, st);
+}
+void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
+                             float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st, bool records_ready) {
+  if (!records_ready && n) k_pack_aos_kept<<<(n + 255) / 256, 256, 0, st>>>(S, n, keepmask, aos);
+  if (m) k_gather_sorted<<<(m + 255) / 256, 256, 0, st>>>(aos, sorted, m, planes, orig);
 }
 void launch_leaf_boxes(const float4 *p0, uint32_t n, uint32_t nLeaves, float radius, float4 *lo, float4 *hi,
                        cudaStream_t st) {

@@ -480,6 +480,12 @@ int gvpm_generate_rays(gvpm_ctx *ctx, const gvpm_box_scene *scene, const gvpm_pi
  * including the one that completed the set (nbPathVolume, the gather's normalisation). */
 int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth, int rr_depth,
                        int min_depth, uint64_t *n_paths);
+/* Same photons, written straight into the 128-byte records the gather reads (no staging buffer, no packing pass in the
+ * build): the layout a renderer that lives on the device would produce.  gvpm_build_points / gvpm_build_points_for_rays
+ * and the BRE / VPM gathers work on them as on uploaded photons, with identical results; the staging-based entry points
+ * (gvpm_photon_staging, peer exchange) do not see them. */
+int gvpm_trace_photons_direct(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth,
+                              int rr_depth, int min_depth, uint64_t *n_paths);
 /* parity aid: copy `bytes` bytes at `dev` (a pointer handed out by this library, e.g. gvpm_photon_staging /
  * gvpm_ray_staging) to host memory, after the work queued on the context's stream */
 int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes);

@@ -98,3 +98,25 @@ def test_vpm_after_frustum_build_rebuilds_the_hierarchy(built):
     np.testing.assert_array_equal(sc, ref.sample_counts)
     H.assert_radiance_close(out, ref.out, 1e-4, "vpm after frustum")
     ctx.close()
+
+
+def test_second_sharded_build_compacts_before_the_sort(built):
+    """the first build of a sharded ray set reports how few photons it kept; the next one compacts the kept (key, index)
+    pairs before sorting (kept-count read-back): same counts, same radiance"""
+    from oracle import binding as ob
+    case = H.make_case(n_photons=80000, w=64, h=64, scale=0.5)
+    idx = shard.band_indices(case.rays.px, case.rays.py, 64, 64, 8, 3, 1)
+    case.rays = case.rays.take(idx)
+    ref = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius, mode="brute")
+    ctx = H.gpu_context(case)
+    outs = []
+    for it in range(3):
+        ctx.upload_photons(case.photons)          # a new iteration's photons
+        kept = ctx.build_points_for_rays(case.radius)
+        assert ctx.accel_kind() == "frustum" and 0 < kept < 0.5 * case.photons.n
+        out, counts = ctx.gather_bre()
+        np.testing.assert_array_equal(counts, ref.counts)
+        H.assert_radiance_close(out, ref.out, 1e-4, f"sharded build {it}")
+        outs.append(kept)
+    assert outs[0] == outs[1] == outs[2]
+    ctx.close()

@@ -109,3 +109,32 @@ def test_gather_on_device_made_inputs(built):
     assert counts[:, 0].sum() > 2000 and paths > 0
     H.assert_radiance_close(out, ref.out, 1e-4, "gather on device-made inputs")
     ctx.close()
+
+
+@pytest.mark.parametrize("build", ["frustum", "bvh"])
+def test_direct_records_give_the_same_gather(built, build):
+    """gvpm_trace_photons_direct writes the gather's 128-byte records in place: same neighbour counts and the same
+    radiance as the staged photons packed by the build"""
+    w, h, n = 64, 48, 50000
+    med, cfg = g.make_medium(), g.make_config(w, h)
+    scene, cam = g.box_scene_default(), g.pinhole_camera(w, h)
+    radius = g.bre_radius(2.0)
+    res = []
+    for direct in (False, True):
+        ctx = _ctx(med, cfg)
+        ctx.trace_photons(scene, n, 77, direct=direct)
+        ctx.generate_rays(scene, cam, 78)
+        if build == "frustum":
+            ctx.build_points_for_rays(radius, want_kept=False)
+        else:
+            ctx.build_points(radius)
+        assert ctx.accel_kind() == build
+        out, counts = ctx.gather_bre()
+        out2, _ = ctx.gather_bre(counts=False)
+        res.append((out.copy(), counts.copy(), out2.copy()))
+        ctx.close()
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    # (a ray's partial sums are added with float atomics in whatever order the warps retire: equal up to rounding)
+    H.assert_radiance_close(res[1][0], res[0][0], 1e-5, "gather on direct records")
+    H.assert_radiance_close(res[1][2], res[0][0], 1e-5, "prefiltered gather on direct records")
+    assert res[0][1][:, 0].sum() > 2000
