@@ -853,6 +853,35 @@ def main():
         if not inplace_ok:
             slice_dev = [mine.clone() for _, mine in views[0]]
     ready = [None, None]   # per staging buffer: what the compute stream must wait for before building from it
+    # Value leg, N > 1: photon DISPATCH (gvpm_dispatch_*): every rank classifies its resident slice against every
+    # receiver's perspective grid and writes the records a receiver can reach into that receiver's inbox (one fused
+    # pack + exchange kernel over the peer mappings); a rank builds over what it was sent.  GVPM_VALUE_EXCHANGE=allgather
+    # keeps the whole-set exchange above for the value leg too.
+    dispatching = world > 1 and os.environ.get("GVPM_VALUE_EXCHANGE", "dispatch") == "dispatch" and prune_build(world) \
+        and os.environ.get("GVPM_ACCEL", "") != "bvh"
+    if dispatching:
+        okd = torch.ones(1, device="cuda", dtype=torch.int32)
+        dblob = None
+        try:
+            dblob = ctx.dispatch_export(world, n_slice)
+        except Exception as e:  # noqa: BLE001 - e.g. rays that are not concurrent: every rank falls back together
+            print(f"[rank {rank}] photon dispatch unavailable ({e}); the value leg all-gathers the set", file=sys.stderr)
+            okd.zero_()
+        dist.all_reduce(okd, op=dist.ReduceOp.MIN)
+        dispatching = int(okd.item()) == 1
+        if dispatching:
+            from gvpm_b200 import _native as NAT
+            mine = torch.frombuffer(bytearray(dblob), dtype=torch.uint8).cuda()
+            allb = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allb, mine)
+            try:
+                ctx.dispatch_connect([bytes(b.cpu().numpy().tobytes()) for b in allb], rank)
+            except Exception as e:  # noqa: BLE001
+                print(f"[rank {rank}] photon dispatch unavailable ({e}); the value leg all-gathers the set", file=sys.stderr)
+                okd.zero_()
+            dist.all_reduce(okd, op=dist.ReduceOp.MIN)
+            dispatching = int(okd.item()) == 1
+    disp_primed = [False]
 
     def host_barrier():
         if host_pg is not None:
@@ -938,8 +967,30 @@ def main():
         else:
             ctx.build_points(inp["radius"])
 
+    disp_next = [0]     # inbox generations run on across the timed loop and the diagnostics below
+
+    def step_dispatch(k=None, gather_results=True):
+        """value leg, N > 1: (dispatch of step k+1's photons in flight) + build over the inbox + gather + result gather"""
+        k = disp_next[0]
+        disp_next[0] += 1
+        b = k & 1
+        # step k+1's photons go out while step k is built and gathered (the slice is resident and never changes: no
+        # dependency on the compute stream; the senders wait for the receivers' release of that inbox on the device)
+        ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)
+        if coll_done[b] is not None:            # the result buffer of step k - 2 has been gathered
+            stream.wait_event(coll_done[b])
+            coll_done[b] = None
+        with torch.cuda.stream(stream):
+            ctx.build_dispatched(b, inp["radius"])
+            ctx.gather_bre_into(out_bufs[b].data_ptr(), None)
+            ctx.dispatch_release(b)
+            if gather_results:
+                collect(k)
+
     def step_resident(k):
         """value leg: (photon all-gather of step k+1 in flight) + build + gather (+ result gather)"""
+        if dispatching:
+            return step_dispatch(k)
         b = k & 1
         wait_ready(b)
         if world > 1:
@@ -972,7 +1023,12 @@ def main():
         host_barrier()
 
     def timed(fn, steps, warmup, from_host):
-        if world > 1 or from_host:
+        disp = dispatching and fn is step_resident
+        if disp:
+            assert not disp_primed[0], "one dispatched run per process (inbox generations)"
+            disp_primed[0] = True
+            ctx.dispatch_photons(0, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)   # step 0 (untimed priming)
+        elif world > 1 or from_host:
             prefetch(0, from_host)              # step 0's photon set (untimed priming)
             host_barrier()
         for k in range(warmup):
@@ -988,7 +1044,10 @@ def main():
         e0.record(stream)
         for k in range(warmup, warmup + steps):
             fn(k)
-        wait_ready((warmup + steps) & 1)        # the K-th exchange issued inside the timed region ends inside it
+        if disp:
+            ctx.dispatch_join()                 # the K-th dispatch issued inside the timed region ends inside it
+        else:
+            wait_ready((warmup + steps) & 1)    # the K-th exchange issued inside the timed region ends inside it
         wait_collects()                         # ... and so do the result gathers
         e1.record(stream)
         ctx.sync()
@@ -1051,6 +1110,10 @@ def main():
     ctx.photon_staging(n_ph)
 
     def step_plain():
+        if dispatching:
+            wait_collects()
+            step_dispatch(gather_results=False)
+            return
         with torch.cuda.stream(stream):
             build_resident()
             ctx.gather_bre_into(out_dev.data_ptr(), None)
@@ -1065,7 +1128,9 @@ def main():
     gather_ms = float(np.mean([k[1] for k in kt]))
     build_ms = float(np.mean([k[0] for k in kt]))
     accel = ctx.accel_kind()
-    if prune_build(world):
+    if dispatching:
+        kept[0] = sum(ctx.dispatch_status((disp_next[0] - 1) & 1))   # records received for the last build (synchronises)
+    elif prune_build(world):
         with torch.cuda.stream(stream):
             kept[0] = ctx.build_points_for_rays(inp["radius"], want_kept=True)
     trav_ms, shade_ms, n_pairs = float(np.mean([k[0] for k in kd])), float(np.mean([k[1] for k in kd])), kd[-1][2]
@@ -1131,6 +1196,10 @@ def main():
                                      "bytes (profiles/), the HBM fraction is reported as the contract asks"},
                 "phases_ms": {"build": build_ms, "gather": float(gk.item()), "traverse": trav_ms,
                               "shade": shade_ms},
+                "value_exchange": ("photon dispatch: each rank classifies its resident slice against every receiver's perspective grid and "
+                                   "writes the 128-byte records a receiver can reach into that receiver's inbox over NVLink "
+                                   "(gvpm_dispatch_*), double-buffered, device-side generation flags" if dispatching else
+                                   ("whole-set exchange (see photon_exchange)" if world > 1 else "single GPU")),
                 "shards": {"mode": shard_mode(world), "band_cycles": band_cycles() if shard_mode(world) == "band" else None,
                            "pruned_build": prune_build(world), "accel": accel,
                            "rays_per_rank": [int(k[1].item()) for k in kept_all],

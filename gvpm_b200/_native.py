@@ -14,6 +14,8 @@ SYNTH_LIB_PATH = os.path.join(_HERE, "synth", "libgvpm_synth.so")
 
 GVPM_OUT_FLOATS = 27
 GVPM_PEER_BLOB_BYTES = 384
+GVPM_DISPATCH_BLOB_BYTES = 512
+GVPM_MAX_PEERS = 8
 PARENT_EMITTER, PARENT_SURFACE, PARENT_MEDIUM, PARENT_OTHER = 0, 1, 2, 3
 PHASE_ISOTROPIC, PHASE_HG = 0, 1
 SURF2MEDIA, MEDIA2MEDIA = 1 << 2, 1 << 4
@@ -102,6 +104,8 @@ ABI_SYMBOLS = [
     "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays", "gvpm_accel_kind",
     "gvpm_photon_staging_select", "gvpm_photon_staging_layout", "gvpm_upload_photons_slice",
     "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons", "gvpm_peer_push_mode",
+    "gvpm_dispatch_export", "gvpm_dispatch_connect", "gvpm_dispatch_photons", "gvpm_build_dispatched", "gvpm_dispatch_release",
+    "gvpm_dispatch_status", "gvpm_dispatch_join",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_reconstruct", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
@@ -158,6 +162,13 @@ def load_lib():
     lib.gvpm_peer_push_photon_slice.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gvpm_peer_wait_photons.argtypes = [vp, C.c_int]
     lib.gvpm_peer_push_mode.argtypes = [vp, C.c_int]
+    lib.gvpm_dispatch_export.argtypes = [vp, C.c_int, C.c_size_t, vp]
+    lib.gvpm_dispatch_connect.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.gvpm_dispatch_photons.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, vp]
+    lib.gvpm_build_dispatched.argtypes = [vp, C.c_int, C.c_float, u32p]
+    lib.gvpm_dispatch_release.argtypes = [vp, C.c_int]
+    lib.gvpm_dispatch_status.argtypes = [vp, u32p, C.c_int]
+    lib.gvpm_dispatch_join.argtypes = [vp]
     lib.gvpm_upload_rays.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t]
     lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_commit_rays.argtypes = [vp]

@@ -107,6 +107,40 @@ class Context:
         """sm_ctas > 0: push kernel of that many CTAs (stores through the peer mappings); 0: copy engines."""
         self._ck(self.lib.gvpm_peer_push_mode(self.h, int(sm_ctas)), "gvpm_peer_push_mode")
 
+    # ---- photon dispatch between ranks (gvpm_dispatch_*) ----
+    def dispatch_export(self, n_peers, region_cap):
+        """-> bytes: this context's dispatch blob (inboxes, control block, ray fit); needs this rank's rays uploaded."""
+        buf = (C.c_ubyte * N.GVPM_DISPATCH_BLOB_BYTES)()
+        self._ck(self.lib.gvpm_dispatch_export(self.h, int(n_peers), int(region_cap), buf), "gvpm_dispatch_export")
+        return bytes(buf)
+
+    def dispatch_connect(self, blobs, self_index):
+        raw = b"".join(blobs)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.lib.gvpm_dispatch_connect(self.h, buf, len(blobs), self_index), "gvpm_dispatch_connect")
+
+    def dispatch_photons(self, which, n_total, begin, count, radius, after_stream=None):
+        self._ck(self.lib.gvpm_dispatch_photons(self.h, which, n_total, begin, count, C.c_float(radius), after_stream),
+                 "gvpm_dispatch_photons")
+
+    def build_dispatched(self, which, radius, want_kept=False):
+        kept = C.c_uint32(0)
+        self._ck(self.lib.gvpm_build_dispatched(self.h, which, C.c_float(radius), C.byref(kept) if want_kept else None),
+                 "gvpm_build_dispatched")
+        return int(kept.value) if want_kept else None
+
+    def dispatch_release(self, which):
+        self._ck(self.lib.gvpm_dispatch_release(self.h, which), "gvpm_dispatch_release")
+
+    def dispatch_join(self):
+        self._ck(self.lib.gvpm_dispatch_join(self.h), "gvpm_dispatch_join")
+
+    def dispatch_status(self, which):
+        """synchronises; -> records received per sender for inbox `which` (raises on a protocol failure)"""
+        counts = (C.c_uint32 * N.GVPM_MAX_PEERS)()
+        self._ck(self.lib.gvpm_dispatch_status(self.h, counts, which), "gvpm_dispatch_status")
+        return [int(c) for c in counts]
+
     def build_points(self, radius):
         self._ck(self.lib.gvpm_build_points(self.h, C.c_float(radius)), "gvpm_build_points")
 

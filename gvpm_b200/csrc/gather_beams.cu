@@ -250,30 +250,83 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
   }
 }
 
+// Only ~40 % of the candidate pairs own a valid kernel record (the traversal tests the supporting LINES), so a kernel
+// that runs the functor under `if (valid)` keeps 9 of 32 lanes busy (ncu: profiles/r2_beams.md).  Two phases per warp
+// instead: phase 1, lane = candidate pair, evaluates the kernel record (fp64 cylinder island), the ownership rule and
+// the filters with full lanes and appends the survivors to a per-warp ring in shared memory, in pair order; whenever
+// the ring holds 32 survivors, phase 2 runs the functor (4 offsets, reconnections, shadow rays) for them with all
+// lanes, then the segmented warp scan by ray and the float atomics.  Pair order is preserved, so a ray's survivors
+// still form runs.
+constexpr int kBeamRing = 64;
+struct BeamShadeShared {
+  uint32_t ray[kBeamRing], beam[kBeamRing];
+  float f[9][kBeamRing];   // v, w, pdfKernel, pdfEdgeFailure, weightKernel, u, contrib.xyz
+};
+
+__device__ __forceinline__ void beam_shade_batch(const GatherParams &P, const BeamShadeShared &Q, uint32_t head, uint32_t cnt,
+                                                 int lane) {
+  float a[GVPM_OUT_FLOATS];
+#pragma unroll
+  for (int j = 0; j < GVPM_OUT_FLOATS; ++j) a[j] = 0.f;
+  const bool valid = (uint32_t)lane < cnt;
+  uint32_t key = 0xffffffffu;
+  if (valid) {
+    const uint32_t e = (head + lane) & (kBeamRing - 1);
+    key = Q.ray[e];
+    const float4 *rec = P.rays + (size_t)key * GVPM_RAY_FLOAT4;
+    const BaseRay R = load_base_ray(rec);
+    const BeamRec beam = load_beam(P, Q.beam[e]);
+    BeamKernelRec kRec;
+    kRec.v = sf(Q.f[0][e]); kRec.w = sf(Q.f[1][e]); kRec.pdfKernel = sf(Q.f[2][e]); kRec.pdfEdgeFailure = sf(Q.f[3][e]);
+    kRec.weightKernel = sf(Q.f[4][e]); kRec.u = sf(Q.f[5][e]);
+    kRec.contrib = v3(Q.f[6][e], Q.f[7][e], Q.f[8][e]);
+    kRec.valid = true;
+    beam_functor(P, rec, R, beam, kRec, a);
+  }
+  const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key);
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const bool same = lane - off >= start;
+#pragma unroll
+    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) {
+      const float vu = __shfl_up_sync(0xffffffffu, a[j], off);
+      if (same) a[j] += vu;
+    }
+  }
+  if (valid && (lane == 31 || (heads >> (lane + 1) & 1u))) {
+    float *o = P.out + (size_t)key * GVPM_OUT_FLOATS;
+#pragma unroll
+    for (int j = 0; j < GVPM_OUT_FLOATS; ++j)
+      if (a[j] != 0.f) atomicAdd(o + j, a[j]);
+  }
+}
+
 __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ GatherParams P) {
+  __shared__ BeamShadeShared ring[4];
   const int lane = threadIdx.x & 31;
+  BeamShadeShared &Q = ring[threadIdx.x >> 5];
+  uint32_t head = 0, qn = 0;
   unsigned long long total = *P.pair_counter;
   if (total > P.pair_cap) total = P.pair_cap;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total;
        i0 += stride) {
     const unsigned long long i = i0 + lane;
-    const bool valid = i < total;
-    float a[GVPM_OUT_FLOATS];
-#pragma unroll
-    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) a[j] = 0.f;
-    uint32_t key = 0xffffffffu;
-    if (valid) {
+    bool shade = false;
+    uint32_t key = 0, bi = 0;
+    BeamKernelRec kRec;
+    if (i < total) {
       const uint2 pr = P.pairs[i];
       key = pr.x;
       const float4 sb = ldg4(P.subs + pr.y);
-      const uint32_t bi = __float_as_uint(sb.z), flags = __float_as_uint(sb.w);
+      bi = __float_as_uint(sb.z);
+      const uint32_t flags = __float_as_uint(sb.w);
       const float4 *rec = P.rays + (size_t)key * GVPM_RAY_FLOAT4;
       const BaseRay R = load_base_ray(rec);
       const BeamRec beam = load_beam(P, bi);
       double tNear = 0.0;
-      const uint32_t origBeam = bi;  // beam records keep the caller's order; only sub-beams are sorted
-      BeamKernelRec kRec;
       bool owner;
       if (P.cfg.beam_kernel_1d) {
         // 1-D kernel: the sub-beam [t1, t2] accepts v in (t1, t2] (beams_struct.h:299-301); first / last sub-beam
@@ -281,7 +334,7 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
         kRec = beam_kernel_eval_1d(P, beam, R);
         owner = ((flags & 1u) || kRec.v.v > sb.x) && ((flags & 2u) || kRec.v.v <= sb.y);
       } else {
-        kRec = beam_kernel_eval(P, beam, R, origBeam, tNear);
+        kRec = beam_kernel_eval(P, beam, R, bi, tNear);   // beam records keep the caller's order; only sub-beams are sorted
         // sub-beam ownership: half-open [t1, t2), first sub-beam also owns tNear < 0, last one the tail
         owner = ((flags & 1u) || tNear >= (double)sb.x) && ((flags & 2u) || tNear < (double)sb.y);
       }
@@ -306,32 +359,31 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
         }
         if (P.dump_pairs) {
           const unsigned long long slot = atomicAdd(P.dump_counter, 1ull);
-          if (slot < P.dump_cap) P.dump_pairs[slot] = make_uint2(key, origBeam | (contributes ? 0x80000000u : 0u));
-        } else if (contributes) {
-          beam_functor(P, rec, R, beam, kRec, a);
+          if (slot < P.dump_cap) P.dump_pairs[slot] = make_uint2(key, bi | (contributes ? 0x80000000u : 0u));
+        } else {
+          shade = contributes;
         }
       }
     }
     if (P.dump_pairs) continue;
-    const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
-    const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key);
-    const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const bool same = lane - off >= start;
-#pragma unroll
-      for (int j = 0; j < GVPM_OUT_FLOATS; ++j) {
-        const float vu = __shfl_up_sync(0xffffffffu, a[j], off);
-        if (same) a[j] += vu;
-      }
+    const uint32_t m = __ballot_sync(0xffffffffu, shade);
+    if (shade) {
+      const uint32_t e = (head + qn + __popc(m & ((1u << lane) - 1u))) & (kBeamRing - 1);
+      Q.ray[e] = key; Q.beam[e] = bi;
+      Q.f[0][e] = kRec.v.v; Q.f[1][e] = kRec.w.v; Q.f[2][e] = kRec.pdfKernel.v; Q.f[3][e] = kRec.pdfEdgeFailure.v;
+      Q.f[4][e] = kRec.weightKernel.v; Q.f[5][e] = kRec.u.v;
+      Q.f[6][e] = kRec.contrib.x.v; Q.f[7][e] = kRec.contrib.y.v; Q.f[8][e] = kRec.contrib.z.v;
     }
-    if (valid && (lane == 31 || (heads >> (lane + 1) & 1u))) {
-      float *o = P.out + (size_t)key * GVPM_OUT_FLOATS;
-#pragma unroll
-      for (int j = 0; j < GVPM_OUT_FLOATS; ++j)
-        if (a[j] != 0.f) atomicAdd(o + j, a[j]);
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32u) {
+      beam_shade_batch(P, Q, head, 32u, lane);
+      head = (head + 32u) & (kBeamRing - 1);
+      qn -= 32u;
+      __syncwarp();
     }
   }
+  if (!P.dump_pairs && qn > 0u) beam_shade_batch(P, Q, head, qn, lane);
 }
 
 // sppm primal photon beams (volumePhotonBeamPass, sppm.cpp:823-860): one thread per (camera beam, sub-beam) candidate

@@ -75,9 +75,49 @@ struct PlaneShared {
   uint16_t queue[kPlWarps][kPlQCap][32];         // per-lane candidate queues (chunk-relative plane index)
   float red[kPlWarps][6];                        // ray-block bounds reduction
   float bounds[6];
+  float tred[kPlWarps][8];                       // ray-bundle reduction: xmin, xmax, ymin, ymax, delta, mint min, maxt max, cos min
+  float bundle[8];
+  uint16_t live[kPlChunk];                       // planes of the chunk the bundle test keeps (chunk-relative)
+  uint32_t nLive;
+  uint32_t amask[kPlWarps];
   uint32_t leafMask;
   uint32_t block;
 };
+
+// Bundle test: can ANY ray of the CTA's ray block meet the plane?  The rays of a block start (nearly) in one point c0
+// (primary rays of a pinhole; delta = largest distance of an origin to c0) and their directions lie in the pyramid
+// spanned by four corner directions dk.  For rays through c0 the plane coordinates t0 = (d.A)/(d.N), t1 = (d.B)/(d.N)
+// (A = e1 x T, B = T x e0, N = e1 x e0, T = c0 - ori) are linear-fractional in d: where d.N keeps its sign over the
+// pyramid their extremes are taken at the corners, so the plane is out of every ray's reach when all four corners
+// put t0 (or t1) on the same side of [0, 1].  Conservative: slack for delta and rounding, planes whose d.N changes
+// sign (or nearly vanishes) are kept.  Everything kept goes through plane_candidate and the strict test per ray.
+__device__ __forceinline__ bool plane_bundle_reject(const float4 q0, const float4 q1, const float4 q2, const float *c0,
+                                                    const float (*dk)[3], float delta) {
+  const float tx = c0[0] - q0.x, ty = c0[1] - q0.y, tz = c0[2] - q0.z;
+  const float nx = q2.y * q1.z - q2.z * q1.y, ny = q2.z * q1.x - q2.x * q1.z, nz = q2.x * q1.y - q2.y * q1.x;   // e1 x e0
+  const float ax = q2.y * tz - q2.z * ty, ay = q2.z * tx - q2.x * tz, az = q2.x * ty - q2.y * tx;               // e1 x T
+  const float bx = ty * q1.z - tz * q1.y, by = tz * q1.x - tx * q1.z, bz = tx * q1.y - ty * q1.x;               // T x e0
+  const float tn = fabsf(tx) + fabsf(ty) + fabsf(tz);
+  // |a| error: (delta + rounding of T) * |d| * |e1|; q0.w = |e0|, q1.w = |e1|, |dk| <= 2
+  const float sa = 2.f * (delta + 4e-6f * tn) * q1.w, sb = 2.f * (delta + 4e-6f * tn) * q0.w;
+  bool pos = true, neg = true, a_lo = true, a_hi = true, b_lo = true, b_hi = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float det = dk[k][0] * nx + dk[k][1] * ny + dk[k][2] * nz;
+    const float a = dk[k][0] * ax + dk[k][1] * ay + dk[k][2] * az;
+    const float b = dk[k][0] * bx + dk[k][1] * by + dk[k][2] * bz;
+    const float ad = fabsf(det), tiny = 1e-4f * q0.w * q1.w;
+    pos = pos && det > tiny;
+    neg = neg && det < -tiny;
+    const float s = det < 0.f ? -1.f : 1.f;
+    const float e = 1e-3f * ad;
+    a_lo = a_lo && a * s < -(e + sa);
+    a_hi = a_hi && (a * s - ad) > (e + sa);
+    b_lo = b_lo && b * s < -(e + sb);
+    b_hi = b_hi && (b * s - ad) > (e + sb);
+  }
+  return (pos || neg) && (a_lo || a_hi || b_lo || b_hi);
+}
 
 // relaxed conservative form of intersectPlane0D: never rejects a pair the strictly rounded test accepts.
 // Margins: the relaxed (FMA) and the strict evaluations of det, T.P, d.Q, e1.Q each differ from the exact value by
@@ -164,6 +204,79 @@ __global__ void __launch_bounds__(kPlWarps * 32, 3) k_plane_gather(const __grid_
       }
       __syncthreads();
     }
+    // the ray bundle of the block: reference ray = the block's first active ray
+    {
+      const uint32_t am = __ballot_sync(0xffffffffu, active);
+      if (lane == 0) S.amask[w] = am;
+      __syncthreads();
+      int fw = -1;
+      for (int i = kPlWarps - 1; i >= 0; --i) if (S.amask[i] != 0u) fw = i;
+      if (fw == w && lane == __ffs(am) - 1) {
+        S.bundle[0] = ox; S.bundle[1] = oy; S.bundle[2] = oz;
+        S.bundle[3] = dx; S.bundle[4] = dy; S.bundle[5] = dz;
+      }
+      if (fw < 0 && threadIdx.x == 0) {
+        S.bundle[0] = S.bundle[1] = S.bundle[2] = 0.f;
+        S.bundle[3] = S.bundle[4] = 0.f; S.bundle[5] = 1.f;
+      }
+      __syncthreads();
+    }
+    float c0[3] = {S.bundle[0], S.bundle[1], S.bundle[2]}, bm[3] = {S.bundle[3], S.bundle[4], S.bundle[5]};
+    float bu[3], bv[3];
+    {   // any orthonormal basis around bm
+      float t[3] = {0.f, 0.f, 0.f};
+      if (fabsf(bm[0]) <= fabsf(bm[1]) && fabsf(bm[0]) <= fabsf(bm[2])) t[0] = 1.f; else if (fabsf(bm[1]) <= fabsf(bm[2])) t[1] = 1.f; else t[2] = 1.f;
+      bu[0] = t[1] * bm[2] - t[2] * bm[1]; bu[1] = t[2] * bm[0] - t[0] * bm[2]; bu[2] = t[0] * bm[1] - t[1] * bm[0];
+      const float il = rsqrtf(bu[0] * bu[0] + bu[1] * bu[1] + bu[2] * bu[2]);
+      bu[0] *= il; bu[1] *= il; bu[2] *= il;
+      bv[0] = bm[1] * bu[2] - bm[2] * bu[1]; bv[1] = bm[2] * bu[0] - bm[0] * bu[2]; bv[2] = bm[0] * bu[1] - bm[1] * bu[0];
+    }
+    __syncthreads();
+    {
+      float r8[8] = {INFINITY, -INFINITY, INFINITY, -INFINITY, 0.f, INFINITY, -INFINITY, 1.f};
+      if (active) {
+        const float z = dx * bm[0] + dy * bm[1] + dz * bm[2];
+        const float iz = 1.f / fmaxf(z, 1e-6f);
+        const float x = (dx * bu[0] + dy * bu[1] + dz * bu[2]) * iz, y = (dx * bv[0] + dy * bv[1] + dz * bv[2]) * iz;
+        const float ex = ox - c0[0], ey = oy - c0[1], ez = oz - c0[2];
+        r8[0] = x; r8[1] = x; r8[2] = y; r8[3] = y;
+        r8[4] = sqrtf(ex * ex + ey * ey + ez * ez);
+        r8[5] = mint; r8[6] = maxt; r8[7] = z;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+          const float v = __shfl_xor_sync(0xffffffffu, r8[k], o);
+          r8[k] = (k == 0 || k == 2 || k == 5 || k == 7) ? fminf(r8[k], v) : fmaxf(r8[k], v);
+        }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) S.tred[w][k] = r8[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        float v = S.tred[0][k];
+        for (int i = 1; i < kPlWarps; ++i)
+          v = (k == 0 || k == 2 || k == 5 || k == 7) ? fminf(v, S.tred[i][k]) : fmaxf(v, S.tred[i][k]);
+        S.bundle[k] = v;
+      }
+      __syncthreads();
+    }
+    // corner directions of the bundle's pyramid (rectangle in the plane at distance 1 along bm, slightly enlarged)
+    float dk[4][3];
+    float bdelta = S.bundle[4];
+    const bool bundleOk = S.bundle[7] > 0.5f && S.bundle[0] <= S.bundle[1];
+    {
+      const float px = 1e-5f + 1e-3f * (S.bundle[1] - S.bundle[0]), py = 1e-5f + 1e-3f * (S.bundle[3] - S.bundle[2]);
+      const float xs[2] = {S.bundle[0] - px, S.bundle[1] + px}, ys[2] = {S.bundle[2] - py, S.bundle[3] + py};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dk[k][c] = bm[c] + xs[k & 1] * bu[c] + ys[k >> 1] * bv[c];
+      const float cm = fmaxf(fmaxf(fabsf(c0[0]), fabsf(c0[1])), fabsf(c0[2]));
+      bdelta = bdelta * 1.001f + 4e-6f * cm;
+    }
     float bl[3], bh[3];
     {
       const float ext = fmaxf(fmaxf(S.bounds[3] - S.bounds[0], S.bounds[4] - S.bounds[1]), S.bounds[5] - S.bounds[2]);
@@ -236,13 +349,30 @@ __global__ void __launch_bounds__(kPlWarps * 32, 3) k_plane_gather(const __grid_
           if ((leafMask >> (p >> 5) & 1u) && gi < nPl) S.tst[p][k] = ldg4(Q + (size_t)k * nPl + gi);
         }
         __syncthreads();
+        // bundle test: planes no ray of the block can meet are dropped for the whole block (one thread per plane)
+        if (threadIdx.x == 0) S.nLive = 0u;
+        __syncthreads();
+        {
+          const int nIn = (int)min((uint32_t)kPlChunk, nPl - chunkBase);
+          for (int p0 = 0; p0 < kPlChunk; p0 += kPlWarps * 32) {
+            const int p = p0 + threadIdx.x;
+            bool keep = p < nIn && (leafMask >> (p >> 5) & 1u);
+            if (keep && bundleOk) keep = !plane_bundle_reject(S.tst[p][0], S.tst[p][1], S.tst[p][2], c0, dk, bdelta);
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(&S.nLive, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) S.live[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+          }
+        }
+        __syncthreads();
+        const int nLive = (int)S.nLive;
         // phase A in sub-steps, phase B whenever a queue could overflow in the next sub-step
-        for (int sub = 0; sub < kPlChunk; sub += kPlSub) {
-          if (!((leafMask >> (sub >> 5)) & ((1u << (kPlSub / 32)) - 1u))) continue;
+        for (int sub = 0; sub < nLive; sub += kPlSub) {
           if (active) {
-            const int pend = min(sub + kPlSub, (int)min((uint32_t)kPlChunk, nPl - chunkBase));
-            for (int p = sub; p < pend; ++p) {
-              if ((p & 31) == 0 && !(leafMask >> (p >> 5) & 1u)) { p += 31; continue; }
+            const int pend = min(sub + kPlSub, nLive);
+            for (int j = sub; j < pend; ++j) {
+              const int p = S.live[j];
               if (plane_candidate(S.tst[p][0], S.tst[p][1], S.tst[p][2], ox, oy, oz, dx, dy, dz, mint, maxt))
                 S.queue[w][qn++][lane] = (uint16_t)p;
             }

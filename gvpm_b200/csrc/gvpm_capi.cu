@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "gvpm_device.cuh"
 
@@ -24,7 +25,14 @@ size_t frustum_occ_bytes();
 void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, uint32_t stride, const uint32_t *par_src,
                          uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
-                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st);
+                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st, uint32_t region_cap = 0,
+                         const uint32_t *region_count = nullptr);
+void launch_frustum_mark(const float4 *rays, uint32_t n_rays, const FrustumGrid &G, uint32_t *occ, int sm_count, cudaStream_t st);
+void launch_dispatch(const DispatchParams &P, cudaStream_t st);
+void launch_dispatch_signal(const SignalParams &P, cudaStream_t st);
+void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *timeout, cudaStream_t st);
+void launch_flag_set(const FlagSetParams &P, cudaStream_t st);
+void launch_translate_idx(uint32_t *idx, unsigned long long n, const float4 *aos, cudaStream_t st);
 void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
                          uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st);
 void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
@@ -159,6 +167,27 @@ struct gvpm_ctx {
   uint32_t n_photons = 0;
   bool photons_loaded = false;
   bool photons_direct = false;   // gvpm_trace_photons_direct: the 128-byte records in `aos` ARE the photon set (no staging, no packing)
+  // dispatched photon set (gvpm_build_dispatched): the records live in an inbox the peers wrote; one region of
+  // region_cap records per sender, region_count[s] (device) of them filled
+  float4 *aos_override = nullptr;
+  uint32_t region_cap = 0;
+  const uint32_t *region_count = nullptr;
+  float4 *records() { return aos_override ? aos_override : aos.as<float4>(); }
+  struct RayFit { bool concurrent = false; float C[3], m[3], u[3], v[3], delta, cosmin, xmin, xmax, ymin, ymax, count; };
+  // photon dispatch between ranks (dispatch.cu, gvpm_dispatch_*)
+  struct Dispatch {
+    int n_peers = 0, self = -1;
+    uint32_t region_cap = 0;
+    bool connected = false;
+    DevBuf inbox[2], ctrl, occ_all, grids_dev[2], keepbits, block_cnt;
+    RayFit fit[GVPM_MAX_PEERS];
+    char *peer_inbox[2][GVPM_MAX_PEERS] = {};   // mapped (or, same process, raw) pointers; [self] = own
+    uint32_t *peer_ctrl[GVPM_MAX_PEERS] = {};
+    bool peer_mapped[GVPM_MAX_PEERS] = {};      // opened through CUDA IPC (to be closed)
+    FrustumGrid *grids_host[2] = {nullptr, nullptr};   // pinned
+    uint32_t gen_push[2] = {0, 0}, gen_build[2] = {0, 0};
+    cudaEvent_t ev_src = nullptr;
+  } disp;
   DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
   Tree tree{};
   float radius = 0.f;
@@ -182,7 +211,7 @@ struct gvpm_ctx {
   uint32_t hint_n = 0;
   double trace_photons_per_path = 0.0;   // running estimate (sizes the first batch of gvpm_trace_photons)    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
   uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
-  struct RayFit { bool concurrent = false; float C[3], m[3], u[3], v[3], delta, cosmin, xmin, xmax, ymin, ymax, count; } pin;
+  RayFit pin;
   float *pin_host = nullptr;         // pinned: 16 fit floats + 8 stats words
 
   DevBuf ray_staging, rays;
@@ -316,7 +345,7 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
     P.cell_start = ctx->cell_start.as<uint32_t>();
   }
   P.planes = ctx->planes.as<float4>();
-  P.aos = ctx->aos.as<float4>();
+  P.aos = ctx->records();
   P.orig = ctx->orig.as<uint32_t>();
   P.rays = ctx->rays.as<float4>();
   P.n_rays = ctx->n_rays;
@@ -616,7 +645,16 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
-                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask};
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask,
+                    &ctx->disp.inbox[0], &ctx->disp.inbox[1], &ctx->disp.ctrl, &ctx->disp.occ_all, &ctx->disp.grids_dev[0], &ctx->disp.grids_dev[1],
+                    &ctx->disp.keepbits, &ctx->disp.block_cnt};
+  for (int p = 0; p < ctx->disp.n_peers; ++p)
+    if (ctx->disp.peer_mapped[p]) {
+      for (int b = 0; b < 2; ++b) if (ctx->disp.peer_inbox[b][p]) cudaIpcCloseMemHandle(ctx->disp.peer_inbox[b][p]);
+      if (ctx->disp.peer_ctrl[p]) cudaIpcCloseMemHandle(ctx->disp.peer_ctrl[p]);
+    }
+  for (int b = 0; b < 2; ++b) if (ctx->disp.grids_host[b]) cudaFreeHost(ctx->disp.grids_host[b]);
+  if (ctx->disp.ev_src) cudaEventDestroy(ctx->disp.ev_src);
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
   if (ctx->pin_host) cudaFreeHost(ctx->pin_host);
@@ -736,6 +774,9 @@ int gvpm_photon_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   ctx->n_photons = (uint32_t)n;
   ctx->photons_loaded = true;
   ctx->photons_direct = false;
+  ctx->aos_override = nullptr;
+  ctx->region_cap = 0;
+  ctx->region_count = nullptr;
   ctx->built = false;
   ++ctx->state_gen;
   if (dev) *dev = ctx->ph_staging.p;
@@ -991,7 +1032,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     const bool direct = ctx->photons_direct;
     PhotonStaging S{};
     if (!direct) S = photon_staging_ptrs(ctx->ph_staging.p, n);
-    const float *pos = direct ? ctx->aos.as<float>() : S.pos;
+    const float *pos = direct ? (const float *)ctx->records() : S.pos;
     const uint32_t stride = direct ? 32u : 3u;
     CK(ctx->bounds_partial.reserve((size_t)bounds_blocks(n) * 6 * sizeof(float)));
     launch_bounds(pos, n, ctx->bounds_partial.as<float>(), ctx->bounds.as<float>(), st, stride);
@@ -999,7 +1040,7 @@ int gvpm_build_points(gvpm_ctx *ctx, float radius) {
     CK(run_sort(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_in.as<uint32_t>(), ctx->keys_out.as<uint32_t>(),
                 ctx->vals_in.as<uint32_t>(), ctx->vals_out.as<uint32_t>(), n, st));
     if (!direct) CK(ctx->aos.reserve(128 * (size_t)n));
-    launch_pack_sorted(S, ctx->aos.as<float4>(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
+    launch_pack_sorted(S, ctx->records(), ctx->vals_out.as<uint32_t>(), n, ctx->planes.as<float4>(),
                        ctx->orig.as<uint32_t>(), st, direct);
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
     float4 *lo = ctx->box_lo.as<float4>(), *hi = ctx->box_hi.as<float4>();
@@ -1153,12 +1194,9 @@ static int analyse_rays(gvpm_ctx *ctx) {
   return GVPM_OK;
 }
 
-static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
-  cudaSetDevice(ctx->device);
-  const uint32_t n = ctx->n_photons;
-  cudaStream_t st = ctx->stream;
-  const gvpm_ctx::RayFit &F = ctx->pin;
-  CK(cudaEventRecord(ctx->ev[0], st));
+// The grid of a concurrent ray set (RayFit) for search radius `radius`: host arithmetic only, so that a rank that SENDS
+// photons (dispatch.cu) derives the receiver's grid from the receiver's RayFit exactly as the receiver does.
+static FrustumGrid make_frustum_grid(const gvpm_ctx::RayFit &F, float radius, bool parity_split) {
   FrustumGrid G{};
   for (int k = 0; k < 3; ++k) { G.C[k] = F.C[k]; G.m[k] = F.m[k]; G.u[k] = F.u[k]; G.v[k] = F.v[k]; }
   G.xmin = F.xmin; G.xmax = F.xmax; G.ymin = F.ymin; G.ymax = F.ymax;
@@ -1184,7 +1222,18 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   for (int c = classes; c < GVPM_GRID_CLASSES; ++c) { G.csize[c] = G.csize[classes - 1]; G.nx[c] = G.ny[c] = 1; G.base[c] = total; }
   G.classes = classes;
   G.n_cells = total;
-  G.parity_split = (ctx->have_cfg && ctx->cfg.path_set && !ctx->cfg.sppm_primal) ? 1 : 0;
+  G.parity_split = parity_split ? 1 : 0;
+  return G;
+}
+
+static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->n_photons;
+  cudaStream_t st = ctx->stream;
+  const gvpm_ctx::RayFit &F = ctx->pin;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  const FrustumGrid G = make_frustum_grid(F, radius, ctx->have_cfg && ctx->cfg.path_set && !ctx->cfg.sppm_primal);
+  const uint32_t total = G.n_cells;
   const uint32_t n_keys = (G.parity_split ? 2u : 1u) * total + 2;   // + NEAR + DROP
   int bits = 1;
   while ((1ull << bits) < (unsigned long long)n_keys) ++bits;
@@ -1213,9 +1262,9 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     PhotonStaging S{};
     if (!direct) S = photon_staging_ptrs(ctx->ph_staging.p, n);
     if (direct)   // position = first three floats of the record, path parity = bit 10 of its meta word
-      launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, ctx->aos.as<float>(), 32u, ctx->aos.as<uint32_t>() + 3, 32u, 10u, n,
+      launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, (const float *)ctx->records(), 32u, (const uint32_t *)ctx->records() + 3, 32u, 10u, n,
                           G, ctx->grid_occ.as<uint32_t>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(),
-                          ctx->bounds.as<unsigned>() + 6, keepmask, block_kept, ctx->sm_count, st);
+                          ctx->bounds.as<unsigned>() + 6, keepmask, block_kept, ctx->sm_count, st, ctx->region_cap, ctx->region_count);
     else
       launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, S.pos, 3u, S.path_id, 1u, 0u, n, G, ctx->grid_occ.as<uint32_t>(),
                           ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, keepmask,
@@ -1244,7 +1293,7 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     }
     launch_cell_starts(sortedKeys, m, n_keys, ctx->cell_start.as<uint32_t>(),
                        ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
-    launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->aos.as<float4>(), ctx->planes.as<float4>(),
+    launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->records(), ctx->planes.as<float4>(),
                             ctx->orig.as<uint32_t>(), st, direct);
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
     if (m == n) {   // kept count of this build -> hint of the next one (no blocking)
@@ -1394,6 +1443,9 @@ static int trace_impl(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint
     ctx->n_photons = (uint32_t)n;
     ctx->photons_loaded = true;
     ctx->photons_direct = true;
+    ctx->aos_override = nullptr;
+    ctx->region_cap = 0;
+    ctx->region_count = nullptr;
     ctx->built = false;
     ++ctx->state_gen;
   } else {
@@ -1463,6 +1515,243 @@ int gvpm_trace_photons(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uin
 int gvpm_trace_photons_direct(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t n, uint64_t seed, int max_depth,
                               int rr_depth, int min_depth, uint64_t *n_paths) {
   return trace_impl(ctx, scene, n, seed, max_depth, rr_depth, min_depth, n_paths, true);
+}
+
+
+// ---- photon dispatch between ranks (dispatch.cu; include/gvpm_b200.h gvpm_dispatch_*) -----------------------------------
+// Control block of a rank (its own device memory; the peers write into it, only the owner reads it), in 32-bit words:
+enum {
+  DC_PUSHED = 0,                           // [2][MAX_PEERS] generation of sender s's last dispatch into my inbox b
+  DC_COUNT = 2 * GVPM_MAX_PEERS,           // [2][MAX_PEERS] records sender s wrote into its region of my inbox b
+  DC_FREED = 4 * GVPM_MAX_PEERS,           // [2][MAX_PEERS] generation up to which RECEIVER d has released its inbox b
+  DC_TIMEOUT = 6 * GVPM_MAX_PEERS,         // set by k_flag_wait when a peer never signalled
+  DC_OVERFLOW = 6 * GVPM_MAX_PEERS + 1,
+  DC_OCC = 6 * GVPM_MAX_PEERS + 16,        // my ray-occupancy mask (frustum_occ_bytes), copied by the peers at connect
+};
+struct DispatchBlob {   // what gvpm_dispatch_export writes (GVPM_DISPATCH_BLOB_BYTES)
+  long long pid;
+  int device, n_peers;
+  unsigned long long region_cap;
+  void *raw_inbox[2], *raw_ctrl;           // valid inside the exporting process
+  cudaIpcMemHandle_t inbox[2], ctrl;
+  gvpm_ctx::RayFit fit;
+};
+static_assert(sizeof(DispatchBlob) <= GVPM_DISPATCH_BLOB_BYTES, "blob size");
+
+int gvpm_dispatch_export(gvpm_ctx *ctx, int n_peers, size_t region_cap, void *blob) {
+  if (!ctx || !blob || n_peers < 1 || n_peers > GVPM_MAX_PEERS || region_cap == 0 ||
+      (unsigned long long)n_peers * region_cap > 0xfffffff0ull)
+    return GVPM_ERR_INVALID;
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_export needs this rank's rays first (gvpm_upload_rays)");
+  if (ctx->disp.n_peers) return fail(ctx, GVPM_ERR_INVALID, "dispatch buffers already exported");
+  cudaSetDevice(ctx->device);
+  int rc = analyse_rays(ctx);
+  if (rc) return rc;
+  if (!ctx->pin.concurrent)
+    return fail(ctx, GVPM_ERR_UNSUPPORTED, "photon dispatch needs concurrent rays (a pinhole's primary rays); use the all-gather exchange");
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  const size_t ctrl_bytes = (size_t)DC_OCC * 4 + frustum_occ_bytes();
+  for (int b = 0; b < 2; ++b) {
+    CK(D.inbox[b].reserve((size_t)n_peers * region_cap * 128));
+    D.inbox[b].pinned = true;
+    CK(D.grids_dev[b].reserve(sizeof(FrustumGrid) * GVPM_MAX_PEERS));
+    if (!D.grids_host[b]) CK(cudaHostAlloc((void **)&D.grids_host[b], sizeof(FrustumGrid) * GVPM_MAX_PEERS, cudaHostAllocDefault));
+  }
+  CK(D.ctrl.reserve(ctrl_bytes));
+  D.ctrl.pinned = true;
+  CK(D.occ_all.reserve(frustum_occ_bytes() * (size_t)n_peers));
+  if (!D.ev_src) CK(cudaEventCreateWithFlags(&D.ev_src, cudaEventDisableTiming));
+  CK(cudaMemsetAsync(D.ctrl.p, 0, ctrl_bytes, ctx->stream));
+  // the occupancy mask depends on the rays alone (projection basis and bounds of the fit), not on the radius
+  const FrustumGrid G = make_frustum_grid(ctx->pin, 1.f, false);
+  launch_frustum_mark(ctx->rays.as<float4>(), ctx->n_rays, G, D.ctrl.as<uint32_t>() + DC_OCC, ctx->sm_count, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  DispatchBlob B{};
+  B.pid = (long long)getpid();
+  B.device = ctx->device;
+  B.n_peers = n_peers;
+  B.region_cap = region_cap;
+  for (int b = 0; b < 2; ++b) {
+    B.raw_inbox[b] = D.inbox[b].p;
+    CK(cudaIpcGetMemHandle(&B.inbox[b], D.inbox[b].p));
+  }
+  B.raw_ctrl = D.ctrl.p;
+  CK(cudaIpcGetMemHandle(&B.ctrl, D.ctrl.p));
+  B.fit = ctx->pin;
+  memset(blob, 0, GVPM_DISPATCH_BLOB_BYTES);
+  memcpy(blob, &B, sizeof(B));
+  D.n_peers = n_peers;
+  D.region_cap = (uint32_t)region_cap;
+  return GVPM_OK;
+}
+
+int gvpm_dispatch_connect(gvpm_ctx *ctx, const void *blobs, int n_peers, int self_index) {
+  if (!ctx || !blobs || self_index < 0 || self_index >= n_peers) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (D.n_peers != n_peers) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_export first, with the same number of peers");
+  if (D.connected) return fail(ctx, GVPM_ERR_INVALID, "dispatch peers already connected");
+  cudaSetDevice(ctx->device);
+  const long long me = (long long)getpid();
+  for (int p = 0; p < n_peers; ++p) {
+    DispatchBlob B;
+    memcpy(&B, (const char *)blobs + (size_t)p * GVPM_DISPATCH_BLOB_BYTES, sizeof(B));
+    if (B.n_peers != n_peers || B.region_cap != D.region_cap)
+      return fail(ctx, GVPM_ERR_INVALID, "dispatch blobs disagree on the number of peers / the region size");
+    D.fit[p] = B.fit;
+    if (B.pid == me) {   // same process (several contexts, tests): the pointers are valid as they are
+      if (B.device != ctx->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, B.device));
+        if (!can) return fail(ctx, GVPM_ERR_UNSUPPORTED, "no peer access between two devices of this process");
+        cudaError_t e = cudaDeviceEnablePeerAccess(B.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+      }
+      for (int b = 0; b < 2; ++b) D.peer_inbox[b][p] = (char *)B.raw_inbox[b];
+      D.peer_ctrl[p] = (uint32_t *)B.raw_ctrl;
+    } else {
+      for (int b = 0; b < 2; ++b) CK(cudaIpcOpenMemHandle((void **)&D.peer_inbox[b][p], B.inbox[b], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle((void **)&D.peer_ctrl[p], B.ctrl, cudaIpcMemLazyEnablePeerAccess));
+      D.peer_mapped[p] = true;
+    }
+    // the receiver's occupancy mask, read once: the classification then touches local memory only
+    CK(cudaMemcpyAsync(D.occ_all.as<char>() + frustum_occ_bytes() * (size_t)p, D.peer_ctrl[p] + DC_OCC, frustum_occ_bytes(),
+                       cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  D.self = self_index;
+  D.connected = true;
+  return GVPM_OK;
+}
+
+int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count, float radius, void *after_stream) {
+  if (!ctx || (which != 0 && which != 1) || begin + count > n_total || !(radius > 0.f)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  if (count > D.region_cap) return fail(ctx, GVPM_ERR_INVALID, "slice larger than the exported region size");
+  if (!ctx->ph_staging.p || ctx->ph_staging.cap < PhotonLayout(n_total).bytes)
+    return fail(ctx, GVPM_ERR_INVALID, "size the selected photon staging buffer for n_total first (gvpm_photon_staging)");
+  cudaSetDevice(ctx->device);
+  cudaStream_t ks = ctx->push_kernel_stream;
+  CK(cudaEventRecord(D.ev_src, after_stream ? (cudaStream_t)after_stream : ctx->stream));
+  CK(cudaStreamWaitEvent(ks, D.ev_src, 0));
+  const uint32_t gen = ++D.gen_push[which];
+  uint32_t *ctrl = D.ctrl.as<uint32_t>();
+  // every receiver must have released its inbox `which` gen - 1 times (flags the receivers write into MY control block)
+  if (gen > 1) {
+    launch_flag_wait(ctrl + DC_FREED + which * GVPM_MAX_PEERS, D.n_peers, gen - 1, ctrl + DC_TIMEOUT, ks);
+    ctx->launches += 1;
+  }
+  const bool parity = ctx->have_cfg && ctx->cfg.path_set && !ctx->cfg.sppm_primal;
+  for (int d = 0; d < D.n_peers; ++d) D.grids_host[which][d] = make_frustum_grid(D.fit[d], radius, parity);
+  CK(cudaMemcpyAsync(D.grids_dev[which].p, D.grids_host[which], sizeof(FrustumGrid) * D.n_peers, cudaMemcpyHostToDevice, ks));
+  const uint32_t nb = (uint32_t)((count + 255) / 256);
+  CK(D.keepbits.reserve(std::max<size_t>(count, 256)));
+  CK(D.block_cnt.reserve((size_t)GVPM_MAX_PEERS * (nb + 2) * 4));
+  DispatchParams P{};
+  P.S = photon_staging_ptrs(ctx->ph_staging.p, n_total);
+  P.begin = (uint32_t)begin;
+  P.count = (uint32_t)count;
+  P.n_dst = D.n_peers;
+  P.grids = D.grids_dev[which].as<FrustumGrid>();
+  P.region_cap = D.region_cap;
+  P.keepbits = D.keepbits.as<uint8_t>();
+  P.block_cnt = D.block_cnt.as<uint32_t>();
+  P.nb = nb;
+  P.overflow = ctrl + DC_OVERFLOW;
+  SignalParams Sg{};
+  Sg.n_dst = D.n_peers;
+  Sg.self = D.self;
+  Sg.nb = nb;
+  Sg.block_cnt = P.block_cnt;
+  Sg.gen = gen;
+  for (int d = 0; d < D.n_peers; ++d) {
+    P.occ[d] = D.occ_all.as<uint32_t>() + (frustum_occ_bytes() / 4) * (size_t)d;
+    P.inbox[d] = (float4 *)(D.peer_inbox[which][d] + (size_t)D.self * D.region_cap * 128);
+    Sg.count_dst[d] = D.peer_ctrl[d] + DC_COUNT + which * GVPM_MAX_PEERS + D.self;
+    Sg.flag_dst[d] = D.peer_ctrl[d] + DC_PUSHED + which * GVPM_MAX_PEERS + D.self;
+  }
+  launch_dispatch(P, ks);
+  launch_dispatch_signal(Sg, ks);
+  ctx->launches += 4;
+  CK(cudaGetLastError());
+  return GVPM_OK;
+}
+
+int gvpm_build_dispatched(gvpm_ctx *ctx, int which, float radius, uint32_t *n_kept) {
+  if (!ctx || (which != 0 && which != 1) || !(radius > 0.f)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  if (!ctx->rays_loaded) return fail(ctx, GVPM_ERR_INVALID, "no rays uploaded");
+  cudaSetDevice(ctx->device);
+  int rc = analyse_rays(ctx);
+  if (rc) return rc;
+  const gvpm_ctx::RayFit &Fa = ctx->pin, &Fb = D.fit[D.self];
+  bool same = Fa.concurrent && Fb.concurrent && Fa.delta == Fb.delta && Fa.xmin == Fb.xmin && Fa.xmax == Fb.xmax &&
+              Fa.ymin == Fb.ymin && Fa.ymax == Fb.ymax && Fa.count == Fb.count;
+  for (int k = 0; k < 3; ++k) same = same && Fa.C[k] == Fb.C[k] && Fa.m[k] == Fb.m[k] && Fa.u[k] == Fb.u[k] && Fa.v[k] == Fb.v[k];
+  if (!same)
+    return fail(ctx, GVPM_ERR_INVALID, "the rays changed since gvpm_dispatch_export: the peers dispatch for the exported ray set");
+  const uint32_t gen = ++D.gen_build[which];
+  uint32_t *ctrl = D.ctrl.as<uint32_t>();
+  launch_flag_wait(ctrl + DC_PUSHED + which * GVPM_MAX_PEERS, D.n_peers, gen, ctrl + DC_TIMEOUT, ctx->stream);
+  ctx->launches += 1;
+  ctx->n_photons = (uint32_t)((size_t)D.n_peers * D.region_cap);
+  ctx->photons_loaded = true;
+  ctx->photons_direct = true;
+  ctx->aos_override = D.inbox[which].as<float4>();
+  ctx->region_cap = D.region_cap;
+  ctx->region_count = ctrl + DC_COUNT + which * GVPM_MAX_PEERS;
+  ctx->built = false;
+  ++ctx->state_gen;
+  if (D.n_peers > 2 && ctx->kept_fraction_hint >= 0.5) ctx->kept_fraction_hint = 0.25;   // most regions are mostly empty
+  rc = build_frustum(ctx, radius, n_kept);
+  if (rc) return rc;
+  // a peer that never signalled (k_flag_wait timed out) or a region overflow: visible once the stream has drained; the
+  // gathers check at their own synchronisation point (gvpm_dispatch_status)
+  return GVPM_OK;
+}
+
+int gvpm_dispatch_release(gvpm_ctx *ctx, int which) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  cudaSetDevice(ctx->device);
+  FlagSetParams F{};
+  F.n = D.n_peers;
+  F.value = D.gen_build[which];
+  for (int s = 0; s < D.n_peers; ++s) F.dst[s] = D.peer_ctrl[s] + DC_FREED + which * GVPM_MAX_PEERS + D.self;
+  launch_flag_set(F, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return GVPM_OK;
+}
+
+int gvpm_dispatch_join(gvpm_ctx *ctx) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  cudaSetDevice(ctx->device);
+  CK(cudaEventRecord(D.ev_src, ctx->push_kernel_stream));
+  CK(cudaStreamWaitEvent(ctx->stream, D.ev_src, 0));
+  return GVPM_OK;
+}
+
+int gvpm_dispatch_status(gvpm_ctx *ctx, uint32_t counts[GVPM_MAX_PEERS], int which) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->push_kernel_stream));
+  uint32_t h[DC_OCC];
+  CK(cudaMemcpy(h, D.ctrl.p, sizeof(h), cudaMemcpyDeviceToHost));
+  if (counts) for (int s = 0; s < GVPM_MAX_PEERS; ++s) counts[s] = s < D.n_peers ? h[DC_COUNT + which * GVPM_MAX_PEERS + s] : 0u;
+  if (h[DC_TIMEOUT]) return fail(ctx, GVPM_ERR_CUDA, "photon dispatch: a peer never signalled (flag wait timed out)");
+  if (h[DC_OVERFLOW]) return fail(ctx, GVPM_ERR_INVALID, "photon dispatch: inbox region overflow");
+  return GVPM_OK;
 }
 
 int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes) {
@@ -1712,6 +2001,10 @@ int gvpm_dump_neighbours_bre(gvpm_ctx *ctx, uint64_t *offsets, uint32_t *idx, si
   CK(cudaMemsetAsync(ctx->work_counter.p, 0, 16, ctx->stream));
   CK(launch_bre_traverse(P, true, ctx->sm_count, ctx->stream));
   ctx->launches += 1;
+  if (ctx->aos_override) {   // dispatched set: report the photons by their index in the whole set
+    launch_translate_idx(ctx->nbr_idx.as<uint32_t>(), total, ctx->aos_override, ctx->stream);
+    ctx->launches += 1;
+  }
   CK(cudaMemcpyAsync(idx, ctx->nbr_idx.p, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return GVPM_OK;

@@ -212,6 +212,31 @@ struct GatherParams {
   unsigned long long dump_cap;
 };
 
+// ---- photon dispatch between ranks (dispatch.cu) -----------------------------------------------------------------------
+struct DispatchParams {
+  PhotonStaging S;                 // this rank's staging arrays (whole-set layout)
+  uint32_t begin, count;           // the slice [begin, begin + count) is dispatched
+  int n_dst;
+  const FrustumGrid *grids;        // [n_dst] device
+  const uint32_t *occ[GVPM_MAX_PEERS];   // local copies of the receivers' occupancy masks
+  float4 *inbox[GVPM_MAX_PEERS];   // receiver d's inbox region of THIS sender (peer-mapped; local for d = self)
+  uint32_t region_cap;             // records per region
+  uint8_t *keepbits;               // [count]
+  uint32_t *block_cnt;             // [n_dst][nb + 1]: counts, then exclusive offsets (+ total at [nb])
+  uint32_t nb;
+  unsigned *overflow;              // set when a region would overflow (cannot happen with region_cap >= count)
+};
+
+struct SignalParams {
+  int n_dst, self;
+  uint32_t nb;
+  const uint32_t *block_cnt;
+  uint32_t *count_dst[GVPM_MAX_PEERS];   // receiver d's count word of THIS sender
+  uint32_t *flag_dst[GVPM_MAX_PEERS];    // receiver d's "pushed" flag of THIS sender
+  uint32_t gen;
+};
+struct FlagSetParams { int n; uint32_t value; uint32_t *dst[GVPM_MAX_PEERS]; };
+
 // ---- on-device generators (generate.cu) -------------------------------------------------------------------------------
 struct RayGenParams {
   gvpm_box_scene scene;

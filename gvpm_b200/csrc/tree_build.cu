@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gvpm_device.cuh"
+#include "frustum_device.cuh"
 
 namespace gvpm {
 
@@ -532,14 +533,6 @@ __global__ void k_pinhole_solve(const double *__restrict__ partial, int nb, floa
   fit[12] = (float)a[12];
   fit[13] = (float)cond;
 }
-// the projection both sides use (photons with q = p - C, rays with q = d): plane coordinates at distance 1 along m
-__device__ __forceinline__ void frustum_project(const float *m, const float *u, const float *v, float qx, float qy, float qz,
-                                                float &x, float &y, float &z) {
-  z = qx * m[0] + qy * m[1] + qz * m[2];
-  const float iz = 1.f / z;
-  x = (qx * u[0] + qy * u[1] + qz * u[2]) * iz;
-  y = (qx * v[0] + qy * v[1] + qz * v[2]) * iz;
-}
 // Pass 2 over the active rays: largest distance of C to a ray's line, smallest cos(d, m), bounds of the projected
 // directions.  stats: [0] delta max, [1] -cos min (as max), [2] -xmin, [3] xmax, [4] -ymin, [5] ymax  (all folded with
 // atomicMax on non-negative-biased float bits: values are stored + 4 to keep them positive)
@@ -575,11 +568,6 @@ __global__ void __launch_bounds__(256) k_pinhole_check(const float4 *__restrict_
 // shared memory per CTA and OR-ed into global memory.  k_frustum_keys drops a photon when no bit under its footprint
 // box is set (no ray can reach it): this is what leaves most of the photon set out of a rank's sort when the image is
 // sharded over GPUs.
-constexpr int kOccRes = 256;
-constexpr int kOccWords = kOccRes * kOccRes / 32;   // 8 KB
-__device__ __forceinline__ int occ_cell(float x, float lo, float inv) {
-  return min(max((int)floorf((x - lo) * inv), 0), kOccRes - 1);
-}
 __global__ void __launch_bounds__(256) k_frustum_mark(const float4 *__restrict__ rays, uint32_t n, const FrustumGrid G,
                                                        uint32_t *__restrict__ occ) {
   __shared__ uint32_t mask[kOccWords];
@@ -607,63 +595,23 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
                                                        uint32_t n, const FrustumGrid G, const uint32_t *__restrict__ occ,
                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                        unsigned *__restrict__ coord_mag, uint32_t *__restrict__ keepmask,
-                                                       uint32_t *__restrict__ block_kept) {
+                                                       uint32_t *__restrict__ block_kept, uint32_t region_cap,
+                                                       const uint32_t *__restrict__ region_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float mag = 0.f;
   bool keep = false;
-  if (i < n) {
+  // dispatched photon sets (dispatch.cu): the index space is one region of region_cap records per sending rank, of which
+  // the first region_count[sender] are filled
+  const bool filled = i < n && (region_cap == 0u || (i % region_cap) < __ldg(region_count + i / region_cap));
+  if (i < n && !filled) {
+    keys[i] = (G.parity_split ? 2u : 1u) * G.n_cells + 1u;
+    vals[i] = i;
+  }
+  if (filled) {
     const float px = pos[(size_t)stride * i], py = pos[(size_t)stride * i + 1], pz = pos[(size_t)stride * i + 2];
     mag = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
-    const float qx = px - G.C[0], qy = py - G.C[1], qz = pz - G.C[2];
-    const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
-    const uint32_t grids = G.parity_split ? 2u : 1u;
-    const uint32_t NEAR = grids * G.n_cells, DROP = NEAR + 1u;
-    uint32_t key;
-    float x, y, z;
-    frustum_project(G.m, G.u, G.v, qx, qy, qz, x, y, z);
-    const float pr = G.pad_r * 1.001f + 1e-6f * rho;
-    if (rho <= 2.f * pr) {
-      key = NEAR;                                   // alpha >= 30 degrees
-    } else if (z < 0.1f * rho) {
-      key = rho <= 6.f * pr ? NEAR : DROP;          // more than 84 degrees off axis: only reachable when very close
-    } else {
-      const float tanT = sqrtf(x * x + y * y);
-      const float ang = atanf(tanT) + asinf(pr / rho) * 1.0005f + 1e-6f;
-      if (ang >= 1.45f) {
-        key = NEAR;
-      } else {
-        const float wfoot = (tanf(ang) - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
-        if (x < G.xmin - wfoot || x > G.xmax + wfoot || y < G.ymin - wfoot || y > G.ymax + wfoot) {
-          key = DROP;
-        } else {
-          int c = 0;
-          while (c < G.classes && wfoot > G.csize[c]) ++c;
-          if (c >= G.classes) {
-            key = NEAR;
-          } else {
-            const float ic = 1.f / G.csize[c];
-            const int nx = (int)G.nx[c], ny = (int)G.ny[c];
-            int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
-            cx = min(max(cx, 0), nx - 1);
-            cy = min(max(cy, 0), ny - 1);
-            // any ray under the photon's footprint box?  (coarse bitmask, conservative: the box is padded by one ulp-ish
-            // margin through wfoot's own 1 % pad)
-            const float oix = kOccRes / fmaxf(G.xmax - G.xmin, 1e-20f), oiy = kOccRes / fmaxf(G.ymax - G.ymin, 1e-20f);
-            const int ox0 = occ_cell(x - wfoot, G.xmin, oix), ox1 = occ_cell(x + wfoot, G.xmin, oix);
-            const int oy0 = occ_cell(y - wfoot, G.ymin, oiy), oy1 = occ_cell(y + wfoot, G.ymin, oiy);
-            bool any = false;
-            for (int yy = oy0; yy <= oy1 && !any; ++yy)
-              for (int w0 = ox0 >> 5; w0 <= (ox1 >> 5); ++w0) {
-                const int b0 = max(ox0 - 32 * w0, 0), b1 = min(ox1 - 32 * w0, 31);
-                const uint32_t bits = (0xffffffffu >> (31 - b1)) & (0xffffffffu << b0);
-                any = any || (__ldg(occ + yy * (kOccRes / 32) + w0) & bits) != 0u;
-              }
-            const uint32_t par = G.parity_split ? ((__ldg(par_src + (size_t)par_stride * i) >> par_shift) & 1u) : 0u;
-            key = any ? par * G.n_cells + G.base[c] + (uint32_t)cy * (uint32_t)nx + (uint32_t)cx : DROP;
-          }
-        }
-      }
-    }
+    const uint32_t key = frustum_key(G, occ, px, py, pz, [&]() { return (__ldg(par_src + (size_t)par_stride * i) >> par_shift) & 1u; });
+    const uint32_t DROP = (G.parity_split ? 2u : 1u) * G.n_cells + 1u;
     keys[i] = key;
     vals[i] = i;
     keep = key != DROP;
@@ -853,11 +801,17 @@ void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t 
 void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, uint32_t stride, const uint32_t *par_src,
                          uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
-                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st) {
+                         uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st, uint32_t region_cap,
+                         const uint32_t *region_count) {
   cudaMemsetAsync(occ, 0, frustum_occ_bytes(), st);
   cudaMemsetAsync(coord_mag, 0, 4, st);
   if (n_rays) k_frustum_mark<<<std::min<uint32_t>((n_rays + 255) / 256, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, n_rays, G, occ);
-  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, par_src, par_stride, par_shift, n, G, occ, keys, vals, coord_mag, keepmask, block_kept);
+  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, par_src, par_stride, par_shift, n, G, occ, keys, vals, coord_mag, keepmask, block_kept, region_cap, region_count);
+}
+// the occupancy mask alone (what a rank publishes to the ranks that send it photons)
+void launch_frustum_mark(const float4 *rays, uint32_t n_rays, const FrustumGrid &G, uint32_t *occ, int sm_count, cudaStream_t st) {
+  cudaMemsetAsync(occ, 0, frustum_occ_bytes(), st);
+  if (n_rays) k_frustum_mark<<<std::min<uint32_t>((n_rays + 255) / 256, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, n_rays, G, occ);
 }
 // scratch: cell_starts_scratch_bytes(n_keys) bytes
 size_t cell_starts_scratch_bytes(uint32_t n_keys) { return 16 + ((size_t)n_keys / 4096 + 2) * sizeof(BigGap); }

@@ -262,6 +262,43 @@ int gvpm_peer_wait_photons(gvpm_ctx *ctx, int which);
  * 0 = cudaMemcpyAsync per field and peer on the copy engines (also the fallback for slices that are not 16-byte
  * aligned in every field). */
 int gvpm_peer_push_mode(gvpm_ctx *ctx, int sm_ctas);
+/* Photon DISPATCH between ranks: the scalable form of the exchange for image-sharded G-BRE iterations (SURVEY.md §8e;
+ * replaces what the reference does with one shared-memory photon map, gvpm.cpp:453 + the BlockScheduler of :999-1052,
+ * when the gather points are split over several GPUs).  Instead of copying every photon to every rank, each rank
+ * classifies the photons of ITS slice against every receiver's perspective grid and ray-occupancy mask (the keep test
+ * of the receiver's own gvpm_build_points_for_rays) and writes the 128-byte gather records of the photons a receiver
+ * can reach straight into that receiver's inbox over NVLink (peer-mapped stores; one fused pack + exchange kernel).
+ * A photon crosses the link once per rank that needs it, and a receiver builds over what it was sent only.
+ *   gvpm_dispatch_export   after gvpm_upload_rays (the rank's own tile rays; they must be concurrent, i.e. a pinhole's
+ *                          primary rays, else GVPM_ERR_UNSUPPORTED - use the gvpm_peer_* exchange): allocates two
+ *                          inboxes of n_peers regions x region_cap records (region_cap >= the largest slice any rank
+ *                          dispatches), publishes the ray fit and the occupancy mask, writes the rank's blob;
+ *   gvpm_dispatch_connect  takes the blobs of all ranks (rank order, own one included).  Contexts of one process (tests,
+ *                          one host thread driving several GPUs) are wired directly, others through CUDA IPC;
+ *   gvpm_dispatch_photons  classifies photons [begin, begin+count) of the selected staging buffer (sized for n_total by
+ *                          gvpm_photon_staging) for search radius `radius` and writes them into inbox `which` of every
+ *                          rank, on an internal highest-priority stream, after the work queued on `after_stream`
+ *                          (NULL = the context's stream) and after every receiver's release of that inbox;
+ *   gvpm_build_dispatched  waits (on the context's stream) until every rank's records for inbox `which` have landed,
+ *                          then builds the perspective grid over them: the gathers (gvpm_gather_bre*) run as after
+ *                          gvpm_build_points_for_rays, with identical neighbour sets and results;
+ *   gvpm_dispatch_release  stream-ordered: the gathers from inbox `which` are done, the senders may refill it;
+ *   gvpm_dispatch_join     the context's stream waits for this rank's dispatches issued so far (end of a timed region);
+ *   gvpm_dispatch_status   synchronises and reports the records received per sender for inbox `which`
+ *                          (counts[GVPM_MAX_PEERS], may be NULL) and any protocol failure (a peer that never signalled).
+ * No host barrier is needed: ordering between ranks goes through generation flags in device memory.  Every rank calls
+ * dispatch / build / release once per iteration and inbox, in the same order. */
+#define GVPM_MAX_PEERS 8
+#define GVPM_DISPATCH_BLOB_BYTES 512
+int gvpm_dispatch_export(gvpm_ctx *ctx, int n_peers, size_t region_cap, void *blob /* [GVPM_DISPATCH_BLOB_BYTES] */);
+int gvpm_dispatch_connect(gvpm_ctx *ctx, const void *blobs /* [n_peers * GVPM_DISPATCH_BLOB_BYTES] */, int n_peers,
+                          int self_index);
+int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin, size_t count, float radius,
+                          void *after_stream);
+int gvpm_build_dispatched(gvpm_ctx *ctx, int which, float radius, uint32_t *n_kept);
+int gvpm_dispatch_release(gvpm_ctx *ctx, int which);
+int gvpm_dispatch_join(gvpm_ctx *ctx);
+int gvpm_dispatch_status(gvpm_ctx *ctx, uint32_t counts[GVPM_MAX_PEERS], int which);
 /* Hilbert sort + implicit 32-ary AABB hierarchy for search radius `radius`
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
