@@ -239,6 +239,8 @@ def cpu_arm(args, inp, seconds):
     """The reference's CPU gather as restated by the oracle (kd layout + AABB hierarchy + stack DFS,
     worker threads pulling ray tiles), on all host cores, on a bounded sample of the same workload."""
     from oracle import binding as ob
+    if "oracle_flags" not in inp:      # BASELINE.md §2: -O3 -march=native, built on the box that is timed (untimed here)
+        inp["oracle_flags"] = ob.prefer_native() if ob._lib is None else "as loaded"
     lib = ob.load()
     from gvpm_b200 import _native as N
     cores = ob.hw_threads()
@@ -249,7 +251,7 @@ def cpu_arm(args, inp, seconds):
     # sample = whole 1024-ray tiles spread evenly over the ray list (every k-th tile)
     n_tiles = max(1, rays.n // 1024)
 
-    def run(tile_ids):
+    def run(tile_ids, threads=None):
         idx = (np.asarray(tile_ids)[:, None] * 1024 + np.arange(1024)[None, :]).reshape(-1)
         idx = idx[idx < rays.n]
         sub = rays.take(idx)
@@ -259,7 +261,7 @@ def cpu_arm(args, inp, seconds):
         tri = inp["tri"]
         rc = lib.gvpm_oracle_bre(tree, C.byref(cph), ph.n, C.byref(cr), 0, sub.n, C.byref(inp["medium"]),
                                  C.byref(inp["cfg"]), tri.ctypes.data_as(N.f32p), tri.size // 9, inp["radius"], 0,
-                                 cores, out.ctypes.data_as(N.f32p), None, None, None, 0, C.byref(ms))
+                                 threads or cores, out.ctypes.data_as(N.f32p), None, None, None, 0, C.byref(ms))
         assert rc >= 0
         return sub.n, ms.value
 
@@ -269,11 +271,22 @@ def cpu_arm(args, inp, seconds):
     want = int(min(n_tiles, max(len(pilot_tiles), rate * seconds / 1024)))
     tiles = np.unique(np.linspace(0, n_tiles - 1, num=want, dtype=np.int64))
     n1, ms1 = run(tiles)
+    # single-thread figure on a slice of the same sample, once per process
+    if "cpu_single" not in inp:
+        k1 = max(2, len(tiles) // max(cores, 1))
+        ns, mss = run(tiles[::max(1, len(tiles) // k1)][:k1], threads=1)
+        inp["cpu_single"] = ns / max(mss, 1e-3) * 1e3
     lib.gvpm_oracle_tree_free(tree)
-    return {"value": n1 / ms1 * 1e3, "unit": "rays/s", "cores": cores, "kind": "port",
+    rate = n1 / ms1 * 1e3
+    r_full = float(inp.get("rays_full_n", rays.n))
+    return {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+            "flags": inp["oracle_flags"], "build_ms": build_ms, "gather_ms_sample": ms1,
+            "single_thread_value": inp["cpu_single"],
+            "iteration_value_including_build": r_full / (build_ms * 1e-3 + r_full / rate),
             "sample": f"{n1} rays ({len(tiles)} of {n_tiles} 1024-ray tiles spread over the image) against all "
                       f"{ph.n} photons; gather only ({ms1:.0f} ms); kd+AABB hierarchy build {build_ms:.0f} ms "
-                      f"single-threaded, not included"}, ms1, n1
+                      f"single-threaded, not included in `value` (iteration_value_including_build adds it to a "
+                      f"whole-image gather at the measured rate)"}, ms1, n1
 
 
 def reference_main(args):
@@ -299,7 +312,7 @@ def reference_main(args):
             "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_tot / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, inp, 1), "cpu_baseline": cb,
+            "config": workload_config(args, inp, max(1, args.gpus)), "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -471,6 +484,8 @@ def technique_config(args, d, world):
 def technique_cpu_arm(args, d, seconds):
     """the oracle restatement of the same gather on all host cores, on a bounded sample of whole 1024-ray tiles"""
     from oracle import binding as ob
+    if "oracle_flags" not in d:      # BASELINE.md §2: -O3 -march=native, built on the box that is timed (untimed here)
+        d["oracle_flags"] = ob.prefer_native() if ob._lib is None else "as loaded"
     cores = ob.hw_threads()
     rays = d["full_rays"] if d.get("full_rays") is not None else d["rays"]
     n_tiles = max(1, rays.n // 1024)

@@ -132,6 +132,12 @@ class Context:
     def dispatch_release(self, which):
         self._ck(self.lib.gvpm_dispatch_release(self.h, which), "gvpm_dispatch_release")
 
+    def measure_read_bandwidth(self, nbytes, reps):
+        """GB/s of `reps` passes of 128-bit loads over an nbytes device buffer (L2 peak when it fits in L2)"""
+        v = C.c_double(0.0)
+        self._ck(self.lib.gvpm_measure_read_bandwidth(self.h, int(nbytes), int(reps), C.byref(v)), "gvpm_measure_read_bandwidth")
+        return float(v.value)
+
     def dispatch_join(self):
         self._ck(self.lib.gvpm_dispatch_join(self.h), "gvpm_dispatch_join")
 

@@ -74,7 +74,7 @@ __device__ __forceinline__ bool solve_quadratic_double(sd a, sd b, sd c, sd &x0,
 }
 
 // cylinder = segment (co, cd, [0, cMaxt]) of radius `radius`; view ray = (vo, vd, maxt = vMaxt)
-__device__ __forceinline__ bool cylinder_intersection(v3 co, v3 cd, sf cMaxt, v3 vo, v3 vd, float vMaxt, sf radius,
+__device__ __noinline__ bool cylinder_intersection(v3 co, v3 cd, sf cMaxt, v3 vo, v3 vd, float vMaxt, sf radius,
                                                       double &tNearOut, double &tFarOut) {
   const v3 d1d2c = cross(vd, cd);
   const sf sinThetaSqr = dot(d1d2c, d1d2c);
@@ -295,9 +295,10 @@ __device__ __forceinline__ BeamKernelRec beam_kernel_null(const GatherParams &P,
 }
 
 // BeamKernelRecord::kernelPDF (3-D optimized): infinite beam from orgBeam along dBeam
+template <bool K1D>
 __device__ __forceinline__ sf beam_kernel_pdf(const GatherParams &P, v3 camO, v3 camD, sf camMaxt, v3 orgBeam,
                                               v3 dBeam, sf newDLength) {
-  if (P.cfg.beam_kernel_1d) return ssqrt(length_sq(cross(camD, dBeam)));
+  if (K1D) return ssqrt(length_sq(cross(camD, dBeam)));
   const sf r(P.radius);
   double tNearBeam, tFarBeam;
   if (!cylinder_intersection(camO, camD, camMaxt, orgBeam, dBeam, INFINITY, r, tNearBeam, tFarBeam)) return sf(0.f);
@@ -335,6 +336,7 @@ __device__ __forceinline__ v3 beam_shift_pos(const GatherParams &P, const BaseRa
 }
 
 // shiftBeam -> shiftBeamDiffuse + diffuseReconnectionPhotonBeam; S / weight keep (0, 1) on failure
+template <bool K1D>
 __device__ __forceinline__ void shift_beam_diffuse(const GatherParams &P, const BeamRec &beam, v3 ok, v3 dk, sf lenK,
                                                    v3 eyeK, sf sensor, sf shiftW, const BeamKernelRec &kRec,
                                                    v3 newPos, v3 &S, sf &weight) {
@@ -375,25 +377,25 @@ __device__ __forceinline__ void shift_beam_diffuse(const GatherParams &P, const 
   const sf lenSqBase = length_sq(beam.o - beam.end), lenSqKernel = length_sq(beam.o - basePos);
   const sf absCosEnd(fabsf(dot(beam.endN, beam.dir).v));
   if (!failed) {
-    const sf GOpNew = sf(1.f) / (newPBDist * newPBDist);
+    const sf GOpNew = frcp(newPBDist * newPBDist);   // radiometric from here on: fast reciprocals (2 ulp), as in the BRE shading
     sPdf = pdfValueSA * GOpNew;
     thr = thr * GOpNew;
     sf pdfBasePos = beam.parentPdf * lenSqBase;
-    if (beam.endOnSurface) pdfBasePos = pdfBasePos / absCosEnd;
-    const sf GOpBase = sf(1.f) / lenSqKernel;
+    if (beam.endOnSurface) pdfBasePos = fdiv(pdfBasePos, absCosEnd);
+    const sf GOpBase = frcp(lenSqKernel);
     pdfBasePos = pdfBasePos * GOpBase;
     if (pdfBasePos.v == 0.f) {
       sPdf = sf(0.f);
     } else {
-      thr = thr / pdfBasePos;
+      thr = thr * frcp(pdfBasePos);
       thr = thr * beam.rrW;
       const MediumRec m = medium_eval(P, sf(0.f), newPBDist);
       if (!P.cfg.long_beams) sPdf = sPdf * m.pdfFailure;
-      thr = thr * (m.T * (sf(1.f) / pdfKernelAndDist));
+      thr = thr * (m.T * frcp(pdfKernelAndDist));
     }
   }
   if (sPdf.v == 0.f) { weight = sf(1.f); return; }
-  const sf shiftKernelPDF = beam_kernel_pdf(P, ok, dk, lenK, beam.o, newPBDir, newPBDist);
+  const sf shiftKernelPDF = beam_kernel_pdf<K1D>(P, ok, dk, lenK, beam.o, newPBDir, newPBDist);
   if (shiftKernelPDF.v == 0.f) { weight = sf(1.f); return; }
   v3 shiftPhotonWeight = beam.prefix * thr;
   const MediumRec mRecShift = medium_eval(P, sf(0.f), shiftW);
@@ -404,19 +406,20 @@ __device__ __forceinline__ void shift_beam_diffuse(const GatherParams &P, const 
   if (P.cfg.use_mis) {
     sf basePdf = beam.parentPdf;
     basePdf = basePdf * lenSqBase;
-    if (beam.endOnSurface) basePdf = basePdf / absCosEnd;
-    basePdf = basePdf / lenSqKernel;
+    if (beam.endOnSurface) basePdf = fdiv(basePdf, absCosEnd);
+    basePdf = fdiv(basePdf, lenSqKernel);
     basePdf = basePdf * pdfKernelAndDist;
     sf offsetPdf = shiftKernelPDF;
     offsetPdf = offsetPdf * sPdf;
     if (offsetPdf.v == 0.f || basePdf.v == 0.f) { weight = sf(1.f); return; }
-    const sf q = sensor * offsetPdf / basePdf;
-    weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
+    const sf q = fdiv(sensor * offsetPdf, basePdf);
+    weight = P.cfg.power_heuristic ? frcp(sf(1.f) + q * q) : frcp(sf(1.f) + q);
   }
 }
 
 // BeamGradRadianceQuery::operator() for one (ray, beam) pair whose kernel record is valid and which
 // passed the filters
+template <bool K1D>
 __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4 *__restrict__ rec, const BaseRay &R,
                                              const BeamRec &beam, const BeamKernelRec &kRec, float *a) {
   const sf r(P.radius);
@@ -433,14 +436,14 @@ __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4
       const v3 ok(s0.x, s0.y, s0.z), dk(s1.x, s1.y, s1.z), eyeK(s2.x, s2.y, s2.z);
       const sf lenK(s0.w), sensor(s1.w), shiftW = kRec.w;
       bool alreadyShift = false;
-      if (P.cfg.use_shift_null && !P.cfg.beam_kernel_1d) {   // "Ignored in case of Beam 1D kernel", :264-265
+      if (P.cfg.use_shift_null && !K1D) {   // "Ignored in case of Beam 1D kernel", :264-265
         const v3 kernelPos = beam.o + beam.dir * kRec.v;
         const sf ZPtoY = length_sq((ok + shiftW * dk) - kernelPos);
         if (ZPtoY < r * r && kRec.w <= lenK) {
           BeamKernelRec kS = beam_kernel_null(P, kRec, beam, ok, dk, sf(P.cfg.epsilon), lenK);
           if (kS.valid) {
             // shiftNull3D
-            kS.contrib = kS.contrib * (kS.pdf() / kRec.pdf());
+            kS.contrib = kS.contrib * fdiv(kS.pdf(), kRec.pdf());
             S = kS.contrib * eyeK;
             weight = sf(0.5f);
             if (P.cfg.use_mis) {
@@ -448,24 +451,24 @@ __device__ __forceinline__ void beam_functor(const GatherParams &P, const float4
               if (offsetPdf.v == 0.f || basePdf.v == 0.f) {
                 weight = sf(1.f);
               } else {
-                const sf q = sensor * (offsetPdf / basePdf);
-                weight = P.cfg.power_heuristic ? sf(1.f) / (sf(1.f) + q * q) : sf(1.f) / (sf(1.f) + q);
+                const sf q = sensor * fdiv(offsetPdf, basePdf);
+                weight = P.cfg.power_heuristic ? frcp(sf(1.f) + q * q) : frcp(sf(1.f) + q);
               }
             }
             alreadyShift = true;
           }
         }
       }
-      if (!alreadyShift && kRec.w <= lenK && P.cfg.beam_kernel_1d) {   // newShiftBeam, :311-317
+      if (K1D && !alreadyShift && kRec.w <= lenK) {   // newShiftBeam, :311-317
         const v3 offsetPos = beam_shift_pos_1d(R, ok, dk, beam.o, beam.dir, kRec.w, kRec.u);
-        shift_beam_diffuse(P, beam, ok, dk, lenK, eyeK, sensor, shiftW, kRec, offsetPos, S, weight);
+        shift_beam_diffuse<K1D>(P, beam, ok, dk, lenK, eyeK, sensor, shiftW, kRec, offsetPos, S, weight);
       } else if (!alreadyShift && kRec.w <= lenK) {
         const sf dd = dot(beam.o - ok, dk);
         const sf minDistSqr = length_sq(beam.o - (ok + dd * dk));
         if (minDistSqr.v > 0.f) {
           const v3 u = (beam.o + beam.dir * kRec.v) - (R.o + kRec.w * R.d);
           const v3 offsetPos = beam_shift_pos(P, R, ok, dk, kRec.w, u, shiftW);
-          shift_beam_diffuse(P, beam, ok, dk, lenK, eyeK, sensor, shiftW, kRec, offsetPos, S, weight);
+          shift_beam_diffuse<K1D>(P, beam, ok, dk, lenK, eyeK, sensor, shiftW, kRec, offsetPos, S, weight);
         } else {
           weight = sf(1.f);
         }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
       const int jj = j < nr ? j : 0;
       const float4 b0 = S.ray[jj][0], b1 = S.ray[jj][1], b2 = S.ray[jj][2], b3 = S.ray[jj][3];
       ox[j] = b0.x; oy[j] = b0.y; oz[j] = b0.z; mint[j] = b0.w;
-      dx[j] = b1.x; dy[j] = b1.y; dz[j] = b1.z; elen[j] = b2.w;
+      dx[j] = b1.x; dy[j] = b1.y; dz[j] = b1.z; elen[j] = fmaxf(b2.w, b1.w);   // edge length / maxt, whichever is larger
       par[j] = ((int)__float_as_uint(b3.y) + (int)__float_as_uint(b3.z)) % 2;
       eid[j] = (int)__float_as_uint(b3.w);
       qn[j] = 0;
@@ -220,6 +220,33 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
             const float sin2 = cx * cx + cy * cy + cz * cz;
             const float ad = (b0.x - ox[j]) * cx + (b0.y - oy[j]) * cy + (b0.z - oz[j]) * cz;
             bool ok = (gm >> j & 1) && (sin2 < 1e-6f || ad * ad < rpad2 * sin2 * 1.001f);
+            if (ok && sin2 >= 1e-2f) {
+              // Where can the beam run inside the cylinder around the camera LINE?  Around the beam parameter tc of the
+              // lines' closest approach, at most r / sin(theta) to either side: the chord [tN, tF].  The kernel record's
+              // tNear - the entry point, moved to an end cap when the camera SEGMENT starts or ends inside the chord
+              // (cylinder_intersection) - lies in it, as does the 1-D kernel's closest-approach parameter, and only the
+              // sub-beam that holds that parameter keeps the pair (ownership rule of k_beam_shade; sppm's per-sub-beam
+              // techniques intersect the sub-beam's own piece of the chord): a sub-beam the chord misses cannot
+              // contribute, nor can a chord that lies entirely in front of or behind the camera segment.  Relaxed
+              // arithmetic: the half-length is the largest a chord can have and is padded for the rounding of tc
+              // (amplified by 1 / sin^2); pairs closer to parallel than ~6 degrees are kept as they are.
+              const float wx = b0.x - ox[j], wy = b0.y - oy[j], wz = b0.z - oz[j];
+              const float a = dx[j] * b1.x + dy[j] * b1.y + dz[j] * b1.z;
+              const float wd = wx * dx[j] + wy * dy[j] + wz * dz[j];
+              const float wb = wx * b1.x + wy * b1.y + wz * b1.z;
+              const float iA = 1.f / sin2;                      // sin2 = |d x b|^2 = 1 - (d.b)^2 for unit directions
+              const float tc = (wd * a - wb) * iA;
+              const float wmag = fabsf(wx) + fabsf(wy) + fabsf(wz);
+              const float h = (P.radius + 4.f * fpad) * sqrtf(iA) * 1.01f + (1e-5f * iA) * (wmag + 1.f) + 1e-4f * fabsf(tc);
+              const float tN = tc - h, tF = tc + h;
+              const uint32_t flags = __float_as_uint(sb.w);
+              if (!(flags & 2u) && tN > sb.y) ok = false;    // chord entirely behind this sub-beam
+              if (!(flags & 1u) && tF < sb.x) ok = false;    // ... or entirely in front of it
+              // camera distance of the beam point at the two chord ends (linear in between)
+              const float zN = wd + tN * a, zF = wd + tF * a;
+              const float padZ = 1e-4f * (1.f + fabsf(zN) + fabsf(zF)) + 16.f * fpad;
+              if (fmaxf(zN, zF) + padZ < mint[j] || fminf(zN, zF) - padZ > elen[j]) ok = false;
+            }
             // the filters only drop pairs (they never make one valid): keep them out of the pair list unless
             // the parity dump needs the geometric set
             if (P.beam_prefilter) {
@@ -261,9 +288,11 @@ constexpr int kBeamRing = 64;
 struct BeamShadeShared {
   uint32_t ray[kBeamRing], beam[kBeamRing];
   float f[9][kBeamRing];   // v, w, pdfKernel, pdfEdgeFailure, weightKernel, u, contrib.xyz
+  float t[32][GVPM_OUT_FLOATS + 2];   // a batch's results, transposed reduction (odd row stride: no bank conflicts)
 };
 
-__device__ __forceinline__ void beam_shade_batch(const GatherParams &P, const BeamShadeShared &Q, uint32_t head, uint32_t cnt,
+template <bool K1D>
+__device__ __forceinline__ void beam_shade_batch(const GatherParams &P, BeamShadeShared &Q, uint32_t head, uint32_t cnt,
                                                  int lane) {
   float a[GVPM_OUT_FLOATS];
 #pragma unroll
@@ -281,28 +310,32 @@ __device__ __forceinline__ void beam_shade_batch(const GatherParams &P, const Be
     kRec.weightKernel = sf(Q.f[4][e]); kRec.u = sf(Q.f[5][e]);
     kRec.contrib = v3(Q.f[6][e], Q.f[7][e], Q.f[8][e]);
     kRec.valid = true;
-    beam_functor(P, rec, R, beam, kRec, a);
+    beam_functor<K1D>(P, rec, R, beam, kRec, a);
   }
+  // per-ray sums over runs of equal ray id, transposed through shared memory: lane j walks column j of the 32 x 27
+  // results in pair order and adds a run's sum with one coalesced atomic instruction (a rolled loop: the 27 x 5
+  // shuffle scan the other shade kernels use is 17 KB of code, and this kernel is bound by instruction fetch)
   const uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
   const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kprev != key);
-  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const bool same = lane - off >= start;
-#pragma unroll
-    for (int j = 0; j < GVPM_OUT_FLOATS; ++j) {
-      const float vu = __shfl_up_sync(0xffffffffu, a[j], off);
-      if (same) a[j] += vu;
+  for (int j = 0; j < GVPM_OUT_FLOATS; ++j) Q.t[lane][j] = a[j];
+  Q.t[lane][GVPM_OUT_FLOATS] = __uint_as_float(key);
+  __syncwarp();
+  if (lane < GVPM_OUT_FLOATS) {
+    float acc = 0.f;
+#pragma unroll 1
+    for (uint32_t p = 0; p < cnt; ++p) {
+      acc += Q.t[p][lane];
+      if (p + 1 == cnt || (heads >> (p + 1) & 1u)) {
+        if (acc != 0.f) atomicAdd(P.out + (size_t)__float_as_uint(Q.t[p][GVPM_OUT_FLOATS]) * GVPM_OUT_FLOATS + lane, acc);
+        acc = 0.f;
+      }
     }
   }
-  if (valid && (lane == 31 || (heads >> (lane + 1) & 1u))) {
-    float *o = P.out + (size_t)key * GVPM_OUT_FLOATS;
-#pragma unroll
-    for (int j = 0; j < GVPM_OUT_FLOATS; ++j)
-      if (a[j] != 0.f) atomicAdd(o + j, a[j]);
-  }
+  __syncwarp();
 }
 
+template <bool K1D>
 __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ GatherParams P) {
   __shared__ BeamShadeShared ring[4];
   const int lane = threadIdx.x & 31;
@@ -311,13 +344,17 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
   unsigned long long total = *P.pair_counter;
   if (total > P.pair_cap) total = P.pair_cap;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < total;
-       i0 += stride) {
+  // one loop, one copy of each phase (the kernel's code size is what bounds it: instruction-fetch stalls)
+  unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (;;) {
+    const bool more = i0 < total;
+    if (!more && qn == 0u) break;
     const unsigned long long i = i0 + lane;
+    i0 += stride;
     bool shade = false;
     uint32_t key = 0, bi = 0;
     BeamKernelRec kRec;
-    if (i < total) {
+    if (more && i < total) {
       const uint2 pr = P.pairs[i];
       key = pr.x;
       const float4 sb = ldg4(P.subs + pr.y);
@@ -328,7 +365,7 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
       const BeamRec beam = load_beam(P, bi);
       double tNear = 0.0;
       bool owner;
-      if (P.cfg.beam_kernel_1d) {
+      if (K1D) {
         // 1-D kernel: the sub-beam [t1, t2] accepts v in (t1, t2] (beams_struct.h:299-301); first / last sub-beam
         // take the rest of (0, length)
         kRec = beam_kernel_eval_1d(P, beam, R);
@@ -365,7 +402,7 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
         }
       }
     }
-    if (P.dump_pairs) continue;
+    if (P.dump_pairs) { if (!more) break; continue; }
     const uint32_t m = __ballot_sync(0xffffffffu, shade);
     if (shade) {
       const uint32_t e = (head + qn + __popc(m & ((1u << lane) - 1u))) & (kBeamRing - 1);
@@ -376,14 +413,14 @@ __global__ void __launch_bounds__(128, 3) k_beam_shade(const __grid_constant__ G
     }
     qn += __popc(m);
     __syncwarp();
-    if (qn >= 32u) {
-      beam_shade_batch(P, Q, head, 32u, lane);
-      head = (head + 32u) & (kBeamRing - 1);
-      qn -= 32u;
+    if (qn >= 32u || (!more && qn > 0u)) {   // a full batch, or what is left once the pair list is exhausted
+      const uint32_t take = min(qn, 32u);
+      beam_shade_batch<K1D>(P, Q, head, take, lane);
+      head = (head + take) & (kBeamRing - 1);
+      qn -= take;
       __syncwarp();
     }
   }
-  if (!P.dump_pairs && qn > 0u) beam_shade_batch(P, Q, head, qn, lane);
 }
 
 // sppm primal photon beams (volumePhotonBeamPass, sppm.cpp:823-860): one thread per (camera beam, sub-beam) candidate
@@ -480,13 +517,14 @@ cudaError_t launch_beam_traverse(const GatherParams &P, int sm_count, cudaStream
 cudaError_t launch_beam_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream) {
   if (total == 0) return cudaSuccess;
   if (g_bs_blocks == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_bs_blocks, k_beam_shade, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_bs_blocks, k_beam_shade<false>, 128, 0);
     if (g_bs_blocks < 1) g_bs_blocks = 1;
   }
   unsigned long long need = (total + 127) / 128;
   unsigned long long grid = (unsigned long long)sm_count * g_bs_blocks * 4;
   if (grid > need) grid = need;
-  k_beam_shade<<<(unsigned)grid, 128, 0, stream>>>(P);
+  if (P.cfg.beam_kernel_1d) k_beam_shade<true><<<(unsigned)grid, 128, 0, stream>>>(P);
+  else k_beam_shade<false><<<(unsigned)grid, 128, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

@@ -471,23 +471,31 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
         x = (L.dx * G.u[0] + L.dy * G.u[1] + L.dz * G.u[2]) * iz;
         y = (L.dx * G.v[0] + L.dy * G.v[1] + L.dz * G.v[2]) * iz;
       }
-      for (int c = 0; c < G.classes; ++c) {
-        const uint32_t nx = G.nx[c], ny = G.ny[c], base = G.base[c];
-        // empty class (in every grid): nothing to do (warp-uniform)
-        bool empty = true;
-        for (uint32_t g = 0; g < nGridsBuilt; ++g)
-          empty = empty && __ldg(P.cell_start + g * G.n_cells + base) == __ldg(P.cell_start + g * G.n_cells + base + nx * ny);
-        if (empty) continue;
+      // One loop over the footprint classes, then the NEAR bucket (photons too close to C for any class: every ray
+      // tests them), then one empty round that flushes what is left: a single copy of the candidate loop and of
+      // flush_candidates (this kernel's instruction-fetch stalls grow with its code size).
+      for (int c = 0; c <= G.classes + 1; ++c) {
+        const bool isNear = c == G.classes, isLast = c == G.classes + 1;
+        const int cc = min(c, G.classes - 1);
+        const uint32_t nx = G.nx[cc], ny = G.ny[cc], base = G.base[cc];
+        if (!isNear && !isLast) {
+          // empty class (in every grid): nothing to do (warp-uniform)
+          bool empty = true;
+          for (uint32_t g = 0; g < nGridsBuilt; ++g)
+            empty = empty && __ldg(P.cell_start + g * G.n_cells + base) == __ldg(P.cell_start + g * G.n_cells + base + nx * ny);
+          if (empty) continue;
+        }
         int x0 = 0, x1 = 0, y0 = 0, y1 = -1;
-        if (active) {
-          const float ic = 1.f / G.csize[c];
+        if (active && !isNear && !isLast) {
+          const float ic = 1.f / G.csize[cc];
           int cx = (int)floorf((x - G.gx0) * ic), cy = (int)floorf((y - G.gy0) * ic);
           cx = min(max(cx, 0), (int)nx - 1);
           cy = min(max(cy, 0), (int)ny - 1);
           x0 = max(cx - 1, 0); x1 = min(cx + 1, (int)nx - 1);
           y0 = max(cy - 1, 0); y1 = min(cy + 1, (int)ny - 1);
         }
-        for (uint32_t pass = 0; pass < nPass; ++pass) {
+        const uint32_t nPassC = (isNear || isLast) ? 1u : nPass;
+        for (uint32_t pass = 0; pass < nPassC; ++pass) {
           const uint32_t gbase = (onlyMine ? (uint32_t)parity : pass) * G.n_cells + base;
           uint32_t s0 = 0u, s1 = 0u, s2 = 0u, n0 = 0u, n1 = 0u, n2 = 0u;
           auto row = [&](int yy, uint32_t &sr, uint32_t &nr) {
@@ -498,12 +506,13 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
           if (y0 <= y1) row(y0, s0, n0);
           if (y0 + 1 <= y1) row(y0 + 1, s1, n1);
           if (y0 + 2 <= y1) row(y0 + 2, s2, n2);
+          if (isNear && active) { s0 = nearBeg; n0 = nearEnd - nearBeg; }
           const uint32_t n01 = n0 + n1, tot = n01 + n2;
-          const uint32_t wmax = __reduce_max_sync(0xffffffffu, tot);
+          const uint32_t wmax = isLast ? 1u : __reduce_max_sync(0xffffffffu, tot);
           // four candidates per step: their loads are issued together (each lane reads its own cells; neighbouring
           // pixels share them, so most of these hit L1)
           for (uint32_t j0 = 0; j0 < wmax; j0 += kTileBatch) {
-            if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
+            if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ || (isLast && qn > 0u))) flush();
 #pragma unroll
             for (uint32_t u0 = 0; u0 < (uint32_t)kTileBatch; u0 += 4) {
               float4 ph[4];
@@ -521,14 +530,6 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
           }
         }
       }
-      // photons too close to C for any footprint class: every ray tests them
-      for (uint32_t j0 = nearBeg; j0 < nearEnd; j0 += kTileBatch) {
-        if (__any_sync(0xffffffffu, qn + (uint32_t)kTileBatch > (uint32_t)kTileQ)) flush();
-        const uint32_t je = min(j0 + (uint32_t)kTileBatch, nearEnd);
-        if (active)
-          for (uint32_t j = j0; j < je; ++j) test(ldg4(P.planes + j), j);
-      }
-      if (__any_sync(0xffffffffu, qn > 0)) flush();
     }
     if (P.counts && have) {
       P.counts[2 * (size_t)ray] = nGeom;

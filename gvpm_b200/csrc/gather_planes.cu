@@ -66,9 +66,10 @@ __global__ void k_plane_leaf_boxes(const float4 *__restrict__ planes, uint32_t n
 constexpr int kPlWarps = 4;               // 128 rays per CTA
 constexpr int kPlChunk = 512;             // planes staged per chunk (16 leaves)
 constexpr int kPlLeaves = kPlChunk / 32;
-constexpr int kPlQCap = 160;              // candidate queue entries per lane
+constexpr int kPlQCap = 96;               // candidate queue entries per lane (52 KB of shared memory per CTA: 4 CTAs per SM)
 constexpr int kPlSub = 64;                // planes tested between queue-level checks
 static_assert(kPlQCap > kPlSub, "queue must hold one sub-step");
+static_assert(kPlWarps == 4 && (kPlChunk / kPlWarps) % 32 == 0, "the bundle test splits a chunk over four warps");
 
 struct PlaneShared {
   float4 tst[kPlChunk][3];                       // Q0-Q2 of the staged chunk
@@ -77,7 +78,8 @@ struct PlaneShared {
   float bounds[6];
   float tred[kPlWarps][8];                       // ray-bundle reduction: xmin, xmax, ymin, ymax, delta, mint min, maxt max, cos min
   float bundle[8];
-  uint16_t live[kPlChunk];                       // planes of the chunk the bundle test keeps (chunk-relative)
+  uint16_t live[kPlChunk];                       // planes of the chunk the bundle test keeps (chunk-relative, ascending)
+  uint16_t liveW[kPlWarps][kPlChunk / kPlWarps]; // per-warp part of it
   uint32_t nLive;
   uint32_t amask[kPlWarps];
   uint32_t leafMask;
@@ -151,7 +153,7 @@ __device__ __forceinline__ bool plane_candidate(const float4 q0, const float4 q1
 }
 
 template <bool kDump>
-__global__ void __launch_bounds__(kPlWarps * 32, 3) k_plane_gather(const __grid_constant__ GatherParams P) {
+__global__ void __launch_bounds__(kPlWarps * 32, 4) k_plane_gather(const __grid_constant__ GatherParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PlaneShared &S = *reinterpret_cast<PlaneShared *>(smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -349,21 +351,27 @@ __global__ void __launch_bounds__(kPlWarps * 32, 3) k_plane_gather(const __grid_
           if ((leafMask >> (p >> 5) & 1u) && gi < nPl) S.tst[p][k] = ldg4(Q + (size_t)k * nPl + gi);
         }
         __syncthreads();
-        // bundle test: planes no ray of the block can meet are dropped for the whole block (one thread per plane)
-        if (threadIdx.x == 0) S.nLive = 0u;
-        __syncthreads();
+        // bundle test: planes no ray of the block can meet are dropped for the whole block (one thread per plane).
+        // Warp w tests the w-th quarter of the chunk and lists its survivors in plane order; the four lists are then
+        // concatenated, so the order of the live list (hence every ray's accumulation order) is the plane order.
         {
           const int nIn = (int)min((uint32_t)kPlChunk, nPl - chunkBase);
-          for (int p0 = 0; p0 < kPlChunk; p0 += kPlWarps * 32) {
-            const int p = p0 + threadIdx.x;
+          constexpr int kPerWarp = kPlChunk / kPlWarps;
+          uint32_t cntW = 0;
+          for (int p0 = 0; p0 < kPerWarp; p0 += 32) {
+            const int p = w * kPerWarp + p0 + lane;
             bool keep = p < nIn && (leafMask >> (p >> 5) & 1u);
             if (keep && bundleOk) keep = !plane_bundle_reject(S.tst[p][0], S.tst[p][1], S.tst[p][2], c0, dk, bdelta);
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            uint32_t base = 0;
-            if (lane == 0 && m) base = atomicAdd(&S.nLive, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) S.live[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+            if (keep) S.liveW[w][cntW + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+            cntW += __popc(m);
           }
+          if (lane == 0) S.amask[w] = cntW;
+          __syncthreads();
+          uint32_t off = 0;
+          for (int i = 0; i < w; ++i) off += S.amask[i];
+          for (uint32_t j = lane; j < cntW; j += 32) S.live[off + j] = S.liveW[w][j];
+          if (threadIdx.x == 0) S.nLive = S.amask[0] + S.amask[1] + S.amask[2] + S.amask[3];
         }
         __syncthreads();
         const int nLive = (int)S.nLive;

@@ -32,6 +32,7 @@ void launch_dispatch(const DispatchParams &P, cudaStream_t st);
 void launch_dispatch_signal(const SignalParams &P, cudaStream_t st);
 void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *timeout, cudaStream_t st);
 void launch_flag_set(const FlagSetParams &P, cudaStream_t st);
+void launch_l2_read(const void *p, size_t bytes, int reps, unsigned *sink, int sm_count, cudaStream_t st);
 void launch_translate_idx(uint32_t *idx, unsigned long long n, const float4 *aos, cudaStream_t st);
 void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
                          uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st);
@@ -1751,6 +1752,25 @@ int gvpm_dispatch_status(gvpm_ctx *ctx, uint32_t counts[GVPM_MAX_PEERS], int whi
   if (counts) for (int s = 0; s < GVPM_MAX_PEERS; ++s) counts[s] = s < D.n_peers ? h[DC_COUNT + which * GVPM_MAX_PEERS + s] : 0u;
   if (h[DC_TIMEOUT]) return fail(ctx, GVPM_ERR_CUDA, "photon dispatch: a peer never signalled (flag wait timed out)");
   if (h[DC_OVERFLOW]) return fail(ctx, GVPM_ERR_INVALID, "photon dispatch: inbox region overflow");
+  return GVPM_OK;
+}
+
+int gvpm_measure_read_bandwidth(gvpm_ctx *ctx, size_t bytes, int reps, double *gb_per_s) {
+  if (!ctx || !gb_per_s || bytes < 4096 || bytes > (1ull << 32) || reps < 1) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(ctx->poisson_io.reserve(bytes + 256));
+  CK(cudaMemsetAsync(ctx->poisson_io.p, 1, bytes + 256, ctx->stream));
+  unsigned *sink = (unsigned *)(ctx->poisson_io.as<char>() + bytes);
+  launch_l2_read(ctx->poisson_io.p, bytes, 2, sink, ctx->sm_count, ctx->stream);   // warm: the buffer is in L2 (if it fits)
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  launch_l2_read(ctx->poisson_io.p, bytes, reps, sink, ctx->sm_count, ctx->stream);
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+  ctx->launches += 2;
+  *gb_per_s = (double)(bytes / 16 * 16) * reps / ((double)ms * 1e-3) / 1e9;
   return GVPM_OK;
 }
 

@@ -207,6 +207,27 @@ __global__ void __launch_bounds__(256) k_pack_samples(const SampleStaging S, uin
   }
 }
 
+// ---- measurement aid: read bandwidth of a buffer that fits in L2 (the roofline's L2 denominator) --------------------------
+// every CTA streams the whole buffer `reps` times with 128-bit loads, 4 in flight per thread; the xor of everything read
+// goes to `sink` so that nothing is optimised away
+__global__ void __launch_bounds__(256) k_l2_read(const uint4 *__restrict__ p, uint32_t n16, int reps, unsigned *__restrict__ sink) {
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (int r = 0; r < reps; ++r) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+      const uint4 a = __ldcg(p + i), b = __ldcg(p + i + stride), c = __ldcg(p + i + 2 * stride), d = __ldcg(p + i + 3 * stride);
+      acc.x ^= a.x ^ b.x ^ c.x ^ d.x; acc.y ^= a.y ^ b.y ^ c.y ^ d.y;
+      acc.z ^= a.z ^ b.z ^ c.z ^ d.z; acc.w ^= a.w ^ b.w ^ c.w ^ d.w;
+    }
+    for (; i < n16; i += stride) { const uint4 a = __ldcg(p + i); acc.x ^= a.x; acc.y ^= a.y; acc.z ^= a.z; acc.w ^= a.w; }
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) atomicAdd(sink, 1u);
+}
+void launch_l2_read(const void *p, size_t bytes, int reps, unsigned *sink, int sm_count, cudaStream_t st) {
+  k_l2_read<<<sm_count * 8, 256, 0, st>>>((const uint4 *)p, (uint32_t)(bytes / 16), reps, sink);
+}
+
 // ---- launchers ------------------------------------------------------------------------------------------------------
 void launch_pack_beams(const BeamStaging &S, uint32_t n, float4 *rec, float *len, cudaStream_t st) {
   if (n) k_pack_beams<<<(n + 255) / 256, 256, 0, st>>>(S, n, rec, len);

@@ -70,19 +70,22 @@ __device__ __forceinline__ bool plane_shift_intersection(v3 o, v3 d, sf mint, sf
 __device__ __forceinline__ void plane_functor(const GatherParams &P, const float4 *__restrict__ rec, v3 rayD,
                                               const PlaneRec &pl, const PlaneIts &bRec, float *a) {
   const v3 sigS(P.sigma_s[0], P.sigma_s[1], P.sigma_s[2]);
-  // getContrib0D
+  // getContrib0D.  From here on every quotient is radiometric only (no decision hangs on it; the shifted intersection
+  // test below keeps its strictly rounded form): fast reciprocal / division (2 ulp), as in the BRE shading
   const MediumRec mCam = medium_eval(P, sf(0.f), bRec.tCam), mRec0 = medium_eval(P, sf(0.f), bRec.t0),
                   mRec1 = medium_eval(P, sf(0.f), bRec.t1);
   const sf phaseBase = phase_eval(P, -pl.w1, -rayD);
-  const sf invJacBase = plane_inv_jacobian(pl.w0, pl.w1, rayD);
+  const sf absBase = abs_dot(pl.w0, cross(pl.w1, rayD));
+  const sf invJacBase = frcp(absBase);   // plane_inv_jacobian
   v3 baseContrib = (((sigS * mCam.T) * sigS) * pl.flux) * phaseBase;
   baseContrib = baseContrib * (mRec1.T * mRec0.T);
-  baseContrib = baseContrib * (sf(1.f) / mRec0.pdfFailure);
-  baseContrib = baseContrib * (sf(1.f) / mRec1.pdfFailure);
+  baseContrib = baseContrib * frcp(mRec0.pdfFailure);
+  baseContrib = baseContrib * frcp(mRec1.pdfFailure);
   baseContrib = baseContrib * invJacBase;
   acc_add(a, 0, baseContrib);
   const sf w0Dot = dot(pl.w0, pl.w1);
   const sf sinW = ssqrt(sf(1.f) - (w0Dot * w0Dot));
+  const sf invT0 = frcp(mRec0.T), invT1 = frcp(mRec1.T), invPhaseBase = frcp(phaseBase);
   float Sx[4], Sy[4], Sz[4], Wk[4];  // staged so that a[] keeps static indices (registers)
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
@@ -102,24 +105,24 @@ __device__ __forceinline__ void plane_functor(const GatherParams &P, const float
         const MediumRec mRec1S = medium_eval(P, sf(0.f), t1New), mRec0S = medium_eval(P, sf(0.f), t0New);
         const sf absNew = abs_dot(pl.w0, cross(newW1, sd_));
         v3 thr = baseContrib;
-        thr = thr * (mRec0S.T / mRec0.T);
-        thr = thr * (mRec1S.T / mRec1.T);
-        thr = thr * (sf(1.f) / invJacBase);
-        thr = thr * (sf(1.f) / absNew);
+        thr = thr * (mRec0S.T * invT0);
+        thr = thr * (mRec1S.T * invT1);
+        thr = thr * absBase;            // 1 / invJacBase
+        thr = thr * frcp(absNew);
         sf jac = invJacBase;
         jac = jac * absNew;
-        jac = jac / (t1New / bRec.t1);
-        if (pl.edgeID != 1) jac = jac / (t0New / bRec.t0);
+        jac = jac * (bRec.t1 * frcp(t1New));                       // / (t1New / bRec.t1)
+        if (pl.edgeID != 1) jac = jac * (bRec.t0 * frcp(t0New));   // / (t0New / bRec.t0)
         const sf phaseNew = phase_eval(P, -newW1, -sd_);
         thr = thr * phaseNew;
-        thr = thr * (sf(1.f) / phaseBase);
+        thr = thr * invPhaseBase;
         weight = sf(0.5f);
         S = thr * jac;
         if (P.cfg.use_mis) {
           const sf basePdf = mRec0.pdfSuccess * mRec1.pdfSuccess * phaseBase;
           const sf offsetPdf = mRec0S.pdfSuccess * mRec1S.pdfSuccess * phaseNew;
           if (offsetPdf.v == 0.f || basePdf.v == 0.f) weight = sf(1.f);
-          else weight = sf(1.f) / (sf(1.f) + sensor * jac * offsetPdf / basePdf);
+          else weight = frcp(sf(1.f) + fdiv(sensor * jac * offsetPdf, basePdf));
         }
       }
     }

@@ -89,6 +89,33 @@ int gvpm_host_bre_iteration(void *h, int it, const gvpm_photon_soa *ph, size_t n
   try { ((VolumeGatherB200 *)h)->computeVolumeGradientPhotonBRE(it, ph, n, rays, nRays, nbPathVolume); return 0; }
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
 }
+// the other three gather drivers of the gvpm plugin (gvpm.cpp:880-986, 782-878, 1081-1203)
+int gvpm_host_beams_iteration(void *h, int it, const gvpm_beam_soa *beams, size_t n, const gvpm_ray_soa *rays, size_t nRays,
+                              size_t nbPathBeams, char *err, size_t errlen) {
+  try { ((VolumeGatherB200 *)h)->computeVolumeGradientBeams(it, beams, n, rays, nRays, nbPathBeams); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+int gvpm_host_planes_iteration(void *h, int it, const gvpm_plane_soa *planes, size_t n, const gvpm_ray_soa *rays,
+                               size_t nRays, size_t nbPathBeams, char *err, size_t errlen) {
+  try { ((VolumeGatherB200 *)h)->computeVolumeGradientPlanes(it, planes, n, rays, nRays, nbPathBeams); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+int gvpm_host_vpm_iteration(void *h, int it, const gvpm_photon_soa *ph, size_t n, const gvpm_ray_soa *rays, size_t nRays,
+                            const gvpm_vpm_sample_soa *samples, size_t nSamples, int nbCameraSamples, float maxRadius,
+                            size_t nbPathVolume, uint32_t *mvol, char *err, size_t errlen) {
+  try {
+    ((VolumeGatherB200 *)h)->computeVolumeGradientPhoton(it, ph, n, rays, nRays, samples, nSamples, nbCameraSamples, maxRadius,
+                                                        nbPathVolume, mvol);
+    return 0;
+  } catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+// VPM is not an APA estimator: accumulators / totalEmittedVolume (gvpm.cpp:487-491); out = [h][w][27]
+int gvpm_host_normalized_accumulators(void *h, float *out, size_t n) {
+  const std::vector<float> a = ((VolumeGatherB200 *)h)->normalizedAccumulators();
+  if (n != a.size()) return -1;
+  memcpy(out, a.data(), n * sizeof(float));
+  return 0;
+}
 int gvpm_host_gradient(void *h, float *thr, float *gx, float *gy, int useAbs, char *err, size_t errlen) {
   try { ((VolumeGatherB200 *)h)->computeGradient(thr, gx, gy, useAbs != 0); return 0; }
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }

@@ -526,6 +526,11 @@ int gvpm_trace_photons_direct(gvpm_ctx *ctx, const gvpm_box_scene *scene, size_t
 /* parity aid: copy `bytes` bytes at `dev` (a pointer handed out by this library, e.g. gvpm_photon_staging /
  * gvpm_ray_staging) to host memory, after the work queued on the context's stream */
 int gvpm_read_device(gvpm_ctx *ctx, const void *dev, void *host, size_t bytes);
+/* measurement aid (the roofline's L2 denominator, BASELINE.json "% of HBM/L2 peak"): `reps` passes of 128-bit loads
+ * over a `bytes`-byte device buffer by a machine-filling grid, timed with CUDA events on the context's stream;
+ * gb_per_s = bytes * reps / time.  A buffer well below the 126 MB L2 gives the L2 read bandwidth, one far above it the
+ * HBM read bandwidth. */
+int gvpm_measure_read_bandwidth(gvpm_ctx *ctx, size_t bytes, int reps, double *gb_per_s);
 /* parity aid: the selected photon staging buffer (which = 0) or the ray staging buffer (which = 1) as they are, without
  * the side effects of gvpm_photon_staging / gvpm_ray_staging (which invalidate the build / the committed rays) */
 int gvpm_staging_peek(gvpm_ctx *ctx, int which, void **dev, size_t *count);

@@ -20,6 +20,19 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
+def prefer_native():
+    """bench.py's CPU legs: build the oracle with -march=native on THIS machine (untimed) and load that build; falls back to
+    the portable build.  Must be called before the first load().  -> the flags in use"""
+    global LIB_PATH
+    assert _lib is None, "prefer_native() after load()"
+    try:
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "native"])
+        LIB_PATH = os.path.join(_HERE, "_native", "libgvpm_oracle.so")
+        return "-O3 -march=native -ffp-contract=off"
+    except Exception:  # noqa: BLE001 - no compiler on the box: the shipped portable build
+        return "-O3 -ffp-contract=off (portable build: native rebuild failed)"
+
+
 def load():
     global _lib
     if _lib is not None:

@@ -29,5 +29,13 @@ for name, nbytes, reps in (("l2", 24 << 20, 400), ("l2_48mb", 48 << 20, 200), ("
     out[name + "_gbs"] = best
     out[name + "_bytes_each"] = nbytes
     del a, b
-out["how"] = "torch b.copy_(a), read+write bytes, back to back, CUDA events, best of 5 batches; l2: 2 x 24 MB (L2-resident), hbm: 2 x 2 GB"
+# read-only sweep with the library's own 128-bit load kernel (gvpm_measure_read_bandwidth): 16 / 32 / 64 MB stay in L2
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from gvpm_b200.api import Context  # noqa: E402
+ctx = Context(0)
+for mb, reps in ((16, 400), (32, 200), (64, 100), (96, 60), (4096, 4)):
+    out[f"read_{mb}mb_gbs"] = max(ctx.measure_read_bandwidth(mb << 20, reps) for _ in range(3))
+ctx.close()
+out["l2_read_peak_gbs"] = max(out["read_16mb_gbs"], out["read_32mb_gbs"], out["read_64mb_gbs"])
+out["how"] = "torch b.copy_(a), read+write bytes, back to back, CUDA events, best of 5 batches; l2: 2 x 24 MB (L2-resident), hbm: 2 x 2 GB; read_*: k_l2_read (gvpm_measure_read_bandwidth), best of 3"
 print(json.dumps(out))
