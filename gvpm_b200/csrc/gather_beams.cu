@@ -69,17 +69,62 @@ struct BeamTravShared {
   uint32_t base[GVPM_MAX_LEVELS];
 };
 
-__device__ __forceinline__ void flush_beam_pairs(const GatherParams &P, const uint32_t *queue, uint32_t ray,
-                                                 uint32_t &qn, uint32_t take, int lane) {
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)take);
-  base = __shfl_sync(0xffffffffu, base, 0);
+// Flush `take` queued candidates of one ray: lane = candidate.  Before a pair is written it passes the CHORD test - with
+// all lanes busy here, where the leaf loop runs it for the rare lanes that pass the line test.
+// Where can the beam run inside the cylinder around the camera LINE?  Around the beam parameter tc of the lines'
+// closest approach, at most r / sin(theta) to either side: the chord [tN, tF].  The kernel record's tNear - the entry
+// point, moved to an end cap when the camera SEGMENT starts or ends inside the chord (cylinder_intersection) - lies in
+// it, as does the 1-D kernel's closest-approach parameter, and only the sub-beam that holds that parameter keeps the
+// pair (ownership rule of k_beam_shade; sppm's per-sub-beam techniques intersect the sub-beam's own piece of the
+// chord): a sub-beam the chord misses cannot contribute, nor can a chord that lies entirely in front of or behind the
+// camera segment.  Relaxed arithmetic: the half-length is the largest a chord can have and is padded for the rounding
+// of tc (amplified by 1 / sin^2); pairs closer to parallel than ~6 degrees are kept as they are.
+__device__ __noinline__ uint32_t flush_beam_pairs(const GatherParams &P, const uint32_t *queue, uint32_t ray,
+                                                  uint32_t qn, uint32_t take, int lane, const float4 *rayRec, float fpad) {
   qn -= take;
+  bool keep = false;
+  uint32_t si = 0;
   if ((uint32_t)lane < take) {
-    const unsigned long long idx = base + lane;
-    if (idx < P.pair_cap) P.pairs[idx] = make_uint2(ray, queue[qn + lane]);
+    si = queue[qn + lane];
+    keep = true;
+    const float4 sb = ldg4(P.subs + si);
+    const uint32_t bi = __float_as_uint(sb.z), flags = __float_as_uint(sb.w);
+    const float4 b0 = ldg4(P.beams + (size_t)bi * GVPM_BEAM_FLOAT4), b1 = ldg4(P.beams + (size_t)bi * GVPM_BEAM_FLOAT4 + 1);
+    const float4 r0 = rayRec[0], r1 = rayRec[1], r2 = rayRec[2];
+    const float cx = r1.y * b1.z - r1.z * b1.y, cy = r1.z * b1.x - r1.x * b1.z, cz = r1.x * b1.y - r1.y * b1.x;
+    const float sin2 = cx * cx + cy * cy + cz * cz;
+    if (sin2 >= 1e-2f) {
+      const float wx = b0.x - r0.x, wy = b0.y - r0.y, wz = b0.z - r0.z;
+      const float a = r1.x * b1.x + r1.y * b1.y + r1.z * b1.z;
+      const float wd = wx * r1.x + wy * r1.y + wz * r1.z;
+      const float wb = wx * b1.x + wy * b1.y + wz * b1.z;
+      const float iA = 1.f / sin2;                      // sin2 = |d x b|^2 = 1 - (d.b)^2 for unit directions
+      const float tc = (wd * a - wb) * iA;
+      const float wmag = fabsf(wx) + fabsf(wy) + fabsf(wz);
+      const float h = (P.radius + 4.f * fpad) * sqrtf(iA) * 1.01f + (1e-5f * iA) * (wmag + 1.f) + 1e-4f * fabsf(tc);
+      const float tN = tc - h, tF = tc + h;
+      if (!(flags & 2u) && tN > sb.y) keep = false;    // chord entirely behind this sub-beam
+      if (!(flags & 1u) && tF < sb.x) keep = false;    // ... or entirely in front of it
+      // camera distance of the beam point at the two chord ends (linear in between)
+      const float zN = wd + tN * a, zF = wd + tF * a;
+      // (+ r: sppm's per-sub-beam techniques put the cylinder around the BEAM; a camera point inside it and the beam
+      // point it is closest to project onto the camera line within r of each other)
+      const float padZ = 1e-4f * (1.f + fabsf(zN) + fabsf(zF)) + 16.f * fpad + P.radius;
+      if (fmaxf(zN, zF) + padZ < r0.w || fminf(zN, zF) - padZ > fmaxf(r2.w, r1.w)) keep = false;
+    }
+  }
+  const uint32_t km = __ballot_sync(0xffffffffu, keep);
+  if (km) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.pair_counter, (unsigned long long)__popc(km));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const unsigned long long idx = base + __popc(km & ((1u << lane) - 1u));
+      if (idx < P.pair_cap) P.pairs[idx] = make_uint2(ray, si);
+    }
   }
   __syncwarp();
+  return qn;
 }
 
 __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __grid_constant__ GatherParams P) {
@@ -149,6 +194,18 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
         for (int j = 0; j < BPK; ++j)
           if (actMask >> j & 1) groups[ng++] = 1u << j;
       }
+    }
+    // rounding pad of the packet (chord test at the flushes)
+    float fpadPacket;
+    {
+      float om = 0.f, tm = 0.f;
+#pragma unroll
+      for (int j = 0; j < BPK; ++j)
+        if (actMask >> j & 1) {
+          om = fmaxf(om, fmaxf(fmaxf(fabsf(ox[j]), fabsf(oy[j])), fabsf(oz[j])));
+          tm = fmaxf(tm, fabsf(elen[j]));
+        }
+      fpadPacket = (om + coordMag + tm + P.radius) * 3.8147e-6f;
     }
     for (int g = 0; g < ng; ++g) {
       const uint32_t gm = groups[g];
@@ -220,33 +277,6 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
             const float sin2 = cx * cx + cy * cy + cz * cz;
             const float ad = (b0.x - ox[j]) * cx + (b0.y - oy[j]) * cy + (b0.z - oz[j]) * cz;
             bool ok = (gm >> j & 1) && (sin2 < 1e-6f || ad * ad < rpad2 * sin2 * 1.001f);
-            if (ok && sin2 >= 1e-2f) {
-              // Where can the beam run inside the cylinder around the camera LINE?  Around the beam parameter tc of the
-              // lines' closest approach, at most r / sin(theta) to either side: the chord [tN, tF].  The kernel record's
-              // tNear - the entry point, moved to an end cap when the camera SEGMENT starts or ends inside the chord
-              // (cylinder_intersection) - lies in it, as does the 1-D kernel's closest-approach parameter, and only the
-              // sub-beam that holds that parameter keeps the pair (ownership rule of k_beam_shade; sppm's per-sub-beam
-              // techniques intersect the sub-beam's own piece of the chord): a sub-beam the chord misses cannot
-              // contribute, nor can a chord that lies entirely in front of or behind the camera segment.  Relaxed
-              // arithmetic: the half-length is the largest a chord can have and is padded for the rounding of tc
-              // (amplified by 1 / sin^2); pairs closer to parallel than ~6 degrees are kept as they are.
-              const float wx = b0.x - ox[j], wy = b0.y - oy[j], wz = b0.z - oz[j];
-              const float a = dx[j] * b1.x + dy[j] * b1.y + dz[j] * b1.z;
-              const float wd = wx * dx[j] + wy * dy[j] + wz * dz[j];
-              const float wb = wx * b1.x + wy * b1.y + wz * b1.z;
-              const float iA = 1.f / sin2;                      // sin2 = |d x b|^2 = 1 - (d.b)^2 for unit directions
-              const float tc = (wd * a - wb) * iA;
-              const float wmag = fabsf(wx) + fabsf(wy) + fabsf(wz);
-              const float h = (P.radius + 4.f * fpad) * sqrtf(iA) * 1.01f + (1e-5f * iA) * (wmag + 1.f) + 1e-4f * fabsf(tc);
-              const float tN = tc - h, tF = tc + h;
-              const uint32_t flags = __float_as_uint(sb.w);
-              if (!(flags & 2u) && tN > sb.y) ok = false;    // chord entirely behind this sub-beam
-              if (!(flags & 1u) && tF < sb.x) ok = false;    // ... or entirely in front of it
-              // camera distance of the beam point at the two chord ends (linear in between)
-              const float zN = wd + tN * a, zF = wd + tF * a;
-              const float padZ = 1e-4f * (1.f + fabsf(zN) + fabsf(zF)) + 16.f * fpad;
-              if (fmaxf(zN, zF) + padZ < mint[j] || fminf(zN, zF) - padZ > elen[j]) ok = false;
-            }
             // the filters only drop pairs (they never make one valid): keep them out of the pair list unless
             // the parity dump needs the geometric set
             if (P.beam_prefilter) {
@@ -267,13 +297,13 @@ __global__ void __launch_bounds__(kBeamWarps * 32, 6) k_beam_traverse(const __gr
           if (c1) S.queue[j][qn[j] + __popc(cmask & ((1u << lane) - 1u))] = si;
           qn[j] += __popc(cmask);
           __syncwarp();
-          if (qn[j] >= 32) flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], 32, lane);
+          if (qn[j] >= 32) qn[j] = flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], 32, lane, S.ray[j], fpadPacket);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < BPK; ++j)
-      if (qn[j] > 0) flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], qn[j], lane);
+      if (qn[j] > 0) qn[j] = flush_beam_pairs(P, S.queue[j], r0 + j, qn[j], qn[j], lane, S.ray[j], fpadPacket);
   }
 }
 

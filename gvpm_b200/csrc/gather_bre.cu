@@ -424,6 +424,10 @@ k_bre_grid_traverse(const __grid_constant__ GatherParams P) {
   // with the pathSet prefilter a ray only ever pairs with photons of its pixel's parity: it scans that grid alone
   const bool onlyMine = G.parity_split && prefilter && P.cfg.path_set;
   const uint32_t nPass = onlyMine ? 1u : nGridsBuilt;
+  if (P.build_ovf && __ldg(P.build_ovf)) {   // incomplete grid (gvpm_capi.cu build_frustum): report it instead of gathering
+    if (blockIdx.x == 0 && threadIdx.x == 0) *P.pair_counter = 1ull << 62;
+    return;
+  }
 
   for (;;) {
     uint32_t tile = 0;
@@ -544,6 +548,7 @@ k_bre_shade(const __grid_constant__ GatherParams P) {
   __shared__ ShadeShared shade_sh[SPPM ? 1 : GVPM_SHADE_THREADS / 32];
   const int lane = threadIdx.x & 31;
   unsigned long long total = *P.pair_counter;
+  if (total >= (1ull << 62)) return;   // incomplete perspective grid: nothing to shade (the host reports it)
   if (total > P.pair_cap) total = P.pair_cap;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   // software pipeline over the grid-stride loop: the pair of the NEXT iteration is already in registers, so its

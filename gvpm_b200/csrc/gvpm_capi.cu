@@ -35,7 +35,8 @@ void launch_flag_set(const FlagSetParams &P, cudaStream_t st);
 void launch_l2_read(const void *p, size_t bytes, int reps, unsigned *sink, int sm_count, cudaStream_t st);
 void launch_translate_idx(uint32_t *idx, unsigned long long n, const float4 *aos, cudaStream_t st);
 void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
-                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st);
+                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st, uint32_t limit, uint32_t *overflow);
+void launch_fill_u32(uint32_t *p, uint32_t n, uint32_t value, cudaStream_t st);
 void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
                              float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st, bool records_ready);
 void launch_scan_u32(uint32_t *vals, uint32_t nb, uint32_t *total, cudaStream_t st);
@@ -170,6 +171,7 @@ struct gvpm_ctx {
   bool photons_direct = false;   // gvpm_trace_photons_direct: the 128-byte records in `aos` ARE the photon set (no staging, no packing)
   // dispatched photon set (gvpm_build_dispatched): the records live in an inbox the peers wrote; one region of
   // region_cap records per sender, region_count[s] (device) of them filled
+  const uint32_t *build_ovf = nullptr;   // device flag of the last frustum build (bounded compaction overflowed)
   float4 *aos_override = nullptr;
   uint32_t region_cap = 0;
   const uint32_t *region_count = nullptr;
@@ -207,6 +209,8 @@ struct gvpm_ctx {
   FrustumGrid grid{};
   DevBuf cell_start, grid_occ, pin_scratch, trace_scratch, keepmask;
   double kept_fraction_hint = 1.0;   // share of the photons the last frustum build kept (sizes the next one's sort)
+  bool kept_hint_valid = false;      // the fraction comes from a count read back from a build over the same kind of set
+  bool force_exact_build = false;    // a bounded build overflowed: size the next one from its exact count (one host sync)
   cudaEvent_t ev_hint = nullptr;
   bool hint_pending = false;
   uint32_t hint_n = 0;
@@ -344,6 +348,7 @@ int fill_params(gvpm_ctx *ctx, GatherParams &P, float *out_dev, uint32_t *counts
   if (ctx->accel == gvpm_ctx::ACCEL_FRUSTUM) {
     P.grid = ctx->grid;
     P.cell_start = ctx->cell_start.as<uint32_t>();
+    P.build_ovf = ctx->build_ovf;
   }
   P.planes = ctx->planes.as<float4>();
   P.aos = ctx->records();
@@ -405,6 +410,9 @@ int enqueue_range(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, unsi
   CK(cudaMemcpyAsync(host_slot, P.pair_counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
   return GVPM_OK;
 }
+
+// pair count a gather reports when its perspective grid is incomplete (bounded compaction overflow, build_frustum)
+static const unsigned long long kBuildOverflow = 1ull << 62;
 
 // the slow path: one host sync per attempt.  Rows [r0, r1) of P.out are cleared first.
 int gather_range_sync(gvpm_ctx *ctx, GatherParams &P, uint32_t r0, uint32_t r1, int depth) {
@@ -476,6 +484,12 @@ int pending_check(gvpm_ctx *ctx, bool block) {
     --ctx->ring_n;
     ctx->last_pairs = total;
     if (total <= g.cap) continue;
+    if (total >= kBuildOverflow) {   // the bounded frustum build was too small: nothing was gathered
+      ctx->force_exact_build = true;
+      return fail(ctx, GVPM_ERR_INVALID,
+                  "the perspective grid was sized from the previous iteration's photon count and this iteration kept over "
+                  "25 % more: the gather did not run.  Build again (the next build reads its exact count) and gather again");
+    }
     // overflow: make the list large enough for the next one
     cudaStreamSynchronize(ctx->stream);
     int rc = reserve_pairs(ctx, total + total / 8 + 1024);
@@ -530,6 +544,12 @@ int gather_finish(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev, const uns
   const unsigned long long total = *host_slot;
   ctx->last_pairs = total;
   if (total <= ctx->pair_cap) return GVPM_OK;
+  if (total >= kBuildOverflow) {
+    ctx->force_exact_build = true;
+    return fail(ctx, GVPM_ERR_INVALID,
+                "the perspective grid was sized from the previous iteration's photon count and this iteration kept over "
+                "25 % more: the gather did not run.  Build again (the next build reads its exact count) and gather again");
+  }
   int rc = reserve_pairs(ctx, total + total / 8 + 1024);
   if (rc) return rc;
   GatherParams P;
@@ -1243,7 +1263,7 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
   if (ctx->hint_pending && cudaEventQuery(ctx->ev_hint) == cudaSuccess) {
     ctx->hint_pending = false;
     const uint32_t keptPrev = *(const uint32_t *)(ctx->pin_host + 30);
-    if (ctx->hint_n) ctx->kept_fraction_hint = (double)keptPrev / (double)ctx->hint_n;
+    if (ctx->hint_n) { ctx->kept_fraction_hint = (double)keptPrev / (double)ctx->hint_n; ctx->kept_hint_valid = true; }
   }
   uint32_t m = n;   // sorted entries
   if (n > 0) {
@@ -1255,7 +1275,7 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     CK(ctx->sort_temp.reserve(sort_temp_bytes(n)));
     CK(ctx->planes.reserve(16 * (size_t)n));
     CK(ctx->orig.reserve(4 * (size_t)n));
-    CK(ctx->keepmask.reserve(4 * ((size_t)n / 32 + 1) + 4 * ((size_t)nb + 2)));
+    CK(ctx->keepmask.reserve(4 * ((size_t)n / 32 + 1) + 4 * ((size_t)nb + 4)));
     const bool direct = ctx->photons_direct;
     if (!direct) CK(ctx->aos.reserve(128 * (size_t)n));
     CK(ctx->grid_occ.reserve(frustum_occ_bytes() + cell_starts_scratch_bytes(n_keys)));
@@ -1271,16 +1291,38 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
                           ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, keepmask,
                           block_kept, ctx->sm_count, st);
     const uint32_t *sortedKeys, *sortedVals;
+    uint32_t *ovf = block_kept + nb + 1;   // set when a bounded compaction meets more kept photons than it was sized for
+    CK(cudaMemsetAsync(ovf, 0, 4, st));
     if (ctx->kept_fraction_hint < 0.5) {
       // sharded image: most photons are out of this rank's reach.  Compact the kept (key, index) pairs in index order
-      // (deterministic) and sort those only; their number sizes the sort, hence one 4-byte read-back.
+      // (deterministic) and sort those only.  Their number sizes the sort: taken from the previous build's count (read
+      // back asynchronously) with a 25 % margin, the slots past the real count filled with DROP keys - no host round
+      // trip in the step.  Without a previous count (first build, or after an overflow) the exact count is read back.
       launch_scan_u32(block_kept, nb, block_kept + nb, st);
-      launch_compact_kept(ctx->keys_in.as<uint32_t>(), keepmask, block_kept, n, ctx->keys_out.as<uint32_t>(),
-                          ctx->vals_out.as<uint32_t>(), st);
-      CK(cudaMemcpyAsync(ctx->pair_count_host, block_kept + nb, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      m = *(const uint32_t *)ctx->pair_count_host;
-      ctx->kept_fraction_hint = (double)m / (double)n;
+      const bool bounded = ctx->kept_hint_valid && !ctx->force_exact_build;
+      if (bounded) {
+        const uint32_t DROP = n_keys - 1;
+        m = (uint32_t)std::min<double>((double)n, ctx->kept_fraction_hint * 1.25 * (double)n + 65536.0);
+        launch_fill_u32(ctx->keys_out.as<uint32_t>(), m, DROP, st);
+        CK(cudaMemsetAsync(ctx->vals_out.p, 0, 4 * (size_t)m, st));
+        launch_compact_kept(ctx->keys_in.as<uint32_t>(), keepmask, block_kept, n, ctx->keys_out.as<uint32_t>(),
+                            ctx->vals_out.as<uint32_t>(), st, m, ovf);
+        CK(cudaMemcpyAsync(ctx->pin_host + 30, block_kept + nb, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_hint, st));
+        ctx->hint_pending = true;
+        ctx->hint_n = n;
+        ctx->launches += 1;
+      } else {
+        launch_compact_kept(ctx->keys_in.as<uint32_t>(), keepmask, block_kept, n, ctx->keys_out.as<uint32_t>(),
+                            ctx->vals_out.as<uint32_t>(), st, n, ovf);
+        CK(cudaMemcpyAsync(ctx->pair_count_host, block_kept + nb, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        m = *(const uint32_t *)ctx->pair_count_host;
+        ctx->kept_fraction_hint = (double)m / (double)n;
+        ctx->kept_hint_valid = true;
+        ctx->force_exact_build = false;
+        ctx->hint_pending = false;
+      }
       if (m) CK(run_sort_bits(ctx->sort_temp.p, ctx->sort_temp.cap, ctx->keys_out.as<uint32_t>(), ctx->keys_in.as<uint32_t>(),
                               ctx->vals_out.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), m, bits, st));
       sortedKeys = ctx->keys_in.as<uint32_t>();
@@ -1292,6 +1334,7 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
       sortedKeys = ctx->keys_out.as<uint32_t>();
       sortedVals = ctx->vals_out.as<uint32_t>();
     }
+    ctx->build_ovf = ovf;
     launch_cell_starts(sortedKeys, m, n_keys, ctx->cell_start.as<uint32_t>(),
                        ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
     launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->records(), ctx->planes.as<float4>(),
@@ -1707,7 +1750,10 @@ int gvpm_build_dispatched(gvpm_ctx *ctx, int which, float radius, uint32_t *n_ke
   ctx->region_count = ctrl + DC_COUNT + which * GVPM_MAX_PEERS;
   ctx->built = false;
   ++ctx->state_gen;
-  if (D.n_peers > 2 && ctx->kept_fraction_hint >= 0.5) ctx->kept_fraction_hint = 0.25;   // most regions are mostly empty
+  if (gen == 1 && which == 0) {   // first build over an inbox: mostly empty regions; its exact count sizes the following ones
+    ctx->kept_fraction_hint = 0.25;
+    ctx->kept_hint_valid = false;
+  }
   rc = build_frustum(ctx, radius, n_kept);
   if (rc) return rc;
   // a peer that never signalled (k_flag_wait timed out) or a region overflow: visible once the stream has drained; the

@@ -641,7 +641,8 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
 // (key, index) of the kept photons, in index order, packed to the front: block_off = exclusive scan of block_kept
 __global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ keepmask,
                                                        const uint32_t *__restrict__ block_off, uint32_t n,
-                                                       uint32_t *__restrict__ keys_c, uint32_t *__restrict__ vals_c) {
+                                                       uint32_t *__restrict__ keys_c, uint32_t *__restrict__ vals_c,
+                                                       uint32_t limit, uint32_t *__restrict__ overflow) {
   __shared__ uint32_t wcnt[8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -651,8 +652,15 @@ __global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict
   if (!(km >> lane & 1u)) return;
   uint32_t pos = block_off[blockIdx.x] + __popc(km & ((1u << lane) - 1u));
   for (int k = 0; k < w; ++k) pos += wcnt[k];
+  if (pos >= limit) {   // more kept photons than the (bounded) sort was sized for: the build is incomplete, say so
+    *overflow = 1u;
+    return;
+  }
   keys_c[pos] = keys[i];
   vals_c[pos] = i;
+}
+__global__ void k_fill_u32(uint32_t *__restrict__ p, uint32_t n, uint32_t value) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = value;
 }
 // cell_start[k] = first sorted slot whose key is >= k, for k in [0, n_keys].  Lane i owns the gap of keys in front of
 // slot i; the warp fills its lanes' gaps one after the other with all 32 lanes writing (coalesced).  Gaps of 4096 cells
@@ -789,8 +797,11 @@ void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *
 }
 size_t frustum_occ_bytes() { return (size_t)kOccWords * 4; }
 void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
-                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st) {
-  if (n) k_compact_kept<<<(n + 255) / 256, 256, 0, st>>>(keys, keepmask, block_off, n, keys_c, vals_c);
+                         uint32_t *keys_c, uint32_t *vals_c, cudaStream_t st, uint32_t limit, uint32_t *overflow) {
+  if (n) k_compact_kept<<<(n + 255) / 256, 256, 0, st>>>(keys, keepmask, block_off, n, keys_c, vals_c, limit, overflow);
+}
+void launch_fill_u32(uint32_t *p, uint32_t n, uint32_t value, cudaStream_t st) {
+  if (n) k_fill_u32<<<std::min<uint32_t>((n + 255) / 256, 2048u), 256, 0, st>>>(p, n, value);
 }
 // records of the kept photons only (keepmask), then the sorted position plane / index map of the first m sorted slots
 void launch_pack_sorted_kept(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,

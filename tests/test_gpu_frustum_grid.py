@@ -120,3 +120,34 @@ def test_second_sharded_build_compacts_before_the_sort(built):
         outs.append(kept)
     assert outs[0] == outs[1] == outs[2]
     ctx.close()
+
+
+def test_bounded_build_overflow_is_reported_and_recovered(built):
+    """A sharded build sizes its sort from the previous iteration's kept count (+25 %, no host round trip).  When an
+    iteration keeps far more, the gather must say so instead of returning a partial result, and the next build (exact
+    count) must give the right answer."""
+    from oracle import binding as ob
+    from gvpm_b200.api import GvpmError
+    case = H.make_case(n_photons=1600000, w=64, h=64, scale=0.5)
+    idx = shard.band_indices(case.rays.px, case.rays.py, 64, 64, 8, 3, 1)
+    case.rays = case.rays.take(idx)
+    ctx = H.gpu_context(case)
+    assert ctx.build_points_for_rays(case.radius) > 65536 * 1.3     # what the set keeps for these rays
+    far = case.photons.copy()
+    far.view("pos")[:] += np.float32(40.0)         # an iteration whose photons no ray can reach
+    for _ in range(3):                              # full sort, then exact compaction, then a bounded one sized for ~0 kept
+        ctx.upload_photons(far)
+        assert ctx.build_points_for_rays(case.radius) == 0
+        out, counts = ctx.gather_bre()
+        assert not counts.any()
+    ctx.upload_photons(case.photons)                # ... followed by one that keeps > 65536 + 25 %
+    ctx.build_points_for_rays(case.radius, want_kept=False)
+    with pytest.raises(GvpmError, match="sized from the previous iteration"):
+        ctx.gather_bre()
+    kept = ctx.build_points_for_rays(case.radius)   # exact count this time
+    assert kept > 65536 * 1.3
+    out, counts = ctx.gather_bre()
+    ref = ob.bre_gather(case.photons, case.rays, case.medium, case.config, case.tri, case.radius, mode="brute")
+    np.testing.assert_array_equal(counts, ref.counts)
+    H.assert_radiance_close(out, ref.out, 1e-4, "after the overflow")
+    ctx.close()
