@@ -122,7 +122,7 @@ def make_inputs(args, rank, world, pin=True):
     cfg = g.make_config(w, h)
     return dict(w=w, h=h, n_ph=n_ph, scale=scale, medium=medium, photons=photons, n_paths=int(n_paths),
                 rays=rays, rays_full_n=full.n, cfg=cfg, tri=g.synth_occluders(), radius=g.bre_radius(scale),
-                keep=keep, full_rays=full if (rank == 0) else None)
+                keep=keep, full_rays=full if (rank == 0 or world > 1) else None, alloc=alloc)
 
 
 def shard_mode(world):
@@ -315,6 +315,52 @@ def reference_main(args):
             "config": workload_config(args, inp, max(1, args.gpus)), "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def rebalance_bands(args, inp, ctx, stream, rank, world):
+    """Untimed pilot iteration (what a progressive integrator knows from its previous iteration): every rank gathers its
+    equal-size bands once with neighbour counts, the per-block costs (contributing pairs + a per-ray term) are summed
+    over the ranks and the bands are re-cut into runs of equal COST (shard.band_owner_weighted).  The photon density of
+    the scene is centre-weighted: with equal-size bands the busiest rank of 8 carries ~40 % more than the average."""
+    import torch
+    import torch.distributed as dist
+    from gvpm_b200 import records as R, shard
+    if shard_mode(world) != "band" or os.environ.get("GVPM_BALANCE", "1") == "0" or not prune_build(world):
+        return None
+    w, h, n_ph = inp["w"], inp["h"], inp["n_ph"]
+    ctx.photon_staging_select(0)
+    ptr, nbytes = ctx.photon_staging(n_ph)
+    st = torch.as_tensor(DevView(ptr, nbytes), device="cuda")
+    with torch.cuda.stream(stream):
+        if rank == 0:
+            ctx.upload_photons(inp["photons"])
+        dist.broadcast(st, src=0)
+        ctx.upload_rays(inp["rays"])
+        ctx.build_points_for_rays(inp["radius"], want_kept=False)
+    out, counts = ctx.gather_bre()
+    del out
+    rays = inp["rays"]
+    n_tiles = ((w + 31) // 32) * ((h + 31) // 32)
+    t = shard.block_index(rays.px, rays.py, h)
+    lam = float(os.environ.get("GVPM_BALANCE_RAY_COST", "3"))      # a ray costs about as much as three contributing pairs
+    cost = np.bincount(t, weights=counts[:, 1].astype(np.float64) + lam, minlength=n_tiles)
+    cost_t = torch.from_numpy(cost).cuda()
+    dist.all_reduce(cost_t)
+    cost = cost_t.cpu().numpy()
+    full = inp["full_rays"]
+    owner = shard.band_owner_weighted(full.px, full.py, w, h, world, cost, band_cycles())
+    per_rank = np.array([cost[np.unique(shard.block_index(full.px[owner == r], full.py[owner == r], h))].sum() for r in range(world)])
+    before = shard.band_owner(full.px, full.py, w, h, world, band_cycles())
+    per_before = np.array([cost[np.unique(shard.block_index(full.px[before == r], full.py[before == r], h))].sum() for r in range(world)])
+    sub = full.take(np.nonzero(owner == rank)[0])
+    rays2 = R.RaySet(sub.n, **inp["alloc"](R._RAY_FIELDS, sub.n))
+    for name, _, _ in R._RAY_FIELDS:
+        getattr(rays2, name)[:] = getattr(sub, name)
+    inp["rays"] = rays2
+    del st
+    return {"cost_model": f"contributing pairs + {lam:g} per ray, per 32x32 block, from one pilot iteration (untimed)",
+            "max_over_mean_equal_blocks": float(per_before.max() / per_before.mean()),
+            "max_over_mean_equal_cost": float(per_rank.max() / per_rank.mean())}
 
 
 def workload_config(args, inp, world):
@@ -776,8 +822,12 @@ def main():
     ctx.set_medium(inp["medium"])
     ctx.set_config(inp["cfg"])
     ctx.set_occluders(inp["tri"])
+    if world > 1:
+        ctx.set_view_direction((0.0, 0.0, 1.0))   # the synthetic sensor looks down +z: one projection plane for all ranks
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
-    n_ph, rays = inp["n_ph"], inp["rays"]
+    n_ph = inp["n_ph"]
+    balance = rebalance_bands(args, inp, ctx, stream, rank, world) if world > 1 else None
+    rays = inp["rays"]
     n_local = rays.n
     # result buffers (device): own shard; rank 0 also the gathered image
     counts_max = torch.tensor([n_local], device="cuda", dtype=torch.int64)
@@ -953,9 +1003,50 @@ def main():
     with torch.cuda.stream(stream):
         out_bufs = [out_dev, torch.zeros_like(out_dev) if overlap_collect else out_dev]
     coll_done = [None, None]
+    # With the dispatch connected, the results go to rank 0 by plain device-to-device copies into an image buffer rank 0
+    # shares over CUDA IPC (gvpm_shared_buffer_*): copy engines over NVLink instead of NCCL's send / receive kernels, which
+    # take SMs from the gather kernels, and exactly n_rays rows per rank instead of rows padded to the largest shard.
+    peer_collect = dispatching and overlap_collect and os.environ.get("GVPM_COLLECT_VIA", "copy") == "copy"
+    img_views = image_bufs = None
+    if peer_collect:
+        from gvpm_b200 import _native as NAT2
+        HB = NAT2.GVPM_SHARED_HANDLE_BYTES
+        n_all = [torch.zeros(1, device="cuda", dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(n_all, torch.tensor([n_local], device="cuda", dtype=torch.int64))
+        rows = [int(t.item()) for t in n_all]
+        my_off, rows_total = sum(rows[:rank]), sum(rows)
+        hb = torch.zeros(2 * HB, dtype=torch.uint8, device="cuda")
+        img_ptrs = []
+        if rank == 0:
+            hs = []
+            for _ in (0, 1):
+                p, h_ = ctx.shared_buffer_create(rows_total * 27 * 4)
+                img_ptrs.append(p)
+                hs.append(h_)
+            hb.copy_(torch.frombuffer(bytearray(b"".join(hs)), dtype=torch.uint8))
+        dist.broadcast(hb, src=0)
+        raw = bytes(hb.cpu().numpy().tobytes())
+        if rank != 0:
+            img_ptrs = [ctx.shared_buffer_open(raw[i * HB:(i + 1) * HB]) for i in (0, 1)]
+        img_views = [torch.as_tensor(DevView(p + my_off * 27 * 4, max(n_local, 1) * 27 * 4), device="cuda").view(torch.float32)
+                     for p in img_ptrs]
+        if rank == 0:
+            image_bufs = [torch.as_tensor(DevView(p, rows_total * 27 * 4), device="cuda").view(torch.float32) for p in img_ptrs]
 
     def collect(k):
-        if world == 1:
+        if world == 1 or os.environ.get("GVPM_COLLECT") == "none":   # "none": diagnostic only (what the result gather costs)
+            return
+        if peer_collect:
+            b = k & 1
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            coll.wait_event(ev)
+            with torch.cuda.stream(coll):
+                if n_local:
+                    img_views[b][:n_local * 27].copy_(out_bufs[b][:n_local * 27], non_blocking=True)
+                ctx.collect_signal(b, 0, coll.cuda_stream)
+            coll_done[b] = torch.cuda.Event()
+            coll_done[b].record(coll)
             return
         if not overlap_collect:
             dist.gather(out_bufs[0], gathered, dst=0)
@@ -983,24 +1074,42 @@ def main():
             ctx.build_points(inp["radius"])
 
     disp_next = [0]     # inbox generations run on across the timed loop and the diagnostics below
+    trace = [] if os.environ.get("GVPM_BENCH_TRACE") else None   # per-step CUDA events (stderr, every rank)
+
+    def mark(what, on=None):
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(on if on is not None else stream)
+            trace.append((what, e))
 
     def step_dispatch(k=None, gather_results=True):
         """value leg, N > 1: (dispatch of step k+1's photons in flight) + build over the inbox + gather + result gather"""
         k = disp_next[0]
         disp_next[0] += 1
         b = k & 1
-        # step k+1's photons go out while step k is built and gathered (the slice is resident and never changes: no
-        # dependency on the compute stream; the senders wait for the receivers' release of that inbox on the device)
-        ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)
         if coll_done[b] is not None:            # the result buffer of step k - 2 has been gathered
             stream.wait_event(coll_done[b])
             coll_done[b] = None
+        side = os.environ.get("GVPM_DISPATCH_STREAM", "inline") == "side"
+        if side:   # on the library's priority stream, concurrently with this step (starved by the persistent gather kernels)
+            ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)
         with torch.cuda.stream(stream):
+            mark(f"s{k}.begin")
             ctx.build_dispatched(b, inp["radius"])
+            mark(f"s{k}.built")
+            # step k+1's photons go out between this step's build and its gather, in the compute stream: ~0.1 ms of
+            # the step, but every rank's records are in place long before any rank starts its next build (the senders
+            # wait for the receivers' release of that inbox on the device)
+            if not side:
+                ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=ctx.stream())
+                mark(f"s{k}.dispatched")
             ctx.gather_bre_into(out_bufs[b].data_ptr(), None)
             ctx.dispatch_release(b)
+            mark(f"s{k}.gathered")
             if gather_results:
                 collect(k)
+                if overlap_collect:
+                    mark(f"s{k}.collected", coll)
 
     def step_resident(k):
         """value leg: (photon all-gather of step k+1 in flight) + build + gather (+ result gather)"""
@@ -1064,12 +1173,20 @@ def main():
         else:
             wait_ready((warmup + steps) & 1)    # the K-th exchange issued inside the timed region ends inside it
         wait_collects()                         # ... and so do the result gathers
+        if disp and peer_collect and rank == 0:
+            ctx.collect_wait(0)                 # rank 0 has every rank's rows of both image buffers
+            ctx.collect_wait(1)
         e1.record(stream)
         ctx.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if trace:
+            t0 = trace[0][1]
+            print(f"[trace rank {rank}] " + " ".join(f"{w}={t0.elapsed_time(e):.3f}" for w, e in trace) +
+                  f" | timed region {e0.elapsed_time(e1):.3f} ms, starts at {t0.elapsed_time(e0):.3f}", file=sys.stderr, flush=True)
+            trace.clear()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -1081,6 +1198,13 @@ def main():
         sampler.start()
     W = max(3, args.warmup)
     ms_total, launches, build_ms, gather_ms = timed(step_resident, args.steps, W, False)
+    collect_ok = None
+    if peer_collect:   # what rank 0 holds after the run = what the ranks gathered in their last two steps
+        sums = torch.stack([out_bufs[b][:n_local * 27].double().sum() for b in (0, 1)])
+        dist.all_reduce(sums)
+        if rank == 0:
+            got = torch.stack([image_bufs[b].double().sum() for b in (0, 1)])
+            collect_ok = bool(torch.allclose(got, sums, rtol=1e-9, atol=0.0)) and bool((got > 0).all())
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, W, True)
     # ---- rows f-1 / f-2: the whole iteration on the device (photons traced, rays generated: nothing uploaded), results
     # to pinned host memory.  N = 1 only; reported next to the host-buffer e2e, never instead of it.
@@ -1211,12 +1335,15 @@ def main():
                                      "bytes (profiles/), the HBM fraction is reported as the contract asks"},
                 "phases_ms": {"build": build_ms, "gather": float(gk.item()), "traverse": trav_ms,
                               "shade": shade_ms},
+                "result_collection_verified": collect_ok,
+                "result_collection": ("device-to-device copies into rank 0's image buffer (CUDA IPC, copy engines), per-rank generation flags"
+                                      if peer_collect else ("NCCL gather to rank 0" if world > 1 else "single GPU")),
                 "value_exchange": ("photon dispatch: each rank classifies its resident slice against every receiver's perspective grid and "
                                    "writes the 128-byte records a receiver can reach into that receiver's inbox over NVLink "
                                    "(gvpm_dispatch_*), double-buffered, device-side generation flags" if dispatching else
                                    ("whole-set exchange (see photon_exchange)" if world > 1 else "single GPU")),
                 "shards": {"mode": shard_mode(world), "band_cycles": band_cycles() if shard_mode(world) == "band" else None,
-                           "pruned_build": prune_build(world), "accel": accel,
+                           "pruned_build": prune_build(world), "accel": accel, "balance": balance,
                            "rays_per_rank": [int(k[1].item()) for k in kept_all],
                            "photons_in_hierarchy_per_rank": [int(k[0].item()) for k in kept_all]},
                 "light_paths": inp["n_paths"]}
@@ -1230,6 +1357,7 @@ def main():
     # tensors allocated on the context's stream must go before the stream does
     # (device tensors and pinned host buffers that were used on it record events on that stream when
     # they are freed)
+    del img_views, image_bufs
     del out_dev, out_bufs, cnt_dev, gathered, stage_t, views, slice_dev, keep_host, host_slice, host_fields, counts_max, h_geom, gk, bk, kept_t, kept_all
     del out_host_t, out_host, rays
     inp.clear()

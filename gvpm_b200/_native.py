@@ -16,6 +16,7 @@ GVPM_OUT_FLOATS = 27
 GVPM_PEER_BLOB_BYTES = 384
 GVPM_DISPATCH_BLOB_BYTES = 512
 GVPM_MAX_PEERS = 8
+GVPM_SHARED_HANDLE_BYTES = 96
 PARENT_EMITTER, PARENT_SURFACE, PARENT_MEDIUM, PARENT_OTHER = 0, 1, 2, 3
 PHASE_ISOTROPIC, PHASE_HG = 0, 1
 SURF2MEDIA, MEDIA2MEDIA = 1 << 2, 1 << 4
@@ -101,11 +102,12 @@ BEAM_TECHNIQUES = {"beam1d": 0, "beam3d_naive": 1, "beam3d_egsr": 2, "beam3d": 3
 ABI_SYMBOLS = [
     "gvpm_abi_version", "gvpm_ctx_create", "gvpm_ctx_destroy", "gvpm_last_error", "gvpm_sync",
     "gvpm_stream", "gvpm_set_medium", "gvpm_set_config", "gvpm_set_occluders",
-    "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays", "gvpm_accel_kind",
+    "gvpm_upload_photons", "gvpm_photon_staging", "gvpm_build_points", "gvpm_build_points_for_rays", "gvpm_accel_kind", "gvpm_set_view_direction",
     "gvpm_photon_staging_select", "gvpm_photon_staging_layout", "gvpm_upload_photons_slice",
     "gvpm_peer_export", "gvpm_peer_connect", "gvpm_peer_push_photon_slice", "gvpm_peer_wait_photons", "gvpm_peer_push_mode",
     "gvpm_dispatch_export", "gvpm_dispatch_connect", "gvpm_dispatch_photons", "gvpm_build_dispatched", "gvpm_dispatch_release",
-    "gvpm_dispatch_status", "gvpm_dispatch_join",
+    "gvpm_dispatch_status", "gvpm_dispatch_join", "gvpm_shared_buffer_create", "gvpm_shared_buffer_open", "gvpm_collect_signal",
+    "gvpm_collect_wait",
     "gvpm_upload_rays", "gvpm_ray_staging", "gvpm_commit_rays", "gvpm_gather_bre", "gvpm_gather_sppm_bre",
     "gvpm_gather_bre_device", "gvpm_gather_bre_into", "gvpm_gather_bre_host", "gvpm_dump_neighbours_bre",
     "gvpm_compute_gradient", "gvpm_poisson_preset", "gvpm_poisson_solve", "gvpm_reconstruct", "gvpm_last_poisson_ms", "gvpm_last_timings", "gvpm_last_gather_detail", "gvpm_launch_count",
@@ -163,6 +165,7 @@ def load_lib():
     lib.gvpm_peer_push_photon_slice.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, vp]
     lib.gvpm_peer_wait_photons.argtypes = [vp, C.c_int]
     lib.gvpm_peer_push_mode.argtypes = [vp, C.c_int]
+    lib.gvpm_set_view_direction.argtypes = [vp, f32p]
     lib.gvpm_dispatch_export.argtypes = [vp, C.c_int, C.c_size_t, vp]
     lib.gvpm_dispatch_connect.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.gvpm_dispatch_photons.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, vp]
@@ -170,6 +173,10 @@ def load_lib():
     lib.gvpm_dispatch_release.argtypes = [vp, C.c_int]
     lib.gvpm_dispatch_status.argtypes = [vp, u32p, C.c_int]
     lib.gvpm_dispatch_join.argtypes = [vp]
+    lib.gvpm_shared_buffer_create.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
+    lib.gvpm_shared_buffer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.gvpm_collect_signal.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.gvpm_collect_wait.argtypes = [vp, C.c_int]
     lib.gvpm_upload_rays.argtypes = [vp, C.POINTER(RaySoA), C.c_size_t]
     lib.gvpm_ray_staging.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.gvpm_commit_rays.argtypes = [vp]

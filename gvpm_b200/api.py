@@ -138,6 +138,25 @@ class Context:
         self._ck(self.lib.gvpm_measure_read_bandwidth(self.h, int(nbytes), int(reps), C.byref(v)), "gvpm_measure_read_bandwidth")
         return float(v.value)
 
+    def shared_buffer_create(self, nbytes):
+        """-> (device pointer, handle bytes): a device buffer other ranks can open and write (CUDA IPC)"""
+        dev = C.c_void_p()
+        h = (C.c_ubyte * N.GVPM_SHARED_HANDLE_BYTES)()
+        self._ck(self.lib.gvpm_shared_buffer_create(self.h, int(nbytes), C.byref(dev), h), "gvpm_shared_buffer_create")
+        return dev.value, bytes(h)
+
+    def shared_buffer_open(self, handle):
+        dev = C.c_void_p()
+        h = (C.c_ubyte * N.GVPM_SHARED_HANDLE_BYTES).from_buffer_copy(handle)
+        self._ck(self.lib.gvpm_shared_buffer_open(self.h, h, C.byref(dev)), "gvpm_shared_buffer_open")
+        return dev.value
+
+    def collect_signal(self, which, root=0, stream=None):
+        self._ck(self.lib.gvpm_collect_signal(self.h, which, root, stream), "gvpm_collect_signal")
+
+    def collect_wait(self, which):
+        self._ck(self.lib.gvpm_collect_wait(self.h, which), "gvpm_collect_wait")
+
     def dispatch_join(self):
         self._ck(self.lib.gvpm_dispatch_join(self.h), "gvpm_dispatch_join")
 
@@ -157,6 +176,14 @@ class Context:
         self._ck(self.lib.gvpm_build_points_for_rays(self.h, C.c_float(radius), C.byref(kept) if want_kept else None),
                  "gvpm_build_points_for_rays")
         return int(kept.value) if want_kept else None
+
+    def set_view_direction(self, direction):
+        """axis of the perspective grid's projection plane (None: the mean ray direction)"""
+        if direction is None:
+            self._ck(self.lib.gvpm_set_view_direction(self.h, None), "gvpm_set_view_direction")
+            return
+        d = (C.c_float * 3)(*[float(v) for v in direction])
+        self._ck(self.lib.gvpm_set_view_direction(self.h, d), "gvpm_set_view_direction")
 
     def accel_kind(self):
         """'bvh' or 'frustum': what the last point build produced"""

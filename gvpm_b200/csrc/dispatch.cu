@@ -30,11 +30,49 @@ __global__ void __launch_bounds__(256) k_dispatch_classify(const __grid_constant
   if (i < P.count) {
     const size_t g = (size_t)P.begin + i;
     const float px = __ldg(P.S.pos + 3 * g), py = __ldg(P.S.pos + 3 * g + 1), pz = __ldg(P.S.pos + 3 * g + 2);
-    for (int d = 0; d < P.n_dst; ++d) {
-      const FrustumGrid &G = P.grids[d];
-      const uint32_t DROP = (G.parity_split ? 2u : 1u) * G.n_cells + 1u;
-      const uint32_t key = frustum_key(G, P.occ[d], px, py, pz, [&]() { return __ldg(P.S.path_id + g) & 1u; });
-      if (key != DROP) bits |= 1u << d;
+    if (P.owner_map) {
+      // every receiver projects on the plane of grids[0]: footprint once (frustum_key's arithmetic with the largest
+      // pad), then the receivers under the footprint box from the owner map.  A superset of what each receiver's own
+      // key keeps (the receiver drops the rest when it builds).
+      const FrustumGrid &G = P.grids[0];
+      const uint32_t all = (1u << P.n_dst) - 1u;
+      const float qx = px - G.C[0], qy = py - G.C[1], qz = pz - G.C[2];
+      const float rho = sqrtf(qx * qx + qy * qy + qz * qz);
+      float x, y, z;
+      frustum_project(G.m, G.u, G.v, qx, qy, qz, x, y, z);
+      const float pr = P.pad_r_max * 1.001f + 1e-6f * rho;
+      if (rho <= 2.f * pr) {
+        bits = all;
+      } else if (z < 0.1f * rho) {
+        bits = rho <= 6.f * pr ? all : 0u;
+      } else {
+        const float tanT = sqrtf(x * x + y * y);
+        const float sA = pr / rho;
+        const float tanA = sA * rsqrtf(1.f - sA * sA) * 1.001f + 1e-6f;
+        const float den = 1.f - tanT * tanA;
+        const float tanS = den > 1e-3f ? (tanT + tanA) / den : 1e30f;
+        if (tanS >= 8.24f) {
+          bits = all;
+        } else {
+          const float wfoot = (tanS - tanT) * 1.01f + 1e-6f * (1.f + tanT) + 1e-5f * (1.f + tanT * tanT);
+          // too wide for a receiver's coarsest class: its NEAR bucket, whatever its rays
+          for (int d = 0; d < P.n_dst; ++d)
+            if (wfoot > P.grids[d].csize[P.grids[d].classes - 1]) bits |= 1u << d;
+          if (!(x + wfoot < P.ux0 || x - wfoot > P.ux1 || y + wfoot < P.uy0 || y - wfoot > P.uy1)) {
+            const int i0 = occ_cell(x - wfoot, P.ux0, P.uix), i1 = occ_cell(x + wfoot, P.ux0, P.uix);
+            const int j0 = occ_cell(y - wfoot, P.uy0, P.uiy), j1 = occ_cell(y + wfoot, P.uy0, P.uiy);
+            for (int jj = j0; jj <= j1 && bits != all; ++jj)
+              for (int ii = i0; ii <= i1; ++ii) bits |= __ldg(P.owner_map + jj * kOccRes + ii);
+          }
+        }
+      }
+    } else {
+      for (int d = 0; d < P.n_dst; ++d) {
+        const FrustumGrid &G = P.grids[d];
+        const uint32_t DROP = (G.parity_split ? 2u : 1u) * G.n_cells + 1u;
+        const uint32_t key = frustum_key(G, P.occ[d], px, py, pz, [&]() { return __ldg(P.S.path_id + g) & 1u; });
+        if (key != DROP) bits |= 1u << d;
+      }
     }
     P.keepbits[i] = (uint8_t)bits;
   }

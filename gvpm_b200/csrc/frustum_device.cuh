@@ -41,10 +41,17 @@ __device__ __forceinline__ uint32_t frustum_key(const FrustumGrid &G, const uint
   const float pr = G.pad_r * 1.001f + 1e-6f * rho;
   if (rho <= 2.f * pr) return NEAR;                       // alpha >= 30 degrees
   if (z < 0.1f * rho) return rho <= 6.f * pr ? NEAR : DROP;   // more than 84 degrees off axis: only reachable when very close
+  // footprint w = tan(theta + alpha) - tan(theta) with tan(theta) = |(x, y)| and sin(alpha) = pr / rho, in algebraic form
+  // (tan of a sum; no atan / asin / tan): tan(alpha) = s / sqrt(1 - s^2), slightly enlarged; theta + alpha beyond ~83
+  // degrees (tan > 8.24, or the sum past 90 degrees: non-positive denominator) is the NEAR case
   const float tanT = sqrtf(x * x + y * y);
-  const float ang = atanf(tanT) + asinf(pr / rho) * 1.0005f + 1e-6f;
-  if (ang >= 1.45f) return NEAR;
-  const float wfoot = (tanf(ang) - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
+  const float sA = pr / rho;                                  // < 0.5 here (rho > 2 pr)
+  const float tanA = sA * rsqrtf(1.f - sA * sA) * 1.001f + 1e-6f;
+  const float den = 1.f - tanT * tanA;
+  if (den <= 1e-3f) return NEAR;
+  const float tanS = (tanT + tanA) / den;
+  if (tanS >= 8.24f) return NEAR;
+  const float wfoot = (tanS - tanT) * 1.01f + 1e-6f * (1.f + tanT);   // 1 % under the class's cell edge
   if (x < G.xmin - wfoot || x > G.xmax + wfoot || y < G.ymin - wfoot || y > G.ymax + wfoot) return DROP;
   int c = 0;
   while (c < G.classes && wfoot > G.csize[c]) ++c;

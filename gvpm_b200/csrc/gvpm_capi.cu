@@ -20,7 +20,8 @@ void launch_bounds(const float *pos, uint32_t n, float *partial, float *bounds, 
 void launch_morton(const float *pos, uint32_t n, const float *bounds, uint32_t *keys, uint32_t *vals,
                    cudaStream_t st, uint32_t stride = 3);
 int pinhole_blocks(uint32_t n);
-void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st);
+void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st,
+                        const float *view_dir);
 size_t frustum_occ_bytes();
 void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, uint32_t stride, const uint32_t *par_src,
                          uint32_t par_stride, uint32_t par_shift, uint32_t n,
@@ -182,13 +183,16 @@ struct gvpm_ctx {
     int n_peers = 0, self = -1;
     uint32_t region_cap = 0;
     bool connected = false;
-    DevBuf inbox[2], ctrl, occ_all, grids_dev[2], keepbits, block_cnt;
+    DevBuf inbox[2], ctrl, occ_all, grids_dev[2], keepbits, block_cnt, owner_map;
+    bool shared_frame = false;                  // every rank projects on the same plane: one classification per photon
+    float ux0 = 0.f, uy0 = 0.f, ux1 = 0.f, uy1 = 0.f;   // bounds of the owner map (union of the ranks' ray bounds)
     RayFit fit[GVPM_MAX_PEERS];
     char *peer_inbox[2][GVPM_MAX_PEERS] = {};   // mapped (or, same process, raw) pointers; [self] = own
     uint32_t *peer_ctrl[GVPM_MAX_PEERS] = {};
     bool peer_mapped[GVPM_MAX_PEERS] = {};      // opened through CUDA IPC (to be closed)
     FrustumGrid *grids_host[2] = {nullptr, nullptr};   // pinned
-    uint32_t gen_push[2] = {0, 0}, gen_build[2] = {0, 0};
+    uint32_t gen_push[2] = {0, 0}, gen_build[2] = {0, 0}, gen_collect[2] = {0, 0};
+    std::vector<void *> shared_owned, shared_opened;   // gvpm_shared_buffer_create / _open
     cudaEvent_t ev_src = nullptr;
   } disp;
   DevBuf aos, keys_in, keys_out, vals_in, vals_out, sort_temp, planes, orig, box_lo, box_hi, bounds_partial, bounds;
@@ -214,8 +218,11 @@ struct gvpm_ctx {
   cudaEvent_t ev_hint = nullptr;
   bool hint_pending = false;
   uint32_t hint_n = 0;
+  uint32_t hint_rays = 0xffffffffu;   // ray count the hint belongs to
   double trace_photons_per_path = 0.0;   // running estimate (sizes the first batch of gvpm_trace_photons)    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
   uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
+  bool have_view_dir = false;        // gvpm_set_view_direction: axis of the perspective grid's projection plane
+  float view_dir[3] = {0.f, 0.f, 1.f};
   RayFit pin;
   float *pin_host = nullptr;         // pinned: 16 fit floats + 8 stats words
 
@@ -668,13 +675,15 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
                     &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask,
                     &ctx->disp.inbox[0], &ctx->disp.inbox[1], &ctx->disp.ctrl, &ctx->disp.occ_all, &ctx->disp.grids_dev[0], &ctx->disp.grids_dev[1],
-                    &ctx->disp.keepbits, &ctx->disp.block_cnt};
+                    &ctx->disp.keepbits, &ctx->disp.block_cnt, &ctx->disp.owner_map};
   for (int p = 0; p < ctx->disp.n_peers; ++p)
     if (ctx->disp.peer_mapped[p]) {
       for (int b = 0; b < 2; ++b) if (ctx->disp.peer_inbox[b][p]) cudaIpcCloseMemHandle(ctx->disp.peer_inbox[b][p]);
       if (ctx->disp.peer_ctrl[p]) cudaIpcCloseMemHandle(ctx->disp.peer_ctrl[p]);
     }
   for (int b = 0; b < 2; ++b) if (ctx->disp.grids_host[b]) cudaFreeHost(ctx->disp.grids_host[b]);
+  for (void *q : ctx->disp.shared_opened) cudaIpcCloseMemHandle(q);
+  for (void *q : ctx->disp.shared_owned) cudaFree(q);
   if (ctx->disp.ev_src) cudaEventDestroy(ctx->disp.ev_src);
   if (ctx->pair_count_host) cudaFreeHost(ctx->pair_count_host);
   if (ctx->sample_stats_host) cudaFreeHost(ctx->sample_stats_host);
@@ -1197,7 +1206,8 @@ static int analyse_rays(gvpm_ctx *ctx) {
   if (n == 0) return GVPM_OK;
   CK(ctx->pin_scratch.reserve(128 + (size_t)pinhole_blocks(n) * 16 * sizeof(double)));
   char *ps = ctx->pin_scratch.as<char>();
-  launch_pinhole_fit(ctx->rays.as<float4>(), n, (double *)(ps + 128), (float *)ps, (unsigned *)(ps + 64), ctx->stream);
+  launch_pinhole_fit(ctx->rays.as<float4>(), n, (double *)(ps + 128), (float *)ps, (unsigned *)(ps + 64), ctx->stream,
+                     ctx->have_view_dir ? ctx->view_dir : nullptr);
   ctx->launches += 3;
   CK(cudaMemcpyAsync(ctx->pin_host, ps, 96, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1568,9 +1578,10 @@ enum {
   DC_PUSHED = 0,                           // [2][MAX_PEERS] generation of sender s's last dispatch into my inbox b
   DC_COUNT = 2 * GVPM_MAX_PEERS,           // [2][MAX_PEERS] records sender s wrote into its region of my inbox b
   DC_FREED = 4 * GVPM_MAX_PEERS,           // [2][MAX_PEERS] generation up to which RECEIVER d has released its inbox b
-  DC_TIMEOUT = 6 * GVPM_MAX_PEERS,         // set by k_flag_wait when a peer never signalled
-  DC_OVERFLOW = 6 * GVPM_MAX_PEERS + 1,
-  DC_OCC = 6 * GVPM_MAX_PEERS + 16,        // my ray-occupancy mask (frustum_occ_bytes), copied by the peers at connect
+  DC_COLLECTED = 6 * GVPM_MAX_PEERS,       // [2][MAX_PEERS] generation of rank s's last result copy into MY image buffer b
+  DC_TIMEOUT = 8 * GVPM_MAX_PEERS,         // set by k_flag_wait when a peer never signalled
+  DC_OVERFLOW = 8 * GVPM_MAX_PEERS + 1,
+  DC_OCC = 8 * GVPM_MAX_PEERS + 16,        // my ray-occupancy mask (frustum_occ_bytes), copied by the peers at connect
 };
 struct DispatchBlob {   // what gvpm_dispatch_export writes (GVPM_DISPATCH_BLOB_BYTES)
   long long pid;
@@ -1667,6 +1678,44 @@ int gvpm_dispatch_connect(gvpm_ctx *ctx, const void *blobs, int n_peers, int sel
   CK(cudaStreamSynchronize(ctx->stream));
   D.self = self_index;
   D.connected = true;
+  // Do all ranks project on the same plane (same axis and basis - gvpm_set_view_direction - and, up to rounding, the same
+  // centre)?  Then a photon is classified ONCE: its footprint box is looked up in an owner map - kOccRes^2 cells over the
+  // union of the ranks' ray bounds, one bit per rank whose own occupancy mask has a ray under the cell (dilated by a cell)
+  // - instead of one key evaluation per receiver.
+  D.shared_frame = n_peers <= 8;
+  float cmag = 0.f;
+  for (int k = 0; k < 3; ++k) cmag = std::max(cmag, std::fabs(D.fit[0].C[k]));
+  for (int p = 1; p < n_peers && D.shared_frame; ++p)
+    for (int k = 0; k < 3; ++k)
+      D.shared_frame = D.shared_frame && D.fit[p].m[k] == D.fit[0].m[k] && D.fit[p].u[k] == D.fit[0].u[k] &&
+                       D.fit[p].v[k] == D.fit[0].v[k] && std::fabs(D.fit[p].C[k] - D.fit[0].C[k]) <= 1e-5f * (1.f + cmag);
+  if (D.shared_frame) {
+    const int R = (int)std::lround(std::sqrt((double)frustum_occ_bytes() * 8.0));   // kOccRes
+    D.ux0 = D.uy0 = 3.4e38f; D.ux1 = D.uy1 = -3.4e38f;
+    for (int p = 0; p < n_peers; ++p) {
+      D.ux0 = std::min(D.ux0, D.fit[p].xmin); D.ux1 = std::max(D.ux1, D.fit[p].xmax);
+      D.uy0 = std::min(D.uy0, D.fit[p].ymin); D.uy1 = std::max(D.uy1, D.fit[p].ymax);
+    }
+    const double uw = std::max((double)D.ux1 - D.ux0, 1e-20), uh = std::max((double)D.uy1 - D.uy0, 1e-20);
+    std::vector<uint32_t> occ(frustum_occ_bytes() / 4 * (size_t)n_peers);
+    CK(cudaMemcpy(occ.data(), D.occ_all.p, occ.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> map((size_t)R * R, 0);
+    for (int p = 0; p < n_peers; ++p) {
+      const gvpm_ctx::RayFit &F = D.fit[p];
+      const double wx = std::max((double)F.xmax - F.xmin, 1e-20) / R, wy = std::max((double)F.ymax - F.ymin, 1e-20) / R;
+      const uint32_t *o = occ.data() + (frustum_occ_bytes() / 4) * (size_t)p;
+      for (int j = 0; j < R; ++j)
+        for (int i = 0; i < R; ++i) {
+          if (!(o[(j * R + i) >> 5] >> ((j * R + i) & 31) & 1u)) continue;
+          const int i0 = (int)std::floor((F.xmin + i * wx - D.ux0) / uw * R) - 1, i1 = (int)std::floor((F.xmin + (i + 1) * wx - D.ux0) / uw * R) + 1;
+          const int j0 = (int)std::floor((F.ymin + j * wy - D.uy0) / uh * R) - 1, j1 = (int)std::floor((F.ymin + (j + 1) * wy - D.uy0) / uh * R) + 1;
+          for (int jj = std::max(j0, 0); jj <= std::min(j1, R - 1); ++jj)
+            for (int ii = std::max(i0, 0); ii <= std::min(i1, R - 1); ++ii) map[(size_t)jj * R + ii] |= (uint8_t)(1u << p);
+        }
+    }
+    CK(D.owner_map.reserve(map.size()));
+    CK(cudaMemcpy(D.owner_map.p, map.data(), map.size(), cudaMemcpyHostToDevice));
+  }
   return GVPM_OK;
 }
 
@@ -1678,9 +1727,16 @@ int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin
   if (!ctx->ph_staging.p || ctx->ph_staging.cap < PhotonLayout(n_total).bytes)
     return fail(ctx, GVPM_ERR_INVALID, "size the selected photon staging buffer for n_total first (gvpm_photon_staging)");
   cudaSetDevice(ctx->device);
+  // after_stream == the context's own stream: the dispatch runs IN that stream (between a build and its gather, say: a
+  // side stream only gets CTA slots as the persistent gather kernels retire theirs, and every rank's next build waits for
+  // the slowest rank's dispatch); any other stream / NULL: on the internal highest-priority stream, after that work
   cudaStream_t ks = ctx->push_kernel_stream;
-  CK(cudaEventRecord(D.ev_src, after_stream ? (cudaStream_t)after_stream : ctx->stream));
-  CK(cudaStreamWaitEvent(ks, D.ev_src, 0));
+  if (after_stream == (void *)ctx->stream) {
+    ks = ctx->stream;
+  } else {
+    CK(cudaEventRecord(D.ev_src, after_stream ? (cudaStream_t)after_stream : ctx->stream));
+    CK(cudaStreamWaitEvent(ks, D.ev_src, 0));
+  }
   const uint32_t gen = ++D.gen_push[which];
   uint32_t *ctrl = D.ctrl.as<uint32_t>();
   // every receiver must have released its inbox `which` gen - 1 times (flags the receivers write into MY control block)
@@ -1689,17 +1745,16 @@ int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin
     ctx->launches += 1;
   }
   const bool parity = ctx->have_cfg && ctx->cfg.path_set && !ctx->cfg.sppm_primal;
-  for (int d = 0; d < D.n_peers; ++d) D.grids_host[which][d] = make_frustum_grid(D.fit[d], radius, parity);
-  CK(cudaMemcpyAsync(D.grids_dev[which].p, D.grids_host[which], sizeof(FrustumGrid) * D.n_peers, cudaMemcpyHostToDevice, ks));
   const uint32_t nb = (uint32_t)((count + 255) / 256);
   CK(D.keepbits.reserve(std::max<size_t>(count, 256)));
   CK(D.block_cnt.reserve((size_t)GVPM_MAX_PEERS * (nb + 2) * 4));
+  static_assert(sizeof(DispatchParams) <= 4000, "kernel parameter space");
   DispatchParams P{};
   P.S = photon_staging_ptrs(ctx->ph_staging.p, n_total);
   P.begin = (uint32_t)begin;
   P.count = (uint32_t)count;
   P.n_dst = D.n_peers;
-  P.grids = D.grids_dev[which].as<FrustumGrid>();
+  for (int d = 0; d < D.n_peers; ++d) P.grids[d] = make_frustum_grid(D.fit[d], radius, parity);
   P.region_cap = D.region_cap;
   P.keepbits = D.keepbits.as<uint8_t>();
   P.block_cnt = D.block_cnt.as<uint32_t>();
@@ -1716,6 +1771,16 @@ int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin
     P.inbox[d] = (float4 *)(D.peer_inbox[which][d] + (size_t)D.self * D.region_cap * 128);
     Sg.count_dst[d] = D.peer_ctrl[d] + DC_COUNT + which * GVPM_MAX_PEERS + D.self;
     Sg.flag_dst[d] = D.peer_ctrl[d] + DC_PUSHED + which * GVPM_MAX_PEERS + D.self;
+  }
+  P.owner_map = D.shared_frame ? D.owner_map.as<uint8_t>() : nullptr;
+  if (D.shared_frame) {
+    P.ux0 = D.ux0; P.uy0 = D.uy0;
+    P.uix = (float)(std::sqrt((double)frustum_occ_bytes() * 8.0) / std::max((double)D.ux1 - D.ux0, 1e-20));
+    P.uiy = (float)(std::sqrt((double)frustum_occ_bytes() * 8.0) / std::max((double)D.uy1 - D.uy0, 1e-20));
+    P.ux1 = D.ux1; P.uy1 = D.uy1;
+    P.pad_r_max = 0.f;
+    for (int d = 0; d < D.n_peers; ++d) P.pad_r_max = std::max(P.pad_r_max, P.grids[d].pad_r);
+    P.pad_r_max += 2e-5f * (1.f + std::fabs(P.grids[0].C[0]) + std::fabs(P.grids[0].C[1]) + std::fabs(P.grids[0].C[2]));   // the centres agree to 1e-5
   }
   launch_dispatch(P, ks);
   launch_dispatch_signal(Sg, ks);
@@ -1771,6 +1836,72 @@ int gvpm_dispatch_release(gvpm_ctx *ctx, int which) {
   F.value = D.gen_build[which];
   for (int s = 0; s < D.n_peers; ++s) F.dst[s] = D.peer_ctrl[s] + DC_FREED + which * GVPM_MAX_PEERS + D.self;
   launch_flag_set(F, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return GVPM_OK;
+}
+
+
+// ---- result collection over the copy engines (rank 0's image buffer, written by every rank) -------------------------------
+int gvpm_shared_buffer_create(gvpm_ctx *ctx, size_t bytes, void **dev, void *handle) {
+  if (!ctx || !dev || !handle || bytes == 0) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  void *p = nullptr;
+  CK(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); CK(e); }
+  ctx->disp.shared_owned.push_back(p);
+  static_assert(sizeof(cudaIpcMemHandle_t) + 16 <= GVPM_SHARED_HANDLE_BYTES, "handle size");
+  memset(handle, 0, GVPM_SHARED_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof(h));
+  const long long pid = (long long)getpid();
+  memcpy((char *)handle + sizeof(h), &pid, 8);
+  memcpy((char *)handle + sizeof(h) + 8, &p, 8);
+  *dev = p;
+  return GVPM_OK;
+}
+
+int gvpm_shared_buffer_open(gvpm_ctx *ctx, const void *handle, void **dev) {
+  if (!ctx || !dev || !handle) return GVPM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaIpcMemHandle_t h;
+  long long pid = 0;
+  void *raw = nullptr;
+  memcpy(&h, handle, sizeof(h));
+  memcpy(&pid, (const char *)handle + sizeof(h), 8);
+  memcpy(&raw, (const char *)handle + sizeof(h) + 8, 8);
+  if (pid == (long long)getpid()) { *dev = raw; return GVPM_OK; }   // same process: the pointer is valid as it is
+  void *p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->disp.shared_opened.push_back(p);
+  *dev = p;
+  return GVPM_OK;
+}
+
+int gvpm_collect_signal(gvpm_ctx *ctx, int which, int root, void *stream) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected || root < 0 || root >= D.n_peers) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  cudaSetDevice(ctx->device);
+  FlagSetParams F{};
+  F.n = 1;
+  F.value = ++D.gen_collect[which];
+  F.dst[0] = D.peer_ctrl[root] + DC_COLLECTED + which * GVPM_MAX_PEERS + D.self;
+  launch_flag_set(F, stream ? (cudaStream_t)stream : ctx->stream);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return GVPM_OK;
+}
+
+int gvpm_collect_wait(gvpm_ctx *ctx, int which) {
+  if (!ctx || (which != 0 && which != 1)) return GVPM_ERR_INVALID;
+  gvpm_ctx::Dispatch &D = ctx->disp;
+  if (!D.connected) return fail(ctx, GVPM_ERR_INVALID, "gvpm_dispatch_connect has not been called");
+  cudaSetDevice(ctx->device);
+  uint32_t *ctrl = D.ctrl.as<uint32_t>();
+  // every rank signals once per iteration and buffer: wait until all have caught up with this rank's own count
+  launch_flag_wait(ctrl + DC_COLLECTED + which * GVPM_MAX_PEERS, D.n_peers, D.gen_collect[which], ctrl + DC_TIMEOUT, ctx->stream);
   ctx->launches += 1;
   CK(cudaGetLastError());
   return GVPM_OK;
@@ -1837,6 +1968,18 @@ int gvpm_staging_peek(gvpm_ctx *ctx, int which, void **dev, size_t *count) {
 
 int gvpm_accel_kind(const gvpm_ctx *ctx) { return ctx ? ctx->accel : 0; }
 
+int gvpm_set_view_direction(gvpm_ctx *ctx, const float dir[3]) {
+  if (!ctx) return GVPM_ERR_INVALID;
+  if (dir) {
+    const double l = std::sqrt((double)dir[0] * dir[0] + (double)dir[1] * dir[1] + (double)dir[2] * dir[2]);
+    if (!(l > 0.0) || !std::isfinite(l)) return fail(ctx, GVPM_ERR_INVALID, "view direction must be a non-zero vector");
+    for (int k = 0; k < 3; ++k) ctx->view_dir[k] = dir[k];
+  }
+  ctx->have_view_dir = dir != nullptr;
+  ctx->pin_gen = ~0ull;   // the rays are analysed again with the new axis
+  return GVPM_OK;
+}
+
 int gvpm_ray_staging(gvpm_ctx *ctx, size_t n, void **dev, size_t *bytes) {
   if (!ctx || n > 0xfffffff0u) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
@@ -1864,6 +2007,12 @@ int gvpm_commit_rays(gvpm_ctx *ctx) {
     CK(cudaGetLastError());
   }
   ctx->rays_loaded = true;
+  if (n != ctx->hint_rays) {   // another ray set (not a re-jittered one): what the last build kept says nothing about the next
+    ctx->hint_rays = n;
+    ctx->kept_hint_valid = false;
+    ctx->hint_pending = false;
+    ctx->kept_fraction_hint = 1.0;
+  }
   return GVPM_OK;
 }
 

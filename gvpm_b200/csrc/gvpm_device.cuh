@@ -218,7 +218,8 @@ struct DispatchParams {
   PhotonStaging S;                 // this rank's staging arrays (whole-set layout)
   uint32_t begin, count;           // the slice [begin, begin + count) is dispatched
   int n_dst;
-  const FrustumGrid *grids;        // [n_dst] device
+  FrustumGrid grids[GVPM_MAX_PEERS];   // the receivers' grids, by value: kernel parameters live in the constant bank, and
+                                       // every thread reads the same field of the same grid at the same time
   const uint32_t *occ[GVPM_MAX_PEERS];   // local copies of the receivers' occupancy masks
   float4 *inbox[GVPM_MAX_PEERS];   // receiver d's inbox region of THIS sender (peer-mapped; local for d = self)
   uint32_t region_cap;             // records per region
@@ -226,6 +227,10 @@ struct DispatchParams {
   uint32_t *block_cnt;             // [n_dst][nb + 1]: counts, then exclusive offsets (+ total at [nb])
   uint32_t nb;
   unsigned *overflow;              // set when a region would overflow (cannot happen with region_cap >= count)
+  // shared projection plane (all receivers use the frame of grids[0]): one classification per photon against the owner map
+  const uint8_t *owner_map;        // kOccRes x kOccRes cells over [ux0, ux1] x [uy0, uy1], bit d = receiver d has rays there
+  float ux0, uy0, ux1, uy1, uix, uiy;   // bounds, cells per unit
+  float pad_r_max;                 // largest r + delta of the receivers (+ the slack for their slightly different centres)
 };
 
 struct SignalParams {

@@ -87,17 +87,24 @@ __global__ void __launch_bounds__(256) k_sub_count(const float *__restrict__ len
     block_tot[blockIdx.x] = t;
   }
 }
-// exclusive scan of nb block totals in place by ONE block (nb <= a few thousand); total -> total_out[0]
+// exclusive scan of nb block totals in place by ONE block (a few thousand to a few ten thousand entries: every thread
+// owns 8 consecutive ones, 8192 per round); total -> total_out[0]
 __global__ void __launch_bounds__(1024) k_sub_scan(uint32_t *__restrict__ block_tot, uint32_t nb, uint32_t *__restrict__ total_out) {
   __shared__ uint32_t ws[32];
   __shared__ uint32_t carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < nb; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nb ? block_tot[i] : 0u;
-    uint32_t inc = v;
+  constexpr uint32_t kPer = 8;
+  for (uint32_t base = 0; base < nb; base += 1024 * kPer) {
+    const uint32_t i0 = base + threadIdx.x * kPer;
+    uint32_t v[kPer], sum = 0u;
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      v[k] = i0 + k < nb ? block_tot[i0 + k] : 0u;
+      sum += v[k];
+    }
+    uint32_t inc = sum;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += u;
@@ -113,10 +120,14 @@ __global__ void __launch_bounds__(1024) k_sub_scan(uint32_t *__restrict__ block_
       ws[lane] = xi - x;   // exclusive prefix of the warp totals
     }
     __syncthreads();
-    const uint32_t excl = carry + ws[w] + (inc - v);
-    if (i < nb) block_tot[i] = excl;
+    uint32_t excl = carry + ws[w] + (inc - sum);
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+      if (i0 + k < nb) block_tot[i0 + k] = excl;
+      excl += v[k];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
+    if (threadIdx.x == 1023) carry = excl;
     __syncthreads();
   }
   if (threadIdx.x == 0) total_out[0] = carry;

@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(256) k_pinhole_accum(const float4 *__restrict_
   }
 }
 // fit[0..2] = C, [3..5] = m, [6..8] = u, [9..11] = v, [12] = count, [13] = conditioning (det / trace^3; 0 = no point)
-__global__ void k_pinhole_solve(const double *__restrict__ partial, int nb, float *__restrict__ fit) {
+__global__ void k_pinhole_solve(const double *__restrict__ partial, int nb, float *__restrict__ fit, int use_dir, float dir_x,
+                                float dir_y, float dir_z) {
   double a[13];
   for (int k = 0; k < 13; ++k) {
     double v = 0.0;
@@ -522,6 +523,11 @@ __global__ void k_pinhole_solve(const double *__restrict__ partial, int nb, floa
   double ml = sqrt(a[9] * a[9] + a[10] * a[10] + a[11] * a[11]);
   double m[3] = {0, 0, 1};
   if (ml > 0.0) { m[0] = a[9] / ml; m[1] = a[10] / ml; m[2] = a[11] / ml; } else cond = 0.0;
+  if (use_dir) {   // the caller's view direction (gvpm_set_view_direction): every rank of a sharded image then projects
+                   // on the same plane, whatever part of the image its own rays cover
+    const double dl = sqrt((double)dir_x * dir_x + (double)dir_y * dir_y + (double)dir_z * dir_z);
+    m[0] = dir_x / dl; m[1] = dir_y / dl; m[2] = dir_z / dl;
+  }
   // any orthonormal basis of the plane orthogonal to m
   double t[3] = {0, 0, 0};
   if (fabs(m[0]) <= fabs(m[1]) && fabs(m[0]) <= fabs(m[2])) t[0] = 1; else if (fabs(m[1]) <= fabs(m[2])) t[1] = 1; else t[2] = 1;
@@ -788,10 +794,12 @@ void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keep
 // ---- frustum grid launchers ----
 int pinhole_blocks(uint32_t n) { int b = (int)((n + 255) / 256); return b < 1 ? 1 : (b > 512 ? 512 : b); }
 // partial: [pinhole_blocks * 16] doubles; fit: 16 floats; stats: 8 words (zeroed here)
-void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st) {
+void launch_pinhole_fit(const float4 *rays, uint32_t n, double *partial, float *fit, unsigned *stats, cudaStream_t st,
+                        const float *view_dir) {
   const int nb = pinhole_blocks(n);
   k_pinhole_accum<<<nb, 256, 0, st>>>(rays, n, partial);
-  k_pinhole_solve<<<1, 1, 0, st>>>(partial, nb, fit);
+  k_pinhole_solve<<<1, 1, 0, st>>>(partial, nb, fit, view_dir ? 1 : 0, view_dir ? view_dir[0] : 0.f, view_dir ? view_dir[1] : 0.f,
+                                  view_dir ? view_dir[2] : 1.f);
   cudaMemsetAsync(stats, 0, 32, st);
   k_pinhole_check<<<nb, 256, 0, st>>>(rays, n, fit, stats);
 }

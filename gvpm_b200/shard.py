@@ -39,6 +39,30 @@ def band_indices(px, py, width, height, world, rank, cycles=2, block=BLOCK):
     return np.nonzero(band_owner(px, py, width, height, world, cycles, block) == rank)[0]
 
 
+def block_index(px, py, height, block=BLOCK):
+    """column-major index of each ray's gather block (the order band_owner cuts into runs)"""
+    tiles_y = (height + block - 1) // block
+    return (np.asarray(px) // block).astype(np.int64) * tiles_y + (np.asarray(py) // block)
+
+
+def band_owner_weighted(px, py, width, height, world, block_cost, cycles=2, block=BLOCK):
+    """band_owner with runs of (almost) equal COST instead of equal block count: block_cost[t] is what gather block t
+    (column-major) cost in the previous iteration (contributing pairs + a per-ray term).  The photon density of a
+    rendered scene is far from uniform over the image, and a sharded iteration is as slow as its busiest rank."""
+    tiles_x = (width + block - 1) // block
+    tiles_y = (height + block - 1) // block
+    n_tiles = tiles_x * tiles_y
+    cost = np.maximum(np.asarray(block_cost, dtype=np.float64).reshape(-1)[:n_tiles], 0.0)
+    assert cost.size == n_tiles
+    runs = max(1, min(n_tiles, cycles * world))
+    total = cost.sum()
+    if not total > 0:
+        return band_owner(px, py, width, height, world, cycles, block)
+    before = np.cumsum(cost) - cost                      # cost in front of each block
+    run_of_block = np.minimum((before / total * runs).astype(np.int64), runs - 1)
+    return run_of_block[block_index(px, py, height, block)] % world
+
+
 def assemble(parts, index_lists, n_total, width=27):
     """Scatter per-rank result rows back to the global ray order.  parts[r]: [>=len(idx_r), width]."""
     out = np.zeros((n_total, width), dtype=np.float32)

@@ -278,7 +278,9 @@ int gvpm_peer_push_mode(gvpm_ctx *ctx, int sm_ctas);
  *   gvpm_dispatch_photons  classifies photons [begin, begin+count) of the selected staging buffer (sized for n_total by
  *                          gvpm_photon_staging) for search radius `radius` and writes them into inbox `which` of every
  *                          rank, on an internal highest-priority stream, after the work queued on `after_stream`
- *                          (NULL = the context's stream) and after every receiver's release of that inbox;
+ *                          (NULL = the context's stream) and after every receiver's release of that inbox; with
+ *                          after_stream = gvpm_stream(ctx) itself the dispatch is queued IN the context's stream (e.g.
+ *                          between a build and its gather, where no persistent gather kernel holds the SMs);
  *   gvpm_build_dispatched  waits (on the context's stream) until every rank's records for inbox `which` have landed,
  *                          then builds the perspective grid over them: the gathers (gvpm_gather_bre*) run as after
  *                          gvpm_build_points_for_rays, with identical neighbour sets and results;
@@ -299,6 +301,16 @@ int gvpm_build_dispatched(gvpm_ctx *ctx, int which, float radius, uint32_t *n_ke
 int gvpm_dispatch_release(gvpm_ctx *ctx, int which);
 int gvpm_dispatch_join(gvpm_ctx *ctx);
 int gvpm_dispatch_status(gvpm_ctx *ctx, uint32_t counts[GVPM_MAX_PEERS], int which);
+/* Result collection ("the primal and gradient buffers gathered at the end of each iteration"): a device buffer that other
+ * ranks can write (CUDA IPC).  The root creates it, the ranks open it and copy their rows in with a plain device-to-device
+ * copy on a side stream - copy engines over NVLink, no SMs taken from the gather kernels - then signal; the root waits for
+ * every rank's signal on its stream before it reads the image.  (Needs gvpm_dispatch_connect: the signals are generation
+ * flags in the root's control block, one set per buffer `which`.) */
+#define GVPM_SHARED_HANDLE_BYTES 96
+int gvpm_shared_buffer_create(gvpm_ctx *ctx, size_t bytes, void **dev, void *handle /* [GVPM_SHARED_HANDLE_BYTES] */);
+int gvpm_shared_buffer_open(gvpm_ctx *ctx, const void *handle, void **dev);
+int gvpm_collect_signal(gvpm_ctx *ctx, int which, int root, void *stream /* the stream the copy was queued on */);
+int gvpm_collect_wait(gvpm_ctx *ctx, int which);
 /* Hilbert sort + implicit 32-ary AABB hierarchy for search radius `radius`
  * (= bsphereR*globalScaleVolume*0.01, gvpm.cpp:989) */
 int gvpm_build_points(gvpm_ctx *ctx, float radius);
@@ -318,6 +330,11 @@ int gvpm_build_points_for_rays(gvpm_ctx *ctx, float radius, uint32_t *n_kept);
  * around its own direction - no traversal.  Same neighbour sets, same results.  n_kept (photons some ray can reach)
  * then costs one device read-back: pass NULL when it is not needed.  gvpm_accel_kind: 0 = box hierarchy, 1 = grid. */
 int gvpm_accel_kind(const gvpm_ctx *ctx);
+/* Optional: the axis of the perspective grid's projection plane (default: the mean direction of the uploaded rays).
+ * The sensor's viewing direction is the natural choice; ranks of a sharded image that all pass the same vector project
+ * on the same plane, which lets gvpm_dispatch_photons classify a photon once for all receivers.  NULL: back to the
+ * default.  Any direction within ~69 degrees of every ray works; results do not depend on it. */
+int gvpm_set_view_direction(gvpm_ctx *ctx, const float dir[3]);
 
 /* ---- camera rays --------------------------------------------------------------------- */
 int gvpm_upload_rays(gvpm_ctx *ctx, const gvpm_ray_soa *r, size_t n);

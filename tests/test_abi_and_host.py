@@ -272,6 +272,36 @@ def test_band_sharding_partitions_every_ray_once_in_compact_bands():
     assert set(np.unique(o)) == {0, 1}
 
 
+def test_weighted_bands_balance_cost_and_still_partition():
+    """band_owner_weighted: every ray owned once, contiguous column-major runs, costs per rank within a few per cent of
+    each other for a centre-weighted density (the uniform deal is far off), identical to band_owner for uniform costs"""
+    from gvpm_b200 import shard
+    w, h = 1920, 1080
+    py, px = np.mgrid[0:h:8, 0:w:8]
+    px, py = px.ravel(), py.ravel()
+    tiles_x, tiles_y = 60, 34
+    bx = np.repeat(np.arange(tiles_x), tiles_y)
+    by = np.tile(np.arange(tiles_y), tiles_x)
+    cost = 1.0 + 8.0 * np.exp(-((bx - 30) / 9.0) ** 2 - ((by - 17) / 7.0) ** 2)     # bright centre
+    t = shard.block_index(px, py, h)
+    ray_cost = cost[t]
+    for world in (2, 4, 8):
+        for cycles in (1, 2):
+            o = shard.band_owner_weighted(px, py, w, h, world, cost, cycles)
+            assert o.min() == 0 and o.max() == world - 1
+            per = np.array([ray_cost[o == r].sum() for r in range(world)])
+            assert per.max() / per.mean() < 1.05, (world, cycles, per / per.mean())
+            uni = shard.band_owner(px, py, w, h, world, cycles)
+            per_u = np.array([ray_cost[uni == r].sum() for r in range(world)])
+            assert per_u.max() / per_u.mean() >= per.max() / per.mean()
+            # runs are contiguous in the column-major block order: a rank owns at most `cycles` intervals of it
+            for r in range(world):
+                blocks = np.unique(t[o == r])
+                assert (np.diff(blocks) > 1).sum() <= cycles - 1 + 0
+    np.testing.assert_array_equal(shard.band_owner_weighted(px, py, w, h, 8, np.ones(tiles_x * tiles_y), 2),
+                                  shard.band_owner(px, py, w, h, 8, 2))
+
+
 GLOO_WORKER = r"""
 import os, sys
 import numpy as np

@@ -13,7 +13,7 @@ from gvpm_b200 import shard
 pytestmark = pytest.mark.gpu
 
 
-def _ranks(case, world, cycles):
+def _ranks(case, world, cycles, view_dir=None):
     from gvpm_b200.api import Context
     n = case.photons.n
     assert n % world == 0
@@ -26,6 +26,8 @@ def _ranks(case, world, cycles):
         ctx.set_medium(case.medium)
         ctx.set_config(case.config)
         ctx.set_occluders(case.tri)
+        if view_dir is not None:   # every rank projects on the same plane: photons are classified once (owner map)
+            ctx.set_view_direction(view_dir)
         ctx.upload_rays(r)
         ctx.photon_staging(n)
         ctx.upload_photons_slice(case.photons.take(np.arange(rank * n_slice, (rank + 1) * n_slice)), n, rank * n_slice)
@@ -42,10 +44,10 @@ def _oracle(case, rays):
     return ob.bre_gather(case.photons, rays, case.medium, case.config, case.tri, case.radius, mode="brute", neighbours=True)
 
 
-@pytest.mark.parametrize("world,cycles", [(2, 2), (4, 1)])
-def test_dispatched_gather_equals_oracle(built, world, cycles):
+@pytest.mark.parametrize("world,cycles,view_dir", [(2, 2, None), (4, 1, None), (4, 2, (0.0, 0.0, 1.0)), (8, 1, (0.05, -0.02, 1.0))])
+def test_dispatched_gather_equals_oracle(built, world, cycles, view_dir):
     case = H.make_case(n_photons=120000, w=256, h=64, scale=1.0)
-    ctxs, rays, n_slice = _ranks(case, world, cycles)
+    ctxs, rays, n_slice = _ranks(case, world, cycles, view_dir)
     n = case.photons.n
     received = 0
     for it in range(3):   # three iterations: both inboxes, and a reuse of the first one (release / free flags)
@@ -66,7 +68,8 @@ def test_dispatched_gather_equals_oracle(built, world, cycles):
             np.testing.assert_array_equal(offsets, ref.offsets)
             np.testing.assert_array_equal(idx, ref.idx)
             got = c.dispatch_status(b)
-            assert 0.999 * sum(got) <= kept <= sum(got) and all(g <= n_slice for g in got)
+            # the owner map of the shared-frame dispatch is a (dilated) superset of each receiver's own keep test
+            assert (0.999 if view_dir is None else 0.8) * sum(got) <= kept <= sum(got) and all(g <= n_slice for g in got)
             assert kept >= len(np.unique(ref.idx & 0x7fffffff))
             if it == 2:
                 received += kept
