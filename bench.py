@@ -1090,7 +1090,7 @@ def main():
         if coll_done[b] is not None:            # the result buffer of step k - 2 has been gathered
             stream.wait_event(coll_done[b])
             coll_done[b] = None
-        side = os.environ.get("GVPM_DISPATCH_STREAM", "inline") == "side"
+        side = os.environ.get("GVPM_DISPATCH_STREAM", "side") == "side"
         if side:   # on the library's priority stream, concurrently with this step (starved by the persistent gather kernels)
             ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)
         with torch.cuda.stream(stream):

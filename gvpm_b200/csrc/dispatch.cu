@@ -25,7 +25,10 @@
 namespace gvpm {
 
 __global__ void __launch_bounds__(256) k_dispatch_classify(const __grid_constant__ DispatchParams P) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // a CTA takes chunks blk, blk + gridDim.x, ... of 256 photons: the launch may be a small persistent grid (a side
+  // stream next to the gather kernels gets few CTA slots, and keeps them)
+  for (uint32_t blk = blockIdx.x; blk < P.nb; blk += gridDim.x) {
+  const uint32_t i = blk * blockDim.x + threadIdx.x;
   uint32_t bits = 0u;
   if (i < P.count) {
     const size_t g = (size_t)P.begin + i;
@@ -86,7 +89,9 @@ __global__ void __launch_bounds__(256) k_dispatch_classify(const __grid_constant
   if (threadIdx.x < (unsigned)P.n_dst) {
     uint32_t t = 0;
     for (int k = 0; k < 8; ++k) t += wcnt[k][threadIdx.x];
-    P.block_cnt[(size_t)threadIdx.x * (P.nb + 1) + blockIdx.x] = t;
+    P.block_cnt[(size_t)threadIdx.x * (P.nb + 1) + blk] = t;
+  }
+  __syncthreads();
   }
 }
 
@@ -130,7 +135,8 @@ __global__ void __launch_bounds__(256) k_dispatch_emit(const __grid_constant__ D
   __shared__ float4 tile[8][32 * 9];   // per warp: 32 records x 8 float4, row stride 9 float4 (as k_pack_aos)
   __shared__ uint32_t wcnt[8][GVPM_MAX_PEERS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t blk = blockIdx.x; blk < P.nb; blk += gridDim.x) {
+  const uint32_t i = blk * blockDim.x + threadIdx.x;
   const uint32_t bits = i < P.count ? P.keepbits[i] : 0u;
   for (int d = 0; d < P.n_dst; ++d) {
     const uint32_t m = __ballot_sync(0xffffffffu, (bits >> d) & 1u);
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(256) k_dispatch_emit(const __grid_constant__ D
   for (int d = 0; d < P.n_dst; ++d) {
     const uint32_t m = __ballot_sync(0xffffffffu, (bits >> d) & 1u);
     if (m == 0u) continue;
-    uint32_t slot = P.block_cnt[(size_t)d * (P.nb + 1) + blockIdx.x];
+    uint32_t slot = P.block_cnt[(size_t)d * (P.nb + 1) + blk];
     for (int k = 0; k < w; ++k) slot += wcnt[k][d];
     const uint32_t cnt = __popc(m);
     if (slot + cnt > P.region_cap) {
@@ -169,6 +175,8 @@ __global__ void __launch_bounds__(256) k_dispatch_emit(const __grid_constant__ D
       const int src = __fns(m, 0, (q >> 3) + 1);   // lane holding the (q >> 3)-th kept record
       dst[q] = t[src * 9 + (q & 7u)];
     }
+  }
+  __syncthreads();
   }
 }
 
@@ -209,14 +217,16 @@ __global__ void k_translate_idx(uint32_t *__restrict__ idx, unsigned long long n
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------
-void launch_dispatch(const DispatchParams &P, cudaStream_t st) {
+// ctas > 0: persistent grids of that many CTAs (a side stream: few slots, held to the end); 0: one CTA per chunk
+void launch_dispatch(const DispatchParams &P, cudaStream_t st, int ctas) {
   if (P.count == 0) {
     cudaMemsetAsync(P.block_cnt, 0, (size_t)P.n_dst * (P.nb + 1) * 4, st);
     return;
   }
-  k_dispatch_classify<<<P.nb, 256, 0, st>>>(P);
+  const uint32_t grid = ctas > 0 ? (uint32_t)ctas < P.nb ? (uint32_t)ctas : P.nb : P.nb;
+  k_dispatch_classify<<<grid, 256, 0, st>>>(P);
   k_dispatch_scan<<<P.n_dst, 1024, 0, st>>>(P.block_cnt, P.nb);
-  k_dispatch_emit<<<P.nb, 256, 0, st>>>(P);
+  k_dispatch_emit<<<grid, 256, 0, st>>>(P);
 }
 void launch_dispatch_signal(const SignalParams &P, cudaStream_t st) { k_dispatch_signal<<<1, 32, 0, st>>>(P); }
 void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *timeout, cudaStream_t st) {

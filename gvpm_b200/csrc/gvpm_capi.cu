@@ -29,7 +29,7 @@ void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, 
                          uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st, uint32_t region_cap = 0,
                          const uint32_t *region_count = nullptr);
 void launch_frustum_mark(const float4 *rays, uint32_t n_rays, const FrustumGrid &G, uint32_t *occ, int sm_count, cudaStream_t st);
-void launch_dispatch(const DispatchParams &P, cudaStream_t st);
+void launch_dispatch(const DispatchParams &P, cudaStream_t st, int ctas);
 void launch_dispatch_signal(const SignalParams &P, cudaStream_t st);
 void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *timeout, cudaStream_t st);
 void launch_flag_set(const FlagSetParams &P, cudaStream_t st);
@@ -221,6 +221,7 @@ struct gvpm_ctx {
   uint32_t hint_rays = 0xffffffffu;   // ray count the hint belongs to
   double trace_photons_per_path = 0.0;   // running estimate (sizes the first batch of gvpm_trace_photons)    // pin_scratch: [0,64) fit floats, [64,96) stats words, [128,..) block partials (doubles)
   uint64_t pin_gen = ~0ull;          // rays_gen the ray analysis below belongs to
+  int dispatch_ctas = 0;             // side-stream dispatch: CTAs of its persistent grids (GVPM_DISPATCH_CTAS; 0 = one per chunk)
   bool have_view_dir = false;        // gvpm_set_view_direction: axis of the perspective grid's projection plane
   float view_dir[3] = {0.f, 0.f, 1.f};
   RayFit pin;
@@ -653,6 +654,8 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   cudaHostAlloc((void **)&ctx->pin_host, 128, cudaHostAllocDefault);
   cudaEventCreateWithFlags(&ctx->ev_hint, cudaEventDisableTiming);
   { const char *e = getenv("GVPM_ACCEL"); ctx->force_bvh = e && !strcmp(e, "bvh"); }
+  // side-stream dispatch: one CTA per SM by default (N = 8, cfg5: 32 CTAs 1.96 ms / step, 96: 1.11, one per chunk: 1.13)
+  { const char *e = getenv("GVPM_DISPATCH_CTAS"); ctx->dispatch_ctas = e ? std::max(0, atoi(e)) : -1; }
   cudaHostAlloc((void **)&ctx->sample_stats_host, 64, cudaHostAllocDefault);
   memset(ctx->sample_stats_host, 0, 64);
   ctx->bounds.reserve(256);
@@ -1782,7 +1785,8 @@ int gvpm_dispatch_photons(gvpm_ctx *ctx, int which, size_t n_total, size_t begin
     for (int d = 0; d < D.n_peers; ++d) P.pad_r_max = std::max(P.pad_r_max, P.grids[d].pad_r);
     P.pad_r_max += 2e-5f * (1.f + std::fabs(P.grids[0].C[0]) + std::fabs(P.grids[0].C[1]) + std::fabs(P.grids[0].C[2]));   // the centres agree to 1e-5
   }
-  launch_dispatch(P, ks);
+  // on the side stream: a small persistent grid (GVPM_DISPATCH_CTAS, default one CTA per SM); in-stream: one CTA per chunk
+  launch_dispatch(P, ks, ks == ctx->stream ? 0 : (ctx->dispatch_ctas < 0 ? ctx->sm_count : ctx->dispatch_ctas));
   launch_dispatch_signal(Sg, ks);
   ctx->launches += 4;
   CK(cudaGetLastError());
