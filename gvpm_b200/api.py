@@ -468,13 +468,21 @@ class Context:
             idx = idx[np.lexsort((idx & np.uint32(0x7FFFFFFF), seg))]
         return offsets, idx
 
-    def compute_gradient(self, acc, w, h, use_abs=False):
+    def compute_gradient(self, acc, w, h, use_abs=False, reuse_primal=False, inv_emitted=1.0):
+        """computeGradient (gvpm.cpp:1205-1306); reuse_primal: throughput by gvpm.cpp:503-532 (inv_emitted = 1 for the
+        APA estimators, 1 / totalEmittedVolume for G-VPM)"""
         acc = np.ascontiguousarray(acc, dtype=np.float32).reshape(-1)
         assert acc.size == w * h * N.GVPM_OUT_FLOATS
         thr, gx, gy = (np.empty(w * h * 3, dtype=np.float32) for _ in range(3))
-        self._ck(self.lib.gvpm_compute_gradient(self.h, acc.ctypes.data_as(N.f32p), w, h, int(use_abs),
-                                                thr.ctypes.data_as(N.f32p), gx.ctypes.data_as(N.f32p),
-                                                gy.ctypes.data_as(N.f32p)), "gvpm_compute_gradient")
+        if reuse_primal:
+            self._ck(self.lib.gvpm_compute_gradient_reuse_primal(self.h, acc.ctypes.data_as(N.f32p), w, h, int(use_abs),
+                                                                 C.c_float(inv_emitted), thr.ctypes.data_as(N.f32p),
+                                                                 gx.ctypes.data_as(N.f32p), gy.ctypes.data_as(N.f32p)),
+                     "gvpm_compute_gradient_reuse_primal")
+        else:
+            self._ck(self.lib.gvpm_compute_gradient(self.h, acc.ctypes.data_as(N.f32p), w, h, int(use_abs),
+                                                    thr.ctypes.data_as(N.f32p), gx.ctypes.data_as(N.f32p),
+                                                    gy.ctypes.data_as(N.f32p)), "gvpm_compute_gradient")
         return thr.reshape(h, w, 3), gx.reshape(h, w, 3), gy.reshape(h, w, 3)
 
     def poisson_solve(self, throughput, dx, dy, direct=None, preset="L2D", **params):

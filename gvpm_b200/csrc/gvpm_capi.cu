@@ -78,7 +78,7 @@ cudaError_t launch_plane_gather(const GatherParams &P, bool dump, int sm_count, 
 cudaError_t launch_vpm_traverse(const GatherParams &P, bool dump, int sm_count, cudaStream_t stream);
 cudaError_t launch_vpm_shade(const GatherParams &P, unsigned long long total, int sm_count, cudaStream_t stream);
 void launch_gradient(const float *acc, int w, int h, int use_abs, float *thr, float *gx, float *gy,
-                     cudaStream_t st);
+                     cudaStream_t st, int reuse = 0, float inv_emitted = 1.f);
 void launch_generate_rays(const RayGenParams &P, cudaStream_t st);
 void launch_trace_count(const TraceParams &P, uint8_t *counts, unsigned long long *block_tot, unsigned long long *totals,
                         cudaStream_t st);
@@ -2923,8 +2923,19 @@ int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *off
   return GVPM_OK;
 }
 
+static int compute_gradient_impl(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, int reuse, float inv_emitted,
+                                 float *throughput, float *gx, float *gy);
 int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, float *throughput,
                           float *gx, float *gy) {
+  return compute_gradient_impl(ctx, acc, w, h, use_abs, 0, 1.f, throughput, gx, gy);
+}
+int gvpm_compute_gradient_reuse_primal(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, float inv_emitted,
+                                       float *throughput, float *gx, float *gy) {
+  if (!(inv_emitted > 0.f)) return GVPM_ERR_INVALID;
+  return compute_gradient_impl(ctx, acc, w, h, use_abs, 1, inv_emitted, throughput, gx, gy);
+}
+static int compute_gradient_impl(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, int reuse, float inv_emitted,
+                                 float *throughput, float *gx, float *gy) {
   if (!ctx || !acc || w <= 0 || h <= 0 || !throughput || !gx || !gy) return GVPM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   const size_t np = (size_t)w * h;
@@ -2932,7 +2943,7 @@ int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use
   CK(ctx->grad_out.reserve(np * 9 * 4));
   CK(cudaMemcpyAsync(ctx->grad_in.p, acc, np * GVPM_OUT_FLOATS * 4, cudaMemcpyHostToDevice, ctx->stream));
   float *o = ctx->grad_out.as<float>();
-  launch_gradient(ctx->grad_in.as<float>(), w, h, use_abs, o, o + 3 * np, o + 6 * np, ctx->stream);
+  launch_gradient(ctx->grad_in.as<float>(), w, h, use_abs, o, o + 3 * np, o + 6 * np, ctx->stream, reuse, inv_emitted);
   ctx->launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(throughput, o, np * 12, cudaMemcpyDeviceToHost, ctx->stream));

@@ -357,7 +357,15 @@ class VolumeGatherB200 {
   void scaleVolumeAPA(int it) { gvpm_host::scaleVolumeAPA(globalScaleVolume, it, m_config); }
 
   // gvpm.cpp:1205-1306 + throughput plane (:479-500): interleaved RGB, row-major, poisson hand-off
-  void computeGradient(float *throughput, float *gX, float *gY, bool useAbs) {
+  // reusePrimal (GPMConfig::reusePrimal): the throughput plane by gvpm.cpp:503-532 instead of mediumFlux
+  void computeGradient(float *throughput, float *gX, float *gY, bool useAbs, bool reusePrimal = false) {
+    if (reusePrimal) {
+      const bool apa = m_config.volTechnique != EVolVPM;   // isAPAVolumeEstimator
+      const float inv = apa || !totalEmittedVolume ? 1.f : 1.f / (float)totalEmittedVolume;
+      check(gvpm_compute_gradient_reuse_primal(m_ctx, m_acc.data(), m_w, m_h, useAbs ? 1 : 0, inv, throughput, gX, gY),
+            "gvpm_compute_gradient_reuse_primal");
+      return;
+    }
     check(gvpm_compute_gradient(m_ctx, m_acc.data(), m_w, m_h, useAbs ? 1 : 0, throughput, gX, gY),
           "gvpm_compute_gradient");
   }

@@ -460,6 +460,11 @@ int gvpm_dump_neighbours_vpm(gvpm_ctx *ctx, int nb_camera_samples, uint64_t *off
  * gvpm.cpp:560-578).  use_abs as the reference's useAbs flag. */
 int gvpm_compute_gradient(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs,
                           float *throughput, float *gx, float *gy);
+/* Same gradients; the throughput plane is the reusePrimal estimate (GPMConfig::reusePrimal, gvpm.cpp:503-532): the
+ * shifted flux the four neighbouring pixels send to a pixel plus its own four weighted fluxes, over 4.  inv_emitted =
+ * 1 for the APA estimators (BRE, beams, planes), 1 / m_totalEmittedVolume for G-VPM (:527-531). */
+int gvpm_compute_gradient_reuse_primal(gvpm_ctx *ctx, const float *acc, int w, int h, int use_abs, float inv_emitted,
+                                       float *throughput, float *gx, float *gy);
 
 /* ---- next step of the hand-off: screened-Poisson reconstruction (gvpm.cpp:610-690) -----------------------------
  * Replaces poisson::Solver (src/integrators/poisson_solver/Solver.cpp: importImagesMTS + setupBackend +

@@ -57,6 +57,35 @@ def test_compute_gradient_kernel(built, use_abs):
     ctx.close()
 
 
+def reuse_primal_reference(acc, w, h, inv_emitted):
+    """numpy restatement of the reusePrimal throughput (gvpm.cpp:503-532), same order of additions"""
+    a = acc.reshape(h, w, 9, 3)
+    S, W = a[:, :, 1:5], a[:, :, 5:9]
+    L, R, T, B = 0, 1, 2, 3
+    t = np.zeros((h, w, 3), dtype=np.float32)
+    t[:, :-1] += S[:, 1:, L]
+    t[:, 1:] += S[:, :-1, R]
+    t[:-1] += S[1:, :, B]
+    t[1:] += S[:-1, :, T]
+    t += ((W[:, :, B] + W[:, :, T]) + W[:, :, R]) + W[:, :, L]
+    return (t * np.float32(0.25)) * np.float32(inv_emitted)
+
+
+@pytest.mark.parametrize("inv_emitted", [1.0, 1.0 / 250000.0])
+def test_reuse_primal_throughput(built, inv_emitted):
+    from gvpm_b200.api import Context
+    rng = np.random.default_rng(5)
+    w, h = 29, 17
+    acc = rng.uniform(0.0, 2.0, size=(h * w * 27)).astype(np.float32)
+    ctx = Context(0)
+    thr, gx, gy = ctx.compute_gradient(acc, w, h, False, reuse_primal=True, inv_emitted=inv_emitted)
+    rt, rx, ry = gradient_reference(acc.copy(), w, h, False)
+    np.testing.assert_array_equal(thr, reuse_primal_reference(acc.copy(), w, h, inv_emitted))
+    np.testing.assert_allclose(gx, rx, rtol=0, atol=1e-6)     # the gradients do not change
+    np.testing.assert_allclose(gy, ry, rtol=0, atol=1e-6)
+    ctx.close()
+
+
 def test_host_driver_two_iterations(built):
     """gvpm_host::VolumeGatherB200 == oracle gather + the reference's normalisation, APA running mean
     (gvpm.cpp:1054-1069) and radius reduction (:181-215) over two iterations."""

@@ -68,3 +68,34 @@ def test_planes_outside_camera_edge_two(built):
     # itself does not care where the sensor is (the reference driver refuses an outside sensor, gvpm.cpp:785-787)
     c = H.make_plane_case(n_planes=1500, w=32, h=24, inside=False)
     _check(c, "planes outside", min_hits=20000)
+
+
+def test_sppm_shaped_plane_pass(built):
+    """sppm's primal photon planes (PhotonPlaneQuery, plane_struct.h:238-256): intersectPlane0D + getContrib0D and nothing
+    else - the gvpm entry with no valid offset path.  Same index sets, the primal equals the oracle's and equals the
+    primal of the gradient-domain run (it never depends on the offsets), shifted terms stay zero, every weight is 1."""
+    from oracle import binding as ob
+    from gvpm_b200.api import Context
+    c = H.make_plane_case(n_planes=1500, w=40, h=24)
+    ref_grad = ob.planes_gather(c.planes, c.rays, c.medium, c.config)
+    rays = c.rays.copy()
+    rays.off_valid[:] = 0
+    ref = ob.planes_gather(c.planes, rays, c.medium, c.config, neighbours=True)
+    ctx = Context(0)
+    ctx.set_medium(c.medium)
+    ctx.set_config(c.config)
+    ctx.upload_planes(c.planes)
+    ctx.build_planes()
+    ctx.upload_rays(rays)
+    out, counts = ctx.gather_planes()
+    offsets, idx = ctx.dump_neighbours_planes()
+    np.testing.assert_array_equal(counts, ref.counts)
+    np.testing.assert_array_equal(idx, ref.idx)
+    H.assert_radiance_close(out, ref.out, 1e-4, "sppm-shaped planes")
+    o = out.reshape(-1, 9, 3)
+    H.assert_radiance_close(o[:, 0], ref_grad.out.reshape(-1, 9, 3)[:, 0], 1e-4, "primal does not depend on the offsets")
+    assert not o[:, 1:5].any()                                  # no shifted contribution
+    for k in range(4):                                          # weight 1: the weighted base equals the primal
+        H.assert_radiance_close(o[:, 5 + k], o[:, 0], 1e-6, "weighted base with weight 1")
+    assert int(ref.counts[:, 0].sum()) > 10000
+    ctx.close()

@@ -62,3 +62,20 @@ def test_vpm_radius_larger_than_build_radius_is_rejected(built):
     with pytest.raises(GvpmError, match="smaller than a sample radius"):
         ctx.gather_vpm(c.nb)
     ctx.close()
+
+
+def test_sppm_shaped_vpm_pass(built):
+    """sppm's point-photon volume pass (sppm.cpp:1095-1112 -> PhotonMap::estimateVolumeRadiance, photonmap.cpp:324-330): a
+    range query per distance sample with the depth bound maxDepth - beam.depth, scaled by transmittance / (pdfSuccess *
+    selBeam) - the gvpm entry with no valid offset path and edge_id = beam.depth.  MVol, index sets and the primal
+    match the oracle; the primal equals the gradient-domain run's."""
+    from oracle import binding as ob
+    c = _case(max_depth=6)
+    ref_grad = ob.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, mode="brute")
+    c.rays = c.rays.copy()
+    c.rays.off_valid[:] = 0
+    ref = _check(c, "sppm-shaped vpm")
+    o = ref.out.reshape(-1, 9, 3)
+    H.assert_radiance_close(o[:, 0], ref_grad.out.reshape(-1, 9, 3)[:, 0], 1e-6, "primal does not depend on the offsets")
+    assert not o[:, 1:5].any()
+    assert ref.sample_counts[:, 0].sum() > ref.sample_counts[:, 1].sum() > 1000     # the depth bound filters some photons

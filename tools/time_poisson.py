@@ -46,5 +46,21 @@ for preset in a.presets:
         line["cores"] = os.cpu_count()
         line["max_rel_err"] = float(np.abs(rec.astype(np.float64) - want).max() / np.abs(want).max())
         line["speedup"] = line["reference_openmp_ms"] / line["gpu_ms_incl_copies"]
+    if not a.no_ref and pr.cuda_available():
+        # the reference's own CUDA backend (BackendCUDA.cu compiled for sm_100a) on the same GPU, host arrays in and out
+        # like gvpm_poisson_solve: wall clock around the whole Solver sequence (import, setupBackend, solve, export)
+        pr.solve(tp, dx, dy, direct, backend="CUDA", **pr.preset(preset))       # warm-up (context, allocations)
+        ts = []
+        for _ in range(a.reps):
+            t0 = time.perf_counter()
+            got = pr.solve(tp, dx, dy, direct, backend="CUDA", **pr.preset(preset))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        line["reference_cuda_ms"] = float(np.mean(ts))
+        line["gpu_wall_ms"] = None
+        t0 = time.perf_counter()
+        ctx.poisson_solve(tp, dx, dy, direct, preset=preset)
+        line["gpu_wall_ms"] = (time.perf_counter() - t0) * 1e3
+        line["vs_reference_cuda"] = line["reference_cuda_ms"] / line["gpu_wall_ms"]
+        line["max_rel_err_vs_reference_cuda"] = float(np.abs(rec.astype(np.float64) - got).max() / np.abs(got).max())
     print(json.dumps(line), flush=True)
 ctx.close()
