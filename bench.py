@@ -221,6 +221,27 @@ def measured_traffic(workload, world):
         return None, None
 
 
+def l2_roofline(workload, world, kernel_ms):
+    """BASELINE.json's metric names "% of HBM/L2 peak": L2 bytes of the dominant kernels (lts__t_bytes.sum of the committed
+    ncu capture) over their live duration, against the L2 read bandwidth measured on this pool's B200s with the library's
+    own 128-bit load sweep over an L2-resident buffer (tools/measure_l2.py -> profiles/r2_l2_peak.json)."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f)[workload]
+        with open(os.path.join(ROOT, "profiles", "r2_l2_peak.json")) as f:
+            pk = json.load(f)
+        b = float(e["l2_bytes_per_launch"])
+        ach = b / (kernel_ms * 1e-3) / 1e9
+        return {"bytes_per_launch": b, "achieved": ach, "peak": float(pk["l2_read_peak_gbs"]), "unit": "GB/s",
+                "frac": ach / float(pk["l2_read_peak_gbs"]),
+                "peak_source": "measured: gvpm_measure_read_bandwidth over 16-64 MB (profiles/r2_l2_peak.json)",
+                "bytes_source": e["source"]}
+    except Exception:
+        return None
+
+
 def _native_lib_path():
     from gvpm_b200 import _native as NAT
     return NAT.LIB_PATH
@@ -368,9 +389,10 @@ def workload_config(args, inp, world):
                         f"{inp['n_ph']} photons/iteration, gvpm G-BRE 3D kernel, mixed shift, area MIS, pathSet",
             "rays": inp["rays_full_n"], "photons": inp["n_ph"], "initialScaleVolume": inp["scale"],
             "radius": inp["radius"],
-            "parallelism": (f"32x32 gather blocks in {band_cycles()} column bands per GPU over {world} GPU(s), "
-                            "photon set exchanged to every GPU, each hierarchy built over the photons its bands "
-                            "reach, results gathered to rank 0" if shard_mode(world) == "band" else
+            "parallelism": (f"32x32 gather blocks in {band_cycles()} cost-balanced column bands per GPU over {world} GPU(s), "
+                            "every GPU holds 1/N of the photon set and sends each photon to the GPUs whose bands can reach "
+                            "it, each perspective grid built over what its GPU received, results collected on rank 0"
+                            if shard_mode(world) == "band" else
                             f"image tiles (32x32) round-robin over {world} GPU(s), photon set broadcast, results "
                             "gathered to rank 0"),
             "l2": (f"photon records {inp['n_ph'] * 128 / 1e9:.2f} GB + rays {inp['rays_full_n'] * 320 / 1e9:.2f} GB per step "
@@ -1326,13 +1348,15 @@ def main():
                 "gpu_launches": int(launches), "native_lib": _native_lib_path(),
                 # the gather is two launches: k_bre_traverse (dominant) + k_bre_shade; SURVEY §8(d)'s
                 # per-ray figure covers both, so the roofline is quoted over the pair
-                "roofline": {"bound": "hbm", "kernel": "k_bre_traverse + k_bre_shade", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": ("k_bre_grid_traverse" if accel == "frustum" else "k_bre_traverse") + " + k_bre_shade",
+                             "achieved": achieved, "l2": l2_roofline(args.workload if not (args.photons or args.scale) else "", world, float(gk.item())),
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "traffic_source": traffic_src, "peak_source": src, "algorithmic_bytes_per_launch": alg,
                              "kernel_ms": float(gk.item()), "traverse_ms": trav_ms, "shade_ms": shade_ms,
                              "neighbours_H": H, "contributing_pairs": n_pairs,
-                             "note": "instruction-bound tree traversal: DRAM traffic is below the algorithmic "
-                                     "bytes (profiles/), the HBM fraction is reported as the contract asks"},
+                             "note": "latency- / issue-bound kernels: DRAM traffic is below the algorithmic bytes and L2 traffic "
+                                     "at a quarter of its peak (profiles/r2_gather_bre.md); the HBM fraction is reported as "
+                                     "the contract asks"},
                 "phases_ms": {"build": build_ms, "gather": float(gk.item()), "traverse": trav_ms,
                               "shade": shade_ms},
                 "result_collection_verified": collect_ok,
