@@ -1112,7 +1112,9 @@ def main():
         if coll_done[b] is not None:            # the result buffer of step k - 2 has been gathered
             stream.wait_event(coll_done[b])
             coll_done[b] = None
-        side = os.environ.get("GVPM_DISPATCH_STREAM", "side") == "side"
+        # side stream (overlapped, small persistent grids) from 4 ranks on; with 2 ranks a slice is half the set and the
+        # dispatch is better off with the whole machine for a moment (N = 2: 2.85 ms inline, 2.95 on the side stream)
+        side = os.environ.get("GVPM_DISPATCH_STREAM", "side" if world > 2 else "inline") == "side"
         if side:   # on the library's priority stream, concurrently with this step (starved by the persistent gather kernels)
             ctx.dispatch_photons(1 - b, n_ph, s_begin, n_slice, inp["radius"], after_stream=h2d.cuda_stream)
         with torch.cuda.stream(stream):
