@@ -27,7 +27,13 @@ void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, 
                          uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
                          uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st, uint32_t region_cap = 0,
-                         const uint32_t *region_count = nullptr);
+                         const uint32_t *region_count = nullptr, uint32_t *cell_count = nullptr);
+size_t cell_scan_temp_bytes(uint32_t n_keys);
+cudaError_t launch_cell_scan(void *temp, size_t temp_bytes, const uint32_t *cell_count, uint32_t *cell_start, uint32_t n_keys,
+                             cudaStream_t st);
+void launch_pack_scatter(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *keys, const uint32_t *rank,
+                         const uint32_t *cell_start, float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st,
+                         bool records_ready, const uint32_t *kept_dev);
 void launch_frustum_mark(const float4 *rays, uint32_t n_rays, const FrustumGrid &G, uint32_t *occ, int sm_count, cudaStream_t st);
 void launch_dispatch(const DispatchParams &P, cudaStream_t st, int ctas);
 void launch_dispatch_signal(const SignalParams &P, cudaStream_t st);
@@ -50,8 +56,8 @@ size_t ray_grid_bytes();
 size_t ray_mask_bytes();
 void launch_ray_region(const float4 *rays, uint32_t nRays, float radius, float *box, void *grid, uint32_t *mask,
                        float *bounds, int sm_count, cudaStream_t st);
-void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *vals,
-                        uint32_t *keepmask, uint32_t *counter, cudaStream_t st);
+void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *keepmask,
+                        uint32_t *block_kept, cudaStream_t st);
 void launch_keys_kept(const float *pos, const uint32_t *vals, uint32_t m, const void *grid, uint32_t *keys, cudaStream_t st);
 void launch_pack_pruned(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *sorted, uint32_t m,
                         float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st);
@@ -211,7 +217,8 @@ struct gvpm_ctx {
   int accel = ACCEL_BVH;
   bool force_bvh = false;            // GVPM_ACCEL=bvh: A/B switch for kernel experiments
   FrustumGrid grid{};
-  DevBuf cell_start, grid_occ, pin_scratch, trace_scratch, keepmask;
+  DevBuf cell_start, grid_occ, pin_scratch, trace_scratch, keepmask, cell_count;
+  bool radix_frustum = false;        // GVPM_FRUSTUM_SORT=radix: the key sort of the perspective grid by radix sort (A/B switch)
   double kept_fraction_hint = 1.0;   // share of the photons the last frustum build kept (sizes the next one's sort)
   bool kept_hint_valid = false;      // the fraction comes from a count read back from a build over the same kind of set
   bool force_exact_build = false;    // a bounded build overflowed: size the next one from its exact count (one host sync)
@@ -654,6 +661,7 @@ int gvpm_ctx_create(int device, gvpm_ctx **out) {
   cudaHostAlloc((void **)&ctx->pin_host, 128, cudaHostAllocDefault);
   cudaEventCreateWithFlags(&ctx->ev_hint, cudaEventDisableTiming);
   { const char *e = getenv("GVPM_ACCEL"); ctx->force_bvh = e && !strcmp(e, "bvh"); }
+  { const char *e = getenv("GVPM_FRUSTUM_SORT"); ctx->radix_frustum = e && !strcmp(e, "radix"); }
   // side-stream dispatch: one CTA per SM by default (N = 8, cfg5: 32 CTAs 1.96 ms / step, 96: 1.11, one per chunk: 1.13)
   { const char *e = getenv("GVPM_DISPATCH_CTAS"); ctx->dispatch_ctas = e ? std::max(0, atoi(e)) : -1; }
   cudaHostAlloc((void **)&ctx->sample_stats_host, 64, cudaHostAllocDefault);
@@ -676,7 +684,7 @@ int gvpm_ctx_destroy(gvpm_ctx *ctx) {
                     &ctx->sub_raw, &ctx->subs, &ctx->beam_box_lo, &ctx->beam_box_hi, &ctx->aos, &ctx->plane_raw,
                     &ctx->plane_pos, &ctx->plane_rec, &ctx->plane_orig, &ctx->plane_box_lo, &ctx->plane_box_hi,
                     &ctx->plane_bounds, &ctx->ray_region, &ctx->poisson_io, &ctx->poisson_ws, &ctx->beam_staging, &ctx->beam_len,
-                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask,
+                    &ctx->beam_aux, &ctx->plane_staging, &ctx->sample_staging, &ctx->cell_start, &ctx->grid_occ, &ctx->pin_scratch, &ctx->trace_scratch, &ctx->keepmask, &ctx->cell_count,
                     &ctx->disp.inbox[0], &ctx->disp.inbox[1], &ctx->disp.ctrl, &ctx->disp.occ_all, &ctx->disp.grids_dev[0], &ctx->disp.grids_dev[1],
                     &ctx->disp.keepbits, &ctx->disp.block_cnt, &ctx->disp.owner_map};
   for (int p = 0; p < ctx->disp.n_peers; ++p)
@@ -1134,10 +1142,16 @@ static int build_pruned_bvh(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     CK(ctx->orig.reserve(4 * (size_t)n));
     CK(ctx->aos.reserve(128 * (size_t)n));
     PhotonStaging S = photon_staging_ptrs(ctx->ph_staging.p, n);
-    launch_keep_pruned(S.pos, n, rr + gridOff, mask, ctx->vals_in.as<uint32_t>(), keepmask, counter, st);
-    ctx->launches += 1;
+    // kept indices in photon order (deterministic): per-CTA counts, exclusive scan, ordered compaction
+    const uint32_t nb = (n + 255) / 256;
+    CK(ctx->keepmask.reserve(4 * ((size_t)nb + 4)));
+    uint32_t *block_kept = ctx->keepmask.as<uint32_t>();
+    launch_keep_pruned(S.pos, n, rr + gridOff, mask, keepmask, block_kept, st);
+    launch_scan_u32(block_kept, nb, block_kept + nb, st);
+    launch_compact_kept(nullptr, keepmask, block_kept, n, nullptr, ctx->vals_in.as<uint32_t>(), st, n, counter);
+    ctx->launches += 3;
     // the number of kept photons sizes the sort and the hierarchy levels: one 4-byte read-back
-    CK(cudaMemcpyAsync(ctx->pair_count_host, counter, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->pair_count_host, block_kept + nb, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     kept = *(const uint32_t *)ctx->pair_count_host;
   }
@@ -1295,18 +1309,40 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
     uint32_t *keepmask = ctx->keepmask.as<uint32_t>(), *block_kept = keepmask + (n / 32 + 1);
     PhotonStaging S{};
     if (!direct) S = photon_staging_ptrs(ctx->ph_staging.p, n);
+    // Counting sort (default): the key pass counts the photons of every cell and gives each its rank in the cell; the
+    // exclusive scan of the counters IS cell_start; the packing pass (or a scatter pass over records that exist already)
+    // puts position plane entry and index at cell_start[key] + rank.  One streaming pass over the keys less than the
+    // radix sort takes for each of its three digits, no gather of the sorted plane, no cell-start search, and nothing
+    // to size from a count: dropped photons and the empty part of a dispatched inbox are simply never written.  The
+    // order inside a cell follows the atomics (the gather's float atomics are unordered anyway).
+    const bool counting = !ctx->radix_frustum;
+    uint32_t *cell_count = nullptr;
+    if (counting) {
+      CK(ctx->cell_count.reserve(((size_t)n_keys + 2) * 4));
+      cell_count = ctx->cell_count.as<uint32_t>();
+      CK(cudaMemsetAsync(cell_count, 0, ((size_t)n_keys + 2) * 4, st));
+      CK(ctx->sort_temp.reserve(std::max(sort_temp_bytes(n), cell_scan_temp_bytes(n_keys))));
+    }
     if (direct)   // position = first three floats of the record, path parity = bit 10 of its meta word
       launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, (const float *)ctx->records(), 32u, (const uint32_t *)ctx->records() + 3, 32u, 10u, n,
                           G, ctx->grid_occ.as<uint32_t>(), ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(),
-                          ctx->bounds.as<unsigned>() + 6, keepmask, block_kept, ctx->sm_count, st, ctx->region_cap, ctx->region_count);
+                          ctx->bounds.as<unsigned>() + 6, keepmask, block_kept, ctx->sm_count, st, ctx->region_cap, ctx->region_count,
+                          cell_count);
     else
       launch_frustum_keys(ctx->rays.as<float4>(), ctx->n_rays, S.pos, 3u, S.path_id, 1u, 0u, n, G, ctx->grid_occ.as<uint32_t>(),
                           ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->bounds.as<unsigned>() + 6, keepmask,
-                          block_kept, ctx->sm_count, st);
-    const uint32_t *sortedKeys, *sortedVals;
+                          block_kept, ctx->sm_count, st, 0, nullptr, cell_count);
+    const uint32_t *sortedKeys = nullptr, *sortedVals = nullptr;
     uint32_t *ovf = block_kept + nb + 1;   // set when a bounded compaction meets more kept photons than it was sized for
     CK(cudaMemsetAsync(ovf, 0, 4, st));
-    if (ctx->kept_fraction_hint < 0.5) {
+    if (counting) {
+      CK(launch_cell_scan(ctx->sort_temp.p, ctx->sort_temp.cap, cell_count, ctx->cell_start.as<uint32_t>(), n_keys, st));
+      launch_pack_scatter(S, n, keepmask, ctx->keys_in.as<uint32_t>(), ctx->vals_in.as<uint32_t>(), ctx->cell_start.as<uint32_t>(),
+                          ctx->records(), ctx->planes.as<float4>(), ctx->orig.as<uint32_t>(), st, direct,
+                          ctx->cell_start.as<uint32_t>() + n_keys - 1);
+      sortedKeys = sortedVals = nullptr;
+      ctx->launches += 4;
+    } else if (ctx->kept_fraction_hint < 0.5) {
       // sharded image: most photons are out of this rank's reach.  Compact the kept (key, index) pairs in index order
       // (deterministic) and sort those only.  Their number sizes the sort: taken from the previous build's count (read
       // back asynchronously) with a 25 % margin, the slots past the real count filled with DROP keys - no host round
@@ -1348,12 +1384,14 @@ static int build_frustum(gvpm_ctx *ctx, float radius, uint32_t *n_kept) {
       sortedVals = ctx->vals_out.as<uint32_t>();
     }
     ctx->build_ovf = ovf;
-    launch_cell_starts(sortedKeys, m, n_keys, ctx->cell_start.as<uint32_t>(),
-                       ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
-    launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->records(), ctx->planes.as<float4>(),
-                            ctx->orig.as<uint32_t>(), st, direct);
+    if (!counting) {
+      launch_cell_starts(sortedKeys, m, n_keys, ctx->cell_start.as<uint32_t>(),
+                         ctx->grid_occ.as<char>() + frustum_occ_bytes(), ctx->sm_count, st);
+      launch_pack_sorted_kept(S, n, keepmask, sortedVals, m, ctx->records(), ctx->planes.as<float4>(),
+                              ctx->orig.as<uint32_t>(), st, direct);
+    }
     CK(cudaEventRecord(ctx->ev_free[ctx->ph_staging_sel], st));   // last read of the staging buffer
-    if (m == n) {   // kept count of this build -> hint of the next one (no blocking)
+    if (!counting && m == n) {   // kept count of this build -> hint of the next one (no blocking)
       CK(cudaMemcpyAsync(ctx->pin_host + 30, ctx->cell_start.as<uint32_t>() + n_keys - 1, 4, cudaMemcpyDeviceToHost, st));
       CK(cudaEventRecord(ctx->ev_hint, st));
       ctx->hint_pending = true;

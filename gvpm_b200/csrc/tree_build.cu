@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "gvpm_device.cuh"
 #include "frustum_device.cuh"
@@ -374,13 +375,15 @@ __global__ void __launch_bounds__(256) k_ray_mask(const float4 *__restrict__ ray
   for (int w = threadIdx.x; w < kGridWords; w += blockDim.x)
     if (mask[w]) atomicOr(gmask + w, mask[w]);
 }
-// Pass 1 over all photons: keep test (cell of the photon marked?) and compaction of the kept indices with one atomic per
-// CTA; keepmask gets one bit per photon (word = 32 consecutive photons) for the record packing pass.  Memory-bound: the
-// Hilbert keys are computed afterwards, for the kept photons only (k_keys_kept).
+// Pass 1 over all photons: keep test (cell of the photon marked?); keepmask gets one bit per photon (word = 32 consecutive
+// photons) and block_kept the CTA's number of kept photons.  The kept indices are then compacted in photon order
+// (exclusive scan of block_kept + k_compact_kept): the order of the sorted set - hence the pair order and every float
+// accumulation order of the gather - does not depend on how the CTAs were scheduled.  Memory-bound: the Hilbert keys are
+// computed afterwards, for the kept photons only (k_keys_kept).
 __global__ void __launch_bounds__(256) k_keep_pruned(const float *__restrict__ pos, uint32_t n, const RayGrid *__restrict__ gp,
-                              const uint32_t *__restrict__ gmask, uint32_t *__restrict__ vals,
-                              uint32_t *__restrict__ keepmask, uint32_t *__restrict__ counter) {
-  __shared__ uint32_t warpCount[8], blockBase;
+                              const uint32_t *__restrict__ gmask, uint32_t *__restrict__ keepmask,
+                              uint32_t *__restrict__ block_kept) {
+  __shared__ uint32_t warpCount[8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   bool keep = false;
@@ -402,11 +405,9 @@ __global__ void __launch_bounds__(256) k_keep_pruned(const float *__restrict__ p
   if (threadIdx.x == 0) {
     uint32_t tot = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const uint32_t c = warpCount[k]; warpCount[k] = tot; tot += c; }
-    blockBase = tot ? atomicAdd(counter, tot) : 0u;
+    for (int k = 0; k < 8; ++k) tot += warpCount[k];
+    block_kept[blockIdx.x] = tot;
   }
-  __syncthreads();
-  if (keep) vals[blockBase + warpCount[w] + __popc(km & ((1u << lane) - 1u))] = i;
 }
 // Pass 2 over the m kept photons: 30-bit Hilbert key, quantised in the grid box
 __global__ void k_keys_kept(const float *__restrict__ pos, const uint32_t *__restrict__ vals, uint32_t m,
@@ -426,8 +427,12 @@ __global__ void k_keys_kept(const float *__restrict__ pos, const uint32_t *__res
 }
 // k_pack_aos for the kept photons only: same streaming layout (the photon set arrives in the caller's order, so the kept
 // ones are scattered evenly), loads and the transposed stores predicated by the keep bits
+// keys != null (counting sort): the kept photon's position plane entry and index go to slot cell_start[key] + rank too
 __global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, uint32_t n, const uint32_t *__restrict__ keepmask,
-                                                        float4 *__restrict__ aos) {
+                                                        float4 *__restrict__ aos, const uint32_t *__restrict__ keys = nullptr,
+                                                        const uint32_t *__restrict__ rank = nullptr,
+                                                        const uint32_t *__restrict__ cell_start = nullptr,
+                                                        float4 *__restrict__ planes = nullptr, uint32_t *__restrict__ orig = nullptr) {
   __shared__ float4 tile[8][32 * 9];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t warpBase = blockIdx.x * blockDim.x + (w << 5);
@@ -449,6 +454,11 @@ __global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, ui
     r[5] = ld3(S.prefix_flux, 0.f);
     r[6] = ld3(S.parent_albedo, 0.f);
     r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (keys) {
+      const uint32_t slot = __ldg(cell_start + __ldg(keys + s)) + __ldg(rank + s);
+      planes[slot] = r[0];
+      orig[slot] = s;
+    }
   }
   __syncwarp();
   float4 *dst = aos + (size_t)warpBase * GVPM_AOS_FLOAT4;
@@ -602,7 +612,11 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                        unsigned *__restrict__ coord_mag, uint32_t *__restrict__ keepmask,
                                                        uint32_t *__restrict__ block_kept, uint32_t region_cap,
-                                                       const uint32_t *__restrict__ region_count) {
+                                                       const uint32_t *__restrict__ region_count,
+                                                       uint32_t *__restrict__ cell_count) {
+  // cell_count != null: counting sort.  vals[i] becomes the photon's rank inside its cell (one atomic on the cell's
+  // counter), cell_start the exclusive scan of the counters, and k_frustum_scatter / k_pack_aos_kept put the photon at
+  // cell_start[key] + rank: no radix sort, no separate gather of the sorted position plane, no cell-start search.
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float mag = 0.f;
   bool keep = false;
@@ -619,8 +633,8 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
     const uint32_t key = frustum_key(G, occ, px, py, pz, [&]() { return (__ldg(par_src + (size_t)par_stride * i) >> par_shift) & 1u; });
     const uint32_t DROP = (G.parity_split ? 2u : 1u) * G.n_cells + 1u;
     keys[i] = key;
-    vals[i] = i;
     keep = key != DROP;
+    vals[i] = (cell_count && keep) ? atomicAdd(cell_count + key, 1u) : i;
   }
   // one keep bit per photon (word = 32 consecutive photons) and the CTA's number of kept photons: the record packing and
   // the compaction in front of the sort (sharded images keep a small part of the set) read them
@@ -644,6 +658,35 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
     if (m > __uint_as_float(*(volatile unsigned *)coord_mag)) atomicMax(coord_mag, __float_as_uint(m));
   }
 }
+// counting sort: the index map alone (orig[cell_start[key] + rank] = photon).  4-byte random writes into an array that
+// stays in L2 (40 MB for 10 M photons); the position plane is then gathered with coalesced writes (k_gather_sorted).
+// Scattering the 16-byte plane entries directly costs more than both passes together: random partial-sector writes into
+// 160 MB are read-modify-write cycles in DRAM (measured: 0.40 ms against 0.06 + 0.24 ms).
+__global__ void __launch_bounds__(256) k_scatter_index(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                                        const uint32_t *__restrict__ keepmask, const uint32_t *__restrict__ cell_start,
+                                                        uint32_t n, uint32_t *__restrict__ orig) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !(__ldg(keepmask + (i >> 5)) >> (i & 31u) & 1u)) return;
+  orig[__ldg(cell_start + keys[i]) + rank[i]] = i;
+}
+// position plane from the index map; m = number of sorted slots, read from the device (cell_start[n_keys - 1] = kept photons)
+__global__ void k_gather_by_index(const float4 *__restrict__ aos, const uint32_t *__restrict__ orig, const uint32_t *__restrict__ m_dev,
+                                  float4 *__restrict__ planes) {
+  const uint32_t m = __ldg(m_dev);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    planes[i] = __ldg(aos + (size_t)__ldg(orig + i) * GVPM_AOS_FLOAT4);
+}
+// counting sort, records in place (traced on the device or dispatched by the peers): position plane + index map
+__global__ void __launch_bounds__(256) k_frustum_scatter(const float4 *__restrict__ aos, const uint32_t *__restrict__ keys,
+                                                          const uint32_t *__restrict__ rank, const uint32_t *__restrict__ keepmask,
+                                                          const uint32_t *__restrict__ cell_start, uint32_t n,
+                                                          float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !(__ldg(keepmask + (i >> 5)) >> (i & 31u) & 1u)) return;
+  const uint32_t slot = __ldg(cell_start + keys[i]) + rank[i];
+  planes[slot] = __ldg(aos + (size_t)i * GVPM_AOS_FLOAT4);
+  orig[slot] = i;
+}
 // (key, index) of the kept photons, in index order, packed to the front: block_off = exclusive scan of block_kept
 __global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ keepmask,
                                                        const uint32_t *__restrict__ block_off, uint32_t n,
@@ -662,7 +705,7 @@ __global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict
     *overflow = 1u;
     return;
   }
-  keys_c[pos] = keys[i];
+  if (keys) keys_c[pos] = keys[i];
   vals_c[pos] = i;
 }
 __global__ void k_fill_u32(uint32_t *__restrict__ p, uint32_t n, uint32_t value) {
@@ -776,9 +819,9 @@ void launch_ray_region(const float4 *rays, uint32_t nRays, float radius, float *
     k_ray_mask<<<std::min<uint32_t>(need, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, nRays, radius, (const RayGrid *)grid, mask);
   }
 }
-void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *vals,
-                        uint32_t *keepmask, uint32_t *counter, cudaStream_t st) {
-  if (n) k_keep_pruned<<<(n + 255) / 256, 256, 0, st>>>(pos, n, (const RayGrid *)grid, mask, vals, keepmask, counter);
+void launch_keep_pruned(const float *pos, uint32_t n, const void *grid, const uint32_t *mask, uint32_t *keepmask,
+                        uint32_t *block_kept, cudaStream_t st) {
+  if (n) k_keep_pruned<<<(n + 255) / 256, 256, 0, st>>>(pos, n, (const RayGrid *)grid, mask, keepmask, block_kept);
 }
 void launch_keys_kept(const float *pos, const uint32_t *vals, uint32_t m, const void *grid, uint32_t *keys, cudaStream_t st) {
   if (m) k_keys_kept<<<(m + 255) / 256, 256, 0, st>>>(pos, vals, m, (const RayGrid *)grid, keys);
@@ -821,11 +864,31 @@ void launch_frustum_keys(const float4 *rays, uint32_t n_rays, const float *pos, 
                          uint32_t par_stride, uint32_t par_shift, uint32_t n,
                          const FrustumGrid &G, uint32_t *occ, uint32_t *keys, uint32_t *vals, unsigned *coord_mag,
                          uint32_t *keepmask, uint32_t *block_kept, int sm_count, cudaStream_t st, uint32_t region_cap,
-                         const uint32_t *region_count) {
+                         const uint32_t *region_count, uint32_t *cell_count) {
   cudaMemsetAsync(occ, 0, frustum_occ_bytes(), st);
   cudaMemsetAsync(coord_mag, 0, 4, st);
   if (n_rays) k_frustum_mark<<<std::min<uint32_t>((n_rays + 255) / 256, 2u * (uint32_t)sm_count), 256, 0, st>>>(rays, n_rays, G, occ);
-  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, par_src, par_stride, par_shift, n, G, occ, keys, vals, coord_mag, keepmask, block_kept, region_cap, region_count);
+  if (n) k_frustum_keys<<<(n + 255) / 256, 256, 0, st>>>(pos, stride, par_src, par_stride, par_shift, n, G, occ, keys, vals, coord_mag, keepmask, block_kept, region_cap, region_count, cell_count);
+}
+// counting sort: cell_start[0 .. n_keys] = exclusive scan of the per-cell counts (cell_count[n_keys] must be 0)
+size_t cell_scan_temp_bytes(uint32_t n_keys) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_keys + 1);
+  return bytes;
+}
+cudaError_t launch_cell_scan(void *temp, size_t temp_bytes, const uint32_t *cell_count, uint32_t *cell_start, uint32_t n_keys,
+                             cudaStream_t st) {
+  return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cell_count, cell_start, (int)n_keys + 1, st);
+}
+// records of the kept photons, index map at cell_start[key] + rank, position plane gathered from it (kept_dev: slots in use)
+void launch_pack_scatter(const PhotonStaging &S, uint32_t n, const uint32_t *keepmask, const uint32_t *keys, const uint32_t *rank,
+                         const uint32_t *cell_start, float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st,
+                         bool records_ready, const uint32_t *kept_dev) {
+  if (!n) return;
+  (void)k_frustum_scatter;
+  if (!records_ready) k_pack_aos_kept<<<(n + 255) / 256, 256, 0, st>>>(S, n, keepmask, aos);
+  k_scatter_index<<<(n + 255) / 256, 256, 0, st>>>(keys, rank, keepmask, cell_start, n, orig);
+  k_gather_by_index<<<std::min<uint32_t>((n + 255) / 256, 148u * 16u), 256, 0, st>>>(aos, orig, kept_dev, planes);
 }
 // the occupancy mask alone (what a rank publishes to the ranks that send it photons)
 void launch_frustum_mark(const float4 *rays, uint32_t n_rays, const FrustumGrid &G, uint32_t *occ, int sm_count, cudaStream_t st) {

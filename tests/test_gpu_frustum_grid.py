@@ -100,10 +100,13 @@ def test_vpm_after_frustum_build_rebuilds_the_hierarchy(built):
     ctx.close()
 
 
-def test_second_sharded_build_compacts_before_the_sort(built):
-    """the first build of a sharded ray set reports how few photons it kept; the next one compacts the kept (key, index)
-    pairs before sorting (kept-count read-back): same counts, same radiance"""
+@pytest.mark.parametrize("sort", ["counting", "radix"])
+def test_second_sharded_build_compacts_before_the_sort(built, sort, monkeypatch):
+    """Repeated builds of a sharded ray set.  Counting sort (default): dropped photons are never written.  Radix sort
+    (GVPM_FRUSTUM_SORT=radix, the A/B switch): the first build reports how few photons it kept, the next ones compact the
+    kept (key, index) pairs before sorting.  Same counts, same radiance either way."""
     from oracle import binding as ob
+    monkeypatch.setenv("GVPM_FRUSTUM_SORT", sort)
     case = H.make_case(n_photons=80000, w=64, h=64, scale=0.5)
     idx = shard.band_indices(case.rays.px, case.rays.py, 64, 64, 8, 3, 1)
     case.rays = case.rays.take(idx)
@@ -122,12 +125,13 @@ def test_second_sharded_build_compacts_before_the_sort(built):
     ctx.close()
 
 
-def test_bounded_build_overflow_is_reported_and_recovered(built):
-    """A sharded build sizes its sort from the previous iteration's kept count (+25 %, no host round trip).  When an
-    iteration keeps far more, the gather must say so instead of returning a partial result, and the next build (exact
-    count) must give the right answer."""
+def test_bounded_build_overflow_is_reported_and_recovered(built, monkeypatch):
+    """Radix-sort variant of the sharded build (GVPM_FRUSTUM_SORT=radix): it sizes its sort from the previous iteration's
+    kept count (+25 %, no host round trip).  When an iteration keeps far more, the gather must say so instead of
+    returning a partial result, and the next build (exact count) must give the right answer."""
     from oracle import binding as ob
     from gvpm_b200.api import GvpmError
+    monkeypatch.setenv("GVPM_FRUSTUM_SORT", "radix")
     case = H.make_case(n_photons=1600000, w=64, h=64, scale=0.5)
     idx = shard.band_indices(case.rays.px, case.rays.py, 64, 64, 8, 3, 1)
     case.rays = case.rays.take(idx)
@@ -151,3 +155,11 @@ def test_bounded_build_overflow_is_reported_and_recovered(built):
     np.testing.assert_array_equal(counts, ref.counts)
     H.assert_radiance_close(out, ref.out, 1e-4, "after the overflow")
     ctx.close()
+
+
+def test_frustum_radix_sort_variant_matches_oracle(built, monkeypatch):
+    """GVPM_FRUSTUM_SORT=radix keeps the radix-sorted build of the perspective grid (stable order inside a cell)"""
+    monkeypatch.setenv("GVPM_FRUSTUM_SORT", "radix")
+    case = H.make_case(n_photons=60000, w=64, h=48, scale=2.0)
+    ref, kept = _check(case, "frustum, radix sort")
+    assert ref.counts[:, 0].sum() > 3000
