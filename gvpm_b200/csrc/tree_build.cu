@@ -427,12 +427,8 @@ __global__ void k_keys_kept(const float *__restrict__ pos, const uint32_t *__res
 }
 // k_pack_aos for the kept photons only: same streaming layout (the photon set arrives in the caller's order, so the kept
 // ones are scattered evenly), loads and the transposed stores predicated by the keep bits
-// keys != null (counting sort): the kept photon's position plane entry and index go to slot cell_start[key] + rank too
 __global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, uint32_t n, const uint32_t *__restrict__ keepmask,
-                                                        float4 *__restrict__ aos, const uint32_t *__restrict__ keys = nullptr,
-                                                        const uint32_t *__restrict__ rank = nullptr,
-                                                        const uint32_t *__restrict__ cell_start = nullptr,
-                                                        float4 *__restrict__ planes = nullptr, uint32_t *__restrict__ orig = nullptr) {
+                                                        float4 *__restrict__ aos) {
   __shared__ float4 tile[8][32 * 9];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t warpBase = blockIdx.x * blockDim.x + (w << 5);
@@ -454,11 +450,6 @@ __global__ void __launch_bounds__(256) k_pack_aos_kept(const PhotonStaging S, ui
     r[5] = ld3(S.prefix_flux, 0.f);
     r[6] = ld3(S.parent_albedo, 0.f);
     r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (keys) {
-      const uint32_t slot = __ldg(cell_start + __ldg(keys + s)) + __ldg(rank + s);
-      planes[slot] = r[0];
-      orig[slot] = s;
-    }
   }
   __syncwarp();
   float4 *dst = aos + (size_t)warpBase * GVPM_AOS_FLOAT4;
@@ -615,8 +606,8 @@ __global__ void __launch_bounds__(256) k_frustum_keys(const float *__restrict__ 
                                                        const uint32_t *__restrict__ region_count,
                                                        uint32_t *__restrict__ cell_count) {
   // cell_count != null: counting sort.  vals[i] becomes the photon's rank inside its cell (one atomic on the cell's
-  // counter), cell_start the exclusive scan of the counters, and k_frustum_scatter / k_pack_aos_kept put the photon at
-  // cell_start[key] + rank: no radix sort, no separate gather of the sorted position plane, no cell-start search.
+  // counter), cell_start the exclusive scan of the counters, and k_scatter_index puts the photon's index at
+  // cell_start[key] + rank: no radix sort, no cell-start search.
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   float mag = 0.f;
   bool keep = false;
@@ -675,17 +666,6 @@ __global__ void k_gather_by_index(const float4 *__restrict__ aos, const uint32_t
   const uint32_t m = __ldg(m_dev);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
     planes[i] = __ldg(aos + (size_t)__ldg(orig + i) * GVPM_AOS_FLOAT4);
-}
-// counting sort, records in place (traced on the device or dispatched by the peers): position plane + index map
-__global__ void __launch_bounds__(256) k_frustum_scatter(const float4 *__restrict__ aos, const uint32_t *__restrict__ keys,
-                                                          const uint32_t *__restrict__ rank, const uint32_t *__restrict__ keepmask,
-                                                          const uint32_t *__restrict__ cell_start, uint32_t n,
-                                                          float4 *__restrict__ planes, uint32_t *__restrict__ orig) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !(__ldg(keepmask + (i >> 5)) >> (i & 31u) & 1u)) return;
-  const uint32_t slot = __ldg(cell_start + keys[i]) + rank[i];
-  planes[slot] = __ldg(aos + (size_t)i * GVPM_AOS_FLOAT4);
-  orig[slot] = i;
 }
 // (key, index) of the kept photons, in index order, packed to the front: block_off = exclusive scan of block_kept
 __global__ void __launch_bounds__(256) k_compact_kept(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ keepmask,
@@ -885,7 +865,6 @@ void launch_pack_scatter(const PhotonStaging &S, uint32_t n, const uint32_t *kee
                          const uint32_t *cell_start, float4 *aos, float4 *planes, uint32_t *orig, cudaStream_t st,
                          bool records_ready, const uint32_t *kept_dev) {
   if (!n) return;
-  (void)k_frustum_scatter;
   if (!records_ready) k_pack_aos_kept<<<(n + 255) / 256, 256, 0, st>>>(S, n, keepmask, aos);
   k_scatter_index<<<(n + 255) / 256, 256, 0, st>>>(keys, rank, keepmask, cell_start, n, orig);
   k_gather_by_index<<<std::min<uint32_t>((n + 255) / 256, 148u * 16u), 256, 0, st>>>(aos, orig, kept_dev, planes);

@@ -163,3 +163,37 @@ def test_frustum_radix_sort_variant_matches_oracle(built, monkeypatch):
     case = H.make_case(n_photons=60000, w=64, h=48, scale=2.0)
     ref, kept = _check(case, "frustum, radix sort")
     assert ref.counts[:, 0].sum() > 3000
+
+
+def test_view_direction_does_not_change_results(built):
+    """gvpm_set_view_direction only picks the projection plane of the perspective grid: same neighbour counts, same
+    radiance for the default (mean ray direction), the sensor axis and a tilted axis; a zero vector is rejected"""
+    from gvpm_b200.api import GvpmError
+    case = H.make_case(n_photons=50000, w=64, h=48, scale=2.0)
+    res = []
+    for d in (None, (0.0, 0.0, 1.0), (0.3, -0.2, 1.0)):
+        ctx = H.gpu_context(case)
+        if d is not None:
+            ctx.set_view_direction(d)
+        ctx.build_points_for_rays(case.radius, want_kept=False)
+        assert ctx.accel_kind() == "frustum"
+        out, counts = ctx.gather_bre()
+        res.append((out, counts))
+        if d is not None:
+            with pytest.raises(GvpmError):
+                ctx.set_view_direction((0.0, 0.0, 0.0))
+        ctx.close()
+    for out, counts in res[1:]:
+        np.testing.assert_array_equal(counts, res[0][1])
+        H.assert_radiance_close(out, res[0][0], 1e-5, "view direction")
+    assert res[0][1][:, 0].sum() > 2000
+
+
+def test_read_bandwidth_probe(built):
+    """gvpm_measure_read_bandwidth (the roofline's L2 / HBM denominators): an L2-resident sweep is faster than an HBM one"""
+    from gvpm_b200.api import Context
+    ctx = Context(0)
+    l2 = max(ctx.measure_read_bandwidth(32 << 20, 50) for _ in range(2))
+    hbm = max(ctx.measure_read_bandwidth(2 << 30, 2) for _ in range(2))
+    assert l2 > hbm > 1000.0, (l2, hbm)
+    ctx.close()
