@@ -200,6 +200,11 @@ __global__ void k_flag_wait(const uint32_t *flags, int n, uint32_t target, unsig
   }
   __threadfence_system();
 }
+// dst |= src: a protocol failure seen by k_flag_wait (a peer that never signalled) makes the grid built over that inbox
+// "incomplete", which the gather reports instead of returning a partial result
+__global__ void k_or_flag(uint32_t *dst, const uint32_t *src) {
+  if (*src) *dst = 1u;
+}
 // the same value into one word of every peer (e.g. "my inbox b is free again")
 __global__ void k_flag_set(const __grid_constant__ FlagSetParams P) {
   if ((int)threadIdx.x < P.n) {
@@ -233,6 +238,7 @@ void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *t
   k_flag_wait<<<1, 1, 0, st>>>(flags, n, target, timeout);
 }
 void launch_flag_set(const FlagSetParams &P, cudaStream_t st) { k_flag_set<<<1, 32, 0, st>>>(P); }
+void launch_or_flag(uint32_t *dst, const uint32_t *src, cudaStream_t st) { k_or_flag<<<1, 1, 0, st>>>(dst, src); }
 void launch_translate_idx(uint32_t *idx, unsigned long long n, const float4 *aos, cudaStream_t st) {
   if (n) k_translate_idx<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, n, aos);
 }

@@ -39,6 +39,7 @@ void launch_dispatch(const DispatchParams &P, cudaStream_t st, int ctas);
 void launch_dispatch_signal(const SignalParams &P, cudaStream_t st);
 void launch_flag_wait(const uint32_t *flags, int n, uint32_t target, unsigned *timeout, cudaStream_t st);
 void launch_flag_set(const FlagSetParams &P, cudaStream_t st);
+void launch_or_flag(uint32_t *dst, const uint32_t *src, cudaStream_t st);
 void launch_l2_read(const void *p, size_t bytes, int reps, unsigned *sink, int sm_count, cudaStream_t st);
 void launch_translate_idx(uint32_t *idx, unsigned long long n, const float4 *aos, cudaStream_t st);
 void launch_compact_kept(const uint32_t *keys, const uint32_t *keepmask, const uint32_t *block_off, uint32_t n,
@@ -502,8 +503,9 @@ int pending_check(gvpm_ctx *ctx, bool block) {
     if (total >= kBuildOverflow) {   // the bounded frustum build was too small: nothing was gathered
       ctx->force_exact_build = true;
       return fail(ctx, GVPM_ERR_INVALID,
-                  "the perspective grid was sized from the previous iteration's photon count and this iteration kept over "
-                  "25 % more: the gather did not run.  Build again (the next build reads its exact count) and gather again");
+                  "the perspective grid is incomplete - it was sized from the previous iteration's photon count and this "
+                  "iteration kept over 25 % more, or a peer's photon dispatch never arrived (gvpm_dispatch_status): the gather "
+                  "did not run.  Build again (the next build reads its exact count) and gather again");
     }
     // overflow: make the list large enough for the next one
     cudaStreamSynchronize(ctx->stream);
@@ -562,8 +564,9 @@ int gather_finish(gvpm_ctx *ctx, float *out_dev, uint32_t *counts_dev, const uns
   if (total >= kBuildOverflow) {
     ctx->force_exact_build = true;
     return fail(ctx, GVPM_ERR_INVALID,
-                "the perspective grid was sized from the previous iteration's photon count and this iteration kept over "
-                "25 % more: the gather did not run.  Build again (the next build reads its exact count) and gather again");
+                "the perspective grid is incomplete - it was sized from the previous iteration's photon count and this "
+                "iteration kept over 25 % more, or a peer's photon dispatch never arrived (gvpm_dispatch_status): the gather "
+                "did not run.  Build again (the next build reads its exact count) and gather again");
   }
   int rc = reserve_pairs(ctx, total + total / 8 + 1024);
   if (rc) return rc;
@@ -1863,8 +1866,14 @@ int gvpm_build_dispatched(gvpm_ctx *ctx, int which, float radius, uint32_t *n_ke
   }
   rc = build_frustum(ctx, radius, n_kept);
   if (rc) return rc;
-  // a peer that never signalled (k_flag_wait timed out) or a region overflow: visible once the stream has drained; the
-  // gathers check at their own synchronisation point (gvpm_dispatch_status)
+  // a peer that never signalled (k_flag_wait timed out) or a region overflow: the grid is incomplete, and the gather says
+  // so (the same device flag a bounded build sets when it overflows); gvpm_dispatch_status names the cause
+  if (ctx->build_ovf) {
+    launch_or_flag(const_cast<uint32_t *>(ctx->build_ovf), ctrl + DC_TIMEOUT, ctx->stream);
+    launch_or_flag(const_cast<uint32_t *>(ctx->build_ovf), ctrl + DC_OVERFLOW, ctx->stream);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+  }
   return GVPM_OK;
 }
 
