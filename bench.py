@@ -7,14 +7,15 @@
 Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M photons per iteration,
 G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
 A step = accel build + gather of every camera-ray medium segment of the image (primal + 4 gradient
-contributions = 27 floats per ray).  N > 1: strong scaling — the 32x32 gather blocks are dealt to the ranks in
-column bands of the image (gvpm_b200/shard.py); the iteration's photon set, of which every rank holds 1/N (what it
-uploaded over its own PCIe link), is exchanged over NVLink into every rank's staging buffer (peer copies, or an NCCL
-all-gather); every rank builds its hierarchy over the photons its own rays can reach (gvpm_build_points_for_rays)
-and gathers its blocks; results are gathered to rank 0 (north_star).  The photon
-exchange of iteration k+1 is double-buffered behind the build + gather of iteration k (a renderer
-traces the next iteration's photons while the current one is gathered); the K timed steps contain
-K exchanges.  No other data-path collective.
+contributions = 27 floats per ray).  N > 1: strong scaling - the 32x32 gather blocks are dealt to the ranks in
+cost-balanced column bands of the image (gvpm_b200/shard.py, costs from one untimed pilot iteration); every rank holds
+1/N of the iteration's photon set and DISPATCHES it (gvpm_dispatch_*): each photon goes, as a packed 128-byte gather
+record over peer-mapped NVLink stores, only to the ranks whose rays can reach it; every rank builds its perspective grid
+over what it received and gathers its blocks; results go to rank 0's shared image buffer by device-to-device copies
+(north_star: "primal and gradient buffers gathered at the end of each iteration").  The dispatch of iteration k+1 is
+double-buffered behind the build + gather of iteration k (a renderer traces the next iteration's photons while the
+current one is gathered); the K timed steps contain K dispatches and K result collections.  Ray sets that are not
+concurrent fall back to the round-1 whole-set exchange (peer copies, or an NCCL all-gather).
 
 value  = rays / s with the rays and each rank's photon slice already resident in HBM.
 e2e    = same through the C ABI with HOST (pinned) buffers: H2D of the photon slice (gvpm_upload_photons_slice)
