@@ -318,7 +318,22 @@ dist.broadcast(photons, src=0)
 assert float(photons.sum()) == 999 * 1000 / 2
 mode = sys.argv[2] if len(sys.argv) > 2 else "tile"
 def indices(r):
+    if mode == "weighted":
+        return np.nonzero(owner_w == r)[0]
     return shard.band_indices(px, py, w, h, world, r, 2) if mode == "band" else shard.local_indices(px, py, w, world, r)
+if mode == "weighted":
+    # bench.py rebalance_bands: every rank measures the cost of its equal-size bands (here: a centre-weighted density),
+    # the per-block costs are summed over the ranks, and every rank derives the SAME cost-balanced partition from them
+    t = shard.block_index(px, py, h)
+    mine0 = shard.band_indices(px, py, w, h, world, rank, 2)
+    dens = 1.0 + 6.0 * np.exp(-((px - w / 2) / 20.0) ** 2 - ((py - h / 2) / 15.0) ** 2)
+    n_tiles = ((w + 31) // 32) * ((h + 31) // 32)
+    cost = torch.from_numpy(np.bincount(t[mine0], weights=dens[mine0], minlength=n_tiles))
+    dist.all_reduce(cost)
+    owner_w = shard.band_owner_weighted(px, py, w, h, world, cost.numpy(), 2)
+    sizes = torch.tensor([float(dens[owner_w == r].sum()) for r in range(world)], dtype=torch.float64)
+    other = sizes.clone(); dist.broadcast(other, src=0)
+    assert torch.equal(sizes, other)                       # identical partition on every rank
 idx = indices(rank)
 n_pad = torch.tensor([len(idx)]); dist.all_reduce(n_pad, op=dist.ReduceOp.MAX); n_pad = int(n_pad)
 out = torch.zeros(n_pad, 27)
@@ -335,14 +350,15 @@ dist.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("mode", ["tile", "band"])
+@pytest.mark.parametrize("mode", ["tile", "band", "weighted"])
 def test_sharded_gather_world2_gloo(tmp_path, mode):
     """The N > 1 plumbing of bench.py (broadcast photons, gather per-rank results of unequal size, reassemble) on
-    2 CPU ranks over gloo, for the round-robin and the column-band partition."""
+    2 CPU ranks over gloo, for the round-robin, the column-band and the cost-balanced column-band partition (costs
+    all-reduced over the ranks as in bench.py rebalance_bands)."""
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533" if mode == "tile" else "29534", str(script), ROOT, mode]
+           "--master-addr", "127.0.0.1", "--master-port", {"tile": "29533", "band": "29534", "weighted": "29535"}[mode], str(script), ROOT, mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "GLOO_OK" in res.stdout
