@@ -1,0 +1,75 @@
+"""ctypes binding of oracle/_ref/libgvpm_functor_ref.so: the REFERENCE'S OWN BRE shift functor
+(VolumeGradientBREQuery::operator(), gvpm/shift/shift_volume_photon.cpp:658-856, with shiftNull / shiftPhotonDiffuse /
+getShiftPos and everything they evaluate) built by `make -C oracle functor_ref` from /root/reference and driven on the
+flattened C-ABI inputs by oracle/ref_functor.cpp.
+
+TEST INFRASTRUCTURE: used by tests/test_oracle_functor_pin.py and tests/golden/make_functor_golden.py only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gvpm_b200 import _native as N
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libgvpm_functor_ref.so")
+REFERENCE_ROOT = os.environ.get("GVPM_REFERENCE_ROOT", "/root/reference")
+_lib = None
+
+
+def build_ref():
+    if os.path.isdir(REFERENCE_ROOT):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "functor_ref", f"REF={REFERENCE_ROOT}"])
+    return os.path.exists(REF_LIB)
+
+
+def have_ref():
+    return os.path.exists(REF_LIB)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not have_ref():
+            raise FileNotFoundError(REF_LIB)
+        _lib = C.CDLL(REF_LIB)
+        _lib.ref_fn_bre_gather.restype = C.c_int
+        _lib.ref_fn_bre_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           N.f32p, C.c_size_t, C.c_float, N.f32p, N.u32p]
+        _lib.ref_fn_vpm_gather.restype = C.c_int
+        _lib.ref_fn_vpm_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.c_void_p, N.f32p, C.c_size_t, C.c_int, N.f32p, N.f32p]
+    return _lib
+
+
+def bre_gather(photons, rays, medium, config, tri, radius):
+    """The reference functor over every (ray, photon) pair of the neighbour predicate (gvpm_accel.h:293-305), photons in
+    index order.  Returns (out [n_rays, 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4]; counts [n_rays])."""
+    lib = load()
+    cph, cr = photons.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    counts = np.zeros(rays.n, dtype=np.uint32)
+    rc = lib.ref_fn_bre_gather(C.byref(cph), photons.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                               tri.ctypes.data_as(N.f32p), tri.size // 9, radius, out.ctypes.data_as(N.f32p),
+                               counts.ctypes.data_as(N.u32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_bre_gather refused the input: {rc}")
+    return out.reshape(rays.n, 27), counts
+
+
+def vpm_gather(photons, rays, samples, medium, config, tri, nb_camera_samples):
+    """The reference's point-VPM functor (VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp:489-655) over the
+    host-drawn distance samples, folded per pixel as gvpm.cpp:1175-1182 does.  Returns (out [n_rays, 27], MVol [n_rays])."""
+    lib = load()
+    cph, cr, cs = photons.as_c(), rays.as_c(), samples.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    mvol = np.zeros(rays.n, dtype=np.float32)
+    rc = lib.ref_fn_vpm_gather(C.byref(cph), photons.n, C.byref(cr), rays.n, C.byref(cs), samples.n, C.byref(medium),
+                               C.byref(config), tri.ctypes.data_as(N.f32p), tri.size // 9, nb_camera_samples,
+                               out.ctypes.data_as(N.f32p), mvol.ctypes.data_as(N.f32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_vpm_gather refused the input: {rc}")
+    return out.reshape(rays.n, 27), mvol

@@ -1,0 +1,463 @@
+// ref_functor.cpp — TEST INFRASTRUCTURE.  Drives the REFERENCE'S OWN point-photon shift functors
+//   VolumeGradientBREQuery::operator()                    gvpm/shift/shift_volume_photon.cpp:658-856   (G-BRE)
+//   VolumeGradientPositionQuery::operator()               :489-655                                     (G-VPM)
+//   shiftNull / shiftPhoton / shiftPhotonDiffuse           :119-158, :49-117, :382-486
+//   getShiftPos                                           :858-896
+//   + getTypeShift / VertexClassifier, diffuseReconnection, HomogeneousMedium::eval, the phase functions, the diffuse
+//     BSDF, the area emitter
+// compiled from /root/reference where it lies (oracle/Makefile, target functor_ref -> _ref/libgvpm_functor_ref.so; no
+// reference source is copied) on the flattened inputs of the C ABI (gvpm_photon_soa / gvpm_ray_soa / gvpm_vpm_sample_soa,
+// include/gvpm_b200.h), so that the oracle's restatement of the functors' CONTROL FLOW (which offsets take the null
+// shift, which the diffuse reconnection, the border rule, the filters, the MIS weights, the accumulation) is pinned to
+// reference output, not only its radiometric building blocks (ref_physics.cpp).
+//
+// What this file does: it rebuilds, for every (camera segment, photon) pair, the reference-side objects the functors
+// read - a GatherPoint with its camera Path and cached vertex weights, four ShiftGatherPoints marked as generated, the
+// photon's light Path (emitter sample, intermediate medium vertices, predecessor, emitter / diffuse surface / medium
+// parent vertex, prefix weights), a GPhotonNodeKD - from the flattened arrays, evaluates the neighbour predicate with the
+// statements of GradientBeamRadianceEstimator::query (gvpm_accel.h:293-301) / PointKDTree::executeQuery
+// (kdtree.h:721-723), and calls the functor.  All radiometry and every branch is the reference's.  Restricted to first
+// medium edges (edge_id = 1: sensorMIS has no geometry terms there, gvpm_struct.h:608-631), which is what primary camera
+// rays are.
+//
+// Objects of the reference that cannot be constructed here (Scene, Sensor, Film, ShapeKDTree, GPMThreadData need the
+// whole renderer) are raw zeroed storage with the two or three members the functor reads poked in; the shadow ray of
+// the reconnection reaches ShapeKDTree::rayIntersect, which functor_stubs.cpp answers with the reference's own
+// Triangle::rayIntersect over the harness' triangle list.
+#include <array>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+// every standard header the reference's headers pull in, BEFORE the access override below (libstdc++ does not survive it)
+#include <algorithm>
+#include <cmath>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <memory>
+#include <numeric>
+#include <queue>
+#include <set>
+#include <sstream>
+#include <stack>
+#include <stdexcept>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+#include <utility>
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <random>
+#include <chrono>
+#include <complex>
+#include <bitset>
+#include <iterator>
+#include <typeinfo>
+#include <cassert>
+#include <cstdio>
+#include <cstdint>
+
+// the functor's configuration, scene and film members are private / protected; the harness pokes them directly
+#define private public
+#define protected public
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/sensor.h>
+#include <mitsuba/render/film.h>
+#include <mitsuba/bidir/path.h>
+#include "gvpm/shift/shift_volume_photon.h"
+#undef private
+#undef protected
+
+#include "ref_physics.cpp"   // makePhase / makeMedium / makeDiffuse / HarnessShape and the ref_phys_* entries
+
+#include "../include/gvpm_b200.h"
+
+namespace mitsuba {
+// the triangle list the stand-in of ShapeKDTree::rayIntersect walks (functor_stubs.cpp)
+extern std::vector<std::array<Point, 3>> g_functor_occluders;
+}
+
+namespace {
+
+template <class T> T *rawZeroed() {
+  void *p = std::calloc(1, sizeof(T) + 64);
+  return reinterpret_cast<T *>(p);
+}
+
+struct LightPath {
+  std::vector<PathVertex> v;
+  std::vector<PathEdge> e;
+  std::vector<ref<BSDF>> bsdfs;
+  std::vector<ref<HarnessShape>> shapes;
+  Path path;
+};
+
+void zero(PathVertex &x) { std::memset(&x, 0, sizeof(x)); x.sampledComponentIndex = -1; x.rrWeight = 1.f; }
+void zero(PathEdge &x) { std::memset(&x, 0, sizeof(x)); }
+
+
+// Everything the functors read that does not depend on the camera segment: medium, emitter, the stand-in scene, the
+// configuration and one light Path + kd node per photon.
+struct World {
+  ref<PhaseFunction> phase;
+  ref<Medium> medium;
+  ref<Emitter> em;
+  Scene *scene = nullptr;
+  GPMThreadData *thdata = nullptr;
+  GPMConfig config;
+  std::vector<LightPath> lps;
+  std::vector<GPhotonNodeKD> nodes;
+
+  ~World() {
+    for (auto &L : lps) { L.path.m_vertices.clear(); L.path.m_edges.clear(); }   // they point into L.v / L.e
+  }
+
+  int build(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
+            size_t n_tri, EVolumeTechnique technique) {
+    initOnce();
+    phase = makePhase(med->phase_type, med->hg_g);
+    medium = makeMedium(med->sigma_s, med->sigma_a, med->sampling_weight, phase.get());
+    Properties ep("area");
+    float one[3] = {1.f, 1.f, 1.f};
+    ep.setSpectrum("radiance", S3(one));
+    em = static_cast<Emitter *>(CreateInstance_area(ep));
+
+    g_functor_occluders.clear();
+    for (size_t t = 0; t < n_tri; ++t)
+      g_functor_occluders.push_back({P3(tri + 9 * t), P3(tri + 9 * t + 3), P3(tri + 9 * t + 6)});
+
+    // Scene -> sensor -> film size, Scene -> kd-tree (any-hit): raw storage, members poked in
+    scene = rawZeroed<Scene>();
+    Sensor *sensor = rawZeroed<Sensor>();
+    Film *film = rawZeroed<Film>();
+    film->m_size = Vector2i(cfg->film_w, cfg->film_h);
+    sensor->m_film.m_ptr = film;
+    scene->m_sensor.m_ptr = sensor;
+    scene->m_kdtree.m_ptr = rawZeroed<ShapeKDTree>();
+    thdata = rawZeroed<GPMThreadData>();
+
+    std::memset((void *)&config, 0, offsetof(GPMConfig, forceAPA));
+    config.maxDepth = cfg->max_depth;
+    config.minDepth = cfg->min_depth;
+    config.lightingInteractionMode = cfg->lighting_mode;
+    config.bsdfInteractionMode = BSDF::EAll;
+    config.useManifold = false;
+    config.useMIS = cfg->use_mis != 0;
+    config.debugShift = EAllShift;
+    config.noMediumShift = true;                    // plugin default, gvpm_struct.h:191
+    config.volTechnique = technique;
+    config.useShiftNull = cfg->use_shift_null != 0;
+    config.pathSet = cfg->path_set != 0;
+    config.powerHeuristic = cfg->power_heuristic != 0;
+    VertexClassifier::roughnessThreshold = 0.05f;   // bounceRoughness default (gvpm_struct.h:236)
+
+    lps.resize(n_ph);
+    nodes.resize(n_ph);
+    const gvpm_medium *medp = med;
+  for (size_t i = 0; i < n_ph; ++i) {
+    LightPath &L = lps[i];
+    const size_t c = (size_t)ph->depth[i] + 1;   // vertexId
+    if (c < 2) return -2;
+    const int ptype = ph->parent_type[i];
+    if ((ptype == 0) != (c == 2)) return -3;     // the emitter sample is vertex 1: parent of the photons with vertexId 2 only
+    L.v.resize(c + 1);
+    L.e.resize(c);
+    for (auto &x : L.v) zero(x);
+    for (auto &x : L.e) zero(x);
+    // prefix: vertex(0).weight * rr * edge(0).weight * prod_{1 <= i < c-1} (...) = prefix_flux (every other factor is 1)
+    L.v[0].type = PathVertex::EEmitterSupernode;
+    L.v[0].weight[EImportance] = S3(ph->prefix_flux + 3 * i);
+    for (size_t k = 0; k < c; ++k) { L.e[k].weight[EImportance] = Spectrum(1.f); L.e[k].medium = medium.get(); }
+    for (size_t k = 1; k <= c; ++k) L.v[k].weight[EImportance] = Spectrum(1.f);
+    const Point pos = P3(ph->pos + 3 * i), parent = P3(ph->parent_pos + 3 * i), pred = P3(ph->pred_pos + 3 * i);
+    const Normal nrm(V3f(ph->parent_n + 3 * i));
+    // vertex 1 is always the emitter sample (getTypeShift walks back to it: the classifier calls it diffuse,
+    // gvpm_struct.h:71, so a light path always has a reconnectable vertex); vertices 2 .. c-3 carry nothing else the
+    // functor reads (medium interactions, classified by the phase function's mean cosine); the predecessor (c-2) its
+    // position
+    if (c >= 3) {
+      L.v[1].type = PathVertex::EEmitterSample;
+      PositionSamplingRecord &pr = L.v[1].getPositionSamplingRecord();
+      new (&pr) PositionSamplingRecord();
+      pr.p = pred;
+      pr.measure = EArea;
+      pr.object = em.get();
+    }
+    for (size_t k = 2; k + 2 < c; ++k) {
+      L.v[k].type = PathVertex::EMediumInteraction;
+      MediumSamplingRecord &m = L.v[k].getMediumSamplingRecord();
+      new (&m) MediumSamplingRecord();
+      m.p = pred;
+      m.medium = medium.get();
+    }
+    if (c >= 3) {
+      PathVertex &q = L.v[c - 2];
+      if (c - 2 == 1) {
+        q.type = PathVertex::EEmitterSample;
+        PositionSamplingRecord &pr = q.getPositionSamplingRecord();
+        new (&pr) PositionSamplingRecord();
+        pr.p = pred;
+        pr.measure = EArea;
+        pr.object = em.get();
+      } else {
+        q.type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = q.getMediumSamplingRecord();
+        new (&m) MediumSamplingRecord();
+        m.p = pred;
+        m.medium = medium.get();
+      }
+    }
+    // parent vertex (c-1)
+    PathVertex &v = L.v[c - 1];
+    v.pdf[EImportance] = ph->parent_pdf[i];
+    v.rrWeight = ph->rr_weight[i];
+    if (ptype == 1) {
+      v.type = PathVertex::ESurfaceInteraction;
+      Intersection &its = v.getIntersection();
+      new (&its) Intersection();
+      its.p = parent;
+      its.geoFrame = Frame(nrm);
+      its.shFrame = its.geoFrame;
+      L.bsdfs.push_back(makeDiffuse(ph->parent_albedo + 3 * i));
+      L.shapes.push_back(new HarnessShape(L.bsdfs.back().get()));
+      its.shape = L.shapes.back().get();
+      its.wi = its.toLocal(normalize(pred - parent));
+      its.t = 1.f;
+    } else if (ptype == 2) {
+      v.type = PathVertex::EMediumInteraction;
+      MediumSamplingRecord &m = v.getMediumSamplingRecord();
+      new (&m) MediumSamplingRecord();
+      m.p = parent;
+      m.medium = medium.get();
+      m.sigmaS = S3(med->sigma_s);
+      m.sigmaA = S3(med->sigma_a);
+    } else if (ptype == 0) {
+      v.type = PathVertex::EEmitterSample;
+      PositionSamplingRecord &pr = v.getPositionSamplingRecord();
+      new (&pr) PositionSamplingRecord();
+      pr.p = parent;
+      pr.n = nrm;
+      pr.measure = EArea;
+      pr.object = em.get();
+    } else {
+      return -4;   // GVPM_PARENT_OTHER: manifold shift, out of scope
+    }
+    // the photon's own vertex and the edge that carries it
+    PathVertex &pv = L.v[c];
+    pv.type = PathVertex::EMediumInteraction;
+    MediumSamplingRecord &pm = pv.getMediumSamplingRecord();
+    new (&pm) MediumSamplingRecord();
+    pm.p = pos;
+    pm.medium = medium.get();
+    pm.sigmaS = S3(med->sigma_s);
+    pm.sigmaA = S3(med->sigma_a);
+    PathEdge &pe = L.e[c - 1];
+    Vector d = pos - parent;
+    pe.length = d.length();
+    pe.d = d / pe.length;   // what the tracer stores; the flattened form recomputes wi = normalize(parent - pos) = -d
+    pe.pdf[EImportance] = ph->edge_pdf[i];
+    for (size_t k = 0; k <= c; ++k) {
+      L.path.append(&L.v[k]);
+      if (k < c) L.path.append(&L.e[k]);
+    }
+    nodes[i].setPosition(pos);
+    nodes[i].setData(GPhotonNodeData(&L.path, (int)c, S3(ph->flux + 3 * i), ph->path_id[i]));
+  }
+    (void)medp;
+    return 0;
+  }
+};
+
+// One camera medium segment with its four offset segments as the functors see them: a GatherPoint with its camera Path
+// and cached vertex weights, four ShiftGatherPoints marked as generated.  Holds pointers into itself: built in place.
+struct CameraSide {
+  PathVertex bv[3];
+  PathEdge be[2];
+  GatherPoint gp;
+  PathVertex sv[4][3];
+  PathEdge se[4][2];
+  std::vector<ShiftGatherPoint> shiftGPs;
+  CameraSide() : shiftGPs(4) {}
+  CameraSide(const CameraSide &) = delete;
+  ~CameraSide() {
+    gp.path.m_vertices.clear(); gp.path.m_edges.clear();
+    for (auto &s : shiftGPs) { s.path.m_vertices.clear(); s.path.m_edges.clear(); }
+  }
+  void build(const gvpm_ray_soa *ry, size_t r, const Medium *mediumPtr) {
+    // base gather point: supernode, sensor sample (pixel position), the medium edge, its end vertex
+    for (auto &x : bv) zero(x);
+    for (auto &x : be) zero(x);
+    bv[0].type = PathVertex::ESensorSupernode;
+    bv[1].type = PathVertex::ESensorSample;
+    {
+      PositionSamplingRecord &pr = bv[1].getPositionSamplingRecord();
+      new (&pr) PositionSamplingRecord();
+      pr.p = P3(ry->o + 3 * r);
+      pr.uv = Point2((Float)ry->px[r] + 0.5f, (Float)ry->py[r] + 0.5f);
+    }
+    be[1].d = V3f(ry->d + 3 * r);
+    be[1].length = ry->edge_len[r];
+    be[1].medium = mediumPtr;
+    gp.path.append(&bv[0]); gp.path.append(&be[0]); gp.path.append(&bv[1]); gp.path.append(&be[1]); gp.path.append(&bv[2]);
+    gp.info.resize(2);
+    gp.info[0].weight = S3(ry->eye_contrib + 3 * r);     // getWeightBeam(e - 1)
+    gp.info[0].vertexWeight = Spectrum(1.f);
+    gp.info[0].pdf = gp.info[0].jacobian = 1.f;
+    gp.info[1].weight = Spectrum(1.f);
+    gp.info[1].vertexWeight = Spectrum(1.f);             // getWeightVertex(e)
+    gp.info[1].pdf = gp.info[1].jacobian = 1.f;
+
+    for (int k = 0; k < 4; ++k) {
+      for (auto &x : sv[k]) zero(x);
+      for (auto &x : se[k]) zero(x);
+      const size_t q = 4 * r + k;
+      sv[k][0].type = PathVertex::ESensorSupernode;
+      sv[k][1].type = PathVertex::ESensorSample;
+      PositionSamplingRecord &pr = sv[k][1].getPositionSamplingRecord();
+      new (&pr) PositionSamplingRecord();
+      pr.p = P3(ry->off_o + 3 * q);
+      se[k][1].d = -V3f(ry->off_d + 3 * q);              // the functor takes shiftDir = -edge(e).d
+      se[k][1].length = ry->off_len[q];
+      se[k][1].medium = ry->off_valid[q] ? mediumPtr : NULL;   // validVolumeEdge
+      ShiftGatherPoint &s = shiftGPs[k];
+      s.generated = true;                                // nothing to trace: generate() returns at once
+      s.path.append(&sv[k][0]); s.path.append(&se[k][0]); s.path.append(&sv[k][1]); s.path.append(&se[k][1]);
+      s.path.append(&sv[k][2]);
+      s.info.resize(2);
+      s.info[0].weight = S3(ry->off_eye + 3 * q);
+      s.info[0].vertexWeight = Spectrum(1.f);
+      s.info[0].pdf = s.info[0].jacobian = 1.f;
+      s.info[1].weight = Spectrum(1.f);
+      s.info[1].vertexWeight = Spectrum(1.f);
+      s.info[1].pdf = ry->off_sensor[q];                 // sensorMIS(1, base, ., .) = (pdf / base pdf) * jacobian
+      s.info[1].jacobian = 1.f;
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ref_fn_version() { return 2; }
+
+// G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
+// neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
+int ref_fn_bre_gather(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                      const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, float *out, uint32_t *counts) {
+  World W;
+  if (int rc = W.build(ph, n_ph, med, cfg, tri, n_tri, cfg->kernel_3d ? EVolBRE3D : EVolBRE2D)) return rc;
+  for (size_t r = 0; r < n_rays; ++r) {
+    for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
+    if (counts) counts[r] = 0;
+    const size_t e = (size_t)ry->edge_id[r];
+    if (e != 1) return -5;
+    CameraSide cam;
+    cam.build(ry, r, W.medium.get());
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    VolumeGradientBREQuery gRec(W.scene, &cam.gp, W.config, *W.thdata, cam.shiftGPs, e, NULL);
+    gRec.newRayBase(ray, W.medium.get());
+    gRec.clear();
+    for (size_t i = 0; i < n_ph; ++i) {
+      // GradientBeamRadianceEstimator::query, gvpm_accel.h:293-305
+      Vector originToCenter = W.nodes[i].getPosition() - ray.o;
+      Float diskDistance = dot(originToCenter, ray.d), radSqr = radius * radius;
+      Float distSqr = (ray(diskDistance) - W.nodes[i].getPosition()).lengthSquared();
+      if (diskDistance > ray.mint && distSqr < radSqr) {
+        Ray baseRay(ray);
+        baseRay.maxt = diskDistance;
+        gRec.newRayBase(baseRay, W.medium.get());
+        gRec(W.nodes[i], radius, ry->xi[r]);
+        if (counts) ++counts[r];
+      }
+    }
+    float *o = out + 27 * r;
+    putS(o, gRec.mediumFlux);
+    for (int k = 0; k < 4; ++k) {
+      putS(o + 3 * (1 + k), gRec.shiftedMediumFlux[k]);
+      putS(o + 3 * (5 + k), gRec.weightedMediumFlux[k]);
+    }
+  }
+  return 0;
+}
+
+// G-VPM: the per-sample part of computeVolumeGradientPhoton, gvpm.cpp:1141-1185, on the host-drawn distance samples of
+// gvpm_vpm_sample_soa.  Per sample: changeEdge / newRayBase / clear, the functor VolumeGradientPositionQuery::operator()
+// (shift_volume_photon.cpp:489-655) on every photon of PointKDTree's range predicate (kdtree.h:721-723) in photon order,
+// then gp.* += gRec.* * normalization (:1177-1182).  out: [n_rays * 27]; mvol: [n_rays] photons found (MVol, :1175).
+int ref_fn_vpm_gather(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t n_rays,
+                      const gvpm_vpm_sample_soa *smp, size_t n_smp, const gvpm_medium *med, const gvpm_config *cfg,
+                      const float *tri, size_t n_tri, int nb_camera_samples, float *out, float *mvol) {
+  World W;
+  if (int rc = W.build(ph, n_ph, med, cfg, tri, n_tri, EDistance)) return rc;
+  struct Pixel { Spectrum mediumFlux, shifted[4], weighted[4]; };
+  std::vector<Pixel> pix(n_rays);
+  for (auto &p : pix) {
+    p.mediumFlux = Spectrum(0.f);
+    for (int k = 0; k < 4; ++k) p.shifted[k] = p.weighted[k] = Spectrum(0.f);
+  }
+  for (size_t r = 0; r < n_rays; ++r) mvol[r] = 0.f;
+  const Float normalization = 1.f / nb_camera_samples;
+  for (size_t s = 0; s < n_smp; ++s) {
+    const size_t r = smp->ray[s];
+    if (r >= n_rays) return -6;
+    const size_t e = (size_t)ry->edge_id[r];
+    if (e != 1) return -5;
+    CameraSide cam;
+    cam.build(ry, r, W.medium.get());
+    VolumeGradientDistanceQuery gRec(W.scene, &cam.gp, W.config, *W.thdata, cam.shiftGPs, 0, NULL);
+    gRec.changeEdge(e, smp->pdf_sel[s]);
+    // Ray ray(oBeam, dBeam, Epsilon, beamDist, 0.f); sampleDistance fills mRec; ray.maxt = mRec.t
+    Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->edge_len[r], 0.f);
+    MediumSamplingRecord mRec;
+    mRec.t = smp->t[s];
+    mRec.p = ray(mRec.t);
+    mRec.medium = W.medium.get();
+    mRec.sigmaS = S3(med->sigma_s);
+    mRec.sigmaA = S3(med->sigma_a);
+    mRec.transmittance = S3(smp->transmittance + 3 * s);
+    mRec.pdfSuccess = smp->pdf_success[s];
+    mRec.pdfSuccessRev = mRec.pdfSuccess;
+    mRec.pdfFailure = 0.f;
+    mRec.time = 0.f;
+    ray.maxt = mRec.t;
+    const Float querySize = smp->radius[s];
+    gRec.newRayBase(ray, mRec, querySize, mRec.pdfSuccess);
+    gRec.clear();
+    const Point q = ray.o + mRec.t * ray.d;
+    size_t found = 0;
+    for (size_t i = 0; i < n_ph; ++i) {
+      // PointKDTree::executeQuery, include/mitsuba/core/kdtree.h:721-723
+      const Float pointDistSquared = (W.nodes[i].getPosition() - q).lengthSquared();
+      if (pointDistSquared < querySize * querySize) {
+        gRec(W.nodes[i]);
+        ++found;
+      }
+    }
+    mvol[r] += (float)found;
+    Pixel &g = pix[r];
+    g.mediumFlux += (gRec.mediumFlux * normalization);
+    for (int k = 0; k < 4; ++k) {
+      g.shifted[k] += (gRec.shiftedMediumFlux[k] * normalization);
+      g.weighted[k] += (gRec.weightedMediumFlux[k] * normalization);
+    }
+  }
+  for (size_t r = 0; r < n_rays; ++r) {
+    float *o = out + 27 * r;
+    putS(o, pix[r].mediumFlux);
+    for (int k = 0; k < 4; ++k) {
+      putS(o + 3 * (1 + k), pix[r].shifted[k]);
+      putS(o + 3 * (5 + k), pix[r].weighted[k]);
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+"""Seeded cases of the shift-functor pins (tests/test_oracle_functor_pin.py, tests/golden/make_functor_golden.py): the
+flattened inputs of the C ABI, evaluated by the reference's own compiled functors (oracle/functor_binding.py) or by the
+oracle restatement (oracle/binding.py).  Camera segments are first medium edges (edge_id = 1), the case the reference
+harness rebuilds (oracle/ref_functor.cpp)."""
+import zlib
+
+import numpy as np
+
+import gvpm_b200 as g
+import gvpm_testlib as H
+from gvpm_b200 import _native as N
+
+
+def _invalid_offsets(c):
+    c.rays.off_valid[::3] = 0
+
+
+def _xi(v):
+    def f(c):
+        c.rays.xi[:] = np.float32(v)
+    return f
+
+
+def _no_tri(c):
+    c.tri = np.zeros(0, np.float32)
+
+
+def _blocker(c):
+    """Sheets 2e-4 above every wall of the unit box.  The reference's reconnection shadow ray only spans
+    [Epsilon, |parent - offset position| * ShadowEpsilon] (shift_volume_photon.cpp:396-399: 0.1 % of the connection), so
+    nothing further from the parent vertex can block it; these sheets cut the connections that leave a wall steeply."""
+    e, tris = 2e-4, []
+    for axis in range(3):
+        for side in (e, 1.0 - e):
+            u, v = [k for k in range(3) if k != axis]
+            def pt(a, b):
+                q = [0.0, 0.0, 0.0]
+                q[axis], q[u], q[v] = side, a, b
+                return q
+            tris += [pt(0, 0), pt(1, 0), pt(1, 1), pt(0, 0), pt(1, 1), pt(0, 1)]
+    c.tri = np.concatenate([np.asarray(c.tri, np.float32).reshape(-1), np.asarray(tris, np.float32).reshape(-1)])
+
+
+# name -> (make_case keywords, post-processing)
+BRE = {
+    "default": (dict(), None),
+    "hg_forward_0.7": (dict(phase="hg", hg_g=0.7), None),     # mean cosine > 0.5: medium vertices classify as glossy
+    "hg_backward_0.4": (dict(phase="hg", hg_g=-0.4), None),
+    "no_mis": (dict(use_mis=False), None),
+    "wide": (dict(scale=10.0), None),                          # kernels overlap the offset rays: null shifts
+    "wide_no_shift_null": (dict(scale=10.0, use_shift_null=False), None),
+    "no_path_set": (dict(path_set=False), None),
+    "power_heuristic_hg": (dict(power_heuristic=True, path_set=False, phase="hg", hg_g=0.3), None),
+    "kernel_2d": (dict(kernel_3d=False), None),
+    "max_depth_4": (dict(max_depth=4), None),
+    "min_depth_3": (dict(min_depth=3), None),
+    "surf2media": (dict(lighting_mode=N.SURF2MEDIA), None),
+    "media2media": (dict(lighting_mode=N.MEDIA2MEDIA), None),
+    "no_occluders": (dict(), _no_tri),
+    "blocker": (dict(), _blocker),
+    "blocker_wide_hg": (dict(scale=8.0, phase="hg", hg_g=0.6), _blocker),
+    "invalid_offsets": (dict(), _invalid_offsets),
+    "xi_0": (dict(), _xi(0.0)),
+    "xi_1": (dict(), _xi(0.99999994)),
+    "big": (dict(n_photons=20000, w=40, h=24, scale=2.0, seed=7, phase="hg", hg_g=0.9), None),
+}
+
+VPM = {
+    "default": (dict(), None),
+    "hg_forward_0.7": (dict(phase="hg", hg_g=0.7), None),
+    "no_mis": (dict(use_mis=False), None),
+    "wide": (dict(scale=8.0), None),
+    "wide_no_shift_null": (dict(scale=8.0, use_shift_null=False), None),
+    "max_depth_4": (dict(max_depth=4), None),
+    "surf2media": (dict(lighting_mode=N.SURF2MEDIA), None),
+    "power_heuristic": (dict(power_heuristic=True), None),
+    "invalid_offsets": (dict(), _invalid_offsets),
+    "blocker": (dict(), _blocker),
+    "one_radius": (dict(vary_radius=False), None),
+}
+VPM_SAMPLES = 8
+
+
+def bre_case(name):
+    kw, post = BRE[name]
+    kw = dict(dict(n_photons=3000, w=16, h=12, scale=3.0), **kw)
+    c = H.make_case(**kw)
+    c.rays.edge_id[:] = 1
+    if post:
+        post(c)
+    return c
+
+
+def vpm_case(name):
+    kw, post = VPM[name]
+    kw = dict(dict(n_photons=6000, w=16, h=12, scale=3.0, vary_radius=True), **kw)
+    vary = kw.pop("vary_radius")
+    c = H.make_case(**kw)
+    c.rays.edge_id[:] = 1
+    if post:
+        post(c)
+    rad = np.full(c.rays.n, c.radius, dtype=np.float32)
+    if vary:   # per-pixel SPPM radii (gp.scaleVol, gvpm.cpp:1131,1191-1195)
+        rad *= np.random.default_rng(2).uniform(0.4, 1.0, c.rays.n).astype(np.float32)
+    c.samples = g.synth_vpm_samples(c.rays, c.medium, rad, nb_camera_samples=VPM_SAMPLES, seed=99)
+    c.nb = VPM_SAMPLES
+    return c
+
+
+def input_crc(c):
+    """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
+    h = 0
+    for a in (c.photons.pos, c.photons.flux, c.photons.parent_pos, c.photons.parent_type, c.rays.o, c.rays.d,
+              c.rays.off_o, c.rays.off_d, c.rays.off_valid, c.rays.xi, c.rays.eye_contrib, c.rays.off_sensor, c.tri):
+        h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    if hasattr(c, "samples"):
+        for a in (c.samples.ray, c.samples.t, c.samples.radius, c.samples.pdf_success):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    return np.uint32(h)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def past_ray_end(c):
+    """Rays with a photon of the neighbour predicate whose projection lies beyond the segment end (within a margin):
+    where the reference's 2-D kernel leaves `baseProjDist > edgeLen` as an empty block (shift_volume_photon.cpp:726-731)
+    and the oracle applies the explicit bound."""
+    p = c.photons.view("pos").astype(np.float64)
+    o, d = c.rays.view("o").astype(np.float64), c.rays.view("d").astype(np.float64)
+    dd = np.einsum("rpk,rk->rp", p[None, :, :] - o[:, None, :], d)
+    foot = o[:, None, :] + dd[:, :, None] * d[:, None, :]
+    dist2 = ((foot - p[None, :, :]) ** 2).sum(axis=2)
+    r2 = float(c.radius) ** 2
+    hit = (dist2 < 1.01 * r2) & (dd > c.rays.edge_len[:, None].astype(np.float64) - 1e-3)
+    return hit.any(axis=1)

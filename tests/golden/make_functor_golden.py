@@ -1,0 +1,36 @@
+"""Regenerates tests/golden/functor_pins.npz from the REFERENCE'S OWN shift functors (oracle/_ref/libgvpm_functor_ref.so:
+VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp, compiled from
+/root/reference by `make -C oracle functor_ref` and driven by oracle/ref_functor.cpp).  Run in the container that holds the
+reference tree:
+    python tests/golden/make_functor_golden.py
+The vectors let tests/test_oracle_functor_pin.py hold the oracle to the reference where the tree is absent."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as ge  # noqa: E402
+import functor_pin_cases as cases  # noqa: E402
+from oracle import functor_binding as fb  # noqa: E402
+
+if __name__ == "__main__":
+    ge.build_cpu_libs()
+    assert fb.build_ref(), "the reference tree is needed to regenerate the vectors"
+    out = {}
+    for name in cases.BRE:
+        c = cases.bre_case(name)
+        res, calls = fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)
+        out[f"bre_{name}_bits"], out[f"bre_{name}_calls"], out[f"bre_{name}_crc"] = cases.bits(res), calls, cases.input_crc(c)
+        print(f"bre {name:24s} functor calls {int(calls.sum()):7d}  non-zero outputs {np.count_nonzero(res):6d}")
+    for name in cases.VPM:
+        c = cases.vpm_case(name)
+        res, mvol = fb.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb)
+        out[f"vpm_{name}_bits"], out[f"vpm_{name}_mvol"], out[f"vpm_{name}_crc"] = cases.bits(res), mvol, cases.input_crc(c)
+        print(f"vpm {name:24s} photons found {int(mvol.sum()):7d}  non-zero outputs {np.count_nonzero(res):6d}")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
