@@ -40,6 +40,9 @@ def load():
         _lib.ref_fn_vpm_gather.restype = C.c_int
         _lib.ref_fn_vpm_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                            C.c_void_p, C.c_void_p, N.f32p, C.c_size_t, C.c_int, N.f32p, N.f32p]
+        _lib.ref_fn_beams_gather.restype = C.c_int
+        _lib.ref_fn_beams_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             N.f32p, C.c_size_t, C.c_float, N.f32p, N.f32p, N.u32p]
     return _lib
 
 
@@ -73,3 +76,32 @@ def vpm_gather(photons, rays, samples, medium, config, tri, nb_camera_samples):
     if rc != 0:
         raise RuntimeError(f"ref_fn_vpm_gather refused the input: {rc}")
     return out.reshape(rays.n, 27), mvol
+
+
+def beam_uniforms(beams, rays, medium, config):
+    """The two sampler draws per (ray, beam) pair as the C ABI derives them (oracle: Scene::beamUniform, dims 0 and 1)."""
+    from oracle import binding as ob
+    lib = ob.load()
+    cr = rays.as_c()
+    xi = np.zeros(rays.n * beams.n * 2, dtype=np.float32)
+    lib.gvpm_oracle_beam_uniforms.restype = None
+    lib.gvpm_oracle_beam_uniforms.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p]
+    lib.gvpm_oracle_beam_uniforms(C.byref(cr), rays.n, beams.n, C.byref(medium), C.byref(config), xi.ctypes.data_as(N.f32p))
+    return xi
+
+
+def beams_gather(beams, rays, medium, config, tri, radius):
+    """The reference's photon-beam functor (BeamGradRadianceQuery::operator(), shift_volume_beams.cpp:139-353) over every
+    (ray, beam) pair in beam order.  Returns (out [n_rays, 27], counts [n_rays, 2])."""
+    lib = load()
+    xi = beam_uniforms(beams, rays, medium, config)
+    cb, cr = beams.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    rc = lib.ref_fn_beams_gather(C.byref(cb), beams.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                                 tri.ctypes.data_as(N.f32p), tri.size // 9, radius, xi.ctypes.data_as(N.f32p),
+                                 out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_beams_gather refused the input: {rc}")
+    return out.reshape(rays.n, 27), counts.reshape(rays.n, 2)

@@ -195,3 +195,19 @@ extern "C" long long gvpm_oracle_subbeams(const gvpm_beam_soa *beams, size_t nBe
   }
   return (long long)subs.size();
 }
+
+// The two uniform numbers per (ray, beam) pair that the restated functor derives from its counter-based hash (dims 0, 1:
+// the point on the photon beam, the point on the camera segment).  Exported so that the reference functor harness
+// (ref_functor.cpp), whose BeamKernelRecord draws them from a Sampler, is fed the very same numbers.
+// xi: [nRays * nBeams * 2].
+extern "C" void gvpm_oracle_beam_uniforms(const gvpm_ray_soa *rays, size_t nRays, size_t nBeams, const gvpm_medium *med,
+                                          const gvpm_config *cfg, float *xi) {
+  Scene<float> sc(*med, *cfg, 1.f);
+  for (size_t i = 0; i < nRays; ++i) {
+    CamRay<float> ray = loadRay<float>(*rays, i);
+    for (size_t j = 0; j < nBeams; ++j) {
+      xi[2 * (i * nBeams + j)] = sc.beamUniform(ray, (uint32_t)j, 0);
+      xi[2 * (i * nBeams + j) + 1] = sc.beamUniform(ray, (uint32_t)j, 1);
+    }
+  }
+}

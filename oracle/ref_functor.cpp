@@ -71,7 +71,9 @@
 #include <mitsuba/render/sensor.h>
 #include <mitsuba/render/film.h>
 #include <mitsuba/bidir/path.h>
+#include <mitsuba/render/sampler.h>
 #include "gvpm/shift/shift_volume_photon.h"
+#include "gvpm/shift/shift_volume_beams.h"
 #undef private
 #undef protected
 
@@ -121,6 +123,11 @@ struct World {
 
   int build(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
             size_t n_tri, EVolumeTechnique technique) {
+    common(med, cfg, tri, n_tri, technique);
+    return photonPaths(ph, n_ph, med);
+  }
+
+  void common(const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri, EVolumeTechnique technique) {
     initOnce();
     phase = makePhase(med->phase_type, med->hg_g);
     medium = makeMedium(med->sigma_s, med->sigma_a, med->sampling_weight, phase.get());
@@ -157,7 +164,10 @@ struct World {
     config.pathSet = cfg->path_set != 0;
     config.powerHeuristic = cfg->power_heuristic != 0;
     VertexClassifier::roughnessThreshold = 0.05f;   // bounceRoughness default (gvpm_struct.h:236)
+  }
 
+  // one light Path + kd node per photon
+  int photonPaths(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med) {
     lps.resize(n_ph);
     nodes.resize(n_ph);
     const gvpm_medium *medp = med;
@@ -275,6 +285,135 @@ struct World {
   }
 };
 
+// The two sampler->next1D() draws of BeamKernelRecord::eval (shift_volume_beams.h:209-236: the point on the photon beam,
+// then the point on the camera segment) are inputs of the flattened form: the caller passes the two numbers per
+// (ray, beam) pair that the C ABI derives from its counter-based hash.
+class PresetSampler : public Sampler {
+public:
+  PresetSampler() : Sampler(Properties()) {}
+  void preset(Float a, Float b) { v[0] = a; v[1] = b; k = 0; }
+  Float next1D() override {
+    if (k >= 2) { std::fprintf(stderr, "gvpm functor ref harness: third sampler draw\n"); std::abort(); }
+    return v[k++];
+  }
+  Point2 next2D() override { Float a = next1D(); return Point2(a, next1D()); }
+  ref<Sampler> clone() override { return NULL; }
+private:
+  Float v[2] = {0, 0};
+  int k = 0;
+};
+
+// One light Path + LTPhotonBeam per flattened beam: the beam is edge i = depth from vertex(i) (origin = parent vertex of
+// the reconnection, shift_volume_beams.cpp:430-436) to vertex(i + 1).
+struct BeamWorld {
+  std::vector<LightPath> lps;
+  std::vector<LTPhotonBeam> beams;
+  ~BeamWorld() {
+    for (auto &L : lps) { L.path.m_vertices.clear(); L.path.m_edges.clear(); }
+  }
+  int build(World &W, const gvpm_beam_soa *bs, size_t n, const gvpm_medium *med, const gvpm_config *cfg, float radius) {
+    lps.resize(n);
+    beams.reserve(n);
+    for (size_t j = 0; j < n; ++j) {
+      LightPath &L = lps[j];
+      const size_t i = (size_t)bs->depth[j];
+      if (i < 1) return -2;
+      const int ptype = bs->parent_type[j];
+      if ((ptype == 0) != (i == 1)) return -3;   // vertex 1 is the emitter sample
+      L.v.resize(i + 2);
+      L.e.resize(i + 1);
+      for (auto &x : L.v) zero(x);
+      for (auto &x : L.e) zero(x);
+      // prefix: vertex(0).weight * rr * edge(0).weight * prod_{1 <= k <= i-1} (...) = prefix_flux (every other factor 1)
+      L.v[0].type = PathVertex::EEmitterSupernode;
+      L.v[0].weight[EImportance] = S3(bs->prefix_flux + 3 * j);
+      for (size_t k = 0; k <= i; ++k) { L.e[k].weight[EImportance] = Spectrum(1.f); L.e[k].medium = W.medium.get(); }
+      for (size_t k = 1; k <= i + 1; ++k) L.v[k].weight[EImportance] = Spectrum(1.f);
+      const Point origin = P3(bs->origin + 3 * j), end = P3(bs->end + 3 * j), pred = P3(bs->pred_pos + 3 * j);
+      const Normal nrm(V3f(bs->parent_n + 3 * j));
+      if (i >= 2) {   // vertex 1: the emitter sample; vertices 2 .. i-1: medium interactions at the predecessor's position
+        L.v[1].type = PathVertex::EEmitterSample;
+        PositionSamplingRecord &pr = L.v[1].getPositionSamplingRecord();
+        new (&pr) PositionSamplingRecord();
+        pr.p = pred;
+        pr.measure = EArea;
+        pr.object = W.em.get();
+      }
+      for (size_t k = 2; k + 1 <= i; ++k) {
+        L.v[k].type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = L.v[k].getMediumSamplingRecord();
+        new (&m) MediumSamplingRecord();
+        m.p = pred;
+        m.medium = W.medium.get();
+      }
+      // parent vertex (i) = the beam origin
+      PathVertex &v = L.v[i];
+      v.pdf[EImportance] = bs->parent_pdf[j];
+      v.rrWeight = bs->rr_weight[j];
+      if (ptype == 1) {
+        v.type = PathVertex::ESurfaceInteraction;
+        Intersection &its = v.getIntersection();
+        new (&its) Intersection();
+        its.p = origin;
+        its.geoFrame = Frame(nrm);
+        its.shFrame = its.geoFrame;
+        L.bsdfs.push_back(makeDiffuse(bs->parent_albedo + 3 * j));
+        L.shapes.push_back(new HarnessShape(L.bsdfs.back().get()));
+        its.shape = L.shapes.back().get();
+        its.wi = its.toLocal(normalize(pred - origin));
+        its.t = 1.f;
+      } else if (ptype == 2) {
+        v.type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = v.getMediumSamplingRecord();
+        new (&m) MediumSamplingRecord();
+        m.p = origin;
+        m.medium = W.medium.get();
+        m.sigmaS = S3(med->sigma_s);
+        m.sigmaA = S3(med->sigma_a);
+      } else if (ptype == 0) {
+        v.type = PathVertex::EEmitterSample;
+        PositionSamplingRecord &pr = v.getPositionSamplingRecord();
+        new (&pr) PositionSamplingRecord();
+        pr.p = origin;
+        pr.n = nrm;
+        pr.measure = EArea;
+        pr.object = W.em.get();
+      } else {
+        return -4;   // GVPM_PARENT_OTHER: manifold shift, out of scope
+      }
+      // end vertex (i + 1): on a surface (its geometric normal enters the base pdf, :506-507) or in the medium
+      PathVertex &ev = L.v[i + 1];
+      if (bs->end_on_surface[j]) {
+        ev.type = PathVertex::ESurfaceInteraction;
+        Intersection &its = ev.getIntersection();
+        new (&its) Intersection();
+        its.p = end;
+        its.geoFrame = Frame(Normal(V3f(bs->end_n + 3 * j)));
+        its.shFrame = its.geoFrame;
+        its.t = 1.f;
+      } else {
+        ev.type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = ev.getMediumSamplingRecord();
+        new (&m) MediumSamplingRecord();
+        m.p = end;
+        m.medium = W.medium.get();
+      }
+      for (size_t k = 0; k <= i + 1; ++k) {
+        L.path.append(&L.v[k]);
+        if (k <= i) L.path.append(&L.e[k]);
+      }
+      beams.emplace_back(&L.path, i, radius, (int)bs->path_id[j]);
+      LTPhotonBeam &b = beams.back();
+      b.flux = S3(bs->flux + 3 * j);            // the constructor's product is an input of the flattened form
+      b.longBeams = cfg->long_beams != 0;
+      // the edge that carries the beam: direction and length as PhotonBeam::setEndPoint derives them
+      L.e[i].d = b.getDir();
+      L.e[i].length = b.getLength();
+    }
+    return 0;
+  }
+};
+
 // One camera medium segment with its four offset segments as the functors see them: a GatherPoint with its camera Path
 // and cached vertex weights, four ShiftGatherPoints marked as generated.  Holds pointers into itself: built in place.
 struct CameraSide {
@@ -346,7 +485,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 2; }
+int ref_fn_version() { return 3; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -455,6 +594,45 @@ int ref_fn_vpm_gather(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa
     for (int k = 0; k < 4; ++k) {
       putS(o + 3 * (1 + k), pix[r].shifted[k]);
       putS(o + 3 * (5 + k), pix[r].weighted[k]);
+    }
+  }
+  return 0;
+}
+
+// G-Beams (beam3d = EBeamBeam3D_Optimized, or beam1d with newShiftBeam as gvpm.cpp:95-98 forces it): the functor
+// BeamGradRadianceQuery::operator() (shift_volume_beams.cpp:139-353) with shiftBeam / shiftBeamDiffuse / shiftNull3D /
+// getShiftPos / getShiftPos1D, BeamKernelRecord (shift_volume_beams.h:24-288) and diffuseReconnectionPhotonBeam, on every
+// (camera segment, beam) pair in beam order with tmin = 0, tmax = infinity (what SubBeamBVH::query selects up to the
+// sub-beam that owns tNear).  xi: [n_rays * n_beams * 2] the two sampler draws per pair.  counts: [n_rays * 2] =
+// functor calls that returned true, and 0.
+int ref_fn_beams_gather(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                        const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, const float *xi, float *out,
+                        uint32_t *counts) {
+  World W;
+  W.common(med, cfg, tri, n_tri, cfg->beam_kernel_1d ? EBeamBeam1D : EBeamBeam3D_Optimized);
+  W.config.newShiftBeam = cfg->beam_kernel_1d != 0;
+  BeamWorld B;
+  if (int rc = B.build(W, bs, n_beams, med, cfg, radius)) return rc;
+  ref<PresetSampler> sampler = new PresetSampler();
+  for (size_t r = 0; r < n_rays; ++r) {
+    for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
+    if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
+    const size_t e = (size_t)ry->edge_id[r];
+    if (e != 1) return -5;
+    CameraSide cam;
+    cam.build(ry, r, W.medium.get());
+    // gvpm.cpp:936: Ray ray(vertex(idEdge).position, d, Epsilon, distTotal - Epsilon, 0.f)
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    BeamGradRadianceQuery gRec(W.scene, &cam.gp, cam.shiftGPs, ray, W.medium.get(), W.config, *W.thdata, e, sampler.get());
+    for (size_t j = 0; j < n_beams; ++j) {
+      sampler->preset(xi[2 * (r * n_beams + j)], xi[2 * (r * n_beams + j) + 1]);
+      if (gRec(&B.beams[j]) && counts) ++counts[2 * r];
+    }
+    float *o = out + 27 * r;
+    putS(o, gRec.mediumFlux);
+    for (int k = 0; k < 4; ++k) {
+      putS(o + 3 * (1 + k), gRec.shiftedMediumFlux[k]);
+      putS(o + 3 * (5 + k), gRec.weightedMediumFlux[k]);
     }
   }
   return 0;

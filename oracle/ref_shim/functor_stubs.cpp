@@ -6,7 +6,8 @@
 //     (include/mitsuba/core/triangle.h:109-145) over the harness' triangle list and the ray's [mint, maxt]; the kd-tree
 //     around it (src/librender/skdtree.cpp) needs the whole renderer.
 //   * the offset-path tracer of ShiftGatherPoint::generate (PathEdge::sampleNext, Path::initialize / release): the harness hands the functor gather points that are marked as generated.
-//   * the manifold shift (SpecularManifold::det, generateShiftPathME, ShiftME): out of scope (useManifold = false,
+//   * the manifold shift (SpecularManifold::det, generateShiftPathME, ShiftME, and the source-path cache of the beam
+//     functor: Path::append(Path), PathEdge::clone): out of scope (useManifold = false,
 //     SURVEY.md §2); parents that would need it are refused by the harness.
 // Nothing here evaluates a radiometric quantity.
 #include <array>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include <mitsuba/mitsuba.h>
+#include <mitsuba/core/stream.h>
 #include <mitsuba/core/triangle.h>
 #include <mitsuba/render/skdtree.h>
 #include <mitsuba/bidir/path.h>
@@ -41,11 +43,17 @@ bool ShapeKDTree::rayIntersect(const Ray &ray) const {
 
 Float VertexClassifier::roughnessThreshold = 0.05f;
 
+// Sampler's serialization (src/librender/sampler.cpp is linked for the base class of the harness' preset sampler)
+void Stream::writeULong(uint64_t) { fn_unreachable("Stream::writeULong"); }
+uint64_t Stream::readULong() { fn_unreachable("Stream::readULong"); return 0; }
+
 bool PathEdge::sampleNext(const Scene *, Sampler *, const PathVertex *, const Ray &, PathVertex *, ETransportMode, bool, bool) {
   fn_unreachable("PathEdge::sampleNext"); return false;
 }
 void Path::initialize(const Scene *, Float, ETransportMode, MemoryPool &) { fn_unreachable("Path::initialize"); }
 void Path::release(MemoryPool &) { fn_unreachable("Path::release"); }
+void Path::append(const Path &, size_t, size_t, bool) { fn_unreachable("Path::append(Path)"); }
+PathEdge *PathEdge::clone(MemoryPool &) const { fn_unreachable("PathEdge::clone"); return NULL; }
 Float SpecularManifold::det(const Path &, int, int) { fn_unreachable("SpecularManifold::det"); return 0; }
 bool generateShiftPathME(const Path &, Path &, size_t, size_t, MemoryPool &, ManifoldPerturbation *, const PathVertex &, Float,
                          Point, Point) { fn_unreachable("generateShiftPathME"); return false; }

@@ -80,6 +80,26 @@ VPM = {
 }
 VPM_SAMPLES = 8
 
+BEAMS = {
+    "default": (dict(), None),                                  # beam3d (EBeamBeam3D_Optimized)
+    "hg_forward_0.7": (dict(phase="hg", hg_g=0.7), None),
+    "no_mis": (dict(use_mis=False), None),
+    "no_shift_null": (dict(use_shift_null=False), None),
+    "no_path_set": (dict(path_set=False), None),
+    "power_heuristic": (dict(power_heuristic=True), None),
+    "long_beams": (dict(long_beams=True), None),
+    "max_depth_4": (dict(max_depth=4), None),
+    "surf2media": (dict(lighting_mode=N.SURF2MEDIA), None),
+    "media2media": (dict(lighting_mode=N.MEDIA2MEDIA), None),
+    "blocker": (dict(), _blocker),
+    "invalid_offsets": (dict(), _invalid_offsets),
+    "narrow": (dict(scale=1.5, n_beams=4000), None),
+    "beam1d": (dict(beam_kernel_1d=True), None),                # EBeamBeam1D with newShiftBeam (gvpm.cpp:95-98)
+    "beam1d_hg_backward": (dict(beam_kernel_1d=True, phase="hg", hg_g=-0.3), None),
+    "beam1d_no_mis_long": (dict(beam_kernel_1d=True, use_mis=False, long_beams=True), None),
+    "beam1d_blocker": (dict(beam_kernel_1d=True), _blocker),
+}
+
 
 def bre_case(name):
     kw, post = BRE[name]
@@ -107,12 +127,28 @@ def vpm_case(name):
     return c
 
 
+def beams_case(name):
+    from gvpm_b200 import records as R
+    kw, post = BEAMS[name]
+    kw = dict(dict(n_beams=1500, w=16, h=12, scale=4.0, rng_seed=99), **kw)
+    n_beams = kw.pop("n_beams")
+    c = H.make_case(n_photons=64, **kw)
+    c.beams, c.n_beam_paths = R.synth_beams(n_beams, c.medium, seed=5, threads=4)
+    c.rays.edge_id[:] = 1
+    if post:
+        post(c)
+    return c
+
+
 def input_crc(c):
     """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
     h = 0
     for a in (c.photons.pos, c.photons.flux, c.photons.parent_pos, c.photons.parent_type, c.rays.o, c.rays.d,
               c.rays.off_o, c.rays.off_d, c.rays.off_valid, c.rays.xi, c.rays.eye_contrib, c.rays.off_sensor, c.tri):
         h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    if hasattr(c, "beams"):
+        for a in (c.beams.origin, c.beams.end, c.beams.flux, c.beams.parent_type, c.beams.parent_pdf, c.beams.path_id):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
     if hasattr(c, "samples"):
         for a in (c.samples.ray, c.samples.t, c.samples.radius, c.samples.pdf_success):
             h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)

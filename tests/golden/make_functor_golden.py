@@ -1,5 +1,6 @@
 """Regenerates tests/golden/functor_pins.npz from the REFERENCE'S OWN shift functors (oracle/_ref/libgvpm_functor_ref.so:
-VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp, compiled from
+VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp,
+BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, compiled from
 /root/reference by `make -C oracle functor_ref` and driven by oracle/ref_functor.cpp).  Run in the container that holds the
 reference tree:
     python tests/golden/make_functor_golden.py
@@ -31,6 +32,12 @@ if __name__ == "__main__":
         res, mvol = fb.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb)
         out[f"vpm_{name}_bits"], out[f"vpm_{name}_mvol"], out[f"vpm_{name}_crc"] = cases.bits(res), mvol, cases.input_crc(c)
         print(f"vpm {name:24s} photons found {int(mvol.sum()):7d}  non-zero outputs {np.count_nonzero(res):6d}")
+    for name in cases.BEAMS:
+        c = cases.beams_case(name)
+        res, counts = fb.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius)
+        out[f"beams_{name}_bits"], out[f"beams_{name}_contrib"] = cases.bits(res), counts[:, 0]
+        out[f"beams_{name}_crc"] = cases.input_crc(c)
+        print(f"beams {name:22s} contributing pairs {int(counts[:, 0].sum()):6d}  non-zero outputs {np.count_nonzero(res):6d}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -49,6 +49,10 @@ def test_golden_is_not_trivial(golden):
     for a, b in (("default", "no_mis"), ("wide", "wide_no_shift_null"), ("default", "power_heuristic"),
                  ("default", "invalid_offsets"), ("default", "max_depth_4"), ("default", "blocker")):
         assert not np.array_equal(golden[f"vpm_{a}_bits"], golden[f"vpm_{b}_bits"]), (a, b)
+    for a, b in (("default", "no_mis"), ("default", "no_shift_null"), ("default", "no_path_set"), ("default", "blocker"),
+                 ("default", "power_heuristic"), ("default", "long_beams"), ("default", "beam1d"), ("default", "max_depth_4"),
+                 ("default", "invalid_offsets"), ("beam1d", "beam1d_blocker"), ("surf2media", "media2media")):
+        assert not np.array_equal(golden[f"beams_{a}_bits"], golden[f"beams_{b}_bits"]), (a, b)
     # the right and top image borders force weight 1 (no reverse shift): weighted base == primal there, < primal inside
     c = cases.bre_case("default")
     right = c.rays.px == c.w - 1
@@ -88,6 +92,18 @@ def test_vpm_functor_equals_reference_golden(built, golden, name):
     _same_rows(cases.bits(res.out), golden[f"vpm_{name}_bits"], f"G-VPM functor, case {name}")
 
 
+@pytest.mark.parametrize("name", list(cases.BEAMS))
+def test_beam_functor_equals_reference_golden(built, golden, name):
+    """BeamGradRadianceQuery::operator() (shift_volume_beams.cpp:139-353) with BeamKernelRecord, shiftNull3D,
+    getShiftPos / getShiftPos1D, shiftBeamDiffuse and diffuseReconnectionPhotonBeam; beam3d and beam1d kernels.  The two
+    sampler draws of the kernel record are fed to the reference as the C ABI derives them."""
+    c = cases.beams_case(name)
+    assert cases.input_crc(c) == golden[f"beams_{name}_crc"], "the seeded inputs changed: regenerate the golden vectors"
+    res = ob.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
+    np.testing.assert_array_equal(res.counts[:, 1], golden[f"beams_{name}_contrib"])   # calls that returned true
+    _same_rows(cases.bits(res.out), golden[f"beams_{name}_bits"], f"G-Beams functor, case {name}")
+
+
 @pytest.mark.skipif(not (fb.have_ref() or os.path.isdir(fb.REFERENCE_ROOT)), reason="reference tree / prebuilt library absent")
 def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
     """Live: the reference functors, compiled here, reproduce the committed vectors (the fixtures are not stale)."""
@@ -103,6 +119,11 @@ def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
         out, mvol = fb.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb)
         np.testing.assert_array_equal(cases.bits(out), golden[f"vpm_{name}_bits"])
         np.testing.assert_array_equal(mvol, golden[f"vpm_{name}_mvol"])
+    for name in ("default", "beam1d", "blocker", "long_beams"):
+        c = cases.beams_case(name)
+        out, counts = fb.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius)
+        np.testing.assert_array_equal(cases.bits(out), golden[f"beams_{name}_bits"])
+        np.testing.assert_array_equal(counts[:, 0], golden[f"beams_{name}_contrib"])
 
 
 def test_harness_refuses_what_it_cannot_rebuild(built):
