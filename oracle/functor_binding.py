@@ -43,6 +43,9 @@ def load():
         _lib.ref_fn_beams_gather.restype = C.c_int
         _lib.ref_fn_beams_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                              N.f32p, C.c_size_t, C.c_float, N.f32p, N.f32p, N.u32p]
+        _lib.ref_fn_planes_gather.restype = C.c_int
+        _lib.ref_fn_planes_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                              N.f32p, N.u32p]
     return _lib
 
 
@@ -104,4 +107,18 @@ def beams_gather(beams, rays, medium, config, tri, radius):
                                  out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p))
     if rc != 0:
         raise RuntimeError(f"ref_fn_beams_gather refused the input: {rc}")
+    return out.reshape(rays.n, 27), counts.reshape(rays.n, 2)
+
+
+def planes_gather(planes, rays, medium, config):
+    """The reference's photon-plane functor (PlaneGradRadianceQuery::operator(), shift_volume_planes.h:56-101) over every
+    (ray, plane) pair in plane order.  Returns (out [n_rays, 27], counts [n_rays, 2])."""
+    lib = load()
+    cp, cr = planes.as_c(), rays.as_c()
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    rc = lib.ref_fn_planes_gather(C.byref(cp), planes.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                                  out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_planes_gather refused the input: {rc}")
     return out.reshape(rays.n, 27), counts.reshape(rays.n, 2)

@@ -74,6 +74,8 @@
 #include <mitsuba/render/sampler.h>
 #include "gvpm/shift/shift_volume_photon.h"
 #include "gvpm/shift/shift_volume_beams.h"
+#include "gvpm/gvpm_plane.h"
+#include "gvpm/shift/shift_volume_planes.h"
 #undef private
 #undef protected
 
@@ -485,7 +487,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 3; }
+int ref_fn_version() { return 4; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -627,6 +629,54 @@ int ref_fn_beams_gather(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_
     for (size_t j = 0; j < n_beams; ++j) {
       sampler->preset(xi[2 * (r * n_beams + j)], xi[2 * (r * n_beams + j) + 1]);
       if (gRec(&B.beams[j]) && counts) ++counts[2 * r];
+    }
+    float *o = out + 27 * r;
+    putS(o, gRec.mediumFlux);
+    for (int k = 0; k < 4; ++k) {
+      putS(o + 3 * (1 + k), gRec.shiftedMediumFlux[k]);
+      putS(o + 3 * (5 + k), gRec.weightedMediumFlux[k]);
+    }
+  }
+  return 0;
+}
+
+// G-Planes 0D: the functor PlaneGradRadianceQuery::operator() (shift_volume_planes.h:56-101) with specularShift
+// (:263-416) and its re-intersection (:427-453), PhotonPlane::intersectPlane0D / getContrib0D / invJacobian
+// (photonmapper/plane_struct.h), on every (camera segment, plane) pair in plane order.  The functor reads no light-path
+// data (its shift keeps origin and w0), so the LTPhotonPlane is filled from the flattened record directly.
+// counts: [n_rays * 2] = planes the base ray intersects (mediumFlux += ...), and 0.
+int ref_fn_planes_gather(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_ray_soa *ry, size_t n_rays,
+                         const gvpm_medium *med, const gvpm_config *cfg, float *out, uint32_t *counts) {
+  World W;
+  W.common(med, cfg, NULL, 0, EVolPlane0D);
+  std::vector<LTPhotonPlane> planes(n_planes);
+  for (size_t j = 0; j < n_planes; ++j) {
+    LTPhotonPlane &p = planes[j];
+    p._ori = P3(ps->origin + 3 * j);
+    p._w0 = V3f(ps->w0 + 3 * j);
+    p._length0 = ps->length0[j];
+    p._w1 = V3f(ps->w1 + 3 * j);
+    p._length1 = ps->length1[j];
+    p.medium = W.medium.get();
+    p._flux = S3(ps->flux + 3 * j);
+    p.depth = p.edgeID = ps->edge_id[j];
+    p.path = NULL;
+    p.pathID = 0;
+  }
+  for (size_t r = 0; r < n_rays; ++r) {
+    for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
+    if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
+    const size_t e = (size_t)ry->edge_id[r];
+    if (e != 1) return -5;
+    CameraSide cam;
+    cam.build(ry, r, W.medium.get());
+    // gvpm.cpp:837: Ray ray(vertex(idEdge).position, d, Epsilon, distTotal - Epsilon, 0.f)
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    PlaneGradRadianceQuery gRec(W.scene, &cam.gp, cam.shiftGPs, ray, W.medium.get(), W.config, *W.thdata, (int)e);
+    for (size_t j = 0; j < n_planes; ++j) {
+      PhotonPlane::IntersectionRecord probe;
+      if (counts && planes[j].intersectPlane0D(ray, probe)) ++counts[2 * r];
+      gRec(&planes[j]);
     }
     float *o = out + 27 * r;
     putS(o, gRec.mediumFlux);

@@ -127,6 +127,29 @@ def vpm_case(name):
     return c
 
 
+PLANES = {
+    "default": (dict(), None),                                  # sensor inside the medium (gvpm.cpp:785-787)
+    "hg_forward_0.3": (dict(phase="hg", hg_g=0.3), None),
+    "hg_forward_0.7": (dict(phase="hg", hg_g=0.7), None),       # the reference itself yields NaN for some pairs here
+    "hg_backward_0.5": (dict(phase="hg", hg_g=-0.5), None),
+    "no_mis": (dict(use_mis=False), None),
+    "sensor_outside": (dict(inside=False), None),
+    "collimated_sheet": (dict(sheet=True), None),
+    "invalid_offsets": (dict(), _invalid_offsets),
+    "many": (dict(n_planes=4000, w=24, h=16, seed=11), None),
+}
+
+
+def planes_case(name):
+    kw, post = PLANES[name]
+    kw = dict(dict(n_planes=1200, w=16, h=12), **kw)
+    c = H.make_plane_case(**kw)
+    c.rays.edge_id[:] = 1
+    if post:
+        post(c)
+    return c
+
+
 def beams_case(name):
     from gvpm_b200 import records as R
     kw, post = BEAMS[name]
@@ -143,9 +166,16 @@ def beams_case(name):
 def input_crc(c):
     """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
     h = 0
-    for a in (c.photons.pos, c.photons.flux, c.photons.parent_pos, c.photons.parent_type, c.rays.o, c.rays.d,
-              c.rays.off_o, c.rays.off_d, c.rays.off_valid, c.rays.xi, c.rays.eye_contrib, c.rays.off_sensor, c.tri):
+    for a in (c.rays.o, c.rays.d, c.rays.off_o, c.rays.off_d, c.rays.off_valid, c.rays.xi, c.rays.eye_contrib,
+              c.rays.off_sensor):
         h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    if hasattr(c, "photons"):
+        for a in (c.photons.pos, c.photons.flux, c.photons.parent_pos, c.photons.parent_type, c.tri):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    if hasattr(c, "planes"):
+        for a in (c.planes.origin, c.planes.w0, c.planes.w1, c.planes.length0, c.planes.length1, c.planes.flux,
+                  c.planes.edge_id):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
     if hasattr(c, "beams"):
         for a in (c.beams.origin, c.beams.end, c.beams.flux, c.beams.parent_type, c.beams.parent_pdf, c.beams.path_id):
             h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)

@@ -1,6 +1,7 @@
 """Regenerates tests/golden/functor_pins.npz from the REFERENCE'S OWN shift functors (oracle/_ref/libgvpm_functor_ref.so:
 VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp,
-BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, compiled from
+BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, PlaneGradRadianceQuery::operator(), shift_volume_planes.h,
+compiled from
 /root/reference by `make -C oracle functor_ref` and driven by oracle/ref_functor.cpp).  Run in the container that holds the
 reference tree:
     python tests/golden/make_functor_golden.py
@@ -38,6 +39,13 @@ if __name__ == "__main__":
         out[f"beams_{name}_bits"], out[f"beams_{name}_contrib"] = cases.bits(res), counts[:, 0]
         out[f"beams_{name}_crc"] = cases.input_crc(c)
         print(f"beams {name:22s} contributing pairs {int(counts[:, 0].sum()):6d}  non-zero outputs {np.count_nonzero(res):6d}")
+    for name in cases.PLANES:
+        c = cases.planes_case(name)
+        res, counts = fb.planes_gather(c.planes, c.rays, c.medium, c.config)
+        out[f"planes_{name}_bits"], out[f"planes_{name}_hits"] = cases.bits(res), counts[:, 0]
+        out[f"planes_{name}_crc"] = cases.input_crc(c)
+        print(f"planes {name:21s} intersected pairs {int(counts[:, 0].sum()):7d}  non-zero outputs {np.count_nonzero(res):6d}"
+              f"  NaN {int(np.isnan(res).sum())}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -1,6 +1,7 @@
-"""Pins the CONTROL FLOW of the oracle's shift functors against the REFERENCE'S OWN compiled functors (rows a5-a9 and a11 of
-SURVEY.md §8): VolumeGradientBREQuery::operator() (gvpm/shift/shift_volume_photon.cpp:658-856) and
-VolumeGradientPositionQuery::operator() (:489-655) with everything they call - the depth / lighting-mode / path-set
+"""Pins the CONTROL FLOW of the oracle's shift functors against the REFERENCE'S OWN compiled functors (rows a5-a9, a11,
+a13-a16 of SURVEY.md §8): VolumeGradientBREQuery::operator() (gvpm/shift/shift_volume_photon.cpp:658-856),
+VolumeGradientPositionQuery::operator() (:489-655), BeamGradRadianceQuery::operator() (shift_volume_beams.cpp:139-353) and
+PlaneGradRadianceQuery::operator() (shift_volume_planes.h:56-101) with everything they call - the depth / lighting-mode / path-set
 filters, the 3-D kernel's random chord position, shiftNull (:119-158), getTypeShift + VertexClassifier, shiftPhotonDiffuse
 (:382-486) with its shadow ray and side test, getShiftPos (:858-896), the border rule, the MIS weights (balance and power
 heuristic) and the accumulation.
@@ -28,7 +29,8 @@ def golden():
 
 def _same_rows(got, want, what, rows=None):
     assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
-    eq = (got == want).all(axis=1)
+    both_nan = np.isnan(got.view(np.float32)) & np.isnan(want.view(np.float32))   # the reference's own NaNs (planes, HG)
+    eq = ((got == want) | both_nan).all(axis=1)
     if rows is not None:
         eq = eq | ~rows
     bad = np.flatnonzero(~eq)
@@ -53,6 +55,10 @@ def test_golden_is_not_trivial(golden):
                  ("default", "power_heuristic"), ("default", "long_beams"), ("default", "beam1d"), ("default", "max_depth_4"),
                  ("default", "invalid_offsets"), ("beam1d", "beam1d_blocker"), ("surf2media", "media2media")):
         assert not np.array_equal(golden[f"beams_{a}_bits"], golden[f"beams_{b}_bits"]), (a, b)
+    for a, b in (("default", "no_mis"), ("default", "invalid_offsets"), ("default", "hg_forward_0.3"),
+                 ("default", "collimated_sheet"), ("default", "sensor_outside")):
+        assert not np.array_equal(golden[f"planes_{a}_bits"], golden[f"planes_{b}_bits"]), (a, b)
+    assert not np.isnan(f("planes_default_bits")).any() and not np.isnan(f("planes_hg_forward_0.3_bits")).any()
     # the right and top image borders force weight 1 (no reverse shift): weighted base == primal there, < primal inside
     c = cases.bre_case("default")
     right = c.rays.px == c.w - 1
@@ -104,6 +110,17 @@ def test_beam_functor_equals_reference_golden(built, golden, name):
     _same_rows(cases.bits(res.out), golden[f"beams_{name}_bits"], f"G-Beams functor, case {name}")
 
 
+@pytest.mark.parametrize("name", list(cases.PLANES))
+def test_plane_functor_equals_reference_golden(built, golden, name):
+    """PlaneGradRadianceQuery::operator() (shift_volume_planes.h:56-101) with specularShift (:263-416), its
+    re-intersection (:427-453) and PhotonPlane::intersectPlane0D / getContrib0D / invJacobian."""
+    c = cases.planes_case(name)
+    assert cases.input_crc(c) == golden[f"planes_{name}_crc"], "the seeded inputs changed: regenerate the golden vectors"
+    res = ob.planes_gather(c.planes, c.rays, c.medium, c.config, mode="brute", threads=2)
+    np.testing.assert_array_equal(res.counts[:, 0], golden[f"planes_{name}_hits"])     # planes the base ray intersects
+    _same_rows(cases.bits(res.out), golden[f"planes_{name}_bits"], f"G-Planes functor, case {name}")
+
+
 @pytest.mark.skipif(not (fb.have_ref() or os.path.isdir(fb.REFERENCE_ROOT)), reason="reference tree / prebuilt library absent")
 def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
     """Live: the reference functors, compiled here, reproduce the committed vectors (the fixtures are not stale)."""
@@ -124,6 +141,11 @@ def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
         out, counts = fb.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius)
         np.testing.assert_array_equal(cases.bits(out), golden[f"beams_{name}_bits"])
         np.testing.assert_array_equal(counts[:, 0], golden[f"beams_{name}_contrib"])
+    for name in ("default", "hg_forward_0.3", "sensor_outside"):
+        c = cases.planes_case(name)
+        out, counts = fb.planes_gather(c.planes, c.rays, c.medium, c.config)
+        np.testing.assert_array_equal(cases.bits(out), golden[f"planes_{name}_bits"])
+        np.testing.assert_array_equal(counts[:, 0], golden[f"planes_{name}_hits"])
 
 
 def test_harness_refuses_what_it_cannot_rebuild(built):
