@@ -46,6 +46,9 @@ def load():
         _lib.ref_fn_planes_gather.restype = C.c_int
         _lib.ref_fn_planes_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                               N.f32p, N.u32p]
+        _lib.ref_fn_sppm_beams_gather.restype = C.c_int
+        _lib.ref_fn_sppm_beams_gather.argtypes = [C.c_void_p, C.c_size_t, N.u32p, N.f32p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p, C.c_void_p, C.c_float, C.c_int, N.f32p, N.f32p, N.u32p]
     return _lib
 
 
@@ -122,3 +125,39 @@ def planes_gather(planes, rays, medium, config):
     if rc != 0:
         raise RuntimeError(f"ref_fn_planes_gather refused the input: {rc}")
     return out.reshape(rays.n, 27), counts.reshape(rays.n, 2)
+
+
+def sppm_beams_gather(beams, rays, medium, config, radius, technique):
+    """sppm's primal beam functor (BeamRadianceQuery<PhotonBeam>::operator(), photonmapper/beams.h:29-223) over every
+    (camera beam, sub-beam) pair of the reference's sub-beam split, in table order.  technique: key of
+    oracle.binding.BEAM_TECHNIQUES.  Returns (Li [n_rays, 3] WITHOUT the camera beam's weight, counts [n_rays, 2])."""
+    from oracle import binding as ob
+    lib, olib = load(), ob.load()
+    tech = ob.BEAM_TECHNIQUES[technique]
+    t12, bi = ob.subbeams(beams)
+    n_sub = len(bi)
+    # ordinal of each sub-beam within its beam (the table is in beam order)
+    first = np.r_[True, bi[1:] != bi[:-1]]
+    start = np.maximum.accumulate(np.where(first, np.arange(n_sub), 0))
+    k = (np.arange(n_sub) - start).astype(np.uint32)
+    naive = technique == "beam3d_naive"
+    dim0 = (2 + 2 * k if naive else np.zeros(n_sub)).astype(np.uint32)
+    dim1 = (3 + 2 * k if naive else np.ones(n_sub)).astype(np.uint32)
+    cb, cr = beams.as_c(), rays.as_c()
+    xi = np.zeros(rays.n * n_sub * 2, dtype=np.float32)
+    olib.gvpm_oracle_beam_uniform_dims.restype = None
+    olib.gvpm_oracle_beam_uniform_dims.argtypes = [C.c_void_p, C.c_size_t, N.u32p, N.u32p, N.u32p, C.c_size_t, C.c_void_p,
+                                                   C.c_void_p, N.f32p]
+    bi = np.ascontiguousarray(bi, dtype=np.uint32)
+    olib.gvpm_oracle_beam_uniform_dims(C.byref(cr), rays.n, bi.ctypes.data_as(N.u32p), dim0.ctypes.data_as(N.u32p),
+                                       dim1.ctypes.data_as(N.u32p), n_sub, C.byref(medium), C.byref(config),
+                                       xi.ctypes.data_as(N.f32p))
+    t12 = np.ascontiguousarray(t12, dtype=np.float32)
+    out = np.zeros(rays.n * 3, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    rc = lib.ref_fn_sppm_beams_gather(C.byref(cb), beams.n, bi.ctypes.data_as(N.u32p), t12.ctypes.data_as(N.f32p), n_sub,
+                                      C.byref(cr), rays.n, C.byref(medium), C.byref(config), radius, tech,
+                                      xi.ctypes.data_as(N.f32p), out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_sppm_beams_gather refused the input: {rc}")
+    return out.reshape(rays.n, 3), counts.reshape(rays.n, 2)

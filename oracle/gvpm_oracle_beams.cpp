@@ -211,3 +211,18 @@ extern "C" void gvpm_oracle_beam_uniforms(const gvpm_ray_soa *rays, size_t nRays
     }
   }
 }
+
+// Same, for arbitrary hash dimensions: entry k of the table is (beam index, dim0, dim1); xi: [nRays * n * 2].  The sppm
+// techniques draw dims (0, 1) per (ray, beam), the naive one dims (2 + 2k, 3 + 2k) for the beam's k-th sub-beam.
+extern "C" void gvpm_oracle_beam_uniform_dims(const gvpm_ray_soa *rays, size_t nRays, const uint32_t *beam,
+                                              const uint32_t *dim0, const uint32_t *dim1, size_t n, const gvpm_medium *med,
+                                              const gvpm_config *cfg, float *xi) {
+  Scene<float> sc(*med, *cfg, 1.f);
+  for (size_t i = 0; i < nRays; ++i) {
+    CamRay<float> ray = loadRay<float>(*rays, i);
+    for (size_t k = 0; k < n; ++k) {
+      xi[2 * (i * n + k)] = sc.beamUniform(ray, beam[k], dim0[k]);
+      xi[2 * (i * n + k) + 1] = sc.beamUniform(ray, beam[k], dim1[k]);
+    }
+  }
+}

@@ -487,7 +487,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 4; }
+int ref_fn_version() { return 5; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -684,6 +684,44 @@ int ref_fn_planes_gather(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_r
       putS(o + 3 * (1 + k), gRec.shiftedMediumFlux[k]);
       putS(o + 3 * (5 + k), gRec.weightedMediumFlux[k]);
     }
+  }
+  return 0;
+}
+
+// sppm primal photon beams: BeamRadianceQuery<PhotonBeam>::operator() (photonmapper/beams.h:29-223), all four techniques of
+// EVolumeTechnique (1D, 3D naive, 3D EGSR, 3D optimized), driven as volumePhotonBeamPass does (sppm.cpp:846-857) with one
+// call per (camera beam, sub-beam [t1, t2]) in the order of the caller's sub-beam table (the SubBeamBVH constructor's
+// split, beams_accel.h:98-124).  technique: 0 = 1D, 1 = naive, 2 = EGSR, 3 = optimized.  xi: [n_rays * n_sub * 2] sampler
+// draws per pair.  out: [n_rays * 3] = bRadQuery.Li (the caller multiplies by beam.weight, sppm.cpp:857);
+// counts: [n_rays * 2] = calls that returned true, and 0.
+int ref_fn_sppm_beams_gather(const gvpm_beam_soa *bs, size_t n_beams, const uint32_t *sub_beam, const float *sub_t12,
+                             size_t n_sub, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                             const gvpm_config *cfg, float radius, int technique, const float *xi, float *out,
+                             uint32_t *counts) {
+  static const EVolumeTechnique kTech[4] = {EBeamBeam1D, EBeamBeam3D_Naive, EBeamBeam3D_EGSR, EBeamBeam3D_Optimized};
+  if (technique < 0 || technique > 3) return -1;
+  World W;
+  W.common(med, cfg, NULL, 0, kTech[technique]);
+  std::vector<PhotonBeam> beams;
+  beams.reserve(n_beams);
+  for (size_t j = 0; j < n_beams; ++j) {
+    beams.emplace_back(P3(bs->origin + 3 * j), W.medium.get(), S3(bs->flux + 3 * j), (int)bs->depth[j], radius);
+    beams.back().setEndPoint(P3(bs->end + 3 * j));
+    beams.back().longBeams = cfg->long_beams != 0;
+  }
+  ref<PresetSampler> sampler = new PresetSampler();
+  for (size_t r = 0; r < n_rays; ++r) {
+    if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
+    const int depth = ry->edge_id[r];   // the camera beam's depth
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    BeamRadianceQuery<PhotonBeam> q(ray, W.medium.get(), cfg->max_depth == -1 ? -1 : cfg->max_depth - depth,
+                                    std::max(0, cfg->min_depth - depth), sampler.get(), kTech[technique]);
+    for (size_t s = 0; s < n_sub; ++s) {
+      if (sub_beam[s] >= n_beams) return -6;
+      sampler->preset(xi[2 * (r * n_sub + s)], xi[2 * (r * n_sub + s) + 1]);
+      if (q(&beams[sub_beam[s]], sub_t12[2 * s], sub_t12[2 * s + 1]) && counts) ++counts[2 * r];
+    }
+    putS(out + 3 * r, q.Li);
   }
   return 0;
 }

@@ -150,6 +150,26 @@ def planes_case(name):
     return c
 
 
+SPPM_BEAM_TECHNIQUES = ("beam1d", "beam3d_naive", "beam3d_egsr", "beam3d")
+SPPM_BEAMS = {
+    "default": dict(),
+    "hg_forward_long_beams": dict(phase="hg", hg_g=0.6, long_beams=True),
+    "depth_window": dict(max_depth=5, min_depth=3),
+}
+
+
+def sppm_beams_case(name, unit_weight=True):
+    """sppm primal beams (camera beams at depth 2: edge_id is used as sppm.cpp:853-854 uses beam.depth).  With
+    unit_weight the camera beam's weight is 1, so that Li * weight (sppm.cpp:857) is Li bit for bit."""
+    from gvpm_b200 import records as R
+    kw = dict(dict(w=16, h=12, scale=4.0, rng_seed=99, sppm_primal=True), **SPPM_BEAMS[name])
+    c = H.make_case(n_photons=64, **kw)
+    c.beams, c.n_beam_paths = R.synth_beams(800, c.medium, seed=5, threads=4)
+    if unit_weight:
+        c.rays.eye_contrib[:] = 1.0
+    return c
+
+
 def beams_case(name):
     from gvpm_b200 import records as R
     kw, post = BEAMS[name]

@@ -1,6 +1,6 @@
 """Regenerates tests/golden/functor_pins.npz from the REFERENCE'S OWN shift functors (oracle/_ref/libgvpm_functor_ref.so:
 VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp,
-BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, PlaneGradRadianceQuery::operator(), shift_volume_planes.h,
+BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, PlaneGradRadianceQuery::operator(), shift_volume_planes.h, sppm's BeamRadianceQuery::operator(), beams.h,
 compiled from
 /root/reference by `make -C oracle functor_ref` and driven by oracle/ref_functor.cpp).  Run in the container that holds the
 reference tree:
@@ -46,6 +46,13 @@ if __name__ == "__main__":
         out[f"planes_{name}_crc"] = cases.input_crc(c)
         print(f"planes {name:21s} intersected pairs {int(counts[:, 0].sum()):7d}  non-zero outputs {np.count_nonzero(res):6d}"
               f"  NaN {int(np.isnan(res).sum())}")
+    for name in cases.SPPM_BEAMS:
+        c = cases.sppm_beams_case(name)
+        for tech in cases.SPPM_BEAM_TECHNIQUES:
+            res, counts = fb.sppm_beams_gather(c.beams, c.rays, c.medium, c.config, c.radius, tech)
+            out[f"sppmbeams_{name}_{tech}_bits"], out[f"sppmbeams_{name}_{tech}_true"] = cases.bits(res), counts[:, 0]
+            print(f"sppm beams {name:22s} {tech:13s} accepted pairs {int(counts[:, 0].sum()):6d}  non-zero {np.count_nonzero(res):5d}")
+        out[f"sppmbeams_{name}_crc"] = cases.input_crc(c)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
