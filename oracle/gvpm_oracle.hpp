@@ -5,17 +5,25 @@
 // cpu_baseline / --impl reference legs of bench.py as the checker and the timed CPU baseline.
 // The product path (gvpm_b200/csrc) never includes, links or calls anything in oracle/.
 //
-// PARITY PARTLY PINNED: the reference ships no test, golden vector or fixture for this path (SURVEY.md §4,
-// §8c) and Mitsuba as a whole cannot be built in this image (Boost, Eigen, Xerces, OpenEXR ... are absent,
-// DESIGN.md §5).  What CAN be compiled from the reference tree is: PointKDTree build + range query, the AABB
-// slab test, GPhotonMap + GradientBeamRadianceEstimator (hierarchy + traversal + neighbour predicate),
-// SubBeamBVH, PhotonPlaneBVH, cylinderIntersection, intersectPlane0D, rayIntersectInternal1D,
-// Triangle::rayIntersect, coordinateSystem(Coherent), solveQuadraticDouble (oracle/ref_harness.cpp ->
-// oracle/_ref/libgvpm_ref.so).  Those parts of this file are pinned BIT-EXACTLY against that code and against
-// golden vectors generated from it (tests/test_oracle_ref_pin.py, tests/golden/ref_pins.npz): everything that
-// decides a neighbour index set.  The shift functors (gvpm/shift/*.cpp: contributions, Jacobians, MIS
-// weights) need libmitsuba-render / libbidir objects and stay restated-only - PARITY UNPINNED for the
-// radiance values, checked by self-consistency (tests/test_oracle*.py).
+// PARITY PINNED TO THE REFERENCE'S OWN COMPILED CODE.  The reference ships no test, golden vector or fixture for this
+// path and Mitsuba as a whole cannot be built in this image (Boost, Eigen, Xerces, OpenEXR ... are
+// absent), but the files of the path compile where they lie under /root/reference (oracle/Makefile,
+// outputs in oracle/_ref/), and this restatement is compared with them BIT-EXACTLY, live and through committed golden
+// vectors generated from them:
+//   * everything that decides a neighbour index set - PointKDTree build + range query, the AABB slab test, GPhotonMap +
+//     GradientBeamRadianceEstimator (hierarchy + traversal + neighbour predicate), SubBeamBVH, PhotonPlaneBVH,
+//     cylinderIntersection, intersectPlane0D, rayIntersectInternal1D, Triangle::rayIntersect,
+//     coordinateSystem(Coherent), solveQuadraticDouble (ref_harness.cpp -> _ref/libgvpm_ref.so;
+//     tests/test_oracle_ref_pin.py, tests/golden/ref_pins.npz);
+//   * the radiometric building blocks - HomogeneousMedium::eval, the phase functions, the diffuse BSDF, the area
+//     emitter, diffuseReconnection (ref_physics.cpp -> _ref/libgvpm_physics_ref.so; tests/test_oracle_physics_pin.py,
+//     tests/golden/physics_pins.npz);
+//   * the shift functors as a whole - VolumeGradientBREQuery, VolumeGradientPositionQuery, BeamGradRadianceQuery (3-D
+//     and 1-D kernels), PlaneGradRadianceQuery and sppm's BeamRadianceQuery, i.e. contributions, Jacobians, MIS
+//     weights, filters, border rule and accumulation (ref_functor.cpp -> _ref/libgvpm_functor_ref.so;
+//     tests/test_oracle_functor_pin.py, tests/golden/functor_pins.npz).
+// Not pinned: sppm's BRE loop body (bre.cpp:195-254, reads the stock RGBE-quantised Photon) and camera segments beyond
+// the first medium edge (sensorMIS's geometry terms arrive pre-multiplied in off_sensor); DESIGN.md §5.
 //
 // Template parameter Real = float restates the SINGLE_PRECISION build
 // (build/config-linux-gcc.py:7); Real = double is the error-budget variant.  Compile with

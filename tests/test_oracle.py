@@ -1,7 +1,8 @@
-"""CPU tests of the oracle (oracle/ = test infrastructure).  The reference ships no golden vector for
-this path (parity unpinned), so the restatement is pinned by self-consistency:
-tree traversal vs brute force (mirrors src/tests/test_kd.cpp:133-214), fp64 vs fp32 error budget,
-closed-form identities of the shift mapping, and a committed regression fixture."""
+"""CPU tests of the oracle (oracle/ = test infrastructure): self-consistency checks that hold whatever the inputs -
+tree traversal vs brute force (mirrors src/tests/test_kd.cpp:133-214), fp64 vs fp32 error budget, closed-form identities of
+the shift mapping, and a committed regression fixture.  The reference ships no golden vector for this path (SURVEY.md §4,
+§8c); the pins against the reference's own compiled code are tests/test_oracle_ref_pin.py (index sets),
+test_oracle_physics_pin.py (radiometry) and test_oracle_functor_pin.py (the shift functors as a whole)."""
 import os
 
 import numpy as np
