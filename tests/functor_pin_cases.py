@@ -51,7 +51,9 @@ BRE = {
     "wide_no_shift_null": (dict(scale=10.0, use_shift_null=False), None),
     "no_path_set": (dict(path_set=False), None),
     "power_heuristic_hg": (dict(power_heuristic=True, path_set=False, phase="hg", hg_g=0.3), None),
-    "kernel_2d": (dict(kernel_3d=False), None),
+    # the reference refuses useShiftNull with a 2-D kernel at load time (gvpm_struct.h:305-311), and so does gvpm_set_config
+    "kernel_2d": (dict(kernel_3d=False, use_shift_null=False), None),
+    "kernel_2d_hg_no_mis": (dict(kernel_3d=False, use_shift_null=False, phase="hg", hg_g=0.4, use_mis=False), None),
     "max_depth_4": (dict(max_depth=4), None),
     "min_depth_3": (dict(min_depth=3), None),
     "surf2media": (dict(lighting_mode=N.SURF2MEDIA), None),

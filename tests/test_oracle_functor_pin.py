@@ -76,7 +76,7 @@ def test_bre_functor_equals_reference_golden(built, golden, name):
     res = ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute", threads=2)
     calls = golden[f"bre_{name}_calls"]
     rows = None
-    if name == "kernel_2d":
+    if name.startswith("kernel_2d"):
         # documented deviation: the reference's 2-D kernel has no bound at the segment end (an empty
         # block, shift_volume_photon.cpp:726-731; with its hierarchy the result there depends on the tree shape), the
         # oracle applies sppm's explicit bound (bre.cpp:240-242).  Rays with such a photon are left out.
