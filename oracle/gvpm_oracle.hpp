@@ -22,8 +22,8 @@
 //     and 1-D kernels), PlaneGradRadianceQuery and sppm's BeamRadianceQuery, i.e. contributions, Jacobians, MIS
 //     weights, filters, border rule and accumulation (ref_functor.cpp -> _ref/libgvpm_functor_ref.so;
 //     tests/test_oracle_functor_pin.py, tests/golden/functor_pins.npz).
-// Not pinned: sppm's BRE loop body (bre.cpp:195-254, reads the stock RGBE-quantised Photon) and camera segments beyond
-// the first medium edge (sensorMIS's geometry terms arrive pre-multiplied in off_sensor); DESIGN.md §5.
+// Not pinned: sppm's BRE loop body (bre.cpp:195-254, reads the stock RGBE-quantised Photon).  Camera segments beyond the
+// first medium edge agree to 5e-7 instead of bit for bit (sensorMIS's cancelling geometry terms); DESIGN.md §5.
 //
 // Template parameter Real = float restates the SINGLE_PRECISION build
 // (build/config-linux-gcc.py:7); Real = double is the error-budget variant.  Compile with

@@ -419,11 +419,9 @@ struct BeamWorld {
 // One camera medium segment with its four offset segments as the functors see them: a GatherPoint with its camera Path
 // and cached vertex weights, four ShiftGatherPoints marked as generated.  Holds pointers into itself: built in place.
 struct CameraSide {
-  PathVertex bv[3];
-  PathEdge be[2];
+  std::vector<PathVertex> bv, sv[4];
+  std::vector<PathEdge> be, se[4];
   GatherPoint gp;
-  PathVertex sv[4][3];
-  PathEdge se[4][2];
   std::vector<ShiftGatherPoint> shiftGPs;
   CameraSide() : shiftGPs(4) {}
   CameraSide(const CameraSide &) = delete;
@@ -431,54 +429,62 @@ struct CameraSide {
     gp.path.m_vertices.clear(); gp.path.m_edges.clear();
     for (auto &s : shiftGPs) { s.path.m_vertices.clear(); s.path.m_edges.clear(); }
   }
-  void build(const gvpm_ray_soa *ry, size_t r, const Medium *mediumPtr) {
-    // base gather point: supernode, sensor sample (pixel position), the medium edge, its end vertex
-    for (auto &x : bv) zero(x);
-    for (auto &x : be) zero(x);
-    bv[0].type = PathVertex::ESensorSupernode;
-    bv[1].type = PathVertex::ESensorSample;
-    {
-      PositionSamplingRecord &pr = bv[1].getPositionSamplingRecord();
-      new (&pr) PositionSamplingRecord();
-      pr.p = P3(ry->o + 3 * r);
-      pr.uv = Point2((Float)ry->px[r] + 0.5f, (Float)ry->py[r] + 0.5f);
+  // vertices 0 .. e+1 and edges 0 .. e of one camera path whose medium segment is edge e: supernode, sensor sample
+  // (pixel position), for e > 1 the vertices up to the segment start (medium-type records at the segment origin; only
+  // the positions of vertex e and e+1 are read, by GOp in sensorMIS), the segment, its end vertex
+  static void layout(std::vector<PathVertex> &v, std::vector<PathEdge> &ed, Path &path, size_t e, const Point &o,
+                     const Vector &dir, Float len, const Medium *mediumPtr) {
+    v.resize(e + 2);
+    ed.resize(e + 1);
+    for (auto &x : v) zero(x);
+    for (auto &x : ed) zero(x);
+    v[0].type = PathVertex::ESensorSupernode;
+    v[1].type = PathVertex::ESensorSample;
+    PositionSamplingRecord &pr = v[1].getPositionSamplingRecord();
+    new (&pr) PositionSamplingRecord();
+    pr.p = o;
+    for (size_t k = 2; k <= e + 1; ++k) {
+      v[k].type = PathVertex::EMediumInteraction;
+      MediumSamplingRecord &m = v[k].getMediumSamplingRecord();
+      new (&m) MediumSamplingRecord();
+      m.p = k <= e ? o : o + dir * len;
+      m.medium = mediumPtr;
     }
-    be[1].d = V3f(ry->d + 3 * r);
-    be[1].length = ry->edge_len[r];
-    be[1].medium = mediumPtr;
-    gp.path.append(&bv[0]); gp.path.append(&be[0]); gp.path.append(&bv[1]); gp.path.append(&be[1]); gp.path.append(&bv[2]);
-    gp.info.resize(2);
-    gp.info[0].weight = S3(ry->eye_contrib + 3 * r);     // getWeightBeam(e - 1)
-    gp.info[0].vertexWeight = Spectrum(1.f);
-    gp.info[0].pdf = gp.info[0].jacobian = 1.f;
-    gp.info[1].weight = Spectrum(1.f);
-    gp.info[1].vertexWeight = Spectrum(1.f);             // getWeightVertex(e)
-    gp.info[1].pdf = gp.info[1].jacobian = 1.f;
-
+    for (size_t k = 0; k <= e + 1; ++k) {
+      path.append(&v[k]);
+      if (k <= e) path.append(&ed[k]);
+    }
+  }
+  static void infos(std::vector<SVertexPDF> &info, size_t e, const Spectrum &weightBeam, Float sensorPdf) {
+    info.resize(e + 1);
+    for (auto &x : info) {
+      x.weight = Spectrum(1.f);
+      x.vertexWeight = Spectrum(1.f);
+      x.pdf = x.jacobian = 1.f;
+    }
+    info[e - 1].weight = weightBeam;   // getWeightBeam(e - 1); getWeightVertex(e) = 1
+    info[e].pdf = sensorPdf;           // sensorMIS(e, base, ., .) = (pdf / base pdf) * jacobian [* terms that cancel, e > 1]
+  }
+  void build(const gvpm_ray_soa *ry, size_t r, const Medium *mediumPtr) {
+    const size_t e = (size_t)ry->edge_id[r];
+    const Point o = P3(ry->o + 3 * r);
+    const Vector d = V3f(ry->d + 3 * r);
+    layout(bv, be, gp.path, e, o, d, ry->edge_len[r], mediumPtr);
+    bv[1].getPositionSamplingRecord().uv = Point2((Float)ry->px[r] + 0.5f, (Float)ry->py[r] + 0.5f);
+    be[e].d = d;
+    be[e].length = ry->edge_len[r];
+    be[e].medium = mediumPtr;
+    infos(gp.info, e, S3(ry->eye_contrib + 3 * r), 1.f);
     for (int k = 0; k < 4; ++k) {
-      for (auto &x : sv[k]) zero(x);
-      for (auto &x : se[k]) zero(x);
       const size_t q = 4 * r + k;
-      sv[k][0].type = PathVertex::ESensorSupernode;
-      sv[k][1].type = PathVertex::ESensorSample;
-      PositionSamplingRecord &pr = sv[k][1].getPositionSamplingRecord();
-      new (&pr) PositionSamplingRecord();
-      pr.p = P3(ry->off_o + 3 * q);
-      se[k][1].d = -V3f(ry->off_d + 3 * q);              // the functor takes shiftDir = -edge(e).d
-      se[k][1].length = ry->off_len[q];
-      se[k][1].medium = ry->off_valid[q] ? mediumPtr : NULL;   // validVolumeEdge
       ShiftGatherPoint &s = shiftGPs[k];
       s.generated = true;                                // nothing to trace: generate() returns at once
-      s.path.append(&sv[k][0]); s.path.append(&se[k][0]); s.path.append(&sv[k][1]); s.path.append(&se[k][1]);
-      s.path.append(&sv[k][2]);
-      s.info.resize(2);
-      s.info[0].weight = S3(ry->off_eye + 3 * q);
-      s.info[0].vertexWeight = Spectrum(1.f);
-      s.info[0].pdf = s.info[0].jacobian = 1.f;
-      s.info[1].weight = Spectrum(1.f);
-      s.info[1].vertexWeight = Spectrum(1.f);
-      s.info[1].pdf = ry->off_sensor[q];                 // sensorMIS(1, base, ., .) = (pdf / base pdf) * jacobian
-      s.info[1].jacobian = 1.f;
+      const Vector od = V3f(ry->off_d + 3 * q);
+      layout(sv[k], se[k], s.path, e, P3(ry->off_o + 3 * q), od, ry->off_len[q], mediumPtr);
+      se[k][e].d = -od;                                  // the functor takes shiftDir = -edge(e).d
+      se[k][e].length = ry->off_len[q];
+      se[k][e].medium = ry->off_valid[q] ? mediumPtr : NULL;   // validVolumeEdge
+      infos(s.info, e, S3(ry->off_eye + 3 * q), ry->off_sensor[q]);
     }
   }
 };
@@ -499,7 +505,7 @@ int ref_fn_bre_gather(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa
     for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
     if (counts) counts[r] = 0;
     const size_t e = (size_t)ry->edge_id[r];
-    if (e != 1) return -5;
+    if (e < 1 || e > 8) return -5;
     CameraSide cam;
     cam.build(ry, r, W.medium.get());
     const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
@@ -550,7 +556,7 @@ int ref_fn_vpm_gather(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa
     const size_t r = smp->ray[s];
     if (r >= n_rays) return -6;
     const size_t e = (size_t)ry->edge_id[r];
-    if (e != 1) return -5;
+    if (e < 1 || e > 8) return -5;
     CameraSide cam;
     cam.build(ry, r, W.medium.get());
     VolumeGradientDistanceQuery gRec(W.scene, &cam.gp, W.config, *W.thdata, cam.shiftGPs, 0, NULL);
@@ -620,7 +626,7 @@ int ref_fn_beams_gather(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_
     for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
     if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
     const size_t e = (size_t)ry->edge_id[r];
-    if (e != 1) return -5;
+    if (e < 1 || e > 8) return -5;
     CameraSide cam;
     cam.build(ry, r, W.medium.get());
     // gvpm.cpp:936: Ray ray(vertex(idEdge).position, d, Epsilon, distTotal - Epsilon, 0.f)
@@ -667,7 +673,7 @@ int ref_fn_planes_gather(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_r
     for (int j = 0; j < 27; ++j) out[27 * r + j] = 0.f;
     if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
     const size_t e = (size_t)ry->edge_id[r];
-    if (e != 1) return -5;
+    if (e < 1 || e > 8) return -5;
     CameraSide cam;
     cam.build(ry, r, W.medium.get());
     // gvpm.cpp:837: Ray ray(vertex(idEdge).position, d, Epsilon, distTotal - Epsilon, 0.f)

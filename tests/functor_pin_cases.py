@@ -185,6 +185,19 @@ def beams_case(name):
     return c
 
 
+# Later camera edges (edge_id = 2, what the synthetic camera outside the medium produces): sensorMIS multiplies geometry
+# and distance terms into its two factors that cancel in their product (gvpm_struct.h:608-631); the flattened form carries
+# the product (off_sensor), so the agreement is up to the rounding of those terms, not bit for bit.
+EDGE2 = [("bre", "default"), ("bre", "wide"), ("bre", "power_heuristic_hg"), ("bre", "blocker_wide_hg"), ("vpm", "wide"),
+         ("beams", "default"), ("beams", "beam1d"), ("beams", "power_heuristic"), ("planes", "default")]
+
+
+def edge2_case(kind, name):
+    c = {"bre": bre_case, "vpm": vpm_case, "beams": beams_case, "planes": planes_case}[kind](name)
+    c.rays.edge_id[:] = 2
+    return c
+
+
 def input_crc(c):
     """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
     h = 0

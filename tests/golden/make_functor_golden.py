@@ -53,6 +53,18 @@ if __name__ == "__main__":
             out[f"sppmbeams_{name}_{tech}_bits"], out[f"sppmbeams_{name}_{tech}_true"] = cases.bits(res), counts[:, 0]
             print(f"sppm beams {name:22s} {tech:13s} accepted pairs {int(counts[:, 0].sum()):6d}  non-zero {np.count_nonzero(res):5d}")
         out[f"sppmbeams_{name}_crc"] = cases.input_crc(c)
+    for kind, name in cases.EDGE2:
+        c = cases.edge2_case(kind, name)
+        if kind == "bre":
+            res = fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)[0]
+        elif kind == "vpm":
+            res = fb.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb)[0]
+        elif kind == "beams":
+            res = fb.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius)[0]
+        else:
+            res = fb.planes_gather(c.planes, c.rays, c.medium, c.config)[0]
+        out[f"edge2_{kind}_{name}_bits"] = cases.bits(res)
+        print(f"edge 2 {kind:6s} {name:22s} non-zero outputs {np.count_nonzero(res):6d}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

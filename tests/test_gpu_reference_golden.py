@@ -123,3 +123,32 @@ def test_gpu_sppm_beams_equal_reference_functor_output(golden, name):
             np.testing.assert_array_equal(counts[:, 1], accepted)
         _close(out, golden[f"sppmbeams_{name}_{tech}_bits"], f"sppm beams {name} {tech}", rows)
     ctx.close()
+
+
+@pytest.mark.parametrize("kind,name", cases.EDGE2)
+def test_gpu_later_camera_edge_equals_reference_functor_output(golden, kind, name):
+    """Camera segment = edge 2 of the camera path (the synthetic camera outside the medium, what bench.py runs): the
+    reference's sensorMIS carries geometry terms there that cancel in the product the ABI receives."""
+    from gvpm_b200.api import Context
+    c = cases.edge2_case(kind, name)
+    want = golden[f"edge2_{kind}_{name}_bits"]
+    if kind == "bre":
+        ctx = H.gpu_context(c)
+        out = ctx.gather_bre()[0]
+    elif kind == "vpm":
+        ctx = H.gpu_context(c)
+        ctx.upload_vpm_samples(c.samples)
+        out = ctx.gather_vpm(c.nb)[0]
+    elif kind == "beams":
+        ctx = _beam_ctx(c)
+        out = ctx.gather_beams()[0]
+    else:
+        ctx = Context(0)
+        ctx.set_medium(c.medium)
+        ctx.set_config(c.config)
+        ctx.upload_planes(c.planes)
+        ctx.build_planes()
+        ctx.upload_rays(c.rays)
+        out = ctx.gather_planes()[0]
+    ctx.close()
+    _close(out, want, f"{kind} {name}, camera edge 2")

@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 
 import functor_pin_cases as cases
+import gvpm_testlib as H
 from oracle import binding as ob
 from oracle import functor_binding as fb
 
@@ -182,12 +183,38 @@ def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
         np.testing.assert_array_equal(counts[:, 0], golden[f"sppmbeams_default_{tech}_true"])
 
 
+def _oracle_out(kind, c):
+    if kind == "bre":
+        return ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, mode="brute", threads=2).out
+    if kind == "vpm":
+        return ob.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, mode="brute", threads=2).out
+    if kind == "beams":
+        return ob.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius, threads=2).out
+    return ob.planes_gather(c.planes, c.rays, c.medium, c.config, mode="brute", threads=2).out
+
+
+@pytest.mark.parametrize("kind,name", cases.EDGE2)
+def test_later_camera_edge_matches_reference_golden(built, golden, kind, name):
+    """Camera segment = edge 2 of the camera path (sensor outside the medium).  The reference's sensorMIS then multiplies
+    geometry and squared-distance ratios into its two factors, which cancel in their product (gvpm_struct.h:608-631); the
+    flattened form carries that product, so only the rounding of the cancelling terms differs: primal bit for bit, the
+    gradient terms within 2e-6."""
+    c = cases.edge2_case(kind, name)
+    got = _oracle_out(kind, c)
+    want = golden[f"edge2_{kind}_{name}_bits"].view(np.float32)
+    np.testing.assert_array_equal(cases.bits(got[:, :3]), cases.bits(want[:, :3]))
+    assert H.rel_err(got, want).max() < 2e-6
+    assert H.rel_err_per_ray(got, want)[0].max() < 2e-6
+    if kind != "planes":   # the depth filters see the other edge id (the plane functor has none)
+        assert not np.array_equal(cases.bits(got), golden[f"{kind}_{name}_bits"])
+
+
 def test_harness_refuses_what_it_cannot_rebuild(built):
-    """Later medium edges (sensorMIS with geometry terms) and glossy parents (manifold shift) are outside the pin."""
+    """Glossy parents (manifold shift) and camera edge 0 are outside the pin."""
     if not fb.have_ref():
         pytest.skip("prebuilt reference library absent")
     c = cases.bre_case("default")
-    c.rays.edge_id[:] = 2
+    c.rays.edge_id[:] = 0
     with pytest.raises(RuntimeError):
         fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)
     c = cases.bre_case("default")
