@@ -49,6 +49,11 @@ def load():
         _lib.ref_fn_sppm_beams_gather.restype = C.c_int
         _lib.ref_fn_sppm_beams_gather.argtypes = [C.c_void_p, C.c_size_t, N.u32p, N.f32p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                   C.c_void_p, C.c_void_p, C.c_float, C.c_int, N.f32p, N.f32p, N.u32p]
+        _lib.ref_fn_sppm_bre_gather.restype = C.c_int
+        _lib.ref_fn_sppm_bre_gather.argtypes = [N.f32p, N.f32p, N.f32p, N.u8p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                C.c_void_p, C.c_float, N.f32p, N.f32p]
+        _lib.ref_fn_rgbe_roundtrip.restype = None
+        _lib.ref_fn_rgbe_roundtrip.argtypes = [N.f32p, C.c_size_t, N.f32p]
     return _lib
 
 
@@ -161,3 +166,37 @@ def sppm_beams_gather(beams, rays, medium, config, radius, technique):
     if rc != 0:
         raise RuntimeError(f"ref_fn_sppm_beams_gather refused the input: {rc}")
     return out.reshape(rays.n, 3), counts.reshape(rays.n, 2)
+
+
+def rgbe_roundtrip(flux):
+    """Spectrum::toRGBE + fromRGBE: what the stock Photon does to its power (photon.h:40-44,124-132)."""
+    lib = load()
+    a = np.ascontiguousarray(flux, dtype=np.float32).reshape(-1)
+    out = np.zeros_like(a)
+    lib.ref_fn_rgbe_roundtrip(a.ctypes.data_as(N.f32p), a.size // 3, out.ctypes.data_as(N.f32p))
+    return out
+
+
+def sppm_bre_gather(photons, direction, rays, medium, config, radius):
+    """The loop body of sppm's BeamRadianceEstimator::query (photonmapper/bre.cpp:167-259) on every (ray, photon) pair in
+    photon order.  `direction` [n, 3] is photon.getDirection(); photons.flux must be RGBE-representable.  Returns
+    out [n_rays, 3] without beam.weight and m_scaleFactor."""
+    from oracle import binding as ob
+    lib, olib = load(), ob.load()
+    cr = rays.as_c()
+    xi = np.zeros(rays.n * photons.n, dtype=np.float32)
+    olib.gvpm_oracle_sppm_uniforms.restype = None
+    olib.gvpm_oracle_sppm_uniforms.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p]
+    olib.gvpm_oracle_sppm_uniforms(C.byref(cr), rays.n, photons.n, C.byref(medium), C.byref(config),
+                                   xi.ctypes.data_as(N.f32p))
+    pos = np.ascontiguousarray(photons.pos, dtype=np.float32)
+    flux = np.ascontiguousarray(photons.flux, dtype=np.float32)
+    d = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1)
+    depth = np.ascontiguousarray(photons.depth, dtype=np.uint8)
+    out = np.zeros(rays.n * 3, dtype=np.float32)
+    rc = lib.ref_fn_sppm_bre_gather(pos.ctypes.data_as(N.f32p), d.ctypes.data_as(N.f32p), flux.ctypes.data_as(N.f32p),
+                                    depth.ctypes.data_as(N.u8p), photons.n, C.byref(cr), rays.n, C.byref(medium),
+                                    C.byref(config), radius, xi.ctypes.data_as(N.f32p), out.ctypes.data_as(N.f32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_sppm_bre_gather refused the input: {rc}")
+    return out.reshape(rays.n, 3)

@@ -315,3 +315,15 @@ extern "C" long long gvpm_oracle_vpm(void *tree, const gvpm_photon_soa *ph, size
   }
   return total;
 }
+
+// The per-(ray, photon) uniform number of the restated sppm BRE (3-D kernel: the sampler->next1D() of bre.cpp:217, here the
+// counter-based hash Scene::sppmUniform).  Exported so that the reference harness (ref_functor.cpp) is fed the same draws.
+// xi: [nRays * nPhotons].
+extern "C" void gvpm_oracle_sppm_uniforms(const gvpm_ray_soa *rays, size_t nRays, size_t nPhotons, const gvpm_medium *med,
+                                          const gvpm_config *cfg, float *xi) {
+  Scene<float> sc(*med, *cfg, 1.f);
+  for (size_t i = 0; i < nRays; ++i) {
+    CamRay<float> ray = loadRay<float>(*rays, i);
+    for (size_t j = 0; j < nPhotons; ++j) xi[i * nPhotons + j] = sc.sppmUniform(ray, (uint32_t)j);
+  }
+}

@@ -22,8 +22,10 @@
 //     and 1-D kernels), PlaneGradRadianceQuery and sppm's BeamRadianceQuery, i.e. contributions, Jacobians, MIS
 //     weights, filters, border rule and accumulation (ref_functor.cpp -> _ref/libgvpm_functor_ref.so;
 //     tests/test_oracle_functor_pin.py, tests/golden/functor_pins.npz).
-// Not pinned: sppm's BRE loop body (bre.cpp:195-254, reads the stock RGBE-quantised Photon).  Camera segments beyond the
-// first medium edge agree to 5e-7 instead of bit for bit (sensorMIS's cancelling geometry terms); DESIGN.md §5.
+//   * sppm's primal functors - BeamRadianceQuery (four techniques) and the loop body of BeamRadianceEstimator::query
+//     (same library and tests).
+// Camera segments beyond the first medium edge agree to 5e-7 instead of bit for bit (sensorMIS's cancelling geometry
+// terms), sppm's BRE under Henyey-Greenstein to 1.2e-6 (the flattened photon direction); DESIGN.md §5.
 //
 // Template parameter Real = float restates the SINGLE_PRECISION build
 // (build/config-linux-gcc.py:7); Real = double is the error-budget variant.  Compile with
@@ -429,7 +431,7 @@ template <typename Real> struct Scene {
     const Real diskDistance = dot(originToCenter, ray.d), radSqr = r * r;
     const Real distSqr = ((ro + diskDistance * ray.d) - ph.pos).lengthSquared();
     if (!(diskDistance > 0 && distSqr < radSqr)) return 0;
-    Real tEval, scale;
+    Real tEval, scale, invPdf = 1;
     if (cfg.kernel_3d) {
       if (diskDistance - (r * 2) > rmaxt) return 0;
       const Real weight = (Real)(1 / ((4.0 / 3.0) * (double)Consts<Real>::pi * std::pow((double)r, 3)));
@@ -439,7 +441,8 @@ template <typename Real> struct Scene {
       if (diskDistanceRand < 0 || diskDistanceRand > rmaxt) return 0;
       const Real invPdfSampling = std::max((Real)(2.0f * deltaT), (Real)0.0001f);
       tEval = diskDistanceRand;
-      scale = weight * invPdfSampling;
+      scale = weight;              // (weight * m_scaleFactor) * invPdfSampling, in the reference's order (:233-235)
+      invPdf = invPdfSampling;
     } else {
       if (diskDistance > rmaxt) return 0;
       tEval = diskDistance;
@@ -448,7 +451,9 @@ template <typename Real> struct Scene {
     if (cfg.max_depth != -1 && ph.depth > cfg.max_depth - ray.edgeId) return 1;
     const V3<Real> wi = normalize(ph.parentPos - ph.pos);   // = -photon.getDirection()
     typename Medium<Real>::Rec mRecBase = medium.eval(0, tEval);
-    result += (((mRecBase.transmittance * ph.flux) * medium.phase(wi, -ray.d)) * scale) * ray.eye;
+    V3<Real> term = ((mRecBase.transmittance * ph.flux) * medium.phase(wi, -ray.d)) * scale;
+    if (cfg.kernel_3d) term = term * invPdf;
+    result += term * ray.eye;
     return 2;
   }
 

@@ -76,6 +76,8 @@
 #include "gvpm/shift/shift_volume_beams.h"
 #include "gvpm/gvpm_plane.h"
 #include "gvpm/shift/shift_volume_planes.h"
+#include <mitsuba/render/photon.h>
+#include "bre.h"
 #undef private
 #undef protected
 
@@ -493,7 +495,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 5; }
+int ref_fn_version() { return 6; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -730,6 +732,62 @@ int ref_fn_sppm_beams_gather(const gvpm_beam_soa *bs, size_t n_beams, const uint
     putS(out + 3 * r, q.Li);
   }
   return 0;
+}
+
+// sppm primal BRE: the loop body of BeamRadianceEstimator::query (photonmapper/bre.cpp:167-259: depth filter, neighbour
+// predicate on the ray re-based at r(r.mint), 3-D kernel with its early-out and per-photon random chord position, 2-D
+// kernel with its segment bound, transmittance, phase function, kernel weight), driven as volumePhotonPassBRE does
+// (sppm.cpp:968-973).  The estimator is raw storage holding ONE leaf node with an all-enclosing box, re-filled per photon:
+// query() then runs its loop body on exactly that photon, and the per-ray sum is taken over the photons in index order
+// (the reference sums in traversal order).  The stock Photon stores its power in RGBE (photon.h:40-44): flux must be
+// RGBE-representable (ref_fn_rgbe_roundtrip); dir = photon.getDirection() is stored unquantised in this fork
+// (MTS_DISCRETIZED_PHOTON 0).  xi: [n_rays * n_ph] the sampler->next1D() of :217 per pair.  out: [n_rays * 3] WITHOUT
+// beam.weight and m_scaleFactor; counts: [n_rays * 2] = 0.
+int ref_fn_sppm_bre_gather(const float *pos, const float *dir, const float *flux, const uint8_t *depth, size_t n_ph,
+                           const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med, const gvpm_config *cfg,
+                           float radius, const float *xi, float *out) {
+  World W;
+  W.common(med, cfg, NULL, 0, cfg->kernel_3d ? EVolBRE3D : EVolBRE2D);
+  BeamRadianceEstimator *bre = rawZeroed<BeamRadianceEstimator>();
+  BeamRadianceEstimator::BRENode *node =
+      reinterpret_cast<BeamRadianceEstimator::BRENode *>(std::calloc(1, sizeof(BeamRadianceEstimator::BRENode)));
+  bre->m_nodes = node;
+  bre->m_scaleFactor = 1.f;
+  bre->m_photonCount = 1;
+  bre->m_depth = 1;
+  node->aabb = AABB(Point(-1e30f, -1e30f, -1e30f), Point(1e30f, 1e30f, 1e30f));
+  node->radius = radius;
+  ref<PresetSampler> sampler = new PresetSampler();
+  for (size_t r = 0; r < n_rays; ++r) {
+    const int beamDepth = ry->edge_id[r];
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    Spectrum sum(0.f);
+    for (size_t i = 0; i < n_ph; ++i) {
+      Photon &p = node->photon;
+      p.setPosition(P3(pos + 3 * i));
+      p.setLeaf(true);
+      S3(flux + 3 * i).toRGBE(p.data.power);
+      p.data.wi = V3f(dir + 3 * i);
+      p.data.depth = depth[i];
+      sampler->preset(xi[r * n_ph + i], 0.f);
+      sum += bre->query(ray, W.medium.get(), cfg->max_depth == -1 ? -1 : cfg->max_depth - beamDepth, cfg->kernel_3d != 0,
+                        sampler.get());
+    }
+    putS(out + 3 * r, sum);
+  }
+  std::free(node);
+  return 0;
+}
+
+// Spectrum::toRGBE / fromRGBE (what Photon does to its power, photon.h:40-44,124-132)
+void ref_fn_rgbe_roundtrip(const float *in, size_t n, float *out) {
+  for (size_t i = 0; i < n; ++i) {
+    uint8_t rgbe[4];
+    S3(in + 3 * i).toRGBE(rgbe);
+    Spectrum s;
+    s.fromRGBE(rgbe);
+    putS(out + 3 * i, s);
+  }
 }
 
 }  // extern "C"

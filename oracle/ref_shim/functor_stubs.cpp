@@ -46,6 +46,9 @@ Float VertexClassifier::roughnessThreshold = 0.05f;
 // Sampler's serialization (src/librender/sampler.cpp is linked for the base class of the harness' preset sampler)
 void Stream::writeULong(uint64_t) { fn_unreachable("Stream::writeULong"); }
 uint64_t Stream::readULong() { fn_unreachable("Stream::readULong"); return 0; }
+// ... and the stock Photon's (src/librender/photon.cpp, linked for sppm's BRE)
+void Stream::writeUShort(unsigned short) { fn_unreachable("Stream::writeUShort"); }
+unsigned short Stream::readUShort() { fn_unreachable("Stream::readUShort"); return 0; }
 
 bool PathEdge::sampleNext(const Scene *, Sampler *, const PathVertex *, const Ray &, PathVertex *, ETransportMode, bool, bool) {
   fn_unreachable("PathEdge::sampleNext"); return false;

@@ -172,6 +172,33 @@ def sppm_beams_case(name, unit_weight=True):
     return c
 
 
+SPPM_BRE = {
+    "kernel_3d": dict(),
+    "kernel_3d_hg_forward": dict(phase="hg", hg_g=0.6),
+    "kernel_2d": dict(kernel_3d=False),
+    "kernel_2d_hg_backward": dict(kernel_3d=False, phase="hg", hg_g=-0.4),
+    "kernel_3d_max_depth_4": dict(max_depth=4),
+    "kernel_3d_wide": dict(scale=8.0),
+}
+
+
+def sppm_bre_case(name, quantise=None):
+    """sppm primal BRE (camera beams at depth 2).  Returns the case with c.direction = photon.getDirection() and
+    parent_pos = pos - direction, the ABI's flattening (include/gvpm_b200.h).  The stock Photon keeps its power in RGBE:
+    `quantise` (the reference's Spectrum::toRGBE / fromRGBE round trip) makes the flux representable; without it the flux is
+    left as generated (the golden file stores the quantised flux)."""
+    kw = dict(dict(n_photons=3000, w=16, h=12, scale=3.0, sppm_primal=True), **SPPM_BRE[name])
+    c = H.make_case(**kw)
+    c.rays.eye_contrib[:] = 1.0
+    pos, par = c.photons.view("pos"), c.photons.view("parent_pos")
+    d = pos - par
+    c.direction = (d / np.sqrt((d * d).sum(axis=1, keepdims=True))).astype(np.float32)
+    par[:] = pos - c.direction
+    if quantise is not None:
+        c.photons.flux[:] = quantise(c.photons.flux)
+    return c
+
+
 def beams_case(name):
     from gvpm_b200 import records as R
     kw, post = BEAMS[name]

@@ -1,6 +1,6 @@
 """Regenerates tests/golden/functor_pins.npz from the REFERENCE'S OWN shift functors (oracle/_ref/libgvpm_functor_ref.so:
 VolumeGradientBREQuery::operator() and VolumeGradientPositionQuery::operator(), shift_volume_photon.cpp,
-BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, PlaneGradRadianceQuery::operator(), shift_volume_planes.h, sppm's BeamRadianceQuery::operator(), beams.h,
+BeamGradRadianceQuery::operator(), shift_volume_beams.cpp, PlaneGradRadianceQuery::operator(), shift_volume_planes.h, sppm's BeamRadianceQuery::operator(), beams.h, and BeamRadianceEstimator::query, bre.cpp,
 compiled from
 /root/reference by `make -C oracle functor_ref` and driven by oracle/ref_functor.cpp).  Run in the container that holds the
 reference tree:
@@ -65,6 +65,13 @@ if __name__ == "__main__":
             res = fb.planes_gather(c.planes, c.rays, c.medium, c.config)[0]
         out[f"edge2_{kind}_{name}_bits"] = cases.bits(res)
         print(f"edge 2 {kind:6s} {name:22s} non-zero outputs {np.count_nonzero(res):6d}")
+    for name in cases.SPPM_BRE:
+        c = cases.sppm_bre_case(name, quantise=fb.rgbe_roundtrip)
+        assert np.array_equal(fb.rgbe_roundtrip(c.photons.flux), c.photons.flux)
+        res = fb.sppm_bre_gather(c.photons, c.direction, c.rays, c.medium, c.config, c.radius)
+        out[f"sppmbre_{name}_bits"], out[f"sppmbre_{name}_flux_bits"] = cases.bits(res), cases.bits(c.photons.flux)
+        out[f"sppmbre_{name}_crc"] = cases.input_crc(c)
+        print(f"sppm bre {name:24s} non-zero outputs {np.count_nonzero(res):5d}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

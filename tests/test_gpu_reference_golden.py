@@ -152,3 +152,16 @@ def test_gpu_later_camera_edge_equals_reference_functor_output(golden, kind, nam
         out = ctx.gather_planes()[0]
     ctx.close()
     _close(out, want, f"{kind} {name}, camera edge 2")
+
+
+@pytest.mark.parametrize("name", list(cases.SPPM_BRE))
+def test_gpu_sppm_bre_equals_reference_loop_body_output(golden, name):
+    """sppm primal BRE against the loop body of the reference's BeamRadianceEstimator::query (bre.cpp:195-254), with the
+    photons' power as the stock Photon's RGBE round trip leaves it."""
+    flux = golden[f"sppmbre_{name}_flux_bits"].view(np.float32)
+    c = cases.sppm_bre_case(name, quantise=lambda f: flux)
+    assert cases.input_crc(c) == golden[f"sppmbre_{name}_crc"]
+    ctx = H.gpu_context(c)
+    out, _ = ctx.gather_sppm_bre()
+    ctx.close()
+    _close(out, golden[f"sppmbre_{name}_bits"], f"sppm BRE {name}")

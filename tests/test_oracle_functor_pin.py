@@ -2,7 +2,8 @@
 a13-a16 of SURVEY.md §8): VolumeGradientBREQuery::operator() (gvpm/shift/shift_volume_photon.cpp:658-856),
 VolumeGradientPositionQuery::operator() (:489-655), BeamGradRadianceQuery::operator() (shift_volume_beams.cpp:139-353) and
 PlaneGradRadianceQuery::operator() (shift_volume_planes.h:56-101), plus sppm's primal BeamRadianceQuery::operator()
-(photonmapper/beams.h:29-223, row a20), with everything they call - the depth / lighting-mode / path-set
+(photonmapper/beams.h:29-223) and the loop body of BeamRadianceEstimator::query (bre.cpp:167-259; row a20), with
+everything they call - the depth / lighting-mode / path-set
 filters, the 3-D kernel's random chord position, shiftNull (:119-158), getTypeShift + VertexClassifier, shiftPhotonDiffuse
 (:382-486) with its shadow ray and side test, getShiftPos (:858-896), the border rule, the MIS weights (balance and power
 heuristic) and the accumulation.
@@ -151,6 +152,29 @@ def test_sppm_beam_functor_equals_reference_golden(built, golden, name, tech):
         np.testing.assert_allclose(res.out, ref, rtol=2e-6, atol=0)
 
 
+def _sppm_bre_case(golden, name):
+    flux = golden[f"sppmbre_{name}_flux_bits"].view(np.float32)     # the photons' power after the reference's RGBE round trip
+    c = cases.sppm_bre_case(name, quantise=lambda f: flux)
+    assert cases.input_crc(c) == golden[f"sppmbre_{name}_crc"], "the seeded inputs changed: regenerate the golden vectors"
+    return c
+
+
+@pytest.mark.parametrize("name", list(cases.SPPM_BRE))
+def test_sppm_bre_loop_body_equals_reference_golden(built, golden, name):
+    """The loop body of sppm's BeamRadianceEstimator::query (photonmapper/bre.cpp:195-254) per (camera beam, photon) pair.
+    Isotropic medium: bit for bit.  Henyey-Greenstein: the reference evaluates the phase function with
+    wi = -photon.getDirection(), the flattened form with normalize(parent_pos - pos) where parent_pos = pos - direction
+    (include/gvpm_b200.h), equal up to the rounding of that subtraction."""
+    c = _sppm_bre_case(golden, name)
+    res = ob.sppm_bre_gather(c.photons, c.rays, c.medium, c.config, c.radius, mode="brute", threads=2)
+    want = golden[f"sppmbre_{name}_bits"]
+    assert np.count_nonzero(want) > 200
+    if "hg" in name:
+        assert H.rel_err(res.out, want.view(np.float32)).max() < 3e-6
+    else:
+        _same_rows(cases.bits(res.out), want, f"sppm BRE loop body, case {name}")
+
+
 @pytest.mark.skipif(not (fb.have_ref() or os.path.isdir(fb.REFERENCE_ROOT)), reason="reference tree / prebuilt library absent")
 def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
     """Live: the reference functors, compiled here, reproduce the committed vectors (the fixtures are not stale)."""
@@ -176,6 +200,11 @@ def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
         out, counts = fb.planes_gather(c.planes, c.rays, c.medium, c.config)
         np.testing.assert_array_equal(cases.bits(out), golden[f"planes_{name}_bits"])
         np.testing.assert_array_equal(counts[:, 0], golden[f"planes_{name}_hits"])
+    for name in ("kernel_3d", "kernel_2d_hg_backward"):
+        c = _sppm_bre_case(golden, name)
+        np.testing.assert_array_equal(cases.bits(fb.rgbe_roundtrip(c.photons.flux)), cases.bits(c.photons.flux))
+        out = fb.sppm_bre_gather(c.photons, c.direction, c.rays, c.medium, c.config, c.radius)
+        np.testing.assert_array_equal(cases.bits(out), golden[f"sppmbre_{name}_bits"])
     c = cases.sppm_beams_case("default")
     for tech in cases.SPPM_BEAM_TECHNIQUES:
         out, counts = fb.sppm_beams_gather(c.beams, c.rays, c.medium, c.config, c.radius, tech)
