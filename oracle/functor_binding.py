@@ -54,6 +54,9 @@ def load():
                                                 C.c_void_p, C.c_float, N.f32p, N.f32p]
         _lib.ref_fn_rgbe_roundtrip.restype = None
         _lib.ref_fn_rgbe_roundtrip.argtypes = [N.f32p, C.c_size_t, N.f32p]
+        _lib.ref_fn_sppm_planes_gather.restype = C.c_int
+        _lib.ref_fn_sppm_planes_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                   N.f32p, N.u32p]
     return _lib
 
 
@@ -200,3 +203,17 @@ def sppm_bre_gather(photons, direction, rays, medium, config, radius):
     if rc != 0:
         raise RuntimeError(f"ref_fn_sppm_bre_gather refused the input: {rc}")
     return out.reshape(rays.n, 3)
+
+
+def sppm_planes_gather(planes, rays, medium, config):
+    """sppm's primal plane functor (PhotonPlaneQuery::operator(), photonmapper/plane_struct.h:238-256) over every (camera
+    beam, plane) pair in plane order.  Returns (Li [n_rays, 3] without the camera beam's weight, counts [n_rays, 2])."""
+    lib = load()
+    cp, cr = planes.as_c(), rays.as_c()
+    out = np.zeros(rays.n * 3, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    rc = lib.ref_fn_sppm_planes_gather(C.byref(cp), planes.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                                       out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p))
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_sppm_planes_gather refused the input: {rc}")
+    return out.reshape(rays.n, 3), counts.reshape(rays.n, 2)

@@ -495,7 +495,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 6; }
+int ref_fn_version() { return 7; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -788,6 +788,38 @@ void ref_fn_rgbe_roundtrip(const float *in, size_t n, float *out) {
     s.fromRGBE(rgbe);
     putS(out + 3 * i, s);
   }
+}
+
+// sppm primal photon planes: PhotonPlaneQuery::operator() (photonmapper/plane_struct.h:238-256) on every (camera beam,
+// plane) pair in plane order.  out: [n_rays * 3] = Li (the caller multiplies by beam.weight); counts: [n_rays * 2] =
+// planes hit, and 0.
+int ref_fn_sppm_planes_gather(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_ray_soa *ry, size_t n_rays,
+                              const gvpm_medium *med, const gvpm_config *cfg, float *out, uint32_t *counts) {
+  World W;
+  W.common(med, cfg, NULL, 0, EVolPlane0D);
+  std::vector<LTPhotonPlane> planes(n_planes);
+  for (size_t j = 0; j < n_planes; ++j) {
+    LTPhotonPlane &p = planes[j];
+    p._ori = P3(ps->origin + 3 * j);
+    p._w0 = V3f(ps->w0 + 3 * j);
+    p._length0 = ps->length0[j];
+    p._w1 = V3f(ps->w1 + 3 * j);
+    p._length1 = ps->length1[j];
+    p.medium = W.medium.get();
+    p._flux = S3(ps->flux + 3 * j);
+    p.depth = p.edgeID = ps->edge_id[j];
+    p.path = NULL;
+    p.pathID = 0;
+  }
+  for (size_t r = 0; r < n_rays; ++r) {
+    if (counts) counts[2 * r] = counts[2 * r + 1] = 0;
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    PhotonPlaneQuery q(ray, W.medium.get(), -1, 0, NULL, EVolPlane0D);
+    for (size_t j = 0; j < n_planes; ++j)
+      if (q(&planes[j]) && counts) ++counts[2 * r];
+    putS(out + 3 * r, q.Li);
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -142,6 +142,16 @@ PLANES = {
 }
 
 
+SPPM_PLANES = ("default", "hg_forward_0.3", "sensor_outside", "collimated_sheet")
+
+
+def sppm_planes_case(name):
+    """sppm primal planes: the same records with no valid offset edge (the gather's primal is PhotonPlaneQuery)."""
+    c = planes_case(name)
+    c.rays.off_valid[:] = 0
+    return c
+
+
 def planes_case(name):
     kw, post = PLANES[name]
     kw = dict(dict(n_planes=1200, w=16, h=12), **kw)

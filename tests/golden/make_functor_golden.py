@@ -72,6 +72,11 @@ if __name__ == "__main__":
         out[f"sppmbre_{name}_bits"], out[f"sppmbre_{name}_flux_bits"] = cases.bits(res), cases.bits(c.photons.flux)
         out[f"sppmbre_{name}_crc"] = cases.input_crc(c)
         print(f"sppm bre {name:24s} non-zero outputs {np.count_nonzero(res):5d}")
+    for name in cases.SPPM_PLANES:
+        c = cases.sppm_planes_case(name)
+        res, counts = fb.sppm_planes_gather(c.planes, c.rays, c.medium, c.config)
+        out[f"sppmplanes_{name}_bits"], out[f"sppmplanes_{name}_hits"] = cases.bits(res), counts[:, 0]
+        print(f"sppm planes {name:18s} hits {int(counts[:, 0].sum()):6d}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -152,6 +152,18 @@ def test_sppm_beam_functor_equals_reference_golden(built, golden, name, tech):
         np.testing.assert_allclose(res.out, ref, rtol=2e-6, atol=0)
 
 
+@pytest.mark.parametrize("name", cases.SPPM_PLANES)
+def test_sppm_plane_functor_equals_reference_golden(built, golden, name):
+    """sppm's PhotonPlaneQuery::operator() (photonmapper/plane_struct.h:238-256): the plane gather with no valid offset edge
+    yields it as its primal, bit for bit; nothing else is accumulated."""
+    c = cases.sppm_planes_case(name)
+    res = ob.planes_gather(c.planes, c.rays, c.medium, c.config, mode="brute", threads=2)
+    np.testing.assert_array_equal(res.counts[:, 0], golden[f"sppmplanes_{name}_hits"])
+    _same_rows(cases.bits(res.out[:, :3].copy()), golden[f"sppmplanes_{name}_bits"], f"sppm plane functor, case {name}")
+    assert not res.out[:, 3:15].any()                       # no shifted contribution
+    assert np.count_nonzero(golden[f"sppmplanes_{name}_bits"]) > 100
+
+
 def _sppm_bre_case(golden, name):
     flux = golden[f"sppmbre_{name}_flux_bits"].view(np.float32)     # the photons' power after the reference's RGBE round trip
     c = cases.sppm_bre_case(name, quantise=lambda f: flux)
