@@ -2,7 +2,10 @@
 """bench.py — one G-BRE 3D mixed-shift gather iteration per step (BASELINE.json configs[4]).
 
     python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
-    python bench.py --impl reference ...                     CPU arm: the oracle restatement on host cores
+    python bench.py --impl reference ...                     CPU arm: the reference's own compiled G-BRE path on host cores
+                                                             (oracle/_ref/libgvpm_functor_ref.so; the oracle restatement when
+                                                             that library or the memory for it is missing, and for the other
+                                                             techniques)
 
 Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M photons per iteration,
 G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
@@ -311,6 +314,108 @@ def cpu_arm(args, inp, seconds):
                       f"whole-image gather at the measured rate)"}, ms1, n1
 
 
+def reference_code_available(inp):
+    """Can the reference's OWN compiled G-BRE path (oracle/_ref/libgvpm_functor_ref.so: GPhotonMap::build,
+    GradientBeamRadianceEstimator, bre->query, VolumeGradientBREQuery; built from /root/reference where that tree exists and
+    shipped with the repo snapshot) be timed on this box?  It keeps one light-path record per photon like the reference
+    does (~1.3 KB per photon here)."""
+    if os.environ.get("GVPM_REFERENCE_ARM", "code") == "port":
+        return False, "GVPM_REFERENCE_ARM=port"
+    try:
+        from oracle import functor_binding as fb
+        if not fb.have_ref():
+            return False, "oracle/_ref/libgvpm_functor_ref.so absent"
+        fb.load()
+    except Exception as e:  # noqa: BLE001
+        return False, f"reference library does not load: {e}"
+    need = 1.6e3 * inp["photons"].n * 1.5
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        avail = None
+    if avail is not None and avail < need:
+        return False, f"host memory: {avail / 1e9:.0f} GB available, {need / 1e9:.0f} GB wanted"
+    return True, ""
+
+
+def reference_code_arm(args, inp, seconds):
+    """The reference's own compiled code on all host cores, on the same bounded sample as cpu_arm (whole 1024-ray tiles
+    spread evenly over the image, against ALL photons): kd build and hierarchy once (single-threaded, as compiled here:
+    Mitsuba's parallel kd build needs its scheduler), then bre->query + the shift functor per sampled ray on `cores`
+    threads (the reference: BlockScheduler over image blocks)."""
+    from oracle import binding as ob
+    from oracle import functor_binding as fb
+    cores = ob.hw_threads()
+    ph, rays = inp["photons"], inp["rays"]
+    st = inp.setdefault("ref_code", {})
+    if "pass" not in st:
+        st["pass"] = fb.BrePass(ph, inp["medium"], inp["cfg"], inp["tri"], inp["radius"], threads=cores)
+    bp = st["pass"]
+    n_tiles = max(1, rays.n // 1024)
+
+    def run(tile_ids, threads=None, want_out=False):
+        idx = (np.asarray(tile_ids)[:, None] * 1024 + np.arange(1024)[None, :]).reshape(-1)
+        idx = idx[idx < rays.n]
+        sub = rays.take(idx)
+        out, calls, ms = bp.run(sub, threads=threads or cores, want_out=want_out)
+        return sub, out, calls, ms
+
+    pilot_tiles = np.unique(np.linspace(0, n_tiles - 1, num=min(n_tiles, max(8, cores // 4)), dtype=np.int64))
+    sub0, _, _, ms0 = run(pilot_tiles)
+    rate = sub0.n / max(ms0, 1e-3) * 1e3
+    want = int(min(n_tiles, max(len(pilot_tiles), rate * seconds / 1024)))
+    tiles = np.unique(np.linspace(0, n_tiles - 1, num=want, dtype=np.int64))
+    sub1, _, calls1, ms1 = run(tiles)
+    if "single" not in st:     # single-thread figure + agreement with the restated port, once, on a slice of the sample
+        k1 = max(2, len(tiles) // max(2 * cores, 1))
+        check_tiles = tiles[::max(1, len(tiles) // k1)][:k1]
+        subs, outs, _, mss = run(check_tiles, threads=1, want_out=True)
+        st["single"] = subs.n / max(mss, 1e-3) * 1e3
+        if os.environ.get("GVPM_REFERENCE_CHECK", "1") != "0":
+            lib = ob.load() if ob._lib is not None else (ob.prefer_native(), ob.load())[1]
+            from gvpm_b200 import _native as N
+            cph, cr = ph.as_c(), subs.as_c()
+            tree = lib.gvpm_oracle_tree_build(C.byref(cph), ph.n, inp["radius"], 0)
+            po = np.zeros(subs.n * 27, dtype=np.float32)
+            pms = C.c_double(0)
+            tri = inp["tri"]
+            for th, key in ((1, "port_single_thread_value"), (cores, "port_value")):
+                rc = lib.gvpm_oracle_bre(tree, C.byref(cph), ph.n, C.byref(cr), 0, subs.n, C.byref(inp["medium"]),
+                                         C.byref(inp["cfg"]), tri.ctypes.data_as(N.f32p), tri.size // 9, inp["radius"], 0,
+                                         th, po.ctypes.data_as(N.f32p), None, None, None, 0, C.byref(pms))
+                assert rc >= 0
+                st[key] = subs.n / max(pms.value, 1e-3) * 1e3
+            st["port_build_ms"] = lib.gvpm_oracle_tree_build_ms(tree)
+            lib.gvpm_oracle_tree_free(tree)
+            _, _, _, msm = run(check_tiles)
+            st["same_rays_value"] = subs.n / max(msm, 1e-3) * 1e3
+            po = po.reshape(-1, 27)
+            scale = np.abs(outs).max(axis=1, keepdims=True)
+            err = np.abs(po - outs) / np.maximum(np.abs(outs), np.where(scale > 0, 1e-3 * scale, 1.0))
+            st["port_max_rel_diff"] = float(err.max())
+            st["check_rays"] = int(subs.n)
+    rate = sub1.n / ms1 * 1e3
+    r_full = float(inp.get("rays_full_n", rays.n))
+    build_ms = bp.kd_build_ms + bp.hierarchy_ms
+    cb = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "reference",
+          "flags": "-O2 -ffp-contract=off, SINGLE_PRECISION SPECTRUM_SAMPLES=3 (oracle/Makefile, target functor_ref)",
+          "build_ms": build_ms, "kd_build_ms": bp.kd_build_ms, "hierarchy_ms": bp.hierarchy_ms,
+          "gather_ms_sample": ms1, "functor_calls_per_ray": float(calls1.mean()), "single_thread_value": st["single"],
+          "iteration_value_including_build": r_full / (build_ms * 1e-3 + r_full / rate),
+          "sample": f"{sub1.n} rays ({len(tiles)} of {n_tiles} 1024-ray tiles spread over the image) against all {ph.n} "
+                    f"photons, on the reference's own compiled code (GPhotonMap::build, GradientBeamRadianceEstimator, "
+                    f"bre->query, VolumeGradientBREQuery: oracle/_ref/libgvpm_functor_ref.so); gather only ({ms1:.0f} ms); "
+                    f"kd build {bp.kd_build_ms:.0f} ms + hierarchy {bp.hierarchy_ms:.0f} ms single-threaded, not included in "
+                    f"`value`"}
+    if "port_value" in st:
+        cb["restated_port_on_same_rays"] = {
+            "rays": st["check_rays"], "reference_value": st["same_rays_value"], "port_value": st["port_value"],
+            "reference_single_thread_value": st["single"], "port_single_thread_value": st["port_single_thread_value"],
+            "port_build_ms": st["port_build_ms"], "max_rel_diff": st["port_max_rel_diff"]}
+    return cb, ms1, sub1.n
+
+
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -322,8 +427,13 @@ def reference_main(args):
     per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
     cb = None
+    use_code, why_not = reference_code_available(inp)
     for i in range(args.warmup + args.steps):
-        cb, ms, n = cpu_arm(args, inp, per)
+        if use_code:
+            cb, ms, n = reference_code_arm(args, inp, per)
+        else:
+            cb, ms, n = cpu_arm(args, inp, per)
+            cb["reference_code_not_timed"] = why_not
         if i >= args.warmup:
             vals.append((n, ms))
     n_tot = sum(v[0] for v in vals)

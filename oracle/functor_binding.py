@@ -57,6 +57,17 @@ def load():
         _lib.ref_fn_sppm_planes_gather.restype = C.c_int
         _lib.ref_fn_sppm_planes_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                    N.f32p, N.u32p]
+        _lib.ref_fn_bre_pass.restype = C.c_int
+        _lib.ref_fn_bre_pass.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         N.f32p, C.c_size_t, C.c_float, C.c_int, N.f32p, N.u32p, C.POINTER(C.c_double)]
+        _lib.ref_fn_bre_open.restype = C.c_void_p
+        _lib.ref_fn_bre_open.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p, C.c_size_t, C.c_float,
+                                         C.c_int, C.POINTER(C.c_double)]
+        _lib.ref_fn_bre_run.restype = C.c_int
+        _lib.ref_fn_bre_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, N.f32p, N.u32p,
+                                        C.POINTER(C.c_double)]
+        _lib.ref_fn_bre_close.restype = None
+        _lib.ref_fn_bre_close.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -217,3 +228,58 @@ def sppm_planes_gather(planes, rays, medium, config):
     if rc != 0:
         raise RuntimeError(f"ref_fn_sppm_planes_gather refused the input: {rc}")
     return out.reshape(rays.n, 3), counts.reshape(rays.n, 2)
+
+
+def bre_pass(photons, rays, medium, config, tri, radius, threads=1, begin=0, end=None):
+    """The whole G-BRE gather pass on the reference's own code: GPhotonMap::build + GradientBeamRadianceEstimator +
+    bre->query + VolumeGradientBREQuery per camera segment (gvpm.cpp:994-1042), rays [begin, end).  Returns
+    (out [m, 27], functor calls [m], (kd build ms, hierarchy ms, gather ms))."""
+    lib = load()
+    end = rays.n if end is None else end
+    cph, cr = photons.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    m = end - begin
+    out = np.zeros(m * 27, dtype=np.float32)
+    counts = np.zeros(m, dtype=np.uint32)
+    times = (C.c_double * 3)()
+    rc = lib.ref_fn_bre_pass(C.byref(cph), photons.n, C.byref(cr), begin, end, C.byref(medium), C.byref(config),
+                             tri.ctypes.data_as(N.f32p), tri.size // 9, radius, threads, out.ctypes.data_as(N.f32p),
+                             counts.ctypes.data_as(N.u32p), times)
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_bre_pass refused the input: {rc}")
+    return out.reshape(m, 27), counts, tuple(times)
+
+
+class BrePass:
+    """The reference's own G-BRE structures over one photon set, kept between gathers (bench.py's reference arm):
+    GPhotonMap::build + GradientBeamRadianceEstimator once, then bre->query + VolumeGradientBREQuery per sampled ray."""
+
+    def __init__(self, photons, medium, config, tri, radius, threads=1):
+        self.lib = load()
+        cph = photons.as_c()
+        tri = np.ascontiguousarray(tri, dtype=np.float32)
+        times = (C.c_double * 3)()
+        self.h = self.lib.ref_fn_bre_open(C.byref(cph), photons.n, C.byref(medium), C.byref(config),
+                                          tri.ctypes.data_as(N.f32p), tri.size // 9, radius, threads, times)
+        if not self.h:
+            raise RuntimeError("ref_fn_bre_open refused the input")
+        self.records_ms, self.kd_build_ms, self.hierarchy_ms = times[0], times[1], times[2]
+
+    def run(self, rays, threads=1, begin=0, end=None, want_out=True):
+        end = rays.n if end is None else end
+        cr = rays.as_c()
+        m = end - begin
+        out = np.zeros(m * 27, dtype=np.float32) if want_out else None
+        counts = np.zeros(m, dtype=np.uint32)
+        ms = C.c_double(0)
+        rc = self.lib.ref_fn_bre_run(self.h, C.byref(cr), begin, end, threads,
+                                     out.ctypes.data_as(N.f32p) if want_out else None, counts.ctypes.data_as(N.u32p),
+                                     C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"ref_fn_bre_run refused the input: {rc}")
+        return (out.reshape(m, 27) if want_out else None), counts, ms.value
+
+    def close(self):
+        if self.h:
+            self.lib.ref_fn_bre_close(self.h)
+            self.h = None

@@ -72,6 +72,7 @@
 #include <mitsuba/render/film.h>
 #include <mitsuba/bidir/path.h>
 #include <mitsuba/render/sampler.h>
+#include "gvpm/gvpm_accel.h"
 #include "gvpm/shift/shift_volume_photon.h"
 #include "gvpm/shift/shift_volume_beams.h"
 #include "gvpm/gvpm_plane.h"
@@ -118,17 +119,23 @@ struct World {
   Scene *scene = nullptr;
   GPMThreadData *thdata = nullptr;
   GPMConfig config;
-  std::vector<LightPath> lps;
+  int buildThreads = 1;
+  std::vector<PathVertex> vArena;
+  std::vector<PathEdge> eArena;
+  std::vector<Path> paths;
+  PathVertex unitEmitter, unitMedium;
+  PathEdge unitEdge;
+  std::map<std::array<uint32_t, 3>, std::pair<ref<BSDF>, ref<HarnessShape>>> bsdfCache;
   std::vector<GPhotonNodeKD> nodes;
 
   ~World() {
-    for (auto &L : lps) { L.path.m_vertices.clear(); L.path.m_edges.clear(); }   // they point into L.v / L.e
+    for (auto &p : paths) { p.m_vertices.clear(); p.m_edges.clear(); }   // they point into the arenas
   }
 
   int build(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
             size_t n_tri, EVolumeTechnique technique) {
     common(med, cfg, tri, n_tri, technique);
-    return photonPaths(ph, n_ph, med);
+    return photonPaths(ph, n_ph, med, buildThreads);
   }
 
   void common(const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri, EVolumeTechnique technique) {
@@ -170,121 +177,143 @@ struct World {
     VertexClassifier::roughnessThreshold = 0.05f;   // bounceRoughness default (gvpm_struct.h:236)
   }
 
-  // one light Path + kd node per photon
-  int photonPaths(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med) {
-    lps.resize(n_ph);
+  // One light Path + kd node per photon.  Per photon four vertices of its own (supernode carrying the prefix weight,
+  // predecessor, parent, the photon's vertex) and the edge that carries it; the vertices in between, which the functor
+  // only classifies and multiplies in as unit weights, are shared unit records.  Diffuse BSDFs are shared per albedo.
+  int photonPaths(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, int threads = 1) {
+    for (size_t i = 0; i < n_ph; ++i) {
+      const size_t c = (size_t)ph->depth[i] + 1;   // vertexId
+      if (c < 2) return -2;
+      const int ptype = ph->parent_type[i];
+      if ((ptype == 0) != (c == 2)) return -3;     // the emitter sample is vertex 1: parent of the photons with vertexId 2 only
+      if (ptype > 2) return -4;                    // GVPM_PARENT_OTHER: manifold shift, out of scope
+      if (ptype == 1) {
+        std::array<uint32_t, 3> key;
+        std::memcpy(key.data(), ph->parent_albedo + 3 * i, 12);
+        if (!bsdfCache.count(key)) {
+          ref<BSDF> b = makeDiffuse(ph->parent_albedo + 3 * i);
+          bsdfCache[key] = std::make_pair(b, ref<HarnessShape>(new HarnessShape(b.get())));
+        }
+      }
+    }
+    vArena.resize(4 * n_ph);
+    eArena.resize(n_ph);
+    paths.resize(n_ph);
     nodes.resize(n_ph);
-    const gvpm_medium *medp = med;
-  for (size_t i = 0; i < n_ph; ++i) {
-    LightPath &L = lps[i];
-    const size_t c = (size_t)ph->depth[i] + 1;   // vertexId
-    if (c < 2) return -2;
-    const int ptype = ph->parent_type[i];
-    if ((ptype == 0) != (c == 2)) return -3;     // the emitter sample is vertex 1: parent of the photons with vertexId 2 only
-    L.v.resize(c + 1);
-    L.e.resize(c);
-    for (auto &x : L.v) zero(x);
-    for (auto &x : L.e) zero(x);
-    // prefix: vertex(0).weight * rr * edge(0).weight * prod_{1 <= i < c-1} (...) = prefix_flux (every other factor is 1)
-    L.v[0].type = PathVertex::EEmitterSupernode;
-    L.v[0].weight[EImportance] = S3(ph->prefix_flux + 3 * i);
-    for (size_t k = 0; k < c; ++k) { L.e[k].weight[EImportance] = Spectrum(1.f); L.e[k].medium = medium.get(); }
-    for (size_t k = 1; k <= c; ++k) L.v[k].weight[EImportance] = Spectrum(1.f);
-    const Point pos = P3(ph->pos + 3 * i), parent = P3(ph->parent_pos + 3 * i), pred = P3(ph->pred_pos + 3 * i);
-    const Normal nrm(V3f(ph->parent_n + 3 * i));
-    // vertex 1 is always the emitter sample (getTypeShift walks back to it: the classifier calls it diffuse,
-    // gvpm_struct.h:71, so a light path always has a reconnectable vertex); vertices 2 .. c-3 carry nothing else the
-    // functor reads (medium interactions, classified by the phase function's mean cosine); the predecessor (c-2) its
-    // position
-    if (c >= 3) {
-      L.v[1].type = PathVertex::EEmitterSample;
-      PositionSamplingRecord &pr = L.v[1].getPositionSamplingRecord();
+    zero(unitEmitter);
+    unitEmitter.type = PathVertex::EEmitterSample;
+    unitEmitter.weight[EImportance] = Spectrum(1.f);
+    {
+      PositionSamplingRecord &pr = unitEmitter.getPositionSamplingRecord();
       new (&pr) PositionSamplingRecord();
-      pr.p = pred;
       pr.measure = EArea;
       pr.object = em.get();
     }
-    for (size_t k = 2; k + 2 < c; ++k) {
-      L.v[k].type = PathVertex::EMediumInteraction;
-      MediumSamplingRecord &m = L.v[k].getMediumSamplingRecord();
+    zero(unitMedium);
+    unitMedium.type = PathVertex::EMediumInteraction;
+    unitMedium.weight[EImportance] = Spectrum(1.f);
+    {
+      MediumSamplingRecord &m = unitMedium.getMediumSamplingRecord();
       new (&m) MediumSamplingRecord();
-      m.p = pred;
       m.medium = medium.get();
     }
-    if (c >= 3) {
-      PathVertex &q = L.v[c - 2];
-      if (c - 2 == 1) {
-        q.type = PathVertex::EEmitterSample;
-        PositionSamplingRecord &pr = q.getPositionSamplingRecord();
+    zero(unitEdge);
+    unitEdge.weight[EImportance] = Spectrum(1.f);
+    unitEdge.medium = medium.get();
+
+    auto one = [&](size_t i) {
+      const size_t c = (size_t)ph->depth[i] + 1;
+      const int ptype = ph->parent_type[i];
+      PathVertex &v0 = vArena[4 * i], &vp = vArena[4 * i + 1], &v = vArena[4 * i + 2], &pv = vArena[4 * i + 3];
+      PathEdge &pe = eArena[i];
+      zero(v0); zero(vp); zero(v); zero(pv); zero(pe);
+      // prefix: vertex(0).weight * rr * edge(0).weight * prod_{1 <= k < c-1} (...) = prefix_flux (every other factor is 1)
+      v0.type = PathVertex::EEmitterSupernode;
+      v0.weight[EImportance] = S3(ph->prefix_flux + 3 * i);
+      vp.weight[EImportance] = v.weight[EImportance] = pv.weight[EImportance] = Spectrum(1.f);
+      const Point pos = P3(ph->pos + 3 * i), parent = P3(ph->parent_pos + 3 * i), pred = P3(ph->pred_pos + 3 * i);
+      const Normal nrm(V3f(ph->parent_n + 3 * i));
+      // the predecessor (c-2) carries its position; it is the emitter sample when c = 3 (vertex 1 is always the emitter
+      // sample: getTypeShift walks back to it and the classifier calls it diffuse, gvpm_struct.h:71)
+      if (c == 3) {
+        vp.type = PathVertex::EEmitterSample;
+        PositionSamplingRecord &pr = vp.getPositionSamplingRecord();
         new (&pr) PositionSamplingRecord();
         pr.p = pred;
         pr.measure = EArea;
         pr.object = em.get();
-      } else {
-        q.type = PathVertex::EMediumInteraction;
-        MediumSamplingRecord &m = q.getMediumSamplingRecord();
+      } else if (c > 3) {
+        vp.type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = vp.getMediumSamplingRecord();
         new (&m) MediumSamplingRecord();
         m.p = pred;
         m.medium = medium.get();
       }
-    }
-    // parent vertex (c-1)
-    PathVertex &v = L.v[c - 1];
-    v.pdf[EImportance] = ph->parent_pdf[i];
-    v.rrWeight = ph->rr_weight[i];
-    if (ptype == 1) {
-      v.type = PathVertex::ESurfaceInteraction;
-      Intersection &its = v.getIntersection();
-      new (&its) Intersection();
-      its.p = parent;
-      its.geoFrame = Frame(nrm);
-      its.shFrame = its.geoFrame;
-      L.bsdfs.push_back(makeDiffuse(ph->parent_albedo + 3 * i));
-      L.shapes.push_back(new HarnessShape(L.bsdfs.back().get()));
-      its.shape = L.shapes.back().get();
-      its.wi = its.toLocal(normalize(pred - parent));
-      its.t = 1.f;
-    } else if (ptype == 2) {
-      v.type = PathVertex::EMediumInteraction;
-      MediumSamplingRecord &m = v.getMediumSamplingRecord();
-      new (&m) MediumSamplingRecord();
-      m.p = parent;
-      m.medium = medium.get();
-      m.sigmaS = S3(med->sigma_s);
-      m.sigmaA = S3(med->sigma_a);
-    } else if (ptype == 0) {
-      v.type = PathVertex::EEmitterSample;
-      PositionSamplingRecord &pr = v.getPositionSamplingRecord();
-      new (&pr) PositionSamplingRecord();
-      pr.p = parent;
-      pr.n = nrm;
-      pr.measure = EArea;
-      pr.object = em.get();
+      // parent vertex (c-1)
+      v.pdf[EImportance] = ph->parent_pdf[i];
+      v.rrWeight = ph->rr_weight[i];
+      if (ptype == 1) {
+        v.type = PathVertex::ESurfaceInteraction;
+        Intersection &its = v.getIntersection();
+        new (&its) Intersection();
+        its.p = parent;
+        its.geoFrame = Frame(nrm);
+        its.shFrame = its.geoFrame;
+        std::array<uint32_t, 3> key;
+        std::memcpy(key.data(), ph->parent_albedo + 3 * i, 12);
+        its.shape = bsdfCache.find(key)->second.second.get();
+        its.wi = its.toLocal(normalize(pred - parent));
+        its.t = 1.f;
+      } else if (ptype == 2) {
+        v.type = PathVertex::EMediumInteraction;
+        MediumSamplingRecord &m = v.getMediumSamplingRecord();
+        new (&m) MediumSamplingRecord();
+        m.p = parent;
+        m.medium = medium.get();
+        m.sigmaS = S3(med->sigma_s);
+        m.sigmaA = S3(med->sigma_a);
+      } else {
+        v.type = PathVertex::EEmitterSample;
+        PositionSamplingRecord &pr = v.getPositionSamplingRecord();
+        new (&pr) PositionSamplingRecord();
+        pr.p = parent;
+        pr.n = nrm;
+        pr.measure = EArea;
+        pr.object = em.get();
+      }
+      // the photon's own vertex and the edge that carries it
+      pv.type = PathVertex::EMediumInteraction;
+      MediumSamplingRecord &pm = pv.getMediumSamplingRecord();
+      new (&pm) MediumSamplingRecord();
+      pm.p = pos;
+      pm.medium = medium.get();
+      pm.sigmaS = S3(med->sigma_s);
+      pm.sigmaA = S3(med->sigma_a);
+      Vector d = pos - parent;
+      pe.weight[EImportance] = Spectrum(1.f);
+      pe.medium = medium.get();
+      pe.length = d.length();
+      pe.d = d / pe.length;   // what the tracer stores; the flattened form recomputes wi = normalize(parent - pos) = -d
+      pe.pdf[EImportance] = ph->edge_pdf[i];
+      Path &path = paths[i];
+      for (size_t k = 0; k <= c; ++k) {
+        PathVertex *vk = k == 0 ? &v0 : k == c ? &pv : k == c - 1 ? &v : k == c - 2 ? &vp : k == 1 ? &unitEmitter : &unitMedium;
+        path.append(vk);
+        if (k < c) path.append(k == c - 1 ? &pe : &unitEdge);
+      }
+      nodes[i].setPosition(pos);
+      nodes[i].setData(GPhotonNodeData(&path, (int)c, S3(ph->flux + 3 * i), ph->path_id[i]));
+    };
+    if (threads <= 1 || n_ph < 4096) {
+      for (size_t i = 0; i < n_ph; ++i) one(i);
     } else {
-      return -4;   // GVPM_PARENT_OTHER: manifold shift, out of scope
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t]() {
+          for (size_t i = n_ph * t / threads, e_ = n_ph * (t + 1) / threads; i < e_; ++i) one(i);
+        });
+      for (auto &t : pool) t.join();
     }
-    // the photon's own vertex and the edge that carries it
-    PathVertex &pv = L.v[c];
-    pv.type = PathVertex::EMediumInteraction;
-    MediumSamplingRecord &pm = pv.getMediumSamplingRecord();
-    new (&pm) MediumSamplingRecord();
-    pm.p = pos;
-    pm.medium = medium.get();
-    pm.sigmaS = S3(med->sigma_s);
-    pm.sigmaA = S3(med->sigma_a);
-    PathEdge &pe = L.e[c - 1];
-    Vector d = pos - parent;
-    pe.length = d.length();
-    pe.d = d / pe.length;   // what the tracer stores; the flattened form recomputes wi = normalize(parent - pos) = -d
-    pe.pdf[EImportance] = ph->edge_pdf[i];
-    for (size_t k = 0; k <= c; ++k) {
-      L.path.append(&L.v[k]);
-      if (k < c) L.path.append(&L.e[k]);
-    }
-    nodes[i].setPosition(pos);
-    nodes[i].setData(GPhotonNodeData(&L.path, (int)c, S3(ph->flux + 3 * i), ph->path_id[i]));
-  }
-    (void)medp;
     return 0;
   }
 };
@@ -467,7 +496,10 @@ struct CameraSide {
     info[e - 1].weight = weightBeam;   // getWeightBeam(e - 1); getWeightVertex(e) = 1
     info[e].pdf = sensorPdf;           // sensorMIS(e, base, ., .) = (pdf / base pdf) * jacobian [* terms that cancel, e > 1]
   }
+  // may be called again on the same object (bench: one CameraSide per worker thread, no allocation per ray)
   void build(const gvpm_ray_soa *ry, size_t r, const Medium *mediumPtr) {
+    gp.path.m_vertices.clear(); gp.path.m_edges.clear();
+    for (auto &s : shiftGPs) { s.path.m_vertices.clear(); s.path.m_edges.clear(); }
     const size_t e = (size_t)ry->edge_id[r];
     const Point o = P3(ry->o + 3 * r);
     const Vector d = V3f(ry->d + 3 * r);
@@ -495,7 +527,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 7; }
+int ref_fn_version() { return 9; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -820,6 +852,114 @@ int ref_fn_sppm_planes_gather(const gvpm_plane_soa *ps, size_t n_planes, const g
     putS(out + 3 * r, q.Li);
   }
   return 0;
+}
+
+// G-BRE, the whole gather pass on the reference's own code: GPhotonMap::build (PointKDTree, sliding midpoint) +
+// GradientBeamRadianceEstimator (hierarchy) + bre->query (traversal, neighbour predicate) + VolumeGradientBREQuery (functor)
+// per camera segment, i.e. computeVolumeGradientPhotonBRE's inner loop (gvpm.cpp:994-1042) without its per-pass
+// normalisation.  Photons enter the map through the protected kd-tree (tryAppend walks whole light paths).  Rays are
+// split over `threads` std::threads (the reference: BlockScheduler over image blocks).  Sums are in traversal order.
+// times_ms: [3] = kd build, hierarchy, gather.
+namespace {
+class FunctorMap : public GPhotonMap {
+public:
+  explicit FunctorMap(size_t n) : GPhotonMap(n, false, Point(0.f), 0.f) {}
+  void add(const GPhotonNodeKD &node) { m_kdtree.push_back(node); }
+};
+double nowMs() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+// Persistent form (bench.py's reference arm: one build, many sampled gathers).
+struct BrePass {
+  World W;
+  ref<FunctorMap> map;
+  ref<GradientBeamRadianceEstimator> bre;
+  float radius = 0;
+};
+
+// times_ms: [3] = light-path records (harness work, not the reference's), kd build, hierarchy
+void *ref_fn_bre_open(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
+                      size_t n_tri, float radius, int threads, double *times_ms) {
+  BrePass *P = new BrePass();
+  P->radius = radius;
+  P->W.buildThreads = threads;
+  double t0 = nowMs();
+  if (P->W.build(ph, n_ph, med, cfg, tri, n_tri, cfg->kernel_3d ? EVolBRE3D : EVolBRE2D)) { delete P; return NULL; }
+  double t1 = nowMs();
+  P->map = new FunctorMap(n_ph);
+  for (size_t i = 0; i < n_ph; ++i) P->map->add(P->W.nodes[i]);
+  std::vector<GPhotonNodeKD>().swap(P->W.nodes);                                                   // the map holds them now
+  P->map->build(true);                                                                             // gvpm.cpp:453
+  double t2 = nowMs();
+  P->bre = new GradientBeamRadianceEstimator(P->map.get(), radius);                                // gvpm.cpp:994
+  double t3 = nowMs();
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = t2 - t1; times_ms[2] = t3 - t2; }
+  return P;
+}
+
+void ref_fn_bre_close(void *h) { delete (BrePass *)h; }
+
+int ref_fn_bre_run(void *h, const gvpm_ray_soa *ry, size_t ray_begin, size_t ray_end, int threads, float *out,
+                   uint32_t *counts, double *gather_ms) {
+  BrePass *P = (BrePass *)h;
+  World &W = P->W;
+  for (size_t r = ray_begin; r < ray_end; ++r)
+    if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
+  const double t2 = nowMs();
+  std::atomic<size_t> next(ray_begin);
+  auto worker = [&]() {
+    CameraSide cam;
+    for (;;) {
+      const size_t b = next.fetch_add(256);
+      if (b >= ray_end) break;
+      const size_t e_ = std::min(ray_end, b + 256);
+      for (size_t r = b; r < e_; ++r) {
+        struct Counting : VolumeGradientBREQuery {
+          using VolumeGradientBREQuery::VolumeGradientBREQuery;
+          uint32_t calls = 0;
+          void operator()(const GPhotonNodeKD &n, Float rad, Float xi) { ++calls; VolumeGradientBREQuery::operator()(n, rad, xi); }
+        };
+        cam.build(ry, r, W.medium.get());
+        const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+        Counting gRec(W.scene, &cam.gp, W.config, *W.thdata, cam.shiftGPs, (size_t)ry->edge_id[r], NULL);
+        gRec.newRayBase(ray, W.medium.get());
+        gRec.clear();
+        P->bre->query(ray, W.medium.get(), gRec, ry->xi[r]);                                       // gvpm.cpp:1042
+        if (out) {
+          float *o = out + 27 * (r - ray_begin);
+          putS(o, gRec.mediumFlux);
+          for (int k = 0; k < 4; ++k) {
+            putS(o + 3 * (1 + k), gRec.shiftedMediumFlux[k]);
+            putS(o + 3 * (5 + k), gRec.weightedMediumFlux[k]);
+          }
+        }
+        if (counts) counts[r - ray_begin] = gRec.calls;
+      }
+    }
+  };
+  if (threads <= 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
+  }
+  if (gather_ms) *gather_ms = nowMs() - t2;
+  return 0;
+}
+
+int ref_fn_bre_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t ray_begin, size_t ray_end,
+                    const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, int threads,
+                    float *out, uint32_t *counts, double *times_ms) {
+  double tm[3] = {0, 0, 0}, g = 0;
+  void *h = ref_fn_bre_open(ph, n_ph, med, cfg, tri, n_tri, radius, 1, tm);
+  if (!h) return -2;
+  const int rc = ref_fn_bre_run(h, ry, ray_begin, ray_end, threads, out, counts, &g);
+  ref_fn_bre_close(h);
+  if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = tm[2]; times_ms[2] = g; }
+  return rc;
 }
 
 }  // extern "C"

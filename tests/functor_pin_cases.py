@@ -235,6 +235,10 @@ def edge2_case(kind, name):
     return c
 
 
+# The whole G-BRE pass on the reference's own code (kd build + hierarchy + traversal + functor), sums in traversal order.
+PASS = ["default", "wide", "hg_forward_0.7", "blocker_wide_hg", "big"]
+
+
 def input_crc(c):
     """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
     h = 0

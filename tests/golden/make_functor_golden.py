@@ -77,6 +77,11 @@ if __name__ == "__main__":
         res, counts = fb.sppm_planes_gather(c.planes, c.rays, c.medium, c.config)
         out[f"sppmplanes_{name}_bits"], out[f"sppmplanes_{name}_hits"] = cases.bits(res), counts[:, 0]
         print(f"sppm planes {name:18s} hits {int(counts[:, 0].sum()):6d}")
+    for name in cases.PASS:
+        c = cases.bre_case(name)
+        res, calls, _ = fb.bre_pass(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
+        out[f"pass_{name}_bits"], out[f"pass_{name}_calls"] = cases.bits(res), calls
+        print(f"pass {name:22s} functor calls {int(calls.sum()):7d}")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

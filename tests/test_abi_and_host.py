@@ -364,12 +364,20 @@ def test_sharded_gather_world2_gloo(tmp_path, mode):
     assert "GLOO_OK" in res.stdout
 
 
-def test_bench_reference_arm_contract_on_cpu():
+@pytest.mark.parametrize("arm", ["code", "port"])
+def test_bench_reference_arm_contract_on_cpu(arm):
     """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU: one JSON line with the
-    contract's keys, the oracle port on the host cores, e2e = value with zero copy bytes."""
+    contract's keys, e2e = value with zero copy bytes.  "code": the reference's own compiled G-BRE path
+    (oracle/_ref/libgvpm_functor_ref.so, kind "reference"; it also reports the restated port on the same rays and their
+    agreement); "port": the oracle restatement (what runs where that library is absent)."""
     import json
+    from oracle import functor_binding as fb
+    if arm == "code" and not fb.have_ref():
+        pytest.skip("prebuilt reference library absent")
+    env = dict(os.environ, GVPM_REFERENCE_ARM=arm)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
-                        "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300)
+                        "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=300,
+                       env=env)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["higher_is_better"] is True
@@ -378,5 +386,11 @@ def test_bench_reference_arm_contract_on_cpu():
         assert k in line, k
     assert line["value"] > 0 and line["vs_baseline"] is None and "workload" in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert cb["kind"] == ("reference" if arm == "code" else "port")
+    assert cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    if arm == "code":
+        chk = cb["restated_port_on_same_rays"]
+        assert chk["max_rel_diff"] < 2e-6 and chk["port_value"] > 0 and chk["reference_value"] > 0
+    else:
+        assert cb["reference_code_not_timed"] == "GVPM_REFERENCE_ARM=port"
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
