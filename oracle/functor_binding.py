@@ -68,6 +68,16 @@ def load():
                                         C.POINTER(C.c_double)]
         _lib.ref_fn_bre_close.restype = None
         _lib.ref_fn_bre_close.argtypes = [C.c_void_p]
+        _lib.ref_fn_beams_pass.restype = C.c_int
+        _lib.ref_fn_beams_pass.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p,
+                                           C.c_size_t, C.c_float, N.f32p, C.c_int, N.f32p, N.u32p, C.POINTER(C.c_double)]
+        _lib.ref_fn_planes_pass.restype = C.c_int
+        _lib.ref_fn_planes_pass.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int,
+                                            N.f32p, C.POINTER(C.c_double)]
+        _lib.ref_fn_vpm_pass.restype = C.c_int
+        _lib.ref_fn_vpm_pass.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_void_p, N.f32p, C.c_size_t, C.c_int, C.c_int, N.f32p, N.f32p,
+                                         C.POINTER(C.c_double)]
     return _lib
 
 
@@ -283,3 +293,51 @@ class BrePass:
         if self.h:
             self.lib.ref_fn_bre_close(self.h)
             self.h = None
+
+
+def beams_pass(beams, rays, medium, config, tri, radius, threads=1):
+    """The whole G-Beams pass on the reference's own code: SubBeamBVH<LTPhotonBeam> + BeamGradRadianceQuery per camera
+    segment (gvpm.cpp:893-941).  Returns (out [n_rays, 27], accepted calls [n_rays], (build ms, gather ms))."""
+    lib = load()
+    xi = beam_uniforms(beams, rays, medium, config)
+    cb, cr = beams.as_c(), rays.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    counts = np.zeros(rays.n * 2, dtype=np.uint32)
+    times = (C.c_double * 2)()
+    rc = lib.ref_fn_beams_pass(C.byref(cb), beams.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config),
+                               tri.ctypes.data_as(N.f32p), tri.size // 9, radius, xi.ctypes.data_as(N.f32p), threads,
+                               out.ctypes.data_as(N.f32p), counts.ctypes.data_as(N.u32p), times)
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_beams_pass refused the input: {rc}")
+    return out.reshape(rays.n, 27), counts.reshape(rays.n, 2)[:, 0], tuple(times)
+
+
+def planes_pass(planes, rays, medium, config, threads=1):
+    """The whole G-Planes pass on the reference's own code: PhotonPlaneBVH<LTPhotonPlane> + PlaneGradRadianceQuery."""
+    lib = load()
+    cp, cr = planes.as_c(), rays.as_c()
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    times = (C.c_double * 2)()
+    rc = lib.ref_fn_planes_pass(C.byref(cp), planes.n, C.byref(cr), rays.n, C.byref(medium), C.byref(config), threads,
+                                out.ctypes.data_as(N.f32p), times)
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_planes_pass refused the input: {rc}")
+    return out.reshape(rays.n, 27), tuple(times)
+
+
+def vpm_pass(photons, rays, samples, medium, config, tri, nb_camera_samples, threads=1):
+    """The whole G-VPM pass on the reference's own code: GPhotonMap::build + evaluate (PointKDTree range query) +
+    VolumeGradientDistanceQuery per distance sample, folded per pixel."""
+    lib = load()
+    cph, cr, cs = photons.as_c(), rays.as_c(), samples.as_c()
+    tri = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros(rays.n * 27, dtype=np.float32)
+    mvol = np.zeros(rays.n, dtype=np.float32)
+    times = (C.c_double * 2)()
+    rc = lib.ref_fn_vpm_pass(C.byref(cph), photons.n, C.byref(cr), rays.n, C.byref(cs), samples.n, C.byref(medium),
+                             C.byref(config), tri.ctypes.data_as(N.f32p), tri.size // 9, nb_camera_samples, threads,
+                             out.ctypes.data_as(N.f32p), mvol.ctypes.data_as(N.f32p), times)
+    if rc != 0:
+        raise RuntimeError(f"ref_fn_vpm_pass refused the input: {rc}")
+    return out.reshape(rays.n, 27), mvol, tuple(times)

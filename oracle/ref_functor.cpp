@@ -73,6 +73,8 @@
 #include <mitsuba/bidir/path.h>
 #include <mitsuba/render/sampler.h>
 #include "gvpm/gvpm_accel.h"
+#include "beams_accel.h"
+#include "plane_accel.h"
 #include "gvpm/shift/shift_volume_photon.h"
 #include "gvpm/shift/shift_volume_beams.h"
 #include "gvpm/gvpm_plane.h"
@@ -527,7 +529,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 9; }
+int ref_fn_version() { return 10; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -960,6 +962,181 @@ int ref_fn_bre_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *
   ref_fn_bre_close(h);
   if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = tm[2]; times_ms[2] = g; }
   return rc;
+}
+
+// ---- whole passes of the other techniques on the reference's own acceleration structures --------------------------------------
+// Each splits the rays over `threads` std::threads (the reference: BlockScheduler over image blocks) and sums in the
+// structure's traversal order.  times_ms: [2] = structure build, gather.
+}  // extern "C"
+
+namespace {
+template <class F> void parallelRays(size_t n, int threads, F f) {
+  std::atomic<size_t> next(0);
+  auto worker = [&]() {
+    CameraSide cam;
+    for (;;) {
+      const size_t b = next.fetch_add(64);
+      if (b >= n) break;
+      for (size_t r = b, e_ = std::min(n, b + 64); r < e_; ++r) f(r, cam);
+    }
+  };
+  if (threads <= 1) { worker(); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+  for (auto &t : pool) t.join();
+}
+void putAll(float *o, const Spectrum &m, const Spectrum *sh, const Spectrum *we) {
+  putS(o, m);
+  for (int k = 0; k < 4; ++k) { putS(o + 3 * (1 + k), sh[k]); putS(o + 3 * (5 + k), we[k]); }
+}
+}  // namespace
+
+extern "C" {
+
+// G-Beams: SubBeamBVH<LTPhotonBeam> (sub-beam split, kd-tree, hierarchy, beams_accel.h:90-243) + BeamGradRadianceQuery per
+// camera segment (gvpm.cpp:936-941).  The functor's two sampler draws are preset per (ray, beam) before each call.
+int ref_fn_beams_pass(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                      const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, const float *xi, int threads,
+                      float *out, uint32_t *counts, double *times_ms) {
+  World W;
+  W.common(med, cfg, tri, n_tri, cfg->beam_kernel_1d ? EBeamBeam1D : EBeamBeam3D_Optimized);
+  W.config.newShiftBeam = cfg->beam_kernel_1d != 0;
+  BeamWorld B;
+  if (int rc = B.build(W, bs, n_beams, med, cfg, radius)) return rc;
+  for (size_t r = 0; r < n_rays; ++r)
+    if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
+  const double t0 = nowMs();
+  std::vector<std::pair<int, LTPhotonBeam>> list;
+  list.reserve(n_beams);
+  for (size_t j = 0; j < n_beams; ++j) list.push_back(std::make_pair((int)j, B.beams[j]));
+  ref<SubBeamBVH<LTPhotonBeam>> bvh = new SubBeamBVH<LTPhotonBeam>(list);
+  const double t1 = nowMs();
+  const LTPhotonBeam *first = &list[0].second;
+  const size_t stride = sizeof(std::pair<int, LTPhotonBeam>);
+  parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
+    cam.build(ry, r, W.medium.get());
+    ref<PresetSampler> sampler = new PresetSampler();
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    BeamGradRadianceQuery gRec(W.scene, &cam.gp, cam.shiftGPs, ray, W.medium.get(), W.config, *W.thdata,
+                               (size_t)ry->edge_id[r], sampler.get());
+    struct Forward {
+      const Ray &baseCameraRay;
+      BeamGradRadianceQuery &q;
+      PresetSampler *s;
+      const float *xi;
+      const char *first;
+      size_t stride;
+      uint32_t accepted;
+      bool operator()(const LTPhotonBeam *b, Float t1_, Float t2_) {
+        const size_t j = (size_t)(((const char *)b - first) / stride);
+        s->preset(xi[2 * j], xi[2 * j + 1]);
+        const bool ok = q(b, t1_, t2_);
+        accepted += ok ? 1u : 0u;
+        return ok;
+      }
+    } fwd{ray, gRec, sampler.get(), xi + 2 * r * n_beams, (const char *)first, stride, 0u};
+    bvh->query(fwd);
+    putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
+    if (counts) { counts[2 * r] = fwd.accepted; counts[2 * r + 1] = 0; }
+  });
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return 0;
+}
+
+// G-Planes: PhotonPlaneBVH<LTPhotonPlane> (plane_accel.h:93-185) + PlaneGradRadianceQuery per camera segment (gvpm.cpp:837-841)
+int ref_fn_planes_pass(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                       const gvpm_config *cfg, int threads, float *out, double *times_ms) {
+  World W;
+  W.common(med, cfg, NULL, 0, EVolPlane0D);
+  std::vector<LTPhotonPlane> planes(n_planes);
+  for (size_t j = 0; j < n_planes; ++j) {
+    LTPhotonPlane &p = planes[j];
+    p._ori = P3(ps->origin + 3 * j);
+    p._w0 = V3f(ps->w0 + 3 * j);
+    p._length0 = ps->length0[j];
+    p._w1 = V3f(ps->w1 + 3 * j);
+    p._length1 = ps->length1[j];
+    p.medium = W.medium.get();
+    p._flux = S3(ps->flux + 3 * j);
+    p.depth = p.edgeID = ps->edge_id[j];
+    p.path = NULL;
+    p.pathID = 0;
+  }
+  for (size_t r = 0; r < n_rays; ++r)
+    if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
+  const double t0 = nowMs();
+  ref<PhotonPlaneBVH<LTPhotonPlane>> bvh = new PhotonPlaneBVH<LTPhotonPlane>(planes);
+  const double t1 = nowMs();
+  parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
+    cam.build(ry, r, W.medium.get());
+    const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
+    PlaneGradRadianceQuery gRec(W.scene, &cam.gp, cam.shiftGPs, ray, W.medium.get(), W.config, *W.thdata, ry->edge_id[r]);
+    bvh->query(gRec);
+    putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
+  });
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return 0;
+}
+
+// G-VPM: GPhotonMap::build + GPhotonMap::evaluate (PointKDTree range query) + VolumeGradientDistanceQuery per distance sample,
+// folded per pixel as gvpm.cpp:1175-1182.  Threads take whole pixels (the samples of a ray are consecutive in the table or
+// not: a first pass buckets them per ray, in table order).
+int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_vpm_sample_soa *smp,
+                    size_t n_smp, const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri,
+                    int nb_camera_samples, int threads, float *out, float *mvol, double *times_ms) {
+  World W;
+  W.buildThreads = threads;
+  if (int rc = W.build(ph, n_ph, med, cfg, tri, n_tri, EDistance)) return rc;
+  std::vector<std::vector<uint32_t>> perRay(n_rays);
+  for (size_t s = 0; s < n_smp; ++s) {
+    if (smp->ray[s] >= n_rays) return -6;
+    perRay[smp->ray[s]].push_back((uint32_t)s);
+  }
+  for (size_t r = 0; r < n_rays; ++r)
+    if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
+  const double t0 = nowMs();
+  ref<FunctorMap> map = new FunctorMap(n_ph);
+  for (size_t i = 0; i < n_ph; ++i) map->add(W.nodes[i]);
+  map->build(true);
+  const double t1 = nowMs();
+  const Float normalization = 1.f / nb_camera_samples;
+  parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
+    Spectrum flux(0.f), sh[4], we[4];
+    for (int k = 0; k < 4; ++k) sh[k] = we[k] = Spectrum(0.f);
+    float found = 0.f;
+    for (uint32_t s : perRay[r]) {
+      cam.build(ry, r, W.medium.get());
+      const size_t e = (size_t)ry->edge_id[r];
+      VolumeGradientDistanceQuery gRec(W.scene, &cam.gp, W.config, *W.thdata, cam.shiftGPs, 0, NULL);
+      gRec.changeEdge(e, smp->pdf_sel[s]);
+      Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->edge_len[r], 0.f);
+      MediumSamplingRecord mRec;
+      mRec.t = smp->t[s];
+      mRec.p = ray(mRec.t);
+      mRec.medium = W.medium.get();
+      mRec.sigmaS = S3(med->sigma_s);
+      mRec.sigmaA = S3(med->sigma_a);
+      mRec.transmittance = S3(smp->transmittance + 3 * s);
+      mRec.pdfSuccess = smp->pdf_success[s];
+      mRec.pdfSuccessRev = mRec.pdfSuccess;
+      mRec.pdfFailure = 0.f;
+      mRec.time = 0.f;
+      ray.maxt = mRec.t;
+      const Float querySize = smp->radius[s];
+      gRec.newRayBase(ray, mRec, querySize, mRec.pdfSuccess);
+      gRec.clear();
+      found += (float)map->evaluate(gRec, ray.o + mRec.t * ray.d, querySize);                      // gvpm.cpp:1175
+      flux += (gRec.mediumFlux * normalization);
+      for (int k = 0; k < 4; ++k) {
+        sh[k] += (gRec.shiftedMediumFlux[k] * normalization);
+        we[k] += (gRec.weightedMediumFlux[k] * normalization);
+      }
+    }
+    putAll(out + 27 * r, flux, sh, we);
+    mvol[r] = found;
+  });
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return 0;
 }
 
 }  // extern "C"

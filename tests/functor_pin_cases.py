@@ -237,6 +237,10 @@ def edge2_case(kind, name):
 
 # The whole G-BRE pass on the reference's own code (kd build + hierarchy + traversal + functor), sums in traversal order.
 PASS = ["default", "wide", "hg_forward_0.7", "blocker_wide_hg", "big"]
+# ... and of the other techniques on the reference's own structures (PointKDTree range query, SubBeamBVH, PhotonPlaneBVH)
+PASS_VPM = ["default", "wide", "hg_forward_0.7", "one_radius"]
+PASS_BEAMS = ["default", "beam1d", "blocker", "long_beams", "narrow"]
+PASS_PLANES = ["default", "hg_forward_0.3", "sensor_outside", "many"]
 
 
 def input_crc(c):

@@ -82,6 +82,19 @@ if __name__ == "__main__":
         res, calls, _ = fb.bre_pass(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
         out[f"pass_{name}_bits"], out[f"pass_{name}_calls"] = cases.bits(res), calls
         print(f"pass {name:22s} functor calls {int(calls.sum()):7d}")
+    for name in cases.PASS_VPM:
+        c = cases.vpm_case(name)
+        res, mvol, _ = fb.vpm_pass(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, threads=2)
+        out[f"passvpm_{name}_bits"], out[f"passvpm_{name}_mvol"] = cases.bits(res), mvol
+    for name in cases.PASS_BEAMS:
+        c = cases.beams_case(name)
+        res, acc, _ = fb.beams_pass(c.beams, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
+        out[f"passbeams_{name}_bits"], out[f"passbeams_{name}_accepted"] = cases.bits(res), acc
+    for name in cases.PASS_PLANES:
+        c = cases.planes_case(name)
+        res, _ = fb.planes_pass(c.planes, c.rays, c.medium, c.config, threads=2)
+        out[f"passplanes_{name}_bits"] = cases.bits(res)
+    print("whole passes of VPM / beams / planes written")
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "functor_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

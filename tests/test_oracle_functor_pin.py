@@ -217,6 +217,15 @@ def test_golden_vectors_are_what_the_reference_computes_now(built, golden):
         out, calls, _ = fb.bre_pass(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
         np.testing.assert_array_equal(cases.bits(out), golden[f"pass_{name}_bits"])
         np.testing.assert_array_equal(calls, golden[f"pass_{name}_calls"])
+    c = cases.vpm_case("wide")
+    out, mvol, _ = fb.vpm_pass(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, threads=2)
+    np.testing.assert_array_equal(cases.bits(out), golden["passvpm_wide_bits"])
+    c = cases.beams_case("blocker")
+    out, acc, _ = fb.beams_pass(c.beams, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
+    np.testing.assert_array_equal(cases.bits(out), golden["passbeams_blocker_bits"])
+    c = cases.planes_case("many")
+    out, _ = fb.planes_pass(c.planes, c.rays, c.medium, c.config, threads=2)
+    np.testing.assert_array_equal(cases.bits(out), golden["passplanes_many_bits"])
     for name in ("kernel_3d", "kernel_2d_hg_backward"):
         c = _sppm_bre_case(golden, name)
         np.testing.assert_array_equal(cases.bits(fb.rgbe_roundtrip(c.photons.flux)), cases.bits(c.photons.flux))
@@ -243,6 +252,39 @@ def test_whole_bre_pass_equals_reference_golden(built, golden, name):
     # the traversal reaches a few photons in the Epsilon sliver past the ray end that the brute-force set has too, and
     # sums in tree order: the functor-level vectors agree up to that order
     assert H.rel_err(res.out, golden[f"bre_{name}_bits"].view(np.float32)).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", cases.PASS_VPM)
+def test_whole_vpm_pass_equals_reference_golden(built, golden, name):
+    """GPhotonMap::build + GPhotonMap::evaluate (PointKDTree range query) + VolumeGradientDistanceQuery per distance sample,
+    folded per pixel (gvpm.cpp:1141-1185), against the oracle's reference-shaped mode: bit for bit, MVol included."""
+    c = cases.vpm_case(name)
+    res = ob.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, mode="kdtree", threads=2)
+    np.testing.assert_array_equal(res.mvol, golden[f"passvpm_{name}_mvol"])
+    _same_rows(cases.bits(res.out), golden[f"passvpm_{name}_bits"], f"whole G-VPM pass, case {name}")
+
+
+@pytest.mark.parametrize("name", cases.PASS_BEAMS)
+def test_whole_beam_pass_matches_reference_golden(built, golden, name):
+    """SubBeamBVH<LTPhotonBeam> (sub-beam split, kd-tree, hierarchy, beams_accel.h:90-243) + BeamGradRadianceQuery per camera
+    segment (gvpm.cpp:893-941): the reference's traversal hands every accepted (ray, beam) pair of the brute-force gather to
+    the functor exactly once; the sums differ by the visiting order only."""
+    c = cases.beams_case(name)
+    res = ob.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
+    np.testing.assert_array_equal(res.counts[:, 1], golden[f"passbeams_{name}_accepted"])
+    want = golden[f"passbeams_{name}_bits"].view(np.float32)
+    assert H.rel_err(res.out, want).max() < 2e-6 and H.rel_err_per_ray(res.out, want)[0].max() < 2e-6
+
+
+@pytest.mark.parametrize("name", cases.PASS_PLANES)
+def test_whole_plane_pass_matches_reference_golden(built, golden, name):
+    """PhotonPlaneBVH<LTPhotonPlane> (plane_accel.h:93-185) + PlaneGradRadianceQuery per camera segment (gvpm.cpp:837-841):
+    same planes as the brute-force gather, sums in the reference's visiting order."""
+    c = cases.planes_case(name)
+    want = golden[f"passplanes_{name}_bits"].view(np.float32)
+    for mode in ("brute", "kdtree"):
+        res = ob.planes_gather(c.planes, c.rays, c.medium, c.config, mode=mode, threads=2)
+        assert H.rel_err(res.out, want).max() < 3e-6 and H.rel_err_per_ray(res.out, want)[0].max() < 3e-6, mode
 
 
 def _oracle_out(kind, c):
