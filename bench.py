@@ -701,6 +701,57 @@ def technique_cpu_arm(args, d, seconds):
                       f"primitives; {how}; gather {ms1:.0f} ms (wall {wall1:.0f} ms)"}, ms1, n1
 
 
+def technique_reference_code_arm(args, d, seconds):
+    """The reference's own compiled code for this technique on all host cores (oracle/_ref/libgvpm_functor_ref.so): its
+    acceleration structure (SubBeamBVH / PhotonPlaneBVH / PointKDTree range query) built once, then its traversal + shift
+    functor on a bounded sample of whole 1024-ray tiles spread over the image."""
+    from oracle import binding as ob
+    from oracle import functor_binding as fb
+    cores = ob.hw_threads()
+    rays = d["full_rays"] if d.get("full_rays") is not None else d["rays"]
+    n_tiles = max(1, rays.n // 1024)
+    tech = d["tech"]
+    st = d.setdefault("ref_code", {})
+    if "pass" not in st:
+        if tech == "vpm":
+            st["pass"] = fb.TechniquePass("vpm", d["photons"], d["medium"], d["cfg"], tri=d["tri"], threads=cores)
+            st["what"] = "GPhotonMap::build + evaluate (PointKDTree range query) + VolumeGradientDistanceQuery"
+        elif tech == "beams":
+            st["pass"] = fb.TechniquePass("beams", d["beams"], d["medium"], d["cfg"], tri=d["tri"], radius=d["radius"])
+            st["what"] = "SubBeamBVH<LTPhotonBeam> + BeamGradRadianceQuery"
+        else:
+            st["pass"] = fb.TechniquePass("planes", d["planes"], d["medium"], d["cfg"])
+            st["what"] = "PhotonPlaneBVH<LTPhotonPlane> + PlaneGradRadianceQuery"
+    tp = st["pass"]
+
+    def run(n_t):
+        tiles = np.unique(np.linspace(0, n_tiles - 1, num=max(1, n_t), dtype=np.int64))
+        idx = (tiles[:, None] * 1024 + np.arange(1024)[None, :]).reshape(-1)
+        idx = idx[idx < rays.n]
+        sub = rays.take(idx)
+        smp = None
+        if tech == "vpm":
+            import gvpm_b200 as g
+            rad = np.full(sub.n, d["radius"], dtype=np.float32)
+            smp = g.synth_vpm_samples(sub, d["medium"], rad, nb_camera_samples=d["nb"], seed=11)
+        t0 = time.perf_counter()
+        _, ms = tp.run(sub, threads=cores, samples=smp, nb_camera_samples=d.get("nb", 0), want_out=False)
+        return sub.n, max(ms, 1e-3), (time.perf_counter() - t0) * 1e3, len(tiles)
+
+    # pilot on tiles spread over the image (the cost per ray follows the primitive density: a corner tile says nothing)
+    n_pilot = min(n_tiles, 8)
+    _, _, wall0, _ = run(n_pilot)
+    want = int(min(n_tiles, max(n_pilot, seconds * 1e3 / max(wall0 / n_pilot, 1e-3))))
+    n1, ms1, wall1, nt = run(want) if want > n_pilot else run(n_pilot)
+    return {"value": n1 / ms1 * 1e3, "unit": "rays/s", "cores": cores, "kind": "reference",
+            "flags": "-O2 -ffp-contract=off, SINGLE_PRECISION SPECTRUM_SAMPLES=3 (oracle/Makefile, target functor_ref)",
+            "build_ms": tp.build_ms,
+            "sample": f"{n1} rays ({nt} of {n_tiles} 1024-ray tiles spread over the image) against all {d['n_prim']} "
+                      f"primitives, on the reference's own compiled code ({st['what']}: "
+                      f"oracle/_ref/libgvpm_functor_ref.so); gather {ms1:.0f} ms (wall {wall1:.0f} ms); structure build "
+                      f"{tp.build_ms:.0f} ms single-threaded, not included in `value`"}, ms1, n1
+
+
 def technique_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -709,8 +760,20 @@ def technique_reference(args):
     d = technique_inputs(args, 0, 1)
     per = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     vals, cb = [], None
+    use_code, why_not = False, "GVPM_REFERENCE_ARM=port"
+    if os.environ.get("GVPM_REFERENCE_ARM", "code") != "port":
+        try:
+            from oracle import functor_binding as fb
+            use_code = fb.have_ref() and fb.load() is not None
+            why_not = "" if use_code else "oracle/_ref/libgvpm_functor_ref.so absent"
+        except Exception as e:  # noqa: BLE001
+            use_code, why_not = False, f"reference library does not load: {e}"
     for i in range(args.warmup + args.steps):
-        cb, ms, n = technique_cpu_arm(args, d, per)
+        if use_code:
+            cb, ms, n = technique_reference_code_arm(args, d, per)
+        else:
+            cb, ms, n = technique_cpu_arm(args, d, per)
+            cb["reference_code_not_timed"] = why_not
         if i >= args.warmup:
             vals.append((n, ms))
     n_tot, ms_tot = sum(v[0] for v in vals), sum(v[1] for v in vals)

@@ -78,6 +78,22 @@ def load():
         _lib.ref_fn_vpm_pass.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                          C.c_void_p, N.f32p, C.c_size_t, C.c_int, C.c_int, N.f32p, N.f32p,
                                          C.POINTER(C.c_double)]
+        dp = C.POINTER(C.c_double)
+        _lib.ref_fn_tech_close.restype = None
+        _lib.ref_fn_tech_close.argtypes = [C.c_void_p]
+        _lib.ref_fn_beams_open.restype = C.c_void_p
+        _lib.ref_fn_beams_open.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p, C.c_size_t, C.c_float, dp]
+        _lib.ref_fn_beams_run.restype = C.c_int
+        _lib.ref_fn_beams_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, N.f32p, C.c_int, N.f32p, N.u32p, dp]
+        _lib.ref_fn_planes_open.restype = C.c_void_p
+        _lib.ref_fn_planes_open.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, dp]
+        _lib.ref_fn_planes_run.restype = C.c_int
+        _lib.ref_fn_planes_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, N.f32p, dp]
+        _lib.ref_fn_vpm_open.restype = C.c_void_p
+        _lib.ref_fn_vpm_open.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, N.f32p, C.c_size_t, C.c_int, dp]
+        _lib.ref_fn_vpm_run.restype = C.c_int
+        _lib.ref_fn_vpm_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                        N.f32p, N.f32p, dp]
     return _lib
 
 
@@ -341,3 +357,52 @@ def vpm_pass(photons, rays, samples, medium, config, tri, nb_camera_samples, thr
     if rc != 0:
         raise RuntimeError(f"ref_fn_vpm_pass refused the input: {rc}")
     return out.reshape(rays.n, 27), mvol, tuple(times)
+
+
+class TechniquePass:
+    """The reference's own structures of one technique kept between gathers (bench.py's technique reference arms).
+    kind "beams": SubBeamBVH<LTPhotonBeam> + BeamGradRadianceQuery (sampler draws from the C ABI's hash, evaluated in the
+    harness); "planes": PhotonPlaneBVH<LTPhotonPlane> + PlaneGradRadianceQuery; "vpm": GPhotonMap (PointKDTree range query) +
+    VolumeGradientDistanceQuery."""
+
+    def __init__(self, kind, prims, medium, config, tri=None, radius=0.0, threads=1):
+        self.lib, self.kind = load(), kind
+        times = (C.c_double * 2)()
+        cp = prims.as_c()
+        tri = np.ascontiguousarray(tri if tri is not None else np.zeros(0), dtype=np.float32)
+        if kind == "beams":
+            self.h = self.lib.ref_fn_beams_open(C.byref(cp), prims.n, C.byref(medium), C.byref(config),
+                                                tri.ctypes.data_as(N.f32p), tri.size // 9, radius, times)
+        elif kind == "planes":
+            self.h = self.lib.ref_fn_planes_open(C.byref(cp), prims.n, C.byref(medium), C.byref(config), times)
+        elif kind == "vpm":
+            self.h = self.lib.ref_fn_vpm_open(C.byref(cp), prims.n, C.byref(medium), C.byref(config),
+                                              tri.ctypes.data_as(N.f32p), tri.size // 9, threads, times)
+        else:
+            raise ValueError(kind)
+        if not self.h:
+            raise RuntimeError(f"the reference harness refused the {kind} input")
+        self.records_ms, self.build_ms = times[0], times[1]
+
+    def run(self, rays, threads=1, samples=None, nb_camera_samples=0, want_out=True):
+        """-> (out [n_rays, 27] or None, gather ms)"""
+        cr = rays.as_c()
+        out = np.zeros(rays.n * 27, dtype=np.float32) if want_out else None
+        op = out.ctypes.data_as(N.f32p) if want_out else None
+        ms = C.c_double(0)
+        if self.kind == "beams":
+            rc = self.lib.ref_fn_beams_run(self.h, C.byref(cr), rays.n, None, threads, op, None, C.byref(ms))
+        elif self.kind == "planes":
+            rc = self.lib.ref_fn_planes_run(self.h, C.byref(cr), rays.n, threads, op, C.byref(ms))
+        else:
+            cs = samples.as_c()
+            rc = self.lib.ref_fn_vpm_run(self.h, C.byref(cr), rays.n, C.byref(cs), samples.n, nb_camera_samples, threads,
+                                         op, None, C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"the reference harness refused the rays: {rc}")
+        return (out.reshape(rays.n, 27) if want_out else None), ms.value
+
+    def close(self):
+        if self.h:
+            self.lib.ref_fn_tech_close(self.h)
+            self.h = None

@@ -529,7 +529,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 10; }
+int ref_fn_version() { return 11; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -970,6 +970,21 @@ int ref_fn_bre_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *
 }  // extern "C"
 
 namespace {
+// The C ABI's counter-based uniform numbers for the beam kernel record (oracle: Scene::beamUniform; CUDA: beam_device.cuh):
+// an input convention of the flattened form, restated here so that a gather needs no [rays x beams] table.
+uint32_t abiHash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+float abiBeamUniform(uint32_t seed, int px, int py, int edge, uint32_t beam, uint32_t dim) {
+  uint32_t h = abiHash32(seed ^ 0x9E3779B9u);
+  h = abiHash32(h ^ (uint32_t)px);
+  h = abiHash32(h ^ ((uint32_t)py * 0x85EBCA6Bu));
+  h = abiHash32(h ^ ((uint32_t)edge * 0xC2B2AE35u));
+  h = abiHash32(h ^ beam);
+  h = abiHash32(h ^ (dim * 0x27D4EB2Fu));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
 template <class F> void parallelRays(size_t n, int threads, F f) {
   std::atomic<size_t> next(0);
   auto worker = [&]() {
@@ -993,26 +1008,57 @@ void putAll(float *o, const Spectrum &m, const Spectrum *sh, const Spectrum *we)
 
 extern "C" {
 
-// G-Beams: SubBeamBVH<LTPhotonBeam> (sub-beam split, kd-tree, hierarchy, beams_accel.h:90-243) + BeamGradRadianceQuery per
-// camera segment (gvpm.cpp:936-941).  The functor's two sampler draws are preset per (ray, beam) before each call.
-int ref_fn_beams_pass(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
-                      const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, const float *xi, int threads,
-                      float *out, uint32_t *counts, double *times_ms) {
+// Persistent handles (bench.py's technique reference arms: one build, many sampled gathers); the *_pass entries are
+// open + run + close.
+struct TechPass {
   World W;
-  W.common(med, cfg, tri, n_tri, cfg->beam_kernel_1d ? EBeamBeam1D : EBeamBeam3D_Optimized);
-  W.config.newShiftBeam = cfg->beam_kernel_1d != 0;
+  gvpm_config cfg;
+  gvpm_medium med;
+  // beams
   BeamWorld B;
-  if (int rc = B.build(W, bs, n_beams, med, cfg, radius)) return rc;
+  std::vector<std::pair<int, LTPhotonBeam>> list;
+  ref<SubBeamBVH<LTPhotonBeam>> beamBVH;
+  // planes
+  std::vector<LTPhotonPlane> planes;
+  ref<PhotonPlaneBVH<LTPhotonPlane>> planeBVH;
+  // point photons
+  ref<FunctorMap> map;
+};
+
+void ref_fn_tech_close(void *h) { delete (TechPass *)h; }
+
+// G-Beams: SubBeamBVH<LTPhotonBeam> (sub-beam split, kd-tree, hierarchy, beams_accel.h:90-243) + BeamGradRadianceQuery per
+// camera segment (gvpm.cpp:936-941).  The functor's two sampler draws are preset per (ray, beam) before each call: from the
+// caller's table xi [n_rays * n_beams * 2], or (xi = NULL) from the C ABI's counter-based hash evaluated here.
+// times_ms: [2] = light-path + beam records (harness work), SubBeamBVH construction.
+void *ref_fn_beams_open(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
+                        size_t n_tri, float radius, double *times_ms) {
+  TechPass *T = new TechPass();
+  T->cfg = *cfg;
+  T->med = *med;
+  const double t0 = nowMs();
+  T->W.common(med, cfg, tri, n_tri, cfg->beam_kernel_1d ? EBeamBeam1D : EBeamBeam3D_Optimized);
+  T->W.config.newShiftBeam = cfg->beam_kernel_1d != 0;
+  if (T->B.build(T->W, bs, n_beams, med, cfg, radius)) { delete T; return NULL; }
+  T->list.reserve(n_beams);
+  for (size_t j = 0; j < n_beams; ++j) T->list.push_back(std::make_pair((int)j, T->B.beams[j]));
+  const double t1 = nowMs();
+  T->beamBVH = new SubBeamBVH<LTPhotonBeam>(T->list);
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return T;
+}
+
+int ref_fn_beams_run(void *h, const gvpm_ray_soa *ry, size_t n_rays, const float *xi, int threads, float *out,
+                     uint32_t *counts, double *gather_ms) {
+  TechPass *T = (TechPass *)h;
+  World &W = T->W;
+  const size_t n_beams = T->list.size();
   for (size_t r = 0; r < n_rays; ++r)
     if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
-  const double t0 = nowMs();
-  std::vector<std::pair<int, LTPhotonBeam>> list;
-  list.reserve(n_beams);
-  for (size_t j = 0; j < n_beams; ++j) list.push_back(std::make_pair((int)j, B.beams[j]));
-  ref<SubBeamBVH<LTPhotonBeam>> bvh = new SubBeamBVH<LTPhotonBeam>(list);
   const double t1 = nowMs();
-  const LTPhotonBeam *first = &list[0].second;
+  const LTPhotonBeam *first = &T->list[0].second;
   const size_t stride = sizeof(std::pair<int, LTPhotonBeam>);
+  const uint32_t seed = T->cfg.rng_seed;
   parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
     cam.build(ry, r, W.medium.get());
     ref<PresetSampler> sampler = new PresetSampler();
@@ -1026,67 +1072,120 @@ int ref_fn_beams_pass(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_so
       const float *xi;
       const char *first;
       size_t stride;
+      uint32_t seed;
+      int px, py, edge;
       uint32_t accepted;
       bool operator()(const LTPhotonBeam *b, Float t1_, Float t2_) {
         const size_t j = (size_t)(((const char *)b - first) / stride);
-        s->preset(xi[2 * j], xi[2 * j + 1]);
+        if (xi) s->preset(xi[2 * j], xi[2 * j + 1]);
+        else s->preset(abiBeamUniform(seed, px, py, edge, (uint32_t)j, 0), abiBeamUniform(seed, px, py, edge, (uint32_t)j, 1));
         const bool ok = q(b, t1_, t2_);
         accepted += ok ? 1u : 0u;
         return ok;
       }
-    } fwd{ray, gRec, sampler.get(), xi + 2 * r * n_beams, (const char *)first, stride, 0u};
-    bvh->query(fwd);
-    putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
+    } fwd{ray, gRec, sampler.get(), xi ? xi + 2 * r * n_beams : NULL, (const char *)first, stride, seed,
+          ry->px[r], ry->py[r], ry->edge_id[r], 0u};
+    T->beamBVH->query(fwd);
+    if (out) putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
     if (counts) { counts[2 * r] = fwd.accepted; counts[2 * r + 1] = 0; }
   });
-  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  if (gather_ms) *gather_ms = nowMs() - t1;
   return 0;
 }
 
+int ref_fn_beams_pass(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                      const gvpm_config *cfg, const float *tri, size_t n_tri, float radius, const float *xi, int threads,
+                      float *out, uint32_t *counts, double *times_ms) {
+  double tm[2] = {0, 0}, g = 0;
+  void *h = ref_fn_beams_open(bs, n_beams, med, cfg, tri, n_tri, radius, tm);
+  if (!h) return -2;
+  const int rc = ref_fn_beams_run(h, ry, n_rays, xi, threads, out, counts, &g);
+  ref_fn_tech_close(h);
+  if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = g; }
+  return rc;
+}
+
 // G-Planes: PhotonPlaneBVH<LTPhotonPlane> (plane_accel.h:93-185) + PlaneGradRadianceQuery per camera segment (gvpm.cpp:837-841)
-int ref_fn_planes_pass(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
-                       const gvpm_config *cfg, int threads, float *out, double *times_ms) {
-  World W;
-  W.common(med, cfg, NULL, 0, EVolPlane0D);
-  std::vector<LTPhotonPlane> planes(n_planes);
+void *ref_fn_planes_open(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_medium *med, const gvpm_config *cfg,
+                         double *times_ms) {
+  TechPass *T = new TechPass();
+  T->cfg = *cfg;
+  T->med = *med;
+  const double t0 = nowMs();
+  T->W.common(med, cfg, NULL, 0, EVolPlane0D);
+  T->planes.resize(n_planes);
   for (size_t j = 0; j < n_planes; ++j) {
-    LTPhotonPlane &p = planes[j];
+    LTPhotonPlane &p = T->planes[j];
     p._ori = P3(ps->origin + 3 * j);
     p._w0 = V3f(ps->w0 + 3 * j);
     p._length0 = ps->length0[j];
     p._w1 = V3f(ps->w1 + 3 * j);
     p._length1 = ps->length1[j];
-    p.medium = W.medium.get();
+    p.medium = T->W.medium.get();
     p._flux = S3(ps->flux + 3 * j);
     p.depth = p.edgeID = ps->edge_id[j];
     p.path = NULL;
     p.pathID = 0;
   }
+  const double t1 = nowMs();
+  T->planeBVH = new PhotonPlaneBVH<LTPhotonPlane>(T->planes);
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return T;
+}
+
+int ref_fn_planes_run(void *h, const gvpm_ray_soa *ry, size_t n_rays, int threads, float *out, double *gather_ms) {
+  TechPass *T = (TechPass *)h;
+  World &W = T->W;
   for (size_t r = 0; r < n_rays; ++r)
     if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
-  const double t0 = nowMs();
-  ref<PhotonPlaneBVH<LTPhotonPlane>> bvh = new PhotonPlaneBVH<LTPhotonPlane>(planes);
   const double t1 = nowMs();
   parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
     cam.build(ry, r, W.medium.get());
     const Ray ray(P3(ry->o + 3 * r), V3f(ry->d + 3 * r), ry->mint[r], ry->maxt[r], 0.f);
     PlaneGradRadianceQuery gRec(W.scene, &cam.gp, cam.shiftGPs, ray, W.medium.get(), W.config, *W.thdata, ry->edge_id[r]);
-    bvh->query(gRec);
-    putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
+    T->planeBVH->query(gRec);
+    if (out) putAll(out + 27 * r, gRec.mediumFlux, gRec.shiftedMediumFlux, gRec.weightedMediumFlux);
   });
-  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  if (gather_ms) *gather_ms = nowMs() - t1;
   return 0;
 }
 
+int ref_fn_planes_pass(const gvpm_plane_soa *ps, size_t n_planes, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med,
+                       const gvpm_config *cfg, int threads, float *out, double *times_ms) {
+  double tm[2] = {0, 0}, g = 0;
+  void *h = ref_fn_planes_open(ps, n_planes, med, cfg, tm);
+  if (!h) return -2;
+  const int rc = ref_fn_planes_run(h, ry, n_rays, threads, out, &g);
+  ref_fn_tech_close(h);
+  if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = g; }
+  return rc;
+}
+
 // G-VPM: GPhotonMap::build + GPhotonMap::evaluate (PointKDTree range query) + VolumeGradientDistanceQuery per distance sample,
-// folded per pixel as gvpm.cpp:1175-1182.  Threads take whole pixels (the samples of a ray are consecutive in the table or
-// not: a first pass buckets them per ray, in table order).
-int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_vpm_sample_soa *smp,
-                    size_t n_smp, const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri,
-                    int nb_camera_samples, int threads, float *out, float *mvol, double *times_ms) {
-  World W;
-  W.buildThreads = threads;
-  if (int rc = W.build(ph, n_ph, med, cfg, tri, n_tri, EDistance)) return rc;
+// folded per pixel as gvpm.cpp:1175-1182.  Threads take whole pixels; a first pass buckets the samples per ray, in table
+// order.  times_ms: [2] = light-path records (harness work), kd build.
+void *ref_fn_vpm_open(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg, const float *tri,
+                      size_t n_tri, int threads, double *times_ms) {
+  TechPass *T = new TechPass();
+  T->cfg = *cfg;
+  T->med = *med;
+  const double t0 = nowMs();
+  T->W.buildThreads = threads;
+  if (T->W.build(ph, n_ph, med, cfg, tri, n_tri, EDistance)) { delete T; return NULL; }
+  const double t1 = nowMs();
+  T->map = new FunctorMap(n_ph);
+  for (size_t i = 0; i < n_ph; ++i) T->map->add(T->W.nodes[i]);
+  std::vector<GPhotonNodeKD>().swap(T->W.nodes);
+  T->map->build(true);
+  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  return T;
+}
+
+int ref_fn_vpm_run(void *h, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_vpm_sample_soa *smp, size_t n_smp,
+                   int nb_camera_samples, int threads, float *out, float *mvol, double *gather_ms) {
+  TechPass *T = (TechPass *)h;
+  World &W = T->W;
+  const gvpm_medium *med = &T->med;
   std::vector<std::vector<uint32_t>> perRay(n_rays);
   for (size_t s = 0; s < n_smp; ++s) {
     if (smp->ray[s] >= n_rays) return -6;
@@ -1094,10 +1193,6 @@ int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *
   }
   for (size_t r = 0; r < n_rays; ++r)
     if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
-  const double t0 = nowMs();
-  ref<FunctorMap> map = new FunctorMap(n_ph);
-  for (size_t i = 0; i < n_ph; ++i) map->add(W.nodes[i]);
-  map->build(true);
   const double t1 = nowMs();
   const Float normalization = 1.f / nb_camera_samples;
   parallelRays(n_rays, threads, [&](size_t r, CameraSide &cam) {
@@ -1125,18 +1220,30 @@ int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *
       const Float querySize = smp->radius[s];
       gRec.newRayBase(ray, mRec, querySize, mRec.pdfSuccess);
       gRec.clear();
-      found += (float)map->evaluate(gRec, ray.o + mRec.t * ray.d, querySize);                      // gvpm.cpp:1175
+      found += (float)T->map->evaluate(gRec, ray.o + mRec.t * ray.d, querySize);                   // gvpm.cpp:1175
       flux += (gRec.mediumFlux * normalization);
       for (int k = 0; k < 4; ++k) {
         sh[k] += (gRec.shiftedMediumFlux[k] * normalization);
         we[k] += (gRec.weightedMediumFlux[k] * normalization);
       }
     }
-    putAll(out + 27 * r, flux, sh, we);
-    mvol[r] = found;
+    if (out) putAll(out + 27 * r, flux, sh, we);
+    if (mvol) mvol[r] = found;
   });
-  if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = nowMs() - t1; }
+  if (gather_ms) *gather_ms = nowMs() - t1;
   return 0;
+}
+
+int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *ry, size_t n_rays, const gvpm_vpm_sample_soa *smp,
+                    size_t n_smp, const gvpm_medium *med, const gvpm_config *cfg, const float *tri, size_t n_tri,
+                    int nb_camera_samples, int threads, float *out, float *mvol, double *times_ms) {
+  double tm[2] = {0, 0}, g = 0;
+  void *h = ref_fn_vpm_open(ph, n_ph, med, cfg, tri, n_tri, threads, tm);
+  if (!h) return -2;
+  const int rc = ref_fn_vpm_run(h, ry, n_rays, smp, n_smp, nb_camera_samples, threads, out, mvol, &g);
+  ref_fn_tech_close(h);
+  if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = g; }
+  return rc;
 }
 
 }  // extern "C"

@@ -394,3 +394,20 @@ def test_bench_reference_arm_contract_on_cpu(arm):
     else:
         assert cb["reference_code_not_timed"] == "GVPM_REFERENCE_ARM=port"
     assert line["e2e"] == {"value": line["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("workload,photons", [("cfg2", 20000), ("cfg3", 3000), ("cfg4", 1500)])
+def test_bench_technique_reference_arm_runs_the_reference_code(workload, photons):
+    """The reference arms of the other techniques time the reference's own structures + functors too (kind "reference")."""
+    import json
+    from oracle import functor_binding as fb
+    if not fb.have_ref():
+        pytest.skip("prebuilt reference library absent")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                        "--photons", str(photons), "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    cb = line["cpu_baseline"]
+    assert line["impl"] == "reference" and cb["kind"] == "reference" and cb["value"] == line["value"] > 0
+    assert "own compiled code" in cb["sample"]

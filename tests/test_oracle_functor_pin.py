@@ -313,6 +313,34 @@ def test_later_camera_edge_matches_reference_golden(built, golden, kind, name):
         assert not np.array_equal(cases.bits(got), golden[f"{kind}_{name}_bits"])
 
 
+def test_persistent_passes_equal_the_one_shot_ones(built, golden):
+    """bench.py's reference arms keep the reference's structures between gathers; the beam pass then draws the kernel
+    record's two numbers from the C ABI's hash inside the harness instead of a table.  Same results as the pinned passes."""
+    if not fb.have_ref():
+        pytest.skip("prebuilt reference library absent")
+    c = cases.beams_case("blocker")
+    tp = fb.TechniquePass("beams", c.beams, c.medium, c.config, tri=c.tri, radius=c.radius)
+    out, _ = tp.run(c.rays, threads=2)
+    tp.close()
+    np.testing.assert_array_equal(cases.bits(out), golden["passbeams_blocker_bits"])
+    c = cases.planes_case("many")
+    tp = fb.TechniquePass("planes", c.planes, c.medium, c.config)
+    out, _ = tp.run(c.rays, threads=2)
+    tp.close()
+    np.testing.assert_array_equal(cases.bits(out), golden["passplanes_many_bits"])
+    c = cases.vpm_case("wide")
+    tp = fb.TechniquePass("vpm", c.photons, c.medium, c.config, tri=c.tri, threads=2)
+    out, _ = tp.run(c.rays, threads=2, samples=c.samples, nb_camera_samples=c.nb)
+    tp.close()
+    np.testing.assert_array_equal(cases.bits(out), golden["passvpm_wide_bits"])
+    c = cases.bre_case("big")
+    bp = fb.BrePass(c.photons, c.medium, c.config, c.tri, c.radius, threads=2)
+    out, calls, _ = bp.run(c.rays, threads=2)
+    bp.close()
+    np.testing.assert_array_equal(cases.bits(out), golden["pass_big_bits"])
+    np.testing.assert_array_equal(calls, golden["pass_big_calls"])
+
+
 def test_harness_refuses_what_it_cannot_rebuild(built):
     """Glossy parents (manifold shift) and camera edge 0 are outside the pin."""
     if not fb.have_ref():
