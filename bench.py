@@ -1552,6 +1552,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             inp["full_rays"] = inp["rays"]
             cb, _, _ = cpu_arm(args, inp, args.cpu_seconds)
+            cb["see_also"] = ("`bench.py --impl reference` times the reference's OWN compiled code (cpu_baseline.kind "
+                              "\"reference\"); this port is ~1.4x faster per thread than the code it restates "
+                              "(profiles/r2_cpu_reference_code.md)")
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     # tensors allocated on the context's stream must go before the stream does
