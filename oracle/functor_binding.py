@@ -94,6 +94,13 @@ def load():
         _lib.ref_fn_vpm_run.restype = C.c_int
         _lib.ref_fn_vpm_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                         N.f32p, N.f32p, dp]
+        for fn in ("ref_fn_shim_photons", "ref_fn_shim_rays"):
+            getattr(_lib, fn).restype = C.c_int
+            getattr(_lib, fn).argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.ref_fn_shim_beams.restype = C.c_int
+        _lib.ref_fn_shim_beams.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        _lib.ref_fn_shim_medium.restype = C.c_int
+        _lib.ref_fn_shim_medium.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -406,3 +413,31 @@ class TechniquePass:
         if self.h:
             self.lib.ref_fn_tech_close(self.h)
             self.h = None
+
+
+def shim_roundtrip(kind, records, medium, config, radius=0.0):
+    """Flattened records -> the reference objects the harness rebuilds -> the reference-side shim
+    (gvpm_b200/host/gvpm_mitsuba_shim.hpp: flattenPhotonMap / appendLightPathBeams / appendGatherPoint) -> records again."""
+    lib = load()
+    out = type(records)(records.n)
+    ci, co = records.as_c(), out.as_c()
+    if kind == "photons":
+        rc = lib.ref_fn_shim_photons(C.byref(ci), records.n, C.byref(medium), C.byref(config), C.byref(co))
+    elif kind == "beams":
+        rc = lib.ref_fn_shim_beams(C.byref(ci), records.n, C.byref(medium), C.byref(config), radius, C.byref(co))
+    elif kind == "rays":
+        rc = lib.ref_fn_shim_rays(C.byref(ci), records.n, C.byref(medium), C.byref(config), C.byref(co))
+    else:
+        raise ValueError(kind)
+    if rc != 0:
+        raise RuntimeError(f"shim round trip ({kind}) failed: {rc}")
+    return out
+
+
+def shim_medium(medium):
+    """gvpm_shim::flattenMedium on the reference's HomogeneousMedium built from the record."""
+    lib = load()
+    out = type(medium)()
+    if lib.ref_fn_shim_medium(C.byref(medium), C.byref(out)) != 0:
+        raise RuntimeError("shim medium round trip failed")
+    return out

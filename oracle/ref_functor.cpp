@@ -87,6 +87,8 @@
 #include "ref_physics.cpp"   // makePhase / makeMedium / makeDiffuse / HarnessShape and the ref_phys_* entries
 
 #include "../include/gvpm_b200.h"
+#include <mitsuba/render/trimesh.h>
+#include "../gvpm_b200/host/gvpm_mitsuba_shim.hpp"   // the reference-side flattening shims, executed by ref_fn_shim_*
 
 namespace mitsuba {
 // the triangle list the stand-in of ShapeKDTree::rayIntersect walks (functor_stubs.cpp)
@@ -529,7 +531,7 @@ struct CameraSide {
 
 extern "C" {
 
-int ref_fn_version() { return 11; }
+int ref_fn_version() { return 12; }
 
 // G-BRE.  out: [n_rays * 27] = mediumFlux, shiftedMediumFlux[4], weightedMediumFlux[4] summed over the photons of the
 // neighbour set in photon order; counts: [n_rays] functor calls (geometric neighbours).  Returns < 0 on unsupported input.
@@ -1244,6 +1246,92 @@ int ref_fn_vpm_pass(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_ray_soa *
   ref_fn_tech_close(h);
   if (times_ms) { times_ms[0] = tm[1]; times_ms[1] = g; }
   return rc;
+}
+
+// ---- round trips through the reference-side shims (gvpm_b200/host/gvpm_mitsuba_shim.hpp, rows a1 / a10) -----------------------
+// flattened arrays -> the reference objects this harness rebuilds -> the shim a maintainer compiles into the plugin ->
+// flattened arrays again.  The outputs are written through the (const) pointers of the caller's empty records.
+}  // extern "C"
+
+namespace {
+template <class T> void copyOut(const T *dst, const std::vector<T> &src) {
+  std::memcpy(const_cast<T *>(dst), src.data(), src.size() * sizeof(T));
+}
+}  // namespace
+
+extern "C" {
+
+// gvpm_shim::flattenPhotonMap over a GPhotonMap holding the rebuilt photons (insertion order, not built)
+int ref_fn_shim_photons(const gvpm_photon_soa *ph, size_t n_ph, const gvpm_medium *med, const gvpm_config *cfg,
+                        const gvpm_photon_soa *out) {
+  World W;
+  if (int rc = W.build(ph, n_ph, med, cfg, NULL, 0, EVolBRE3D)) return rc;
+  ref<FunctorMap> map = new FunctorMap(n_ph);
+  for (size_t i = 0; i < n_ph; ++i) map->add(W.nodes[i]);
+  gvpm_shim::PhotonArrays a;
+  gvpm_shim::flattenPhotonMap(*map, a, W.config.noMediumShift);
+  if (a.size() != n_ph) return -7;
+  copyOut(out->pos, a.pos); copyOut(out->flux, a.flux); copyOut(out->parent_pos, a.parent_pos);
+  copyOut(out->pred_pos, a.pred_pos); copyOut(out->parent_n, a.parent_n); copyOut(out->prefix_flux, a.prefix_flux);
+  copyOut(out->parent_albedo, a.parent_albedo); copyOut(out->parent_pdf, a.parent_pdf); copyOut(out->edge_pdf, a.edge_pdf);
+  copyOut(out->rr_weight, a.rr_weight); copyOut(out->parent_type, a.parent_type); copyOut(out->depth, a.depth);
+  copyOut(out->path_id, a.path_id);
+  return 0;
+}
+
+// gvpm_shim::appendLightPathBeams on the rebuilt light path of every beam (minDepth = the beam's edge: that edge only)
+int ref_fn_shim_beams(const gvpm_beam_soa *bs, size_t n_beams, const gvpm_medium *med, const gvpm_config *cfg, float radius,
+                      const gvpm_beam_soa *out) {
+  World W;
+  W.common(med, cfg, NULL, 0, EBeamBeam3D_Optimized);
+  BeamWorld B;
+  if (int rc = B.build(W, bs, n_beams, med, cfg, radius)) return rc;
+  gvpm_shim::BeamArrays a;
+  for (size_t j = 0; j < n_beams; ++j) {
+    unsigned int pathCounter = bs->path_id[j];
+    size_t skipped = 0;
+    if (gvpm_shim::appendLightPathBeams(a, &B.lps[j].path, (int)bs->depth[j], n_beams, Point(0.f), 0.f, pathCounter, skipped,
+                                        W.config.noMediumShift) != 1) return -7;
+  }
+  copyOut(out->origin, a.origin); copyOut(out->end, a.end); copyOut(out->flux, a.flux); copyOut(out->prefix_flux, a.prefix_flux);
+  copyOut(out->parent_n, a.parent_n); copyOut(out->parent_albedo, a.parent_albedo); copyOut(out->pred_pos, a.pred_pos);
+  copyOut(out->end_n, a.end_n); copyOut(out->parent_pdf, a.parent_pdf); copyOut(out->rr_weight, a.rr_weight);
+  copyOut(out->parent_type, a.parent_type); copyOut(out->end_on_surface, a.end_on_surface); copyOut(out->depth, a.depth);
+  copyOut(out->path_id, a.path_id);
+  return 0;
+}
+
+// gvpm_shim::appendGatherPoint on the rebuilt GatherPoint + ShiftGatherPoints of every camera segment
+int ref_fn_shim_rays(const gvpm_ray_soa *ry, size_t n_rays, const gvpm_medium *med, const gvpm_config *cfg,
+                     const gvpm_ray_soa *out) {
+  World W;
+  W.common(med, cfg, NULL, 0, EVolBRE3D);
+  gvpm_shim::RayArrays a;
+  ref<PresetSampler> sampler = new PresetSampler();
+  for (size_t r = 0; r < n_rays; ++r) {
+    if (ry->edge_id[r] < 1 || ry->edge_id[r] > 8) return -5;
+    CameraSide cam;
+    cam.build(ry, r, W.medium.get());
+    cam.gp.pixel = Point2i(ry->px[r], ry->py[r]);
+    sampler->preset(ry->xi[r], 0.f);
+    gvpm_shim::appendGatherPoint(a, r, cam.gp, cam.shiftGPs.data(), W.medium.get(), 0, -1, sampler.get());
+    if (a.size() != r + 1) return -7;
+  }
+  copyOut(out->o, a.o); copyOut(out->d, a.d); copyOut(out->mint, a.mint); copyOut(out->maxt, a.maxt);
+  copyOut(out->edge_len, a.edge_len); copyOut(out->eye_contrib, a.eye_contrib); copyOut(out->xi, a.xi);
+  copyOut(out->px, a.px); copyOut(out->py, a.py); copyOut(out->edge_id, a.edge_id); copyOut(out->off_valid, a.off_valid);
+  copyOut(out->off_o, a.off_o); copyOut(out->off_d, a.off_d); copyOut(out->off_len, a.off_len);
+  copyOut(out->off_eye, a.off_eye); copyOut(out->off_sensor, a.off_sensor);
+  return 0;
+}
+
+// gvpm_shim::flattenMedium on the reference's HomogeneousMedium built from the record
+int ref_fn_shim_medium(const gvpm_medium *med, gvpm_medium *out) {
+  initOnce();
+  ref<PhaseFunction> phase = makePhase(med->phase_type, med->hg_g);
+  ref<Medium> medium = makeMedium(med->sigma_s, med->sigma_a, med->sampling_weight, phase.get());
+  *out = gvpm_shim::flattenMedium(medium.get(), false, med->sampling_weight);
+  return 0;
 }
 
 }  // extern "C"
