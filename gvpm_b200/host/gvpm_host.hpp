@@ -179,24 +179,29 @@ inline void loadGPMConfig(const Properties &props, GPMConfig &c, GPMConfigExtra 
   if (c.volTechnique == EVolBeam1D) x.newShiftBeam = true;   // "Use the correct fix here", gvpm.cpp:96-98
 }
 
-// GPMIntegrator::scaleVolumeAPA, gvpm.cpp:181-215 (m_independentScale = false): host-side, double.
-inline void scaleVolumeAPA(double &globalScaleVolume, int it, const GPMConfig &config) {
+// GPMIntegrator::scaleVolumeAPA, gvpm.cpp:181-215 (m_independentScale = false): host-side.  Real = the reference build's
+// Float: alpha and globalScaleVolume are Floats there, so `(it + alpha) / (it + 1)` is evaluated in Float before it is
+// widened to the double ratioVolAPA, and the product with cbrt / sqrt (double) is rounded back to Float.  double = the
+// reference's CMake default (DOUBLE_PRECISION) and what the drivers below keep; float reproduces a SINGLE_PRECISION build
+// bit for bit (gvpm_host_scale_apa_f32; pinned to the reference's compiled function, tests/test_oracle_integrator_pin.py).
+template <typename Real>
+inline void scaleVolumeAPA(Real &globalScaleVolume, int it, const GPMConfig &config) {
   it -= 1;  // "Fix the bug as it == 1 at the first iteration."
-  const double ratioVolAPA = (it + config.alpha) / (it + 1);
+  const double ratioVolAPA = (double)(((Real)it + (Real)config.alpha) / (Real)(it + 1));
   // EVolumeTechniqueHelper::use3DKernel (volume_utils.h:35-41): EDistance, EVolBRE3D and every EBeamBeam3D_*;
   // beam1d and plane0d reduce linearly, bre2d by the square root
   const bool k3 = config.volTechnique == EVolVPM || config.volTechnique == EVolBRE3D || config.volTechnique == EVolBeam3D,
              k2 = config.volTechnique == EVolBRE2D;
   if (config.forceAPA.empty()) {
-    if (k3 || config.use3DKernelReduction) globalScaleVolume *= std::cbrt(ratioVolAPA);
-    else if (k2) globalScaleVolume *= std::sqrt(ratioVolAPA);
-    else globalScaleVolume *= ratioVolAPA;
+    if (k3 || config.use3DKernelReduction) globalScaleVolume = (Real)(globalScaleVolume * std::cbrt(ratioVolAPA));
+    else if (k2) globalScaleVolume = (Real)(globalScaleVolume * std::sqrt(ratioVolAPA));
+    else globalScaleVolume = (Real)(globalScaleVolume * ratioVolAPA);
   } else if (config.forceAPA == "1D") {
-    globalScaleVolume *= ratioVolAPA;
+    globalScaleVolume = (Real)(globalScaleVolume * ratioVolAPA);
   } else if (config.forceAPA == "2D") {
-    globalScaleVolume *= std::sqrt(ratioVolAPA);
+    globalScaleVolume = (Real)(globalScaleVolume * std::sqrt(ratioVolAPA));
   } else if (config.forceAPA == "3D") {
-    globalScaleVolume *= std::cbrt(ratioVolAPA);
+    globalScaleVolume = (Real)(globalScaleVolume * std::cbrt(ratioVolAPA));
   } else {
     throw std::runtime_error("No Force APA: " + config.forceAPA);
   }

@@ -77,6 +77,12 @@ int gvpm_host_scale_apa(double *scale, int it, const gvpm_host_params *p, char *
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
 }
 
+// ... as a SINGLE_PRECISION build of the reference evaluates it (Float = float): bit-identical to GPMIntegrator::scaleVolumeAPA
+int gvpm_host_scale_apa_f32(float *scale, int it, const gvpm_host_params *p, char *err, size_t errlen) {
+  try { scaleVolumeAPA(*scale, it, to_cfg(p)); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
+
 void *gvpm_host_create(int device, int w, int h, const gvpm_host_params *p, const gvpm_medium *m,
                        float bsphereR, const float *tris, size_t nTris, char *err, size_t errlen) {
   try { return new VolumeGatherB200(device, w, h, to_cfg(p), *m, bsphereR, tris, nTris); }
