@@ -183,7 +183,7 @@ inline void loadGPMConfig(const Properties &props, GPMConfig &c, GPMConfigExtra 
 // Float: alpha and globalScaleVolume are Floats there, so `(it + alpha) / (it + 1)` is evaluated in Float before it is
 // widened to the double ratioVolAPA, and the product with cbrt / sqrt (double) is rounded back to Float.  double = the
 // reference's CMake default (DOUBLE_PRECISION) and what the drivers below keep; float reproduces a SINGLE_PRECISION build
-// bit for bit (gvpm_host_scale_apa_f32; pinned to the reference's compiled function, tests/test_oracle_integrator_pin.py).
+// bit for bit (gvpm_host_scale_apa_f32; checked against the reference's compiled function).
 template <typename Real>
 inline void scaleVolumeAPA(Real &globalScaleVolume, int it, const GPMConfig &config) {
   it -= 1;  // "Fix the bug as it == 1 at the first iteration."
