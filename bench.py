@@ -430,12 +430,19 @@ def reference_main(args):
     use_code, why_not = reference_code_available(inp)
     for i in range(args.warmup + args.steps):
         if use_code:
-            cb, ms, n = reference_code_arm(args, inp, per)
-        else:
+            try:
+                cb, ms, n = reference_code_arm(args, inp, per)
+            except Exception as e:  # noqa: BLE001 - the arm must still print its line: fall back to the restated port
+                use_code, why_not = False, f"reference code failed: {type(e).__name__}: {e}"
+                inp.pop("ref_code", None)
+                vals = []
+        if not use_code:
             cb, ms, n = cpu_arm(args, inp, per)
             cb["reference_code_not_timed"] = why_not
         if i >= args.warmup:
             vals.append((n, ms))
+    if not vals:
+        vals.append((n, ms))
     n_tot = sum(v[0] for v in vals)
     ms_tot = sum(v[1] for v in vals)
     value = n_tot / ms_tot * 1e3
@@ -770,12 +777,19 @@ def technique_reference(args):
             use_code, why_not = False, f"reference library does not load: {e}"
     for i in range(args.warmup + args.steps):
         if use_code:
-            cb, ms, n = technique_reference_code_arm(args, d, per)
-        else:
+            try:
+                cb, ms, n = technique_reference_code_arm(args, d, per)
+            except Exception as e:  # noqa: BLE001 - fall back to the restated port
+                use_code, why_not = False, f"reference code failed: {type(e).__name__}: {e}"
+                d.pop("ref_code", None)
+                vals = []
+        if not use_code:
             cb, ms, n = technique_cpu_arm(args, d, per)
             cb["reference_code_not_timed"] = why_not
         if i >= args.warmup:
             vals.append((n, ms))
+    if not vals:
+        vals.append((n, ms))
     n_tot, ms_tot = sum(v[0] for v in vals), sum(v[1] for v in vals)
     value = n_tot / ms_tot * 1e3
     cb["value"] = value
