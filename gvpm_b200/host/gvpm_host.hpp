@@ -434,23 +434,24 @@ struct SPPMConfig {   // the SPPMIntegrator members the volume passes read (sppm
   unsigned rngSeed = 0;   // replaces the per-thread Sampler of the 3-D kernels (counter-based hash)
 };
 
-// SPPMIntegrator::scaleVolumeAPA, sppm.cpp:255-290 (m_independentScale = false)
-inline void scaleVolumeAPA(double &globalScaleVolume, int it, const SPPMConfig &config) {
+// SPPMIntegrator::scaleVolumeAPA, sppm.cpp:255-290 (m_independentScale = false); Real as for the gvpm schedule above
+template <typename Real>
+inline void scaleVolumeAPA(Real &globalScaleVolume, int it, const SPPMConfig &config) {
   it -= 1;
-  const double ratioVolAPA = (it + config.alpha) / (it + 1);
+  const double ratioVolAPA = (double)(((Real)it + (Real)config.alpha) / (Real)(it + 1));
   const int t = config.volTechnique;
   const bool use3D = t == ESppmBRE3D || t == ESppmBeam3DNaive || t == ESppmBeam3DEGSR || t == ESppmBeam3DOptimized ||
                      t == 6 /* ESppmDistance: EVolumeTechniqueHelper::use3DKernel counts EDistance */;
   if (config.forceAPA.empty()) {
-    if (use3D) globalScaleVolume *= std::cbrt(ratioVolAPA);
-    else if (t == ESppmBRE2D) globalScaleVolume *= std::sqrt(ratioVolAPA);
-    else globalScaleVolume *= ratioVolAPA;
+    if (use3D) globalScaleVolume = (Real)(globalScaleVolume * std::cbrt(ratioVolAPA));
+    else if (t == ESppmBRE2D) globalScaleVolume = (Real)(globalScaleVolume * std::sqrt(ratioVolAPA));
+    else globalScaleVolume = (Real)(globalScaleVolume * ratioVolAPA);
   } else if (config.forceAPA == "1D") {
-    globalScaleVolume *= ratioVolAPA;
+    globalScaleVolume = (Real)(globalScaleVolume * ratioVolAPA);
   } else if (config.forceAPA == "2D") {
-    globalScaleVolume *= std::sqrt(ratioVolAPA);
+    globalScaleVolume = (Real)(globalScaleVolume * std::sqrt(ratioVolAPA));
   } else if (config.forceAPA == "3D") {
-    globalScaleVolume *= std::cbrt(ratioVolAPA);
+    globalScaleVolume = (Real)(globalScaleVolume * std::cbrt(ratioVolAPA));
   } else {
     throw std::runtime_error("No Force APA: " + config.forceAPA);
   }

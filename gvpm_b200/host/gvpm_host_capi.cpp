@@ -192,6 +192,12 @@ int gvpm_host_sppm_scale_apa(double *scale, int it, const gvpm_host_sppm_params 
   try { scaleVolumeAPA(*scale, it, to_sppm(p)); return 0; }
   catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
 }
+
+// ... as a SINGLE_PRECISION build of the reference evaluates it
+int gvpm_host_sppm_scale_apa_f32(float *scale, int it, const gvpm_host_sppm_params *p, char *err, size_t errlen) {
+  try { scaleVolumeAPA(*scale, it, to_sppm(p)); return 0; }
+  catch (const std::exception &e) { set_err(err, errlen, e.what()); return -1; }
+}
 void *gvpm_host_sppm_create(int device, int w, int h, const gvpm_host_sppm_params *p, const gvpm_medium *m,
                             float bsphereR, char *err, size_t errlen) {
   try { return new SPPMVolumeGatherB200(device, w, h, to_sppm(p), *m, bsphereR); }

@@ -38,6 +38,8 @@ def load():
         _lib.ref_int_scale_volume_apa.argtypes = [C.c_float, C.c_int, C.c_float, C.c_int, C.c_char_p, C.c_int, f32p]
         _lib.ref_int_compute_gradient.restype = None
         _lib.ref_int_compute_gradient.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, f32p, f32p]
+        _lib.ref_int_sppm_scale_volume_apa.restype = None
+        _lib.ref_int_sppm_scale_volume_apa.argtypes = [C.c_float, C.c_int, C.c_float, C.c_int, C.c_char_p, f32p]
     return _lib
 
 
@@ -57,3 +59,10 @@ def compute_gradient(acc, w, h, use_abs, technique="bre3d", total_emitted_volume
     load().ref_int_compute_gradient(acc.ctypes.data_as(f32p), w, h, int(use_abs), TECHNIQUES[technique],
                                     total_emitted_volume, gx.ctypes.data_as(f32p), gy.ctypes.data_as(f32p))
     return gx.reshape(h, w, 3), gy.reshape(h, w, 3)
+
+
+def sppm_scale_volume_apa(scale0, n, alpha, technique, force_apa=""):
+    """SPPMIntegrator::scaleVolumeAPA (sppm.cpp:255-290): globalScaleVolume after iteration it = 1 .. n."""
+    out = np.zeros(n, dtype=np.float32)
+    load().ref_int_sppm_scale_volume_apa(scale0, n, alpha, TECHNIQUES[technique], force_apa.encode(), out.ctypes.data_as(f32p))
+    return out

@@ -1,5 +1,5 @@
 """Regenerates tests/golden/integrator_pins.npz from two member functions of the REFERENCE'S OWN integrator class
-(GPMIntegrator::scaleVolumeAPA and GPMIntegrator::computeGradient, gvpm/gvpm.cpp, compiled from /root/reference by
+(GPMIntegrator::scaleVolumeAPA and GPMIntegrator::computeGradient, gvpm/gvpm.cpp; SPPMIntegrator::scaleVolumeAPA, sppm.cpp; compiled from /root/reference by
 `make -C oracle integrator_ref`).  Run in the container that holds the reference tree:
     python tests/golden/make_integrator_golden.py"""
 import os
@@ -19,6 +19,8 @@ if __name__ == "__main__":
     out = {}
     for key, (tech, force, k3, alpha, s0) in cases.SCHEDULES.items():
         out[f"scale_{key}"] = ib.scale_volume_apa(s0, cases.N_ITER, alpha, tech, force, k3)
+    for key, (tech, force, alpha, s0) in cases.SPPM_SCHEDULES.items():
+        out[f"sppmscale_{key}"] = ib.sppm_scale_volume_apa(s0, cases.N_ITER, alpha, tech, force)
     acc = cases.accumulators()
     for key, (tech, use_abs, emitted) in cases.GRADIENTS.items():
         gx, gy = ib.compute_gradient(acc, cases.W, cases.H, use_abs, tech, emitted)

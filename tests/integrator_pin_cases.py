@@ -18,6 +18,19 @@ SCHEDULES = {
 }
 # the host mirror's technique numbering (gvpm_b200/host/gvpm_host.hpp:34)
 HOST_TECHNIQUE = {"bre2d": 0, "bre3d": 1, "distance": 2, "beam3d": 3, "plane0d": 4, "beam1d": 5}
+# sppm: key -> (reference technique name, forceAPA, alpha, initialScaleVolume); the sppm mirror's technique numbering
+# (gvpm_b200/host/gvpm_host.hpp:425)
+SPPM_SCHEDULES = {
+    "bre3d": ("bre3d", "", 0.7, 0.3),
+    "bre2d": ("bre2d", "", 0.7, 1.0),
+    "beam1d": ("beam1d", "", 0.6, 1.0),
+    "beam3d_naive": ("beam3d_naive", "", 0.7, 1.0),
+    "beam3d_egsr": ("beam3d_egsr", "", 0.7, 2.0),
+    "beam3d": ("beam3d", "", 0.8, 1.0),
+    "beam1d_force_3d": ("beam1d", "3D", 0.7, 1.0),
+    "bre3d_force_2d": ("bre3d", "2D", 0.7, 1.0),
+}
+SPPM_HOST_TECHNIQUE = {"bre2d": 0, "bre3d": 1, "beam1d": 2, "beam3d_naive": 3, "beam3d_egsr": 4, "beam3d": 5}
 # key -> (reference technique name, useAbs, m_totalEmittedVolume)
 GRADIENTS = {
     "bre3d": ("bre3d", False, 250000),

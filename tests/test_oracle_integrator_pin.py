@@ -1,6 +1,6 @@
 """Rows a18 / a19 of SURVEY.md §8 pinned to the REFERENCE'S OWN compiled code: GPMIntegrator::scaleVolumeAPA
 (gvpm/gvpm.cpp:181-215, the per-iteration kernel reduction) and GPMIntegrator::computeGradient (:1205-1304, gradient images
-from the per-pixel accumulators).  oracle/_ref/libgvpm_integrator_ref.so is built from /root/reference (oracle/Makefile,
+from the per-pixel accumulators), plus SPPMIntegrator::scaleVolumeAPA (photonmapper/sppm.cpp:255-290).  oracle/_ref/libgvpm_integrator_ref.so is built from /root/reference (oracle/Makefile,
 target `integrator_ref`; oracle/ref_integrator.cpp includes gvpm.cpp where it lies and calls the two member functions on raw
 storage); tests/golden/integrator_pins.npz holds its outputs (tests/golden/make_integrator_golden.py)."""
 import ctypes as C
@@ -11,7 +11,7 @@ import pytest
 
 import integrator_pin_cases as cases
 from oracle import integrator_binding as ib
-from test_abi_and_host import HostParams, _host, host_params
+from test_abi_and_host import HostParams, SppmHostParams, _host, host_params
 from test_gpu_host_and_gradient import gradient_reference
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "integrator_pins.npz")
@@ -48,6 +48,29 @@ def test_host_schedule_equals_reference(golden, key):
     np.testing.assert_allclose(np.array(got_d), want.astype(np.float64), rtol=3e-6, atol=0)
 
 
+@pytest.mark.parametrize("key", list(cases.SPPM_SCHEDULES))
+def test_sppm_host_schedule_equals_reference(golden, key):
+    """SPPMIntegrator::scaleVolumeAPA (sppm.cpp:255-290) against the sppm host mirror: float form bit for bit, double form
+    within 3e-6."""
+    tech, force, alpha, s0 = cases.SPPM_SCHEDULES[key]
+    want = golden[f"sppmscale_{key}"]
+    h = _host()
+    h.gvpm_host_sppm_scale_apa_f32.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(SppmHostParams), C.c_char_p, C.c_size_t]
+    h.gvpm_host_sppm_scale_apa.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(SppmHostParams), C.c_char_p, C.c_size_t]
+    p = SppmHostParams(maxDepth=-1, minDepth=0, alpha=alpha, initialScaleVolume=s0,
+                       volTechnique=cases.SPPM_HOST_TECHNIQUE[tech], rngSeed=0, forceAPA=force.encode())
+    err = C.create_string_buffer(256)
+    sf, sd = C.c_float(s0), C.c_double(s0)
+    got_f, got_d = [], []
+    for it in range(1, cases.N_ITER + 1):
+        assert h.gvpm_host_sppm_scale_apa_f32(C.byref(sf), it, C.byref(p), err, 256) == 0
+        assert h.gvpm_host_sppm_scale_apa(C.byref(sd), it, C.byref(p), err, 256) == 0
+        got_f.append(sf.value)
+        got_d.append(sd.value)
+    np.testing.assert_array_equal(np.array(got_f, np.float32), want)
+    np.testing.assert_allclose(np.array(got_d), want.astype(np.float64), rtol=3e-6, atol=0)
+
+
 @pytest.mark.parametrize("key", list(cases.GRADIENTS))
 def test_gradient_restatement_equals_reference(golden, key):
     """computeGradient, volume terms: the numpy restatement the CUDA kernel is tested against
@@ -69,6 +92,8 @@ def test_golden_vectors_are_what_the_reference_computes_now(golden):
         assert ib.build_ref()
     for key, (tech, force, k3, alpha, s0) in cases.SCHEDULES.items():
         np.testing.assert_array_equal(ib.scale_volume_apa(s0, cases.N_ITER, alpha, tech, force, k3), golden[f"scale_{key}"])
+    for key, (tech, force, alpha, s0) in cases.SPPM_SCHEDULES.items():
+        np.testing.assert_array_equal(ib.sppm_scale_volume_apa(s0, cases.N_ITER, alpha, tech, force), golden[f"sppmscale_{key}"])
     acc = cases.accumulators()
     for key, (tech, use_abs, emitted) in cases.GRADIENTS.items():
         gx, gy = ib.compute_gradient(acc, cases.W, cases.H, use_abs, tech, emitted)
