@@ -114,6 +114,22 @@ void zero(PathVertex &x) { std::memset(&x, 0, sizeof(x)); x.sampledComponentInde
 void zero(PathEdge &x) { std::memset(&x, 0, sizeof(x)); }
 
 
+// A surface parent that VertexClassifier calls glossy (roughness 0 <= bounceRoughness): getTypeShift then answers
+// EManifoldShift, which the functors refuse with useManifold = false (GVPM_PARENT_OTHER of the flattened form).  Nothing of
+// it is ever evaluated.
+class GlossyStub : public BSDF {
+public:
+  GlossyStub() : BSDF(Properties("harness_glossy")) {
+    m_components.push_back(EGlossyReflection | EFrontSide);
+    BSDF::configure();
+  }
+  Spectrum sample(BSDFSamplingRecord &, const Point2 &) const override { std::abort(); }
+  Spectrum sample(BSDFSamplingRecord &, Float &, const Point2 &) const override { std::abort(); }
+  Spectrum eval(const BSDFSamplingRecord &, EMeasure) const override { std::abort(); }
+  Float pdf(const BSDFSamplingRecord &, EMeasure) const override { std::abort(); }
+  Float getRoughness(const Intersection &, int) const override { return 0.f; }
+};
+
 // Everything the functors read that does not depend on the camera segment: medium, emitter, the stand-in scene, the
 // configuration and one light Path + kd node per photon.
 struct World {
@@ -130,6 +146,8 @@ struct World {
   PathVertex unitEmitter, unitMedium;
   PathEdge unitEdge;
   std::map<std::array<uint32_t, 3>, std::pair<ref<BSDF>, ref<HarnessShape>>> bsdfCache;
+  ref<BSDF> glossy;
+  ref<HarnessShape> glossyShape;
   std::vector<GPhotonNodeKD> nodes;
 
   ~World() {
@@ -190,7 +208,11 @@ struct World {
       if (c < 2) return -2;
       const int ptype = ph->parent_type[i];
       if ((ptype == 0) != (c == 2)) return -3;     // the emitter sample is vertex 1: parent of the photons with vertexId 2 only
-      if (ptype > 2) return -4;                    // GVPM_PARENT_OTHER: manifold shift, out of scope
+      if (ptype > 3) return -4;
+      if (ptype == 3 && !glossy) {                  // GVPM_PARENT_OTHER: a glossy surface parent
+        glossy = new GlossyStub();
+        glossyShape = new HarnessShape(glossy.get());
+      }
       if (ptype == 1) {
         std::array<uint32_t, 3> key;
         std::memcpy(key.data(), ph->parent_albedo + 3 * i, 12);
@@ -266,6 +288,16 @@ struct World {
         std::array<uint32_t, 3> key;
         std::memcpy(key.data(), ph->parent_albedo + 3 * i, 12);
         its.shape = bsdfCache.find(key)->second.second.get();
+        its.wi = its.toLocal(normalize(pred - parent));
+        its.t = 1.f;
+      } else if (ptype == 3) {
+        v.type = PathVertex::ESurfaceInteraction;
+        Intersection &its = v.getIntersection();
+        new (&its) Intersection();
+        its.p = parent;
+        its.geoFrame = Frame(nrm.lengthSquared() > 0 ? nrm : Normal(0.f, 0.f, 1.f));
+        its.shFrame = its.geoFrame;
+        its.shape = glossyShape.get();
         its.wi = its.toLocal(normalize(pred - parent));
         its.t = 1.f;
       } else if (ptype == 2) {
@@ -415,8 +447,22 @@ struct BeamWorld {
         pr.n = nrm;
         pr.measure = EArea;
         pr.object = W.em.get();
+      } else if (ptype == 3) {   // GVPM_PARENT_OTHER: a glossy surface parent (the functor refuses the manifold shift)
+        if (!W.glossy) {
+          W.glossy = new GlossyStub();
+          W.glossyShape = new HarnessShape(W.glossy.get());
+        }
+        v.type = PathVertex::ESurfaceInteraction;
+        Intersection &its = v.getIntersection();
+        new (&its) Intersection();
+        its.p = origin;
+        its.geoFrame = Frame(nrm.lengthSquared() > 0 ? nrm : Normal(0.f, 0.f, 1.f));
+        its.shFrame = its.geoFrame;
+        its.shape = W.glossyShape.get();
+        its.wi = its.toLocal(normalize(pred - origin));
+        its.t = 1.f;
       } else {
-        return -4;   // GVPM_PARENT_OTHER: manifold shift, out of scope
+        return -4;
       }
       // end vertex (i + 1): on a surface (its geometric normal enters the base pdf, :506-507) or in the medium
       PathVertex &ev = L.v[i + 1];

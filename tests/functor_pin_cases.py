@@ -243,6 +243,20 @@ PASS_BEAMS = ["default", "beam1d", "blocker", "long_beams", "narrow"]
 PASS_PLANES = ["default", "hg_forward_0.3", "sensor_outside", "many"]
 
 
+# Parents that need the manifold shift (GVPM_PARENT_OTHER: a glossy surface): the reference refuses them with
+# useManifold = false - null shifts still apply, every other offset keeps weight 1 and no shifted flux.  Every third photon /
+# beam beyond the first bounce gets such a parent.  (CPU pin only: the synthetic scene has no glossy surface.)
+GLOSSY = [("bre", "default"), ("bre", "wide"), ("bre", "no_mis"), ("vpm", "wide"), ("beams", "default"), ("beams", "beam1d")]
+
+
+def glossy_case(kind, name):
+    c = {"bre": bre_case, "vpm": vpm_case, "beams": beams_case}[kind](name)
+    rec = c.beams if kind == "beams" else c.photons
+    m = (np.arange(rec.n) % 3 == 0) & (rec.parent_type != 0)
+    rec.parent_type[m] = N.PARENT_OTHER if hasattr(N, "PARENT_OTHER") else 3
+    return c
+
+
 def input_crc(c):
     """Fingerprint of the generated inputs: the golden outputs only mean something for exactly these arrays."""
     h = 0

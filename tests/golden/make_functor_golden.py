@@ -82,6 +82,15 @@ if __name__ == "__main__":
         res, calls, _ = fb.bre_pass(c.photons, c.rays, c.medium, c.config, c.tri, c.radius, threads=2)
         out[f"pass_{name}_bits"], out[f"pass_{name}_calls"] = cases.bits(res), calls
         print(f"pass {name:22s} functor calls {int(calls.sum()):7d}")
+    for kind, name in cases.GLOSSY:
+        c = cases.glossy_case(kind, name)
+        if kind == "bre":
+            res = fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)[0]
+        elif kind == "vpm":
+            res = fb.vpm_gather(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb)[0]
+        else:
+            res = fb.beams_gather(c.beams, c.rays, c.medium, c.config, c.tri, c.radius)[0]
+        out[f"glossy_{kind}_{name}_bits"] = cases.bits(res)
     for name in cases.PASS_VPM:
         c = cases.vpm_case(name)
         res, mvol, _ = fb.vpm_pass(c.photons, c.rays, c.samples, c.medium, c.config, c.tri, c.nb, threads=2)

@@ -341,8 +341,20 @@ def test_persistent_passes_equal_the_one_shot_ones(built, golden):
     np.testing.assert_array_equal(calls, golden["pass_big_calls"])
 
 
+@pytest.mark.parametrize("kind,name", cases.GLOSSY)
+def test_glossy_parents_fail_the_shift_as_the_reference_does(built, golden, kind, name):
+    """GVPM_PARENT_OTHER: a surface parent that VertexClassifier calls glossy sends getTypeShift to EManifoldShift, which the
+    functors refuse with useManifold = false (shift_volume_photon.cpp:100-110, shift_volume_beams.cpp:398-407): the offset
+    keeps weight 1 and no shifted flux unless the null shift applies.  Bit for bit against the reference functors."""
+    c = cases.glossy_case(kind, name)
+    got = _oracle_out(kind, c) if kind != "bre" else ob.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius,
+                                                                   mode="brute", threads=2).out
+    _same_rows(cases.bits(got), golden[f"glossy_{kind}_{name}_bits"], f"glossy parents, {kind} {name}")
+    assert not np.array_equal(golden[f"glossy_{kind}_{name}_bits"], golden[f"{kind}_{name}_bits"])
+
+
 def test_harness_refuses_what_it_cannot_rebuild(built):
-    """Glossy parents (manifold shift) and camera edge 0 are outside the pin."""
+    """Unknown parent types and camera edge 0 are outside the pin."""
     if not fb.have_ref():
         pytest.skip("prebuilt reference library absent")
     c = cases.bre_case("default")
@@ -350,6 +362,6 @@ def test_harness_refuses_what_it_cannot_rebuild(built):
     with pytest.raises(RuntimeError):
         fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)
     c = cases.bre_case("default")
-    c.photons.parent_type[:5] = 3
+    c.photons.parent_type[:5] = 4
     with pytest.raises(RuntimeError):
         fb.bre_gather(c.photons, c.rays, c.medium, c.config, c.tri, c.radius)
