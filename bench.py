@@ -1567,7 +1567,7 @@ def main():
             inp["full_rays"] = inp["rays"]
             cb, _, _ = cpu_arm(args, inp, args.cpu_seconds)
             cb["see_also"] = ("`bench.py --impl reference` times the reference's OWN compiled code (cpu_baseline.kind "
-                              "\"reference\"); this port is ~1.4x faster per thread than the code it restates "
+                              "\"reference\"); this port is 1.2x - 1.4x faster than the code it restates "
                               "(profiles/r2_cpu_reference_code.md)")
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
