@@ -982,7 +982,20 @@ def technique_main(args):
                 "phases_ms": {"build": build_ms, "gather": gather_ms, "traverse": trav_ms, "shade": shade_ms},
                 "light_paths": d["n_paths"]}
         if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = technique_cpu_arm(args, d, args.cpu_seconds)
+            # the reference's own compiled structures + functors where that library is present (its sub-beam / plane BVHs,
+            # not the port's brute force), else the restated port
+            cb = None
+            if os.environ.get("GVPM_REFERENCE_ARM", "code") != "port":
+                try:
+                    from oracle import functor_binding as fb
+                    if fb.have_ref():
+                        cb, _, _ = technique_reference_code_arm(args, d, args.cpu_seconds)
+                except Exception as e:  # noqa: BLE001
+                    cb = None
+                    d.pop("ref_code", None)
+                    line["cpu_baseline_reference_code_failed"] = f"{type(e).__name__}: {e}"
+            if cb is None:
+                cb, _, _ = technique_cpu_arm(args, d, args.cpu_seconds)
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     del out_t, mvol_t, gathered, send, flush, stream, n_pad, stats, mx
