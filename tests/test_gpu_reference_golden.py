@@ -165,3 +165,23 @@ def test_gpu_sppm_bre_equals_reference_loop_body_output(golden, name):
     out, _ = ctx.gather_sppm_bre()
     ctx.close()
     _close(out, golden[f"sppmbre_{name}_bits"], f"sppm BRE {name}")
+
+
+@pytest.mark.parametrize("kind,name", cases.GLOSSY)
+def test_gpu_glossy_parents_equal_reference_functor_output(golden, kind, name):
+    """GVPM_PARENT_OTHER: the reference's functors refuse the manifold shift (useManifold = false); the offset keeps weight 1
+    and no shifted flux unless the null shift applies."""
+    c = cases.glossy_case(kind, name)
+    want = golden[f"glossy_{kind}_{name}_bits"]
+    if kind == "bre":
+        ctx = H.gpu_context(c)
+        out = ctx.gather_bre()[0]
+    elif kind == "vpm":
+        ctx = H.gpu_context(c)
+        ctx.upload_vpm_samples(c.samples)
+        out = ctx.gather_vpm(c.nb)[0]
+    else:
+        ctx = _beam_ctx(c)
+        out = ctx.gather_beams()[0]
+    ctx.close()
+    _close(out, want, f"glossy parents, {kind} {name}")
