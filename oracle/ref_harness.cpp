@@ -17,8 +17,8 @@
 //   Triangle::rayIntersect, include/mitsuba/core/triangle.h:109-145                          -> ref_triangle
 //   coordinateSystem / coordinateSystemCoherent, src/libcore/util.cpp:592-609                -> ref_coordsys
 //   solveQuadraticDouble, src/libcore/util.cpp:487-525                                       -> ref_quadratic
-// Not reachable this way (they need libmitsuba-render / libbidir objects: Path, Medium, BSDF, Scene): the shift
-// functors themselves (gvpm/shift/*.cpp) — those stay restated-only, see DESIGN.md §5.
+// The shift functors themselves (gvpm/shift/*.cpp), which need Path / Medium / BSDF / Scene objects, are driven by a second
+// harness: ref_functor.cpp -> _ref/libgvpm_functor_ref.so.
 #include "gvpm/gvpm_accel.h"
 #include "beams_accel.h"
 #include "plane_accel.h"

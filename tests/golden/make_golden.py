@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Generates tests/golden/bre_small.npz: oracle (fp32, brute force) outputs for a small seeded case.
 
-The reference cannot be built or imported in this image and ships no fixture for the
-path, so this is a regression pin of OUR restatement, not reference output ("parity unpinned").
+A regression pin of OUR restatement on camera edge 2 (the synthetic camera outside the medium), not reference output: the
+reference ships no fixture for the path.  The vectors that ARE reference output - from the reference's own compiled functors -
+are tests/golden/functor_pins.npz (tests/golden/make_functor_golden.py).
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import os

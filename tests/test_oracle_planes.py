@@ -1,4 +1,5 @@
-"""CPU tests of the G-Planes 0D oracle (oracle/ = test infrastructure; parity unpinned): the
+"""CPU self-consistency tests of the G-Planes 0D oracle (oracle/ = test infrastructure; the pin against the reference's
+compiled PlaneGradRadianceQuery is tests/test_oracle_functor_pin.py): the
 reference-shaped balanced kd-tree + AABB hierarchy + DFS against brute force, a closed-form contribution, the
 identity of the specular shift for coincident offset rays, the host mirror of transformBeam, and a committed
 regression fixture."""
