@@ -403,9 +403,12 @@ class VolumeGatherB200 {
       m_haveSmoke[p] = 1;
       for (int j = 0; j < GVPM_OUT_FLOATS; ++j) pix[p * GVPM_OUT_FLOATS + j] += m_iter[r * GVPM_OUT_FLOATS + j];
     }
+    // Spectrum /= Float and Spectrum / Float multiply by the reciprocal (include/mitsuba/core/spectrum.h:415-456): the
+    // same two roundings here, so that the running mean is the reference's bit for bit
+    const float rnb = 1.0f / nb, rit = 1.0f / (float)it;
     for (size_t i = 0; i < m_acc.size(); ++i) {
-      const float fluxVolIter = pix[i] / nb;
-      m_acc[i] = (m_acc[i] * (float)(it - 1) + fluxVolIter) / (float)it;  // APA estimator
+      const float fluxVolIter = pix[i] * rnb;
+      m_acc[i] = (m_acc[i] * (float)(it - 1) + fluxVolIter) * rit;  // APA estimator
     }
   }
   void check(int rc, const char *what) {
@@ -591,8 +594,9 @@ class SPPMVolumeGatherB200 {
       const size_t p = ((size_t)y * m_w + x) * 3;
       for (int j = 0; j < 3; ++j) pix[p + j] += m_iter[r * 3 + j];
     }
+    const float rshot = 1.0f / shot, rit = 1.0f / (float)it;   // reciprocal multiplies, as Spectrum's operators do
     for (size_t i = 0; i < m_fluxVol.size(); ++i)
-      m_fluxVol[i] = (m_fluxVol[i] * (float)(it - 1) + pix[i] / shot) / (float)it;
+      m_fluxVol[i] = (m_fluxVol[i] * (float)(it - 1) + pix[i] * rshot) * rit;
   }
   void check(int rc, const char *what) {
     if (rc != GVPM_OK) throw std::runtime_error(std::string(what) + " failed: " + gvpm_last_error(m_ctx));
