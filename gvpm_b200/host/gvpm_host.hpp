@@ -355,7 +355,10 @@ class VolumeGatherB200 {
   // accumulators of the non-APA estimator divided by m_totalEmittedVolume (gvpm.cpp:487-491)
   std::vector<float> normalizedAccumulators() const {
     std::vector<float> a(m_acc);
-    if (totalEmittedVolume) for (float &v : a) v /= (float)totalEmittedVolume;
+    if (totalEmittedVolume) {
+      const float inv = 1.0f / (float)totalEmittedVolume;   // Spectrum / Float: reciprocal multiply (spectrum.h:415-425)
+      for (float &v : a) v *= inv;
+    }
     return a;
   }
 
