@@ -3,9 +3,12 @@
 
     python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
     python bench.py --impl reference ...                     CPU arm: the reference's own compiled G-BRE path on host cores
-                                                             (oracle/_ref/libgvpm_functor_ref.so; the oracle restatement when
-                                                             that library or the memory for it is missing, and for the other
-                                                             techniques)
+                                                             (oracle/_ref/libgvpm_functor_ref.so: kd-tree / BVH, traversal and
+                                                             shift functor, for every workload; the oracle restatement when
+                                                             that library or the memory for it is missing)
+    python bench.py --workload poisson1080 [--impl reference]   row f-3: one screened-Poisson reconstruction per step; the
+                                                             reference arm is the reference's own solver (OpenMP backend),
+                                                             the GPU line also times its CUDA backend on the same device
 
 Workload "cfg5": synthetic 1920x1080 homogeneous-medium Cornell scene, 10 M photons per iteration,
 G-BRE 3D kernel, mixed shift (useShiftNull), area MIS, pathSet; radius = bsphereR * scale * 0.01.
@@ -52,13 +55,17 @@ TECHNIQUES = {
 }
 
 
+# row f-3: screened-Poisson reconstruction of one gradient-domain image set (poisson::Solver, gvpm.cpp:610-690)
+POISSON = {"poisson1080": (1920, 1080, "L2D"), "poisson720": (1280, 720, "L2D"), "poisson1080_l1": (1920, 1080, "L1D")}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + sorted(TECHNIQUES))
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + sorted(TECHNIQUES) + sorted(POISSON))
     ap.add_argument("--scale", type=float, default=None, help="initialScaleVolume (paper preset 0.1)")
     ap.add_argument("--photons", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU-baseline sample time")
@@ -1016,8 +1023,94 @@ def technique_main(args):
     ctx.close()
 
 # --------------------------------------------------------------------------------------------
+def poisson_main(args):
+    """`--workload poisson1080 | poisson720 | poisson1080_l1`: one screened-Poisson reconstruction per step (host arrays in
+    and out through gvpm_poisson_solve, as the plugin calls it).  The reference arm is the reference's OWN solver compiled
+    from /root/reference (oracle/_ref/libgvpm_poisson_ref.so, OpenMP backend on the host cores): cpu_baseline.kind
+    "reference"; where its CUDA backend was built too (libgvpm_poisson_ref_cuda.so) the GPU run times it on the same
+    device (`reference_cuda_ms`).  Same calls as tools/time_poisson.py."""
+    import importlib.util
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    w, h, preset = POISSON[args.workload]
+    spec = importlib.util.spec_from_file_location("mpg", os.path.join(ROOT, "tests", "golden", "make_poisson_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    from oracle import poisson_ref as pr     # checker / reference arm, never the product path
+    _, tp, dx, dy, direct = G.images(h, w, 11)
+    config = {"workload": f"{args.workload}: screened-Poisson reconstruction ({preset}) of a synthetic {w}x{h} gradient-domain "
+                          f"image set (throughput, dx, dy, direct), host arrays in and out", "pixels": w * h, "preset": preset}
+    base = {"metric": "reconstructed pixels/sec (screened Poisson)", "unit": "pixels/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config}
+
+    def reference_cpu(reps):
+        ts, out = [], None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = pr.solve(tp, dx, dy, direct, backend="OpenMP", **pr.preset(preset))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return float(np.mean(ts)), out
+
+    if args.impl == "reference":
+        if not pr.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgvpm_poisson_ref.so absent"}))
+            return
+        reference_cpu(min(1, args.warmup))
+        ms, _ = reference_cpu(max(1, min(args.steps, 5)))
+        value = w * h / (ms * 1e-3)
+        cb = {"value": value, "unit": "pixels/s", "cores": os.cpu_count(), "kind": "reference",
+              "sample": f"whole {w}x{h} reconstruction, the reference's own poisson::Solver (OpenMP backend), {ms:.0f} ms"}
+        print(json.dumps(dict(base, impl="reference", value=value, ms_per_step=ms, cpu_baseline=cb,
+                              e2e={"value": value, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})))
+        return
+    from gvpm_b200.api import Context
+    ctx = Context(0)
+    for _ in range(max(3, args.warmup)):
+        rec = ctx.poisson_solve(tp, dx, dy, direct, preset=preset)
+    clocks = ClockSampler(0)
+    clocks.start()
+    dev_ms, wall = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        rec = ctx.poisson_solve(tp, dx, dy, direct, preset=preset)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        dev_ms.append(ctx.last_poisson_ms())
+    ck = clocks.stop()
+    ms, wall_ms = float(np.mean(dev_ms)), float(np.mean(wall))
+    nbytes = int(tp.nbytes + dx.nbytes + dy.nbytes + direct.nbytes)
+    line = dict(base, value=w * h / (ms * 1e-3), ms_per_step=ms, clocks=ck,
+                e2e={"value": w * h / (wall_ms * 1e-3), "unit": "pixels/s", "h2d_bytes_per_step": nbytes,
+                     "d2h_bytes_per_step": int(rec.nbytes), "ms_per_step": wall_ms},
+                timing="value: CUDA events inside gvpm_poisson_solve (copies included); e2e: wall clock around the call")
+    if not args.no_cpu_baseline and pr.available():
+        rms, want = reference_cpu(1)
+        line["cpu_baseline"] = {"value": w * h / (rms * 1e-3), "unit": "pixels/s", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": f"one whole {w}x{h} reconstruction, the reference's own poisson::Solver "
+                                          f"(OpenMP backend), {rms:.0f} ms"}
+        line["max_rel_err_vs_reference"] = float(np.abs(rec.astype(np.float64) - want).max() / np.abs(want).max())
+    if pr.cuda_available():
+        pr.solve(tp, dx, dy, direct, backend="CUDA", **pr.preset(preset))       # warm-up (context, allocations)
+        ts = []
+        for _ in range(max(1, min(args.steps, 5))):
+            t0 = time.perf_counter()
+            got = pr.solve(tp, dx, dy, direct, backend="CUDA", **pr.preset(preset))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        line["reference_cuda_ms"] = float(np.mean(ts))
+        line["vs_reference_cuda"] = line["reference_cuda_ms"] / wall_ms
+        line["max_rel_err_vs_reference_cuda"] = float(np.abs(rec.astype(np.float64) - got).max() / np.abs(got).max())
+    try:
+        line["gpu_launches"] = int(ctx.launch_count())     # kernels this context launched (warm-up included)
+    except Exception:  # noqa: BLE001
+        pass
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse()
+    if args.workload in POISSON:
+        return poisson_main(args)
     if args.workload in TECHNIQUES:
         return technique_main(args)
     if args.impl == "reference":

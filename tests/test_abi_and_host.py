@@ -411,3 +411,18 @@ def test_bench_technique_reference_arm_runs_the_reference_code(workload, photons
     cb = line["cpu_baseline"]
     assert line["impl"] == "reference" and cb["kind"] == "reference" and cb["value"] == line["value"] > 0
     assert "own compiled code" in cb["sample"]
+
+
+def test_bench_poisson_reference_arm_on_cpu():
+    """`bench.py --workload poisson720 --impl reference`: the reference's own poisson::Solver (OpenMP backend, compiled from
+    /root/reference into oracle/_ref) on the host cores, one JSON line with the contract's keys."""
+    import json
+    from oracle import poisson_ref as pr
+    if not pr.available():
+        pytest.skip("prebuilt reference solver absent")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "poisson720",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pixels/s" and line["cpu_baseline"]["kind"] == "reference"
+    assert line["value"] > 0 and line["config"]["pixels"] == 1280 * 720
